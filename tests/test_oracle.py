@@ -1,0 +1,205 @@
+"""CPU tests of the oracle (the restatement of the reference's TF-2.1 graph).
+
+The reference ships no tests or golden vectors, so the oracle is pinned by
+(1) its own frozen outputs in tests/golden (drift guard), (2) fp64-vs-fp32 agreement,
+(3) finite differences, (4) independent torch.nn.functional implementations of each block and
+(5) the closed-form facts of SURVEY §8c (lr(0)=0, masked keys get exactly zero weight, ...).
+"""
+import math
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sketchformer_oracle as O
+from oracle.make_golden import TINY, CFG1
+from sketchformer_b200 import synth
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("name,kw,cont,B", [("tiny_tokens.npz", TINY, False, 4),
+                                            ("tiny_continuous.npz", TINY, True, 4),
+                                            ("cfg1_tokens.npz", CFG1, False, 8)])
+def test_golden_replay(golden_dir, name, kw, cont, B):
+    g = _load(golden_dir, name)
+    cfg = O.OracleConfig(use_continuous_data=cont, **kw)
+    gen = synth.continuous_batch if cont else synth.token_batch
+    x, y = (gen(B, cfg.max_seq_len, cfg.n_classes, 1234) if cont
+            else gen(B, cfg.max_seq_len, cfg.n_classes, 1234, vocab=cfg.vocab_size))
+    assert np.array_equal(x, g["x"]) and np.array_equal(y, g["y"])
+    p = O.init_params(cfg, 0, torch.float32)
+    crc = np.array([zlib.crc32(np.ascontiguousarray(v.numpy()).tobytes()) for v in p.values()], dtype=np.uint32)
+    assert np.array_equal(crc, g["param_crc"]), "torch CPU RNG stream changed: regenerate goldens"
+    p = O.init_params(cfg, 0, torch.float64)
+    opt = O.AdamTF(p, cfg.d_model)
+    for s in range(3):
+        tape = {} if s == 0 else None
+        losses, grads = O.train_step(p, opt, torch.from_numpy(x), torch.from_numpy(y), cfg, tape=tape,
+                                     dtype=torch.float64)
+        for k, v in losses.items():
+            assert v == pytest.approx(float(g[f"f64/step{s}/{k}"]), rel=1e-9, abs=1e-12)
+        if s == 0:
+            for k, v in grads.items():
+                assert float(v.norm()) == pytest.approx(float(g[f"grad_norm/{k}"]), rel=1e-7, abs=1e-12)
+            for k, v in tape.items():
+                assert float(v.norm()) == pytest.approx(float(g[f"act_norm/{k}"]), rel=1e-7)
+
+
+def test_fp32_tracks_fp64(golden_dir):
+    g = _load(golden_dir, "cfg1_tokens.npz")
+    for s in range(3):
+        for k in ("recon_loss", "class_loss", "total_loss"):
+            a, b = float(g[f"f32/step{s}/{k}"]), float(g[f"f64/step{s}/{k}"])
+            assert abs(a - b) <= 2e-5 * abs(b)
+
+
+def test_first_step_has_zero_lr(golden_dir):
+    # lr(0)=0 => step 0 and step 1 see identical weights => identical losses
+    g = _load(golden_dir, "tiny_tokens.npz")
+    assert float(g["f64/step0/total_loss"]) == float(g["f64/step1/total_loss"])
+    assert float(g["f64/step2/total_loss"]) != float(g["f64/step1/total_loss"])
+    assert O.warmup_decay_lr(0, 256) == 0.0
+    assert O.warmup_decay_lr(5000, 256) == pytest.approx(256 ** -0.5 * 5000 ** -0.5)
+    assert O.warmup_decay_lr(1, 128) == pytest.approx(128 ** -0.5 * 5000 ** -1.5)
+    assert O.warmup_decay_lr(20000, 128) == pytest.approx(128 ** -0.5 * 20000 ** -0.5)
+
+
+def test_param_counts():
+    # SURVEY §8d
+    assert O.count_params(O.init_params(O.OracleConfig(**CFG1))) == 2272630
+    cfg2 = O.OracleConfig(d_model=256, dff=1024, max_seq_len=200, n_classes=345)
+    assert O.count_params(O.init_params(cfg2)) == 8299989
+    cfg4 = O.OracleConfig(d_model=256, dff=1024, max_seq_len=200, n_classes=345, use_continuous_data=True)
+    assert O.count_params(O.init_params(cfg4)) == 7532270
+
+
+def test_positional_encoding_and_masks():
+    pe = O.positional_encoding(1000, 128)
+    assert pe.shape == (1, 1000, 128) and pe.dtype == torch.float32
+    assert pe[0, 0, 0] == 0 and pe[0, 0, 1] == 1
+    assert float(pe[0, 3, 0]) == pytest.approx(math.sin(3.0), rel=1e-6)
+    assert float(pe[0, 7, 5]) == pytest.approx(math.cos(7 / 10000 ** (4 / 128)), rel=1e-6)
+    x = torch.tensor([[5, 6, 0, 0], [7, 0, 0, 0]])
+    enc, comb, dec = O.create_masks(x, x[:, :-1], torch.float32)
+    assert enc.shape == (2, 1, 1, 4) and comb.shape == (2, 1, 3, 3)
+    assert enc[0, 0, 0].tolist() == [0, 0, 1, 1]
+    assert comb[0, 0].tolist() == [[0, 1, 1], [0, 0, 1], [0, 0, 1]]
+    assert comb[1, 0].tolist() == [[0, 1, 1], [0, 1, 1], [0, 1, 1]]
+    xc = torch.zeros(1, 3, 5); xc[0, 2, 4] = 1
+    assert O.create_padding_mask(xc, torch.float32)[0, 0, 0].tolist() == [0, 0, 1]
+
+
+def test_sdpa_against_torch_functional():
+    g = torch.Generator().manual_seed(1)
+    q = torch.randn(2, 4, 7, 16, generator=g, dtype=torch.float64)
+    k = torch.randn(2, 4, 9, 16, generator=g, dtype=torch.float64)
+    v = torch.randn(2, 4, 9, 16, generator=g, dtype=torch.float64)
+    pad = torch.zeros(2, 1, 1, 9, dtype=torch.float64); pad[0, ..., 6:] = 1; pad[1, ..., 3:] = 1
+    o, w = O.scaled_dot_product_attention(q, k, v, pad)
+    ref = F.scaled_dot_product_attention(q, k, v, attn_mask=(pad == 0))
+    assert torch.allclose(o, ref, atol=1e-12)
+    assert torch.allclose(w.sum(-1), torch.ones_like(w.sum(-1)), atol=1e-12)
+    assert float(w[0, :, :, 6:].abs().max()) == 0.0 and float(w[1, :, :, 3:].abs().max()) == 0.0
+    # fully-masked row in fp32 -> uniform, not NaN
+    full = torch.ones(1, 1, 1, 9)
+    _, wf = O.scaled_dot_product_attention(q[:1].float(), k[:1].float(), v[:1].float(), full)
+    assert torch.allclose(wf, torch.full_like(wf, 1 / 9), atol=1e-6)
+
+
+def test_layernorm_and_losses_against_functional():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 5, 32, generator=g, dtype=torch.float64)
+    p = {"ln.g": torch.randn(32, generator=g, dtype=torch.float64), "ln.b": torch.randn(32, generator=g, dtype=torch.float64)}
+    assert torch.allclose(O.layer_norm(p, "ln", x), F.layer_norm(x, (32,), p["ln.g"], p["ln.b"], eps=1e-6), atol=1e-12)
+    logits = torch.randn(3, 5, 11, generator=g, dtype=torch.float64)
+    tgt = torch.tensor([[1, 2, 3, 0, 0], [4, 0, 0, 0, 0], [5, 6, 7, 8, 9]])
+    ref = F.cross_entropy(logits.reshape(-1, 11), tgt.reshape(-1), ignore_index=0, reduction="sum") / 15
+    assert float(O.reconstruction_loss(tgt, logits)) == pytest.approx(float(ref), rel=1e-12)
+    cl = torch.randn(4, 10, generator=g, dtype=torch.float64)
+    lab = torch.tensor([[1], [0], [9], [3]])
+    assert float(O.class_loss(lab, cl)) == pytest.approx(float(F.cross_entropy(cl, lab[:, 0])), rel=1e-12)
+
+
+def test_continuous_loss_formula():
+    # SURVEY A.4, written out with explicit loops
+    g = torch.Generator().manual_seed(3)
+    x, _ = synth.continuous_batch(2, 6, 3, 5)
+    real = torch.from_numpy(x).double()
+    pred = torch.randn(2, 6, 5, generator=g, dtype=torch.float64)
+    B, T = 2, 6
+    M = 0.0
+    for b in range(B):
+        for t in range(T):
+            z = pred[b, t, 2:]
+            M += float(torch.logsumexp(z, 0) - z[int(real[b, t, 2:].argmax())])
+    M /= B * T
+    tot = 0.0
+    for b in range(B):
+        for t in range(T):
+            loc = 0.5 * float(((real[b, t, :2] - pred[b, t, :2]) ** 2).sum())
+            tot += (loc + M) * (0.0 if real[b, t, 4] == 1 else 1.0)
+    assert float(O.continuous_reconstruction_loss(real, pred)) == pytest.approx(tot / (B * T), rel=1e-12)
+
+
+def test_dense_expander_is_rank1():
+    p = {"exp.k": torch.tensor([[1., 2., 3.]]), "exp.b": torch.tensor([.5, .25, 0.])}
+    e = torch.tensor([[1., -1.], [2., 0.]])
+    pre = O.dense_expander(p, e)
+    assert pre.shape == (2, 3, 2)
+    for b in range(2):
+        for t in range(3):
+            for c in range(2):
+                assert float(pre[b, t, c]) == float(e[b, c] * p["exp.k"][0, t] + p["exp.b"][t])
+
+
+def test_finite_difference_gradients():
+    cfg = O.OracleConfig(num_layers=1, d_model=16, dff=32, num_heads=2, lowerdim=8, max_seq_len=6,
+                         vocab_size=12, n_classes=3)
+    x, y = synth.token_batch(3, 6, 3, 7, vocab=12)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    p = O.init_params(cfg, 3, torch.float64)
+    for v in p.values():
+        v.requires_grad_(True)
+    _, losses = O.forward_losses(p, xt, yt, cfg, True, None, None, torch.float64)
+    losses["total_loss"].backward()
+    rng = np.random.default_rng(0)
+    for name in ("enc.emb", "enc.l0.mha.wk.k", "enc.l0.ln1.g", "pool.V", "exp.k", "dec.l0.mha2.wv.k",
+                 "dec.l0.ffn.w1.b", "out.k", "cls.b"):
+        w = p[name]
+        flat = w.detach().reshape(-1)
+        for idx in rng.choice(flat.numel(), size=min(3, flat.numel()), replace=False):
+            old = float(flat[idx]); h = 1e-6
+            with torch.no_grad():
+                w.reshape(-1)[idx] = old + h
+                lp = float(O.forward_losses(p, xt, yt, cfg, True, None, None, torch.float64)[1]["total_loss"])
+                w.reshape(-1)[idx] = old - h
+                lm = float(O.forward_losses(p, xt, yt, cfg, True, None, None, torch.float64)[1]["total_loss"])
+                w.reshape(-1)[idx] = old
+            fd = (lp - lm) / (2 * h)
+            assert float(w.grad.reshape(-1)[idx]) == pytest.approx(fd, rel=2e-5, abs=2e-8), name
+
+
+def test_adam_matches_tf_form():
+    w = {"a": torch.tensor([1.0, -2.0], dtype=torch.float64)}
+    opt = O.AdamTF(w, 128)
+    opt.iterations = 10
+    g = {"a": torch.tensor([0.5, 0.25], dtype=torch.float64)}
+    lr = O.warmup_decay_lr(10, 128)
+    m = 0.1 * g["a"]; v = 0.02 * g["a"] ** 2
+    alpha = lr * math.sqrt(1 - 0.98 ** 11) / (1 - 0.9 ** 11)
+    expect = torch.tensor([1.0, -2.0], dtype=torch.float64) - alpha * m / (v.sqrt() + 1e-9)
+    opt.apply(w, g)
+    assert torch.allclose(w["a"], expect, atol=1e-15) and opt.iterations == 11
+
+
+def test_greedy_decode_runs_and_starts_with_sos(golden_dir):
+    g = _load(golden_dir, "tiny_tokens.npz")
+    rec = g["pred/recon"]
+    assert rec.shape[0] == 2 and rec.shape[1] <= TINY["max_seq_len"] + 1
+    assert (rec[:, 0] == TINY["vocab_size"] - 2).all()
