@@ -1,0 +1,220 @@
+/*
+ * skf.h — C ABI of libskf.so, the B200 (sm_100a) device path of the Sketchformer hot path.
+ *
+ * The reference (leosampaio/sketchformer, TF 2.1) has NO native/FFI boundary of its own: its
+ * device path is a tf.function over stock TF ops.  The entry points below are therefore the
+ * boundary SURVEY.md §8(b) dictates; each one cites the reference Python symbol it replaces
+ * (paths relative to the reference repository).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every function returns 0 (SKF_OK) or a negative skf_status; skf_last_error() returns a
+ *    thread-local message for the last failure on the calling thread;
+ *  - no allocation, no ownership transfer: every buffer is a device pointer owned by the caller
+ *    (torch tensors on the Python side); sizes come from the skf_*_bytes / skf_param_* queries;
+ *  - every launch takes the cudaStream_t as `void* stream`, is asynchronous and never
+ *    synchronises (CUDA-graph capturable); one caller per stream;
+ *  - `round_tf32` arguments: when non-zero the stored result is rounded (to nearest) to TF32
+ *    precision because a later tcgen05 kind::tf32 GEMM consumes it and the tensor core would
+ *    otherwise truncate the low 13 mantissa bits (biased);
+ *  - all floating-point tensors are fp32, row-major, leading dimension given in ELEMENTS;
+ *    token / label ids are int64 (models/sketchformer.py:317-322);
+ *  - weights use the Keras orientation kernel = (in, out).
+ */
+#ifndef SKF_H_
+#define SKF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum skf_status {
+  SKF_OK = 0,
+  SKF_ERR_BAD_SHAPE = -1,
+  SKF_ERR_BAD_ALIGN = -2,
+  SKF_ERR_UNSUPPORTED = -3,
+  SKF_ERR_CUDA = -4,
+  SKF_ERR_NCCL = -5,
+  SKF_ERR_BAD_ARG = -6
+} skf_status;
+
+/* Model / batch description.  Mirrors the hparam surface of models/sketchformer.py:24-53 and
+ * dataloaders/distributed_stroke3.py:15-25 that changes device work. */
+typedef struct skf_cfg {
+  int32_t B;                  /* batch_size (per rank)                                  */
+  int32_t T;                  /* max_seq_len: encoder length Te = T, decoder Td = T - 1 */
+  int32_t d;                  /* d_model                                                */
+  int32_t f;                  /* dff                                                    */
+  int32_t H;                  /* num_heads                                              */
+  int32_t L;                  /* num_layers                                             */
+  int32_t V;                  /* vocab size (1004 for the dictionary tokenizer)         */
+  int32_t C;                  /* n_classes                                              */
+  int32_t u;                  /* lowerdim (hidden width of the pooling attention)       */
+  int32_t continuous;         /* use_continuous_data (stroke-5 input, Dense(5) head)    */
+  int32_t blind_decoder_mask; /* cross-attention mask all-zero when 1                   */
+  int32_t do_classification;
+  int32_t do_reconstruction;
+  int32_t warmup_steps;       /* 5000: hard-coded at models/sketchformer.py:113-114      */
+  float class_weight;
+  float recon_weight;
+  float adam_beta1, adam_beta2, adam_eps; /* 0.9, 0.98, 1e-9 (sketchformer.py:121-123)  */
+  int32_t world_size;         /* data-parallel ranks: gradients are scaled by 1/world   */
+  int32_t gemm_backend;       /* 0 = tcgen05 TF32 tensor-core GEMMs, 1 = SIMT fp32 (debug)*/
+  int32_t attn_backend;       /* 0 = default, 1 = SIMT fp32 (debug)                      */
+} skf_cfg;
+
+const char* skf_last_error(void);
+/* Process-wide options.  "tma_tf32": 1 = tensor maps use CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 (the TMA
+ * unit converts fp32->tf32 on load) instead of pre-rounded operands.  Set before creating plans. */
+int skf_set_option(const char* name, int value);
+int skf_version(void);
+/* 1 if the current device can run the sm_100a kernels. */
+int skf_device_ok(void);
+
+/* ---------------- parameter arena ---------------------------------------------------------
+ * All trainable variables live in one flat fp32 arena (same layout for params, grads and the
+ * two Adam moments).  q/k/v kernels of a self-attention block are fused column-wise into
+ * "<mha>.wqkv" (d, 3d); cross-attention keeps "<mha2>.wq" (d,d) and "<mha2>.wkv" (d, 2d).    */
+typedef struct skf_param_entry {
+  char name[56];
+  int64_t offset; /* in floats */
+  int32_t rows, cols;
+} skf_param_entry;
+
+int64_t skf_param_count(const skf_cfg* cfg);
+/* Fills up to `cap` entries, returns the number of entries (or <0). */
+int skf_param_table(const skf_cfg* cfg, skf_param_entry* out, int cap);
+
+/* ---------------- operator-level entry points -------------------------------------------- */
+
+/* Encoder.call / Decoder.call head, builders/layers/transformer.py:288-296, 325-334:
+ * out[b,t,:] = table[tok[b,t],:] * sqrt(d) + PE[t,:].  tok has row stride tok_ld (int64).   */
+int skf_embed_fwd(const int64_t* tok, int64_t tok_ld, const float* table, const float* pe,
+                  float* out, int B, int T, int d, int V, int round_tf32, void* stream);
+/* dtable[tok[b,t],:] += dout[b,t,:] * sqrt(d)   (IndexedSlices scatter-add)     */
+int skf_embed_bwd(const int64_t* tok, int64_t tok_ld, const float* dout, float* dtable, int B,
+                  int T, int d, int V, void* stream);
+/* builders/utils.py:17-32 — fills pe[rows, d] (float64 math, rounded to fp32).             */
+int skf_positional_encoding(float* pe, int rows, int d, void* stream);
+/* builders/utils.py:35-43 — pad[b,t] = (tok[b,t]==0) (tokens) as uint8.                    */
+int skf_pad_flags(const int64_t* tok, int64_t tok_ld, uint8_t* pad, int B, int T, void* stream);
+
+/* tf.keras.layers.Dense (builders/layers/transformer.py:154-158,196-197) and its gradients.
+ * Y[M,N] = epilogue(op(A)[M,K] * op(B)[K,N]).  A is addressed as A[m*sa_m + k*sa_k], B as
+ * B[k*sb_k + n*sb_n] (element strides), so one entry point serves forward (X*W), dgrad (dY*W^T)
+ * and wgrad (X^T*dY).  Epilogue: v = acc; v += bias[n]; act; v *= (mask[m,n] > 0);
+ * v += resid[m,n]; Y = accumulate ? Y + v : v.  backend: 0 tcgen05, 1 SIMT.                */
+typedef enum skf_act { SKF_ACT_NONE = 0, SKF_ACT_RELU = 1, SKF_ACT_TANH = 2 } skf_act;
+typedef struct skf_gemm_epilogue {
+  const float* bias;  /* [N] or NULL */
+  const float* resid; /* [M, ld_resid] or NULL */
+  int64_t ld_resid;
+  const float* mask;  /* [M, ld_mask] or NULL: multiply by (mask > 0) (ReLU backward)        */
+  int64_t ld_mask;
+  int32_t act;        /* skf_act */
+  int32_t accumulate; /* atomically add into Y (split-K weight gradients)                    */
+  int32_t round_tf32; /* round the stored value to TF32 (operand of a later tensor-core GEMM)*/
+  int32_t split_k;    /* >1: split the K range over this many CTAs (needs accumulate=1)       */
+} skf_gemm_epilogue;
+int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,
+             int64_t sb_n, float* Y, int64_t ldy, int M, int N, int K,
+             const skf_gemm_epilogue* epi, int backend, void* stream);
+
+/* builders/utils.py:71-105 + split_heads (transformer.py:160-165), fused.
+ * Q rows are b*Tq+i, K/V rows b*Tk+j; head h occupies columns [h*dh,(h+1)*dh) of each.
+ * mask_mode: 0 none, 1 key padding (key_pad[b,j]!=0 masked), 2 causal | key padding.
+ * Masked logits get -1e9 added after the 1/sqrt(dh) scaling exactly as the reference does.
+ * lse[b,h,i] = logsumexp of the masked scaled logits (saved for backward).                 */
+int skf_attn_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V,
+                 int64_t ldv, float* O, int64_t ldo, float* lse, const uint8_t* key_pad, int B,
+                 int H, int Tq, int Tk, int dh, int mask_mode, int round_tf32, int backend,
+                 void* stream);
+/* delta is a scratch [B,H,Tq] buffer (rowsum(dO*O)).                                        */
+int skf_attn_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V,
+                 int64_t ldv, const float* O, int64_t ldo, const float* dO, int64_t lddo,
+                 const float* lse, float* delta, float* dQ, int64_t lddq, float* dK,
+                 int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad, int B, int H,
+                 int Tq, int Tk, int dh, int mask_mode, int round_tf32, int backend, void* stream);
+
+/* x + sublayer -> LayerNormalization(eps=1e-6) (transformer.py:209-224): s = a + b (+bias);
+ * y = LN(s)*gamma+beta.  s, mean, rstd are saved for backward (any may be NULL).           */
+int skf_add_layernorm_fwd(const float* a, const float* b, const float* bias, const float* gamma,
+                          const float* beta, float* s, float* y, float* mean, float* rstd,
+                          int rows, int d, int round_tf32, void* stream);
+/* ds = dLN(dy); dgamma += .., dbeta += .. (accumulated atomically into zeroed buffers)      */
+int skf_layernorm_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
+                      const float* gamma, float* ds, float* dgamma, float* dbeta, int rows,
+                      int d, int round_tf32, void* stream);
+/* out[n] += sum_m x[m,n]  (bias gradients)                                                  */
+int skf_colsum(const float* x, int64_t ldx, float* out, int M, int N, void* stream);
+
+/* SelfAttnV1.call (transformer.py:61-74) after the tanh GEMM: score[b,t] = u[b,t,:].Vattn;
+ * a = softmax over t (no padding mask); emb[b,:] = sum_t a[b,t] x[b,t,:].                  */
+int skf_pool_fwd(const float* x, const float* u, const float* vattn, float* a, float* emb,
+                 int B, int T, int d, int U, int round_tf32, void* stream);
+/* Given demb: dx[b,t,:] (+)= a*demb ; dupre = (dscore*Vattn)*(1-u^2) ; dV += sum u*dscore    */
+int skf_pool_bwd(const float* x, const float* u, const float* vattn, const float* a,
+                 const float* demb, float* dx, int dx_accumulate, float* dupre, float* dvattn,
+                 int B, int T, int d, int U, int round_tf32, void* stream);
+
+/* DenseExpander.call (transformer.py:370-376): pre[b,t,c] = emb[b,c]*w[t] + beta[t].        */
+int skf_expand_fwd(const float* emb, const float* w, const float* beta, float* pre, int B,
+                   int T, int d, int round_tf32, void* stream);
+int skf_expand_bwd(const float* dpre, const float* emb, const float* w, float* demb,
+                   int demb_accumulate, float* dw, float* dbeta, int B, int T, int d,
+                   void* stream);
+
+/* Token reconstruction loss + accuracy (builders/losses.py:26-41, sketchformer.py:335-339):
+ * loss = sum_rows CE(z,tgt)*[tgt!=0] / rows ; correct = #(argmax z == tgt) over ALL rows.
+ * dlogits (may alias logits) = (softmax(z) - onehot)*[tgt!=0]*scale.  tgt row stride tgt_ld;
+ * stats[0] += loss_sum (unnormalised), stats[1] += correct.  stats are doubles on device.   */
+int skf_token_ce(const float* logits, int64_t ldl, const int64_t* tgt, int64_t tgt_ld, int B,
+                 int Td, int V, float grad_scale, float* dlogits, int64_t lddl, double* stats,
+                 int32_t* argmax_out, int round_tf32, void* stream);
+/* Classification head loss (builders/losses.py:21-24): -log_softmax(z)[y] batch mean.       */
+int skf_class_ce(const float* logits, int64_t ldl, const int64_t* labels, int B, int C,
+                 float grad_scale, float* dlogits, int64_t lddl, double* stats,
+                 int32_t* argmax_out, float* probs, void* stream);
+
+/* TF-2.1 Adam with the Noam schedule evaluated on the device step counter
+ * (builders/schedulers.py:25-29).  *step is read, used, and incremented.        */
+int skf_adam_step(float* params, const float* grads, float* m, float* v, int64_t n,
+                  int64_t* step, int d_model, int warmup_steps, float beta1, float beta2,
+                  float eps, float grad_scale, void* stream);
+
+/* ---------------- whole-step plan --------------------------------------------------------- */
+typedef struct skf_plan skf_plan;
+
+size_t skf_workspace_bytes(const skf_cfg* cfg);
+/* params/grads/adam_m/adam_v: arenas of skf_param_count() floats; workspace of
+ * skf_workspace_bytes() bytes, 256-byte aligned.  grads/adam may be NULL for inference.     */
+int skf_plan_create(const skf_cfg* cfg, float* params, float* grads, float* adam_m,
+                    float* adam_v, void* workspace, size_t workspace_bytes, skf_plan** out);
+void skf_plan_destroy(skf_plan* plan);
+/* One-time device initialisation of constants in the workspace (PE table, counters).       */
+int skf_plan_init(skf_plan* plan, void* stream);
+/* Offset (bytes) and size of a named workspace tensor, for tests / introspection.          */
+int skf_plan_tensor(const skf_plan* plan, const char* name, size_t* offset, size_t* bytes);
+
+/* Transformer.model_trainer (models/sketchformer.py:325-349): forward, losses, backward; when
+ * apply_adam != 0 also the optimizer step.  tokens int64 [B,T] (or float [B,T,5] when
+ * cfg.continuous), labels int64 [B,1]; both device pointers.  Metric sums accumulate in the
+ * workspace tensor "stats" (doubles).                                                      */
+int skf_train_step(skf_plan* plan, const void* tokens, const int64_t* labels, int apply_adam,
+                   void* stream);
+/* Only the optimizer (after an external gradient all-reduce).                               */
+int skf_apply_adam(skf_plan* plan, void* stream);
+/* Transformer.encode_from_seq / predict_class (sketchformer.py:162-168, 223-228):
+ * writes embedding [B,d], class probabilities [B,C] and argmax [B] into the workspace.      */
+int skf_encode(skf_plan* plan, const void* tokens, void* stream);
+/* Transformer.call in inference mode incl. decoder logits for teacher-forced input.         */
+int skf_forward(skf_plan* plan, const void* tokens, void* stream);
+/* Number of kernels launched by this plan since creation (bench `gpu_launches`).           */
+int64_t skf_plan_launches(const skf_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKF_H_ */

@@ -1,0 +1,667 @@
+// HBM-bound kernels of the Sketchformer hot path: embedding gather, LayerNorm fwd/bwd, column
+// sums, pooling bottleneck, DenseExpander, softmax-CE heads, Adam.  Each kernel cites the
+// reference op it replaces; all are coalesced along the feature axis and use warp shuffles for
+// row reductions.  (The tensor-core GEMM / attention kernels live in skf_gemm_tc.cu etc.)
+#include <math.h>
+#include <stdarg.h>
+
+#include "skf_common.cuh"
+
+namespace skf {
+
+thread_local char g_err[512] = {0};
+thread_local int64_t g_launch_count = 0;
+char* err_buf() { return g_err; }
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+__device__ __forceinline__ float maybe_round(float v, int r) { return r ? round_tf32(v) : v; }
+
+// ---------------------------------------------------------------------------------------------
+// K1: embedding gather * sqrt(d) + PE     (builders/layers/transformer.py:292-294, 330-332)
+// one warp per (b,t) row, 128-bit loads/stores along d
+// ---------------------------------------------------------------------------------------------
+__global__ void embed_fwd_k(const int64_t* __restrict__ tok, int64_t tok_ld,
+                            const float* __restrict__ table, const float* __restrict__ pe,
+                            float* __restrict__ out, int B, int T, int d, int V, float scale,
+                            int rnd) {
+  int row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= B * T) return;
+  int b = row / T, t = row - b * T;
+  int64_t id = tok[(int64_t)b * tok_ld + t];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  const float4* e4 = reinterpret_cast<const float4*>(table + id * d);
+  const float4* p4 = reinterpret_cast<const float4*>(pe + (int64_t)t * d);
+  float4* o4 = reinterpret_cast<float4*>(out + (int64_t)row * d);
+  for (int c = threadIdx.x; c < d / 4; c += 32) {
+    float4 e = __ldg(e4 + c), p = __ldg(p4 + c), o;
+    // two roundings like the reference (x *= sqrt(d); x += pe), no FMA contraction
+    o.x = maybe_round(__fadd_rn(__fmul_rn(e.x, scale), p.x), rnd);
+    o.y = maybe_round(__fadd_rn(__fmul_rn(e.y, scale), p.y), rnd);
+    o.z = maybe_round(__fadd_rn(__fmul_rn(e.z, scale), p.z), rnd);
+    o.w = maybe_round(__fadd_rn(__fmul_rn(e.w, scale), p.w), rnd);
+    o4[c] = o;
+  }
+}
+
+// dtable[tok] += dout * sqrt(d)  (tf IndexedSlices -> dense-equivalent)
+__global__ void embed_bwd_k(const int64_t* __restrict__ tok, int64_t tok_ld,
+                            const float* __restrict__ dout, float* __restrict__ dtable, int B,
+                            int T, int d, int V, float scale) {
+  int row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= B * T) return;
+  int b = row / T, t = row - b * T;
+  int64_t id = tok[(int64_t)b * tok_ld + t];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  const float* g = dout + (int64_t)row * d;
+  float* dst = dtable + id * d;
+  for (int c = threadIdx.x; c < d; c += 32) atomicAdd(dst + c, g[c] * scale);
+}
+
+// builders/utils.py:17-32 in float64, rounded once to fp32
+__global__ void posenc_k(float* __restrict__ pe, int rows, int d) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * d) return;
+  int p = idx / d, i = idx - p * d;
+  double rate = 1.0 / pow(10000.0, (double)(2 * (i / 2)) / (double)(float)d);
+  double a = (double)p * rate;
+  pe[idx] = (float)((i & 1) ? cos(a) : sin(a));
+}
+
+__global__ void pad_flags_k(const int64_t* __restrict__ tok, int64_t tok_ld,
+                            uint8_t* __restrict__ pad, int B, int T) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * T) return;
+  int b = idx / T, t = idx - b * T;
+  pad[idx] = tok[(int64_t)b * tok_ld + t] == 0 ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual add + LayerNormalization(eps=1e-6)   (transformer.py:217-218, 222, 250-260)
+// one warp per row; the row lives in registers (d <= 1024)
+// ---------------------------------------------------------------------------------------------
+constexpr int LN_MAX_VEC = 8;  // float4 per lane -> d <= 1024
+
+__global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restrict__ b,
+                             const float* __restrict__ bias, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float* __restrict__ s_out,
+                             float* __restrict__ y, float* __restrict__ mean_out,
+                             float* __restrict__ rstd_out, int rows, int d, int rnd) {
+  int row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= rows) return;
+  int lane = threadIdx.x;
+  int nv = d / 4;
+  float4 v[LN_MAX_VEC];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; k++) {
+    int c = lane + k * 32;
+    if (c < nv) {
+      float4 x = reinterpret_cast<const float4*>(a + (int64_t)row * d)[c];
+      if (b) {
+        float4 z = reinterpret_cast<const float4*>(b + (int64_t)row * d)[c];
+        if (bias) {
+          float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
+          z.x += bb.x; z.y += bb.y; z.z += bb.z; z.w += bb.w;
+        }
+        x.x += z.x; x.y += z.y; x.z += z.z; x.w += z.w;
+      }
+      v[k] = x;
+      sum += (x.x + x.y) + (x.z + x.w);
+    }
+  }
+  sum = warp_sum(sum);
+  float mean = sum / (float)d;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; k++) {
+    int c = lane + k * 32;
+    if (c < nv) {
+      float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  sq = warp_sum(sq);
+  float rstd = 1.0f / sqrtf(sq / (float)d + 1e-6f);
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; k++) {
+    int c = lane + k * 32;
+    if (c < nv) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      float4 o;
+      o.x = maybe_round((v[k].x - mean) * rstd * g.x + be.x, rnd);
+      o.y = maybe_round((v[k].y - mean) * rstd * g.y + be.y, rnd);
+      o.z = maybe_round((v[k].z - mean) * rstd * g.z + be.z, rnd);
+      o.w = maybe_round((v[k].w - mean) * rstd * g.w + be.w, rnd);
+      reinterpret_cast<float4*>(y + (int64_t)row * d)[c] = o;
+      if (s_out) reinterpret_cast<float4*>(s_out + (int64_t)row * d)[c] = v[k];
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// LayerNorm backward.  Each block walks rows blockIdx.x, +gridDim.x, ...; one warp per row;
+// dgamma/dbeta partials stay in registers across the walk, then smem -> one atomic per column.
+__global__ void ln_bwd_k(const float* __restrict__ dy, const float* __restrict__ s,
+                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const float* __restrict__ gamma, float* __restrict__ ds,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d,
+                         int rnd) {
+  extern __shared__ float sm[];  // [2][d]
+  int lane = threadIdx.x, w = threadIdx.y, nw = blockDim.y;
+  int nv = d / 4;
+  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; k++) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = threadIdx.y * 32 + lane; c < 2 * d; c += nw * 32) sm[c] = 0.f;
+  __syncthreads();
+  for (int row = blockIdx.x * nw + w; row < rows; row += gridDim.x * nw) {
+    float mu = mean[row], rs = rstd[row];
+    float4 g[LN_MAX_VEC], xh[LN_MAX_VEC];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VEC; k++) {
+      int c = lane + k * 32;
+      if (c < nv) {
+        float4 dyv = reinterpret_cast<const float4*>(dy + (int64_t)row * d)[c];
+        float4 sv = reinterpret_cast<const float4*>(s + (int64_t)row * d)[c];
+        float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        xh[k] = make_float4((sv.x - mu) * rs, (sv.y - mu) * rs, (sv.z - mu) * rs, (sv.w - mu) * rs);
+        g[k] = make_float4(dyv.x * ga.x, dyv.y * ga.y, dyv.z * ga.z, dyv.w * ga.w);
+        c1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
+        c2 += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
+        ag[k].x += dyv.x * xh[k].x; ag[k].y += dyv.y * xh[k].y;
+        ag[k].z += dyv.z * xh[k].z; ag[k].w += dyv.w * xh[k].w;
+        ab[k].x += dyv.x; ab[k].y += dyv.y; ab[k].z += dyv.z; ab[k].w += dyv.w;
+      }
+    }
+    c1 = warp_sum(c1) / (float)d;
+    c2 = warp_sum(c2) / (float)d;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_VEC; k++) {
+      int c = lane + k * 32;
+      if (c < nv) {
+        float4 o;
+        o.x = maybe_round(rs * (g[k].x - c1 - xh[k].x * c2), rnd);
+        o.y = maybe_round(rs * (g[k].y - c1 - xh[k].y * c2), rnd);
+        o.z = maybe_round(rs * (g[k].z - c1 - xh[k].z * c2), rnd);
+        o.w = maybe_round(rs * (g[k].w - c1 - xh[k].w * c2), rnd);
+        reinterpret_cast<float4*>(ds + (int64_t)row * d)[c] = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LN_MAX_VEC; k++) {
+    int c = lane + k * 32;
+    if (c < nv) {
+      atomicAdd(&sm[c * 4 + 0], ag[k].x); atomicAdd(&sm[c * 4 + 1], ag[k].y);
+      atomicAdd(&sm[c * 4 + 2], ag[k].z); atomicAdd(&sm[c * 4 + 3], ag[k].w);
+      atomicAdd(&sm[d + c * 4 + 0], ab[k].x); atomicAdd(&sm[d + c * 4 + 1], ab[k].y);
+      atomicAdd(&sm[d + c * 4 + 2], ab[k].z); atomicAdd(&sm[d + c * 4 + 3], ab[k].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.y * 32 + lane; c < d; c += nw * 32) {
+    atomicAdd(dgamma + c, sm[c]);
+    atomicAdd(dbeta + c, sm[d + c]);
+  }
+}
+
+// out[n] += sum_m x[m,n]   (bias gradients).  block (32,8): 32 consecutive columns x 8 row lanes
+__global__ void colsum_k(const float* __restrict__ x, int64_t ldx, float* __restrict__ out,
+                         int M, int N) {
+  __shared__ float sm[8][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (col < N)
+    for (int m = blockIdx.y * 8 + threadIdx.y; m < M; m += gridDim.y * 8) acc += x[(int64_t)m * ldx + col];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += sm[i][threadIdx.x];
+    atomicAdd(out + col, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: pooling bottleneck SelfAttnV1 (transformer.py:61-74).  One CTA per sample.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = is_max ? -INFINITY : 0.f;
+  for (int i = 0; i < nw; i++) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void pool_fwd_k(const float* __restrict__ x, const float* __restrict__ u,
+                           const float* __restrict__ vattn, float* __restrict__ a_out,
+                           float* __restrict__ emb, int T, int d, int U, int rnd) {
+  extern __shared__ float sm[];  // sc[T] + red[32]
+  float* sc = sm;
+  float* red = sm + T;
+  int b = blockIdx.x;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int t = w; t < T; t += nw) {
+    const float* ur = u + ((int64_t)b * T + t) * U;
+    float acc = 0.f;
+    for (int j = lane; j < U; j += 32) acc += ur[j] * __ldg(vattn + j);
+    acc = warp_sum(acc);
+    if (lane == 0) sc[t] = acc;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) mx = fmaxf(mx, sc[t]);
+  mx = block_reduce(mx, red, true);
+  float sum = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float e = expf(sc[t] - mx);
+    sc[t] = e;
+    sum += e;
+  }
+  sum = block_reduce(sum, red, false);
+  float inv = 1.0f / sum;
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float p = sc[t] * inv;
+    sc[t] = p;
+    a_out[(int64_t)b * T + t] = p;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc = 0.f;
+    const float* xb = x + (int64_t)b * T * d + c;
+    for (int t = 0; t < T; t++) acc += sc[t] * xb[(int64_t)t * d];
+    emb[(int64_t)b * d + c] = maybe_round(acc, rnd);
+  }
+}
+
+__global__ void pool_bwd_k(const float* __restrict__ x, const float* __restrict__ u,
+                           const float* __restrict__ vattn, const float* __restrict__ a,
+                           const float* __restrict__ demb, float* __restrict__ dx, int dx_acc,
+                           float* __restrict__ dupre, float* __restrict__ dvattn, int T, int d,
+                           int U, int rnd) {
+  extern __shared__ float sm[];  // da[T] + red[32]
+  float* da = sm;
+  float* red = sm + T;
+  int b = blockIdx.x;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* de = demb + (int64_t)b * d;
+  // da_t = demb . x_t
+  for (int t = w; t < T; t += nw) {
+    const float* xr = x + ((int64_t)b * T + t) * d;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc += xr[c] * de[c];
+    acc = warp_sum(acc);
+    if (lane == 0) da[t] = acc;
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) dot += a[(int64_t)b * T + t] * da[t];
+  dot = block_reduce(dot, red, false);
+  __syncthreads();
+  // dscore_t = a_t (da_t - dot)   (softmax over t)
+  for (int t = threadIdx.x; t < T; t += blockDim.x) da[t] = a[(int64_t)b * T + t] * (da[t] - dot);
+  __syncthreads();
+  // dx[b,t,c] (+)= a_t * demb_c
+  for (int t = w; t < T; t += nw) {
+    float at = a[(int64_t)b * T + t];
+    float* dr = dx + ((int64_t)b * T + t) * d;
+    for (int c = lane; c < d; c += 32) {
+      float v = at * de[c];
+      dr[c] = dx_acc ? dr[c] + v : v;
+    }
+  }
+  // dupre[b,t,j] = dscore_t * V_j * (1 - u^2);  dV_j += sum_t u[b,t,j] * dscore_t
+  for (int j = threadIdx.x; j < U; j += blockDim.x) {
+    float vj = __ldg(vattn + j), acc = 0.f;
+    for (int t = 0; t < T; t++) {
+      int64_t o = ((int64_t)b * T + t) * U + j;
+      float uu = u[o];
+      acc += uu * da[t];
+      dupre[o] = maybe_round(da[t] * vj * (1.0f - uu * uu), rnd);
+    }
+    atomicAdd(dvattn + j, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8: DenseExpander (transformer.py:370-376): pre[b,t,c] = emb[b,c]*w[t] + beta[t]
+// ---------------------------------------------------------------------------------------------
+__global__ void expand_fwd_k(const float* __restrict__ emb, const float* __restrict__ w,
+                             const float* __restrict__ beta, float* __restrict__ pre, int B,
+                             int T, int d, int rnd) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*T*d/4
+  int64_t total = (int64_t)B * T * (d / 4);
+  if (idx >= total) return;
+  int c4 = (int)(idx % (d / 4));
+  int64_t bt = idx / (d / 4);
+  int t = (int)(bt % T);
+  int b = (int)(bt / T);
+  float4 e = __ldg(reinterpret_cast<const float4*>(emb + (int64_t)b * d) + c4);
+  float wt = __ldg(w + t), be = __ldg(beta + t);
+  float4 o;
+  o.x = maybe_round(__fadd_rn(__fmul_rn(e.x, wt), be), rnd);
+  o.y = maybe_round(__fadd_rn(__fmul_rn(e.y, wt), be), rnd);
+  o.z = maybe_round(__fadd_rn(__fmul_rn(e.z, wt), be), rnd);
+  o.w = maybe_round(__fadd_rn(__fmul_rn(e.w, wt), be), rnd);
+  reinterpret_cast<float4*>(pre)[idx] = o;
+}
+
+// demb[b,c] (+)= sum_t dpre[b,t,c] w[t]        (grid = B, thread per c)
+__global__ void expand_bwd_emb_k(const float* __restrict__ dpre, const float* __restrict__ w,
+                                 float* __restrict__ demb, int acc, int T, int d) {
+  int b = blockIdx.x;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float s = 0.f;
+    const float* p = dpre + (int64_t)b * T * d + c;
+    for (int t = 0; t < T; t++) s += p[(int64_t)t * d] * __ldg(w + t);
+    float* o = demb + (int64_t)b * d + c;
+    *o = acc ? *o + s : s;
+  }
+}
+// dw[t] += sum_{b,c} dpre[b,t,c] emb[b,c];  dbeta[t] += sum_{b,c} dpre[b,t,c]   (grid = T)
+__global__ void expand_bwd_w_k(const float* __restrict__ dpre, const float* __restrict__ emb,
+                               float* __restrict__ dw, float* __restrict__ dbeta, int B, int T,
+                               int d) {
+  __shared__ float red[32];
+  int t = blockIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < B * d; i += blockDim.x) {
+    int b = i / d, c = i - b * d;
+    float g = dpre[((int64_t)b * T + t) * d + c];
+    s1 += g * emb[i];
+    s2 += g;
+  }
+  s1 = block_reduce(s1, red, false);
+  s2 = block_reduce(s2, red, false);
+  if (threadIdx.x == 0) {
+    atomicAdd(dw + t, s1);
+    atomicAdd(dbeta + t, s2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7/K9: softmax cross-entropy heads (builders/losses.py:21-41; sketchformer.py:335-344).
+// One warp per row.  argmax returns the lowest index among ties (tf.argmax).
+// ---------------------------------------------------------------------------------------------
+__global__ void softmax_ce_k(const float* __restrict__ logits, int64_t ldl,
+                             const int64_t* __restrict__ tgt, int64_t tgt_ld, int rows, int Tc,
+                             int ncols, int ignore_zero, float scale, float* dlogits,
+                             int64_t lddl, float* __restrict__ probs, int64_t ldp,
+                             int32_t* __restrict__ argmax_out, double* __restrict__ stats,
+                             int rnd) {
+  __shared__ float s_loss[8];
+  __shared__ int s_corr[8];
+  int lane = threadIdx.x, w = threadIdx.y;
+  int row = blockIdx.x * blockDim.y + w;
+  float loss = 0.f;
+  int corr = 0;
+  if (row < rows) {
+    const float* z = logits + (int64_t)row * ldl;
+    int b = row / Tc, t = row - b * Tc;
+    int64_t y = tgt ? tgt[(int64_t)b * tgt_ld + t] : -1;
+    float mx = -INFINITY;
+    int am = 0x7fffffff;
+    for (int j = lane; j < ncols; j += 32) {
+      float v = z[j];
+      if (v > mx) { mx = v; am = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      int oa = __shfl_xor_sync(0xffffffffu, am, o);
+      if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+    }
+    float se = 0.f;
+    for (int j = lane; j < ncols; j += 32) se += expf(z[j] - mx);
+    se = warp_sum(se);
+    float lse = mx + logf(se);
+    float inv = 1.0f / se;
+    float mrow = (ignore_zero && y == 0) ? 0.f : 1.f;
+    if (tgt) {
+      float zt = (y >= 0 && y < ncols) ? z[y] : 0.f;
+      loss = (lse - zt) * mrow;
+      corr = (am == (int)y) ? 1 : 0;
+    }
+    if (argmax_out && lane == 0) argmax_out[row] = am;
+    if (probs)
+      for (int j = lane; j < ncols; j += 32) probs[(int64_t)row * ldp + j] = expf(z[j] - mx) * inv;
+    if (dlogits) {
+      float sc = scale * mrow;
+      for (int j = lane; j < ncols; j += 32) {
+        float p = expf(z[j] - mx) * inv;
+        float g = (p - (j == (int)y ? 1.f : 0.f)) * sc;
+        dlogits[(int64_t)row * lddl + j] = maybe_round(g, rnd);
+      }
+    }
+  }
+  if (stats) {
+    if (lane == 0) { s_loss[w] = loss; s_corr[w] = corr; }
+    __syncthreads();
+    if (w == 0 && lane == 0) {
+      double l = 0.0, c = 0.0;
+      for (int i = 0; i < blockDim.y; i++) { l += (double)s_loss[i]; c += (double)s_corr[i]; }
+      atomicAdd(stats + 0, l);
+      atomicAdd(stats + 1, c);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K11: TF-2.1 Adam + Noam schedule, flat arena, 128-bit accesses
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_k(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, int64_t n, const int64_t* __restrict__ step,
+                       float rsqrt_d, float warm_pow, float b1, float b2, float eps,
+                       float gscale) {
+  int64_t it = *step;                       // optimizer.iterations BEFORE the increment
+  float sf = (float)it;
+  float arg1 = 1.0f / sqrtf(sf);            // inf at step 0
+  float arg2 = sf * warm_pow;
+  float lr = rsqrt_d * fminf(arg1, arg2);   // lr(0) == 0
+  double t = (double)(it + 1);
+  float alpha = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+  int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i4);
+    float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float4 mm = *reinterpret_cast<float4*>(m + i4);
+    float4 vv = *reinterpret_cast<float4*>(v + i4);
+#define SKF_ADAM1(c)                                         \
+  {                                                          \
+    float gr = gg.c * gscale;                                \
+    mm.c += (gr - mm.c) * omb1;                              \
+    vv.c += (gr * gr - vv.c) * omb2;                         \
+    pp.c -= (mm.c * alpha) / (sqrtf(vv.c) + eps);            \
+  }
+    SKF_ADAM1(x) SKF_ADAM1(y) SKF_ADAM1(z) SKF_ADAM1(w)
+#undef SKF_ADAM1
+    *reinterpret_cast<float4*>(p + i4) = pp;
+    *reinterpret_cast<float4*>(m + i4) = mm;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+  } else {
+    for (int64_t i = i4; i < n; i++) {
+      float gr = g[i] * gscale;
+      float mi = m[i] + (gr - m[i]) * omb1;
+      float vi = v[i] + (gr * gr - v[i]) * omb2;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] -= (mi * alpha) / (sqrtf(vi) + eps);
+    }
+  }
+}
+__global__ void step_inc_k(int64_t* step) { *step += 1; }
+
+}  // namespace skf
+
+using namespace skf;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* skf_last_error(void) { return skf::err_buf(); }
+int skf_version(void) { return 1; }
+int skf_device_ok(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+int skf_embed_fwd(const int64_t* tok, int64_t tok_ld, const float* table, const float* pe,
+                  float* out, int B, int T, int d, int V, int round_tf32, void* stream) {
+  SKF_REQUIRE(d % 4 == 0 && B > 0 && T > 0, SKF_ERR_BAD_SHAPE, "embed_fwd: d %% 4 != 0 or empty");
+  dim3 blk(32, 8);
+  embed_fwd_k<<<cdiv((long)B * T, 8), blk, 0, as_stream(stream)>>>(tok, tok_ld, table, pe, out, B, T,
+                                                                  d, V, sqrtf((float)d), round_tf32);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_embed_bwd(const int64_t* tok, int64_t tok_ld, const float* dout, float* dtable, int B,
+                  int T, int d, int V, void* stream) {
+  dim3 blk(32, 8);
+  embed_bwd_k<<<cdiv((long)B * T, 8), blk, 0, as_stream(stream)>>>(tok, tok_ld, dout, dtable, B, T, d,
+                                                                  V, sqrtf((float)d));
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_positional_encoding(float* pe, int rows, int d, void* stream) {
+  posenc_k<<<cdiv((long)rows * d, 256), 256, 0, as_stream(stream)>>>(pe, rows, d);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_pad_flags(const int64_t* tok, int64_t tok_ld, uint8_t* pad, int B, int T, void* stream) {
+  pad_flags_k<<<cdiv((long)B * T, 256), 256, 0, as_stream(stream)>>>(tok, tok_ld, pad, B, T);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_add_layernorm_fwd(const float* a, const float* b, const float* bias, const float* gamma,
+                          const float* beta, float* s, float* y, float* mean, float* rstd,
+                          int rows, int d, int round_tf32, void* stream) {
+  SKF_REQUIRE(d % 4 == 0 && d <= 128 * LN_MAX_VEC, SKF_ERR_BAD_SHAPE, "layernorm: d=%d unsupported", d);
+  dim3 blk(32, 8);
+  add_ln_fwd_k<<<cdiv(rows, 8), blk, 0, as_stream(stream)>>>(a, b, bias, gamma, beta, s, y, mean, rstd,
+                                                            rows, d, round_tf32);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_layernorm_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
+                      const float* gamma, float* ds, float* dgamma, float* dbeta, int rows,
+                      int d, int round_tf32, void* stream) {
+  SKF_REQUIRE(d % 4 == 0 && d <= 128 * LN_MAX_VEC, SKF_ERR_BAD_SHAPE, "layernorm: d=%d unsupported", d);
+  dim3 blk(32, 8);
+  int grid = cdiv(rows, 8);
+  if (grid > 148 * 4) grid = 148 * 4;
+  ln_bwd_k<<<grid, blk, 2 * d * sizeof(float), as_stream(stream)>>>(dy, s, mean, rstd, gamma, ds,
+                                                                   dgamma, dbeta, rows, d, round_tf32);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_colsum(const float* x, int64_t ldx, float* out, int M, int N, void* stream) {
+  dim3 blk(32, 8);
+  int gy = cdiv(M, 8 * 16);
+  if (gy > 64) gy = 64;
+  if (gy < 1) gy = 1;
+  colsum_k<<<dim3(cdiv(N, 32), gy), blk, 0, as_stream(stream)>>>(x, ldx, out, M, N);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_pool_fwd(const float* x, const float* u, const float* vattn, float* a, float* emb, int B,
+                 int T, int d, int U, int round_tf32, void* stream) {
+  size_t sm = (T + 32) * sizeof(float);
+  pool_fwd_k<<<B, 256, sm, as_stream(stream)>>>(x, u, vattn, a, emb, T, d, U, round_tf32);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_pool_bwd(const float* x, const float* u, const float* vattn, const float* a,
+                 const float* demb, float* dx, int dx_accumulate, float* dupre, float* dvattn,
+                 int B, int T, int d, int U, int round_tf32, void* stream) {
+  size_t sm = (T + 32) * sizeof(float);
+  pool_bwd_k<<<B, 256, sm, as_stream(stream)>>>(x, u, vattn, a, demb, dx, dx_accumulate, dupre, dvattn,
+                                               T, d, U, round_tf32);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_expand_fwd(const float* emb, const float* w, const float* beta, float* pre, int B, int T,
+                   int d, int round_tf32, void* stream) {
+  SKF_REQUIRE(d % 4 == 0, SKF_ERR_BAD_SHAPE, "expand: d %% 4");
+  int64_t total = (int64_t)B * T * (d / 4);
+  expand_fwd_k<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(emb, w, beta, pre, B, T, d, round_tf32);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_expand_bwd(const float* dpre, const float* emb, const float* w, float* demb,
+                   int demb_accumulate, float* dw, float* dbeta, int B, int T, int d,
+                   void* stream) {
+  expand_bwd_emb_k<<<B, 256, 0, as_stream(stream)>>>(dpre, w, demb, demb_accumulate, T, d);
+  SKF_LAUNCH_CHECK();
+  expand_bwd_w_k<<<T, 256, 0, as_stream(stream)>>>(dpre, emb, dw, dbeta, B, T, d);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_token_ce(const float* logits, int64_t ldl, const int64_t* tgt, int64_t tgt_ld, int B,
+                 int Td, int V, float grad_scale, float* dlogits, int64_t lddl, double* stats,
+                 int32_t* argmax_out, int round_tf32, void* stream) {
+  dim3 blk(32, 8);
+  int rows = B * Td;
+  softmax_ce_k<<<cdiv(rows, 8), blk, 0, as_stream(stream)>>>(logits, ldl, tgt, tgt_ld, rows, Td, V, 1,
+                                                            grad_scale, dlogits, lddl, nullptr, 0,
+                                                            argmax_out, stats, round_tf32);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_class_ce(const float* logits, int64_t ldl, const int64_t* labels, int B, int C,
+                 float grad_scale, float* dlogits, int64_t lddl, double* stats,
+                 int32_t* argmax_out, float* probs, void* stream) {
+  dim3 blk(32, 8);
+  softmax_ce_k<<<cdiv(B, 8), blk, 0, as_stream(stream)>>>(logits, ldl, labels, 1, B, 1, C, 0, grad_scale,
+                                                         dlogits, lddl, probs, C, argmax_out, stats, 0);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, int64_t* step,
+                  int d_model, int warmup_steps, float beta1, float beta2, float eps,
+                  float grad_scale, void* stream) {
+  float rsqrt_d = (float)(1.0 / sqrt((double)(float)d_model));
+  float warm_pow = (float)pow((double)warmup_steps, -1.5);
+  adam_k<<<cdiv(cdiv(n, 4), 256), 256, 0, as_stream(stream)>>>(params, grads, m, v, n, step, rsqrt_d,
+                                                              warm_pow, beta1, beta2, eps, grad_scale);
+  SKF_LAUNCH_CHECK();
+  step_inc_k<<<1, 1, 0, as_stream(stream)>>>(step);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+}  // extern "C"

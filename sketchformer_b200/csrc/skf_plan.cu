@@ -1,0 +1,736 @@
+// Whole-step orchestration: parameter arena layout, workspace layout, forward, losses, backward
+// and optimizer of Transformer.model_trainer (models/sketchformer.py:325-349), plus the inference
+// entry points (encode_from_seq / predict_class, sketchformer.py:162-168, 223-228).
+// Host code only decides WHICH kernel runs on WHICH buffer; every byte of arithmetic happens in
+// the CUDA kernels of this library.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "skf_common.cuh"
+
+namespace skf {
+
+int attn_fwd_simt(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
+                  const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
+int attn_bwd_simt(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
+                  const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
+                  const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
+extern int g_tma_tf32_type;
+
+// ---------------------------------------------------------------------------------------------
+// parameter arena
+// ---------------------------------------------------------------------------------------------
+struct PEntry {
+  std::string name;
+  int64_t off;
+  int rows, cols;
+};
+struct ParamLayout {
+  std::vector<PEntry> e;
+  std::map<std::string, int> idx;
+  int64_t total = 0;
+  void add(const std::string& n, int rows, int cols) {
+    total = (total + 3) & ~(int64_t)3;  // 16-byte aligned tensors (TMA / float4)
+    idx[n] = (int)e.size();
+    e.push_back({n, total, rows, cols});
+    total += (int64_t)rows * cols;
+  }
+  int64_t off(const std::string& n) const { return e[idx.at(n)].off; }
+  bool has(const std::string& n) const { return idx.count(n) != 0; }
+};
+
+static int check_cfg(const skf_cfg* c) {
+  SKF_REQUIRE(c != nullptr, SKF_ERR_BAD_ARG, "cfg is NULL");
+  SKF_REQUIRE(c->B > 0 && c->T > 1 && c->d > 0 && c->f > 0 && c->H > 0 && c->L > 0, SKF_ERR_BAD_SHAPE,
+              "cfg: non-positive dimension");
+  SKF_REQUIRE(c->d % c->H == 0, SKF_ERR_BAD_SHAPE, "cfg: d_model %% num_heads != 0");
+  SKF_REQUIRE(c->d % 4 == 0 && c->f % 4 == 0, SKF_ERR_BAD_SHAPE, "cfg: d_model and dff must be multiples of 4");
+  int dh = c->d / c->H;
+  SKF_REQUIRE(dh == 16 || dh == 32 || dh == 64, SKF_ERR_UNSUPPORTED, "cfg: head dim %d not in {16,32,64}", dh);
+  SKF_REQUIRE(c->u > 0, SKF_ERR_UNSUPPORTED, "cfg: lowerdim=0 (no bottleneck) is not built yet");
+  SKF_REQUIRE(c->u % 4 == 0, SKF_ERR_BAD_SHAPE, "cfg: lowerdim must be a multiple of 4");
+  SKF_REQUIRE(!c->continuous, SKF_ERR_UNSUPPORTED, "cfg: use_continuous_data is not built yet");
+  SKF_REQUIRE(c->V > 0 && c->V % 4 == 0, SKF_ERR_BAD_SHAPE, "cfg: vocab size must be a positive multiple of 4");
+  SKF_REQUIRE(!c->do_classification || c->C > 0, SKF_ERR_BAD_SHAPE, "cfg: n_classes");
+  SKF_REQUIRE(c->T <= 1000, SKF_ERR_BAD_SHAPE, "cfg: max_seq_len > maximum_position_encoding (1000)");
+  return SKF_OK;
+}
+
+static void add_mha_self(ParamLayout& L, const std::string& p, int d) {
+  L.add(p + ".wqkv.k", d, 3 * d);
+  L.add(p + ".wqkv.b", 1, 3 * d);
+  L.add(p + ".wo.k", d, d);
+  L.add(p + ".wo.b", 1, d);
+}
+static void add_ffn_ln(ParamLayout& L, const std::string& p, int d, int f, int nln) {
+  L.add(p + ".ffn.w1.k", d, f);
+  L.add(p + ".ffn.w1.b", 1, f);
+  L.add(p + ".ffn.w2.k", f, d);
+  L.add(p + ".ffn.w2.b", 1, d);
+  for (int i = 1; i <= nln; i++) {
+    L.add(p + ".ln" + std::to_string(i) + ".g", 1, d);
+    L.add(p + ".ln" + std::to_string(i) + ".b", 1, d);
+  }
+}
+
+static ParamLayout build_layout(const skf_cfg& c) {
+  ParamLayout L;
+  L.add("enc.emb", c.V, c.d);
+  for (int i = 0; i < c.L; i++) {
+    std::string p = "enc.l" + std::to_string(i);
+    add_mha_self(L, p + ".mha", c.d);
+    add_ffn_ln(L, p, c.d, c.f, 2);
+  }
+  L.add("pool.W", c.d, c.u);
+  L.add("pool.b", 1, c.u);
+  L.add("pool.V", 1, c.u);
+  if (c.do_classification) {
+    L.add("cls.k", c.d, c.C);
+    L.add("cls.b", 1, c.C);
+  }
+  if (c.do_reconstruction) {
+    L.add("exp.k", 1, c.T);
+    L.add("exp.b", 1, c.T);
+    L.add("dec.emb", c.V, c.d);
+    for (int i = 0; i < c.L; i++) {
+      std::string p = "dec.l" + std::to_string(i);
+      add_mha_self(L, p + ".mha1", c.d);
+      L.add(p + ".mha2.wq.k", c.d, c.d);
+      L.add(p + ".mha2.wq.b", 1, c.d);
+      L.add(p + ".mha2.wkv.k", c.d, 2 * c.d);
+      L.add(p + ".mha2.wkv.b", 1, 2 * c.d);
+      L.add(p + ".mha2.wo.k", c.d, c.d);
+      L.add(p + ".mha2.wo.b", 1, c.d);
+      add_ffn_ln(L, p, c.d, c.f, 3);
+    }
+    L.add("out.k", c.d, c.V);
+    L.add("out.b", 1, c.V);
+  }
+  L.total = (L.total + 3) & ~(int64_t)3;
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+struct WEntry {
+  size_t off, bytes;
+};
+struct Workspace {
+  std::map<std::string, WEntry> t;
+  size_t total = 0;
+  void add(const std::string& n, size_t bytes) {
+    total = (total + 255) & ~(size_t)255;
+    t[n] = {total, bytes};
+    total += bytes;
+  }
+};
+
+static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
+  Workspace W;
+  const size_t F = sizeof(float);
+  const size_t Me = (size_t)c.B * c.T, Md = (size_t)c.B * (c.T - 1);
+  const size_t d = c.d, f = c.f, H = c.H;
+  W.add("step", 8);
+  W.add("stats_step", 8 * sizeof(double));
+  W.add("stats_run", 16 * sizeof(double));
+  W.add("pe", (size_t)c.T * d * F);
+  W.add("wc", (size_t)PL.total * F);  // TF32-rounded compute copy of the weights
+  W.add("enc_pad", Me);
+  W.add("dec_pad", Md);
+  W.add("enc.x0", Me * d * F);
+  for (int i = 0; i < c.L; i++) {
+    std::string p = "enc.l" + std::to_string(i);
+    W.add(p + ".qkv", Me * 3 * d * F);
+    W.add(p + ".ctx", Me * d * F);
+    W.add(p + ".lse", (size_t)c.B * H * c.T * F);
+    W.add(p + ".s1", Me * d * F);
+    W.add(p + ".mean1", Me * F);
+    W.add(p + ".rstd1", Me * F);
+    W.add(p + ".out1", Me * d * F);
+    W.add(p + ".hff", Me * f * F);
+    W.add(p + ".s2", Me * d * F);
+    W.add(p + ".mean2", Me * F);
+    W.add(p + ".rstd2", Me * F);
+    W.add(p + ".out2", Me * d * F);
+  }
+  W.add("pool.u", Me * c.u * F);
+  W.add("pool.a", Me * F);
+  W.add("embedding", (size_t)c.B * d * F);
+  size_t Cp = ((size_t)c.C + 3) & ~(size_t)3;
+  W.add("cls.logits", (size_t)c.B * Cp * F);
+  W.add("cls.dlogits", (size_t)c.B * Cp * F);
+  W.add("cls.probs", (size_t)c.B * (c.C > 0 ? c.C : 1) * F);
+  W.add("cls.argmax", (size_t)c.B * 4);
+  if (c.do_reconstruction) {
+    W.add("pre_decoder", Me * d * F);
+    W.add("dec.x0", Md * d * F);
+    for (int i = 0; i < c.L; i++) {
+      std::string p = "dec.l" + std::to_string(i);
+      W.add(p + ".qkv", Md * 3 * d * F);
+      W.add(p + ".ctx1", Md * d * F);
+      W.add(p + ".lse1", (size_t)c.B * H * (c.T - 1) * F);
+      W.add(p + ".s1", Md * d * F);
+      W.add(p + ".mean1", Md * F);
+      W.add(p + ".rstd1", Md * F);
+      W.add(p + ".out1", Md * d * F);
+      W.add(p + ".q2", Md * d * F);
+      W.add(p + ".kv2", Me * 2 * d * F);
+      W.add(p + ".ctx2", Md * d * F);
+      W.add(p + ".lse2", (size_t)c.B * H * (c.T - 1) * F);
+      W.add(p + ".s2", Md * d * F);
+      W.add(p + ".mean2", Md * F);
+      W.add(p + ".rstd2", Md * F);
+      W.add(p + ".out2", Md * d * F);
+      W.add(p + ".hff", Md * f * F);
+      W.add(p + ".s3", Md * d * F);
+      W.add(p + ".mean3", Md * F);
+      W.add(p + ".rstd3", Md * F);
+      W.add(p + ".out3", Md * d * F);
+    }
+    W.add("recon.logits", Md * (size_t)c.V * F);
+    W.add("recon.argmax", Md * 4);
+  }
+  // backward scratch
+  W.add("g.a", Me * d * F);
+  W.add("g.b", Me * d * F);
+  W.add("g.c", Me * d * F);
+  W.add("g.h", Me * f * F);
+  W.add("g.qkv", Me * 3 * d * F);
+  W.add("g.q2", Me * d * F);
+  W.add("g.kv2", Me * 2 * d * F);
+  W.add("g.pre", Me * d * F);
+  W.add("g.emb", (size_t)c.B * d * F);
+  W.add("g.u", Me * c.u * F);
+  W.add("g.delta", (size_t)c.B * H * c.T * F);
+  W.total = (W.total + 255) & ~(size_t)255;
+  return W;
+}
+
+}  // namespace skf
+
+using namespace skf;
+
+struct skf_plan {
+  skf_cfg c;
+  ParamLayout PL;
+  Workspace W;
+  float *params, *grads, *am, *av;
+  uint8_t* ws;
+  int64_t launches = 0;
+  bool round_ops = false;  // round GEMM operands to TF32 when they are produced
+  const float* wc = nullptr;
+
+  float* wsf(const std::string& n) const { return reinterpret_cast<float*>(ws + W.t.at(n).off); }
+  template <class T>
+  T* wsp(const std::string& n) const { return reinterpret_cast<T*>(ws + W.t.at(n).off); }
+  const float* w(const std::string& n) const { return wc + PL.off(n); }       // GEMM operand copy
+  const float* pw(const std::string& n) const { return params + PL.off(n); }  // exact fp32 master
+  float* g(const std::string& n) const { return grads + PL.off(n); }
+};
+
+namespace skf {
+
+__global__ void round_copy_k(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = round_tf32(src[i]);
+}
+
+// stats_step: [0] recon CE sum, [1] recon correct, [2] class CE sum, [3] class correct
+// stats_run : [0] sum recon_loss [1] recon correct [2] recon count [3] sum class_loss [4] class correct
+//             [5] class count [6] sum total_loss [7] steps | [8..12] last step: recon_loss, recon_acc,
+//             class_loss, class_acc, total_loss     (builders/keras_metrics.py:19-42 running means)
+__global__ void stats_finalize_k(const double* __restrict__ st, double* __restrict__ run, double n_recon,
+                                 double n_class, double recon_w, double class_w, int do_recon, int do_class) {
+  double rl = do_recon ? recon_w * st[0] / n_recon : 0.0;
+  double cl = do_class ? class_w * st[2] / n_class : 0.0;
+  double tot = rl + cl;
+  if (do_recon) { run[0] += rl; run[1] += st[1]; run[2] += n_recon; }
+  if (do_class) { run[3] += cl; run[4] += st[3]; run[5] += n_class; }
+  run[6] += tot;
+  run[7] += 1.0;
+  run[8] = rl;
+  run[9] = do_recon ? st[1] / n_recon : 0.0;
+  run[10] = cl;
+  run[11] = do_class ? st[3] / n_class : 0.0;
+  run[12] = tot;
+}
+
+// ---- GEMM front-end used by the plan ---------------------------------------------------------
+struct Gemm {
+  const skf_plan* P;
+  cudaStream_t st;
+  int run(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
+          int64_t ldy, int M, int N, int K, skf_gemm_epilogue e) const {
+    bool tc = P->c.gemm_backend == 0 && gemm_tc_supported(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e);
+    if (!P->round_ops) e.round_tf32 = 0;
+    if (e.accumulate) {
+      // split-K so that the grid fills the 148 SMs about twice
+      long tiles = tc ? (long)cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256))
+                      : (long)cdiv(M, 64) * cdiv(N, 64);
+      int want = (int)((2 * 148 + tiles - 1) / tiles);
+      int maxs = K / 256 > 0 ? K / 256 : 1;
+      e.split_k = want < 1 ? 1 : (want > maxs ? maxs : want);
+    }
+    return tc ? gemm_tc(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, st)
+              : gemm_simt(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, st);
+  }
+  // Y[M,N] = act(X[M,K] * W[K,N] + bias) (+ resid)
+  int fwd(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, int act,
+          const float* resid, int rnd) const {
+    skf_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.bias = bias; e.act = act; e.resid = resid; e.ld_resid = N; e.round_tf32 = rnd;
+    return run(X, K, 1, W, N, 1, Y, N, M, N, K, e);
+  }
+  // dX[M,K] = dY[M,N] * W[K,N]^T  (* (mask>0)) (+ resid)
+  int dgrad(const float* dY, const float* W, float* dX, int M, int N, int K, const float* mask,
+            const float* resid, int rnd) const {
+    skf_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.mask = mask; e.ld_mask = K; e.resid = resid; e.ld_resid = K; e.round_tf32 = rnd;
+    return run(dY, N, 1, W, 1, N, dX, K, M, K, N, e);
+  }
+  // dW[K,N] += X[M,K]^T * dY[M,N] ; db[N] += colsum(dY)
+  int wgrad(const float* X, const float* dY, float* dW, float* db, int M, int N, int K) const {
+    skf_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.accumulate = 1;
+    SKF_TRY(run(X, 1, K, dY, N, 1, dW, N, K, N, M, e));
+    if (db) SKF_TRY(skf_colsum(dY, N, db, M, N, st));
+    return SKF_OK;
+  }
+};
+
+static int attn_fwd_any(const skf_plan* P, const float* Q, int64_t ldq, const float* K, int64_t ldk,
+                        const float* V, int64_t ldv, float* O, int64_t ldo, float* lse, const uint8_t* pad,
+                        int Tq, int Tk, int mode, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  return attn_fwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode,
+                       P->round_ops ? 1 : 0, st);
+}
+static int attn_bwd_any(const skf_plan* P, const float* Q, int64_t ldq, const float* K, int64_t ldk,
+                        const float* V, int64_t ldv, const float* O, int64_t ldo, const float* dO, int64_t lddo,
+                        const float* lse, float* delta, float* dQ, int64_t lddq, float* dK, int64_t lddk,
+                        float* dV, int64_t lddv, const uint8_t* pad, int Tq, int Tk, int mode, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  return attn_bwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad,
+                       c.B, c.H, Tq, Tk, c.d / c.H, mode, P->round_ops ? 1 : 0, st);
+}
+
+// ---- forward -----------------------------------------------------------------------------------
+static int refresh_compute_weights(skf_plan* P, cudaStream_t st) {
+  if (!P->round_ops) {
+    P->wc = P->params;
+    return SKF_OK;
+  }
+  float* dst = P->wsf("wc");
+  round_copy_k<<<cdiv(P->PL.total, 256), 256, 0, st>>>(P->params, dst, P->PL.total);
+  SKF_LAUNCH_CHECK();
+  P->wc = dst;
+  return SKF_OK;
+}
+
+static int forward_encoder(skf_plan* P, const int64_t* tok, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  const int B = c.B, T = c.T, d = c.d, f = c.f, Me = B * T;
+  const int rnd = P->round_ops ? 1 : 0;
+  Gemm G{P, st};
+  uint8_t* enc_pad = P->wsp<uint8_t>("enc_pad");
+  SKF_TRY(skf_pad_flags(tok, T, enc_pad, B, T, st));
+  float* x = P->wsf("enc.x0");
+  SKF_TRY(skf_embed_fwd(tok, T, P->pw("enc.emb"), P->wsf("pe"), x, B, T, d, c.V, rnd, st));
+  for (int i = 0; i < c.L; i++) {
+    std::string p = "enc.l" + std::to_string(i);
+    float* qkv = P->wsf(p + ".qkv");
+    SKF_TRY(G.fwd(x, P->w(p + ".mha.wqkv.k"), P->pw(p + ".mha.wqkv.b"), qkv, Me, 3 * d, d, SKF_ACT_NONE, nullptr, 0));
+    float* ctx = P->wsf(p + ".ctx");
+    SKF_TRY(attn_fwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, ctx, d, P->wsf(p + ".lse"), enc_pad,
+                         T, T, 1, st));
+    float* s1 = P->wsf(p + ".s1");
+    SKF_TRY(G.fwd(ctx, P->w(p + ".mha.wo.k"), P->pw(p + ".mha.wo.b"), s1, Me, d, d, SKF_ACT_NONE, x, 0));
+    float* out1 = P->wsf(p + ".out1");
+    SKF_TRY(skf_add_layernorm_fwd(s1, nullptr, nullptr, P->pw(p + ".ln1.g"), P->pw(p + ".ln1.b"), nullptr, out1,
+                                  P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), Me, d, rnd, st));
+    float* hff = P->wsf(p + ".hff");
+    SKF_TRY(G.fwd(out1, P->w(p + ".ffn.w1.k"), P->pw(p + ".ffn.w1.b"), hff, Me, f, d, SKF_ACT_RELU, nullptr, 1));
+    float* s2 = P->wsf(p + ".s2");
+    SKF_TRY(G.fwd(hff, P->w(p + ".ffn.w2.k"), P->pw(p + ".ffn.w2.b"), s2, Me, d, f, SKF_ACT_NONE, out1, 0));
+    float* out2 = P->wsf(p + ".out2");
+    SKF_TRY(skf_add_layernorm_fwd(s2, nullptr, nullptr, P->pw(p + ".ln2.g"), P->pw(p + ".ln2.b"), nullptr, out2,
+                                  P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), Me, d, rnd, st));
+    x = out2;
+  }
+  // bottleneck (SelfAttnV1.call transformer.py:61-74)
+  float* u = P->wsf("pool.u");
+  SKF_TRY(G.fwd(x, P->w("pool.W"), P->pw("pool.b"), u, Me, c.u, d, SKF_ACT_TANH, nullptr, 0));
+  SKF_TRY(skf_pool_fwd(x, u, P->pw("pool.V"), P->wsf("pool.a"), P->wsf("embedding"), B, T, d, c.u, 0, st));
+  if (c.do_classification) {
+    int Cp = (c.C + 3) & ~3;
+    skf_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.bias = P->pw("cls.b");
+    // classifier runs in exact fp32 (C=345 rows are not 16-byte multiples; the op is tiny)
+    SKF_TRY(gemm_simt(P->wsf("embedding"), d, 1, P->pw("cls.k"), c.C, 1, P->wsf("cls.logits"), Cp,
+                      B, c.C, d, &e, st));
+  }
+  return SKF_OK;
+}
+
+static int forward_decoder(skf_plan* P, const int64_t* tok, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  const int B = c.B, T = c.T, Td = c.T - 1, d = c.d, f = c.f, Me = B * T, Md = B * Td;
+  const int rnd = P->round_ops ? 1 : 0;
+  Gemm G{P, st};
+  float* pre = P->wsf("pre_decoder");
+  SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre,
+                         B, T, d, rnd, st));
+  uint8_t* dec_pad = P->wsp<uint8_t>("dec_pad");
+  SKF_TRY(skf_pad_flags(tok, T, dec_pad, B, Td, st));      // tar_inp = tar[:, :-1]
+  float* x = P->wsf("dec.x0");
+  SKF_TRY(skf_embed_fwd(tok, T, P->pw("dec.emb"), P->wsf("pe"), x, B, Td, d, c.V, rnd, st));
+  const uint8_t* cross_pad = c.blind_decoder_mask ? nullptr : P->wsp<uint8_t>("enc_pad");
+  const int cross_mode = c.blind_decoder_mask ? 0 : 1;
+  for (int i = 0; i < c.L; i++) {
+    std::string p = "dec.l" + std::to_string(i);
+    float* qkv = P->wsf(p + ".qkv");
+    SKF_TRY(G.fwd(x, P->w(p + ".mha1.wqkv.k"), P->pw(p + ".mha1.wqkv.b"), qkv, Md, 3 * d, d, SKF_ACT_NONE, nullptr, 0));
+    float* ctx1 = P->wsf(p + ".ctx1");
+    SKF_TRY(attn_fwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, ctx1, d, P->wsf(p + ".lse1"), dec_pad,
+                         Td, Td, 2, st));
+    float* s1 = P->wsf(p + ".s1");
+    SKF_TRY(G.fwd(ctx1, P->w(p + ".mha1.wo.k"), P->pw(p + ".mha1.wo.b"), s1, Md, d, d, SKF_ACT_NONE, x, 0));
+    float* out1 = P->wsf(p + ".out1");
+    SKF_TRY(skf_add_layernorm_fwd(s1, nullptr, nullptr, P->pw(p + ".ln1.g"), P->pw(p + ".ln1.b"), nullptr, out1,
+                                  P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), Md, d, rnd, st));
+    float* q2 = P->wsf(p + ".q2");
+    SKF_TRY(G.fwd(out1, P->w(p + ".mha2.wq.k"), P->pw(p + ".mha2.wq.b"), q2, Md, d, d, SKF_ACT_NONE, nullptr, 0));
+    float* kv2 = P->wsf(p + ".kv2");
+    SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), kv2, Me, 2 * d, d, SKF_ACT_NONE, nullptr, 0));
+    float* ctx2 = P->wsf(p + ".ctx2");
+    SKF_TRY(attn_fwd_any(P, q2, d, kv2, 2 * d, kv2 + d, 2 * d, ctx2, d, P->wsf(p + ".lse2"), cross_pad, Td, T,
+                         cross_mode, st));
+    float* s2 = P->wsf(p + ".s2");
+    SKF_TRY(G.fwd(ctx2, P->w(p + ".mha2.wo.k"), P->pw(p + ".mha2.wo.b"), s2, Md, d, d, SKF_ACT_NONE, out1, 0));
+    float* out2 = P->wsf(p + ".out2");
+    SKF_TRY(skf_add_layernorm_fwd(s2, nullptr, nullptr, P->pw(p + ".ln2.g"), P->pw(p + ".ln2.b"), nullptr, out2,
+                                  P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), Md, d, rnd, st));
+    float* hff = P->wsf(p + ".hff");
+    SKF_TRY(G.fwd(out2, P->w(p + ".ffn.w1.k"), P->pw(p + ".ffn.w1.b"), hff, Md, f, d, SKF_ACT_RELU, nullptr, 1));
+    float* s3 = P->wsf(p + ".s3");
+    SKF_TRY(G.fwd(hff, P->w(p + ".ffn.w2.k"), P->pw(p + ".ffn.w2.b"), s3, Md, d, f, SKF_ACT_NONE, out2, 0));
+    float* out3 = P->wsf(p + ".out3");
+    SKF_TRY(skf_add_layernorm_fwd(s3, nullptr, nullptr, P->pw(p + ".ln3.g"), P->pw(p + ".ln3.b"), nullptr, out3,
+                                  P->wsf(p + ".mean3"), P->wsf(p + ".rstd3"), Md, d, rnd, st));
+    x = out3;
+  }
+  SKF_TRY(G.fwd(x, P->w("out.k"), P->pw("out.b"), P->wsf("recon.logits"), Md, c.V, d, SKF_ACT_NONE, nullptr, 0));
+  return SKF_OK;
+}
+
+// ---- losses ------------------------------------------------------------------------------------
+static int losses(skf_plan* P, const int64_t* tok, const int64_t* labels, bool want_grad, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  const int B = c.B, T = c.T, Td = T - 1;
+  double* ss = P->wsp<double>("stats_step");
+  SKF_CUDA(cudaMemsetAsync(ss, 0, 8 * sizeof(double), st));
+  if (c.do_reconstruction) {
+    float* lg = P->wsf("recon.logits");
+    float scale = c.recon_weight / (float)((double)B * Td);
+    SKF_TRY(skf_token_ce(lg, c.V, tok + 1, T, B, Td, c.V, scale, want_grad ? lg : nullptr, c.V, ss + 0,
+                         P->wsp<int32_t>("recon.argmax"), P->round_ops ? 1 : 0, st));
+  }
+  if (c.do_classification) {
+    int Cp = (c.C + 3) & ~3;
+    float scale = c.class_weight / (float)B;
+    SKF_TRY(skf_class_ce(P->wsf("cls.logits"), Cp, labels, B, c.C, scale, want_grad ? P->wsf("cls.dlogits") : nullptr,
+                         Cp, labels ? ss + 2 : nullptr, P->wsp<int32_t>("cls.argmax"), P->wsf("cls.probs"), st));
+  }
+  if (labels) {
+    stats_finalize_k<<<1, 1, 0, st>>>(ss, P->wsp<double>("stats_run"), (double)B * Td, (double)B,
+                                      (double)c.recon_weight, (double)c.class_weight, c.do_reconstruction,
+                                      c.do_classification);
+    SKF_LAUNCH_CHECK();
+  }
+  return SKF_OK;
+}
+
+// ---- backward ----------------------------------------------------------------------------------
+static int backward(skf_plan* P, const int64_t* tok, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  const int B = c.B, T = c.T, Td = T - 1, d = c.d, f = c.f, Me = B * T, Md = B * Td;
+  const int rnd = P->round_ops ? 1 : 0;
+  Gemm G{P, st};
+  SKF_CUDA(cudaMemsetAsync(P->grads, 0, (size_t)P->PL.total * sizeof(float), st));
+  float *gA = P->wsf("g.a"), *gB = P->wsf("g.b"), *gC = P->wsf("g.c"), *gH = P->wsf("g.h");
+  float *gQKV = P->wsf("g.qkv"), *gQ2 = P->wsf("g.q2"), *gKV2 = P->wsf("g.kv2"), *gPre = P->wsf("g.pre");
+  float *gEmb = P->wsf("g.emb"), *gU = P->wsf("g.u"), *delta = P->wsf("g.delta");
+  const uint8_t* enc_pad = P->wsp<uint8_t>("enc_pad");
+  bool have_demb = false;
+
+  if (c.do_reconstruction) {
+    const uint8_t* dec_pad = P->wsp<uint8_t>("dec_pad");
+    const uint8_t* cross_pad = c.blind_decoder_mask ? nullptr : enc_pad;
+    const int cross_mode = c.blind_decoder_mask ? 0 : 1;
+    float* pre = P->wsf("pre_decoder");
+    float* dlog = P->wsf("recon.logits");  // holds dlogits after losses()
+    std::string last = "dec.l" + std::to_string(c.L - 1);
+    SKF_TRY(G.wgrad(P->wsf(last + ".out3"), dlog, P->g("out.k"), P->g("out.b"), Md, c.V, d));
+    SKF_TRY(G.dgrad(dlog, P->w("out.k"), gA, Md, c.V, d, nullptr, nullptr, 0));
+    for (int i = c.L - 1; i >= 0; i--) {
+      std::string p = "dec.l" + std::to_string(i);
+      const float* xin = i == 0 ? P->wsf("dec.x0") : P->wsf("dec.l" + std::to_string(i - 1) + ".out3");
+      // LN3 + FFN
+      SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s3"), P->wsf(p + ".mean3"), P->wsf(p + ".rstd3"), P->pw(p + ".ln3.g"),
+                                gB, P->g(p + ".ln3.g"), P->g(p + ".ln3.b"), Md, d, rnd, st));
+      SKF_TRY(G.wgrad(P->wsf(p + ".hff"), gB, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Md, d, f));
+      SKF_TRY(G.dgrad(gB, P->w(p + ".ffn.w2.k"), gH, Md, d, f, P->wsf(p + ".hff"), nullptr, 1));
+      SKF_TRY(G.wgrad(P->wsf(p + ".out2"), gH, P->g(p + ".ffn.w1.k"), P->g(p + ".ffn.w1.b"), Md, f, d));
+      SKF_TRY(G.dgrad(gH, P->w(p + ".ffn.w1.k"), gA, Md, f, d, nullptr, gB, 0));
+      // LN2 + cross attention
+      SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s2"), P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), P->pw(p + ".ln2.g"),
+                                gB, P->g(p + ".ln2.g"), P->g(p + ".ln2.b"), Md, d, rnd, st));
+      SKF_TRY(G.wgrad(P->wsf(p + ".ctx2"), gB, P->g(p + ".mha2.wo.k"), P->g(p + ".mha2.wo.b"), Md, d, d));
+      SKF_TRY(G.dgrad(gB, P->w(p + ".mha2.wo.k"), gC, Md, d, d, nullptr, nullptr, 0));
+      float* kv2 = P->wsf(p + ".kv2");
+      SKF_TRY(attn_bwd_any(P, P->wsf(p + ".q2"), d, kv2, 2 * d, kv2 + d, 2 * d, P->wsf(p + ".ctx2"), d, gC, d,
+                           P->wsf(p + ".lse2"), delta, gQ2, d, gKV2, 2 * d, gKV2 + d, 2 * d, cross_pad, Td, T,
+                           cross_mode, st));
+      SKF_TRY(G.wgrad(P->wsf(p + ".out1"), gQ2, P->g(p + ".mha2.wq.k"), P->g(p + ".mha2.wq.b"), Md, d, d));
+      SKF_TRY(G.wgrad(pre, gKV2, P->g(p + ".mha2.wkv.k"), P->g(p + ".mha2.wkv.b"), Me, 2 * d, d));
+      SKF_TRY(G.dgrad(gKV2, P->w(p + ".mha2.wkv.k"), gPre, Me, 2 * d, d, nullptr, i == c.L - 1 ? nullptr : gPre, 0));
+      SKF_TRY(G.dgrad(gQ2, P->w(p + ".mha2.wq.k"), gA, Md, d, d, nullptr, gB, 0));
+      // LN1 + masked self attention
+      SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s1"), P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), P->pw(p + ".ln1.g"),
+                                gB, P->g(p + ".ln1.g"), P->g(p + ".ln1.b"), Md, d, rnd, st));
+      SKF_TRY(G.wgrad(P->wsf(p + ".ctx1"), gB, P->g(p + ".mha1.wo.k"), P->g(p + ".mha1.wo.b"), Md, d, d));
+      SKF_TRY(G.dgrad(gB, P->w(p + ".mha1.wo.k"), gC, Md, d, d, nullptr, nullptr, 0));
+      float* qkv = P->wsf(p + ".qkv");
+      SKF_TRY(attn_bwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, P->wsf(p + ".ctx1"), d, gC, d,
+                           P->wsf(p + ".lse1"), delta, gQKV, 3 * d, gQKV + d, 3 * d, gQKV + 2 * d, 3 * d, dec_pad,
+                           Td, Td, 2, st));
+      SKF_TRY(G.wgrad(xin, gQKV, P->g(p + ".mha1.wqkv.k"), P->g(p + ".mha1.wqkv.b"), Md, 3 * d, d));
+      SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha1.wqkv.k"), gA, Md, 3 * d, d, nullptr, gB, 0));
+    }
+    SKF_TRY(skf_embed_bwd(tok, T, gA, P->g("dec.emb"), B, Td, d, c.V, st));
+    SKF_TRY(skf_expand_bwd(gPre, P->wsf("embedding"), P->pw("exp.k"), gEmb, 0, P->g("exp.k"),
+                           P->g("exp.b"), B, T, d, st));
+    have_demb = true;
+  }
+  if (c.do_classification) {
+    int Cp = (c.C + 3) & ~3;
+    float* dl = P->wsf("cls.dlogits");
+    skf_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.accumulate = 1;
+    SKF_TRY(gemm_simt(P->wsf("embedding"), 1, d, dl, Cp, 1, P->g("cls.k"), c.C, d, c.C, B, &e, st));
+    SKF_TRY(skf_colsum(dl, Cp, P->g("cls.b"), B, c.C, st));
+    memset(&e, 0, sizeof(e));
+    if (have_demb) { e.resid = gEmb; e.ld_resid = d; }
+    SKF_TRY(gemm_simt(dl, Cp, 1, P->pw("cls.k"), 1, c.C, gEmb, d, B, d, c.C, &e, st));
+    have_demb = true;
+  }
+  if (!have_demb) return SKF_OK;
+  // bottleneck backward
+  {
+    std::string last = "enc.l" + std::to_string(c.L - 1);
+    const float* x = P->wsf(last + ".out2");
+    SKF_TRY(skf_pool_bwd(x, P->wsf("pool.u"), P->pw("pool.V"), P->wsf("pool.a"), gEmb, gA, 0, gU,
+                         P->g("pool.V"), B, T, d, c.u, rnd, st));
+    SKF_TRY(G.wgrad(x, gU, P->g("pool.W"), P->g("pool.b"), Me, c.u, d));
+    SKF_TRY(G.dgrad(gU, P->w("pool.W"), gA, Me, c.u, d, nullptr, gA, 0));
+  }
+  for (int i = c.L - 1; i >= 0; i--) {
+    std::string p = "enc.l" + std::to_string(i);
+    const float* xin = i == 0 ? P->wsf("enc.x0") : P->wsf("enc.l" + std::to_string(i - 1) + ".out2");
+    SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s2"), P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), P->pw(p + ".ln2.g"),
+                              gB, P->g(p + ".ln2.g"), P->g(p + ".ln2.b"), Me, d, rnd, st));
+    SKF_TRY(G.wgrad(P->wsf(p + ".hff"), gB, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Me, d, f));
+    SKF_TRY(G.dgrad(gB, P->w(p + ".ffn.w2.k"), gH, Me, d, f, P->wsf(p + ".hff"), nullptr, 1));
+    SKF_TRY(G.wgrad(P->wsf(p + ".out1"), gH, P->g(p + ".ffn.w1.k"), P->g(p + ".ffn.w1.b"), Me, f, d));
+    SKF_TRY(G.dgrad(gH, P->w(p + ".ffn.w1.k"), gA, Me, f, d, nullptr, gB, 0));
+    SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s1"), P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), P->pw(p + ".ln1.g"),
+                              gB, P->g(p + ".ln1.g"), P->g(p + ".ln1.b"), Me, d, rnd, st));
+    SKF_TRY(G.wgrad(P->wsf(p + ".ctx"), gB, P->g(p + ".mha.wo.k"), P->g(p + ".mha.wo.b"), Me, d, d));
+    SKF_TRY(G.dgrad(gB, P->w(p + ".mha.wo.k"), gC, Me, d, d, nullptr, nullptr, 0));
+    float* qkv = P->wsf(p + ".qkv");
+    SKF_TRY(attn_bwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, P->wsf(p + ".ctx"), d, gC, d,
+                         P->wsf(p + ".lse"), delta, gQKV, 3 * d, gQKV + d, 3 * d, gQKV + 2 * d, 3 * d, enc_pad, T, T,
+                         1, st));
+    SKF_TRY(G.wgrad(xin, gQKV, P->g(p + ".mha.wqkv.k"), P->g(p + ".mha.wqkv.b"), Me, 3 * d, d));
+    SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha.wqkv.k"), gA, Me, 3 * d, d, nullptr, gB, 0));
+  }
+  SKF_TRY(skf_embed_bwd(tok, T, gA, P->g("enc.emb"), B, T, d, c.V, st));
+  return SKF_OK;
+}
+
+}  // namespace skf
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int skf_set_option(const char* name, int value) {
+  if (name && strcmp(name, "tma_tf32") == 0) {
+    skf::g_tma_tf32_type = value ? 1 : 0;
+    return SKF_OK;
+  }
+  return skf::fail(SKF_ERR_BAD_ARG, "unknown option %s", name ? name : "(null)");
+}
+
+int64_t skf_param_count(const skf_cfg* cfg) {
+  if (check_cfg(cfg) != SKF_OK) return -1;
+  return build_layout(*cfg).total;
+}
+
+int skf_param_table(const skf_cfg* cfg, skf_param_entry* out, int cap) {
+  SKF_TRY(check_cfg(cfg));
+  ParamLayout L = build_layout(*cfg);
+  int n = (int)L.e.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    memset(&out[i], 0, sizeof(out[i]));
+    strncpy(out[i].name, L.e[i].name.c_str(), sizeof(out[i].name) - 1);
+    out[i].offset = L.e[i].off;
+    out[i].rows = L.e[i].rows;
+    out[i].cols = L.e[i].cols;
+  }
+  return n;
+}
+
+size_t skf_workspace_bytes(const skf_cfg* cfg) {
+  if (check_cfg(cfg) != SKF_OK) return 0;
+  ParamLayout L = build_layout(*cfg);
+  return build_workspace(*cfg, L).total;
+}
+
+int skf_plan_create(const skf_cfg* cfg, float* params, float* grads, float* adam_m, float* adam_v, void* workspace,
+                    size_t workspace_bytes, skf_plan** out) {
+  SKF_TRY(check_cfg(cfg));
+  SKF_REQUIRE(out != nullptr && params != nullptr && workspace != nullptr, SKF_ERR_BAD_ARG, "plan_create: NULL argument");
+  SKF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, SKF_ERR_BAD_ALIGN, "workspace must be 256-byte aligned");
+  SKF_REQUIRE((reinterpret_cast<uintptr_t>(params) & 15) == 0, SKF_ERR_BAD_ALIGN, "params must be 16-byte aligned");
+  skf_plan* P = new skf_plan();
+  P->c = *cfg;
+  if (P->c.world_size < 1) P->c.world_size = 1;
+  P->PL = build_layout(*cfg);
+  P->W = build_workspace(*cfg, P->PL);
+  if (workspace_bytes < P->W.total) {
+    size_t need = P->W.total;
+    delete P;
+    return skf::fail(SKF_ERR_BAD_SHAPE, "workspace too small: %zu < %zu", workspace_bytes, need);
+  }
+  P->params = params; P->grads = grads; P->am = adam_m; P->av = adam_v;
+  P->ws = reinterpret_cast<uint8_t*>(workspace);
+  P->round_ops = (cfg->gemm_backend == 0) && !skf::g_tma_tf32_type;
+  P->wc = params;
+  *out = P;
+  return SKF_OK;
+}
+
+void skf_plan_destroy(skf_plan* plan) { delete plan; }
+
+int skf_plan_init(skf_plan* P, void* stream) {
+  SKF_REQUIRE(P != nullptr, SKF_ERR_BAD_ARG, "plan is NULL");
+  cudaStream_t st = as_stream(stream);
+  int64_t l0 = skf::g_launch_count;
+  SKF_CUDA(cudaMemsetAsync(P->ws + P->W.t.at("step").off, 0, 8, st));
+  SKF_CUDA(cudaMemsetAsync(P->ws + P->W.t.at("stats_step").off, 0, 8 * sizeof(double), st));
+  SKF_CUDA(cudaMemsetAsync(P->ws + P->W.t.at("stats_run").off, 0, 16 * sizeof(double), st));
+  SKF_TRY(skf_positional_encoding(P->wsf("pe"), P->c.T, P->c.d, stream));
+  P->launches += skf::g_launch_count - l0;
+  return SKF_OK;
+}
+
+int skf_plan_tensor(const skf_plan* P, const char* name, size_t* offset, size_t* bytes) {
+  SKF_REQUIRE(P != nullptr && name != nullptr, SKF_ERR_BAD_ARG, "plan_tensor: NULL argument");
+  auto it = P->W.t.find(name);
+  SKF_REQUIRE(it != P->W.t.end(), SKF_ERR_BAD_ARG, "no workspace tensor named %s", name);
+  if (offset) *offset = it->second.off;
+  if (bytes) *bytes = it->second.bytes;
+  return SKF_OK;
+}
+
+int skf_apply_adam(skf_plan* P, void* stream) {
+  SKF_REQUIRE(P != nullptr && P->grads && P->am && P->av, SKF_ERR_BAD_ARG, "apply_adam: plan has no optimizer state");
+  int64_t l0 = skf::g_launch_count;
+  const skf_cfg& c = P->c;
+  SKF_TRY(skf_adam_step(P->params, P->grads, P->am, P->av, P->PL.total, P->wsp<int64_t>("step"), c.d,
+                        c.warmup_steps, c.adam_beta1, c.adam_beta2, c.adam_eps, 1.0f / (float)c.world_size, stream));
+  P->launches += skf::g_launch_count - l0;
+  return SKF_OK;
+}
+
+int skf_train_step(skf_plan* P, const void* tokens, const int64_t* labels, int apply_adam, void* stream) {
+  SKF_REQUIRE(P != nullptr && tokens != nullptr, SKF_ERR_BAD_ARG, "train_step: NULL argument");
+  SKF_REQUIRE(P->grads != nullptr, SKF_ERR_BAD_ARG, "train_step: plan created without a gradient arena");
+  SKF_REQUIRE(!P->c.do_classification || labels != nullptr, SKF_ERR_BAD_ARG, "train_step: labels required");
+  cudaStream_t st = as_stream(stream);
+  const int64_t* tok = reinterpret_cast<const int64_t*>(tokens);
+  int64_t l0 = skf::g_launch_count;
+  SKF_TRY(refresh_compute_weights(P, st));
+  SKF_TRY(forward_encoder(P, tok, st));
+  if (P->c.do_reconstruction) SKF_TRY(forward_decoder(P, tok, st));
+  SKF_TRY(losses(P, tok, labels, true, st));
+  SKF_TRY(backward(P, tok, st));
+  P->launches += skf::g_launch_count - l0;
+  if (apply_adam) SKF_TRY(skf_apply_adam(P, stream));
+  return SKF_OK;
+}
+
+int skf_encode(skf_plan* P, const void* tokens, void* stream) {
+  SKF_REQUIRE(P != nullptr && tokens != nullptr, SKF_ERR_BAD_ARG, "encode: NULL argument");
+  cudaStream_t st = as_stream(stream);
+  int64_t l0 = skf::g_launch_count;
+  SKF_TRY(refresh_compute_weights(P, st));
+  SKF_TRY(forward_encoder(P, reinterpret_cast<const int64_t*>(tokens), st));
+  if (P->c.do_classification) {
+    int Cp = (P->c.C + 3) & ~3;
+    SKF_TRY(skf_class_ce(P->wsf("cls.logits"), Cp, nullptr, P->c.B, P->c.C, 0.f, nullptr, Cp, nullptr,
+                         P->wsp<int32_t>("cls.argmax"), P->wsf("cls.probs"), stream));
+  }
+  P->launches += skf::g_launch_count - l0;
+  return SKF_OK;
+}
+
+int skf_forward(skf_plan* P, const void* tokens, void* stream) {
+  SKF_REQUIRE(P != nullptr && tokens != nullptr, SKF_ERR_BAD_ARG, "forward: NULL argument");
+  cudaStream_t st = as_stream(stream);
+  const int64_t* tok = reinterpret_cast<const int64_t*>(tokens);
+  int64_t l0 = skf::g_launch_count;
+  SKF_TRY(refresh_compute_weights(P, st));
+  SKF_TRY(forward_encoder(P, tok, st));
+  if (P->c.do_reconstruction) SKF_TRY(forward_decoder(P, tok, st));
+  SKF_TRY(losses(P, tok, nullptr, false, st));
+  P->launches += skf::g_launch_count - l0;
+  return SKF_OK;
+}
+
+int64_t skf_plan_launches(const skf_plan* P) { return P ? P->launches : 0; }
+
+// ---- thin operator wrappers -------------------------------------------------------------------
+int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
+             int64_t ldy, int M, int N, int K, const skf_gemm_epilogue* epi, int backend, void* stream) {
+  if (backend == 0) return gemm_tc(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
+  return gemm_simt(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
+}
+
+int skf_attn_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, float* O,
+                 int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh,
+                 int mask_mode, int round_tf32, int backend, void* stream) {
+  (void)backend;
+  return attn_fwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, round_tf32,
+                       as_stream(stream));
+}
+
+int skf_attn_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv,
+                 const float* O, int64_t ldo, const float* dO, int64_t lddo, const float* lse, float* delta,
+                 float* dQ, int64_t lddq, float* dK, int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad,
+                 int B, int H, int Tq, int Tk, int dh, int mask_mode, int round_tf32, int backend, void* stream) {
+  (void)backend;
+  return attn_bwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad,
+                       B, H, Tq, Tk, dh, mask_mode, round_tf32, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+"""Device engine: owns the HBM arenas (torch tensors as plain containers) and drives libskf.so.
+
+Layout in HBM (all fp32 unless noted):
+  params / grads / adam_m / adam_v : one flat arena each, layout from skf_param_table()
+  workspace                        : every activation saved for backward + scratch, named tensors
+The arithmetic of the hot path (models/sketchformer.py:325-349 of the reference) happens entirely in
+the CUDA kernels behind include/skf.h; this file only moves pointers.
+"""
+import ctypes as C
+from typing import Dict
+
+import torch
+
+from . import _lib
+from ._lib import SkfCfg, SkfParamEntry, check
+
+
+def make_cfg(B, T, d, f, H, L, V, n_classes, lowerdim, *, continuous=False, blind_decoder_mask=True,
+             do_classification=True, do_reconstruction=True, class_weight=1.0, recon_weight=1.0,
+             world_size=1, gemm_backend=0, attn_backend=0) -> SkfCfg:
+    return SkfCfg(B=B, T=T, d=d, f=f, H=H, L=L, V=V, C=n_classes, u=lowerdim, continuous=int(continuous),
+                  blind_decoder_mask=int(blind_decoder_mask), do_classification=int(do_classification),
+                  do_reconstruction=int(do_reconstruction), warmup_steps=5000, class_weight=class_weight,
+                  recon_weight=recon_weight, adam_beta1=0.9, adam_beta2=0.98, adam_eps=1e-9,
+                  world_size=world_size, gemm_backend=gemm_backend, attn_backend=attn_backend)
+
+
+class Engine:
+    METRIC_NAMES = ("recon_loss", "recon_acc", "class_loss", "class_acc", "total_loss")
+
+    def __init__(self, cfg: SkfCfg, device="cuda:0", training=True):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SkfError("no CUDA device: the Sketchformer engine has no CPU path")
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        if not self.lib.skf_device_ok():
+            raise _lib.SkfError("device is not sm_100 (B200): libskf.so is built for sm_100a only")
+        self.cfg = cfg
+        n = self.lib.skf_param_count(C.byref(cfg))
+        if n <= 0:
+            check(int(n) if n < 0 else -1, "skf_param_count")
+        self.n_params_arena = int(n)
+        ent = (SkfParamEntry * 512)()
+        cnt = self.lib.skf_param_table(C.byref(cfg), ent, 512)
+        if cnt < 0:
+            check(cnt, "skf_param_table")
+        self.table = {ent[i].name.decode(): (int(ent[i].offset), int(ent[i].rows), int(ent[i].cols))
+                      for i in range(cnt)}
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.params = torch.zeros(n, **f32)
+        self.grads = torch.zeros(n, **f32) if training else None
+        self.adam_m = torch.zeros(n, **f32) if training else None
+        self.adam_v = torch.zeros(n, **f32) if training else None
+        wsb = int(self.lib.skf_workspace_bytes(C.byref(cfg)))
+        self.workspace = torch.empty(wsb, dtype=torch.uint8, device=self.device)
+        self._plan = C.c_void_p()
+
+        def ptr(t):
+            return C.c_void_p(t.data_ptr()) if t is not None else None
+
+        check(self.lib.skf_plan_create(C.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.adam_m),
+                                       ptr(self.adam_v), ptr(self.workspace), wsb, C.byref(self._plan)),
+              "skf_plan_create")
+        check(self.lib.skf_plan_init(self._plan, self._stream()), "skf_plan_init")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None) and self._plan.value:
+                self.lib.skf_plan_destroy(self._plan)
+                self._plan = C.c_void_p()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- workspace introspection -----------------------------------------------------------
+    def tensor(self, name, shape=None, dtype=torch.float32):
+        off, nb = C.c_size_t(), C.c_size_t()
+        check(self.lib.skf_plan_tensor(self._plan, name.encode(), C.byref(off), C.byref(nb)), f"tensor {name}")
+        t = self.workspace[off.value: off.value + nb.value].view(dtype)
+        return t.view(*shape) if shape is not None else t
+
+    # ---- parameters: Keras/oracle naming <-> arena ------------------------------------------------
+    def _view(self, arena, name):
+        off, r, c = self.table[name]
+        return arena[off: off + r * c].view(r, c)
+
+    def _map(self, name):
+        """oracle name -> (arena tensor name, column slice or None)"""
+        d = self.cfg.d
+        for tag, fused, order in ((".mha.", "wqkv", ("wq", "wk", "wv")), (".mha1.", "wqkv", ("wq", "wk", "wv")),
+                                  (".mha2.", "wkv", ("wk", "wv"))):
+            if tag in name:
+                head, rest = name.split(tag)
+                w, kind = rest.split(".")
+                if w in order:
+                    i = order.index(w)
+                    return f"{head}{tag}{fused}.{kind}", slice(i * d, (i + 1) * d)
+        return name, None
+
+    def load_params(self, named: Dict[str, torch.Tensor]):
+        """Import tensors named as in oracle/sketchformer_oracle.py (Keras shapes, kernel=(in,out))."""
+        seen = set()
+        for name, val in named.items():
+            tname, sl = self._map(name)
+            dst = self._view(self.params, tname)
+            v = val.detach().to(torch.float32)
+            if name == "pool.V" or v.dim() == 1:
+                v = v.reshape(1, -1)
+            v = v.to(self.device)
+            if sl is None:
+                assert tuple(dst.shape) == tuple(v.shape), (name, tuple(dst.shape), tuple(v.shape))
+                dst.copy_(v)
+            else:
+                dst[:, sl].copy_(v)
+            seen.add(tname)
+        missing = set(self.table) - seen
+        if missing:
+            raise KeyError(f"parameters not provided: {sorted(missing)[:5]}...")
+
+    def _export(self, arena, like: Dict[str, torch.Tensor]):
+        out = {}
+        for name, ref in like.items():
+            tname, sl = self._map(name)
+            src = self._view(arena, tname)
+            v = src if sl is None else src[:, sl]
+            out[name] = v.detach().cpu().reshape(ref.shape).clone()
+        return out
+
+    def export_params(self, like):
+        return self._export(self.params, like)
+
+    def export_grads(self, like):
+        return self._export(self.grads, like)
+
+    # ---- hot path ----------------------------------------------------------------------------
+    def _check_tokens(self, tokens):
+        assert tokens.is_cuda and tokens.dtype == torch.int64 and tokens.is_contiguous()
+        assert tuple(tokens.shape) == (self.cfg.B, self.cfg.T), tuple(tokens.shape)
+
+    def train_step(self, tokens: torch.Tensor, labels: torch.Tensor, apply_adam=True):
+        self._check_tokens(tokens)
+        assert labels.is_cuda and labels.dtype == torch.int64 and labels.numel() == self.cfg.B
+        check(self.lib.skf_train_step(self._plan, C.c_void_p(tokens.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                      int(apply_adam), self._stream()), "skf_train_step")
+
+    def apply_adam(self):
+        check(self.lib.skf_apply_adam(self._plan, self._stream()), "skf_apply_adam")
+
+    def encode(self, tokens):
+        self._check_tokens(tokens)
+        check(self.lib.skf_encode(self._plan, C.c_void_p(tokens.data_ptr()), self._stream()), "skf_encode")
+
+    def forward(self, tokens):
+        self._check_tokens(tokens)
+        check(self.lib.skf_forward(self._plan, C.c_void_p(tokens.data_ptr()), self._stream()), "skf_forward")
+
+    def launches(self):
+        return int(self.lib.skf_plan_launches(self._plan))
+
+    def step_count(self):
+        return int(self.tensor("step", dtype=torch.int64)[0].item())
+
+    def stats(self):
+        """Raw running sums (device -> host read of 16 doubles)."""
+        return self.tensor("stats_run", dtype=torch.float64).cpu().numpy().copy()
+
+    def metrics(self):
+        """Running means exactly like builders/keras_metrics.py:41-42 (never reset in train())."""
+        s = self.stats()
+        steps = max(s[7], 1.0)
+        return {"recon_loss": s[0] / steps, "recon_acc": s[1] / max(s[2], 1.0), "class_loss": s[3] / steps,
+                "class_acc": s[4] / max(s[5], 1.0), "total_loss": s[6] / steps}
+
+    def last_step_metrics(self):
+        s = self.stats()
+        return dict(zip(self.METRIC_NAMES, (float(x) for x in s[8:13])))

@@ -1,0 +1,311 @@
+"""Operator-level parity on a B200: every C-ABI kernel against the oracle's op (or its direct
+torch-CPU fp64 equivalent) on seeded inputs.  Integer/index outputs must be bit-exact; fp32
+kernels within 1e-5 (SIMT, exact fp32) or 1e-3 (tcgen05 TF32), the north-star's tolerance."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+from oracle import sketchformer_oracle as O
+from sketchformer_b200 import _lib, synth
+from tests.gpu_util import gemm, ptr, rel_err, stream, to_tf32
+
+pytestmark = pytest.mark.gpu
+
+TOL_EXACT = 2e-5   # fp32 SIMT kernels vs fp64 oracle
+TOL_TF32 = 1e-3    # tensor-core kernels (north-star: 1e-3 fp32 relative)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    lib = _lib.load()
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert lib.skf_device_ok() == 1, "not an sm_100 device"
+    return lib
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+def test_positional_encoding_and_embed(lib):
+    B, T, d, V = 5, 37, 128, 1004
+    pe = torch.empty(T, d, device="cuda")
+    _lib.check(lib.skf_positional_encoding(ptr(pe), T, d, stream()))
+    ref = O.positional_encoding(1000, d)[0, :T]
+    # float64 sin/cos on device vs numpy: at most 1 ulp of fp32 after the final rounding
+    assert float((pe.cpu() - ref).abs().max()) <= 1.2e-7
+    x, _ = synth.token_batch(B, T, 10, 3)
+    tok = dev(torch.from_numpy(x))
+    g = torch.Generator().manual_seed(0)
+    table = (torch.rand(V, d, generator=g) - 0.5) * 0.1
+    out = torch.empty(B, T, d, device="cuda")
+    _lib.check(lib.skf_embed_fwd(ptr(tok), T, ptr(dev(table)), ptr(dev(ref)), ptr(out), B, T, d, V, 0, stream()))
+    p = {"enc.emb": table}
+    cfg = O.OracleConfig(d_model=d, max_seq_len=T)
+    want = O.embed_input(p, "enc", torch.from_numpy(x), cfg, torch.float32)
+    assert torch.equal(out.cpu(), want), "embedding gather*sqrt(d)+PE must be bit-exact in fp32"
+    # decoder view: tar_inp = tok[:, :-1] with the row stride of the full batch
+    out2 = torch.empty(B, T - 1, d, device="cuda")
+    _lib.check(lib.skf_embed_fwd(ptr(tok), T, ptr(dev(table)), ptr(dev(ref)), ptr(out2), B, T - 1, d, V, 0, stream()))
+    assert torch.equal(out2.cpu(), want[:, :-1])
+    # pad flags (builders/utils.py:35-43)
+    pad = torch.empty(B, T, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.skf_pad_flags(ptr(tok), T, ptr(pad), B, T, stream()))
+    assert torch.equal(pad.cpu().bool(), torch.from_numpy(x) == 0)
+    # backward scatter-add (duplicates accumulate)
+    dout = torch.randn(B, T, d, generator=g)
+    dtab = torch.zeros(V, d, device="cuda")
+    _lib.check(lib.skf_embed_bwd(ptr(tok), T, ptr(dev(dout)), ptr(dtab), B, T, d, V, stream()))
+    want_g = torch.zeros(V, d, dtype=torch.float64)
+    want_g.index_add_(0, torch.from_numpy(x).reshape(-1), dout.double().reshape(-1, d) * math.sqrt(d))
+    assert rel_err(dtab, want_g) < TOL_EXACT
+
+
+@pytest.mark.parametrize("rows,d", [(77, 64), (300, 128), (1000, 256), (129, 512)])
+def test_layernorm_fwd_bwd(lib, rows, d):
+    g = torch.Generator().manual_seed(rows)
+    a = torch.randn(rows, d, generator=g)
+    b = torch.randn(rows, d, generator=g)
+    bias = torch.randn(d, generator=g)
+    gamma = torch.rand(d, generator=g) + 0.5
+    beta = torch.randn(d, generator=g)
+    s = torch.empty(rows, d, device="cuda"); y = torch.empty_like(s)
+    mean = torch.empty(rows, device="cuda"); rstd = torch.empty_like(mean)
+    _lib.check(lib.skf_add_layernorm_fwd(ptr(dev(a)), ptr(dev(b)), ptr(dev(bias)), ptr(dev(gamma)), ptr(dev(beta)),
+                                         ptr(s), ptr(y), ptr(mean), ptr(rstd), rows, d, 0, stream()))
+    sd = (a.double() + (b.double() + bias.double())).requires_grad_(True)
+    p = {"ln.g": gamma.double().requires_grad_(True), "ln.b": beta.double().requires_grad_(True)}
+    want = O.layer_norm(p, "ln", sd)
+    assert rel_err(s, sd) < 1e-6 and rel_err(y, want) < TOL_EXACT
+    dy = torch.randn(rows, d, generator=g)
+    want.backward(dy.double())
+    ds = torch.empty(rows, d, device="cuda")
+    dg = torch.zeros(d, device="cuda"); db = torch.zeros(d, device="cuda")
+    _lib.check(lib.skf_layernorm_bwd(ptr(dev(dy)), ptr(s), ptr(mean), ptr(rstd), ptr(dev(gamma)), ptr(ds), ptr(dg),
+                                     ptr(db), rows, d, 0, stream()))
+    assert rel_err(ds, sd.grad) < TOL_EXACT
+    assert rel_err(dg, p["ln.g"].grad) < TOL_EXACT and rel_err(db, p["ln.b"].grad) < TOL_EXACT
+
+
+def test_colsum(lib):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1234, 345, generator=g)
+    out = torch.zeros(345, device="cuda")
+    xd = dev(x)
+    _lib.check(lib.skf_colsum(ptr(xd), 345, ptr(out), 1234, 345, stream()))
+    assert rel_err(out, x.double().sum(0)) < TOL_EXACT
+
+
+def test_pool_fwd_bwd(lib):
+    B, T, d, U = 6, 50, 128, 64
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, T, d, generator=g).double().requires_grad_(True)
+    p = {"pool.W": (torch.randn(d, U, generator=g) * 0.05).double().requires_grad_(True),
+         "pool.b": (torch.randn(U, generator=g) * 0.1).double().requires_grad_(True),
+         "pool.V": ((torch.rand(U, 1, generator=g) - 0.5)).double().requires_grad_(True)}
+    cfg = O.OracleConfig(d_model=d, lowerdim=U, max_seq_len=T)
+    emb, ai = O.bottleneck(p, x, cfg)
+    u = torch.tanh(x.detach() @ p["pool.W"].detach() + p["pool.b"].detach()).float()
+    xd, ud, vd = dev(x.detach().float()), dev(u), dev(p["pool.V"].detach().float().reshape(-1))
+    a = torch.empty(B, T, device="cuda"); e = torch.empty(B, d, device="cuda")
+    _lib.check(lib.skf_pool_fwd(ptr(xd), ptr(ud), ptr(vd), ptr(a), ptr(e), B, T, d, U, 0, stream()))
+    assert rel_err(a, ai[..., 0]) < TOL_EXACT and rel_err(e, emb) < TOL_EXACT
+    demb = torch.randn(B, d, generator=g)
+    emb.backward(demb.double())
+    dx = torch.empty(B, T, d, device="cuda"); dupre = torch.empty(B, T, U, device="cuda")
+    dv = torch.zeros(U, device="cuda")
+    _lib.check(lib.skf_pool_bwd(ptr(xd), ptr(ud), ptr(vd), ptr(a), ptr(dev(demb)), ptr(dx), 0, ptr(dupre), ptr(dv),
+                                B, T, d, U, 0, stream()))
+    assert rel_err(dv, p["pool.V"].grad.reshape(-1)) < TOL_EXACT
+    # dW = x^T dupre, db = colsum(dupre), dx_total = dx + dupre W^T
+    dup = dupre.double().cpu()
+    assert rel_err(x.detach().reshape(-1, d).T @ dup.reshape(-1, U), p["pool.W"].grad) < TOL_EXACT
+    assert rel_err(dup.reshape(-1, U).sum(0), p["pool.b"].grad) < TOL_EXACT
+    assert rel_err(dx.double().cpu() + dup @ p["pool.W"].detach().T, x.grad) < TOL_EXACT
+
+
+def test_expand_fwd_bwd(lib):
+    B, T, d = 5, 33, 64
+    g = torch.Generator().manual_seed(3)
+    emb = torch.randn(B, d, generator=g).double().requires_grad_(True)
+    p = {"exp.k": torch.randn(1, T, generator=g).double().requires_grad_(True),
+         "exp.b": torch.randn(T, generator=g).double().requires_grad_(True)}
+    pre = O.dense_expander(p, emb)
+    out = torch.empty(B, T, d, device="cuda")
+    ed, wd, bd = dev(emb.detach().float()), dev(p["exp.k"].detach().float().reshape(-1)), dev(p["exp.b"].detach().float())
+    _lib.check(lib.skf_expand_fwd(ptr(ed), ptr(wd), ptr(bd), ptr(out), B, T, d, 0, stream()))
+    assert rel_err(out, pre) < 1e-6
+    dpre = torch.randn(B, T, d, generator=g)
+    pre.backward(dpre.double())
+    demb = torch.empty(B, d, device="cuda"); dw = torch.zeros(T, device="cuda"); db = torch.zeros(T, device="cuda")
+    _lib.check(lib.skf_expand_bwd(ptr(dev(dpre)), ptr(ed), ptr(wd), ptr(demb), 0, ptr(dw), ptr(db), B, T, d, stream()))
+    assert rel_err(demb, emb.grad) < TOL_EXACT
+    assert rel_err(dw, p["exp.k"].grad.reshape(-1)) < TOL_EXACT and rel_err(db, p["exp.b"].grad) < TOL_EXACT
+
+
+def test_token_and_class_ce(lib):
+    B, Td, V = 7, 29, 1004
+    x, y = synth.token_batch(B, Td + 1, 345, 11)
+    g = torch.Generator().manual_seed(4)
+    logits = (torch.randn(B, Td, V, generator=g) * 2).double().requires_grad_(True)
+    tgt = torch.from_numpy(x)[:, 1:]
+    loss = O.reconstruction_loss(tgt, logits)
+    loss.backward()
+    tok = dev(torch.from_numpy(x))
+    lg = dev(logits.detach().float())
+    dl = torch.empty_like(lg)
+    stats = torch.zeros(2, dtype=torch.float64, device="cuda")
+    am = torch.empty(B * Td, dtype=torch.int32, device="cuda")
+    scale = 1.0 / (B * Td)
+    _lib.check(lib.skf_token_ce(ptr(lg), V, C.c_void_p(tok.data_ptr() + 8), Td + 1, B, Td, V, scale, ptr(dl), V,
+                                ptr(stats), ptr(am), 0, stream()))
+    st = stats.cpu()
+    assert abs(float(st[0]) * scale - float(loss)) < 1e-5 * abs(float(loss))
+    want_am = logits.detach().float().argmax(-1).reshape(-1).to(torch.int32)
+    assert torch.equal(am.cpu(), want_am), "argmax must be bit-exact"
+    assert float(st[1]) == float((want_am.long() == tgt.reshape(-1)).sum())
+    assert rel_err(dl, logits.grad) < TOL_EXACT
+    # classification head
+    Cn = 345
+    cl = (torch.randn(B, Cn, generator=g)).double().requires_grad_(True)
+    lab = torch.from_numpy(y)
+    closs = O.class_loss(lab, cl)
+    closs.backward()
+    Cp = 348
+    clp = torch.zeros(B, Cp); clp[:, :Cn] = cl.detach().float()
+    cld = dev(clp)
+    dcl = torch.zeros(B, Cp, device="cuda"); probs = torch.empty(B, Cn, device="cuda")
+    cst = torch.zeros(2, dtype=torch.float64, device="cuda"); cam = torch.empty(B, dtype=torch.int32, device="cuda")
+    _lib.check(lib.skf_class_ce(ptr(cld), Cp, ptr(dev(lab)), B, Cn, 1.0 / B, ptr(dcl), Cp, ptr(cst), ptr(cam),
+                                ptr(probs), stream()))
+    assert abs(float(cst.cpu()[0]) / B - float(closs)) < 1e-5 * abs(float(closs))
+    assert rel_err(dcl[:, :Cn], cl.grad) < TOL_EXACT
+    assert rel_err(probs, torch.softmax(cl.detach(), -1)) < TOL_EXACT
+    assert torch.equal(cam.cpu().long(), cl.detach().argmax(-1))
+
+
+def test_adam_matches_oracle(lib):
+    n = 10007
+    g = torch.Generator().manual_seed(5)
+    w = {"a": torch.randn(n, generator=g)}
+    opt = O.AdamTF({"a": w["a"].double()}, 128)
+    w64 = {"a": w["a"].double().clone()}
+    pd = dev(w["a"]); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for it in range(4):
+        grad = torch.randn(n, generator=g) * 0.01
+        _lib.check(lib.skf_adam_step(ptr(pd), ptr(dev(grad)), ptr(m), ptr(v), n, ptr(step), 128, 5000, 0.9, 0.98, 1e-9,
+                                     1.0, stream()))
+        opt.apply(w64, {"a": grad.double()})
+        if it == 0:   # lr(0) == 0: weights bit-identical, moments moved
+            assert torch.equal(pd.cpu(), w["a"]) and float(m.abs().sum()) > 0
+    assert int(step.item()) == 4
+    # the update magnitude is ~lr*1; compare the accumulated displacement
+    assert rel_err(pd.cpu().double() - w["a"].double(), w64["a"] - w["a"].double()) < 1e-4
+    assert rel_err(m, opt.m["a"]) < 1e-5 and rel_err(v, opt.v["a"]) < 1e-5
+
+
+def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed):
+    g = torch.Generator().manual_seed(seed)
+    d = H * dh
+    q = torch.randn(B, Tq, d, generator=g).double().requires_grad_(True)
+    k = torch.randn(B, Tk, d, generator=g).double().requires_grad_(True)
+    v = torch.randn(B, Tk, d, generator=g).double().requires_grad_(True)
+    lens = torch.randint(max(1, Tk // 3), Tk + 1, (B,), generator=g)
+    pad = (torch.arange(Tk)[None, :] >= lens[:, None])
+    mask = None
+    if mode >= 1:
+        mask = pad[:, None, None, :].double()
+    if mode == 2:
+        mask = torch.maximum(mask, O.create_look_ahead_mask(Tq, torch.float64))
+    o, w = O.scaled_dot_product_attention(O.split_heads(q, H), O.split_heads(k, H), O.split_heads(v, H), mask)
+    o = o.permute(0, 2, 1, 3).reshape(B, Tq, d)
+    do = torch.randn(B, Tq, d, generator=g)
+    o.backward(do.double())
+    qd, kd, vd = dev(q.detach().float()), dev(k.detach().float()), dev(v.detach().float())
+    od = torch.empty(B, Tq, d, device="cuda"); lse = torch.empty(B, H, Tq, device="cuda")
+    padd = dev(pad.to(torch.uint8)) if mode >= 1 else None
+    _lib.check(lib.skf_attn_fwd(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(lse), ptr(padd), B, H, Tq, Tk, dh,
+                                mode, 0, 1, stream()))
+    e_o = rel_err(od, o)
+    dq = torch.empty_like(qd); dk = torch.empty_like(kd); dv = torch.empty_like(vd)
+    delta = torch.empty(B, H, Tq, device="cuda")
+    _lib.check(lib.skf_attn_bwd(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(dev(do)), d, ptr(lse), ptr(delta),
+                                ptr(dq), d, ptr(dk), d, ptr(dv), d, ptr(padd), B, H, Tq, Tk, dh, mode, 0, 1, stream()))
+    return e_o, rel_err(dq, q.grad), rel_err(dk, k.grad), rel_err(dv, v.grad)
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,mode", [(2, 4, 24, 24, 16, 1), (2, 4, 23, 23, 16, 2), (2, 4, 23, 24, 16, 0),
+                                               (3, 8, 200, 200, 32, 1), (3, 8, 199, 199, 32, 2),
+                                               (3, 8, 199, 200, 32, 0), (2, 8, 130, 131, 64, 2),
+                                               (2, 2, 70, 257, 64, 1)])
+def test_attention_simt(lib, B, H, Tq, Tk, dh, mode):
+    if mode == 2 and Tq != Tk:
+        Tk = Tq
+    errs = _attn_case(lib, B, H, Tq, Tk, dh, mode, 100 + Tq)
+    assert max(errs) < TOL_EXACT, errs
+
+
+MAJORS = [("fwd", False, True), ("dgrad", False, False), ("wgrad", True, True), ("tn", True, False)]
+
+
+def _gemm_case(M, N, K, a_mn, b_mn, backend, seed, **epi):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(K, N, generator=g)
+    if backend == 0:
+        A, Bm = to_tf32(A), to_tf32(Bm)      # operands are pre-rounded in the tensor-core pipeline
+    Ast = dev(A.T) if a_mn else dev(A)        # MN-major: stored [K, M]
+    Bst = dev(Bm) if b_mn else dev(Bm.T)      # K-major: stored [N, K]
+    sa = (1, M) if a_mn else (K, 1)
+    sb = (N, 1) if b_mn else (1, K)
+    Y = torch.zeros(M, N, device="cuda")
+    kw = {}
+    want = A.double() @ Bm.double()
+    if epi.get("bias"):
+        bias = torch.randn(N, generator=g); kw["bias"] = dev(bias); want = want + bias.double()
+    if epi.get("act") == 1:
+        kw["act"] = 1; want = torch.relu(want)
+    if epi.get("act") == 2:
+        kw["act"] = 2; want = torch.tanh(want)
+    if epi.get("mask"):
+        mk = torch.randn(M, N, generator=g); kw["mask"] = dev(mk); want = want * (mk > 0)
+    if epi.get("resid"):
+        rs = torch.randn(M, N, generator=g); kw["resid"] = dev(rs); want = want + rs.double()
+    if epi.get("split_k"):
+        kw["accumulate"] = 1; kw["split_k"] = epi["split_k"]
+    gemm(Ast, sa[0], sa[1], Bst, sb[0], sb[1], Y, N, M, N, K, backend, **kw)
+    torch.cuda.synchronize()
+    return rel_err(Y, want)
+
+
+@pytest.mark.parametrize("name,a_mn,b_mn", MAJORS)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (200, 100, 96), (333, 768, 256), (64, 1004, 128)])
+def test_gemm_simt(lib, name, a_mn, b_mn, M, N, K):
+    assert _gemm_case(M, N, K, a_mn, b_mn, 1, 7) < TOL_EXACT
+    assert _gemm_case(M, N, K, a_mn, b_mn, 1, 8, bias=True, act=1, resid=True) < TOL_EXACT
+    assert _gemm_case(M, N, K, a_mn, b_mn, 1, 9, mask=True) < TOL_EXACT
+    assert _gemm_case(M, N, K, a_mn, b_mn, 1, 10, split_k=3) < TOL_EXACT
+
+
+@pytest.mark.parametrize("name,a_mn,b_mn", MAJORS)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 64, 256), (256, 128, 64), (200, 100, 96), (1600, 768, 256),
+                                   (512, 1004, 128), (256, 256, 4000), (3000, 1024, 256)])
+def test_gemm_tcgen05(lib, name, a_mn, b_mn, M, N, K):
+    # operands are exactly TF32-representable, so the only error is fp32 accumulation order
+    assert _gemm_case(M, N, K, a_mn, b_mn, 0, 7) < TOL_EXACT
+    assert _gemm_case(M, N, K, a_mn, b_mn, 0, 8, bias=True, act=1, resid=True) < TOL_EXACT
+    assert _gemm_case(M, N, K, a_mn, b_mn, 0, 9, mask=True) < TOL_EXACT
+    assert _gemm_case(M, N, K, a_mn, b_mn, 0, 10, split_k=3) < TOL_EXACT
+
+
+def test_gemm_tcgen05_unrounded_operands_within_tolerance(lib):
+    """fp32 operands that are NOT pre-rounded get truncated by kind::tf32: still inside 1e-3."""
+    g = torch.Generator().manual_seed(12)
+    M, N, K = 512, 256, 256
+    A = torch.randn(M, K, generator=g); Bm = torch.randn(K, N, generator=g)
+    Y = torch.zeros(M, N, device="cuda")
+    gemm(dev(A), K, 1, dev(Bm), N, 1, Y, N, M, N, K, 0)
+    assert rel_err(Y, A.double() @ Bm.double()) < TOL_TF32
