@@ -118,10 +118,8 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t b_s = a_s + TC_A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ks++) {                     // UMMA_K = 8 for tf32
-          const uint64_t ad = A_MN ? make_smem_desc_sw128(a_s + ks * 1024, 4096, 1024)
-                                   : make_smem_desc_sw128(a_s + ks * 32, 0, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc_sw128(b_s + ks * 1024, 4096, 1024)
-                                   : make_smem_desc_sw128(b_s + ks * 32, 0, 1024);
+          const uint64_t ad = A_MN ? make_desc_mnmajor(a_s + ks * 1024, 4096) : make_desc_kmajor(a_s + ks * 32);
+          const uint64_t bd = B_MN ? make_desc_mnmajor(b_s + ks * 1024, 4096) : make_desc_kmajor(b_s + ks * 32);
           mma_tf32_ss(tmem_base, ad, bd, idesc, (i | ks) != 0 ? 1u : 0u);
         }
         tc_commit(empty_bar(s));     // slot reusable once these MMAs have read it
@@ -139,6 +137,7 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll 1
     for (int c = 0; c < BN / 32; c++) {
       uint32_t r[32];
+      __syncwarp();
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_ld_wait();
       const int nb = n0 + c * 32;
@@ -218,7 +217,7 @@ static EncodeTiledFn get_encode() {
 
 // 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart.
 int make_tmap_2d(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                 uint32_t box_inner, uint32_t box_outer) {
+                 uint32_t box_inner, uint32_t box_outer, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   SKF_REQUIRE(enc != nullptr, SKF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {inner, outer};
@@ -227,7 +226,8 @@ int make_tmap_2d(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t ou
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapDataType dt = g_tma_tf32_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = enc(out, dt, 2, const_cast<float*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SKF_REQUIRE(r == CUDA_SUCCESS, SKF_ERR_CUDA,
               "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r,
@@ -298,10 +298,10 @@ int gemm_tc(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t 
     if (tiles256 < 2 * 148) BN = 128;
   }
   CUtensorMap ta, tb;
-  if (!a_mn) SKF_TRY(make_tmap_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)(M == 1 ? K : sa_m), TC_BK, TC_BM));
-  else SKF_TRY(make_tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)sa_k, 32, TC_BK));
-  if (!b_mn) SKF_TRY(make_tmap_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, TC_BK, (uint32_t)BN));
-  else SKF_TRY(make_tmap_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, TC_BK));
+  if (!a_mn) SKF_TRY(make_tmap_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)(M == 1 ? K : sa_m), TC_BK, TC_BM, false));
+  else SKF_TRY(make_tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)sa_k, 32, TC_BK, true));
+  if (!b_mn) SKF_TRY(make_tmap_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, TC_BK, (uint32_t)BN, false));
+  else SKF_TRY(make_tmap_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, TC_BK, true));
   switch (BN) {
     case 64: return dispatch_major<64>(a_mn, b_mn, ta, tb, Y, ldy, M, N, K, k_chunk, split, e, st);
     case 128: return dispatch_major<128>(a_mn, b_mn, ta, tb, Y, ldy, M, N, K, k_chunk, split, e, st);

@@ -120,15 +120,27 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // ---- descriptors ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2=SW128)
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                         uint32_t sbo_bytes) {
+//  layout: 2 = SWIZZLE_128B (16-byte chunks; K-major operands),
+//          1 = SWIZZLE_128B_BASE32B (32-byte chunks; the ONLY layout for MN-major 32-bit operands:
+//              atom = 4 k-rows x 128 B, TMA side = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
+}
+// K-major fp32/tf32 tile: rows of 128 B (32 elements), 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr) {
+  return make_smem_desc(smem_addr, 16, 1024, 2);
+}
+// MN-major fp32/tf32 tile built from TMA boxes {32 mn, BK k}: 32-element MN chunks `mn_chunk_bytes`
+// apart (LBO), 4-k-row atoms 512 B apart (SBO).
+__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t smem_addr, uint32_t mn_chunk_bytes) {
+  return make_smem_desc(smem_addr, mn_chunk_bytes, 512, 1);
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor):
 //  [4,6) c=F32(1) | [7,10) a=TF32(2) | [10,13) b=TF32(2) | [15] a MN-major | [16] b MN-major |

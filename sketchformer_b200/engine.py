@@ -160,6 +160,10 @@ class Engine:
     def launches(self):
         return int(self.lib.skf_plan_launches(self._plan))
 
+    def set_step(self, n: int):
+        """optimizer.iterations (drives the Noam schedule and Adam's bias correction); restored on resume."""
+        self.tensor("step", dtype=torch.int64).fill_(int(n))
+
     def step_count(self):
         return int(self.tensor("step", dtype=torch.int64)[0].item())
 

@@ -1,10 +1,6 @@
 """Helpers shared by the GPU parity tests (all calls go through the C ABI of libskf.so)."""
-import ctypes as C
-
 import torch
 
-from sketchformer_b200 import _lib
-from sketchformer_b200._lib import SkfGemmEpilogue
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
@@ -16,22 +12,7 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return num / den if den > 0 else num
 
 
-def ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else None
-
-
-def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
-def gemm(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, backend, bias=None, resid=None, mask=None, act=0,
-         accumulate=0, round_tf32=0, split_k=0):
-    lib = _lib.load()
-    e = SkfGemmEpilogue(bias=ptr(bias), resid=ptr(resid), ld_resid=(resid.stride(0) if resid is not None else 0),
-                        mask=ptr(mask), ld_mask=(mask.stride(0) if mask is not None else 0), act=act,
-                        accumulate=accumulate, round_tf32=round_tf32, split_k=split_k)
-    _lib.check(lib.skf_gemm(ptr(A), sa_m, sa_k, ptr(B), sb_k, sb_n, ptr(Y), ldy, M, N, K, C.byref(e), backend,
-                            stream()), "skf_gemm")
+from sketchformer_b200.ops import gemm, ptr, stream  # noqa: F401,E402
 
 
 def to_tf32(x: torch.Tensor) -> torch.Tensor:
