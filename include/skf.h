@@ -63,6 +63,8 @@ typedef struct skf_cfg {
   int32_t world_size;         /* data-parallel ranks: gradients are scaled by 1/world   */
   int32_t gemm_backend;       /* 0 = tcgen05 TF32 tensor-core GEMMs, 1 = SIMT fp32 (debug)*/
   int32_t attn_backend;       /* 0 = default, 1 = SIMT fp32 (debug)                      */
+  int32_t gemm_precision;     /* tcgen05 GEMMs: 0 = TF32 everywhere, 1 = 3xTF32 (fp32-accurate) forward
+                                 + TF32 backward, 2 = 3xTF32 everywhere                     */
 } skf_cfg;
 
 const char* skf_last_error(void);
@@ -117,7 +119,13 @@ typedef struct skf_gemm_epilogue {
   int32_t accumulate; /* atomically add into Y (split-K weight gradients)                    */
   int32_t round_tf32; /* round the stored value to TF32 (operand of a later tensor-core GEMM)*/
   int32_t split_k;    /* >1: split the K range over this many CTAs (needs accumulate=1)       */
+  /* Both non-NULL (tcgen05 backend only): error-compensated "3xTF32" product
+   * A*B ~= Ah*Bh + Ah*Bl + Al*Bh with Xl = X - tf32(X) from skf_split_lo(); same strides as A / B. */
+  const float* a_lo;
+  const float* b_lo;
 } skf_gemm_epilogue;
+/* lo[i] = x[i] - tf32(x[i])  (exact in fp32): the low half of the 3xTF32 operand split.     */
+int skf_split_lo(const float* x, float* lo, int64_t n, void* stream);
 int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,
              int64_t sb_n, float* Y, int64_t ldy, int M, int N, int K,
              const skf_gemm_epilogue* epi, int backend, void* stream);

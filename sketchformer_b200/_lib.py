@@ -16,7 +16,7 @@ class SkfCfg(C.Structure):
                                          "blind_decoder_mask", "do_classification", "do_reconstruction",
                                          "warmup_steps")] + \
                [(n, C.c_float) for n in ("class_weight", "recon_weight", "adam_beta1", "adam_beta2", "adam_eps")] + \
-               [(n, C.c_int32) for n in ("world_size", "gemm_backend", "attn_backend")]
+               [(n, C.c_int32) for n in ("world_size", "gemm_backend", "attn_backend", "gemm_precision")]
 
 
 class SkfParamEntry(C.Structure):
@@ -26,7 +26,7 @@ class SkfParamEntry(C.Structure):
 class SkfGemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("resid", C.c_void_p), ("ld_resid", C.c_int64), ("mask", C.c_void_p),
                 ("ld_mask", C.c_int64), ("act", C.c_int32), ("accumulate", C.c_int32), ("round_tf32", C.c_int32),
-                ("split_k", C.c_int32)]
+                ("split_k", C.c_int32), ("a_lo", C.c_void_p), ("b_lo", C.c_void_p)]
 
 
 P, I, L, F, SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
@@ -44,6 +44,7 @@ SIGNATURES = {
     "skf_positional_encoding": (I, [P, I, I, P]),
     "skf_pad_flags": (I, [P, L, P, I, I, P]),
     "skf_gemm": (I, [P, L, L, P, L, L, P, L, I, I, I, C.POINTER(SkfGemmEpilogue), I, P]),
+    "skf_split_lo": (I, [P, P, L, P]),
     "skf_attn_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, P]),
     "skf_attn_bwd": (I, [P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, P]),
     "skf_add_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P]),

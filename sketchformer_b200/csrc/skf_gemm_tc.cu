@@ -33,12 +33,16 @@ struct TcCfg {
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-int g_tma_tf32_type = 0;  // 1: tensor maps use CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 (TMA converts)
+// 1 (default): tensor maps are typed CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, i.e. the TMA unit rounds fp32 -> tf32
+// (to nearest) on the way into shared memory; measured on B200 (tools/tf32_probe.py): unbiased, rel. error
+// 1.5e-5 vs 7.4e-4 (biased) when kind::tf32 truncates raw fp32 bits.  0: plain FLOAT32 maps.
+int g_tma_tf32_type = 1;
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-          float* __restrict__ Y, int64_t ldy, int M, int N, int K, int k_chunk,
+          const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
+          float* __restrict__ Y, int64_t ldy, int M, int N, int K, int k_chunk, int nseg,
           skf_gemm_epilogue e) {
   using C = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -60,10 +64,17 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int kb = blockIdx.z * k_chunk;
   const int ke = min(K, kb + k_chunk);
   const int nkb = (ke - kb + TC_BK - 1) / TC_BK;
+  // nseg == 3: error-compensated "3xTF32" product  A*B ~= Ah*Bh + Ah*Bl + Al*Bh  (fp32-accurate);
+  // the three passes accumulate into the same TMEM tile, so they are just a 3x longer K loop.
+  const int niter = nseg * nkb;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (nseg > 1) {
+      prefetch_tmap(&tmAlo);
+      prefetch_tmap(&tmBlo);
+    }
     for (int s = 0; s < C::STAGES; s++) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -82,34 +93,37 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < nkb; i++) {
+      for (int i = 0; i < niter; i++) {
         const int s = i % C::STAGES;
         const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
+        const int seg = i / nkb;
+        const CUtensorMap* ma = seg == 2 ? &tmAlo : &tmA;
+        const CUtensorMap* mb = seg == 1 ? &tmBlo : &tmB;
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_arrive_expect_tx(full_bar(s), C::STAGE);
         const uint32_t a_s = base + s * C::STAGE;
         const uint32_t b_s = a_s + TC_A_BYTES;
-        const int k0 = kb + i * TC_BK;
+        const int k0 = kb + (i - seg * nkb) * TC_BK;
         if (!A_MN) {
-          tma_load_2d(a_s, &tmA, full_bar(s), k0, m0);              // box {32 k, 128 m}
+          tma_load_2d(a_s, ma, full_bar(s), k0, m0);                // box {32 k, 128 m}
         } else {
 #pragma unroll
           for (int j = 0; j < TC_BM / 32; j++)                       // box {32 m, 32 k}
-            tma_load_2d(a_s + j * 4096, &tmA, full_bar(s), m0 + 32 * j, k0);
+            tma_load_2d(a_s + j * 4096, ma, full_bar(s), m0 + 32 * j, k0);
         }
         if (!B_MN) {
-          tma_load_2d(b_s, &tmB, full_bar(s), k0, n0);              // box {32 k, BN n}
+          tma_load_2d(b_s, mb, full_bar(s), k0, n0);                // box {32 k, BN n}
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 32; j++)                          // box {32 n, 32 k}
-            tma_load_2d(b_s + j * 4096, &tmB, full_bar(s), n0 + 32 * j, k0);
+            tma_load_2d(b_s + j * 4096, mb, full_bar(s), n0 + 32 * j, k0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int i = 0; i < nkb; i++) {
+      for (int i = 0; i < niter; i++) {
         const int s = i % C::STAGES;
         const uint32_t ph = (uint32_t)(i / C::STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
@@ -251,7 +265,7 @@ int gemm_tc_supported(const float* A, int64_t sa_m, int64_t sa_k, const float* B
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* Y, int64_t ldy, int M, int N, int K,
+static int launch_tc(const CUtensorMap* tm, int nseg, float* Y, int64_t ldy, int M, int N, int K,
                      int k_chunk, int split, const skf_gemm_epilogue& e, cudaStream_t st) {
   using C = TcCfg<BN>;
   static bool attr_done = false;
@@ -260,19 +274,19 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, float* Y, int
     attr_done = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), split);
-  gemm_tc_k<BN, A_MN, B_MN><<<grid, 192, C::SMEM, st>>>(ta, tb, Y, ldy, M, N, K, k_chunk, e);
+  gemm_tc_k<BN, A_MN, B_MN><<<grid, 192, C::SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], Y, ldy, M, N, K, k_chunk, nseg, e);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
 
 template <int BN>
-static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, float* Y,
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tm, int nseg, float* Y,
                           int64_t ldy, int M, int N, int K, int k_chunk, int split, const skf_gemm_epilogue& e,
                           cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false>(ta, tb, Y, ldy, M, N, K, k_chunk, split, e, st);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true>(ta, tb, Y, ldy, M, N, K, k_chunk, split, e, st);
-  if (a_mn && !b_mn) return launch_tc<BN, true, false>(ta, tb, Y, ldy, M, N, K, k_chunk, split, e, st);
-  return launch_tc<BN, true, true>(ta, tb, Y, ldy, M, N, K, k_chunk, split, e, st);
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false>(tm, nseg, Y, ldy, M, N, K, k_chunk, split, e, st);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true>(tm, nseg, Y, ldy, M, N, K, k_chunk, split, e, st);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false>(tm, nseg, Y, ldy, M, N, K, k_chunk, split, e, st);
+  return launch_tc<BN, true, true>(tm, nseg, Y, ldy, M, N, K, k_chunk, split, e, st);
 }
 
 int gemm_tc(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n,
@@ -297,15 +311,23 @@ int gemm_tc(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t 
     long tiles256 = (long)cdiv(M, TC_BM) * cdiv(N, 256) * split;
     if (tiles256 < 2 * 148) BN = 128;
   }
-  CUtensorMap ta, tb;
-  if (!a_mn) SKF_TRY(make_tmap_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)(M == 1 ? K : sa_m), TC_BK, TC_BM, false));
-  else SKF_TRY(make_tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)sa_k, 32, TC_BK, true));
-  if (!b_mn) SKF_TRY(make_tmap_2d(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, TC_BK, (uint32_t)BN, false));
-  else SKF_TRY(make_tmap_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, TC_BK, true));
+  const int nseg = (e.a_lo && e.b_lo) ? 3 : 1;
+  SKF_REQUIRE(nseg == 1 || (((reinterpret_cast<uintptr_t>(e.a_lo) | reinterpret_cast<uintptr_t>(e.b_lo)) & 15) == 0),
+              SKF_ERR_BAD_ALIGN, "gemm_tc: a_lo/b_lo must be 16-byte aligned");
+  CUtensorMap tm[4];  // A, B, A_lo, B_lo  (the lo tensors share the strides of A / B)
+  for (int i = 0; i < (nseg == 3 ? 2 : 1); i++) {
+    const float* a = i == 0 ? A : e.a_lo;
+    const float* b = i == 0 ? B : e.b_lo;
+    if (!a_mn) SKF_TRY(make_tmap_2d(&tm[2 * i], a, (uint64_t)K, (uint64_t)M, (uint64_t)(M == 1 ? K : sa_m), TC_BK, TC_BM, false));
+    else SKF_TRY(make_tmap_2d(&tm[2 * i], a, (uint64_t)M, (uint64_t)K, (uint64_t)sa_k, 32, TC_BK, true));
+    if (!b_mn) SKF_TRY(make_tmap_2d(&tm[2 * i + 1], b, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, TC_BK, (uint32_t)BN, false));
+    else SKF_TRY(make_tmap_2d(&tm[2 * i + 1], b, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, TC_BK, true));
+  }
+  if (nseg == 1) { tm[2] = tm[0]; tm[3] = tm[1]; }
   switch (BN) {
-    case 64: return dispatch_major<64>(a_mn, b_mn, ta, tb, Y, ldy, M, N, K, k_chunk, split, e, st);
-    case 128: return dispatch_major<128>(a_mn, b_mn, ta, tb, Y, ldy, M, N, K, k_chunk, split, e, st);
-    default: return dispatch_major<256>(a_mn, b_mn, ta, tb, Y, ldy, M, N, K, k_chunk, split, e, st);
+    case 64: return dispatch_major<64>(a_mn, b_mn, tm, nseg, Y, ldy, M, N, K, k_chunk, split, e, st);
+    case 128: return dispatch_major<128>(a_mn, b_mn, tm, nseg, Y, ldy, M, N, K, k_chunk, split, e, st);
+    default: return dispatch_major<256>(a_mn, b_mn, tm, nseg, Y, ldy, M, N, K, k_chunk, split, e, st);
   }
 }
 

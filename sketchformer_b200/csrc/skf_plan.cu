@@ -3,6 +3,7 @@
 // entry points (encode_from_seq / predict_class, sketchformer.py:162-168, 223-228).
 // Host code only decides WHICH kernel runs on WHICH buffer; every byte of arithmetic happens in
 // the CUDA kernels of this library.
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -136,7 +137,13 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
   W.add("stats_step", 8 * sizeof(double));
   W.add("stats_run", 16 * sizeof(double));
   W.add("pe", (size_t)c.T * d * F);
-  W.add("wc", (size_t)PL.total * F);  // TF32-rounded compute copy of the weights
+  W.add("wc", (size_t)PL.total * F);  // TF32-rounded compute copy of the weights (tma_tf32=0 only)
+  W.add("wlo", (size_t)PL.total * F); // w - tf32(w): low halves of the weights for the 3xTF32 GEMMs
+  {
+    size_t wmax = std::max<size_t>(std::max<size_t>(f, 3 * d), std::max<size_t>((size_t)c.V, (size_t)c.u));
+    W.add("lo.a", Me * wmax * F);     // low half of the activation operand A of the current GEMM
+    W.add("lo.b", Me * wmax * F);     // low half of operand B (weight gradients: both operands are activations)
+  }
   W.add("enc_pad", Me);
   W.add("dec_pad", Md);
   W.add("enc.x0", Me * d * F);
@@ -221,6 +228,7 @@ struct skf_plan {
   int64_t launches = 0;
   bool round_ops = false;  // round GEMM operands to TF32 when they are produced
   const float* wc = nullptr;
+  const float* wlo = nullptr;
 
   float* wsf(const std::string& n) const { return reinterpret_cast<float*>(ws + W.t.at(n).off); }
   template <class T>
@@ -231,6 +239,34 @@ struct skf_plan {
 };
 
 namespace skf {
+
+// lo = x - tf32(x).  rna: the TMA (TFLOAT32 maps) rounds to nearest; otherwise kind::tf32 truncates.
+__global__ void split_lo_k(const float* __restrict__ x, float* __restrict__ lo, int64_t n, int rna) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(x + i), o;
+    if (rna) {
+      o.x = v.x - round_tf32(v.x); o.y = v.y - round_tf32(v.y);
+      o.z = v.z - round_tf32(v.z); o.w = v.w - round_tf32(v.w);
+    } else {
+      o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+      o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+      o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+      o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    }
+    *reinterpret_cast<float4*>(lo + i) = o;
+  } else {
+    for (; i < n; i++) {
+      float v = x[i];
+      lo[i] = rna ? v - round_tf32(v) : v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    }
+  }
+}
+int split_lo(const float* x, float* lo, int64_t n, cudaStream_t st) {
+  split_lo_k<<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(x, lo, n, g_tma_tf32_type);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
 
 __global__ void round_copy_k(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,10 +297,21 @@ __global__ void stats_finalize_k(const double* __restrict__ st, double* __restri
 struct Gemm {
   const skf_plan* P;
   cudaStream_t st;
+  // a_elems / b_elems: number of floats of a dense activation operand (its low half is computed here);
+  // 0 means the operand is a weight (its low half lives in the "wlo" arena at the same offset).
   int run(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
-          int64_t ldy, int M, int N, int K, skf_gemm_epilogue e) const {
+          int64_t ldy, int M, int N, int K, skf_gemm_epilogue e, bool x3 = false, int64_t a_elems = 0,
+          int64_t b_elems = 0) const {
     bool tc = P->c.gemm_backend == 0 && gemm_tc_supported(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e);
     if (!P->round_ops) e.round_tf32 = 0;
+    if (tc && x3) {
+      float* la = P->wsf("lo.a");
+      float* lb = P->wsf("lo.b");
+      if (a_elems > 0) { SKF_TRY(split_lo(A, la, a_elems, st)); e.a_lo = la; }
+      else e.a_lo = P->wlo + (A - P->wc);
+      if (b_elems > 0) { SKF_TRY(split_lo(B, lb, b_elems, st)); e.b_lo = lb; }
+      else e.b_lo = P->wlo + (B - P->wc);
+    }
     if (e.accumulate) {
       // split-K so that the grid fills the 148 SMs about twice
       long tiles = tc ? (long)cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256))
@@ -282,7 +329,7 @@ struct Gemm {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
     e.bias = bias; e.act = act; e.resid = resid; e.ld_resid = N; e.round_tf32 = rnd;
-    return run(X, K, 1, W, N, 1, Y, N, M, N, K, e);
+    return run(X, K, 1, W, N, 1, Y, N, M, N, K, e, P->c.gemm_precision >= 1, (int64_t)M * K, 0);
   }
   // dX[M,K] = dY[M,N] * W[K,N]^T  (* (mask>0)) (+ resid)
   int dgrad(const float* dY, const float* W, float* dX, int M, int N, int K, const float* mask,
@@ -290,14 +337,14 @@ struct Gemm {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
     e.mask = mask; e.ld_mask = K; e.resid = resid; e.ld_resid = K; e.round_tf32 = rnd;
-    return run(dY, N, 1, W, 1, N, dX, K, M, K, N, e);
+    return run(dY, N, 1, W, 1, N, dX, K, M, K, N, e, P->c.gemm_precision >= 2, (int64_t)M * N, 0);
   }
   // dW[K,N] += X[M,K]^T * dY[M,N] ; db[N] += colsum(dY)
   int wgrad(const float* X, const float* dY, float* dW, float* db, int M, int N, int K) const {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
     e.accumulate = 1;
-    SKF_TRY(run(X, 1, K, dY, N, 1, dW, N, K, N, M, e));
+    SKF_TRY(run(X, 1, K, dY, N, 1, dW, N, K, N, M, e, P->c.gemm_precision >= 2, (int64_t)M * K, (int64_t)M * N));
     if (db) SKF_TRY(skf_colsum(dY, N, db, M, N, st));
     return SKF_OK;
   }
@@ -321,6 +368,11 @@ static int attn_bwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
 
 // ---- forward -----------------------------------------------------------------------------------
 static int refresh_compute_weights(skf_plan* P, cudaStream_t st) {
+  if (P->c.gemm_backend == 0 && P->c.gemm_precision >= 1) {
+    float* wl = P->wsf("wlo");
+    SKF_TRY(split_lo(P->params, wl, P->PL.total, st));
+    P->wlo = wl;
+  }
   if (!P->round_ops) {
     P->wc = P->params;
     return SKF_OK;
@@ -571,6 +623,11 @@ static int backward(skf_plan* P, const int64_t* tok, cudaStream_t st) {
 // C ABI
 // =============================================================================================
 extern "C" {
+
+int skf_split_lo(const float* x, float* lo, int64_t n, void* stream) {
+  SKF_REQUIRE(x && lo && n > 0, SKF_ERR_BAD_ARG, "split_lo: bad argument");
+  return skf::split_lo(x, lo, n, as_stream(stream));
+}
 
 int skf_set_option(const char* name, int value) {
   if (name && strcmp(name, "tma_tf32") == 0) {

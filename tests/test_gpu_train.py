@@ -23,12 +23,13 @@ from tests.gpu_util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def build(cfg_kw, B, backend, **flags):
+def build(cfg_kw, B, backend, precision=1, **flags):
     ocfg = O.OracleConfig(**cfg_kw, **flags)
     c = make_cfg(B, ocfg.max_seq_len, ocfg.d_model, ocfg.dff, ocfg.num_heads, ocfg.num_layers, ocfg.vocab_size,
                  ocfg.n_classes, ocfg.lowerdim, blind_decoder_mask=ocfg.blind_decoder_mask,
                  do_classification=ocfg.do_classification, do_reconstruction=ocfg.do_reconstruction,
-                 class_weight=ocfg.class_weight, recon_weight=ocfg.recon_weight, gemm_backend=backend)
+                 class_weight=ocfg.class_weight, recon_weight=ocfg.recon_weight, gemm_backend=backend,
+                 gemm_precision=precision)
     return ocfg, Engine(c)
 
 

@@ -22,14 +22,15 @@ if __name__ == "__main__":
     ap.add_argument("--cfg", default="tiny")
     ap.add_argument("--backend", type=int, default=1)
     ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--tma-tf32", type=int, default=0)
+    ap.add_argument("--tma-tf32", type=int, default=1)
+    ap.add_argument("--precision", type=int, default=1)
+    ap.add_argument("--quiet", action="store_true")
     ap.add_argument("--all", action="store_true")
     a = ap.parse_args()
     kw, B = {"tiny": (TINY, 4), "cfg1": (CFG1, 8), "cfg2": (CFG2, 16)}[a.cfg]
     B = a.batch or B
-    if a.tma_tf32:
-        _lib.check(_lib.load().skf_set_option(b"tma_tf32", 1))
-    ocfg, eng = build(kw, B, a.backend)
+    _lib.check(_lib.load().skf_set_option(b"tma_tf32", a.tma_tf32))
+    ocfg, eng = build(kw, B, a.backend, a.precision)
     x, y = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 1234, vocab=ocfg.vocab_size)
     xt, yt = torch.from_numpy(x), torch.from_numpy(y)
     p = O.init_params(ocfg, 0, torch.float64)
@@ -47,7 +48,7 @@ if __name__ == "__main__":
     for k, ref in tape.items():
         e = rel_err(acts[k], ref)
         worst = max(worst, e)
-        if a.all or e > 1e-4:
+        if a.all or (e > 1e-4 and not a.quiet):
             print(f"  act  {k:28s} {e:.3e}")
     print(f"worst activation rel err {worst:.3e}")
     got = eng.export_grads(grads)
@@ -57,6 +58,9 @@ if __name__ == "__main__":
         num = float((got[k].double() - ref.double()).norm())
         e = num / max(float(ref.norm()), 1e-4 * G)
         worst = max(worst, e)
-        if a.all or e > 1e-4:
+        if a.all or (e > 1e-4 and not a.quiet):
             print(f"  grad {k:28s} {e:.3e}   |ref|={float(ref.norm()):.3e}")
+    top = sorted(((float((got[k].double() - grads[k].double()).norm()) / max(float(grads[k].norm()), 1e-4 * G), k)
+                  for k in grads), reverse=True)[:6]
+    print("top grad errs:", [(k, f"{e:.2e}") for e, k in top])
     print(f"worst gradient rel err {worst:.3e}  (global grad norm {G:.3e})")
