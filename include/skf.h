@@ -134,7 +134,9 @@ int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
  * Q rows are b*Tq+i, K/V rows b*Tk+j; head h occupies columns [h*dh,(h+1)*dh) of each.
  * mask_mode: 0 none, 1 key padding (key_pad[b,j]!=0 masked), 2 causal | key padding.
  * Masked logits get -1e9 added after the 1/sqrt(dh) scaling exactly as the reference does.
- * lse[b,h,i] = logsumexp of the masked scaled logits (saved for backward).                 */
+ * lse[b,h,i] = logsumexp of the masked scaled logits (saved for backward).
+ * backend: 0 = tcgen05 kind::tf32 (head dim 32, Tq,Tk <= 224), 2 = tcgen05 with the 3xTF32 split
+ * (fp32-accurate, forward only), 1 = SIMT fp32 (any supported shape).                           */
 int skf_attn_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V,
                  int64_t ldv, float* O, int64_t ldo, float* lse, const uint8_t* key_pad, int B,
                  int H, int Tq, int Tk, int dh, int mask_mode, int round_tf32, int backend,

@@ -230,15 +230,21 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart.
+int make_tmap_2d_typed(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                       uint32_t box_inner, uint32_t box_outer, bool mn_major, bool tf32_convert);
 int make_tmap_2d(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
                  uint32_t box_inner, uint32_t box_outer, bool mn_major) {
+  return make_tmap_2d_typed(out, ptr, inner, outer, ld, box_inner, box_outer, mn_major, g_tma_tf32_type != 0);
+}
+int make_tmap_2d_typed(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                       uint32_t box_inner, uint32_t box_outer, bool mn_major, bool tf32_convert) {
   EncodeTiledFn enc = get_encode();
   SKF_REQUIRE(enc != nullptr, SKF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {inner, outer};
   cuuint64_t gstr[1] = {ld * sizeof(float)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapDataType dt = g_tma_tf32_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUtensorMapDataType dt = tf32_convert ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = enc(out, dt, 2, const_cast<float*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

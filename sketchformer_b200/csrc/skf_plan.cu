@@ -18,6 +18,12 @@ int attn_bwd_simt(const float*, int64_t, const float*, int64_t, const float*, in
                   const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
                   const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
 extern int g_tma_tf32_type;
+int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
+int attn_fwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
+                const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
+int attn_bwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
+                const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
+                const uint8_t*, int, int, int, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // parameter arena
@@ -354,6 +360,9 @@ static int attn_fwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
                         const float* V, int64_t ldv, float* O, int64_t ldo, float* lse, const uint8_t* pad,
                         int Tq, int Tk, int mode, cudaStream_t st) {
   const skf_cfg& c = P->c;
+  if (c.attn_backend == 0 && attn_tc_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
+    return attn_fwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode,
+                       c.gemm_precision >= 1 ? 1 : 0, st);
   return attn_fwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode,
                        P->round_ops ? 1 : 0, st);
 }
@@ -362,6 +371,9 @@ static int attn_bwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
                         const float* lse, float* delta, float* dQ, int64_t lddq, float* dK, int64_t lddk,
                         float* dV, int64_t lddv, const uint8_t* pad, int Tq, int Tk, int mode, cudaStream_t st) {
   const skf_cfg& c = P->c;
+  if (c.attn_backend == 0 && c.gemm_precision < 2 && attn_tc_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
+    return attn_bwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad, c.B,
+                       c.H, Tq, Tk, c.d / c.H, mode, st);
   return attn_bwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad,
                        c.B, c.H, Tq, Tk, c.d / c.H, mode, P->round_ops ? 1 : 0, st);
 }
@@ -776,7 +788,10 @@ int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
 int skf_attn_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, float* O,
                  int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh,
                  int mask_mode, int round_tf32, int backend, void* stream) {
-  (void)backend;
+  // backend: 0 = tcgen05 TF32, 2 = tcgen05 3xTF32 (fp32-accurate), 1 = SIMT fp32
+  if (backend == 0 || backend == 2)
+    return attn_fwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, backend == 2,
+                       as_stream(stream));
   return attn_fwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, round_tf32,
                        as_stream(stream));
 }
@@ -785,7 +800,9 @@ int skf_attn_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
                  const float* O, int64_t ldo, const float* dO, int64_t lddo, const float* lse, float* delta,
                  float* dQ, int64_t lddq, float* dK, int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad,
                  int B, int H, int Tq, int Tk, int dh, int mask_mode, int round_tf32, int backend, void* stream) {
-  (void)backend;
+  if (backend == 0)
+    return attn_bwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B,
+                       H, Tq, Tk, dh, mask_mode, as_stream(stream));
   return attn_bwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad,
                        B, H, Tq, Tk, dh, mask_mode, round_tf32, as_stream(stream));
 }

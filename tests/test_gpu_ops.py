@@ -218,7 +218,7 @@ def test_adam_matches_oracle(lib):
     assert rel_err(m, opt.m["a"]) < 1e-5 and rel_err(v, opt.v["a"]) < 1e-5
 
 
-def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed):
+def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed, fwd_backend=1, bwd_backend=1):
     g = torch.Generator().manual_seed(seed)
     d = H * dh
     q = torch.randn(B, Tq, d, generator=g).double().requires_grad_(True)
@@ -239,13 +239,16 @@ def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed):
     od = torch.empty(B, Tq, d, device="cuda"); lse = torch.empty(B, H, Tq, device="cuda")
     padd = dev(pad.to(torch.uint8)) if mode >= 1 else None
     _lib.check(lib.skf_attn_fwd(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(lse), ptr(padd), B, H, Tq, Tk, dh,
-                                mode, 0, 1, stream()))
+                                mode, 0, fwd_backend, stream()))
     e_o = rel_err(od, o)
+    e_lse = rel_err(lse, torch.logsumexp((O.split_heads(q, H) @ O.split_heads(k, H).transpose(-1, -2)).detach() / dh ** 0.5
+                                         + (mask * -1e9 if mask is not None else 0), -1))
+    e_o = max(e_o, e_lse)
     dq = torch.empty_like(qd); dk = torch.empty_like(kd); dv = torch.empty_like(vd)
     delta = torch.empty(B, H, Tq, device="cuda")
     do_d = dev(do)
     _lib.check(lib.skf_attn_bwd(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(do_d), d, ptr(lse), ptr(delta),
-                                ptr(dq), d, ptr(dk), d, ptr(dv), d, ptr(padd), B, H, Tq, Tk, dh, mode, 0, 1, stream()))
+                                ptr(dq), d, ptr(dk), d, ptr(dv), d, ptr(padd), B, H, Tq, Tk, dh, mode, 0, bwd_backend, stream()))
     return e_o, rel_err(dq, q.grad), rel_err(dk, k.grad), rel_err(dv, v.grad)
 
 
@@ -258,6 +261,21 @@ def test_attention_simt(lib, B, H, Tq, Tk, dh, mode):
         Tk = Tq
     errs = _attn_case(lib, B, H, Tq, Tk, dh, mode, 100 + Tq)
     assert max(errs) < TOL_EXACT, errs
+
+
+TC_ATTN = [(3, 8, 200, 200, 32, 1), (3, 8, 199, 199, 32, 2), (3, 8, 199, 200, 32, 0), (2, 4, 64, 64, 32, 1),
+           (2, 2, 130, 100, 32, 0), (2, 4, 23, 24, 32, 0), (1, 2, 224, 224, 32, 2)]
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,mode", TC_ATTN)
+def test_attention_tcgen05(lib, B, H, Tq, Tk, dh, mode):
+    # forward 3xTF32 (fp32-accurate) + backward single-pass TF32
+    e_o, e_q, e_k, e_v = _attn_case(lib, B, H, Tq, Tk, dh, mode, 200 + Tq, fwd_backend=2, bwd_backend=0)
+    assert e_o < TOL_EXACT, e_o
+    assert max(e_q, e_k, e_v) < TOL_TF32, (e_q, e_k, e_v)
+    # forward single-pass TF32
+    e_o, _, _, _ = _attn_case(lib, B, H, Tq, Tk, dh, mode, 300 + Tq, fwd_backend=0, bwd_backend=1)
+    assert e_o < TOL_TF32, e_o
 
 
 MAJORS = [("fwd", False, True), ("dgrad", False, False), ("wgrad", True, True), ("tn", True, False)]
@@ -311,6 +329,23 @@ def test_gemm_tcgen05(lib, name, a_mn, b_mn, M, N, K):
     assert _gemm_case(M, N, K, a_mn, b_mn, 0, 8, bias=True, act=1, resid=True) < TOL_EXACT
     assert _gemm_case(M, N, K, a_mn, b_mn, 0, 9, mask=True) < TOL_EXACT
     assert _gemm_case(M, N, K, a_mn, b_mn, 0, 10, split_k=3) < TOL_EXACT
+
+
+def test_gemm_tcgen05_3xtf32_is_fp32_accurate(lib):
+    from sketchformer_b200.ops import split_lo
+    g = torch.Generator().manual_seed(13)
+    for (M, N, K, a_mn, b_mn) in ((512, 256, 256, False, True), (300, 1024, 256, False, False), (256, 512, 1000, True, True)):
+        A = torch.randn(M, K, generator=g); Bm = torch.randn(K, N, generator=g)
+        Ast = dev(A.T) if a_mn else dev(A)
+        Bst = dev(Bm) if b_mn else dev(Bm.T)
+        sa = (1, M) if a_mn else (K, 1)
+        sb = (N, 1) if b_mn else (1, K)
+        Y = torch.zeros(M, N, device="cuda")
+        gemm(Ast, sa[0], sa[1], Bst, sb[0], sb[1], Y, N, M, N, K, 0, a_lo=split_lo(Ast), b_lo=split_lo(Bst))
+        e3 = rel_err(Y, A.double() @ Bm.double())
+        gemm(Ast, sa[0], sa[1], Bst, sb[0], sb[1], Y, N, M, N, K, 0)
+        e1 = rel_err(Y, A.double() @ Bm.double())
+        assert e3 < 5e-6 and e1 < TOL_TF32 and e3 < e1 / 20, (e1, e3)
 
 
 def test_gemm_tcgen05_unrounded_operands_within_tolerance(lib):
