@@ -188,15 +188,19 @@ def main():
         if e2e:
             stats_host.copy_(eng.tensor("stats_run", dtype=torch.float64), non_blocking=True)
 
+    host_ms = [0.0]
+
     def timed(n, e2e=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(n):
             step(i, e2e)
         e1.record()
+        host_ms[0] = (time.perf_counter() - t0) * 1e3      # host submission time (diagnostic only)
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
@@ -212,6 +216,7 @@ def main():
     l0 = eng.launches()
     ms = timed(args.steps)
     launches = eng.launches() - l0
+    host_submit_ms = host_ms[0] / args.steps
     for i in range(2):
         step(i, True)
     ms_e2e = timed(args.steps, e2e=True)
@@ -239,7 +244,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "sketches/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": BATCH * c["max_seq_len"] * 8 + BATCH * 8, "d2h_bytes_per_step": 128,
                         "last_total_loss": loss_after},
-                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof}
+                "gpu_launches": launches, "host_submit_ms_per_step": host_submit_ms, "clocks": sampler.summary(), "roofline": roof}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_steps(2, 1, budget_s=25.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "sketches/s", "cores": r["cores"], "kind": "port",

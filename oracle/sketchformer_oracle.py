@@ -249,9 +249,38 @@ def mha(p, name, v, k, q, mask, H, tape=None):
     return dense(p, name + ".wo", concat), w
 
 
+_RELU_PATTERN = None   # test hook, see relu_pattern()
+
+
+class relu_pattern:
+    """Context manager for the parity tests: inside it, ffn() uses the given 0/1 activation pattern
+    (name -> bool tensor shaped like the hidden layer) instead of recomputing `pre > 0`.  ReLU is not
+    differentiable at 0: a forward perturbation eps flips a fraction ~eps of the units and moves the
+    gradient by ~sqrt(eps) in L2, so gradients are compared at the SAME activation pattern and the
+    pattern itself is compared separately (tests/test_gpu_train.py)."""
+
+    def __init__(self, pattern=None, record=None):
+        self.pattern = dict(pattern or {})
+        self.pattern["__record__"] = record      # dict filled with the oracle's own pattern, or None
+
+    def __enter__(self):
+        global _RELU_PATTERN
+        self.prev, _RELU_PATTERN = _RELU_PATTERN, self.pattern
+        return self
+
+    def __exit__(self, *exc):
+        global _RELU_PATTERN
+        _RELU_PATTERN = self.prev
+
+
 def ffn(p, name, x):
     """point_wise_feed_forward_network transformer.py:194-198."""
-    return dense(p, name + ".w2", torch.relu(dense(p, name + ".w1", x)))
+    pre = dense(p, name + ".w1", x)
+    pat = _RELU_PATTERN.get(name) if _RELU_PATTERN else None
+    if _RELU_PATTERN and _RELU_PATTERN.get("__record__") is not None:
+        _RELU_PATTERN["__record__"][name] = (pre > 0).detach()
+    h = torch.relu(pre) if pat is None else pre * pat.to(pre.dtype)
+    return dense(p, name + ".w2", h)
 
 
 def embed_input(p, prefix, x, cfg, dtype):

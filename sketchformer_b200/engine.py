@@ -17,7 +17,7 @@ from ._lib import SkfCfg, SkfParamEntry, check
 
 def make_cfg(B, T, d, f, H, L, V, n_classes, lowerdim, *, continuous=False, blind_decoder_mask=True,
              do_classification=True, do_reconstruction=True, class_weight=1.0, recon_weight=1.0,
-             world_size=1, gemm_backend=0, attn_backend=0, gemm_precision=1) -> SkfCfg:
+             world_size=1, gemm_backend=0, attn_backend=0, gemm_precision=2) -> SkfCfg:
     return SkfCfg(B=B, T=T, d=d, f=f, H=H, L=L, V=V, C=n_classes, u=lowerdim, continuous=int(continuous),
                   blind_decoder_mask=int(blind_decoder_mask), do_classification=int(do_classification),
                   do_reconstruction=int(do_reconstruction), warmup_steps=5000, class_weight=class_weight,
@@ -29,7 +29,7 @@ def make_cfg(B, T, d, f, H, L, V, n_classes, lowerdim, *, continuous=False, blin
 class Engine:
     METRIC_NAMES = ("recon_loss", "recon_acc", "class_loss", "class_acc", "total_loss")
 
-    def __init__(self, cfg: SkfCfg, device="cuda:0", training=True):
+    def __init__(self, cfg: SkfCfg, device="cuda:0", training=True, share_from=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.SkfError("no CUDA device: the Sketchformer engine has no CPU path")
@@ -49,10 +49,16 @@ class Engine:
         self.table = {ent[i].name.decode(): (int(ent[i].offset), int(ent[i].rows), int(ent[i].cols))
                       for i in range(cnt)}
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.params = torch.zeros(n, **f32)
-        self.grads = torch.zeros(n, **f32) if training else None
-        self.adam_m = torch.zeros(n, **f32) if training else None
-        self.adam_v = torch.zeros(n, **f32) if training else None
+        if share_from is not None:
+            # another plan (other batch size) over the SAME parameter / optimizer arenas
+            assert share_from.table == self.table, "shared arenas need an identical parameter layout"
+            self.params, self.grads = share_from.params, share_from.grads
+            self.adam_m, self.adam_v = share_from.adam_m, share_from.adam_v
+        else:
+            self.params = torch.zeros(n, **f32)
+            self.grads = torch.zeros(n, **f32) if training else None
+            self.adam_m = torch.zeros(n, **f32) if training else None
+            self.adam_v = torch.zeros(n, **f32) if training else None
         wsb = int(self.lib.skf_workspace_bytes(C.byref(cfg)))
         self.workspace = torch.empty(wsb, dtype=torch.uint8, device=self.device)
         self._plan = C.c_void_p()
@@ -167,6 +173,10 @@ class Engine:
 
     def step_count(self):
         return int(self.tensor("step", dtype=torch.int64)[0].item())
+
+    def reset_metrics(self):
+        """MetricManager.reset (builders/keras_metrics.py): zero the running sums."""
+        self.tensor("stats_run", dtype=torch.float64).zero_()
 
     def stats(self):
         """Raw running sums (device -> host read of 16 doubles)."""

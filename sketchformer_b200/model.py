@@ -1,0 +1,230 @@
+"""Host-side mirror of the reference's model plugin for the hot path.
+
+`Transformer` presents the surface of models/sketchformer.py:17-365 + core/models.py:18-136 that
+train.py / evaluate-metrics.py / the metrics and experiments drive: same registry
+name, hparam names/defaults, constructor, `train_on_batch`, `predict_class`, `encode_from_seq`,
+`predict`, `predict_from_embedding`.  Every byte of arithmetic runs in libskf.so (include/skf.h);
+this class only stages host batches into HBM and reads results back.  There is no CPU path: without
+a B200 and the built library the constructor raises.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .engine import Engine, make_cfg
+from .hparams import HParams, combine_hparams_into_one
+from .init import init_params
+
+
+class Transformer:
+    name = "sketch-transformer-tf2"                                   # models/sketchformer.py:18
+    quick_metrics = ["recon_loss", "recon_acc", "class_loss", "class_acc", "total_loss"]
+    slow_metrics = ["sketch-reconstruction", "val-clas-acc", "tsne", "tsne-predicted"]
+
+    # ---- hparams (names, types and defaults are the reference's) ---------------------------
+    @classmethod
+    def base_default_hparams(cls):
+        """core/models.py:18-31"""
+        return HParams(batch_size=128, num_epochs=10, save_every=1., safety_save=.5, autograph=True,
+                       log_every=100, notify_every=1000, slack_config="token.secret", goal="No description")
+
+    @classmethod
+    def specific_default_hparams(cls):
+        """models/sketchformer.py:24-53"""
+        return HParams(num_layers=4, d_model=128, dff=512, num_heads=8, dropout_rate=0.1,
+                       lowerdim=256, attn_version=1,
+                       do_classification=True, class_weight=1.0, class_buffer_layers=0, class_dropout=0.1,
+                       do_reconstruction=True, recon_weight=1.0, blind_decoder_mask=True,
+                       is_training=True, optimizer="Adam", lr=0.01, lr_scheduler="WarmupDecay",
+                       warmup_steps=10000)
+
+    @classmethod
+    def default_hparams(cls):
+        """core/models.py:109-114"""
+        return combine_hparams_into_one(cls.specific_default_hparams(), cls.base_default_hparams())
+
+    @classmethod
+    def get_config_filepath(cls, output_dir, exp_id):
+        """core/models.py:116-119"""
+        return os.path.join(output_dir, "{}-{}".format(cls.name, exp_id), "config.json")
+
+    @classmethod
+    def parse_hparams(cls, base, specific):
+        """core/models.py:121-136"""
+        hps = cls.default_hparams()
+        if base is not None:
+            hps = hps.parse(base)
+        if specific is not None:
+            hps = hps.parse(specific)
+        return hps
+
+    # ---- construction ----------------------------------------------------------------------
+    def __init__(self, hps, dataset, out_dir=None, experiment_id="0", device="cuda:0", world_size=1, seed=0,
+                 gemm_precision=None):
+        self.hps = hps if isinstance(hps, dict) else dict(hps.values())
+        self.dataset = dataset
+        self.experiment_id = experiment_id
+        dhps = dataset.hps if isinstance(dataset.hps, dict) else dict(dataset.hps.values())
+        self.continuous = bool(dhps["use_continuous_data"])
+        self.vocab_size = None if self.continuous else dataset.tokenizer.VOCAB_SIZE   # sketchformer.py:59
+        self.seq_len = dhps["max_seq_len"]                                            # sketchformer.py:60
+        self.batches_per_epoch = max(1, getattr(dataset, "n_samples", 0) // self.hps["batch_size"])
+        if out_dir is not None:                                                       # core/models.py:68-81
+            self.out_dir = os.path.join(out_dir, self.identifier)
+            self.plots_out_dir = os.path.join(self.out_dir, "plots")
+            self.wgt_out_dir = os.path.join(self.out_dir, "weights")
+            self.tmp_out_dir = os.path.join(self.out_dir, "tmp")
+            for p in (self.out_dir, self.plots_out_dir, self.wgt_out_dir, self.tmp_out_dir):
+                os.makedirs(p, exist_ok=True)
+            self.config_filepath = self.get_config_filepath(out_dir, experiment_id)
+        self.current_step = 0
+        self._device = torch.device(device)
+        self._world = world_size
+        self._seed = seed
+        self._precision = gemm_precision
+        self._engines = {}
+        self._stage = {}
+        self.build_model()
+
+    @property
+    def identifier(self):
+        return "{}-{}".format(self.name, self.experiment_id)
+
+    def _unsupported(self):
+        h = self.hps
+        if h["attn_version"] != 1:
+            return "attn_version=2 (SelfAttnV2 bottleneck)"
+        if not h["lowerdim"]:
+            return "lowerdim=0 (no bottleneck)"
+        if h["class_buffer_layers"]:
+            return "class_buffer_layers>0"
+        if h["optimizer"].lower() != "adam":
+            return "optimizer=%s (only Adam is built)" % h["optimizer"]
+        if h["lr_scheduler"] not in ("WarmupDecay", "warmup-decay"):
+            return "lr_scheduler=%s (the reference's step-decay call site raises too)" % h["lr_scheduler"]
+        return None
+
+    def build_model(self):
+        """models/sketchformer.py:63-129 — here: validate the flags and create the training plan."""
+        why = self._unsupported()
+        if why:
+            raise NotImplementedError(f"sketch-transformer-tf2 on B200: {why} is not built yet")
+        self._weights = None
+        self._engine(self.hps["batch_size"], training=True)
+
+    def _cfg(self, B):
+        h = self.hps
+        kw = {} if self._precision is None else {"gemm_precision": self._precision}
+        return make_cfg(B, self.seq_len, h["d_model"], h["dff"], h["num_heads"], h["num_layers"],
+                        self.vocab_size or 0, self.dataset.n_classes, h["lowerdim"], continuous=self.continuous,
+                        blind_decoder_mask=h["blind_decoder_mask"], do_classification=h["do_classification"],
+                        do_reconstruction=h["do_reconstruction"], class_weight=h["class_weight"],
+                        recon_weight=h["recon_weight"], world_size=self._world, **kw)
+
+    def _engine(self, B, training=False):
+        """One plan per batch size; all plans share the parameter arena of the training plan."""
+        if B in self._engines:
+            return self._engines[B]
+        first = not self._engines
+        eng = Engine(self._cfg(B), device=self._device, training=training or first,
+                     share_from=None if first else self._train_engine)
+        if first:
+            self._train_engine = eng
+            eng.load_params(init_params(dict(self.hps, max_seq_len=self.seq_len, vocab_size=self.vocab_size,
+                                             n_classes=self.dataset.n_classes), seed=self._seed))
+        self._engines[B] = eng
+        return eng
+
+    # ---- staging ---------------------------------------------------------------------------
+    def _to_device(self, key, arr, dtype):
+        """Host numpy (or torch CPU) -> pinned staging ring -> HBM, asynchronously on the current stream.
+        A slot is reused only after the copy that last read it has completed (event)."""
+        t = torch.as_tensor(np.ascontiguousarray(arr)) if not torch.is_tensor(arr) else arr
+        if t.is_cuda:
+            return t.to(dtype).contiguous()
+        t = t.to(dtype)
+        ring = self._stage.setdefault((key, tuple(t.shape)), {"slots": [], "next": 0})
+        if len(ring["slots"]) < 3:
+            ring["slots"].append((torch.empty(t.shape, dtype=dtype).pin_memory(),
+                                  torch.empty(t.shape, dtype=dtype, device=self._device), torch.cuda.Event()))
+            host, dev, ev = ring["slots"][-1]
+        else:
+            host, dev, ev = ring["slots"][ring["next"]]
+            ring["next"] = (ring["next"] + 1) % len(ring["slots"])
+            ev.synchronize()
+        host.copy_(t)
+        dev.copy_(host, non_blocking=True)
+        ev.record()
+        return dev
+
+    # ---- training --------------------------------------------------------------------------
+    def train_on_batch(self, batch, sync_metrics=True):
+        """models/sketchformer.py:351-359: `inp = tar = data`; returns the running-mean quick metrics
+        (builders/keras_metrics.py:41-42).  `sync_metrics=False` skips the device->host read."""
+        data, labels = batch
+        B = int(data.shape[0])
+        eng = self._engine(B, training=True)
+        if self.hps["dropout_rate"] != 0.0:
+            raise NotImplementedError("dropout_rate != 0 is not built yet (parity runs use dropout_rate=0)")
+        x = self._to_device("x", data, torch.int64 if not self.continuous else torch.float32)
+        y = self._to_device("y", labels, torch.int64)
+        if eng is not self._train_engine:          # odd batch size: same arenas, carry the optimizer step over
+            eng.set_step(self._train_engine.step_count())
+        eng.train_step(x, y, apply_adam=True)
+        if eng is not self._train_engine:
+            self._train_engine.set_step(eng.step_count())
+        self.current_step += 1
+        return eng.metrics() if sync_metrics else None
+
+    def prepare_for_start_of_epoch(self):
+        pass
+
+    def prepare_for_end_of_epoch(self):
+        """models/sketchformer.py:364-365: metrics_manager.reset()"""
+        for e in self._engines.values():
+            e.reset_metrics()
+
+    # ---- inference -------------------------------------------------------------------------
+    def encode_from_seq(self, inp_seq):
+        """models/sketchformer.py:162-168 -> {'embedding' (B,d) float32, 'class' (B,C) probabilities}"""
+        inp_seq = np.asarray(inp_seq)
+        if inp_seq.ndim == 1:
+            inp_seq = inp_seq[None]
+        B = inp_seq.shape[0]
+        eng = self._engine(B)
+        eng.encode(self._to_device("x", inp_seq, torch.int64))
+        out = {"embedding": eng.tensor("embedding", (B, self.hps["d_model"])).cpu().numpy(), "class": None}
+        if self.hps["do_classification"]:
+            out["class"] = eng.tensor("cls.probs", (B, self.dataset.n_classes)).cpu().numpy()
+            out["_argmax"] = eng.tensor("cls.argmax", dtype=torch.int32)[:B].cpu().numpy()
+        return out
+
+    def predict_class(self, inp_seq):
+        """models/sketchformer.py:223-228 -> {'class' (B,) int32, 'embedding' (B,d)}"""
+        out = self.encode_from_seq(inp_seq)
+        am = out.pop("_argmax", None)
+        if self.hps["do_classification"]:
+            out["class"] = am.astype(np.int32)
+        return out
+
+    # ---- checkpoints (own format: the flat arenas + step) ------------------------------------
+    def state_dict(self):
+        e = self._train_engine
+        return {"params": e.params.cpu(), "adam_m": e.adam_m.cpu(), "adam_v": e.adam_v.cpu(),
+                "step": e.step_count(), "current_step": self.current_step, "table": dict(e.table)}
+
+    def load_state_dict(self, sd):
+        e = self._train_engine
+        assert sd["table"] == e.table, "checkpoint was written for a different model layout"
+        e.params.copy_(sd["params"]); e.adam_m.copy_(sd["adam_m"]); e.adam_v.copy_(sd["adam_v"])
+        e.set_step(sd["step"])
+        self.current_step = sd["current_step"]
+
+
+models_by_name = {Transformer.name: Transformer}
+
+
+def get_model_by_name(model_name):
+    """models/__init__.py:16-17"""
+    return models_by_name[model_name]

@@ -2,11 +2,21 @@
 activations, losses, every gradient tensor, and the weights after three optimizer steps.
 
 Tolerances (written here as the north-star asks): relative L2 error per tensor
-  * 1e-3 with the tcgen05 TF32 tensor-core GEMMs (north-star: "within 1e-3 fp32 relative"),
-  * 2e-4 with the exact-fp32 SIMT backend (which isolates TF32 rounding from logic errors),
-token / class argmax bit-exact.  Gradient tensors whose true norm is ~0 (the key-projection bias:
-softmax is shift-invariant, so its gradient is identically zero) are measured against 1e-4 of the
-global gradient norm instead of their own norm.
+  * 1e-3 with the tcgen05 tensor-core kernels (north-star: "within 1e-3 fp32 relative"),
+  * 2e-4 with the exact-fp32 SIMT backend (which isolates tensor-core rounding from logic errors),
+token / class argmax bit-exact.
+
+Two properties of the model make a naive per-tensor comparison ill-posed, so the test handles them
+explicitly (both hold for ANY fp32 implementation, the reference's included):
+  * ReLU is not differentiable at 0.  A forward perturbation eps flips ~eps of the hidden units and
+    moves d(loss)/d(ffn.w1) by ~sqrt(eps) in L2 (measured: forward 4e-5 -> gradient 1.7e-3).  The
+    gradients are therefore compared with the oracle evaluated at the engine's own ReLU activation
+    pattern (oracle.relu_pattern), and the pattern itself is required to agree with the oracle's on
+    all but a 1e-3 fraction of units.
+  * softmax is shift-invariant, so the key-projection bias (wk.b) has an identically-zero gradient:
+    what any implementation computes there is rounding noise, which Adam normalises to O(lr) steps.
+    Those tensors are measured against 1e-4 of the global gradient norm and skipped in the
+    "weights after three steps" displacement check.
 """
 import os
 
@@ -23,13 +33,13 @@ from tests.gpu_util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def build(cfg_kw, B, backend, precision=1, **flags):
+def build(cfg_kw, B, backend, precision=2, attn_backend=-1, **flags):
     ocfg = O.OracleConfig(**cfg_kw, **flags)
     c = make_cfg(B, ocfg.max_seq_len, ocfg.d_model, ocfg.dff, ocfg.num_heads, ocfg.num_layers, ocfg.vocab_size,
                  ocfg.n_classes, ocfg.lowerdim, blind_decoder_mask=ocfg.blind_decoder_mask,
                  do_classification=ocfg.do_classification, do_reconstruction=ocfg.do_reconstruction,
                  class_weight=ocfg.class_weight, recon_weight=ocfg.recon_weight, gemm_backend=backend,
-                 gemm_precision=precision)
+                 attn_backend=backend if attn_backend < 0 else attn_backend, gemm_precision=precision)
     return ocfg, Engine(c)
 
 
@@ -60,7 +70,20 @@ def engine_activations(eng, ocfg, B):
     return out
 
 
-CASES = [("tiny", TINY, 4), ("cfg1", CFG1, 8)]
+def engine_relu_pattern(eng, ocfg, B):
+    """name -> bool (B, T, dff): which hidden units of every FFN were active in the engine's forward."""
+    T, f, pat = ocfg.max_seq_len, ocfg.dff, {}
+    for i in range(ocfg.num_layers):
+        pat[f"enc.l{i}.ffn"] = (eng.tensor(f"enc.l{i}.hff", (B, T, f)) > 0).cpu()
+        if ocfg.do_reconstruction:
+            pat[f"dec.l{i}.ffn"] = (eng.tensor(f"dec.l{i}.hff", (B, T - 1, f)) > 0).cpu()
+    return pat
+
+
+# cfg2 dimensions (head dim 32: the tcgen05 attention kernels) at a batch the fp64 oracle does in ~1 s
+CFG2 = dict(num_layers=4, d_model=256, dff=1024, num_heads=8, lowerdim=256, max_seq_len=200, vocab_size=1004,
+            n_classes=345)
+CASES = [("tiny", TINY, 4), ("cfg1", CFG1, 8), ("cfg2-b6", CFG2, 6)]
 
 
 @pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
@@ -73,11 +96,17 @@ def test_train_step_matches_oracle(name, cfg_kw, B, backend):
     p = O.init_params(ocfg, 0, torch.float64)
     eng.load_params(p)
     opt = O.AdamTF(p, ocfg.d_model)
-    tape = {}
-    losses, grads = O.train_step(p, opt, xt, yt, ocfg, tape=tape, dtype=torch.float64)
     xd, yd = xt.cuda(), yt.cuda()
     eng.train_step(xd, yd, apply_adam=True)
     torch.cuda.synchronize()
+    # oracle at the engine's ReLU activation pattern (see module docstring)
+    pattern = engine_relu_pattern(eng, ocfg, B)
+    own, tape = {}, {}
+    with O.relu_pattern(pattern, record=own):
+        losses, grads = O.train_step(p, opt, xt, yt, ocfg, tape=tape, dtype=torch.float64)
+    flips = sum(int((own[k] != pattern[k]).sum()) for k in pattern)
+    units = sum(pattern[k].numel() for k in pattern)
+    assert flips <= 1e-3 * units, f"ReLU pattern differs on {flips} of {units} hidden units"
 
     bad = []
     acts = engine_activations(eng, ocfg, B)
@@ -115,6 +144,8 @@ def test_train_step_matches_oracle(name, cfg_kw, B, backend):
     assert eng.step_count() == 4002
     newp = eng.export_params(p)
     for k, ref in p.items():
+        if float(grads[k].double().norm()) < 1e-6 * G:
+            continue      # identically-zero gradient (key bias): Adam random-walks on rounding noise
         # compare the displacement produced by the optimizer (weights barely move in 2 tiny-lr steps)
         num = float(((newp[k].double() - p_before[k]) - (ref - p_before[k])).norm())
         den = max(float((ref - p_before[k]).norm()), 1e-12)

@@ -12,7 +12,7 @@ from oracle import sketchformer_oracle as O            # noqa: E402
 from oracle.make_golden import CFG1, TINY              # noqa: E402
 from sketchformer_b200 import synth, _lib              # noqa: E402
 from tests.gpu_util import rel_err                     # noqa: E402
-from tests.test_gpu_train import build, engine_activations   # noqa: E402
+from tests.test_gpu_train import build, engine_activations, engine_relu_pattern   # noqa: E402
 
 CFG2 = dict(num_layers=4, d_model=256, dff=1024, num_heads=8, lowerdim=256, max_seq_len=200, vocab_size=1004,
             n_classes=345)
@@ -22,26 +22,33 @@ if __name__ == "__main__":
     ap.add_argument("--cfg", default="tiny")
     ap.add_argument("--backend", type=int, default=1)
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--attn-backend", type=int, default=-1, help="-1: same as --backend")
     ap.add_argument("--tma-tf32", type=int, default=1)
-    ap.add_argument("--precision", type=int, default=1)
+    ap.add_argument("--precision", type=int, default=2)
     ap.add_argument("--quiet", action="store_true")
     ap.add_argument("--all", action="store_true")
+    ap.add_argument("--free-relu", action="store_true", help="do not impose the engine's ReLU pattern on the oracle")
     a = ap.parse_args()
     kw, B = {"tiny": (TINY, 4), "cfg1": (CFG1, 8), "cfg2": (CFG2, 16)}[a.cfg]
     B = a.batch or B
     _lib.check(_lib.load().skf_set_option(b"tma_tf32", a.tma_tf32))
-    ocfg, eng = build(kw, B, a.backend, a.precision)
+    ocfg, eng = build(kw, B, a.backend, a.precision, attn_backend=a.attn_backend)
     x, y = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 1234, vocab=ocfg.vocab_size)
     xt, yt = torch.from_numpy(x), torch.from_numpy(y)
     p = O.init_params(ocfg, 0, torch.float64)
     eng.load_params(p)
     opt = O.AdamTF(p, ocfg.d_model)
-    tape = {}
-    t0 = time.time()
-    losses, grads = O.train_step(p, opt, xt, yt, ocfg, tape=tape, dtype=torch.float64)
-    print(f"oracle fp64 step: {time.time() - t0:.2f}s", losses)
+    tape, own = {}, {}
     eng.train_step(xt.cuda(), yt.cuda(), True)
     torch.cuda.synchronize()
+    pattern = engine_relu_pattern(eng, ocfg, B) if not a.free_relu else None
+    t0 = time.time()
+    with O.relu_pattern(pattern, record=own):
+        losses, grads = O.train_step(p, opt, xt, yt, ocfg, tape=tape, dtype=torch.float64)
+    print(f"oracle fp64 step: {time.time() - t0:.2f}s", losses)
+    if pattern:
+        print("relu flips:", sum(int((own[k] != pattern[k]).sum()) for k in pattern), "of",
+              sum(v.numel() for v in pattern.values()))
     print("engine:", eng.last_step_metrics(), "launches", eng.launches())
     acts = engine_activations(eng, ocfg, B)
     worst = 0.0

@@ -1,0 +1,47 @@
+"""Runs the dominant kernels of the cfg2 step in isolation (for `ncu --set full -k regex:...`):
+FFN-1 GEMM (25600x256 . 256x1024, bias+ReLU), encoder self-attention fwd/bwd (B128 H8 T200 dh32).
+    python tools/prof_ops.py [gemm|attn|all] [reps]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sketchformer_b200 import _lib                              # noqa: E402
+from sketchformer_b200.ops import gemm, ptr, stream             # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+lib = _lib.load()
+torch.manual_seed(0)
+if what in ("gemm", "all"):
+    M, K, N = 25600, 256, 1024
+    X = torch.randn(M, K, device="cuda")
+    W = torch.randn(K, N, device="cuda")
+    b = torch.zeros(N, device="cuda")
+    Y = torch.empty(M, N, device="cuda")
+    for _ in range(reps):
+        gemm(X, K, 1, W, N, 1, Y, N, M, N, K, 0, bias=b, act=1)
+    # FFN-2 shape with residual
+    W2 = torch.randn(N, K, device="cuda")
+    Y2 = torch.empty(M, K, device="cuda")
+    for _ in range(reps):
+        gemm(Y, N, 1, W2, K, 1, Y2, K, M, K, N, 0, bias=b[:K].contiguous(), resid=X)
+if what in ("attn", "all"):
+    B, H, T, dh = 128, 8, 200, 32
+    d = H * dh
+    qkv = torch.randn(B * T, 3 * d, device="cuda")
+    O = torch.empty(B * T, d, device="cuda")
+    dO = torch.randn(B * T, d, device="cuda")
+    dqkv = torch.empty_like(qkv)
+    lse = torch.empty(B * H * T, device="cuda")
+    delta = torch.empty_like(lse)
+    pad = torch.zeros(B * T, dtype=torch.uint8, device="cuda")
+    for _ in range(reps):
+        _lib.check(lib.skf_attn_fwd(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d,
+                                    ptr(lse), ptr(pad), B, H, T, T, dh, 1, 0, 0, stream()))
+        _lib.check(lib.skf_attn_bwd(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d,
+                                    ptr(dO), d, ptr(lse), ptr(delta), ptr(dqkv), 3 * d, ptr(dqkv[:, d:]), 3 * d,
+                                    ptr(dqkv[:, 2 * d:]), 3 * d, ptr(pad), B, H, T, T, dh, 1, 0, 0, stream()))
+torch.cuda.synchronize()
+print("done")
