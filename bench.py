@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--backend", type=int, default=0, help="0 tcgen05 TF32 GEMMs, 1 SIMT fp32 (debug)")
+    ap.add_argument("--precision", type=int, default=-1,
+                    help="tensor-core GEMM passes: 0 TF32 everywhere, 1 3xTF32 forward, 2 3xTF32 everywhere (default: engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -158,7 +160,8 @@ def main():
     c = CFG2
     eng = Engine(make_cfg(BATCH, c["max_seq_len"], c["d_model"], c["dff"], c["num_heads"], c["num_layers"],
                           c["vocab_size"], c["n_classes"], c["lowerdim"], world_size=world,
-                          gemm_backend=args.backend), device=f"cuda:{local}")
+                          gemm_backend=args.backend, **({} if args.precision < 0 else {"gemm_precision": args.precision})),
+                 device=f"cuda:{local}")
     # identical random-init weights on every rank (Keras default initialisers, seed 0)
     from sketchformer_b200.init import init_params
     eng.load_params(init_params(c, seed=0))

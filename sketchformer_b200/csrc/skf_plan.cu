@@ -18,6 +18,10 @@ int attn_bwd_simt(const float*, int64_t, const float*, int64_t, const float*, in
                   const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
                   const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
 extern int g_tma_tf32_type;
+int gemm_tc2_supported(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const float*, int64_t, int, int,
+                       int, const skf_gemm_epilogue*);
+int gemm_tc2(const float*, int64_t, int64_t, const float*, int64_t, int64_t, float*, int64_t, int, int, int,
+             const skf_gemm_epilogue*, int, cudaStream_t);
 int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
 int attn_fwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
                 const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
@@ -143,13 +147,7 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
   W.add("stats_step", 8 * sizeof(double));
   W.add("stats_run", 16 * sizeof(double));
   W.add("pe", (size_t)c.T * d * F);
-  W.add("wc", (size_t)PL.total * F);  // TF32-rounded compute copy of the weights (tma_tf32=0 only)
-  W.add("wlo", (size_t)PL.total * F); // w - tf32(w): low halves of the weights for the 3xTF32 GEMMs
-  {
-    size_t wmax = std::max<size_t>(std::max<size_t>(f, 3 * d), std::max<size_t>((size_t)c.V, (size_t)c.u));
-    W.add("lo.a", Me * wmax * F);     // low half of the activation operand A of the current GEMM
-    W.add("lo.b", Me * wmax * F);     // low half of operand B (weight gradients: both operands are activations)
-  }
+  W.add("wc", g_tma_tf32_type ? 256 : (size_t)PL.total * F);  // TF32-rounded copy of the weights (tma_tf32=0 only)
   W.add("enc_pad", Me);
   W.add("dec_pad", Md);
   W.add("enc.x0", Me * d * F);
@@ -234,7 +232,6 @@ struct skf_plan {
   int64_t launches = 0;
   bool round_ops = false;  // round GEMM operands to TF32 when they are produced
   const float* wc = nullptr;
-  const float* wlo = nullptr;
 
   float* wsf(const std::string& n) const { return reinterpret_cast<float*>(ws + W.t.at(n).off); }
   template <class T>
@@ -306,27 +303,18 @@ struct Gemm {
   // a_elems / b_elems: number of floats of a dense activation operand (its low half is computed here);
   // 0 means the operand is a weight (its low half lives in the "wlo" arena at the same offset).
   int run(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
-          int64_t ldy, int M, int N, int K, skf_gemm_epilogue e, bool x3 = false, int64_t a_elems = 0,
-          int64_t b_elems = 0) const {
-    bool tc = P->c.gemm_backend == 0 && gemm_tc_supported(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e);
+          int64_t ldy, int M, int N, int K, skf_gemm_epilogue e, bool x3 = false) const {
+    const bool tc = P->c.gemm_backend == 0 && gemm_tc2_supported(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e);
     if (!P->round_ops) e.round_tf32 = 0;
-    if (tc && x3) {
-      float* la = P->wsf("lo.a");
-      float* lb = P->wsf("lo.b");
-      if (a_elems > 0) { SKF_TRY(split_lo(A, la, a_elems, st)); e.a_lo = la; }
-      else e.a_lo = P->wlo + (A - P->wc);
-      if (b_elems > 0) { SKF_TRY(split_lo(B, lb, b_elems, st)); e.b_lo = lb; }
-      else e.b_lo = P->wlo + (B - P->wc);
-    }
     if (e.accumulate) {
-      // split-K so that the grid fills the 148 SMs about twice
-      long tiles = tc ? (long)cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256))
-                      : (long)cdiv(M, 64) * cdiv(N, 64);
-      int want = (int)((2 * 148 + tiles - 1) / tiles);
+      // split-K so that the persistent grid (one CTA per SM) has about one tile per SM
+      const long tiles = tc ? (long)cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256))
+                            : (long)cdiv(M, 64) * cdiv(N, 64);
+      int want = (int)((tc ? 148 : 2 * 148) / tiles);
       int maxs = K / 256 > 0 ? K / 256 : 1;
       e.split_k = want < 1 ? 1 : (want > maxs ? maxs : want);
     }
-    return tc ? gemm_tc(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, st)
+    return tc ? gemm_tc2(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, x3 ? 1 : 0, st)
               : gemm_simt(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, st);
   }
   // Y[M,N] = act(X[M,K] * W[K,N] + bias) (+ resid)
@@ -335,7 +323,7 @@ struct Gemm {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
     e.bias = bias; e.act = act; e.resid = resid; e.ld_resid = N; e.round_tf32 = rnd;
-    return run(X, K, 1, W, N, 1, Y, N, M, N, K, e, P->c.gemm_precision >= 1, (int64_t)M * K, 0);
+    return run(X, K, 1, W, N, 1, Y, N, M, N, K, e, P->c.gemm_precision >= 1);
   }
   // dX[M,K] = dY[M,N] * W[K,N]^T  (* (mask>0)) (+ resid)
   int dgrad(const float* dY, const float* W, float* dX, int M, int N, int K, const float* mask,
@@ -343,14 +331,14 @@ struct Gemm {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
     e.mask = mask; e.ld_mask = K; e.resid = resid; e.ld_resid = K; e.round_tf32 = rnd;
-    return run(dY, N, 1, W, 1, N, dX, K, M, K, N, e, P->c.gemm_precision >= 2, (int64_t)M * N, 0);
+    return run(dY, N, 1, W, 1, N, dX, K, M, K, N, e, P->c.gemm_precision >= 2);
   }
   // dW[K,N] += X[M,K]^T * dY[M,N] ; db[N] += colsum(dY)
   int wgrad(const float* X, const float* dY, float* dW, float* db, int M, int N, int K) const {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
     e.accumulate = 1;
-    SKF_TRY(run(X, 1, K, dY, N, 1, dW, N, K, N, M, e, P->c.gemm_precision >= 2, (int64_t)M * K, (int64_t)M * N));
+    SKF_TRY(run(X, 1, K, dY, N, 1, dW, N, K, N, M, e, P->c.gemm_precision == 2));
     if (db) SKF_TRY(skf_colsum(dY, N, db, M, N, st));
     return SKF_OK;
   }
@@ -380,11 +368,6 @@ static int attn_bwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
 
 // ---- forward -----------------------------------------------------------------------------------
 static int refresh_compute_weights(skf_plan* P, cudaStream_t st) {
-  if (P->c.gemm_backend == 0 && P->c.gemm_precision >= 1) {
-    float* wl = P->wsf("wlo");
-    SKF_TRY(split_lo(P->params, wl, P->PL.total, st));
-    P->wlo = wl;
-  }
   if (!P->round_ops) {
     P->wc = P->params;
     return SKF_OK;
@@ -781,7 +764,10 @@ int64_t skf_plan_launches(const skf_plan* P) { return P ? P->launches : 0; }
 // ---- thin operator wrappers -------------------------------------------------------------------
 int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
              int64_t ldy, int M, int N, int K, const skf_gemm_epilogue* epi, int backend, void* stream) {
-  if (backend == 0) return gemm_tc(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
+  if (backend == 0 || backend == 2)      // persistent tcgen05 kernel: single-pass TF32 / 3xTF32
+    return gemm_tc2(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, backend == 2, as_stream(stream));
+  if (backend == 3)                      // first-generation (one tile per CTA) tcgen05 kernel, kept for A/B runs
+    return gemm_tc(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
   return gemm_simt(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
 }
 

@@ -20,13 +20,24 @@ if what in ("gemm", "all"):
     W = torch.randn(K, N, device="cuda")
     b = torch.zeros(N, device="cuda")
     Y = torch.empty(M, N, device="cuda")
-    for _ in range(reps):
-        gemm(X, K, 1, W, N, 1, Y, N, M, N, K, 0, bias=b, act=1)
+    import time
+    for backend in (2, 0, 3):
+        for _ in range(reps):
+            gemm(X, K, 1, W, N, 1, Y, N, M, N, K, backend, bias=b, act=1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            gemm(X, K, 1, W, N, 1, Y, N, M, N, K, backend, bias=b, act=1)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 20
+        print(f"FFN-1 gemm backend {backend}: {us:.1f} us  {2.0 * M * N * K / us / 1e6:.1f} TFLOP/s (algorithmic)")
     # FFN-2 shape with residual
     W2 = torch.randn(N, K, device="cuda")
     Y2 = torch.empty(M, K, device="cuda")
     for _ in range(reps):
-        gemm(Y, N, 1, W2, K, 1, Y2, K, M, K, N, 0, bias=b[:K].contiguous(), resid=X)
+        gemm(Y, N, 1, W2, K, 1, Y2, K, M, K, N, 2, bias=b[:K].contiguous(), resid=X)
 if what in ("attn", "all"):
     B, H, T, dh = 128, 8, 200, 32
     d = H * dh
