@@ -1,0 +1,699 @@
+// Scaled-dot-product attention (builders/utils.py:71-105, split_heads transformer.py:160-165) and its
+// backward on the 5th-gen tensor cores, head dim 32, flash-style: the (Tq,Tk) score matrix never
+// exists in HBM, masks come from per-key pad flags + indices, and the other sequence is streamed in
+// 64-row blocks so that a CTA needs only 64-96 KB of shared memory and 128-256 TMEM columns and
+// two or three CTAs share an SM (their TMA / MMA / softmax phases overlap each other).
+//
+//   fwd : per key block    S = Q K^T ; online softmax (running max / sum, O rescaled in TMEM) ; O += P V
+//   dq  : per key block    S, dP = dO V^T ; dS = P (dP - delta) / sqrt(dh) ; dQ += dS K      (lanes = queries)
+//   dkv : per query block  S^T = K Q^T, dP^T = V dO^T ; dV += P^T dO ; dK += dS^T Q         (lanes = keys)
+//
+// One thread per TMEM lane does the row math in registers and writes P / dS back to TMEM, where the
+// second MMA reads it as its A operand (tcgen05.mma TS form).
+//
+// Precision (X3 = true, the default of the plan): products of two operands that come from memory
+// (Q K^T, dO V^T) run as the error-compensated 3xTF32 sum  Ah*Bh + Ah*Bl + Al*Bh  with the hi/lo split
+// done in shared memory after the TMA load (kind::tf32 truncates, so hi is what the tensor core sees
+// of the raw tile and lo = x - trunc(x)).  Products whose A operand is produced in registers
+// (P, dS) round it to TF32 (nearest) once and use two passes  A*Bh + A*Bl ; the softmax row sum is
+// taken over the rounded P, so numerator and denominator see the same weights.
+#include "skf_common.cuh"
+#include "skf_ptx.cuh"
+
+namespace skf {
+using namespace ptx;
+
+int make_tmap_2d_typed(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                       uint32_t box_inner, uint32_t box_outer, bool mn_major, bool tf32_convert);
+
+constexpr int A2_DH = 32;              // head dim (one 128-byte swizzle row)
+constexpr int A2_BLK = 64;             // rows of the streamed operand per iteration
+constexpr int A2_T128 = 128 * 128;     // 128 rows x 128 B
+constexpr int A2_T64 = 64 * 128;       //  64 rows x 128 B
+constexpr int A2_MAXT = 256;           // longest sequence (pad / lse / delta staging)
+constexpr float A2_MASK_NEG = -1e9f;
+
+struct Attn2Args {
+  int H, Tq, Tk, mode;
+  float scale;
+  const uint8_t* key_pad;  // [B, Tk] or nullptr
+  float* out0;             // fwd: O      dq: dQ     dkv: dK
+  int64_t ld0;
+  float* out1;             // fwd: lse    dq: delta  dkv: dV
+  int64_t ld1;
+  const float* lse;        // dq / dkv
+  const float* delta;      // dkv
+  const float* O;          // dq (for delta)
+  int64_t ldO;
+  const float* dO;         // dq (for delta)
+  int64_t lddO;
+};
+
+__device__ __forceinline__ bool a2_masked(int mode, int qi, int kj, int padj) {
+  bool m = false;
+  if (mode >= 1) m = padj != 0;
+  if (mode == 2) m = m || (kj > qi);
+  return m;
+}
+
+// lo = x - trunc_tf32(x), elementwise over a tile (the raw and lo tiles share their swizzled layout)
+__device__ __forceinline__ void a2_split(const uint8_t* raw, uint8_t* lo, int bytes) {
+  for (int i = threadIdx.x * 16; i < bytes; i += 128 * 16) {
+    const float4 v = *reinterpret_cast<const float4*>(raw + i);
+    float4 l;
+    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    *reinterpret_cast<float4*>(lo + i) = l;
+  }
+}
+
+// D[128 x N] = A B^T, both K-major smem tiles with dh = 32 (4 k-steps); X3: Ah*Bl + Al*Bh + Ah*Bh
+template <bool X3>
+__device__ __forceinline__ void a2_mma_ss(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl,
+                                          uint32_t idesc) {
+  uint32_t acc = 0;
+  if (X3) {
+#pragma unroll
+    for (int ks = 0; ks < A2_DH / 8; ks++) {
+      mma_tf32_ss(d, make_desc_kmajor(ah + ks * 32), make_desc_kmajor(bl + ks * 32), idesc, acc);
+      acc = 1;
+    }
+#pragma unroll
+    for (int ks = 0; ks < A2_DH / 8; ks++)
+      mma_tf32_ss(d, make_desc_kmajor(al + ks * 32), make_desc_kmajor(bh + ks * 32), idesc, 1u);
+  }
+#pragma unroll
+  for (int ks = 0; ks < A2_DH / 8; ks++) {
+    mma_tf32_ss(d, make_desc_kmajor(ah + ks * 32), make_desc_kmajor(bh + ks * 32), idesc, acc);
+    acc = 1;
+  }
+}
+
+// D[128 x 32] (+)= A[tmem, 64 columns] * B[64 rows x 32, MN-major smem]; X3: A*Bl + A*Bh
+template <bool X3>
+__device__ __forceinline__ void a2_mma_ts(uint32_t d, uint32_t a_tmem, uint32_t bh, uint32_t bl, uint32_t idesc,
+                                          uint32_t accumulate) {
+  uint32_t acc = accumulate;
+  if (X3) {
+#pragma unroll
+    for (int k = 0; k < A2_BLK / 8; k++) {
+      mma_tf32_ts(d, a_tmem + k * 8, make_desc_mnmajor(bl + k * 1024, 4096), idesc, acc);
+      acc = 1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < A2_BLK / 8; k++) {
+    mma_tf32_ts(d, a_tmem + k * 8, make_desc_mnmajor(bh + k * 1024, 4096), idesc, acc);
+    acc = 1;
+  }
+}
+
+struct A2Common {
+  uint32_t base;   // 1024-aligned smem window
+  uint8_t* gen;
+  uint32_t bar0;   // 8 mbarriers
+  uint32_t tmem;
+};
+
+template <int TMEM_COLS>
+__device__ __forceinline__ void a2_prologue(A2Common& c, uint8_t* smem_raw, int data_bytes) {
+  const uint32_t raw = smem_u32(smem_raw);
+  c.base = (raw + 1023u) & ~1023u;
+  c.gen = smem_raw + (c.base - raw);
+  c.bar0 = c.base + data_bytes;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; i++) mbar_init(c.bar0 + 8 * i, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) {
+    tmem_alloc(c.bar0 + 64, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem = *reinterpret_cast<volatile uint32_t*>(c.gen + data_bytes + 64);
+}
+
+template <int TMEM_COLS>
+__device__ __forceinline__ void a2_free(const A2Common& c) {
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(c.tmem, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward.  smem: Q | Ql | K | Kl | V | Vl | pad[256] | barriers     tmem: S/P [0,64)  O [64,96)
+// ---------------------------------------------------------------------------------------------------
+constexpr int A2F_DATA = 2 * A2_T128 + 4 * A2_T64 + A2_MAXT;
+template <bool X3>
+__global__ void __launch_bounds__(128, 3)
+attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
+            const __grid_constant__ CUtensorMap mV, const Attn2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  A2Common c;
+  a2_prologue<128>(c, smem_raw, A2F_DATA);
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sQ = c.base, sQl = sQ + A2_T128, sK = sQl + A2_T128, sKl = sK + A2_T64, sV = sKl + A2_T64,
+                 sVl = sV + A2_T64;
+  uint8_t* gQ = c.gen;
+  uint8_t* gK = gQ + 2 * A2_T128;
+  uint8_t* gV = gK + 2 * A2_T64;
+  uint8_t* pad_s = gV + 2 * A2_T64;
+  const uint32_t bar_q = c.bar0, bar_k = c.bar0 + 8, bar_v = c.bar0 + 16, bar_s = c.bar0 + 24, bar_o = c.bar0 + 32;
+  const int kmax = a.mode == 2 ? min(a.Tk, q0 + 128) : a.Tk;   // causal: keys above the tile's last row never count
+  const int nblk = (kmax + A2_BLK - 1) / A2_BLK;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, A2_T128);
+    tma_load_2d(sQ, &mQ, bar_q, h * A2_DH, b * a.Tq + q0);
+    mbar_arrive_expect_tx(bar_k, A2_T64);
+    tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk);
+    mbar_arrive_expect_tx(bar_v, A2_T64);
+    tma_load_2d(sV, &mV, bar_v, h * A2_DH, b * a.Tk);
+  }
+  for (int i = tid; i < A2_MAXT; i += 128)
+    pad_s[i] = (a.key_pad && i < a.Tk) ? a.key_pad[(int64_t)b * a.Tk + i] : 0;
+  mbar_wait(bar_q, 0);
+  if (X3) a2_split(gQ, gQ + A2_T128, A2_T128);
+
+  const uint32_t tS = c.tmem, tO = c.tmem + 64;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
+  const uint32_t idesc_o = make_idesc_tf32(128, A2_DH, 0, 1);
+  const int qi = q0 + tid;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int j = 0; j < nblk; j++) {
+    const uint32_t ph = (uint32_t)j & 1u;
+    const int k0 = j * A2_BLK;
+    mbar_wait(bar_k, ph);
+    if (X3) a2_split(gK, gK + A2_T64, A2_T64);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      a2_mma_ss<X3>(tS, sQ, sQl, sK, sKl, idesc_s);
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nblk) {     // K buffers are free again: prefetch the next key block
+      mbar_arrive_expect_tx(bar_k, A2_T64);
+      tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk + k0 + A2_BLK);
+    }
+    // ---- online softmax: this thread owns query row qi == TMEM lane tid ----------------------
+    uint32_t r0[32], r1[32];
+    __syncwarp();
+    tmem_ld32(tS + lane_off, r0);
+    tmem_ld32(tS + lane_off + 32, r1);
+    tmem_ld_wait();
+    float bmax = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) {
+      const int kj = k0 + jj;
+      float s = __uint_as_float(r0[jj]) * a.scale;
+      if (a2_masked(a.mode, qi, kj, pad_s[kj & (A2_MAXT - 1)])) s += A2_MASK_NEG;
+      s = kj < a.Tk ? s : -INFINITY;
+      r0[jj] = __float_as_uint(s);
+      bmax = fmaxf(bmax, s);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) {
+      const int kj = k0 + 32 + jj;
+      float s = __uint_as_float(r1[jj]) * a.scale;
+      if (a2_masked(a.mode, qi, kj, pad_s[kj & (A2_MAXT - 1)])) s += A2_MASK_NEG;
+      s = kj < a.Tk ? s : -INFINITY;
+      r1[jj] = __float_as_uint(s);
+      bmax = fmaxf(bmax, s);
+    }
+    const float m_new = fmaxf(m_run, bmax);
+    const float alpha = __expf(m_run - m_new);        // 0 on the first block (m_run = -inf)
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) {
+      const float p = round_tf32(__expf(__uint_as_float(r0[jj]) - m_new));
+      sum += p;
+      r0[jj] = __float_as_uint(p);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) {
+      const float p = round_tf32(__expf(__uint_as_float(r1[jj]) - m_new));
+      sum += p;
+      r1[jj] = __float_as_uint(p);
+    }
+    l_run = l_run * alpha + sum;
+    m_run = m_new;
+    __syncwarp();
+    tmem_st32(tS + lane_off, r0);
+    tmem_st32(tS + lane_off + 32, r1);
+    if (j > 0) {                                       // rescale the running output (previous P V has completed)
+      tmem_ld32(tO + lane_off, r0);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) r0[jj] = __float_as_uint(__uint_as_float(r0[jj]) * alpha);
+      tmem_st32(tO + lane_off, r0);
+    }
+    tmem_st_wait();
+    mbar_wait(bar_v, ph);
+    if (X3) a2_split(gV, gV + A2_T64, A2_T64);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      a2_mma_ts<X3>(tO, tS, sV, sVl, idesc_o, j > 0 ? 1u : 0u);
+      tc_commit(bar_o);
+    }
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nblk) {     // V buffers are free again
+      mbar_arrive_expect_tx(bar_v, A2_T64);
+      tma_load_2d(sV, &mV, bar_v, h * A2_DH, b * a.Tk + k0 + A2_BLK);
+    }
+  }
+  {
+    uint32_t r[32];
+    __syncwarp();
+    tmem_ld32(tO + lane_off, r);
+    tmem_ld_wait();
+    if (qi < a.Tq) {
+      const float inv = 1.0f / l_run;
+      float4* dst = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tq + qi) * a.ld0 + h * A2_DH);
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++)
+        dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * inv, __uint_as_float(r[4 * jj + 1]) * inv,
+                              __uint_as_float(r[4 * jj + 2]) * inv, __uint_as_float(r[4 * jj + 3]) * inv);
+      if (a.out1) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = m_run + logf(l_run);
+    }
+  }
+  a2_free<128>(c);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward, dQ.  smem: Q | Ql | dO | dOl | K | Kl | X | Xl | pad[256] | barriers   (X = V block, then the
+// MN-major copy of the K block).   tmem: S [0,64)  dP -> dS [64,128)  dQ [128,160)
+// ---------------------------------------------------------------------------------------------------
+constexpr int A2Q_DATA = 4 * A2_T128 + 4 * A2_T64 + A2_MAXT;
+template <bool X3>
+__global__ void __launch_bounds__(128, 2)
+attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mdO,
+               const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
+               const __grid_constant__ CUtensorMap mKmn, const Attn2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  A2Common c;
+  a2_prologue<256>(c, smem_raw, A2Q_DATA);
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sQ = c.base, sQl = sQ + A2_T128, sdO = sQl + A2_T128, sdOl = sdO + A2_T128, sK = sdOl + A2_T128,
+                 sKl = sK + A2_T64, sX = sKl + A2_T64, sXl = sX + A2_T64;
+  uint8_t* gQ = c.gen;
+  uint8_t* gdO = gQ + 2 * A2_T128;
+  uint8_t* gK = gdO + 2 * A2_T128;
+  uint8_t* gX = gK + 2 * A2_T64;
+  uint8_t* pad_s = gX + 2 * A2_T64;
+  const uint32_t bar_q = c.bar0, bar_k = c.bar0 + 8, bar_v = c.bar0 + 16, bar_x = c.bar0 + 24, bar_s = c.bar0 + 32,
+                 bar_o = c.bar0 + 40;
+  const int kmax = a.mode == 2 ? min(a.Tk, q0 + 128) : a.Tk;
+  const int nblk = (kmax + A2_BLK - 1) / A2_BLK;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, 2 * A2_T128);
+    tma_load_2d(sQ, &mQ, bar_q, h * A2_DH, b * a.Tq + q0);
+    tma_load_2d(sdO, &mdO, bar_q, h * A2_DH, b * a.Tq + q0);
+    mbar_arrive_expect_tx(bar_k, A2_T64);
+    tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk);
+    mbar_arrive_expect_tx(bar_v, A2_T64);
+    tma_load_2d(sX, &mV, bar_v, h * A2_DH, b * a.Tk);
+  }
+  for (int i = tid; i < A2_MAXT; i += 128)
+    pad_s[i] = (a.key_pad && i < a.Tk) ? a.key_pad[(int64_t)b * a.Tk + i] : 0;
+  // delta_i = sum_c dO[i,c] O[i,c]  (row per thread, 128 B each from global)
+  const int qi = q0 + tid;
+  float delta = 0.f, lse = 0.f;
+  if (qi < a.Tq) {
+    const float4* o4 = reinterpret_cast<const float4*>(a.O + ((int64_t)b * a.Tq + qi) * a.ldO + h * A2_DH);
+    const float4* g4 = reinterpret_cast<const float4*>(a.dO + ((int64_t)b * a.Tq + qi) * a.lddO + h * A2_DH);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      const float4 o = o4[jj], g = g4[jj];
+      delta += (o.x * g.x + o.y * g.y) + (o.z * g.z + o.w * g.w);
+    }
+    lse = a.lse[((int64_t)b * a.H + h) * a.Tq + qi];
+    a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = delta;
+  }
+  mbar_wait(bar_q, 0);
+  if (X3) {
+    a2_split(gQ, gQ + A2_T128, A2_T128);
+    a2_split(gdO, gdO + A2_T128, A2_T128);
+  }
+  const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdQ = c.tmem + 128;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
+  const uint32_t idesc_o = make_idesc_tf32(128, A2_DH, 0, 1);
+
+  for (int j = 0; j < nblk; j++) {
+    const uint32_t ph = (uint32_t)j & 1u;
+    const int k0 = j * A2_BLK;
+    mbar_wait(bar_k, ph);
+    mbar_wait(bar_v, ph);
+    if (X3) {
+      a2_split(gK, gK + A2_T64, A2_T64);
+      a2_split(gX, gX + A2_T64, A2_T64);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      a2_mma_ss<X3>(tS, sQ, sQl, sK, sKl, idesc_s);
+      a2_mma_ss<X3>(tdP, sdO, sdOl, sX, sXl, idesc_s);
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    if (tid == 0) {                       // V and K (K-major) buffers are free
+      mbar_arrive_expect_tx(bar_x, A2_T64);
+      tma_load_2d(sX, &mKmn, bar_x, h * A2_DH, b * a.Tk + k0);
+      if (j + 1 < nblk) {
+        mbar_arrive_expect_tx(bar_k, A2_T64);
+        tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk + k0 + A2_BLK);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      uint32_t rs[32], rp[32];
+      __syncwarp();
+      tmem_ld32(tS + lane_off + half * 32, rs);
+      tmem_ld32(tdP + lane_off + half * 32, rp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) {
+        const int kj = k0 + half * 32 + jj;
+        float s = __uint_as_float(rs[jj]) * a.scale;
+        if (a2_masked(a.mode, qi, kj, pad_s[kj & (A2_MAXT - 1)])) s += A2_MASK_NEG;
+        const bool ok = kj < a.Tk && qi < a.Tq;
+        const float p = ok ? __expf(s - lse) : 0.f;
+        const float ds = ok ? p * (__uint_as_float(rp[jj]) - delta) * a.scale : 0.f;
+        rp[jj] = __float_as_uint(round_tf32(ds));
+      }
+      __syncwarp();
+      tmem_st32(tdP + lane_off + half * 32, rp);
+    }
+    tmem_st_wait();
+    mbar_wait(bar_x, ph);
+    if (X3) a2_split(gX, gX + A2_T64, A2_T64);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      a2_mma_ts<X3>(tdQ, tdP, sX, sXl, idesc_o, j > 0 ? 1u : 0u);
+      tc_commit(bar_o);
+    }
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < nblk) {
+      mbar_arrive_expect_tx(bar_v, A2_T64);
+      tma_load_2d(sX, &mV, bar_v, h * A2_DH, b * a.Tk + k0 + A2_BLK);
+    }
+  }
+  {
+    uint32_t r[32];
+    __syncwarp();
+    tmem_ld32(tdQ + lane_off, r);
+    tmem_ld_wait();
+    if (qi < a.Tq) {
+      float4* dst = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tq + qi) * a.ld0 + h * A2_DH);
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++)
+        dst[jj] = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
+                              __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
+    }
+  }
+  a2_free<256>(c);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward, dK / dV.  smem: K | Kl | V | Vl | A | Al | B | Bl | lse[256] | delta[256] | barriers
+//   (A, B = Q block, dO block K-major for the score MMAs, then their MN-major copies for the output MMAs)
+// tmem: S^T -> P^T [0,64)  dP^T -> dS^T [64,128)  dV [128,160)  dK [160,192)
+// ---------------------------------------------------------------------------------------------------
+constexpr int A2K_DATA = 4 * A2_T128 + 4 * A2_T64 + 2 * A2_MAXT * 4;
+template <bool X3>
+__global__ void __launch_bounds__(128, 2)
+attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
+                const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mdO,
+                const __grid_constant__ CUtensorMap mQmn, const __grid_constant__ CUtensorMap mdOmn,
+                const Attn2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  A2Common c;
+  a2_prologue<256>(c, smem_raw, A2K_DATA);
+  const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * 128;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sK = c.base, sKl = sK + A2_T128, sV = sKl + A2_T128, sVl = sV + A2_T128, sA = sVl + A2_T128,
+                 sAl = sA + A2_T64, sB = sAl + A2_T64, sBl = sB + A2_T64;
+  uint8_t* gK = c.gen;
+  uint8_t* gV = gK + 2 * A2_T128;
+  uint8_t* gA = gV + 2 * A2_T128;
+  uint8_t* gB = gA + 2 * A2_T64;
+  float* lse_s = reinterpret_cast<float*>(gB + 2 * A2_T64);
+  float* del_s = lse_s + A2_MAXT;
+  const uint32_t bar_q = c.bar0, bar_a = c.bar0 + 8, bar_b = c.bar0 + 16, bar_s = c.bar0 + 24, bar_o = c.bar0 + 32;
+  const int nqb = (a.Tq + A2_BLK - 1) / A2_BLK;
+  const int ib0 = a.mode == 2 ? j0 / A2_BLK : 0;     // causal: queries before the tile's first key see none of it
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, 2 * A2_T128);
+    tma_load_2d(sK, &mK, bar_q, h * A2_DH, b * a.Tk + j0);
+    tma_load_2d(sV, &mV, bar_q, h * A2_DH, b * a.Tk + j0);
+    if (ib0 < nqb) {
+      mbar_arrive_expect_tx(bar_a, 2 * A2_T64);
+      tma_load_2d(sA, &mQ, bar_a, h * A2_DH, b * a.Tq + ib0 * A2_BLK);
+      tma_load_2d(sB, &mdO, bar_a, h * A2_DH, b * a.Tq + ib0 * A2_BLK);
+    }
+  }
+  for (int i = tid; i < A2_MAXT; i += 128) {
+    lse_s[i] = i < a.Tq ? a.lse[((int64_t)b * a.H + h) * a.Tq + i] : 0.f;
+    del_s[i] = i < a.Tq ? a.delta[((int64_t)b * a.H + h) * a.Tq + i] : 0.f;
+  }
+  const int kj = j0 + tid;
+  const int padj = (a.key_pad && kj < a.Tk) ? a.key_pad[(int64_t)b * a.Tk + kj] : 0;
+  mbar_wait(bar_q, 0);
+  if (X3) {
+    a2_split(gK, gK + A2_T128, A2_T128);
+    a2_split(gV, gV + A2_T128, A2_T128);
+  }
+  const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdV = c.tmem + 128, tdK = c.tmem + 160;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
+  const uint32_t idesc_o = make_idesc_tf32(128, A2_DH, 0, 1);
+
+  int it = 0;
+  for (int ib = ib0; ib < nqb; ib++, it++) {
+    const uint32_t ph = (uint32_t)it & 1u;
+    const int i0 = ib * A2_BLK;
+    mbar_wait(bar_a, ph);
+    if (X3) {
+      a2_split(gA, gA + A2_T64, A2_T64);
+      a2_split(gB, gB + A2_T64, A2_T64);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      a2_mma_ss<X3>(tS, sK, sKl, sA, sAl, idesc_s);      // S^T  = K Q^T
+      a2_mma_ss<X3>(tdP, sV, sVl, sB, sBl, idesc_s);     // dP^T = V dO^T
+      tc_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    if (tid == 0) {                        // reload the same query block MN-major for the output MMAs
+      mbar_arrive_expect_tx(bar_b, 2 * A2_T64);
+      tma_load_2d(sA, &mQmn, bar_b, h * A2_DH, b * a.Tq + i0);
+      tma_load_2d(sB, &mdOmn, bar_b, h * A2_DH, b * a.Tq + i0);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      uint32_t rs[32], rp[32];
+      __syncwarp();
+      tmem_ld32(tS + lane_off + half * 32, rs);
+      tmem_ld32(tdP + lane_off + half * 32, rp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) {
+        const int qi = i0 + half * 32 + jj;
+        float s = __uint_as_float(rs[jj]) * a.scale;
+        if (a2_masked(a.mode, qi, kj, padj)) s += A2_MASK_NEG;
+        const bool ok = kj < a.Tk && qi < a.Tq;
+        const float p = ok ? __expf(s - lse_s[qi & (A2_MAXT - 1)]) : 0.f;
+        const float ds = ok ? p * (__uint_as_float(rp[jj]) - del_s[qi & (A2_MAXT - 1)]) * a.scale : 0.f;
+        rs[jj] = __float_as_uint(round_tf32(p));
+        rp[jj] = __float_as_uint(round_tf32(ds));
+      }
+      __syncwarp();
+      tmem_st32(tS + lane_off + half * 32, rs);
+      tmem_st32(tdP + lane_off + half * 32, rp);
+    }
+    tmem_st_wait();
+    mbar_wait(bar_b, ph);
+    if (X3) {
+      a2_split(gA, gA + A2_T64, A2_T64);
+      a2_split(gB, gB + A2_T64, A2_T64);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      a2_mma_ts<X3>(tdV, tS, sB, sBl, idesc_o, it > 0 ? 1u : 0u);     // dV += P^T dO
+      a2_mma_ts<X3>(tdK, tdP, sA, sAl, idesc_o, it > 0 ? 1u : 0u);    // dK += dS^T Q
+      tc_commit(bar_o);
+    }
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    if (tid == 0 && ib + 1 < nqb) {
+      mbar_arrive_expect_tx(bar_a, 2 * A2_T64);
+      tma_load_2d(sA, &mQ, bar_a, h * A2_DH, b * a.Tq + i0 + A2_BLK);
+      tma_load_2d(sB, &mdO, bar_a, h * A2_DH, b * a.Tq + i0 + A2_BLK);
+    }
+  }
+  {
+    uint32_t rv[32], rk[32];
+    __syncwarp();
+    if (it > 0) {
+      tmem_ld32(tdV + lane_off, rv);
+      tmem_ld32(tdK + lane_off, rk);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) rv[jj] = rk[jj] = 0u;
+    }
+    if (kj < a.Tk) {
+      float4* dk = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tk + kj) * a.ld0 + h * A2_DH);
+      float4* dv = reinterpret_cast<float4*>(a.out1 + ((int64_t)b * a.Tk + kj) * a.ld1 + h * A2_DH);
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) {
+        dk[jj] = make_float4(__uint_as_float(rk[4 * jj]), __uint_as_float(rk[4 * jj + 1]),
+                             __uint_as_float(rk[4 * jj + 2]), __uint_as_float(rk[4 * jj + 3]));
+        dv[jj] = make_float4(__uint_as_float(rv[4 * jj]), __uint_as_float(rv[4 * jj + 1]),
+                             __uint_as_float(rv[4 * jj + 2]), __uint_as_float(rv[4 * jj + 3]));
+      }
+    }
+  }
+  a2_free<256>(c);
+}
+
+// ---- host --------------------------------------------------------------------------------------
+int attn2_supported(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, int Tq,
+                    int Tk, int dh) {
+  if (dh != A2_DH) return 0;
+  if (Tk > A2_MAXT || Tq > A2_MAXT || Tq < 1 || Tk < 1) return 0;
+  if ((ldq | ldk | ldv) & 3) return 0;
+  if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) | reinterpret_cast<uintptr_t>(V)) & 15) return 0;
+  return 1;
+}
+
+// rows: box height (128 for the lane-side operand, 64 for the streamed one); conv: TMA rounds to TF32
+static int a2_map(CUtensorMap* m, const float* p, int64_t ld, int H, int64_t nrows, int rows, bool mn, bool conv) {
+  return make_tmap_2d_typed(m, p, (uint64_t)H * A2_DH, (uint64_t)nrows, (uint64_t)ld, A2_DH, (uint32_t)rows, mn, conv);
+}
+
+template <class Kern>
+static int a2_attr(Kern k, int bytes) {
+  SKF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  SKF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  return SKF_OK;
+}
+
+int attn2_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, float* O,
+              int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh, int mode, int x3,
+              cudaStream_t st) {
+  SKF_REQUIRE(attn2_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, dh), SKF_ERR_UNSUPPORTED, "attn2_fwd: shape");
+  SKF_REQUIRE((ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, SKF_ERR_BAD_ALIGN, "attn2_fwd: O");
+  SKF_REQUIRE(mode == 0 || key_pad != nullptr || mode == 2, SKF_ERR_BAD_ARG, "attn2_fwd: mode 1 needs key_pad");
+  CUtensorMap mQ, mK, mV;
+  SKF_TRY(a2_map(&mQ, Q, ldq, H, (int64_t)B * Tq, 128, false, !x3));
+  SKF_TRY(a2_map(&mK, K, ldk, H, (int64_t)B * Tk, A2_BLK, false, !x3));
+  SKF_TRY(a2_map(&mV, V, ldv, H, (int64_t)B * Tk, A2_BLK, true, !x3));
+  Attn2Args a;
+  memset(&a, 0, sizeof(a));
+  a.H = H; a.Tq = Tq; a.Tk = Tk; a.mode = mode; a.scale = 1.0f / sqrtf((float)dh);
+  a.key_pad = key_pad; a.out0 = O; a.ld0 = ldo; a.out1 = lse;
+  const int smem = A2F_DATA + 1024 + 128;
+  dim3 grid(cdiv(Tq, 128), H, B);
+  if (x3) {
+    static bool done = false;
+    if (!done) { SKF_TRY(a2_attr(attn2_fwd_k<true>, smem)); done = true; }
+    attn2_fwd_k<true><<<grid, 128, smem, st>>>(mQ, mK, mV, a);
+  } else {
+    static bool done = false;
+    if (!done) { SKF_TRY(a2_attr(attn2_fwd_k<false>, smem)); done = true; }
+    attn2_fwd_k<false><<<grid, 128, smem, st>>>(mQ, mK, mV, a);
+  }
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int attn2_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, const float* O,
+              int64_t ldo, const float* dO, int64_t lddo, const float* lse, float* delta, float* dQ, int64_t lddq,
+              float* dK, int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad, int B, int H, int Tq, int Tk,
+              int dh, int mode, int x3, cudaStream_t st) {
+  SKF_REQUIRE(attn2_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, dh), SKF_ERR_UNSUPPORTED, "attn2_bwd: shape");
+  SKF_REQUIRE(((lddo | lddq | lddk | lddv | ldo) & 3) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(dO) | reinterpret_cast<uintptr_t>(dQ) | reinterpret_cast<uintptr_t>(dK) |
+                    reinterpret_cast<uintptr_t>(dV) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
+              SKF_ERR_BAD_ALIGN, "attn2_bwd: alignment");
+  const bool conv = !x3;
+  CUtensorMap mQ128, mdO128, mK64, mV64, mK64mn, mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn;
+  SKF_TRY(a2_map(&mQ128, Q, ldq, H, (int64_t)B * Tq, 128, false, conv));
+  SKF_TRY(a2_map(&mdO128, dO, lddo, H, (int64_t)B * Tq, 128, false, conv));
+  SKF_TRY(a2_map(&mK64, K, ldk, H, (int64_t)B * Tk, A2_BLK, false, conv));
+  SKF_TRY(a2_map(&mV64, V, ldv, H, (int64_t)B * Tk, A2_BLK, false, conv));
+  SKF_TRY(a2_map(&mK64mn, K, ldk, H, (int64_t)B * Tk, A2_BLK, true, conv));
+  SKF_TRY(a2_map(&mK128, K, ldk, H, (int64_t)B * Tk, 128, false, conv));
+  SKF_TRY(a2_map(&mV128, V, ldv, H, (int64_t)B * Tk, 128, false, conv));
+  SKF_TRY(a2_map(&mQ64, Q, ldq, H, (int64_t)B * Tq, A2_BLK, false, conv));
+  SKF_TRY(a2_map(&mdO64, dO, lddo, H, (int64_t)B * Tq, A2_BLK, false, conv));
+  SKF_TRY(a2_map(&mQ64mn, Q, ldq, H, (int64_t)B * Tq, A2_BLK, true, conv));
+  SKF_TRY(a2_map(&mdO64mn, dO, lddo, H, (int64_t)B * Tq, A2_BLK, true, conv));
+  Attn2Args a;
+  memset(&a, 0, sizeof(a));
+  a.H = H; a.Tq = Tq; a.Tk = Tk; a.mode = mode; a.scale = 1.0f / sqrtf((float)dh); a.key_pad = key_pad;
+  a.lse = lse; a.O = O; a.ldO = ldo; a.dO = dO; a.lddO = lddo;
+  {
+    const int smem = A2Q_DATA + 1024 + 128;
+    a.out0 = dQ; a.ld0 = lddq; a.out1 = delta;
+    dim3 grid(cdiv(Tq, 128), H, B);
+    if (x3) {
+      static bool done = false;
+      if (!done) { SKF_TRY(a2_attr(attn2_bwd_dq_k<true>, smem)); done = true; }
+      attn2_bwd_dq_k<true><<<grid, 128, smem, st>>>(mQ128, mdO128, mK64, mV64, mK64mn, a);
+    } else {
+      static bool done = false;
+      if (!done) { SKF_TRY(a2_attr(attn2_bwd_dq_k<false>, smem)); done = true; }
+      attn2_bwd_dq_k<false><<<grid, 128, smem, st>>>(mQ128, mdO128, mK64, mV64, mK64mn, a);
+    }
+    SKF_LAUNCH_CHECK();
+  }
+  {
+    const int smem = A2K_DATA + 1024 + 128;
+    a.out0 = dK; a.ld0 = lddk; a.out1 = dV; a.ld1 = lddv; a.delta = delta;
+    dim3 grid(cdiv(Tk, 128), H, B);
+    if (x3) {
+      static bool done = false;
+      if (!done) { SKF_TRY(a2_attr(attn2_bwd_dkv_k<true>, smem)); done = true; }
+      attn2_bwd_dkv_k<true><<<grid, 128, smem, st>>>(mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn, a);
+    } else {
+      static bool done = false;
+      if (!done) { SKF_TRY(a2_attr(attn2_bwd_dkv_k<false>, smem)); done = true; }
+      attn2_bwd_dkv_k<false><<<grid, 128, smem, st>>>(mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn, a);
+    }
+    SKF_LAUNCH_CHECK();
+  }
+  return SKF_OK;
+}
+
+}  // namespace skf

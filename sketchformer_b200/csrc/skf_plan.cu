@@ -28,6 +28,12 @@ int attn_fwd_tc(const float*, int64_t, const float*, int64_t, const float*, int6
 int attn_bwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
                 const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
                 const uint8_t*, int, int, int, int, int, int, cudaStream_t);
+int attn2_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
+int attn2_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
+              const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
+int attn2_bwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
+              const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
+              const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // parameter arena
@@ -348,9 +354,9 @@ static int attn_fwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
                         const float* V, int64_t ldv, float* O, int64_t ldo, float* lse, const uint8_t* pad,
                         int Tq, int Tk, int mode, cudaStream_t st) {
   const skf_cfg& c = P->c;
-  if (c.attn_backend == 0 && attn_tc_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
-    return attn_fwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode,
-                       c.gemm_precision >= 1 ? 1 : 0, st);
+  if (c.attn_backend == 0 && attn2_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
+    return attn2_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode,
+                     c.gemm_precision >= 1 ? 1 : 0, st);
   return attn_fwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode,
                        P->round_ops ? 1 : 0, st);
 }
@@ -359,9 +365,9 @@ static int attn_bwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
                         const float* lse, float* delta, float* dQ, int64_t lddq, float* dK, int64_t lddk,
                         float* dV, int64_t lddv, const uint8_t* pad, int Tq, int Tk, int mode, cudaStream_t st) {
   const skf_cfg& c = P->c;
-  if (c.attn_backend == 0 && c.gemm_precision < 2 && attn_tc_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
-    return attn_bwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad, c.B,
-                       c.H, Tq, Tk, c.d / c.H, mode, st);
+  if (c.attn_backend == 0 && attn2_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
+    return attn2_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad, c.B,
+                     c.H, Tq, Tk, c.d / c.H, mode, c.gemm_precision >= 2 ? 1 : 0, st);
   return attn_bwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad,
                        c.B, c.H, Tq, Tk, c.d / c.H, mode, P->round_ops ? 1 : 0, st);
 }
@@ -774,9 +780,13 @@ int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
 int skf_attn_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, float* O,
                  int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh,
                  int mask_mode, int round_tf32, int backend, void* stream) {
-  // backend: 0 = tcgen05 TF32, 2 = tcgen05 3xTF32 (fp32-accurate), 1 = SIMT fp32
+  // backend: 0 = tcgen05 flash kernels, single-pass TF32; 2 = the same with the 3xTF32 split (fp32-grade);
+  //          1 = SIMT fp32; 3 / 4 = first-generation one-shot tcgen05 kernel (TF32 / 3xTF32), kept for A/B runs
   if (backend == 0 || backend == 2)
-    return attn_fwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, backend == 2,
+    return attn2_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, backend == 2,
+                     as_stream(stream));
+  if (backend == 3 || backend == 4)
+    return attn_fwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, backend == 4,
                        as_stream(stream));
   return attn_fwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, round_tf32,
                        as_stream(stream));
@@ -786,7 +796,10 @@ int skf_attn_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
                  const float* O, int64_t ldo, const float* dO, int64_t lddo, const float* lse, float* delta,
                  float* dQ, int64_t lddq, float* dK, int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad,
                  int B, int H, int Tq, int Tk, int dh, int mask_mode, int round_tf32, int backend, void* stream) {
-  if (backend == 0)
+  if (backend == 0 || backend == 2)
+    return attn2_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B,
+                     H, Tq, Tk, dh, mask_mode, backend == 2, as_stream(stream));
+  if (backend == 3)
     return attn_bwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B,
                        H, Tq, Tk, dh, mask_mode, as_stream(stream));
   return attn_bwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad,

@@ -48,11 +48,26 @@ if what in ("attn", "all"):
     lse = torch.empty(B * H * T, device="cuda")
     delta = torch.empty_like(lse)
     pad = torch.zeros(B * T, dtype=torch.uint8, device="cuda")
-    for _ in range(reps):
+    def run(fb, bb, mode=1):
         _lib.check(lib.skf_attn_fwd(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d,
-                                    ptr(lse), ptr(pad), B, H, T, T, dh, 1, 0, 0, stream()))
-        _lib.check(lib.skf_attn_bwd(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d,
-                                    ptr(dO), d, ptr(lse), ptr(delta), ptr(dqkv), 3 * d, ptr(dqkv[:, d:]), 3 * d,
-                                    ptr(dqkv[:, 2 * d:]), 3 * d, ptr(pad), B, H, T, T, dh, 1, 0, 0, stream()))
+                                    ptr(lse), ptr(pad), B, H, T, T, dh, mode, 0, fb, stream()))
+        if bb >= 0:
+            _lib.check(lib.skf_attn_bwd(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d,
+                                        ptr(dO), d, ptr(lse), ptr(delta), ptr(dqkv), 3 * d, ptr(dqkv[:, d:]), 3 * d,
+                                        ptr(dqkv[:, 2 * d:]), 3 * d, ptr(pad), B, H, T, T, dh, mode, 0, bb, stream()))
+
+    for name, fb, bb in (("flash x3 fwd", 2, -1), ("flash x3 fwd+bwd", 2, 2), ("flash tf32 fwd", 0, -1),
+                         ("flash tf32 fwd+bwd", 0, 0), ("legacy x3 fwd", 4, -1), ("legacy fwd+bwd tf32", 3, 3)):
+        for mode in (1, 2):
+            for _ in range(reps):
+                run(fb, bb, mode)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                run(fb, bb, mode)
+            e1.record()
+            torch.cuda.synchronize()
+            print(f"attention {name:22s} mode {mode}: {e0.elapsed_time(e1) * 100:.1f} us")
 torch.cuda.synchronize()
 print("done")
