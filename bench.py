@@ -144,10 +144,12 @@ def main():
     if args.impl == "reference":
         return reference_main(args)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     from sketchformer_b200 import synth
-    from sketchformer_b200.engine import Engine, make_cfg
+    from sketchformer_b200.data import get_dataloader_by_name
+    from sketchformer_b200.model import get_model_by_name
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -157,39 +159,31 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     assert world == args.gpus or world == 1 and args.gpus == 1, "launch with torchrun for --gpus > 1"
 
+    # the reference-facing plugin API: registry names and hparam strings exactly as train.py passes them
     c = CFG2
-    eng = Engine(make_cfg(BATCH, c["max_seq_len"], c["d_model"], c["dff"], c["num_heads"], c["num_layers"],
-                          c["vocab_size"], c["n_classes"], c["lowerdim"], world_size=world,
-                          gemm_backend=args.backend, **({} if args.precision < 0 else {"gemm_precision": args.precision})),
-                 device=f"cuda:{local}")
-    # identical random-init weights on every rank (Keras default initialisers, seed 0)
-    from sketchformer_b200.init import init_params
-    eng.load_params(init_params(c, seed=0))
+    Model = get_model_by_name("sketch-transformer-tf2")
+    Loader = get_dataloader_by_name("stroke3-synthetic")
+    data_hps = Loader.parse_hparams(f"max_seq_len={c['max_seq_len']}")
+    model_hps = Model.parse_hparams(base=f"batch_size={BATCH}",
+                                    specific=f"num_layers={c['num_layers']},d_model={c['d_model']},dff={c['dff']},"
+                                             f"num_heads={c['num_heads']},lowerdim={c['lowerdim']},dropout_rate=0.0")
+    dataset = Loader(data_hps, None, n_classes=c["n_classes"], seed=1234 + 1000 * rank)
+    model = Model(model_hps, dataset, None, "bench", device=f"cuda:{local}", world_size=world, seed=0,
+                  gemm_precision=None if args.precision < 0 else args.precision)
+    eng = model._train_engine           # identical random-init weights on every rank (Keras initialisers, seed 0)
 
-    NB = 8   # distinct synthetic batches per rank, resident in HBM (value) / pinned host memory (e2e)
-    host = [synth.token_batch(BATCH, c["max_seq_len"], c["n_classes"], 1234 + 1000 * rank + i) for i in range(NB)]
-    pin_x = [torch.from_numpy(x).pin_memory() for x, _ in host]
-    pin_y = [torch.from_numpy(y).pin_memory() for _, y in host]
-    dev_x = [x.cuda(non_blocking=True) for x in pin_x]
-    dev_y = [y.cuda(non_blocking=True) for y in pin_y]
-    stage_x, stage_y = torch.empty_like(dev_x[0]), torch.empty_like(dev_y[0])
-    stats_host = torch.empty(16, dtype=torch.float64).pin_memory()
+    NB = 8   # distinct synthetic batches per rank: resident in HBM (value) / host numpy arrays (e2e)
+    it = dataset.batch_iterator("train", BATCH)
+    host = [next(it) for _ in range(NB)]
+    dev_x = [torch.from_numpy(x).cuda() for x, _ in host]
+    dev_y = [torch.from_numpy(y).cuda() for _, y in host]
+    last = {}
 
     def step(i, e2e=False):
-        if e2e:
-            stage_x.copy_(pin_x[i % NB], non_blocking=True)
-            stage_y.copy_(pin_y[i % NB], non_blocking=True)
-            x, y = stage_x, stage_y
-        else:
-            x, y = dev_x[i % NB], dev_y[i % NB]
-        if world > 1:
-            eng.train_step(x, y, apply_adam=False)
-            dist.all_reduce(eng.grads)            # NCCL sum over NVLink; 1/world folded into Adam
-            eng.apply_adam()
-        else:
-            eng.train_step(x, y, apply_adam=True)
-        if e2e:
-            stats_host.copy_(eng.tensor("stats_run", dtype=torch.float64), non_blocking=True)
+        if e2e:       # public API, host buffers in, metrics dict (floats on the host) out
+            last.update(model.train_on_batch(host[i % NB]))
+        else:         # inputs already resident in HBM, no device->host read
+            model.train_on_batch((dev_x[i % NB], dev_y[i % NB]), sync_metrics=False)
 
     host_ms = [0.0]
 
@@ -211,43 +205,46 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for i in range(args.warmup):
+    for i in range(args.warmup):          # >= 3: two eager steps, then the CUDA graph is captured and replayed
         step(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = eng.launches()
     ms = timed(args.steps)
-    launches = eng.launches() - l0
     host_submit_ms = host_ms[0] / args.steps
     for i in range(2):
         step(i, True)
     ms_e2e = timed(args.steps, e2e=True)
     sampler.stop_flag = True
-    loss_after = float(stats_host[12])
+    launches_per_step = getattr(eng, "graph_launches", 0) + (0 if world == 1 else 2)
 
     value = world * BATCH * args.steps / (ms / 1e3)
     e2e_value = world * BATCH * args.steps / (ms_e2e / 1e3)
     peaks, peak_src = load_peaks()
+    precision = int(eng.cfg.gemm_precision)
 
-    # roofline of the dominant kernel (the tcgen05 TF32 GEMM): CUDA events around every launch of the
-    # FFN-1 GEMM shape through the C ABI, on this stream, after the timed region
-    roof = gemm_roofline(eng, c, peaks, peak_src, args.backend)
+    # roofline of the dominant kernel (the persistent tcgen05 GEMM): CUDA events around launches of the FFN-1
+    # shape through the C ABI, on this stream, after the timed region
+    roof = gemm_roofline(eng, c, peaks, peak_src, 2 if precision >= 1 else 0)
     roof["step_core_tflops"] = value / world * core_flops_per_sketch() / 1e12
     roof["step_frac_of_tf32_peak"] = roof["step_core_tflops"] / (peaks["bf16_tflops_sustained"] / 2)
 
     if rank == 0:
+        mode = {0: "tf32 single pass everywhere", 1: "3xTF32 forward, TF32 backward",
+                2: "3xTF32 (fp32-grade) forward and backward"}.get(precision, str(precision))
         line = {"metric": "sketches/sec", "value": value, "unit": "sketches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.backend == 0 else "f32",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "parallelism": f"dp{world}", "global_batch": BATCH * world,
                            "l2": "per-step working set 3.5 GB (activations saved for backward) >> 126 MB L2; 8 distinct batches",
-                           "gemm_backend": "tcgen05 kind::tf32" if args.backend == 0 else "simt fp32"},
+                           "precision": mode, "cuda_graph": bool(getattr(eng, "_graph", None)),
+                           "api": "sketchformer_b200.model.Transformer.train_on_batch (reference models/sketchformer.py:351)"},
                 "e2e": {"value": e2e_value, "unit": "sketches/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": BATCH * c["max_seq_len"] * 8 + BATCH * 8, "d2h_bytes_per_step": 128,
-                        "last_total_loss": loss_after},
-                "gpu_launches": launches, "host_submit_ms_per_step": host_submit_ms, "clocks": sampler.summary(), "roofline": roof}
+                        "last_total_loss": last.get("total_loss")},
+                "gpu_launches": launches_per_step * args.steps, "host_submit_ms_per_step": host_submit_ms,
+                "clocks": sampler.summary(), "roofline": roof}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_steps(2, 1, budget_s=25.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": "sketches/s", "cores": r["cores"], "kind": "port",
@@ -260,7 +257,8 @@ def main():
 
 def gemm_roofline(eng, c, peaks, peak_src, backend):
     """achieved TFLOP/s of the dominant kernel on its own stream (CUDA events), FFN-1 shape of cfg2:
-    [B*T, d] x [d, dff] + bias + ReLU = 2*25600*256*1024 = 13.42 GFLOP per launch."""
+    [B*T, d] x [d, dff] + bias + ReLU = 2*25600*256*1024 = 13.42 algorithmic GFLOP per launch.
+    backend 2 = 3xTF32 (three tensor-core passes per algorithmic FLOP), 0 = single-pass TF32."""
     import torch
     from sketchformer_b200.ops import gemm
     M, K, N = BATCH * c["max_seq_len"], c["d_model"], c["dff"]
@@ -282,9 +280,12 @@ def gemm_roofline(eng, c, peaks, peak_src, backend):
     flops = 2.0 * M * N * K
     achieved = flops / (us * 1e-6) / 1e12
     peak = peaks["bf16_tflops"] / 2
-    return {"bound": "tensor", "kernel": "gemm_tc_k<256,false,true> (FFN-1: 25600x256x1024, bias+ReLU epilogue)",
+    passes = 3 if backend == 2 else 1
+    return {"bound": "tensor", "kernel": f"gemm2_k<256,false,true,{'true' if backend == 2 else 'false'}> "
+                                         "(FFN-1: 25600x256x1024, bias+ReLU epilogue)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "us_per_launch": us, "flops_per_launch": flops,
+            "us_per_launch": us, "flops_per_launch": flops, "mma_passes": passes,
+            "tensor_pipe_tflops": achieved * passes, "tensor_pipe_frac": achieved * passes / peak,
             "peak_source": peak_src + "; TF32 = 1/2 of the bf16 burst figure",
             "hbm_algorithmic_bytes": 4.0 * (M * K + K * N + M * N)}
 

@@ -153,6 +153,33 @@ class Engine:
         check(self.lib.skf_train_step(self._plan, C.c_void_p(tokens.data_ptr()), C.c_void_p(labels.data_ptr()),
                                       int(apply_adam), self._stream()), "skf_train_step")
 
+    # ---- CUDA-graph replay of the whole step ------------------------------------------------------
+    def capture_train_step(self, apply_adam=True):
+        """Capture fwd + losses + bwd (+ Adam) into a CUDA graph that reads the static buffers
+        `self.graph_tokens` / `self.graph_labels`.  The ~280 kernel launches of a step then cost one
+        cudaGraphLaunch on the host.  Call after at least one eager step (function attributes, TMEM and
+        tensor-map encoders are initialised lazily)."""
+        if getattr(self, "_graph", None) is not None and self._graph_adam == bool(apply_adam):
+            return self._graph
+        B, T = self.cfg.B, self.cfg.T
+        self.graph_tokens = torch.zeros(B, T, dtype=torch.int64, device=self.device)
+        self.graph_labels = torch.zeros(B, 1, dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        l0 = self.launches()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.train_step(self.graph_tokens, self.graph_labels, apply_adam)
+        self.graph_launches = self.launches() - l0     # kernels per replay
+        self._graph, self._graph_adam = g, bool(apply_adam)
+        return g
+
+    def replay_train_step(self, tokens=None, labels=None):
+        """Copy a device batch into the static buffers (if given) and replay the captured step."""
+        if tokens is not None:
+            self.graph_tokens.copy_(tokens, non_blocking=True)
+            self.graph_labels.copy_(labels.view(self.cfg.B, 1), non_blocking=True)
+        self._graph.replay()
+
     def apply_adam(self):
         check(self.lib.skf_apply_adam(self._plan, self._stream()), "skf_apply_adam")
 

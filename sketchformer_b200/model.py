@@ -61,7 +61,7 @@ class Transformer:
 
     # ---- construction ----------------------------------------------------------------------
     def __init__(self, hps, dataset, out_dir=None, experiment_id="0", device="cuda:0", world_size=1, seed=0,
-                 gemm_precision=None):
+                 gemm_precision=None, use_cuda_graph=True):
         self.hps = hps if isinstance(hps, dict) else dict(hps.values())
         self.dataset = dataset
         self.experiment_id = experiment_id
@@ -83,6 +83,7 @@ class Transformer:
         self._world = world_size
         self._seed = seed
         self._precision = gemm_precision
+        self._use_graph = use_cuda_graph
         self._engines = {}
         self._stage = {}
         self.build_model()
@@ -158,6 +159,25 @@ class Transformer:
         ev.record()
         return dev
 
+    def _h2d_into(self, key, arr, dtype, dst):
+        """Host batch -> pinned ring slot -> the graph's static device buffer `dst`."""
+        t = torch.as_tensor(np.ascontiguousarray(arr)) if not torch.is_tensor(arr) else arr
+        if t.is_cuda:
+            dst.copy_(t.to(dtype).view(dst.shape), non_blocking=True)
+            return
+        t = t.to(dtype).view(dst.shape)
+        ring = self._stage.setdefault(("g" + key, tuple(t.shape)), {"slots": [], "next": 0})
+        if len(ring["slots"]) < 3:
+            ring["slots"].append((torch.empty(t.shape, dtype=dtype).pin_memory(), torch.cuda.Event()))
+            host, ev = ring["slots"][-1]
+        else:
+            host, ev = ring["slots"][ring["next"]]
+            ring["next"] = (ring["next"] + 1) % len(ring["slots"])
+            ev.synchronize()
+        host.copy_(t)
+        dst.copy_(host, non_blocking=True)
+        ev.record()
+
     # ---- training --------------------------------------------------------------------------
     def train_on_batch(self, batch, sync_metrics=True):
         """models/sketchformer.py:351-359: `inp = tar = data`; returns the running-mean quick metrics
@@ -167,15 +187,35 @@ class Transformer:
         eng = self._engine(B, training=True)
         if self.hps["dropout_rate"] != 0.0:
             raise NotImplementedError("dropout_rate != 0 is not built yet (parity runs use dropout_rate=0)")
-        x = self._to_device("x", data, torch.int64 if not self.continuous else torch.float32)
-        y = self._to_device("y", labels, torch.int64)
-        if eng is not self._train_engine:          # odd batch size: same arenas, carry the optimizer step over
-            eng.set_step(self._train_engine.step_count())
-        eng.train_step(x, y, apply_adam=True)
-        if eng is not self._train_engine:
-            self._train_engine.set_step(eng.step_count())
+        dt = torch.int64 if not self.continuous else torch.float32
+        solo = self._world == 1           # data parallel: gradients are all-reduced before the optimizer
+        if self._use_graph and eng is self._train_engine and self.current_step >= 2:
+            # steady state: pinned host -> static device buffers -> one cudaGraphLaunch for the whole step
+            eng.capture_train_step(apply_adam=solo)
+            self._h2d_into("x", data, dt, eng.graph_tokens)
+            self._h2d_into("y", labels, torch.int64, eng.graph_labels)
+            eng.replay_train_step()
+        else:
+            x = self._to_device("x", data, dt)
+            y = self._to_device("y", labels, torch.int64)
+            if eng is not self._train_engine:          # odd batch size: same arenas, carry the optimizer step over
+                eng.set_step(self._train_engine.step_count())
+            eng.train_step(x, y, apply_adam=solo)
+            if eng is not self._train_engine and solo:
+                self._train_engine.set_step(eng.step_count())
+        if not solo:
+            self._allreduce_and_step(eng)
         self.current_step += 1
         return eng.metrics() if sync_metrics else None
+
+    def _allreduce_and_step(self, eng):
+        """sum the flat gradient arena over the ranks (NCCL over NVLink; 1/world is folded
+        into the Adam kernel), then the optimizer.  The reference has no multi-GPU path."""
+        import torch.distributed as dist
+        dist.all_reduce(eng.grads)
+        eng.apply_adam()
+        if eng is not self._train_engine:
+            self._train_engine.set_step(eng.step_count())
 
     def prepare_for_start_of_epoch(self):
         pass
