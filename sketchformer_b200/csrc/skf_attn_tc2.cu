@@ -58,7 +58,7 @@ __device__ __forceinline__ bool a2_masked(int mode, int qi, int kj, int padj) {
 
 // lo = x - trunc_tf32(x), elementwise over a tile (the raw and lo tiles share their swizzled layout)
 __device__ __forceinline__ void a2_split(const uint8_t* raw, uint8_t* lo, int bytes) {
-  for (int i = threadIdx.x * 16; i < bytes; i += 128 * 16) {
+  for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16) {
     const float4 v = *reinterpret_cast<const float4*>(raw + i);
     float4 l;
     l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -294,12 +294,22 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
 }
 
 // ---------------------------------------------------------------------------------------------------
-// backward, dQ.  smem: Q | Ql | dO | dOl | K | Kl | X | Xl | pad[256] | barriers   (X = V block, then the
+// backward kernels: 256 threads = two warpgroups over the same 128 TMEM lanes; warpgroup g owns columns
+// [32g, 32g+32) of every 64-column block, so the row math of a block is spread over 8 warps.
+// The logits are handled in the log2 domain: t = S * (scale*log2e) + bias, p = exp2(t - lse*log2e), where
+// bias carries the reference's additive -1e9 mask (builders/utils.py:93-97) for padded keys and -inf for
+// keys / queries outside the sequence.  dS is accumulated WITHOUT the trailing 1/sqrt(dh), which is
+// applied once to the dQ / dK accumulators in the epilogue.
+// ---------------------------------------------------------------------------------------------------
+constexpr float A2_LOG2E = 1.4426950408889634f;
+
+// ---------------------------------------------------------------------------------------------------
+// backward, dQ.  smem: Q | Ql | dO | dOl | K | Kl | X | Xl | bias[256] | barriers   (X = V block, then the
 // MN-major copy of the K block).   tmem: S [0,64)  dP -> dS [64,128)  dQ [128,160)
 // ---------------------------------------------------------------------------------------------------
-constexpr int A2Q_DATA = 4 * A2_T128 + 4 * A2_T64 + A2_MAXT;
+constexpr int A2Q_DATA = 4 * A2_T128 + 4 * A2_T64 + A2_MAXT * 4;
 template <bool X3>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mdO,
                const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
                const __grid_constant__ CUtensorMap mKmn, const Attn2Args a) {
@@ -307,14 +317,14 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
   A2Common c;
   a2_prologue<256>(c, smem_raw, A2Q_DATA);
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, row = tid & 127;
   const uint32_t sQ = c.base, sQl = sQ + A2_T128, sdO = sQl + A2_T128, sdOl = sdO + A2_T128, sK = sdOl + A2_T128,
                  sKl = sK + A2_T64, sX = sKl + A2_T64, sXl = sX + A2_T64;
   uint8_t* gQ = c.gen;
   uint8_t* gdO = gQ + 2 * A2_T128;
   uint8_t* gK = gdO + 2 * A2_T128;
   uint8_t* gX = gK + 2 * A2_T64;
-  uint8_t* pad_s = gX + 2 * A2_T64;
+  float* bias_s = reinterpret_cast<float*>(gX + 2 * A2_T64);
   const uint32_t bar_q = c.bar0, bar_k = c.bar0 + 8, bar_v = c.bar0 + 16, bar_x = c.bar0 + 24, bar_s = c.bar0 + 32,
                  bar_o = c.bar0 + 40;
   const int kmax = a.mode == 2 ? min(a.Tk, q0 + 128) : a.Tk;
@@ -329,11 +339,15 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
     mbar_arrive_expect_tx(bar_v, A2_T64);
     tma_load_2d(sX, &mV, bar_v, h * A2_DH, b * a.Tk);
   }
-  for (int i = tid; i < A2_MAXT; i += 128)
-    pad_s[i] = (a.key_pad && i < a.Tk) ? a.key_pad[(int64_t)b * a.Tk + i] : 0;
+  for (int i = tid; i < A2_MAXT; i += 256) {
+    float bj = 0.f;
+    if (i >= a.Tk) bj = -INFINITY;
+    else if (a.mode >= 1 && a.key_pad && a.key_pad[(int64_t)b * a.Tk + i]) bj = A2_MASK_NEG * A2_LOG2E;
+    bias_s[i] = bj;
+  }
   // delta_i = sum_c dO[i,c] O[i,c]  (row per thread, 128 B each from global)
-  const int qi = q0 + tid;
-  float delta = 0.f, lse = 0.f;
+  const int qi = q0 + row;
+  float delta = 0.f, lse2 = INFINITY;       // rows past the sequence: p = exp2(-inf) = 0
   if (qi < a.Tq) {
     const float4* o4 = reinterpret_cast<const float4*>(a.O + ((int64_t)b * a.Tq + qi) * a.ldO + h * A2_DH);
     const float4* g4 = reinterpret_cast<const float4*>(a.dO + ((int64_t)b * a.Tq + qi) * a.lddO + h * A2_DH);
@@ -342,8 +356,8 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
       const float4 o = o4[jj], g = g4[jj];
       delta += (o.x * g.x + o.y * g.y) + (o.z * g.z + o.w * g.w);
     }
-    lse = a.lse[((int64_t)b * a.H + h) * a.Tq + qi];
-    a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = delta;
+    lse2 = a.lse[((int64_t)b * a.H + h) * a.Tq + qi] * A2_LOG2E;
+    if (wg == 0) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = delta;
   }
   mbar_wait(bar_q, 0);
   if (X3) {
@@ -351,9 +365,11 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
     a2_split(gdO, gdO + A2_T128, A2_T128);
   }
   const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdQ = c.tmem + 128;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
   const uint32_t idesc_o = make_idesc_tf32(128, A2_DH, 0, 1);
+  const float c1 = a.scale * A2_LOG2E;
+  const int qw = q0 + (warp & 3) * 32;      // first query row of this warp
 
   for (int j = 0; j < nblk; j++) {
     const uint32_t ph = (uint32_t)j & 1u;
@@ -382,25 +398,23 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
         tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk + k0 + A2_BLK);
       }
     }
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
+    {
       uint32_t rs[32], rp[32];
+      const int kc = k0 + wg * 32;          // first key column of this thread's half block
       __syncwarp();
-      tmem_ld32(tS + lane_off + half * 32, rs);
-      tmem_ld32(tdP + lane_off + half * 32, rp);
+      tmem_ld32(tS + lane_off + wg * 32, rs);
+      tmem_ld32(tdP + lane_off + wg * 32, rp);
       tmem_ld_wait();
+      const bool diag = a.mode == 2 && kc + 31 > qw;      // warp-uniform: some (q, k) pair has k > q
 #pragma unroll
       for (int jj = 0; jj < 32; jj++) {
-        const int kj = k0 + half * 32 + jj;
-        float s = __uint_as_float(rs[jj]) * a.scale;
-        if (a2_masked(a.mode, qi, kj, pad_s[kj & (A2_MAXT - 1)])) s += A2_MASK_NEG;
-        const bool ok = kj < a.Tk && qi < a.Tq;
-        const float p = ok ? __expf(s - lse) : 0.f;
-        const float ds = ok ? p * (__uint_as_float(rp[jj]) - delta) * a.scale : 0.f;
-        rp[jj] = __float_as_uint(round_tf32(ds));
+        float t = fmaf(__uint_as_float(rs[jj]), c1, bias_s[kc + jj]);
+        if (diag && kc + jj > qi) t += A2_MASK_NEG * A2_LOG2E;
+        const float p = exp2f(t - lse2);
+        rp[jj] = __float_as_uint(round_tf32(p * (__uint_as_float(rp[jj]) - delta)));
       }
       __syncwarp();
-      tmem_st32(tdP + lane_off + half * 32, rp);
+      tmem_st32(tdP + lane_off + wg * 32, rp);
     }
     tmem_st_wait();
     mbar_wait(bar_x, ph);
@@ -420,7 +434,7 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
       tma_load_2d(sX, &mV, bar_v, h * A2_DH, b * a.Tk + k0 + A2_BLK);
     }
   }
-  {
+  if (wg == 0) {
     uint32_t r[32];
     __syncwarp();
     tmem_ld32(tdQ + lane_off, r);
@@ -429,21 +443,21 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
       float4* dst = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tq + qi) * a.ld0 + h * A2_DH);
 #pragma unroll
       for (int jj = 0; jj < 8; jj++)
-        dst[jj] = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
-                              __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
+        dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * a.scale, __uint_as_float(r[4 * jj + 1]) * a.scale,
+                              __uint_as_float(r[4 * jj + 2]) * a.scale, __uint_as_float(r[4 * jj + 3]) * a.scale);
     }
   }
   a2_free<256>(c);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// backward, dK / dV.  smem: K | Kl | V | Vl | A | Al | B | Bl | lse[256] | delta[256] | barriers
+// backward, dK / dV.  smem: K | Kl | V | Vl | A | Al | B | Bl | lse2[256] | delta[256] | barriers
 //   (A, B = Q block, dO block K-major for the score MMAs, then their MN-major copies for the output MMAs)
 // tmem: S^T -> P^T [0,64)  dP^T -> dS^T [64,128)  dV [128,160)  dK [160,192)
 // ---------------------------------------------------------------------------------------------------
 constexpr int A2K_DATA = 4 * A2_T128 + 4 * A2_T64 + 2 * A2_MAXT * 4;
 template <bool X3>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
                 const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mdO,
                 const __grid_constant__ CUtensorMap mQmn, const __grid_constant__ CUtensorMap mdOmn,
@@ -452,14 +466,14 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
   A2Common c;
   a2_prologue<256>(c, smem_raw, A2K_DATA);
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * 128;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, row = tid & 127;
   const uint32_t sK = c.base, sKl = sK + A2_T128, sV = sKl + A2_T128, sVl = sV + A2_T128, sA = sVl + A2_T128,
                  sAl = sA + A2_T64, sB = sAl + A2_T64, sBl = sB + A2_T64;
   uint8_t* gK = c.gen;
   uint8_t* gV = gK + 2 * A2_T128;
   uint8_t* gA = gV + 2 * A2_T128;
   uint8_t* gB = gA + 2 * A2_T64;
-  float* lse_s = reinterpret_cast<float*>(gB + 2 * A2_T64);
+  float* lse_s = reinterpret_cast<float*>(gB + 2 * A2_T64);     // lse * log2e, +inf for queries past the sequence
   float* del_s = lse_s + A2_MAXT;
   const uint32_t bar_q = c.bar0, bar_a = c.bar0 + 8, bar_b = c.bar0 + 16, bar_s = c.bar0 + 24, bar_o = c.bar0 + 32;
   const int nqb = (a.Tq + A2_BLK - 1) / A2_BLK;
@@ -475,21 +489,25 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
       tma_load_2d(sB, &mdO, bar_a, h * A2_DH, b * a.Tq + ib0 * A2_BLK);
     }
   }
-  for (int i = tid; i < A2_MAXT; i += 128) {
-    lse_s[i] = i < a.Tq ? a.lse[((int64_t)b * a.H + h) * a.Tq + i] : 0.f;
+  for (int i = tid; i < A2_MAXT; i += 256) {
+    lse_s[i] = i < a.Tq ? a.lse[((int64_t)b * a.H + h) * a.Tq + i] * A2_LOG2E : INFINITY;
     del_s[i] = i < a.Tq ? a.delta[((int64_t)b * a.H + h) * a.Tq + i] : 0.f;
   }
-  const int kj = j0 + tid;
-  const int padj = (a.key_pad && kj < a.Tk) ? a.key_pad[(int64_t)b * a.Tk + kj] : 0;
+  const int kj = j0 + row;
+  float bias = 0.f;                                   // this thread's key: -inf outside the sequence, -1e9 if padded
+  if (kj >= a.Tk) bias = -INFINITY;
+  else if (a.mode >= 1 && a.key_pad && a.key_pad[(int64_t)b * a.Tk + kj]) bias = A2_MASK_NEG * A2_LOG2E;
   mbar_wait(bar_q, 0);
   if (X3) {
     a2_split(gK, gK + A2_T128, A2_T128);
     a2_split(gV, gV + A2_T128, A2_T128);
   }
   const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdV = c.tmem + 128, tdK = c.tmem + 160;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
   const uint32_t idesc_o = make_idesc_tf32(128, A2_DH, 0, 1);
+  const float c1 = a.scale * A2_LOG2E;
+  const int kw = j0 + (warp & 3) * 32;               // first key of this warp
 
   int it = 0;
   for (int ib = ib0; ib < nqb; ib++, it++) {
@@ -515,27 +533,25 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
       tma_load_2d(sA, &mQmn, bar_b, h * A2_DH, b * a.Tq + i0);
       tma_load_2d(sB, &mdOmn, bar_b, h * A2_DH, b * a.Tq + i0);
     }
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
+    {
       uint32_t rs[32], rp[32];
+      const int qc = i0 + wg * 32;          // first query column of this thread's half block
       __syncwarp();
-      tmem_ld32(tS + lane_off + half * 32, rs);
-      tmem_ld32(tdP + lane_off + half * 32, rp);
+      tmem_ld32(tS + lane_off + wg * 32, rs);
+      tmem_ld32(tdP + lane_off + wg * 32, rp);
       tmem_ld_wait();
+      const bool diag = a.mode == 2 && kw + 31 > qc;      // warp-uniform: some (q, k) pair has k > q
 #pragma unroll
       for (int jj = 0; jj < 32; jj++) {
-        const int qi = i0 + half * 32 + jj;
-        float s = __uint_as_float(rs[jj]) * a.scale;
-        if (a2_masked(a.mode, qi, kj, padj)) s += A2_MASK_NEG;
-        const bool ok = kj < a.Tk && qi < a.Tq;
-        const float p = ok ? __expf(s - lse_s[qi & (A2_MAXT - 1)]) : 0.f;
-        const float ds = ok ? p * (__uint_as_float(rp[jj]) - del_s[qi & (A2_MAXT - 1)]) * a.scale : 0.f;
+        float t = fmaf(__uint_as_float(rs[jj]), c1, bias);
+        if (diag && kj > qc + jj) t += A2_MASK_NEG * A2_LOG2E;
+        const float p = exp2f(t - lse_s[qc + jj]);
         rs[jj] = __float_as_uint(round_tf32(p));
-        rp[jj] = __float_as_uint(round_tf32(ds));
+        rp[jj] = __float_as_uint(round_tf32(p * (__uint_as_float(rp[jj]) - del_s[qc + jj])));
       }
       __syncwarp();
-      tmem_st32(tS + lane_off + half * 32, rs);
-      tmem_st32(tdP + lane_off + half * 32, rp);
+      tmem_st32(tS + lane_off + wg * 32, rs);
+      tmem_st32(tdP + lane_off + wg * 32, rp);
     }
     tmem_st_wait();
     mbar_wait(bar_b, ph);
@@ -561,26 +577,24 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
     }
   }
   {
-    uint32_t rv[32], rk[32];
+    // warpgroup 0 stores dK (scaled by 1/sqrt(dh)), warpgroup 1 stores dV
+    uint32_t r[32];
     __syncwarp();
     if (it > 0) {
-      tmem_ld32(tdV + lane_off, rv);
-      tmem_ld32(tdK + lane_off, rk);
+      tmem_ld32((wg == 0 ? tdK : tdV) + lane_off, r);
       tmem_ld_wait();
     } else {
 #pragma unroll
-      for (int jj = 0; jj < 32; jj++) rv[jj] = rk[jj] = 0u;
+      for (int jj = 0; jj < 32; jj++) r[jj] = 0u;
     }
     if (kj < a.Tk) {
-      float4* dk = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tk + kj) * a.ld0 + h * A2_DH);
-      float4* dv = reinterpret_cast<float4*>(a.out1 + ((int64_t)b * a.Tk + kj) * a.ld1 + h * A2_DH);
+      const float sc = wg == 0 ? a.scale : 1.0f;
+      float* base = wg == 0 ? a.out0 + ((int64_t)b * a.Tk + kj) * a.ld0 : a.out1 + ((int64_t)b * a.Tk + kj) * a.ld1;
+      float4* dst = reinterpret_cast<float4*>(base + h * A2_DH);
 #pragma unroll
-      for (int jj = 0; jj < 8; jj++) {
-        dk[jj] = make_float4(__uint_as_float(rk[4 * jj]), __uint_as_float(rk[4 * jj + 1]),
-                             __uint_as_float(rk[4 * jj + 2]), __uint_as_float(rk[4 * jj + 3]));
-        dv[jj] = make_float4(__uint_as_float(rv[4 * jj]), __uint_as_float(rv[4 * jj + 1]),
-                             __uint_as_float(rv[4 * jj + 2]), __uint_as_float(rv[4 * jj + 3]));
-      }
+      for (int jj = 0; jj < 8; jj++)
+        dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * sc, __uint_as_float(r[4 * jj + 1]) * sc,
+                              __uint_as_float(r[4 * jj + 2]) * sc, __uint_as_float(r[4 * jj + 3]) * sc);
     }
   }
   a2_free<256>(c);
@@ -670,11 +684,11 @@ int attn2_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
     if (x3) {
       static bool done = false;
       if (!done) { SKF_TRY(a2_attr(attn2_bwd_dq_k<true>, smem)); done = true; }
-      attn2_bwd_dq_k<true><<<grid, 128, smem, st>>>(mQ128, mdO128, mK64, mV64, mK64mn, a);
+      attn2_bwd_dq_k<true><<<grid, 256, smem, st>>>(mQ128, mdO128, mK64, mV64, mK64mn, a);
     } else {
       static bool done = false;
       if (!done) { SKF_TRY(a2_attr(attn2_bwd_dq_k<false>, smem)); done = true; }
-      attn2_bwd_dq_k<false><<<grid, 128, smem, st>>>(mQ128, mdO128, mK64, mV64, mK64mn, a);
+      attn2_bwd_dq_k<false><<<grid, 256, smem, st>>>(mQ128, mdO128, mK64, mV64, mK64mn, a);
     }
     SKF_LAUNCH_CHECK();
   }
@@ -685,11 +699,11 @@ int attn2_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
     if (x3) {
       static bool done = false;
       if (!done) { SKF_TRY(a2_attr(attn2_bwd_dkv_k<true>, smem)); done = true; }
-      attn2_bwd_dkv_k<true><<<grid, 128, smem, st>>>(mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn, a);
+      attn2_bwd_dkv_k<true><<<grid, 256, smem, st>>>(mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn, a);
     } else {
       static bool done = false;
       if (!done) { SKF_TRY(a2_attr(attn2_bwd_dkv_k<false>, smem)); done = true; }
-      attn2_bwd_dkv_k<false><<<grid, 128, smem, st>>>(mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn, a);
+      attn2_bwd_dkv_k<false><<<grid, 256, smem, st>>>(mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn, a);
     }
     SKF_LAUNCH_CHECK();
   }

@@ -85,8 +85,9 @@ __global__ void pad_flags_k(const int64_t* __restrict__ tok, int64_t tok_ld,
 // residual add + LayerNormalization(eps=1e-6)   (transformer.py:217-218, 222, 250-260)
 // one warp per row; the row lives in registers (d <= 1024)
 // ---------------------------------------------------------------------------------------------
-constexpr int LN_MAX_VEC = 8;  // float4 per lane -> d <= 1024
+constexpr int LN_MAX_VEC = 8;  // float4 per lane -> d <= 1024 (kernels are instantiated for 1, 2, 4, 8)
 
+template <int LN_NV>
 __global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restrict__ b,
                              const float* __restrict__ bias, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float* __restrict__ s_out,
@@ -96,10 +97,10 @@ __global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restric
   if (row >= rows) return;
   int lane = threadIdx.x;
   int nv = d / 4;
-  float4 v[LN_MAX_VEC];
+  float4 v[LN_NV];
   float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; k++) {
+  for (int k = 0; k < LN_NV; k++) {
     int c = lane + k * 32;
     if (c < nv) {
       float4 x = reinterpret_cast<const float4*>(a + (int64_t)row * d)[c];
@@ -119,7 +120,7 @@ __global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restric
   float mean = sum / (float)d;
   float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; k++) {
+  for (int k = 0; k < LN_NV; k++) {
     int c = lane + k * 32;
     if (c < nv) {
       float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
@@ -129,7 +130,7 @@ __global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restric
   sq = warp_sum(sq);
   float rstd = 1.0f / sqrtf(sq / (float)d + 1e-6f);
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; k++) {
+  for (int k = 0; k < LN_NV; k++) {
     int c = lane + k * 32;
     if (c < nv) {
       float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
@@ -151,7 +152,8 @@ __global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restric
 
 // LayerNorm backward.  Each block walks rows blockIdx.x, +gridDim.x, ...; one warp per row;
 // dgamma/dbeta partials stay in registers across the walk, then smem -> one atomic per column.
-__global__ void ln_bwd_k(const float* __restrict__ dy, const float* __restrict__ s,
+template <int LN_NV>
+__global__ void __launch_bounds__(256) ln_bwd_k(const float* __restrict__ dy, const float* __restrict__ s,
                          const float* __restrict__ mean, const float* __restrict__ rstd,
                          const float* __restrict__ gamma, float* __restrict__ ds,
                          float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d,
@@ -159,17 +161,17 @@ __global__ void ln_bwd_k(const float* __restrict__ dy, const float* __restrict__
   extern __shared__ float sm[];  // [2][d]
   int lane = threadIdx.x, w = threadIdx.y, nw = blockDim.y;
   int nv = d / 4;
-  float4 ag[LN_MAX_VEC], ab[LN_MAX_VEC];
+  float4 ag[LN_NV], ab[LN_NV];
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; k++) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < LN_NV; k++) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c = threadIdx.y * 32 + lane; c < 2 * d; c += nw * 32) sm[c] = 0.f;
   __syncthreads();
   for (int row = blockIdx.x * nw + w; row < rows; row += gridDim.x * nw) {
     float mu = mean[row], rs = rstd[row];
-    float4 g[LN_MAX_VEC], xh[LN_MAX_VEC];
+    float4 g[LN_NV], xh[LN_NV];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < LN_MAX_VEC; k++) {
+    for (int k = 0; k < LN_NV; k++) {
       int c = lane + k * 32;
       if (c < nv) {
         float4 dyv = reinterpret_cast<const float4*>(dy + (int64_t)row * d)[c];
@@ -187,7 +189,7 @@ __global__ void ln_bwd_k(const float* __restrict__ dy, const float* __restrict__
     c1 = warp_sum(c1) / (float)d;
     c2 = warp_sum(c2) / (float)d;
 #pragma unroll
-    for (int k = 0; k < LN_MAX_VEC; k++) {
+    for (int k = 0; k < LN_NV; k++) {
       int c = lane + k * 32;
       if (c < nv) {
         float4 o;
@@ -200,7 +202,7 @@ __global__ void ln_bwd_k(const float* __restrict__ dy, const float* __restrict__
     }
   }
 #pragma unroll
-  for (int k = 0; k < LN_MAX_VEC; k++) {
+  for (int k = 0; k < LN_NV; k++) {
     int c = lane + k * 32;
     if (c < nv) {
       atomicAdd(&sm[c * 4 + 0], ag[k].x); atomicAdd(&sm[c * 4 + 1], ag[k].y);
@@ -216,21 +218,52 @@ __global__ void ln_bwd_k(const float* __restrict__ dy, const float* __restrict__
   }
 }
 
-// out[n] += sum_m x[m,n]   (bias gradients).  block (32,8): 32 consecutive columns x 8 row lanes
-__global__ void colsum_k(const float* __restrict__ x, int64_t ldx, float* __restrict__ out,
-                         int M, int N) {
-  __shared__ float sm[8][33];
-  int col = blockIdx.x * 32 + threadIdx.x;
-  float acc = 0.f;
-  if (col < N)
-    for (int m = blockIdx.y * 8 + threadIdx.y; m < M; m += gridDim.y * 8) acc += x[(int64_t)m * ldx + col];
-  sm[threadIdx.y][threadIdx.x] = acc;
+// out[n] += sum_m x[m,n]   (bias gradients).  Each block owns 128 consecutive columns (one float4 per
+// lane) and a strided set of rows; 8 warps x 4 rows in flight per warp keep ~16 KB of loads outstanding
+// per block; partial sums go through shared memory to one atomic per column per block.
+__global__ void __launch_bounds__(256) colsum_k(const float* __restrict__ x, int64_t ldx, float* __restrict__ out,
+                                                int M, int N) {
+  __shared__ float4 sm[8][32];
+  const int lane = threadIdx.x, w = threadIdx.y;
+  const int col = blockIdx.x * 128 + lane * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N) {
+    const bool vec = (col + 3 < N) && ((ldx & 3) == 0);
+    const int stride = gridDim.y * 8;
+    int m = blockIdx.y * 8 + w;
+    if (vec) {
+      for (; m + 3 * stride < M; m += 4 * stride) {
+        const float4 a0 = *reinterpret_cast<const float4*>(x + (int64_t)m * ldx + col);
+        const float4 a1 = *reinterpret_cast<const float4*>(x + (int64_t)(m + stride) * ldx + col);
+        const float4 a2 = *reinterpret_cast<const float4*>(x + (int64_t)(m + 2 * stride) * ldx + col);
+        const float4 a3 = *reinterpret_cast<const float4*>(x + (int64_t)(m + 3 * stride) * ldx + col);
+        acc.x += (a0.x + a1.x) + (a2.x + a3.x); acc.y += (a0.y + a1.y) + (a2.y + a3.y);
+        acc.z += (a0.z + a1.z) + (a2.z + a3.z); acc.w += (a0.w + a1.w) + (a2.w + a3.w);
+      }
+      for (; m < M; m += stride) {
+        const float4 a0 = *reinterpret_cast<const float4*>(x + (int64_t)m * ldx + col);
+        acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+      }
+    } else {
+      for (; m < M; m += stride) {
+        const float* r = x + (int64_t)m * ldx + col;
+        acc.x += r[0];
+        if (col + 1 < N) acc.y += r[1];
+        if (col + 2 < N) acc.z += r[2];
+        if (col + 3 < N) acc.w += r[3];
+      }
+    }
+  }
+  sm[w][lane] = acc;
   __syncthreads();
-  if (threadIdx.y == 0 && col < N) {
-    float t = 0.f;
+  if (w == 0 && col < N) {
+    float4 t = sm[0][lane];
 #pragma unroll
-    for (int i = 0; i < 8; i++) t += sm[i][threadIdx.x];
-    atomicAdd(out + col, t);
+    for (int i = 1; i < 8; i++) { t.x += sm[i][lane].x; t.y += sm[i][lane].y; t.z += sm[i][lane].z; t.w += sm[i][lane].w; }
+    atomicAdd(out + col, t.x);
+    if (col + 1 < N) atomicAdd(out + col + 1, t.y);
+    if (col + 2 < N) atomicAdd(out + col + 2, t.z);
+    if (col + 3 < N) atomicAdd(out + col + 3, t.w);
   }
 }
 
@@ -563,8 +596,12 @@ int skf_add_layernorm_fwd(const float* a, const float* b, const float* bias, con
                           int rows, int d, int round_tf32, void* stream) {
   SKF_REQUIRE(d % 4 == 0 && d <= 128 * LN_MAX_VEC, SKF_ERR_BAD_SHAPE, "layernorm: d=%d unsupported", d);
   dim3 blk(32, 8);
-  add_ln_fwd_k<<<cdiv(rows, 8), blk, 0, as_stream(stream)>>>(a, b, bias, gamma, beta, s, y, mean, rstd,
-                                                            rows, d, round_tf32);
+  const int grid = cdiv(rows, 8);
+  cudaStream_t st = as_stream(stream);
+  if (d <= 128) add_ln_fwd_k<1><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32);
+  else if (d <= 256) add_ln_fwd_k<2><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32);
+  else if (d <= 512) add_ln_fwd_k<4><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32);
+  else add_ln_fwd_k<8><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -574,20 +611,27 @@ int skf_layernorm_bwd(const float* dy, const float* s, const float* mean, const 
                       int d, int round_tf32, void* stream) {
   SKF_REQUIRE(d % 4 == 0 && d <= 128 * LN_MAX_VEC, SKF_ERR_BAD_SHAPE, "layernorm: d=%d unsupported", d);
   dim3 blk(32, 8);
-  int grid = cdiv(rows, 8);
-  if (grid > 148 * 4) grid = 148 * 4;
-  ln_bwd_k<<<grid, blk, 2 * d * sizeof(float), as_stream(stream)>>>(dy, s, mean, rstd, gamma, ds,
-                                                                   dgamma, dbeta, rows, d, round_tf32);
+  int grid = cdiv(rows, 8 * 4);              // >= 4 rows per warp so the dgamma/dbeta partials amortise
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  const size_t sm = 2 * d * sizeof(float);
+  cudaStream_t st = as_stream(stream);
+  if (d <= 128) ln_bwd_k<1><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32);
+  else if (d <= 256) ln_bwd_k<2><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32);
+  else if (d <= 512) ln_bwd_k<4><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32);
+  else ln_bwd_k<8><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
 
 int skf_colsum(const float* x, int64_t ldx, float* out, int M, int N, void* stream) {
   dim3 blk(32, 8);
-  int gy = cdiv(M, 8 * 16);
-  if (gy > 64) gy = 64;
+  const int gx = cdiv(N, 128);
+  int gy = (148 * 4 + gx - 1) / gx;           // ~4 blocks per SM in total
+  const int maxy = cdiv(M, 8 * 4);
+  if (gy > maxy) gy = maxy;
   if (gy < 1) gy = 1;
-  colsum_k<<<dim3(cdiv(N, 32), gy), blk, 0, as_stream(stream)>>>(x, ldx, out, M, N);
+  colsum_k<<<dim3(gx, gy), blk, 0, as_stream(stream)>>>(x, ldx, out, M, N);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
