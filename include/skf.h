@@ -103,6 +103,25 @@ int skf_positional_encoding(float* pe, int rows, int d, void* stream);
 /* builders/utils.py:35-43 — pad[b,t] = (tok[b,t]==0) (tokens) as uint8.                    */
 int skf_pad_flags(const int64_t* tok, int64_t tok_ld, uint8_t* pad, int B, int T, void* stream);
 
+/* use_continuous_data=True (stroke-5 rows [dx,dy,p_down,p_up,p_pad], float32).  x has batch stride x_ld
+ * (elements) and row stride 5.
+ * builders/utils.py:38-39 — pad[b,t] = (x[b,t,4] == 1).                                      */
+int skf_pad_flags_cont(const float* x, int64_t x_ld, uint8_t* pad, int B, int T, void* stream);
+/* Encoder/Decoder.call with use_continuous_input (transformer.py:275-276, 292-294, 314-315):
+ * out[b,t,:] = (x[b,t,:] . W[5,d] + bias) * sqrt(d) + PE[t,:].                               */
+int skf_embed_cont_fwd(const float* x, int64_t x_ld, const float* W, const float* bias, const float* pe,
+                       float* out, int B, int T, int d, int round_tf32, void* stream);
+/* dW[5,d] += sqrt(d) x^T dout ; db[d] += sqrt(d) colsum(dout)                                 */
+int skf_embed_cont_bwd(const float* x, int64_t x_ld, const float* dout, float* dW, float* db, int B, int T,
+                       int d, void* stream);
+/* Continuous reconstruction loss (builders/losses.py:43-66):
+ * loss = weight * mean_{b,t}((loc + M) * mask), loc = mean_2((real_xy - pred_xy)^2),
+ * M = mean_{b,t} CE3(argmax real[2:5], pred[2:5]) over ALL positions, mask = (real[...,4] != 1).
+ * stats[0] += sum loc*mask, stats[1] += sum CE3, stats[2] += sum mask (doubles, zeroed by the caller);
+ * dpred (optional, [B*Td, lddp]) = d loss / d pred.  real has batch stride real_ld, row stride 5. */
+int skf_cont_loss(const float* pred, int64_t ldp, const float* real, int64_t real_ld, int B, int Td,
+                  float weight, float* dpred, int64_t lddp, double* stats, void* stream);
+
 /* tf.keras.layers.Dense (builders/layers/transformer.py:154-158,196-197) and its gradients.
  * Y[M,N] = epilogue(op(A)[M,K] * op(B)[K,N]).  A is addressed as A[m*sa_m + k*sa_k], B as
  * B[k*sb_k + n*sb_n] (element strides), so one entry point serves forward (X*W), dgrad (dY*W^T)
@@ -221,6 +240,18 @@ int skf_apply_adam(skf_plan* plan, void* stream);
 int skf_encode(skf_plan* plan, const void* tokens, void* stream);
 /* Transformer.call in inference mode incl. decoder logits for teacher-forced input.         */
 int skf_forward(skf_plan* plan, const void* tokens, void* stream);
+/* Transformer.predict_from_embedding (sketchformer.py:255-311): greedy decoding with per-layer key /
+ * value caches.  skf_decode_begin: `embedding` device [B,d] (NULL = the workspace tensor "embedding" left
+ * by skf_encode), `expected_len` device int32 [B] or NULL (cross-attention key mask j >= len when
+ * blind_decoder_mask=0; ignored when blind); also classifies the embedding ("cls.argmax").  It expands the
+ * embedding, projects every layer's cross keys / values once and seeds the prefix with the start token
+ * (SOS, or the stroke row [0,0,1,0,0]).  skf_decode_steps runs decoder positions [first, first+n): each
+ * appends argmax(logits) (or [dx,dy,softmax(pen)]) to the workspace tensor "gen.tokens" int64 [B,T+1]
+ * ("gen.strokes" float [B,T+1,5]).  "gen.state" int32: [0] = number of valid output columns once every row
+ * has emitted EOS (pen state 2), else 0; [1] = steps executed.  No host synchronisation inside.          */
+int skf_decode_begin(skf_plan* plan, const float* embedding, const int32_t* expected_len,
+                     int64_t sos_token, int64_t eos_token, void* stream);
+int skf_decode_steps(skf_plan* plan, int first_step, int n_steps, void* stream);
 /* Number of kernels launched by this plan since creation (bench `gpu_launches`).           */
 int64_t skf_plan_launches(const skf_plan* plan);
 

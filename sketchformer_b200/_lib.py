@@ -43,6 +43,10 @@ SIGNATURES = {
     "skf_embed_bwd": (I, [P, L, P, P, I, I, I, I, P]),
     "skf_positional_encoding": (I, [P, I, I, P]),
     "skf_pad_flags": (I, [P, L, P, I, I, P]),
+    "skf_pad_flags_cont": (I, [P, L, P, I, I, P]),
+    "skf_embed_cont_fwd": (I, [P, L, P, P, P, P, I, I, I, I, P]),
+    "skf_embed_cont_bwd": (I, [P, L, P, P, P, I, I, I, P]),
+    "skf_cont_loss": (I, [P, L, P, L, I, I, F, P, L, P, P]),
     "skf_gemm": (I, [P, L, L, P, L, L, P, L, I, I, I, C.POINTER(SkfGemmEpilogue), I, P]),
     "skf_split_lo": (I, [P, P, L, P]),
     "skf_attn_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, P]),
@@ -66,6 +70,8 @@ SIGNATURES = {
     "skf_apply_adam": (I, [P, P]),
     "skf_encode": (I, [P, P, P]),
     "skf_forward": (I, [P, P, P]),
+    "skf_decode_begin": (I, [P, P, P, L, L, P]),
+    "skf_decode_steps": (I, [P, I, I, P]),
     "skf_plan_launches": (L, [P]),
 }
 

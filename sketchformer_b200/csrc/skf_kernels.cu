@@ -81,6 +81,121 @@ __global__ void pad_flags_k(const int64_t* __restrict__ tok, int64_t tok_ld,
   pad[idx] = tok[(int64_t)b * tok_ld + t] == 0 ? 1 : 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K1c / K10: continuous (stroke-5) input embedding and output loss, use_continuous_data=True
+// (builders/layers/transformer.py:275-276, 292-294; builders/losses.py:43-66; builders/utils.py:38-39)
+// ---------------------------------------------------------------------------------------------
+// pad[b,t] = (x[b,t,4] == 1)
+__global__ void pad_flags_cont_k(const float* __restrict__ x, int64_t x_ld, uint8_t* __restrict__ pad, int B, int T) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * T) return;
+  int b = idx / T, t = idx - b * T;
+  pad[idx] = x[(int64_t)b * x_ld + (int64_t)t * 5 + 4] == 1.0f ? 1 : 0;
+}
+
+// out[b,t,:] = (x[b,t,:5] . W[5,d] + bias) * sqrt(d) + PE[t,:]     (Dense(d_model) on the stroke-5 row)
+__global__ void embed_cont_fwd_k(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ W,
+                                 const float* __restrict__ bias, const float* __restrict__ pe,
+                                 float* __restrict__ out, int B, int T, int d, float scale, int rnd) {
+  int row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= B * T) return;
+  int b = row / T, t = row - b * T;
+  const float* xr = x + (int64_t)b * x_ld + (int64_t)t * 5;
+  float x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3], x4 = xr[4];
+  for (int c = threadIdx.x; c < d; c += 32) {
+    float acc = x0 * __ldg(W + c);
+    acc = fmaf(x1, __ldg(W + d + c), acc);
+    acc = fmaf(x2, __ldg(W + 2 * d + c), acc);
+    acc = fmaf(x3, __ldg(W + 3 * d + c), acc);
+    acc = fmaf(x4, __ldg(W + 4 * d + c), acc);
+    acc += __ldg(bias + c);
+    out[(int64_t)row * d + c] = maybe_round(__fadd_rn(__fmul_rn(acc, scale), __ldg(pe + (int64_t)t * d + c)), rnd);
+  }
+}
+
+// dW[k,c] += sqrt(d) * sum_rows x[row,k] dout[row,c] ; db[c] += sqrt(d) * sum_rows dout[row,c]
+// thread per column, blockIdx.y strides the rows
+__global__ void embed_cont_bwd_k(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ dout,
+                                 float* __restrict__ dW, float* __restrict__ db, int B, int T, int d, float scale) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, ab = 0.f;
+  for (int row = blockIdx.y; row < B * T; row += gridDim.y) {
+    int b = row / T, t = row - b * T;
+    const float* xr = x + (int64_t)b * x_ld + (int64_t)t * 5;
+    float g = dout[(int64_t)row * d + c];
+    a0 = fmaf(xr[0], g, a0); a1 = fmaf(xr[1], g, a1); a2 = fmaf(xr[2], g, a2);
+    a3 = fmaf(xr[3], g, a3); a4 = fmaf(xr[4], g, a4); ab += g;
+  }
+  atomicAdd(dW + c, a0 * scale); atomicAdd(dW + d + c, a1 * scale); atomicAdd(dW + 2 * d + c, a2 * scale);
+  atomicAdd(dW + 3 * d + c, a3 * scale); atomicAdd(dW + 4 * d + c, a4 * scale); atomicAdd(db + c, ab * scale);
+}
+
+// builders/losses.py:43-66 sums.  stats[0] += sum loc*mask, stats[1] += sum CE3, stats[2] += sum mask
+// loc = mean_2((real_xy - pred_xy)^2), CE3 = lse(pred[2:5]) - pred[2 + argmax(real[2:5])], mask = real[4] != 1
+__device__ __forceinline__ void cont_row(const float* r, const float* p, float& loc, float& ce, float& mask,
+                                         int& label, float* sm3) {
+  float d0 = r[0] - p[0], d1 = r[1] - p[1];
+  loc = 0.5f * (d0 * d0 + d1 * d1);
+  label = 0;
+  float best = r[2];
+  if (r[3] > best) { best = r[3]; label = 1; }
+  if (r[4] > best) { best = r[4]; label = 2; }
+  float mx = fmaxf(p[2], fmaxf(p[3], p[4]));
+  float e0 = expf(p[2] - mx), e1 = expf(p[3] - mx), e2 = expf(p[4] - mx);
+  float se = e0 + e1 + e2;
+  ce = mx + logf(se) - p[2 + label];
+  mask = r[4] != 1.0f ? 1.f : 0.f;
+  if (sm3) { float inv = 1.0f / se; sm3[0] = e0 * inv; sm3[1] = e1 * inv; sm3[2] = e2 * inv; }
+}
+
+__global__ void cont_loss_stats_k(const float* __restrict__ pred, int64_t ldp, const float* __restrict__ real,
+                                  int64_t real_ld, int B, int Td, double* __restrict__ stats) {
+  __shared__ float red[3][8];
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  float loc = 0.f, ce = 0.f, mask = 0.f;
+  if (idx < B * Td) {
+    int b = idx / Td, t = idx - b * Td, label;
+    float l;
+    cont_row(real + (int64_t)b * real_ld + (int64_t)t * 5, pred + (int64_t)idx * ldp, l, ce, mask, label, nullptr);
+    loc = l * mask;
+  }
+  loc = warp_sum(loc); ce = warp_sum(ce); mask = warp_sum(mask);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { red[0][w] = loc; red[1][w] = ce; red[2][w] = mask; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0, m = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) { a += red[0][i]; c += red[1][i]; m += red[2][i]; }
+    atomicAdd(stats + 0, a); atomicAdd(stats + 1, c); atomicAdd(stats + 2, m);
+  }
+}
+
+// d loss / d pred with loss = weight * mean((loc + M) * mask), M = mean(CE3):
+//   d/dxy = weight/N * mask * (pred - real) ; d/dpen = weight * (sum mask / N) / N * (softmax - onehot)
+__global__ void cont_loss_grad_k(const float* pred, int64_t ldp, const float* __restrict__ real,
+                                 int64_t real_ld, int B, int Td, const double* __restrict__ stats, float weight,
+                                 float* dpred, int64_t lddp) {   // dpred may alias pred (row-local read, then write)
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Td) return;
+  int b = idx / Td, t = idx - b * Td, label;
+  const float* r = real + (int64_t)b * real_ld + (int64_t)t * 5;
+  const float* p = pred + (int64_t)idx * ldp;
+  float loc, ce, mask, sm3[3];
+  cont_row(r, p, loc, ce, mask, label, sm3);
+  const float invN = 1.0f / (float)((double)B * Td);
+  const float wpen = weight * (float)(stats[2] * (double)invN) * invN;
+  float* g = dpred + (int64_t)idx * lddp;
+  const float p0 = p[0], p1 = p[1];
+  g[0] = weight * invN * mask * (p0 - r[0]);
+  g[1] = weight * invN * mask * (p1 - r[1]);
+  g[2] = wpen * (sm3[0] - (label == 0 ? 1.f : 0.f));
+  g[3] = wpen * (sm3[1] - (label == 1 ? 1.f : 0.f));
+  g[4] = wpen * (sm3[2] - (label == 2 ? 1.f : 0.f));
+  for (int j = 5; j < (int)lddp; j++) g[j] = 0.f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // residual add + LayerNormalization(eps=1e-6)   (transformer.py:217-218, 222, 250-260)
 // one warp per row; the row lives in registers (d <= 1024)
@@ -588,6 +703,48 @@ int skf_positional_encoding(float* pe, int rows, int d, void* stream) {
 int skf_pad_flags(const int64_t* tok, int64_t tok_ld, uint8_t* pad, int B, int T, void* stream) {
   pad_flags_k<<<cdiv((long)B * T, 256), 256, 0, as_stream(stream)>>>(tok, tok_ld, pad, B, T);
   SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+
+int skf_pad_flags_cont(const float* x, int64_t x_ld, uint8_t* pad, int B, int T, void* stream) {
+  pad_flags_cont_k<<<cdiv((long)B * T, 256), 256, 0, as_stream(stream)>>>(x, x_ld, pad, B, T);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_embed_cont_fwd(const float* x, int64_t x_ld, const float* W, const float* bias, const float* pe,
+                       float* out, int B, int T, int d, int round_tf32, void* stream) {
+  SKF_REQUIRE(B > 0 && T > 0 && d > 0, SKF_ERR_BAD_SHAPE, "embed_cont_fwd: empty");
+  dim3 blk(32, 8);
+  embed_cont_fwd_k<<<cdiv((long)B * T, 8), blk, 0, as_stream(stream)>>>(x, x_ld, W, bias, pe, out, B, T, d,
+                                                                       sqrtf((float)d), round_tf32);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_embed_cont_bwd(const float* x, int64_t x_ld, const float* dout, float* dW, float* db, int B, int T,
+                       int d, void* stream) {
+  int gy = (int)((long)B * T / 64);
+  gy = gy < 1 ? 1 : (gy > 296 ? 296 : gy);
+  embed_cont_bwd_k<<<dim3(cdiv(d, 128), gy), 128, 0, as_stream(stream)>>>(x, x_ld, dout, dW, db, B, T, d,
+                                                                         sqrtf((float)d));
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_cont_loss(const float* pred, int64_t ldp, const float* real, int64_t real_ld, int B, int Td,
+                  float weight, float* dpred, int64_t lddp, double* stats, void* stream) {
+  SKF_REQUIRE(pred && real && stats && B > 0 && Td > 0 && ldp >= 5, SKF_ERR_BAD_ARG, "cont_loss: bad argument");
+  const int rows = B * Td;
+  cont_loss_stats_k<<<cdiv(rows, 256), 256, 0, as_stream(stream)>>>(pred, ldp, real, real_ld, B, Td, stats);
+  SKF_LAUNCH_CHECK();
+  if (dpred) {
+    SKF_REQUIRE(lddp >= 5, SKF_ERR_BAD_ARG, "cont_loss: lddp < 5");
+    cont_loss_grad_k<<<cdiv(rows, 256), 256, 0, as_stream(stream)>>>(pred, ldp, real, real_ld, B, Td, stats, weight,
+                                                                    dpred, lddp);
+    SKF_LAUNCH_CHECK();
+  }
   return SKF_OK;
 }
 

@@ -34,6 +34,12 @@ int attn2_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_
 int attn2_bwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
               const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
               const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
+int decode_attn(const float*, int64_t, const float*, const float*, int64_t, float*, float*, int64_t, int64_t, int, int,
+                const uint8_t*, int64_t, int, float*, int64_t, int, int, int, cudaStream_t);
+int decode_init(int64_t*, float*, uint8_t*, uint8_t*, uint8_t*, int32_t*, const int32_t*, int, int, int64_t, int,
+                cudaStream_t);
+int decode_pick(const float*, int64_t, int, int64_t*, float*, uint8_t*, uint8_t*, int32_t*, int, int, int, int64_t,
+                int, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // parameter arena
@@ -67,8 +73,8 @@ static int check_cfg(const skf_cfg* c) {
   SKF_REQUIRE(dh == 16 || dh == 32 || dh == 64, SKF_ERR_UNSUPPORTED, "cfg: head dim %d not in {16,32,64}", dh);
   SKF_REQUIRE(c->u > 0, SKF_ERR_UNSUPPORTED, "cfg: lowerdim=0 (no bottleneck) is not built yet");
   SKF_REQUIRE(c->u % 4 == 0, SKF_ERR_BAD_SHAPE, "cfg: lowerdim must be a multiple of 4");
-  SKF_REQUIRE(!c->continuous, SKF_ERR_UNSUPPORTED, "cfg: use_continuous_data is not built yet");
-  SKF_REQUIRE(c->V > 0 && c->V % 4 == 0, SKF_ERR_BAD_SHAPE, "cfg: vocab size must be a positive multiple of 4");
+  SKF_REQUIRE(c->continuous || (c->V > 0 && c->V % 4 == 0), SKF_ERR_BAD_SHAPE,
+              "cfg: vocab size must be a positive multiple of 4");
   SKF_REQUIRE(!c->do_classification || c->C > 0, SKF_ERR_BAD_SHAPE, "cfg: n_classes");
   SKF_REQUIRE(c->T <= 1000, SKF_ERR_BAD_SHAPE, "cfg: max_seq_len > maximum_position_encoding (1000)");
   return SKF_OK;
@@ -93,7 +99,12 @@ static void add_ffn_ln(ParamLayout& L, const std::string& p, int d, int f, int n
 
 static ParamLayout build_layout(const skf_cfg& c) {
   ParamLayout L;
-  L.add("enc.emb", c.V, c.d);
+  if (c.continuous) {            // Dense(d_model) on stroke-5 rows (transformer.py:275-276)
+    L.add("enc.emb.k", 5, c.d);
+    L.add("enc.emb.b", 1, c.d);
+  } else {
+    L.add("enc.emb", c.V, c.d);
+  }
   for (int i = 0; i < c.L; i++) {
     std::string p = "enc.l" + std::to_string(i);
     add_mha_self(L, p + ".mha", c.d);
@@ -109,7 +120,12 @@ static ParamLayout build_layout(const skf_cfg& c) {
   if (c.do_reconstruction) {
     L.add("exp.k", 1, c.T);
     L.add("exp.b", 1, c.T);
-    L.add("dec.emb", c.V, c.d);
+    if (c.continuous) {
+      L.add("dec.emb.k", 5, c.d);
+      L.add("dec.emb.b", 1, c.d);
+    } else {
+      L.add("dec.emb", c.V, c.d);
+    }
     for (int i = 0; i < c.L; i++) {
       std::string p = "dec.l" + std::to_string(i);
       add_mha_self(L, p + ".mha1", c.d);
@@ -121,8 +137,8 @@ static ParamLayout build_layout(const skf_cfg& c) {
       L.add(p + ".mha2.wo.b", 1, c.d);
       add_ffn_ln(L, p, c.d, c.f, 3);
     }
-    L.add("out.k", c.d, c.V);
-    L.add("out.b", 1, c.V);
+    L.add("out.k", c.d, c.continuous ? 5 : c.V);   // sketchformer.py:86 / 91
+    L.add("out.b", 1, c.continuous ? 5 : c.V);
   }
   L.total = (L.total + 3) & ~(int64_t)3;
   return L;
@@ -206,8 +222,27 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
       W.add(p + ".rstd3", Md * F);
       W.add(p + ".out3", Md * d * F);
     }
-    W.add("recon.logits", Md * (size_t)c.V * F);
+    W.add("recon.logits", Md * (size_t)(c.continuous ? 8 : c.V) * F);   // continuous: [Md, 5] with ld 8
     W.add("recon.argmax", Md * 4);
+    // greedy decode (predict / predict_from_embedding): generated prefix, flags, per-layer self-attention
+    // key/value caches [B, T, 2d] and one-position activations
+    const size_t Bz = (size_t)c.B, Tp = (size_t)c.T + 1;
+    W.add("gen.tokens", Bz * Tp * 8);
+    W.add("gen.strokes", Bz * Tp * 5 * F);
+    W.add("gen.pad", Bz * Tp);
+    W.add("gen.cross_pad", Bz * c.T);
+    W.add("gen.fin", Bz);
+    W.add("gen.state", 8 * 4);
+    for (int i = 0; i < c.L; i++) W.add("gen.kv" + std::to_string(i), Bz * c.T * 2 * d * F);
+    W.add("gen.x", Bz * d * F);
+    W.add("gen.qkv", Bz * 3 * d * F);
+    W.add("gen.ctx", Bz * d * F);
+    W.add("gen.s", Bz * d * F);
+    W.add("gen.o1", Bz * d * F);
+    W.add("gen.q2", Bz * d * F);
+    W.add("gen.o2", Bz * d * F);
+    W.add("gen.h", Bz * f * F);
+    W.add("gen.logits", Bz * (size_t)(c.continuous ? 8 : c.V) * F);
   }
   // backward scratch
   W.add("g.a", Me * d * F);
@@ -238,6 +273,8 @@ struct skf_plan {
   int64_t launches = 0;
   bool round_ops = false;  // round GEMM operands to TF32 when they are produced
   const float* wc = nullptr;
+  int64_t gen_sos = 0, gen_eos = 0;   // greedy decode: start / stop token ids (utils/tokenizer.py:29-33)
+  bool gen_ready = false;
 
   float* wsf(const std::string& n) const { return reinterpret_cast<float*>(ws + W.t.at(n).off); }
   template <class T>
@@ -287,16 +324,19 @@ __global__ void round_copy_k(const float* __restrict__ src, float* __restrict__ 
 //             [5] class count [6] sum total_loss [7] steps | [8..12] last step: recon_loss, recon_acc,
 //             class_loss, class_acc, total_loss     (builders/keras_metrics.py:19-42 running means)
 __global__ void stats_finalize_k(const double* __restrict__ st, double* __restrict__ run, double n_recon,
-                                 double n_class, double recon_w, double class_w, int do_recon, int do_class) {
+                                 double n_class, double recon_w, double class_w, int do_recon, int do_class,
+                                 int continuous) {
   double rl = do_recon ? recon_w * st[0] / n_recon : 0.0;
+  // builders/losses.py:43-66: mean((loc + M) * mask) with M = mean(CE3); st[4..6] = sum loc*mask, sum CE3, sum mask
+  if (do_recon && continuous) rl = recon_w * (st[4] + st[5] / n_recon * st[6]) / n_recon;
   double cl = do_class ? class_w * st[2] / n_class : 0.0;
   double tot = rl + cl;
-  if (do_recon) { run[0] += rl; run[1] += st[1]; run[2] += n_recon; }
+  if (do_recon) { run[0] += rl; run[1] += continuous ? 0.0 : st[1]; run[2] += n_recon; }
   if (do_class) { run[3] += cl; run[4] += st[3]; run[5] += n_class; }
   run[6] += tot;
   run[7] += 1.0;
   run[8] = rl;
-  run[9] = do_recon ? st[1] / n_recon : 0.0;
+  run[9] = do_recon && !continuous ? st[1] / n_recon : 0.0;
   run[10] = cl;
   run[11] = do_class ? st[3] / n_class : 0.0;
   run[12] = tot;
@@ -385,15 +425,39 @@ static int refresh_compute_weights(skf_plan* P, cudaStream_t st) {
   return SKF_OK;
 }
 
-static int forward_encoder(skf_plan* P, const int64_t* tok, cudaStream_t st) {
+// pad flags + input embedding of `rows` positions per sample of the batch `in` ([B,T] int64 tokens, or
+// [B,T,5] float stroke-5 rows when cfg.continuous); prefix = "enc" / "dec"
+static int embed_any(skf_plan* P, const void* in, const std::string& prefix, uint8_t* pad, float* x, int rows,
+                     cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  const int rnd = P->round_ops ? 1 : 0;
+  if (c.continuous) {
+    const float* xs = reinterpret_cast<const float*>(in);
+    SKF_TRY(skf_pad_flags_cont(xs, (int64_t)c.T * 5, pad, c.B, rows, st));
+    return skf_embed_cont_fwd(xs, (int64_t)c.T * 5, P->pw(prefix + ".emb.k"), P->pw(prefix + ".emb.b"), P->wsf("pe"),
+                              x, c.B, rows, c.d, rnd, st);
+  }
+  const int64_t* tok = reinterpret_cast<const int64_t*>(in);
+  SKF_TRY(skf_pad_flags(tok, c.T, pad, c.B, rows, st));
+  return skf_embed_fwd(tok, c.T, P->pw(prefix + ".emb"), P->wsf("pe"), x, c.B, rows, c.d, c.V, rnd, st);
+}
+static int embed_any_bwd(skf_plan* P, const void* in, const std::string& prefix, const float* dx, int rows,
+                         cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  if (c.continuous)
+    return skf_embed_cont_bwd(reinterpret_cast<const float*>(in), (int64_t)c.T * 5, dx, P->g(prefix + ".emb.k"),
+                              P->g(prefix + ".emb.b"), c.B, rows, c.d, st);
+  return skf_embed_bwd(reinterpret_cast<const int64_t*>(in), c.T, dx, P->g(prefix + ".emb"), c.B, rows, c.d, c.V, st);
+}
+
+static int forward_encoder(skf_plan* P, const void* tok, cudaStream_t st) {
   const skf_cfg& c = P->c;
   const int B = c.B, T = c.T, d = c.d, f = c.f, Me = B * T;
   const int rnd = P->round_ops ? 1 : 0;
   Gemm G{P, st};
   uint8_t* enc_pad = P->wsp<uint8_t>("enc_pad");
-  SKF_TRY(skf_pad_flags(tok, T, enc_pad, B, T, st));
   float* x = P->wsf("enc.x0");
-  SKF_TRY(skf_embed_fwd(tok, T, P->pw("enc.emb"), P->wsf("pe"), x, B, T, d, c.V, rnd, st));
+  SKF_TRY(embed_any(P, tok, "enc", enc_pad, x, T, st));
   for (int i = 0; i < c.L; i++) {
     std::string p = "enc.l" + std::to_string(i);
     float* qkv = P->wsf(p + ".qkv");
@@ -431,7 +495,7 @@ static int forward_encoder(skf_plan* P, const int64_t* tok, cudaStream_t st) {
   return SKF_OK;
 }
 
-static int forward_decoder(skf_plan* P, const int64_t* tok, cudaStream_t st) {
+static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
   const skf_cfg& c = P->c;
   const int B = c.B, T = c.T, Td = c.T - 1, d = c.d, f = c.f, Me = B * T, Md = B * Td;
   const int rnd = P->round_ops ? 1 : 0;
@@ -440,9 +504,8 @@ static int forward_decoder(skf_plan* P, const int64_t* tok, cudaStream_t st) {
   SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre,
                          B, T, d, rnd, st));
   uint8_t* dec_pad = P->wsp<uint8_t>("dec_pad");
-  SKF_TRY(skf_pad_flags(tok, T, dec_pad, B, Td, st));      // tar_inp = tar[:, :-1]
   float* x = P->wsf("dec.x0");
-  SKF_TRY(skf_embed_fwd(tok, T, P->pw("dec.emb"), P->wsf("pe"), x, B, Td, d, c.V, rnd, st));
+  SKF_TRY(embed_any(P, tok, "dec", dec_pad, x, Td, st));   // tar_inp = tar[:, :-1]
   const uint8_t* cross_pad = c.blind_decoder_mask ? nullptr : P->wsp<uint8_t>("enc_pad");
   const int cross_mode = c.blind_decoder_mask ? 0 : 1;
   for (int i = 0; i < c.L; i++) {
@@ -478,17 +541,29 @@ static int forward_decoder(skf_plan* P, const int64_t* tok, cudaStream_t st) {
                                   P->wsf(p + ".mean3"), P->wsf(p + ".rstd3"), Md, d, rnd, st));
     x = out3;
   }
+  if (c.continuous) {            // Dense(5), sketchformer.py:86 (5 columns: exact-fp32 SIMT GEMM, ld 8)
+    skf_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.bias = P->pw("out.b");
+    return gemm_simt(x, d, 1, P->pw("out.k"), 5, 1, P->wsf("recon.logits"), 8, Md, 5, d, &e, st);
+  }
   SKF_TRY(G.fwd(x, P->w("out.k"), P->pw("out.b"), P->wsf("recon.logits"), Md, c.V, d, SKF_ACT_NONE, nullptr, 0));
   return SKF_OK;
 }
 
 // ---- losses ------------------------------------------------------------------------------------
-static int losses(skf_plan* P, const int64_t* tok, const int64_t* labels, bool want_grad, cudaStream_t st) {
+static int losses(skf_plan* P, const void* in, const int64_t* labels, bool want_grad, cudaStream_t st) {
   const skf_cfg& c = P->c;
   const int B = c.B, T = c.T, Td = T - 1;
+  const int64_t* tok = reinterpret_cast<const int64_t*>(in);
   double* ss = P->wsp<double>("stats_step");
   SKF_CUDA(cudaMemsetAsync(ss, 0, 8 * sizeof(double), st));
-  if (c.do_reconstruction) {
+  if (c.do_reconstruction && c.continuous) {
+    // tar_real = data[:, 1:, :]; the gradient overwrites the predictions in place
+    const float* x = reinterpret_cast<const float*>(in);
+    float* pr = P->wsf("recon.logits");
+    SKF_TRY(skf_cont_loss(pr, 8, x + 5, (int64_t)T * 5, B, Td, c.recon_weight, want_grad ? pr : nullptr, 8, ss + 4, st));
+  } else if (c.do_reconstruction) {
     float* lg = P->wsf("recon.logits");
     float scale = c.recon_weight / (float)((double)B * Td);
     SKF_TRY(skf_token_ce(lg, c.V, tok + 1, T, B, Td, c.V, scale, want_grad ? lg : nullptr, c.V, ss + 0,
@@ -503,14 +578,14 @@ static int losses(skf_plan* P, const int64_t* tok, const int64_t* labels, bool w
   if (labels) {
     stats_finalize_k<<<1, 1, 0, st>>>(ss, P->wsp<double>("stats_run"), (double)B * Td, (double)B,
                                       (double)c.recon_weight, (double)c.class_weight, c.do_reconstruction,
-                                      c.do_classification);
+                                      c.do_classification, c.continuous);
     SKF_LAUNCH_CHECK();
   }
   return SKF_OK;
 }
 
 // ---- backward ----------------------------------------------------------------------------------
-static int backward(skf_plan* P, const int64_t* tok, cudaStream_t st) {
+static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
   const skf_cfg& c = P->c;
   const int B = c.B, T = c.T, Td = T - 1, d = c.d, f = c.f, Me = B * T, Md = B * Td;
   const int rnd = P->round_ops ? 1 : 0;
@@ -529,8 +604,19 @@ static int backward(skf_plan* P, const int64_t* tok, cudaStream_t st) {
     float* pre = P->wsf("pre_decoder");
     float* dlog = P->wsf("recon.logits");  // holds dlogits after losses()
     std::string last = "dec.l" + std::to_string(c.L - 1);
-    SKF_TRY(G.wgrad(P->wsf(last + ".out3"), dlog, P->g("out.k"), P->g("out.b"), Md, c.V, d));
-    SKF_TRY(G.dgrad(dlog, P->w("out.k"), gA, Md, c.V, d, nullptr, nullptr, 0));
+    if (c.continuous) {
+      skf_gemm_epilogue e;
+      memset(&e, 0, sizeof(e));
+      e.accumulate = 1;
+      e.split_k = 64;
+      SKF_TRY(gemm_simt(P->wsf(last + ".out3"), 1, d, dlog, 8, 1, P->g("out.k"), 5, d, 5, Md, &e, st));
+      SKF_TRY(skf_colsum(dlog, 8, P->g("out.b"), Md, 5, st));
+      memset(&e, 0, sizeof(e));
+      SKF_TRY(gemm_simt(dlog, 8, 1, P->pw("out.k"), 1, 5, gA, d, Md, d, 5, &e, st));
+    } else {
+      SKF_TRY(G.wgrad(P->wsf(last + ".out3"), dlog, P->g("out.k"), P->g("out.b"), Md, c.V, d));
+      SKF_TRY(G.dgrad(dlog, P->w("out.k"), gA, Md, c.V, d, nullptr, nullptr, 0));
+    }
     for (int i = c.L - 1; i >= 0; i--) {
       std::string p = "dec.l" + std::to_string(i);
       const float* xin = i == 0 ? P->wsf("dec.x0") : P->wsf("dec.l" + std::to_string(i - 1) + ".out3");
@@ -566,7 +652,7 @@ static int backward(skf_plan* P, const int64_t* tok, cudaStream_t st) {
       SKF_TRY(G.wgrad(xin, gQKV, P->g(p + ".mha1.wqkv.k"), P->g(p + ".mha1.wqkv.b"), Md, 3 * d, d));
       SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha1.wqkv.k"), gA, Md, 3 * d, d, nullptr, gB, 0));
     }
-    SKF_TRY(skf_embed_bwd(tok, T, gA, P->g("dec.emb"), B, Td, d, c.V, st));
+    SKF_TRY(embed_any_bwd(P, tok, "dec", gA, Td, st));
     SKF_TRY(skf_expand_bwd(gPre, P->wsf("embedding"), P->pw("exp.k"), gEmb, 0, P->g("exp.k"),
                            P->g("exp.b"), B, T, d, st));
     have_demb = true;
@@ -614,8 +700,94 @@ static int backward(skf_plan* P, const int64_t* tok, cudaStream_t st) {
     SKF_TRY(G.wgrad(xin, gQKV, P->g(p + ".mha.wqkv.k"), P->g(p + ".mha.wqkv.b"), Me, 3 * d, d));
     SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha.wqkv.k"), gA, Me, 3 * d, d, nullptr, gB, 0));
   }
-  SKF_TRY(skf_embed_bwd(tok, T, gA, P->g("enc.emb"), B, T, d, c.V, st));
+  SKF_TRY(embed_any_bwd(P, tok, "enc", gA, T, st));
   return SKF_OK;
+}
+
+// ---- greedy decode (models/sketchformer.py:255-311) ----------------------------------------------
+static int classify_embedding(skf_plan* P, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  int Cp = (c.C + 3) & ~3;
+  skf_gemm_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.bias = P->pw("cls.b");
+  SKF_TRY(gemm_simt(P->wsf("embedding"), c.d, 1, P->pw("cls.k"), c.C, 1, P->wsf("cls.logits"), Cp, c.B, c.C, c.d, &e, st));
+  return skf_class_ce(P->wsf("cls.logits"), Cp, nullptr, c.B, c.C, 0.f, nullptr, Cp, nullptr,
+                      P->wsp<int32_t>("cls.argmax"), P->wsf("cls.probs"), st);
+}
+
+static int decode_begin(skf_plan* P, const float* embedding, const int32_t* expected_len, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  const int B = c.B, T = c.T, d = c.d, Me = B * T;
+  const int rnd = P->round_ops ? 1 : 0;
+  Gemm G{P, st};
+  SKF_TRY(refresh_compute_weights(P, st));
+  if (embedding && embedding != P->wsf("embedding"))
+    SKF_CUDA(cudaMemcpyAsync(P->wsf("embedding"), embedding, (size_t)B * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (c.do_classification) SKF_TRY(classify_embedding(P, st));     // sketchformer.py:307-310
+  // the expanded embedding and every layer's cross-attention keys / values do not depend on the prefix
+  float* pre = P->wsf("pre_decoder");
+  SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, d, rnd, st));
+  for (int i = 0; i < c.L; i++) {
+    std::string p = "dec.l" + std::to_string(i);
+    SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), P->wsf(p + ".kv2"), Me, 2 * d, d,
+                  SKF_ACT_NONE, nullptr, 0));
+  }
+  SKF_TRY(decode_init(P->wsp<int64_t>("gen.tokens"), P->wsf("gen.strokes"), P->wsp<uint8_t>("gen.pad"),
+                      P->wsp<uint8_t>("gen.cross_pad"), P->wsp<uint8_t>("gen.fin"), P->wsp<int32_t>("gen.state"),
+                      expected_len, B, T, P->gen_sos, c.continuous, st));
+  return SKF_OK;
+}
+
+// position `i` of every sample: decoder input = column i of the generated prefix -> column i+1
+static int decode_step(skf_plan* P, int i, bool cross_masked, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  const int B = c.B, T = c.T, d = c.d, f = c.f, H = c.H, dh = c.d / c.H;
+  const int rnd = P->round_ops ? 1 : 0;
+  Gemm G{P, st};
+  float *x = P->wsf("gen.x"), *qkv = P->wsf("gen.qkv"), *ctx = P->wsf("gen.ctx"), *sb = P->wsf("gen.s");
+  float *o1 = P->wsf("gen.o1"), *q2 = P->wsf("gen.q2"), *o2 = P->wsf("gen.o2"), *hf = P->wsf("gen.h");
+  uint8_t* pad = P->wsp<uint8_t>("gen.pad");
+  const float* pe = P->wsf("pe") + (size_t)i * d;
+  if (c.continuous)
+    SKF_TRY(skf_embed_cont_fwd(P->wsf("gen.strokes") + (size_t)i * 5, (int64_t)(T + 1) * 5, P->pw("dec.emb.k"),
+                               P->pw("dec.emb.b"), pe, x, B, 1, d, rnd, st));
+  else
+    SKF_TRY(skf_embed_fwd(P->wsp<int64_t>("gen.tokens") + i, T + 1, P->pw("dec.emb"), pe, x, B, 1, d, c.V, rnd, st));
+  for (int l = 0; l < c.L; l++) {
+    std::string p = "dec.l" + std::to_string(l);
+    float* kvc = P->wsf("gen.kv" + std::to_string(l));
+    SKF_TRY(G.fwd(x, P->w(p + ".mha1.wqkv.k"), P->pw(p + ".mha1.wqkv.b"), qkv, B, 3 * d, d, SKF_ACT_NONE, nullptr, 0));
+    // combined mask of the prefix: keys 0..i, generated PAD positions masked (create_masks on `output`)
+    SKF_TRY(decode_attn(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, kvc, kvc + d, 2 * d, (int64_t)T * 2 * d, i, i + 1, pad,
+                        T + 1, 1 << 30, ctx, d, B, H, dh, st));
+    SKF_TRY(G.fwd(ctx, P->w(p + ".mha1.wo.k"), P->pw(p + ".mha1.wo.b"), sb, B, d, d, SKF_ACT_NONE, x, 0));
+    SKF_TRY(skf_add_layernorm_fwd(sb, nullptr, nullptr, P->pw(p + ".ln1.g"), P->pw(p + ".ln1.b"), nullptr, o1, nullptr,
+                                  nullptr, B, d, rnd, st));
+    SKF_TRY(G.fwd(o1, P->w(p + ".mha2.wq.k"), P->pw(p + ".mha2.wq.b"), q2, B, d, d, SKF_ACT_NONE, nullptr, 0));
+    float* kv2 = P->wsf(p + ".kv2");
+    SKF_TRY(decode_attn(q2, d, nullptr, nullptr, 0, kv2, kv2 + d, 2 * d, (int64_t)T * 2 * d, -1, T,
+                        cross_masked ? P->wsp<uint8_t>("gen.cross_pad") : nullptr, T, 1 << 30, ctx, d, B, H, dh, st));
+    SKF_TRY(G.fwd(ctx, P->w(p + ".mha2.wo.k"), P->pw(p + ".mha2.wo.b"), sb, B, d, d, SKF_ACT_NONE, o1, 0));
+    SKF_TRY(skf_add_layernorm_fwd(sb, nullptr, nullptr, P->pw(p + ".ln2.g"), P->pw(p + ".ln2.b"), nullptr, o2, nullptr,
+                                  nullptr, B, d, rnd, st));
+    SKF_TRY(G.fwd(o2, P->w(p + ".ffn.w1.k"), P->pw(p + ".ffn.w1.b"), hf, B, f, d, SKF_ACT_RELU, nullptr, 1));
+    SKF_TRY(G.fwd(hf, P->w(p + ".ffn.w2.k"), P->pw(p + ".ffn.w2.b"), sb, B, d, f, SKF_ACT_NONE, o2, 0));
+    SKF_TRY(skf_add_layernorm_fwd(sb, nullptr, nullptr, P->pw(p + ".ln3.g"), P->pw(p + ".ln3.b"), nullptr, x, nullptr,
+                                  nullptr, B, d, rnd, st));
+  }
+  float* lg = P->wsf("gen.logits");
+  if (c.continuous) {
+    skf_gemm_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.bias = P->pw("out.b");
+    SKF_TRY(gemm_simt(x, d, 1, P->pw("out.k"), 5, 1, lg, 8, B, 5, d, &e, st));
+  } else {
+    SKF_TRY(G.fwd(x, P->w("out.k"), P->pw("out.b"), lg, B, c.V, d, SKF_ACT_NONE, nullptr, 0));
+  }
+  return decode_pick(lg, c.continuous ? 8 : c.V, c.V, P->wsp<int64_t>("gen.tokens"), P->wsf("gen.strokes"),
+                     P->wsp<uint8_t>("gen.pad"), P->wsp<uint8_t>("gen.fin"), P->wsp<int32_t>("gen.state"), B, T, i,
+                     P->gen_eos, c.continuous, st);
 }
 
 }  // namespace skf
@@ -725,7 +897,7 @@ int skf_train_step(skf_plan* P, const void* tokens, const int64_t* labels, int a
   SKF_REQUIRE(P->grads != nullptr, SKF_ERR_BAD_ARG, "train_step: plan created without a gradient arena");
   SKF_REQUIRE(!P->c.do_classification || labels != nullptr, SKF_ERR_BAD_ARG, "train_step: labels required");
   cudaStream_t st = as_stream(stream);
-  const int64_t* tok = reinterpret_cast<const int64_t*>(tokens);
+  const void* tok = tokens;
   int64_t l0 = skf::g_launch_count;
   SKF_TRY(refresh_compute_weights(P, st));
   SKF_TRY(forward_encoder(P, tok, st));
@@ -742,7 +914,7 @@ int skf_encode(skf_plan* P, const void* tokens, void* stream) {
   cudaStream_t st = as_stream(stream);
   int64_t l0 = skf::g_launch_count;
   SKF_TRY(refresh_compute_weights(P, st));
-  SKF_TRY(forward_encoder(P, reinterpret_cast<const int64_t*>(tokens), st));
+  SKF_TRY(forward_encoder(P, tokens, st));
   if (P->c.do_classification) {
     int Cp = (P->c.C + 3) & ~3;
     SKF_TRY(skf_class_ce(P->wsf("cls.logits"), Cp, nullptr, P->c.B, P->c.C, 0.f, nullptr, Cp, nullptr,
@@ -755,12 +927,46 @@ int skf_encode(skf_plan* P, const void* tokens, void* stream) {
 int skf_forward(skf_plan* P, const void* tokens, void* stream) {
   SKF_REQUIRE(P != nullptr && tokens != nullptr, SKF_ERR_BAD_ARG, "forward: NULL argument");
   cudaStream_t st = as_stream(stream);
-  const int64_t* tok = reinterpret_cast<const int64_t*>(tokens);
+  const void* tok = tokens;
   int64_t l0 = skf::g_launch_count;
   SKF_TRY(refresh_compute_weights(P, st));
   SKF_TRY(forward_encoder(P, tok, st));
   if (P->c.do_reconstruction) SKF_TRY(forward_decoder(P, tok, st));
   SKF_TRY(losses(P, tok, nullptr, false, st));
+  P->launches += skf::g_launch_count - l0;
+  return SKF_OK;
+}
+
+int skf_decode_begin(skf_plan* P, const float* embedding, const int32_t* expected_len, int64_t sos_token,
+                     int64_t eos_token, void* stream) {
+  SKF_REQUIRE(P != nullptr, SKF_ERR_BAD_ARG, "decode_begin: plan is NULL");
+  if (!P->c.do_reconstruction) {        // classification of a given embedding only (sketchformer.py:307-310)
+    SKF_REQUIRE(P->c.do_classification, SKF_ERR_UNSUPPORTED, "decode: the model has neither decoder nor classifier");
+    cudaStream_t st = as_stream(stream);
+    if (embedding && embedding != P->wsf("embedding"))
+      SKF_CUDA(cudaMemcpyAsync(P->wsf("embedding"), embedding, (size_t)P->c.B * P->c.d * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    return classify_embedding(P, st);
+  }
+  SKF_REQUIRE(P->c.blind_decoder_mask || expected_len != nullptr, SKF_ERR_UNSUPPORTED,
+              "decode: blind_decoder_mask=False needs expected_len (the i+1 cross mask of the reference changes "
+              "earlier positions every step and is not cacheable)");
+  int64_t l0 = skf::g_launch_count;
+  P->gen_sos = sos_token;
+  P->gen_eos = eos_token;
+  SKF_TRY(decode_begin(P, embedding, P->c.blind_decoder_mask ? nullptr : expected_len, as_stream(stream)));
+  P->gen_ready = true;
+  P->launches += skf::g_launch_count - l0;
+  return SKF_OK;
+}
+
+int skf_decode_steps(skf_plan* P, int first_step, int n_steps, void* stream) {
+  SKF_REQUIRE(P != nullptr && P->gen_ready, SKF_ERR_BAD_ARG, "decode_steps: call skf_decode_begin first");
+  SKF_REQUIRE(first_step >= 0 && n_steps >= 0 && first_step + n_steps <= P->c.T, SKF_ERR_BAD_SHAPE,
+              "decode_steps: steps [%d, %d) outside [0, max_seq_len=%d)", first_step, first_step + n_steps, P->c.T);
+  int64_t l0 = skf::g_launch_count;
+  for (int i = first_step; i < first_step + n_steps; i++)
+    SKF_TRY(decode_step(P, i, !P->c.blind_decoder_mask, as_stream(stream)));
   P->launches += skf::g_launch_count - l0;
   return SKF_OK;
 }

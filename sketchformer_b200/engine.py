@@ -144,8 +144,12 @@ class Engine:
 
     # ---- hot path ----------------------------------------------------------------------------
     def _check_tokens(self, tokens):
-        assert tokens.is_cuda and tokens.dtype == torch.int64 and tokens.is_contiguous()
-        assert tuple(tokens.shape) == (self.cfg.B, self.cfg.T), tuple(tokens.shape)
+        """[B,T] int64 token ids, or [B,T,5] float32 stroke-5 rows when cfg.continuous (sketchformer.py:316-322)."""
+        assert tokens.is_cuda and tokens.is_contiguous()
+        if self.cfg.continuous:
+            assert tokens.dtype == torch.float32 and tuple(tokens.shape) == (self.cfg.B, self.cfg.T, 5), tokens.shape
+        else:
+            assert tokens.dtype == torch.int64 and tuple(tokens.shape) == (self.cfg.B, self.cfg.T), tokens.shape
 
     def train_step(self, tokens: torch.Tensor, labels: torch.Tensor, apply_adam=True):
         self._check_tokens(tokens)
@@ -162,7 +166,10 @@ class Engine:
         if getattr(self, "_graph", None) is not None and self._graph_adam == bool(apply_adam):
             return self._graph
         B, T = self.cfg.B, self.cfg.T
-        self.graph_tokens = torch.zeros(B, T, dtype=torch.int64, device=self.device)
+        if self.cfg.continuous:
+            self.graph_tokens = torch.zeros(B, T, 5, dtype=torch.float32, device=self.device)
+        else:
+            self.graph_tokens = torch.zeros(B, T, dtype=torch.int64, device=self.device)
         self.graph_labels = torch.zeros(B, 1, dtype=torch.int64, device=self.device)
         torch.cuda.synchronize(self.device)
         l0 = self.launches()
@@ -190,6 +197,35 @@ class Engine:
     def forward(self, tokens):
         self._check_tokens(tokens)
         check(self.lib.skf_forward(self._plan, C.c_void_p(tokens.data_ptr()), self._stream()), "skf_forward")
+
+    def decode(self, embedding=None, expected_len=None, sos=1002, eos=1003, chunk=32):
+        """Greedy decode (models/sketchformer.py:255-311) from `embedding` (device [B,d]; None = the one left
+        in the workspace by encode()).  Steps are enqueued `chunk` at a time; between chunks ONE int32 is read
+        back to stop early once every row has finished.  Returns the prefix incl. the start token:
+        int32 [B, n] tokens or float32 [B, n, 5] strokes, n <= T+1 (the reference's `output`)."""
+        B, T = self.cfg.B, self.cfg.T
+        if embedding is not None:
+            assert embedding.is_cuda and embedding.dtype == torch.float32 and embedding.is_contiguous()
+            assert tuple(embedding.shape) == (B, self.cfg.d), tuple(embedding.shape)
+        if expected_len is not None:
+            expected_len = expected_len.to(device=self.device, dtype=torch.int32).contiguous()
+            assert expected_len.numel() == B
+        check(self.lib.skf_decode_begin(self._plan, C.c_void_p(embedding.data_ptr()) if embedding is not None else None,
+                                        C.c_void_p(expected_len.data_ptr()) if expected_len is not None else None,
+                                        int(sos), int(eos), self._stream()), "skf_decode_begin")
+        if not self.cfg.do_reconstruction:
+            return None                      # classification of the embedding only ("cls.argmax")
+        state = self.tensor("gen.state", dtype=torch.int32)
+        cols, i = 0, 0
+        while i < T and cols == 0:
+            n = min(chunk, T - i)
+            check(self.lib.skf_decode_steps(self._plan, i, n, self._stream()), "skf_decode_steps")
+            i += n
+            cols = int(state[0].item())
+        cols = cols or T + 1
+        if self.cfg.continuous:
+            return self.tensor("gen.strokes", (B, T + 1, 5))[:, :cols].clone()
+        return self.tensor("gen.tokens", (B, T + 1), dtype=torch.int64)[:, :cols].to(torch.int32)
 
     def launches(self):
         return int(self.lib.skf_plan_launches(self._plan))

@@ -13,6 +13,7 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
     V, C, u = hps["vocab_size"], hps["n_classes"], hps["lowerdim"]
     do_class = hps.get("do_classification", True)
     do_recon = hps.get("do_reconstruction", True)
+    continuous = bool(hps.get("use_continuous_data", False))
     gen = torch.Generator().manual_seed(seed)
     p: Dict[str, torch.Tensor] = {}
 
@@ -37,7 +38,13 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
         p[name + ".g"] = torch.ones(d, dtype=torch.float64)
         p[name + ".b"] = torch.zeros(d, dtype=torch.float64)
 
-    p["enc.emb"] = uni05((V, d))
+    def embed(prefix):
+        if continuous:                  # Dense(d_model) on stroke-5 rows, transformer.py:275-276
+            dense(prefix + ".emb", 5, d)
+        else:
+            p[prefix + ".emb"] = uni05((V, d))
+
+    embed("enc")
     for i in range(L):
         mha(f"enc.l{i}.mha", d)
         dense(f"enc.l{i}.ffn.w1", d, f)
@@ -52,7 +59,7 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
     if do_recon:
         p["exp.k"] = glorot(1, T, (1, T))
         p["exp.b"] = torch.zeros(T, dtype=torch.float64)
-        p["dec.emb"] = uni05((V, d))
+        embed("dec")
         for i in range(L):
             mha(f"dec.l{i}.mha1", d)
             mha(f"dec.l{i}.mha2", d)
@@ -60,5 +67,5 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
             dense(f"dec.l{i}.ffn.w2", f, d)
             for j in (1, 2, 3):
                 ln(f"dec.l{i}.ln{j}")
-        dense("out", d, V)
+        dense("out", d, 5 if continuous else V)
     return {k: v.to(dtype) for k, v in p.items()}

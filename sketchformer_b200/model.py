@@ -133,7 +133,8 @@ class Transformer:
         if first:
             self._train_engine = eng
             eng.load_params(init_params(dict(self.hps, max_seq_len=self.seq_len, vocab_size=self.vocab_size,
-                                             n_classes=self.dataset.n_classes), seed=self._seed))
+                                             n_classes=self.dataset.n_classes,
+                                             use_continuous_data=self.continuous), seed=self._seed))
         self._engines[B] = eng
         return eng
 
@@ -206,7 +207,19 @@ class Transformer:
         if not solo:
             self._allreduce_and_step(eng)
         self.current_step += 1
-        return eng.metrics() if sync_metrics else None
+        return self._quick_metrics(eng) if sync_metrics else None
+
+    def _quick_metrics(self, eng):
+        """Only the metrics build_model() registers (models/sketchformer.py:85-107): no recon_acc with
+        continuous data, no class_* without the classifier, no recon_* without the decoder."""
+        m = eng.metrics()
+        if self.continuous or not self.hps["do_reconstruction"]:
+            m.pop("recon_acc", None)
+        if not self.hps["do_reconstruction"]:
+            m.pop("recon_loss", None)
+        if not self.hps["do_classification"]:
+            m.pop("class_loss", None), m.pop("class_acc", None)
+        return m
 
     def _allreduce_and_step(self, eng):
         """sum the flat gradient arena over the ranks (NCCL over NVLink; 1/world is folded
@@ -229,11 +242,11 @@ class Transformer:
     def encode_from_seq(self, inp_seq):
         """models/sketchformer.py:162-168 -> {'embedding' (B,d) float32, 'class' (B,C) probabilities}"""
         inp_seq = np.asarray(inp_seq)
-        if inp_seq.ndim == 1:
+        if inp_seq.ndim == (2 if self.continuous else 1):
             inp_seq = inp_seq[None]
         B = inp_seq.shape[0]
         eng = self._engine(B)
-        eng.encode(self._to_device("x", inp_seq, torch.int64))
+        eng.encode(self._to_device("x", inp_seq, torch.float32 if self.continuous else torch.int64))
         out = {"embedding": eng.tensor("embedding", (B, self.hps["d_model"])).cpu().numpy(), "class": None}
         if self.hps["do_classification"]:
             out["class"] = eng.tensor("cls.probs", (B, self.dataset.n_classes)).cpu().numpy()
@@ -246,6 +259,52 @@ class Transformer:
         am = out.pop("_argmax", None)
         if self.hps["do_classification"]:
             out["class"] = am.astype(np.int32)
+        return out
+
+    def _sos_eos(self):
+        tok = getattr(self.dataset, "tokenizer", None)
+        return (tok.SOS, tok.EOS) if tok is not None else (0, 0)
+
+    def predict_from_embedding(self, emb, expected_len=None):
+        """models/sketchformer.py:255-311 -> {'recon' (B, n<=T+1) int32 tokens | (B, n, 5) float32 strokes,
+        'class' (B,) int32, 'attn_weights': None}.  KV-cached greedy decode on the device (skf_decode_*);
+        `expected_len` is ignored when blind_decoder_mask=True, exactly as the reference's decode() does.
+        The per-step attention maps the reference returns are never materialised here."""
+        emb = np.asarray(emb, dtype=np.float32)
+        if emb.ndim == 1:
+            emb = emb[None]
+        B = emb.shape[0]
+        eng = self._engine(B)
+        out = {}
+        e = self._to_device("emb", emb, torch.float32)
+        el = None
+        if expected_len is not None and not self.hps["blind_decoder_mask"]:
+            el = torch.as_tensor(np.asarray(expected_len)).to(torch.int32)
+        sos, eos = self._sos_eos()
+        recon = eng.decode(e, el, sos, eos)          # also classifies the embedding on the device
+        if self.hps["do_reconstruction"]:
+            out["recon"] = recon.cpu().numpy()
+            out["attn_weights"] = None
+        if self.hps["do_classification"]:
+            out["class"] = eng.tensor("cls.argmax", dtype=torch.int32)[:B].cpu().numpy().astype(np.int32)
+        return out
+
+    def predict(self, inp_seq):
+        """models/sketchformer.py:201-221 -> {'embedding', 'class' (B,) int32, 'recon', 'attn_weights'}"""
+        inp_seq = np.asarray(inp_seq)
+        out = self.predict_class(inp_seq)
+        if self.hps["do_reconstruction"]:
+            if inp_seq.ndim == (2 if self.continuous else 1):
+                inp_seq = inp_seq[None]
+            B = inp_seq.shape[0]
+            eng = self._engine(B)
+            tlen = None
+            if not self.hps["blind_decoder_mask"]:          # exact length of the input sketch
+                tlen = (inp_seq[..., -1] != 1).sum(-1) if self.continuous else (inp_seq > 0).sum(-1)
+                tlen = torch.as_tensor(tlen).to(torch.int32)
+            sos, eos = self._sos_eos()
+            out["recon"] = eng.decode(None, tlen, sos, eos).cpu().numpy()   # embedding still in the workspace
+            out["attn_weights"] = None
         return out
 
     # ---- checkpoints (own format: the flat arenas + step) ------------------------------------

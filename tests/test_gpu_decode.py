@@ -1,0 +1,151 @@
+"""Greedy decode parity (Transformer.predict / predict_from_embedding, models/sketchformer.py:201-311):
+the KV-cached CUDA decode (skf_decode_begin / skf_decode_steps through the C ABI) against the oracle, which
+re-runs the whole decoder on the growing prefix exactly like the reference.
+
+Token ids are compared bit-exactly.  A greedy argmax is discontinuous, so if the sequences differ the test
+looks at the first differing step and accepts it only when the oracle's own logits of the two candidates
+are tied to within 1e-3 of the logit range (the north-star's fp32 tolerance); otherwise it fails.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sketchformer_oracle as O
+from oracle.make_golden import CFG1, TINY
+from sketchformer_b200 import synth
+from tests.gpu_util import rel_err
+from tests.test_gpu_train import build
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_same_tokens(p, ocfg, emb, got, want, expected_len=None):
+    got, want = np.asarray(got), np.asarray(want)
+    n = min(got.shape[1], want.shape[1])
+    diff = np.argwhere(got[:, :n] != want[:, :n])
+    if diff.size == 0:
+        assert got.shape == want.shape, (got.shape, want.shape)
+        return
+    j = int(diff[:, 1].min())                      # first step at which any row differs
+    prefix = torch.from_numpy(want[:, :j].astype(np.int64))
+    nattn = expected_len if expected_len is not None else j
+    dummy = O.make_dummy_input(ocfg, expected_len, nattn, want.shape[0], torch.float64)
+    _, combined, dec_pad = O.create_masks(dummy, prefix, torch.float64)
+    z = O.decode(p, emb.double(), prefix, dec_pad, combined, ocfg, dtype=torch.float64)["recon"][:, -1]
+    for b in np.unique(diff[diff[:, 1] == j][:, 0]):
+        zb = z[b]
+        gap = abs(float(zb[int(got[b, j])] - zb[int(want[b, j])]))
+        assert gap <= 1e-3 * float(zb.max() - zb.min()), f"row {b} step {j}: {got[b, j]} vs {want[b, j]}, gap {gap}"
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("name,cfg_kw,B", [("tiny", TINY, 4), ("cfg1", CFG1, 8)], ids=["tiny", "cfg1"])
+def test_greedy_decode_tokens(name, cfg_kw, B, backend):
+    ocfg, eng = build(cfg_kw, B, backend)
+    p = O.init_params(ocfg, 3, torch.float64)
+    eng.load_params(p)
+    sos, eos = ocfg.vocab_size - 2, ocfg.vocab_size - 1
+    x, _ = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 99, vocab=ocfg.vocab_size)
+    xt = torch.from_numpy(x)
+    want = O.predict(p, xt, ocfg, sos=sos, eos=eos, dtype=torch.float64)
+    eng.encode(xt.cuda())
+    got = eng.decode(None, None, sos, eos, chunk=7).cpu().numpy()
+    assert got.dtype == np.int32 and got[:, 0].tolist() == [sos] * B
+    _assert_same_tokens(p, ocfg, want["embedding"], got, want["recon"].numpy())
+    assert torch.equal(eng.tensor("cls.argmax", dtype=torch.int32).cpu()[:B], want["class"])
+    # from a host embedding (predict_from_embedding): same result
+    got2 = eng.decode(want["embedding"].float().cuda().contiguous(), None, sos, eos).cpu().numpy()
+    _assert_same_tokens(p, ocfg, want["embedding"], got2, want["recon"].numpy())
+
+
+@pytest.mark.parametrize("b_pad,b_eos,cols", [(1.0, 2.4, 5), (3.0, 2.3, 25), (3.0, 2.35, 25)])
+def test_greedy_decode_stops_at_eos_and_masks_generated_pad(b_pad, b_eos, cols):
+    """Output-layer biases chosen (by scanning the oracle) so that (a) rows emit EOS at different early steps
+    and the loop stops once ALL have (5 columns), (b) PAD tokens are generated mid-sequence and must be
+    masked as keys of later steps (create_masks on the prefix), (c) some rows finish and the rest run on."""
+    B = 4
+    ocfg, eng = build(TINY, B, 1)
+    p = O.init_params(ocfg, 5, torch.float64)
+    sos, eos = ocfg.vocab_size - 2, ocfg.vocab_size - 1
+    p["out.b"][0] = b_pad
+    p["out.b"][eos] = b_eos
+    eng.load_params(p)
+    x, _ = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 7, vocab=ocfg.vocab_size)
+    xt = torch.from_numpy(x)
+    want = O.predict(p, xt, ocfg, sos=sos, eos=eos, dtype=torch.float64)
+    assert want["recon"].shape[1] == cols
+    eng.encode(xt.cuda())
+    got = eng.decode(None, None, sos, eos, chunk=3).cpu().numpy()
+    _assert_same_tokens(p, ocfg, want["embedding"], got, want["recon"].numpy())
+
+
+def test_greedy_decode_expected_len_mask():
+    """blind_decoder_mask=False: predict() passes the exact input length, cross-attention keys beyond it are
+    masked (make_dummy_input, sketchformer.py:230-253)."""
+    B = 4
+    ocfg, eng = build(TINY, B, 1, blind_decoder_mask=False)
+    p = O.init_params(ocfg, 1, torch.float64)
+    eng.load_params(p)
+    sos, eos = ocfg.vocab_size - 2, ocfg.vocab_size - 1
+    x, _ = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 11, vocab=ocfg.vocab_size)
+    xt = torch.from_numpy(x)
+    want = O.predict(p, xt, ocfg, sos=sos, eos=eos, dtype=torch.float64)
+    tlen = (xt > 0).sum(-1)
+    eng.encode(xt.cuda())
+    got = eng.decode(None, tlen, sos, eos).cpu().numpy()
+    _assert_same_tokens(p, ocfg, want["embedding"], got, want["recon"].numpy(), expected_len=tlen.float())
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+def test_greedy_decode_continuous(backend):
+    B = 4
+    ocfg, eng = build(TINY, B, backend, use_continuous_data=True)
+    p = O.init_params(ocfg, 2, torch.float64)
+    eng.load_params(p)
+    x, _ = synth.continuous_batch(B, ocfg.max_seq_len, ocfg.n_classes, 13)
+    xt = torch.from_numpy(x)
+    want = O.predict(p, xt, ocfg, dtype=torch.float64)
+    eng.encode(xt.cuda())
+    got = eng.decode(None, None).cpu()
+    assert tuple(got.shape) == tuple(want["recon"].shape)
+    assert got[:, 0].tolist() == [[0., 0., 1., 0., 0.]] * B
+    assert rel_err(got, want["recon"]) < (2e-4 if backend == 1 else 1e-3)
+
+
+def test_golden_tiny_greedy_decode(golden_dir):
+    """Committed fixture: weights after three oracle train steps, greedy decode of the first two sketches."""
+    g = np.load(os.path.join(golden_dir, "tiny_tokens.npz"))
+    ocfg, eng = build(TINY, 2, 0)
+    like = O.init_params(ocfg, 0, torch.float64)
+    p = {k: torch.from_numpy(g[f"p_after/{k}"]).double().reshape(like[k].shape) for k in like}
+    eng.load_params(p)
+    x = torch.from_numpy(g["x"][:2])
+    eng.encode(x.cuda())
+    got = eng.decode(None, None, ocfg.vocab_size - 2, ocfg.vocab_size - 1).cpu().numpy()
+    want = g["pred/recon"]
+    emb = O.encode_from_seq(p, x, ocfg, torch.float64)["embedding"]
+    _assert_same_tokens(p, ocfg, emb, got, want)
+
+
+def test_model_predict_api():
+    """The reference-facing plugin: predict / predict_from_embedding return the reference's keys and types."""
+    from sketchformer_b200.data import get_dataloader_by_name
+    from sketchformer_b200.model import get_model_by_name
+    Model, Loader = get_model_by_name("sketch-transformer-tf2"), get_dataloader_by_name("stroke3-synthetic")
+    ds = Loader(Loader.parse_hparams("max_seq_len=32"), None, n_classes=10)
+    hps = Model.parse_hparams(base="batch_size=4", specific="num_layers=2,d_model=64,dff=128,num_heads=4,lowerdim=32,"
+                                                            "dropout_rate=0.0")
+    model = Model(hps, ds, None, "t")
+    x, y = next(ds.batch_iterator("valid", 4))
+    out = model.predict(x)
+    assert set(out) >= {"embedding", "class", "recon", "attn_weights"}
+    assert out["recon"].dtype == np.int32 and out["recon"].shape[0] == 4 and 2 <= out["recon"].shape[1] <= 33
+    assert out["recon"][:, 0].tolist() == [ds.tokenizer.SOS] * 4
+    assert out["class"].dtype == np.int32 and out["class"].shape == (4,)
+    out2 = model.predict_from_embedding(out["embedding"])
+    assert np.array_equal(out2["recon"], out["recon"]) and np.array_equal(out2["class"], out["class"])
+    # one sketch (1-D input) like the interpolation experiment does
+    one = model.predict(x[0])
+    assert one["recon"].shape[0] == 1

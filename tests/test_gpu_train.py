@@ -36,7 +36,8 @@ pytestmark = pytest.mark.gpu
 def build(cfg_kw, B, backend, precision=2, attn_backend=-1, **flags):
     ocfg = O.OracleConfig(**cfg_kw, **flags)
     c = make_cfg(B, ocfg.max_seq_len, ocfg.d_model, ocfg.dff, ocfg.num_heads, ocfg.num_layers, ocfg.vocab_size,
-                 ocfg.n_classes, ocfg.lowerdim, blind_decoder_mask=ocfg.blind_decoder_mask,
+                 ocfg.n_classes, ocfg.lowerdim, continuous=ocfg.use_continuous_data,
+                 blind_decoder_mask=ocfg.blind_decoder_mask,
                  do_classification=ocfg.do_classification, do_reconstruction=ocfg.do_reconstruction,
                  class_weight=ocfg.class_weight, recon_weight=ocfg.recon_weight, gemm_backend=backend,
                  attn_backend=backend if attn_backend < 0 else attn_backend, gemm_precision=precision)
@@ -202,3 +203,58 @@ def test_ablation_flags():
         for k, ref in grads.items():
             num = float((got[k].double() - ref.double()).norm())
             assert num / max(float(ref.norm()), 1e-4 * G) < 2e-4, (flags, k)
+
+
+CONT_CASES = [("tiny", TINY, 4), ("cfg4-b4", CFG2, 4)]
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("name,cfg_kw,B", CONT_CASES, ids=[c[0] for c in CONT_CASES])
+def test_continuous_train_step_matches_oracle(name, cfg_kw, B, backend):
+    """BASELINE.json configs[3]: use_continuous_data=True — Dense(5->d) input embedding, Dense(5) output
+    layer, MSE + 3-way CE loss with the reference's normalisation (builders/losses.py:43-66), pad flags from
+    the stroke-5 pad bit (builders/utils.py:38-39)."""
+    tol = 2e-4 if backend == 1 else 1e-3
+    ocfg, eng = build(cfg_kw, B, backend, use_continuous_data=True)
+    x, y = synth.continuous_batch(B, ocfg.max_seq_len, ocfg.n_classes, 4321)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    p = O.init_params(ocfg, 0, torch.float64)
+    assert "enc.emb.k" in p and tuple(p["out.k"].shape) == (ocfg.d_model, 5)
+    eng.load_params(p)
+    opt = O.AdamTF(p, ocfg.d_model)
+    eng.train_step(xt.cuda(), yt.cuda(), apply_adam=True)
+    torch.cuda.synchronize()
+    pattern = engine_relu_pattern(eng, ocfg, B)
+    own, tape = {}, {}
+    with O.relu_pattern(pattern, record=own):
+        losses, grads = O.train_step(p, opt, xt, yt, ocfg, tape=tape, dtype=torch.float64)
+    flips = sum(int((own[k] != pattern[k]).sum()) for k in pattern)
+    assert flips <= 1e-3 * sum(pattern[k].numel() for k in pattern)
+    acts = engine_activations(eng, ocfg, B)
+    bad = [(k, rel_err(acts[k], ref)) for k, ref in tape.items() if not rel_err(acts[k], ref) < tol]
+    assert not bad, f"activations off: {bad[:8]}"
+    m = eng.last_step_metrics()
+    for k in ("recon_loss", "class_loss", "total_loss"):
+        assert abs(m[k] - losses[k]) <= tol * abs(losses[k]), (k, m[k], losses[k])
+    assert m["class_acc"] == pytest.approx(losses["class_acc"], abs=1e-12)
+    got = eng.export_grads(grads)
+    G = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
+    for k, ref in grads.items():
+        num = float((got[k].double() - ref.double()).norm())
+        if not num / max(float(ref.double().norm()), 1e-4 * G) < tol:
+            bad.append((k, num / max(float(ref.double().norm()), 1e-4 * G)))
+    assert not bad, f"gradients off: {sorted(bad, key=lambda t: -t[1])[:8]}"
+
+
+def test_golden_tiny_continuous_losses(golden_dir):
+    """The CUDA path reproduces the committed golden losses of the continuous fixture (oracle fp64)."""
+    g = np.load(os.path.join(golden_dir, "tiny_continuous.npz"))
+    ocfg, eng = build(TINY, int(g["x"].shape[0]), 0, use_continuous_data=True)
+    eng.load_params(O.init_params(ocfg, 0, torch.float32))
+    xd, yd = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    for s in range(3):
+        eng.train_step(xd, yd, True)
+        m = eng.last_step_metrics()
+        for k in ("recon_loss", "class_loss", "total_loss"):
+            want = float(g[f"f64/step{s}/{k}"])
+            assert abs(m[k] - want) <= 1e-3 * abs(want), (s, k, m[k], want)

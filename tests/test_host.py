@@ -55,15 +55,17 @@ def test_bad_configs_are_rejected_with_a_message():
     c = make_cfg(8, 64, 130, 512, 8, 4, 1004, 10, 256)     # d_model % heads != 0
     assert lib.skf_param_count(C.byref(c)) < 0
     assert b"num_heads" in lib.skf_last_error()
-    c = make_cfg(8, 64, 128, 512, 8, 4, 1004, 10, 256, continuous=True)
+    c = make_cfg(8, 64, 128, 512, 8, 4, 1002, 10, 256)    # vocab not a multiple of 4
     assert lib.skf_workspace_bytes(C.byref(c)) == 0
-    assert b"continuous" in lib.skf_last_error()
+    assert b"vocab" in lib.skf_last_error()
+    c = make_cfg(8, 64, 128, 512, 8, 4, 0, 10, 256, continuous=True)   # stroke-5 input needs no vocabulary
+    assert lib.skf_workspace_bytes(C.byref(c)) > 0
     with pytest.raises(_lib.SkfError):
         _lib.check(lib.skf_set_option(b"nope", 1), "set_option")
 
 
 def test_product_initialiser_equals_oracle():
-    for kw in (TINY, CFG1):
+    for kw in (TINY, CFG1, dict(TINY, use_continuous_data=True)):
         a = init_params(kw, 0)
         b = O.init_params(O.OracleConfig(**kw), 0)
         assert list(a) == list(b)
