@@ -147,7 +147,13 @@ __device__ __forceinline__ void a2_free(const A2Common& c) {
 // ---------------------------------------------------------------------------------------------------
 // forward.  smem: Q | Ql | K | Kl | V | Vl | pad[256] | barriers     tmem: S/P [0,64)  O [64,96)
 // ---------------------------------------------------------------------------------------------------
-constexpr int A2F_DATA = 2 * A2_T128 + 4 * A2_T64 + A2_MAXT;
+constexpr int A2F_DATA = 2 * A2_T128 + 4 * A2_T64 + A2_MAXT * 4;
+constexpr float A2_LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float a2_ex2(float x) {      // 2^x, MUFU.EX2 (2 ulp; the result is rounded to TF32 anyway)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <bool X3>
 __global__ void __launch_bounds__(128, 3)
 attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
@@ -162,7 +168,7 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
   uint8_t* gQ = c.gen;
   uint8_t* gK = gQ + 2 * A2_T128;
   uint8_t* gV = gK + 2 * A2_T64;
-  uint8_t* pad_s = gV + 2 * A2_T64;
+  float* bias_s = reinterpret_cast<float*>(gV + 2 * A2_T64);
   const uint32_t bar_q = c.bar0, bar_k = c.bar0 + 8, bar_v = c.bar0 + 16, bar_s = c.bar0 + 24, bar_o = c.bar0 + 32;
   const int kmax = a.mode == 2 ? min(a.Tk, q0 + 128) : a.Tk;   // causal: keys above the tile's last row never count
   const int nblk = (kmax + A2_BLK - 1) / A2_BLK;
@@ -175,10 +181,18 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     mbar_arrive_expect_tx(bar_v, A2_T64);
     tma_load_2d(sV, &mV, bar_v, h * A2_DH, b * a.Tk);
   }
-  for (int i = tid; i < A2_MAXT; i += 128)
-    pad_s[i] = (a.key_pad && i < a.Tk) ? a.key_pad[(int64_t)b * a.Tk + i] : 0;
+  // logits are handled in the log2 domain: t = S * (scale*log2e) + bias[key]; bias carries the reference's
+  // additive -1e9 mask (builders/utils.py:93-97) for padded keys and -inf for keys outside the sequence
+  for (int i = tid; i < A2_MAXT; i += 128) {
+    float bj = 0.f;
+    if (i >= a.Tk) bj = -INFINITY;
+    else if (a.mode >= 1 && a.key_pad && a.key_pad[(int64_t)b * a.Tk + i]) bj = A2_MASK_NEG * A2_LOG2E;
+    bias_s[i] = bj;
+  }
   mbar_wait(bar_q, 0);
   if (X3) a2_split(gQ, gQ + A2_T128, A2_T128);
+  const float c1 = a.scale * A2_LOG2E;
+  const int qw = q0 + (tid & ~31);            // first query row of this warp
 
   const uint32_t tS = c.tmem, tO = c.tmem + 64;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
@@ -212,36 +226,52 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     tmem_ld32(tS + lane_off + 32, r1);
     tmem_ld_wait();
     float bmax = -INFINITY;
+    const bool diag = a.mode == 2 && k0 + A2_BLK - 1 > qw;      // warp-uniform: some (q, k) pair has k > q
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s + k0);
 #pragma unroll
-    for (int jj = 0; jj < 32; jj++) {
-      const int kj = k0 + jj;
-      float s = __uint_as_float(r0[jj]) * a.scale;
-      if (a2_masked(a.mode, qi, kj, pad_s[kj & (A2_MAXT - 1)])) s += A2_MASK_NEG;
-      s = kj < a.Tk ? s : -INFINITY;
-      r0[jj] = __float_as_uint(s);
-      bmax = fmaxf(bmax, s);
+    for (int jj = 0; jj < 32; jj += 4) {
+      const float4 bv = b4[jj >> 2];
+      float t0 = fmaf(__uint_as_float(r0[jj]), c1, bv.x), t1 = fmaf(__uint_as_float(r0[jj + 1]), c1, bv.y);
+      float t2 = fmaf(__uint_as_float(r0[jj + 2]), c1, bv.z), t3 = fmaf(__uint_as_float(r0[jj + 3]), c1, bv.w);
+      if (diag) {
+        const int kj = k0 + jj;
+        if (kj > qi) t0 += A2_MASK_NEG * A2_LOG2E;
+        if (kj + 1 > qi) t1 += A2_MASK_NEG * A2_LOG2E;
+        if (kj + 2 > qi) t2 += A2_MASK_NEG * A2_LOG2E;
+        if (kj + 3 > qi) t3 += A2_MASK_NEG * A2_LOG2E;
+      }
+      r0[jj] = __float_as_uint(t0); r0[jj + 1] = __float_as_uint(t1);
+      r0[jj + 2] = __float_as_uint(t2); r0[jj + 3] = __float_as_uint(t3);
+      bmax = fmaxf(fmaxf(bmax, fmaxf(t0, t1)), fmaxf(t2, t3));
     }
 #pragma unroll
-    for (int jj = 0; jj < 32; jj++) {
-      const int kj = k0 + 32 + jj;
-      float s = __uint_as_float(r1[jj]) * a.scale;
-      if (a2_masked(a.mode, qi, kj, pad_s[kj & (A2_MAXT - 1)])) s += A2_MASK_NEG;
-      s = kj < a.Tk ? s : -INFINITY;
-      r1[jj] = __float_as_uint(s);
-      bmax = fmaxf(bmax, s);
+    for (int jj = 0; jj < 32; jj += 4) {
+      const float4 bv = b4[8 + (jj >> 2)];
+      float t0 = fmaf(__uint_as_float(r1[jj]), c1, bv.x), t1 = fmaf(__uint_as_float(r1[jj + 1]), c1, bv.y);
+      float t2 = fmaf(__uint_as_float(r1[jj + 2]), c1, bv.z), t3 = fmaf(__uint_as_float(r1[jj + 3]), c1, bv.w);
+      if (diag) {
+        const int kj = k0 + 32 + jj;
+        if (kj > qi) t0 += A2_MASK_NEG * A2_LOG2E;
+        if (kj + 1 > qi) t1 += A2_MASK_NEG * A2_LOG2E;
+        if (kj + 2 > qi) t2 += A2_MASK_NEG * A2_LOG2E;
+        if (kj + 3 > qi) t3 += A2_MASK_NEG * A2_LOG2E;
+      }
+      r1[jj] = __float_as_uint(t0); r1[jj + 1] = __float_as_uint(t1);
+      r1[jj + 2] = __float_as_uint(t2); r1[jj + 3] = __float_as_uint(t3);
+      bmax = fmaxf(fmaxf(bmax, fmaxf(t0, t1)), fmaxf(t2, t3));
     }
-    const float m_new = fmaxf(m_run, bmax);
-    const float alpha = __expf(m_run - m_new);        // 0 on the first block (m_run = -inf)
+    const float m_new = fmaxf(m_run, bmax);            // finite: key 0 of every block row set exists (k0 < Tk)
+    const float alpha = a2_ex2(m_run - m_new);         // 0 on the first block (m_run = -inf)
     float sum = 0.f;
 #pragma unroll
     for (int jj = 0; jj < 32; jj++) {
-      const float p = round_tf32(__expf(__uint_as_float(r0[jj]) - m_new));
+      const float p = round_tf32(a2_ex2(__uint_as_float(r0[jj]) - m_new));
       sum += p;
       r0[jj] = __float_as_uint(p);
     }
 #pragma unroll
     for (int jj = 0; jj < 32; jj++) {
-      const float p = round_tf32(__expf(__uint_as_float(r1[jj]) - m_new));
+      const float p = round_tf32(a2_ex2(__uint_as_float(r1[jj]) - m_new));
       sum += p;
       r1[jj] = __float_as_uint(p);
     }
@@ -287,7 +317,8 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       for (int jj = 0; jj < 8; jj++)
         dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * inv, __uint_as_float(r[4 * jj + 1]) * inv,
                               __uint_as_float(r[4 * jj + 2]) * inv, __uint_as_float(r[4 * jj + 3]) * inv);
-      if (a.out1) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = m_run + logf(l_run);
+      // natural-log logsumexp of the masked scaled logits (m_run is in the log2 domain)
+      if (a.out1) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = m_run * 0.6931471805599453f + logf(l_run);
     }
   }
   a2_free<128>(c);
@@ -301,8 +332,6 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
 // keys / queries outside the sequence.  dS is accumulated WITHOUT the trailing 1/sqrt(dh), which is
 // applied once to the dQ / dK accumulators in the epilogue.
 // ---------------------------------------------------------------------------------------------------
-constexpr float A2_LOG2E = 1.4426950408889634f;
-
 // ---------------------------------------------------------------------------------------------------
 // backward, dQ.  smem: Q | Ql | dO | dOl | K | Kl | X | Xl | bias[256] | barriers   (X = V block, then the
 // MN-major copy of the K block).   tmem: S [0,64)  dP -> dS [64,128)  dQ [128,160)

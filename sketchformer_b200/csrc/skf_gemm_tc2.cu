@@ -24,6 +24,11 @@
 #include "skf_common.cuh"
 #include "skf_ptx.cuh"
 
+#ifndef SKF_SPLIT_UNROLL_N
+#define SKF_SPLIT_UNROLL_N 8
+#endif
+constexpr int kSplitUnroll = SKF_SPLIT_UNROLL_N;   // float4s in flight per splitter thread
+
 namespace skf {
 
 using namespace ptx;
@@ -338,7 +343,7 @@ gemm2_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           const float4* src = reinterpret_cast<const float4*>(gen + s * C::STAGE);
           float4* dst = reinterpret_cast<float4*>(gen + s * C::STAGE + C::RAW);
           // elementwise, so the (identical) swizzled layouts of the raw and lo tiles do not matter
-#pragma unroll 4
+#pragma unroll kSplitUnroll
           for (int k = tid; k < C::RAW / 16; k += 128) {
             const float4 x = src[k];
             float4 l;

@@ -1,0 +1,481 @@
+// 2-CTA (cta_group::2) variant of the persistent 3xTF32 tcgen05 GEMM in skf_gemm_tc2.cu.
+//
+// Why: in 3xTF32 mode the single-CTA kernel is SHARED-MEMORY-BANDWIDTH bound, not tensor bound.  Per 32-deep
+// k-block a CTA moves 48 KB of TMA writes + 96 KB of hi/lo splitter traffic + 12 MMAs x 12 KB of operand
+// reads = 288 KB through a 128 B/clk crossbar (2250 clk) while the 12 MMAs need only 1536 clk (measured: 62 %
+// of the TF32 peak).  A CTA pair shares the B operand: each CTA stages only HALF of the 256-column B tile
+// (its own 128 columns) and the pair's tensor cores exchange the halves, so per CTA the traffic drops to
+// 32 + 64 + 96 = 192 KB = 1500 clk < 1536 clk: tensor bound again.  The smaller stage (64 KB instead of
+// 96 KB) also buys a third pipeline stage.
+//
+//   cluster tile = 256 (M) x 256 (N); CTA r of the pair owns rows [128 r, 128 r + 128) of A and of the
+//   accumulator (its own TMEM) and stages columns [128 r, 128 r + 128) of B.
+//   warp 0   TMA producer (each CTA: its A rows, its B half -> local full barrier)
+//   warps 6-9 splitter   (each CTA: lo = x - trunc_tf32(x) for its tiles; one arrive per warp on the
+//                         LEADER's xfull barrier, remote for CTA 1)
+//   warp 1   MMA issuer  (leader CTA only): tcgen05.mma.cta_group::2 256x256x8, commits multicast to
+//                         both CTAs' empty / tfull barriers
+//   warps 2-5 epilogue   (each CTA drains its 128 TMEM lanes; tempty arrives go to the leader)
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "skf_common.cuh"
+#include "skf_ptx.cuh"
+
+#ifndef SKF_SPLIT_UNROLL_N
+#define SKF_SPLIT_UNROLL_N 8
+#endif
+constexpr int kSplitUnroll3 = SKF_SPLIT_UNROLL_N;   // float4s in flight per splitter thread
+
+namespace skf {
+
+using namespace ptx;
+
+int make_tmap_2d_typed(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                       uint32_t box_inner, uint32_t box_outer, bool mn_major, bool tf32_convert);
+
+constexpr int T3_BM = 128;                 // rows per CTA (256 per cluster)
+constexpr int T3_BN = 256;                 // columns per cluster tile
+constexpr int T3_BNH = 128;                // B columns staged per CTA
+constexpr int T3_BK = 32;
+constexpr int T3_A_BYTES = T3_BM * 128;    // 16 KB
+constexpr int T3_B_BYTES = T3_BNH * 128;   // 16 KB
+constexpr int T3_RAW = T3_A_BYTES + T3_B_BYTES;
+constexpr int T3_STAGE = 2 * T3_RAW;       // raw + lo tiles: 64 KB
+constexpr int T3_STAGES = 3;
+constexpr int T3_EPI_TILE = 32 * 128;
+constexpr int T3_EPI_BUFS = 2;
+constexpr int T3_EPI_BYTES = 4 * T3_EPI_BUFS * T3_EPI_TILE;   // 32 KB
+constexpr int T3_SMEM = T3_STAGES * T3_STAGE + T3_EPI_BYTES + 1024 + 256;
+constexpr int T3_THREADS = 320;
+constexpr int T3_TMEM_COLS = 512;          // two 256-column accumulators
+
+struct Gemm3Params {
+  int M, N, K;
+  int k_chunk;
+  int mt, nt, splits;   // cluster-tile grid (mt counts 256-row blocks)
+  skf_gemm_epilogue e;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma2_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void t3_tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void t3_tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void t3_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void t3_bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float t3_trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T3_THREADS, 1)
+gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+        const __grid_constant__ CUtensorMap tmY, const Gemm3Params p) {
+  constexpr int S = T3_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;      // identical in both CTAs (same kernel, same layout)
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t epi0 = base + S * T3_STAGE;
+  const uint32_t bar0 = epi0 + T3_EPI_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };               // local: TMA -> splitter
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };        // local: MMA commit (multicast) -> TMA
+  auto xfull_bar = [&](int s) { return bar0 + 8u * (2 * S + s); };    // leader: 8 splitter warps -> MMA
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * S + a); };    // local: MMA commit (multicast) -> epilogue
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * S + 2 + a); };   // leader: 8 epilogue warps -> MMA
+  const uint32_t tmem_slot = bar0 + 8u * (3 * S + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(gen + S * T3_STAGE + T3_EPI_BYTES + 8 * (3 * S + 4));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int nclusters = gridDim.x >> 1;
+  const int ntiles = p.mt * p.nt * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmY);
+    for (int s = 0; s < S; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(xfull_bar(s), 8);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(tmem_slot, T3_TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  auto tile_coords = [&](int t, int& m0, int& n0, int& kb, int& nkb) {
+    const int n = t % p.nt;
+    const int r = t / p.nt;
+    const int m = r % p.mt;
+    const int z = r / p.mt;
+    m0 = m * (2 * T3_BM) + (int)rank * T3_BM;     // this CTA's rows
+    n0 = n * T3_BN;
+    kb = z * p.k_chunk;
+    const int ke = min(p.K, kb + p.k_chunk);
+    nkb = (ke - kb + T3_BK - 1) / T3_BK;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = cluster_id; t < ntiles; t += nclusters) {
+        int m0, n0, kb, nkb;
+        tile_coords(t, m0, n0, kb, nkb);
+        const int nh = n0 + (int)rank * T3_BNH;   // this CTA's half of the B tile
+        for (int i = 0; i < nkb; i++, it++) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), T3_RAW);
+          const uint32_t a_s = base + s * T3_STAGE;
+          const uint32_t b_s = a_s + T3_A_BYTES;
+          const int k0 = kb + i * T3_BK;
+          if (!A_MN) {
+            tma_load_2d(a_s, &tmA, full_bar(s), k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < T3_BM / 32; j++) tma_load_2d(a_s + j * 4096, &tmA, full_bar(s), m0 + 32 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_s, &tmB, full_bar(s), k0, nh);
+          } else {
+#pragma unroll
+            for (int j = 0; j < T3_BNH / 32; j++) tma_load_2d(b_s + j * 4096, &tmB, full_bar(s), nh + 32 * j, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(2 * T3_BM, T3_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      uint32_t it = 0;
+      int ti = 0;
+      for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
+        int m0, n0, kb, nkb;
+        tile_coords(t, m0, n0, kb, nkb);
+        const int a = ti & 1;
+        const uint32_t aph = (ti >> 1) & 1u;
+        mbar_wait_cluster(tempty_bar(a), aph ^ 1u);     // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(a * T3_BN);
+        for (int i = 0; i < nkb; i++, it++) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1u;
+          mbar_wait_cluster(xfull_bar(s), ph);          // both CTAs' raw + lo tiles are in place
+          tc_fence_after();
+          const uint32_t a_s = base + s * T3_STAGE;
+          const uint32_t b_s = a_s + T3_A_BYTES;
+          const uint32_t al_s = a_s + T3_RAW;
+          const uint32_t bl_s = al_s + T3_A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < T3_BK / 8; ks++) {
+            const uint32_t ao = A_MN ? ks * 1024 : ks * 32;
+            const uint32_t bo = B_MN ? ks * 1024 : ks * 32;
+            const uint64_t ad = A_MN ? make_desc_mnmajor(a_s + ao, 4096) : make_desc_kmajor(a_s + ao);
+            const uint64_t bd = B_MN ? make_desc_mnmajor(b_s + bo, 4096) : make_desc_kmajor(b_s + bo);
+            const uint64_t ald = A_MN ? make_desc_mnmajor(al_s + ao, 4096) : make_desc_kmajor(al_s + ao);
+            const uint64_t bld = B_MN ? make_desc_mnmajor(bl_s + bo, 4096) : make_desc_kmajor(bl_s + bo);
+            mma2_tf32_ss(acc, ad, bld, idesc, (i | ks) != 0 ? 1u : 0u);   // small terms first
+            mma2_tf32_ss(acc, ald, bd, idesc, 1u);
+            mma2_tf32_ss(acc, ad, bd, idesc, 1u);
+          }
+          tc_commit2(empty_bar(s));
+        }
+        tc_commit2(tfull_bar(a));
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ epilogue (4 warps, both CTAs)
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    const uint32_t stg0 = epi0 + (uint32_t)(ew * T3_EPI_BUFS) * T3_EPI_TILE;
+    uint8_t* stg0_gen = gen + S * T3_STAGE + (ew * T3_EPI_BUFS) * T3_EPI_TILE;
+    const skf_gemm_epilogue& e = p.e;
+    int ti = 0;
+    uint32_t nstore = 0;
+    for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
+      int m0, n0, kb, nkb;
+      tile_coords(t, m0, n0, kb, nkb);
+      const int a = ti & 1;
+      const uint32_t aph = (ti >> 1) & 1u;
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+      const int mrow0 = m0 + q * 32;
+      const int m = mrow0 + lane;
+      const bool row_ok = m < p.M;
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T3_BN);
+      constexpr int NCH = T3_BN / 32;
+#pragma unroll 1
+      for (int c = 0; c < NCH; c++) {
+        const int nb = n0 + c * 32;
+        const bool live = nb < p.N && mrow0 < p.M;
+        uint32_t r[32];
+        if (live) {
+          tmem_ld32(acc + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+        }
+        if (c == NCH - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+        }
+        if (!live) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+        if (!e.accumulate) {
+          if (e.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (nb + 4 * j < p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + nb) + j);
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+          }
+          if (e.act == SKF_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
+          } else if (e.act == SKF_ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = tanhf(v[j]);
+          }
+          if (e.mask && row_ok) {
+            const float4* mrow = reinterpret_cast<const float4*>(e.mask + (int64_t)m * e.ld_mask + nb);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (nb + 4 * j < p.N) {
+                const float4 k4 = mrow[j];
+                v[4 * j] = k4.x > 0.f ? v[4 * j] : 0.f;
+                v[4 * j + 1] = k4.y > 0.f ? v[4 * j + 1] : 0.f;
+                v[4 * j + 2] = k4.z > 0.f ? v[4 * j + 2] : 0.f;
+                v[4 * j + 3] = k4.w > 0.f ? v[4 * j + 3] : 0.f;
+              }
+          }
+          if (e.resid && row_ok) {
+            const float4* rrow = reinterpret_cast<const float4*>(e.resid + (int64_t)m * e.ld_resid + nb);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (nb + 4 * j < p.N) {
+                const float4 r4 = rrow[j];
+                v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+              }
+          }
+          if (e.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
+          }
+        }
+        const uint32_t buf = nstore % T3_EPI_BUFS;
+        if (lane == 0) t3_bulk_wait_read<T3_EPI_BUFS - 1>();
+        __syncwarp();
+        uint8_t* srow = stg0_gen + buf * T3_EPI_TILE + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          *reinterpret_cast<float4*>(srow + ((j ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t src = stg0 + buf * T3_EPI_TILE;
+          if (e.accumulate) t3_tma_reduce_add_2d(&tmY, src, nb, mrow0);
+          else t3_tma_store_2d(&tmY, src, nb, mrow0);
+          t3_bulk_commit();
+        }
+        nstore++;
+      }
+    }
+    if (lane == 0) t3_bulk_wait_read<0>();
+  } else {
+    // ------------------------------------------------------------------ splitter (4 warps, both CTAs)
+    const int tid = threadIdx.x - 192;
+    uint32_t it = 0;
+    uint32_t xfull_leader[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) xfull_leader[s] = map_to_cta(xfull_bar(s), 0);
+    for (int t = cluster_id; t < ntiles; t += nclusters) {
+      int m0, n0, kb, nkb;
+      tile_coords(t, m0, n0, kb, nkb);
+      for (int i = 0; i < nkb; i++, it++) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1u;
+        mbar_wait(full_bar(s), ph);
+        const float4* src = reinterpret_cast<const float4*>(gen + s * T3_STAGE);
+        float4* dst = reinterpret_cast<float4*>(gen + s * T3_STAGE + T3_RAW);
+#pragma unroll kSplitUnroll3
+        for (int k = tid; k < T3_RAW / 16; k += 128) {
+          const float4 x = src[k];
+          float4 l;
+          l.x = x.x - t3_trunc_tf32(x.x); l.y = x.y - t3_trunc_tf32(x.y);
+          l.z = x.z - t3_trunc_tf32(x.z); l.w = x.w - t3_trunc_tf32(x.w);
+          dst[k] = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          uint32_t target = xfull_leader[0];
+#pragma unroll
+          for (int ss = 1; ss < S; ss++) target = (s == ss) ? xfull_leader[ss] : target;
+          mbar_arrive_cluster(target);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();          // the peer may still read this CTA's smem / signal its barriers until here
+  if (warp == 1) tmem_dealloc2(tmem_base, T3_TMEM_COLS);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static int g3_clusters = 0;
+
+template <bool A_MN, bool B_MN>
+static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SKF_CUDA(cudaFuncSetAttribute(gemm3_k<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
+    attr_done = true;
+  }
+  if (!g3_clusters) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t qc;
+    memset(&qc, 0, sizeof(qc));
+    qc.gridDim = dim3(sms > 1 ? (sms & ~1) : 2);
+    qc.blockDim = dim3(T3_THREADS);
+    qc.dynamicSmemBytes = T3_SMEM;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, gemm3_k<A_MN, B_MN>, &qc) != cudaSuccess || nc <= 0) {
+      cudaGetLastError();
+      nc = sms / 2;
+    }
+    g3_clusters = nc < 1 ? 1 : nc;
+  }
+  const int ntiles = p.mt * p.nt * p.splits;
+  const int ncl = ntiles < g3_clusters ? ntiles : g3_clusters;
+  gemm3_k<A_MN, B_MN><<<2 * ncl, T3_THREADS, T3_SMEM, st>>>(tm[0], tm[1], tm[2], p);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int gemm_tc3_clusters() { return g3_clusters; }
+
+// The pair kernel is only built for the 256-column tile shape and needs at least one full 256-row cluster
+// tile.  Measured on B200 (tools/prof_ops.py, M = 25600): 4-7 % faster than the single-CTA kernel when the
+// weight matrix has >= 256 x 1024 elements (FFN, QKV), 7 % slower on the 256 x 256 projections.
+int gemm_tc3_wanted(int M, int N, int K) { return N > 128 && M > 128 && (long)N * K >= 256L * 768; }
+
+int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
+             int64_t ldy, int M, int N, int K, const skf_gemm_epilogue* epi, cudaStream_t st) {
+  skf_gemm_epilogue e;
+  memset(&e, 0, sizeof(e));
+  if (epi) e = *epi;
+  int split = e.split_k > 1 ? e.split_k : 1;
+  SKF_REQUIRE(split == 1 || e.accumulate, SKF_ERR_BAD_ARG, "gemm: split_k needs accumulate");
+  SKF_REQUIRE(!(e.accumulate && (e.bias || e.resid || e.mask || e.act)), SKF_ERR_BAD_ARG,
+              "gemm: accumulate excludes other epilogue terms");
+  const bool a_mn = !(sa_k == 1);
+  const bool b_mn = !(sb_k == 1);
+  Gemm3Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.k_chunk = cdiv(cdiv(K, split), T3_BK) * T3_BK;
+  p.splits = cdiv(K, p.k_chunk);
+  p.mt = cdiv(M, 2 * T3_BM);
+  p.nt = cdiv(N, T3_BN);
+  p.e = e;
+  p.e.a_lo = p.e.b_lo = nullptr;
+  CUtensorMap tm[3];
+  // raw fp32 bits in shared memory (the splitter needs them): plain FLOAT32 maps
+  if (!a_mn) SKF_TRY(make_tmap_2d_typed(&tm[0], A, (uint64_t)K, (uint64_t)M, (uint64_t)(M == 1 ? K : sa_m), T3_BK, T3_BM, false, false));
+  else SKF_TRY(make_tmap_2d_typed(&tm[0], A, (uint64_t)M, (uint64_t)K, (uint64_t)sa_k, 32, T3_BK, true, false));
+  if (!b_mn) SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, T3_BK, (uint32_t)T3_BNH, false, false));
+  else SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, T3_BK, true, false));
+  SKF_TRY(make_tmap_2d_typed(&tm[2], Y, (uint64_t)N, (uint64_t)M, (uint64_t)ldy, 32, 32, false, false));
+  if (!a_mn && !b_mn) return launch_tc3<false, false>(tm, p, st);
+  if (!a_mn && b_mn) return launch_tc3<false, true>(tm, p, st);
+  if (a_mn && !b_mn) return launch_tc3<true, false>(tm, p, st);
+  return launch_tc3<true, true>(tm, p, st);
+}
+
+}  // namespace skf

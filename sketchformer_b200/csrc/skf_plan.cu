@@ -22,6 +22,10 @@ int gemm_tc2_supported(const float*, int64_t, int64_t, const float*, int64_t, in
                        int, const skf_gemm_epilogue*);
 int gemm_tc2(const float*, int64_t, int64_t, const float*, int64_t, int64_t, float*, int64_t, int, int, int,
              const skf_gemm_epilogue*, int, cudaStream_t);
+int gemm_tc3(const float*, int64_t, int64_t, const float*, int64_t, int64_t, float*, int64_t, int, int, int,
+             const skf_gemm_epilogue*, cudaStream_t);
+int gemm_tc3_wanted(int, int, int);
+int g_gemm_pair = 1;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
 int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
 int attn_fwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
                 const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
@@ -354,12 +358,16 @@ struct Gemm {
     if (!P->round_ops) e.round_tf32 = 0;
     if (e.accumulate) {
       // split-K so that the persistent grid (one CTA per SM) has about one tile per SM
-      const long tiles = tc ? (long)cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256))
-                            : (long)cdiv(M, 64) * cdiv(N, 64);
-      int want = (int)((tc ? 148 : 2 * 148) / tiles);
+      const bool pair = tc && x3 && g_gemm_pair && gemm_tc3_wanted(M, N, K);
+      const long tiles = pair ? (long)cdiv(M, 256) * cdiv(N, 256)
+                         : tc ? (long)cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256))
+                              : (long)cdiv(M, 64) * cdiv(N, 64);
+      int want = (int)((pair ? 74 : tc ? 148 : 2 * 148) / tiles);
       int maxs = K / 256 > 0 ? K / 256 : 1;
       e.split_k = want < 1 ? 1 : (want > maxs ? maxs : want);
     }
+    if (tc && x3 && g_gemm_pair && gemm_tc3_wanted(M, N, K))
+      return gemm_tc3(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, st);
     return tc ? gemm_tc2(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, x3 ? 1 : 0, st)
               : gemm_simt(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, st);
   }
@@ -803,6 +811,10 @@ int skf_split_lo(const float* x, float* lo, int64_t n, void* stream) {
 }
 
 int skf_set_option(const char* name, int value) {
+  if (name && strcmp(name, "gemm_pair") == 0) {
+    skf::g_gemm_pair = value ? 1 : 0;
+    return SKF_OK;
+  }
   if (name && strcmp(name, "tma_tf32") == 0) {
     skf::g_tma_tf32_type = value ? 1 : 0;
     return SKF_OK;
@@ -980,6 +992,11 @@ int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
     return gemm_tc2(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, backend == 2, as_stream(stream));
   if (backend == 3)                      // first-generation (one tile per CTA) tcgen05 kernel, kept for A/B runs
     return gemm_tc(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
+  if (backend == 5) {                    // 3xTF32 on CTA pairs (cta_group::2), 256 x 256 cluster tiles
+    SKF_REQUIRE(gemm_tc2_supported(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi), SKF_ERR_BAD_ALIGN,
+                "gemm (pair): operand strides/alignment not TMA-compatible");
+    return gemm_tc3(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
+  }
   return gemm_simt(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
 }
 

@@ -364,6 +364,23 @@ def test_gemm_tcgen05_3xtf32(lib, name, a_mn, b_mn, M, N, K):
     assert _gemm_case(M, N, K, a_mn, b_mn, 2, 21, bias=True, act=2) < 2e-4
 
 
+PAIR_SHAPES = [(256, 256, 32), (512, 256, 64), (200, 1004, 96), (1600, 768, 256), (384, 512, 4000),
+               (3000, 1024, 256), (25472, 256, 1024)]
+
+
+@pytest.mark.parametrize("name,a_mn,b_mn", MAJORS)
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+def test_gemm_tcgen05_pair_3xtf32(lib, name, a_mn, b_mn, M, N, K):
+    """backend 5: the 3xTF32 product on CTA pairs (tcgen05 cta_group::2, 256x256 cluster tiles, each CTA
+    stages half of the B tile); ragged M / N / K tails, all four operand majors, every epilogue."""
+    if M > 20000 and name != "fwd":
+        pytest.skip("full-size schedule checked once")
+    assert _gemm_case(M, N, K, a_mn, b_mn, 5, 17) < TOL_X3
+    assert _gemm_case(M, N, K, a_mn, b_mn, 5, 18, bias=True, act=1, resid=True) < TOL_X3
+    assert _gemm_case(M, N, K, a_mn, b_mn, 5, 19, mask=True) < TOL_X3
+    assert _gemm_case(M, N, K, a_mn, b_mn, 5, 20, split_k=3) < TOL_X3
+
+
 def test_gemm_tcgen05_3xtf32_beats_single_pass(lib):
     g = torch.Generator().manual_seed(13)
     for (M, N, K) in ((512, 256, 256), (300, 1024, 256), (256, 512, 1000)):

@@ -21,7 +21,7 @@ if what in ("gemm", "all"):
     b = torch.zeros(N, device="cuda")
     Y = torch.empty(M, N, device="cuda")
     import time
-    for backend in (2, 0, 3):
+    for backend in (2, 5, 0, 3):
         for _ in range(reps):
             gemm(X, K, 1, W, N, 1, Y, N, M, N, K, backend, bias=b, act=1)
         torch.cuda.synchronize()
@@ -33,6 +33,41 @@ if what in ("gemm", "all"):
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 20
         print(f"FFN-1 gemm backend {backend}: {us:.1f} us  {2.0 * M * N * K / us / 1e6:.1f} TFLOP/s (algorithmic)")
+    for (m, n, k, nm) in ((M, K, N, "FFN-2 fwd"), (M, 3 * K, K, "QKV fwd"), (M, K, K, "WO fwd")):
+        Xa = torch.randn(m, k, device="cuda"); Wb = torch.randn(k, n, device="cuda"); Yc = torch.empty(m, n, device="cuda")
+        for backend in (2, 5):
+            for _ in range(reps):
+                gemm(Xa, k, 1, Wb, n, 1, Yc, n, m, n, k, backend)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                gemm(Xa, k, 1, Wb, n, 1, Yc, n, m, n, k, backend)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / 20
+            print(f"{nm} backend {backend}: {us:.1f} us  {2.0 * m * n * k / us / 1e6:.1f} TFLOP/s (algorithmic)")
+        # dgrad (B K-major) and wgrad (both MN-major, split-K) of the same layer
+        dX = torch.empty(m, k, device="cuda")
+        dW = torch.zeros(k, n, device="cuda")
+        for backend in (2, 5):
+            for what2 in ("dgrad", "wgrad"):
+                def run():
+                    if what2 == "dgrad":
+                        gemm(Yc, n, 1, Wb, 1, n, dX, k, m, k, n, backend)
+                    else:
+                        gemm(Xa, 1, k, Yc, n, 1, dW, n, k, n, m, backend, accumulate=1, split_k=max(1, min(m // 256, (74 if backend == 5 else 148) // max(1, ((k + 255) // 256 if backend == 5 else (k + 127) // 128) * ((n + 255) // 256)))))
+                for _ in range(reps):
+                    run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    run()
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / 20
+                print(f"{nm}->{what2} backend {backend}: {us:.1f} us  {2.0 * m * n * k / us / 1e6:.1f} TFLOP/s")
     # FFN-2 shape with residual
     W2 = torch.randn(N, K, device="cuda")
     Y2 = torch.empty(M, K, device="cuda")
