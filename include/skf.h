@@ -64,7 +64,10 @@ typedef struct skf_cfg {
   int32_t gemm_backend;       /* 0 = tcgen05 TF32 tensor-core GEMMs, 1 = SIMT fp32 (debug)*/
   int32_t attn_backend;       /* 0 = default, 1 = SIMT fp32 (debug)                      */
   int32_t gemm_precision;     /* tcgen05 GEMMs: 0 = TF32 everywhere, 1 = 3xTF32 (fp32-accurate) forward
-                                 + TF32 backward, 2 = 3xTF32 everywhere                     */
+                                 + TF32 backward, 2 = 3xTF32 everywhere, 3 = like 2 with single-pass
+                                 TF32 weight gradients                                        */
+  float dropout_rate;         /* models/sketchformer.py:31; applied by skf_train_step only (training=True) */
+  uint32_t dropout_seed;      /* seed of the counter-based dropout masks (see skf_dropout)   */
 } skf_cfg;
 
 const char* skf_last_error(void);
@@ -95,6 +98,13 @@ int skf_param_table(const skf_cfg* cfg, skf_param_entry* out, int cap);
  * out[b,t,:] = table[tok[b,t],:] * sqrt(d) + PE[t,:].  tok has row stride tok_ld (int64).   */
 int skf_embed_fwd(const int64_t* tok, int64_t tok_ld, const float* table, const float* pe,
                   float* out, int B, int T, int d, int V, int round_tf32, void* stream);
+/* tf.keras.layers.Dropout (inverted dropout, training=True) with a counter-based mask: element i of dropout
+ * site `site` is kept iff hash(seed, site, *step, i) >= rate * 2^24 (top 24 bits of two murmur3 finalisers)
+ * and scaled by 1/(1-rate); `step` is a device pointer to optimizer.iterations, so every train step draws a
+ * new mask, the backward pass regenerates it, and nothing is stored.  y may alias x.  Used after the input
+ * embeddings (transformer.py:296, 334) and on the gradient flowing back through them.              */
+int skf_dropout(const float* x, float* y, int64_t n, float rate, uint32_t seed, uint32_t site,
+                const int64_t* step, void* stream);
 /* dtable[tok[b,t],:] += dout[b,t,:] * sqrt(d)   (IndexedSlices scatter-add)     */
 int skf_embed_bwd(const int64_t* tok, int64_t tok_ld, const float* dout, float* dtable, int B,
                   int T, int d, int V, void* stream);
@@ -172,10 +182,22 @@ int skf_attn_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
 int skf_add_layernorm_fwd(const float* a, const float* b, const float* bias, const float* gamma,
                           const float* beta, float* s, float* y, float* mean, float* rstd,
                           int rows, int d, int round_tf32, void* stream);
+/* Same with dropout on the sublayer output (transformer.py:217-218, 221-222, 250-260):
+ * s = a + dropout(b + bias), mask as in skf_dropout with element index row*d + col.          */
+int skf_add_dropout_layernorm_fwd(const float* a, const float* b, const float* bias, const float* gamma,
+                                  const float* beta, float* s, float* y, float* mean, float* rstd,
+                                  int rows, int d, float rate, uint32_t seed, uint32_t site,
+                                  const int64_t* step, void* stream);
 /* ds = dLN(dy); dgamma += .., dbeta += .. (accumulated atomically into zeroed buffers)      */
 int skf_layernorm_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
                       const float* gamma, float* ds, float* dgamma, float* dbeta, int rows,
                       int d, int round_tf32, void* stream);
+/* Same, additionally writing ds_drop = dropout_mask(ds) (the gradient of the sublayer output b of
+ * skf_add_dropout_layernorm_fwd; ds itself is the gradient of the residual input a).          */
+int skf_layernorm_dropout_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
+                              const float* gamma, float* ds, float* ds_drop, float* dgamma, float* dbeta,
+                              int rows, int d, float rate, uint32_t seed, uint32_t site,
+                              const int64_t* step, void* stream);
 /* out[n] += sum_m x[m,n]  (bias gradients)                                                  */
 int skf_colsum(const float* x, int64_t ldx, float* out, int M, int N, void* stream);
 

@@ -218,11 +218,38 @@ def layer_norm(p, name, x, eps=1e-6):
     return (x - mu) * torch.rsqrt(var + eps) * p[name + ".g"] + p[name + ".b"]
 
 
-def _dropout(x, rate, training, gen):
+_DROPOUT_MASKS = None   # test hook, see dropout_masks()
+
+
+class dropout_masks:
+    """Context manager for the parity tests: inside it every Dropout layer takes its keep-mask from
+    `provider(site_name, shape) -> bool array` instead of torch's RNG (TF's stateful dropout RNG cannot be
+    reproduced by any other implementation; the CUDA path's counter-based masks can, oracle/dropout_rng.py).
+    Site names: enc.x0, enc.l{i}.attn, enc.l{i}.ffn, dec.x0, dec.l{i}.attn1, dec.l{i}.attn2, dec.l{i}.ffn."""
+
+    def __init__(self, provider):
+        self.provider = provider
+
+    def __enter__(self):
+        global _DROPOUT_MASKS
+        self.prev, _DROPOUT_MASKS = _DROPOUT_MASKS, self.provider
+        return self
+
+    def __exit__(self, *exc):
+        global _DROPOUT_MASKS
+        _DROPOUT_MASKS = self.prev
+
+
+def _dropout(x, rate, training, gen, site=None):
+    """tf.keras.layers.Dropout: inverted dropout, x * keep * 1/(1-rate) when training."""
     if not training or rate == 0.0:
         return x
-    keep = (torch.rand(x.shape, generator=gen) >= rate).to(x.dtype)
-    return x * keep / (1.0 - rate)
+    if _DROPOUT_MASKS is not None and site is not None:
+        keep = torch.as_tensor(_DROPOUT_MASKS(site, tuple(x.shape))).to(x.dtype)
+    else:
+        keep = (torch.rand(x.shape, generator=gen) >= rate).to(x.dtype)
+    scale = torch.tensor(1.0, dtype=torch.float32) / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(rate, dtype=torch.float32))
+    return x * keep * scale.to(x.dtype)
 
 
 def split_heads(x, H):
@@ -300,14 +327,14 @@ def encoder(p, x, mask, cfg, training, gen, tape, dtype):
     h = embed_input(p, "enc", x, cfg, dtype)
     if tape is not None:
         tape["enc.x0"] = h
-    h = _dropout(h, cfg.dropout_rate, training, gen)
+    h = _dropout(h, cfg.dropout_rate, training, gen, "enc.x0")
     for i in range(cfg.num_layers):
         n = f"enc.l{i}"
         a, _ = mha(p, n + ".mha", h, h, h, mask, cfg.num_heads, tape)
-        a = _dropout(a, cfg.dropout_rate, training, gen)
+        a = _dropout(a, cfg.dropout_rate, training, gen, n + ".attn")
         out1 = layer_norm(p, n + ".ln1", h + a)
         ff = ffn(p, n + ".ffn", out1)
-        ff = _dropout(ff, cfg.dropout_rate, training, gen)
+        ff = _dropout(ff, cfg.dropout_rate, training, gen, n + ".ffn")
         h = layer_norm(p, n + ".ln2", out1 + ff)
         if tape is not None:
             tape[n + ".out1"] = out1
@@ -351,17 +378,17 @@ def decoder(p, x, enc_output, look_ahead_mask, padding_mask, cfg, training, gen,
     h = embed_input(p, "dec", x, cfg, dtype)
     if tape is not None:
         tape["dec.x0"] = h
-    h = _dropout(h, cfg.dropout_rate, training, gen)
+    h = _dropout(h, cfg.dropout_rate, training, gen, "dec.x0")
     for i in range(cfg.num_layers):
         n = f"dec.l{i}"
         a1, w1 = mha(p, n + ".mha1", h, h, h, look_ahead_mask, cfg.num_heads, tape)
-        a1 = _dropout(a1, cfg.dropout_rate, training, gen)
+        a1 = _dropout(a1, cfg.dropout_rate, training, gen, n + ".attn1")
         out1 = layer_norm(p, n + ".ln1", a1 + h)
         a2, w2 = mha(p, n + ".mha2", enc_output, enc_output, out1, padding_mask, cfg.num_heads, tape)
-        a2 = _dropout(a2, cfg.dropout_rate, training, gen)
+        a2 = _dropout(a2, cfg.dropout_rate, training, gen, n + ".attn2")
         out2 = layer_norm(p, n + ".ln2", a2 + out1)
         ff = ffn(p, n + ".ffn", out2)
-        ff = _dropout(ff, cfg.dropout_rate, training, gen)
+        ff = _dropout(ff, cfg.dropout_rate, training, gen, n + ".ffn")
         h = layer_norm(p, n + ".ln3", ff + out2)
         attention_weights[f"decoder_layer{i + 1}_block1"] = w1
         attention_weights[f"decoder_layer{i + 1}_block2"] = w2

@@ -16,7 +16,8 @@ class SkfCfg(C.Structure):
                                          "blind_decoder_mask", "do_classification", "do_reconstruction",
                                          "warmup_steps")] + \
                [(n, C.c_float) for n in ("class_weight", "recon_weight", "adam_beta1", "adam_beta2", "adam_eps")] + \
-               [(n, C.c_int32) for n in ("world_size", "gemm_backend", "attn_backend", "gemm_precision")]
+               [(n, C.c_int32) for n in ("world_size", "gemm_backend", "attn_backend", "gemm_precision")] + \
+               [("dropout_rate", C.c_float), ("dropout_seed", C.c_uint32)]
 
 
 class SkfParamEntry(C.Structure):
@@ -40,6 +41,7 @@ SIGNATURES = {
     "skf_param_count": (L, [C.POINTER(SkfCfg)]),
     "skf_param_table": (I, [C.POINTER(SkfCfg), C.POINTER(SkfParamEntry), I]),
     "skf_embed_fwd": (I, [P, L, P, P, P, I, I, I, I, I, P]),
+    "skf_dropout": (I, [P, P, L, F, C.c_uint32, C.c_uint32, P, P]),
     "skf_embed_bwd": (I, [P, L, P, P, I, I, I, I, P]),
     "skf_positional_encoding": (I, [P, I, I, P]),
     "skf_pad_flags": (I, [P, L, P, I, I, P]),
@@ -53,6 +55,8 @@ SIGNATURES = {
     "skf_attn_bwd": (I, [P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, P]),
     "skf_add_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "skf_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, P]),
+    "skf_add_dropout_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, F, C.c_uint32, C.c_uint32, P, P]),
+    "skf_layernorm_dropout_bwd": (I, [P, P, P, P, P, P, P, P, P, I, I, F, C.c_uint32, C.c_uint32, P, P]),
     "skf_colsum": (I, [P, L, P, I, I, P]),
     "skf_pool_fwd": (I, [P, P, P, P, P, I, I, I, I, I, P]),
     "skf_pool_bwd": (I, [P, P, P, P, P, P, I, P, P, I, I, I, I, I, P]),

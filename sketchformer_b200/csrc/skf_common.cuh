@@ -64,6 +64,30 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// Counter-based dropout mask (tf.keras.layers.Dropout, builders/layers/transformer.py:217,221,250,255,259,296,334):
+// keep(element) is a pure function of (seed, site, optimizer step, element index), so the backward pass and a
+// CUDA-graph replay regenerate the mask instead of storing it, and the oracle reproduces it bit-exactly
+// (oracle/dropout_rng.py).  Two murmur3 finalisers; the top 24 bits are compared with rate * 2^24.
+struct DropSpec {
+  float scale;              // 1 / (1 - rate); rate == 0 <=> thresh == 0 (no dropout)
+  uint32_t thresh;          // (uint32)(rate * 2^24)
+  uint32_t seed;
+  uint32_t site;
+  const int64_t* step;      // device pointer to optimizer.iterations
+};
+__device__ __forceinline__ uint32_t skf_fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+// key = per-launch constant skf_drop_key(); returns x kept (scaled) or 0
+__device__ __forceinline__ uint32_t skf_drop_key(const DropSpec& d) {
+  return d.seed ^ ((uint32_t)(*d.step) * 0x632BE5ABu);
+}
+__device__ __forceinline__ float skf_drop_apply(float x, uint32_t key, uint32_t site, uint32_t idx, uint32_t thresh,
+                                                float scale) {
+  const uint32_t h = skf_fmix32(skf_fmix32(idx + 0x9E3779B9u * (site + 1u)) ^ key);
+  return (h >> 8) >= thresh ? x * scale : 0.f;
+}
 #endif
 
 // ---- internal launchers shared between the C ABI and the plan ------------------------------

@@ -437,7 +437,10 @@ int gemm_tc2(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
               "gemm: accumulate excludes other epilogue terms");
   const bool a_mn = !(sa_k == 1);
   const bool b_mn = !(sb_k == 1);
-  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  // 3xTF32 with a single 256-column tile per row block (N <= 256, e.g. the d_model-wide projections): 128-column
+  // tiles double the tile count (better wave quantisation on 148 SMs) and buy a third smem stage; measured
+  // 8-18 % faster on B200 (FFN-2 25600x1024x256: 91.8 -> 74.9 us).  Split-K weight gradients keep 256.
+  const int BN = N <= 64 ? 64 : ((N <= 128 || (x3 && N <= 256 && !e.accumulate)) ? 128 : 256);
   Gemm2Params p;
   p.M = M; p.N = N; p.K = K;
   p.k_chunk = cdiv(cdiv(K, split), T2_BK) * T2_BK;

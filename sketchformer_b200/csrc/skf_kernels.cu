@@ -207,13 +207,14 @@ __global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restric
                              const float* __restrict__ bias, const float* __restrict__ gamma,
                              const float* __restrict__ beta, float* __restrict__ s_out,
                              float* __restrict__ y, float* __restrict__ mean_out,
-                             float* __restrict__ rstd_out, int rows, int d, int rnd) {
+                             float* __restrict__ rstd_out, int rows, int d, int rnd, DropSpec dr) {
   int row = blockIdx.x * blockDim.y + threadIdx.y;
   if (row >= rows) return;
   int lane = threadIdx.x;
   int nv = d / 4;
   float4 v[LN_NV];
   float sum = 0.f;
+  const uint32_t dkey = dr.thresh ? skf_drop_key(dr) : 0u;
 #pragma unroll
   for (int k = 0; k < LN_NV; k++) {
     int c = lane + k * 32;
@@ -224,6 +225,13 @@ __global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restric
         if (bias) {
           float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
           z.x += bb.x; z.y += bb.y; z.z += bb.z; z.w += bb.w;
+        }
+        if (dr.thresh) {          // Dropout on the sublayer output, before the residual add
+          const uint32_t e0 = (uint32_t)row * (uint32_t)d + 4u * c;
+          z.x = skf_drop_apply(z.x, dkey, dr.site, e0, dr.thresh, dr.scale);
+          z.y = skf_drop_apply(z.y, dkey, dr.site, e0 + 1, dr.thresh, dr.scale);
+          z.z = skf_drop_apply(z.z, dkey, dr.site, e0 + 2, dr.thresh, dr.scale);
+          z.w = skf_drop_apply(z.w, dkey, dr.site, e0 + 3, dr.thresh, dr.scale);
         }
         x.x += z.x; x.y += z.y; x.z += z.z; x.w += z.w;
       }
@@ -272,8 +280,9 @@ __global__ void __launch_bounds__(256) ln_bwd_k(const float* __restrict__ dy, co
                          const float* __restrict__ mean, const float* __restrict__ rstd,
                          const float* __restrict__ gamma, float* __restrict__ ds,
                          float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d,
-                         int rnd) {
+                         int rnd, float* __restrict__ ds_drop, DropSpec dr) {
   extern __shared__ float sm[];  // [2][d]
+  const uint32_t dkey = (ds_drop && dr.thresh) ? skf_drop_key(dr) : 0u;
   int lane = threadIdx.x, w = threadIdx.y, nw = blockDim.y;
   int nv = d / 4;
   float4 ag[LN_NV], ab[LN_NV];
@@ -313,6 +322,16 @@ __global__ void __launch_bounds__(256) ln_bwd_k(const float* __restrict__ dy, co
         o.z = maybe_round(rs * (g[k].z - c1 - xh[k].z * c2), rnd);
         o.w = maybe_round(rs * (g[k].w - c1 - xh[k].w * c2), rnd);
         reinterpret_cast<float4*>(ds + (int64_t)row * d)[c] = o;
+        if (ds_drop) {
+          if (dr.thresh) {
+            const uint32_t e0 = (uint32_t)row * (uint32_t)d + 4u * c;
+            o.x = skf_drop_apply(o.x, dkey, dr.site, e0, dr.thresh, dr.scale);
+            o.y = skf_drop_apply(o.y, dkey, dr.site, e0 + 1, dr.thresh, dr.scale);
+            o.z = skf_drop_apply(o.z, dkey, dr.site, e0 + 2, dr.thresh, dr.scale);
+            o.w = skf_drop_apply(o.w, dkey, dr.site, e0 + 3, dr.thresh, dr.scale);
+          }
+          reinterpret_cast<float4*>(ds_drop + (int64_t)row * d)[c] = o;
+        }
       }
     }
   }
@@ -330,6 +349,22 @@ __global__ void __launch_bounds__(256) ln_bwd_k(const float* __restrict__ dy, co
   for (int c = threadIdx.y * 32 + lane; c < d; c += nw * 32) {
     atomicAdd(dgamma + c, sm[c]);
     atomicAdd(dbeta + c, sm[d + c]);
+  }
+}
+
+// y[i] = keep(i) ? x[i] / (1 - rate) : 0   (tf.keras.layers.Dropout, training=True)
+__global__ void dropout_k(const float* x, float* y, int64_t n, DropSpec dr) {
+  const uint32_t key = skf_drop_key(dr);
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(x + i);
+    v.x = skf_drop_apply(v.x, key, dr.site, (uint32_t)i, dr.thresh, dr.scale);
+    v.y = skf_drop_apply(v.y, key, dr.site, (uint32_t)i + 1, dr.thresh, dr.scale);
+    v.z = skf_drop_apply(v.z, key, dr.site, (uint32_t)i + 2, dr.thresh, dr.scale);
+    v.w = skf_drop_apply(v.w, key, dr.site, (uint32_t)i + 3, dr.thresh, dr.scale);
+    *reinterpret_cast<float4*>(y + i) = v;
+  } else {
+    for (; i < n; i++) y[i] = skf_drop_apply(x[i], key, dr.site, (uint32_t)i, dr.thresh, dr.scale);
   }
 }
 
@@ -748,6 +783,48 @@ int skf_cont_loss(const float* pred, int64_t ldp, const float* real, int64_t rea
   return SKF_OK;
 }
 
+static DropSpec make_dropout(float rate, uint32_t seed, uint32_t site, const int64_t* step) {
+  DropSpec dr;
+  dr.scale = 1.0f / (1.0f - rate);
+  dr.thresh = (uint32_t)(rate * 16777216.0f);
+  dr.seed = seed; dr.site = site; dr.step = step;
+  return dr;
+}
+static int check_dropout(float rate, const int64_t* step) {
+  SKF_REQUIRE(rate >= 0.f && rate < 1.f, SKF_ERR_BAD_ARG, "dropout rate %f outside [0, 1)", (double)rate);
+  SKF_REQUIRE(rate == 0.f || step != nullptr, SKF_ERR_BAD_ARG, "dropout needs the device step counter");
+  return SKF_OK;
+}
+
+int skf_dropout(const float* x, float* y, int64_t n, float rate, uint32_t seed, uint32_t site, const int64_t* step,
+                void* stream) {
+  SKF_REQUIRE(x && y && n > 0, SKF_ERR_BAD_ARG, "dropout: bad argument");
+  SKF_TRY(check_dropout(rate, step));
+  SKF_REQUIRE(rate > 0.f, SKF_ERR_BAD_ARG, "dropout: rate must be > 0 (skip the call otherwise)");
+  SKF_REQUIRE(n < (int64_t)1 << 32, SKF_ERR_BAD_SHAPE, "dropout: more than 2^32 elements per site");
+  dropout_k<<<cdiv(cdiv(n, 4), 256), 256, 0, as_stream(stream)>>>(x, y, n, make_dropout(rate, seed, site, step));
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_add_dropout_layernorm_fwd(const float* a, const float* b, const float* bias, const float* gamma,
+                                  const float* beta, float* s, float* y, float* mean, float* rstd, int rows, int d,
+                                  float rate, uint32_t seed, uint32_t site, const int64_t* step, void* stream) {
+  SKF_REQUIRE(d % 4 == 0 && d <= 128 * LN_MAX_VEC, SKF_ERR_BAD_SHAPE, "layernorm: d=%d unsupported", d);
+  SKF_TRY(check_dropout(rate, step));
+  SKF_REQUIRE(rate == 0.f || b != nullptr, SKF_ERR_BAD_ARG, "layernorm: dropout needs the sublayer operand b");
+  dim3 blk(32, 8);
+  const int grid = cdiv(rows, 8);
+  cudaStream_t st = as_stream(stream);
+  DropSpec dr = make_dropout(rate, seed, site, step);
+  if (d <= 128) add_ln_fwd_k<1><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
+  else if (d <= 256) add_ln_fwd_k<2><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
+  else if (d <= 512) add_ln_fwd_k<4><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
+  else add_ln_fwd_k<8><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
 int skf_add_layernorm_fwd(const float* a, const float* b, const float* bias, const float* gamma,
                           const float* beta, float* s, float* y, float* mean, float* rstd,
                           int rows, int d, int round_tf32, void* stream) {
@@ -755,17 +832,38 @@ int skf_add_layernorm_fwd(const float* a, const float* b, const float* bias, con
   dim3 blk(32, 8);
   const int grid = cdiv(rows, 8);
   cudaStream_t st = as_stream(stream);
-  if (d <= 128) add_ln_fwd_k<1><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32);
-  else if (d <= 256) add_ln_fwd_k<2><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32);
-  else if (d <= 512) add_ln_fwd_k<4><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32);
-  else add_ln_fwd_k<8><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32);
+  DropSpec dr = make_dropout(0.f, 0, 0, nullptr);
+  if (d <= 128) add_ln_fwd_k<1><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
+  else if (d <= 256) add_ln_fwd_k<2><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
+  else if (d <= 512) add_ln_fwd_k<4><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
+  else add_ln_fwd_k<8><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
+}
+
+static int ln_bwd_launch(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
+                         float* ds, float* ds_drop, float* dgamma, float* dbeta, int rows, int d, int round_tf32,
+                         DropSpec dr, void* stream);
+
+int skf_layernorm_dropout_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
+                              const float* gamma, float* ds, float* ds_drop, float* dgamma, float* dbeta, int rows,
+                              int d, float rate, uint32_t seed, uint32_t site, const int64_t* step, void* stream) {
+  SKF_TRY(check_dropout(rate, step));
+  SKF_REQUIRE(ds_drop != nullptr, SKF_ERR_BAD_ARG, "layernorm_dropout_bwd: ds_drop is NULL");
+  return ln_bwd_launch(dy, s, mean, rstd, gamma, ds, ds_drop, dgamma, dbeta, rows, d, 0,
+                       make_dropout(rate, seed, site, step), stream);
 }
 
 int skf_layernorm_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
                       const float* gamma, float* ds, float* dgamma, float* dbeta, int rows,
                       int d, int round_tf32, void* stream) {
+  return ln_bwd_launch(dy, s, mean, rstd, gamma, ds, nullptr, dgamma, dbeta, rows, d, round_tf32,
+                       make_dropout(0.f, 0, 0, nullptr), stream);
+}
+
+static int ln_bwd_launch(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
+                         float* ds, float* ds_drop, float* dgamma, float* dbeta, int rows, int d, int round_tf32,
+                         DropSpec dr, void* stream) {
   SKF_REQUIRE(d % 4 == 0 && d <= 128 * LN_MAX_VEC, SKF_ERR_BAD_SHAPE, "layernorm: d=%d unsupported", d);
   dim3 blk(32, 8);
   int grid = cdiv(rows, 8 * 4);              // >= 4 rows per warp so the dgamma/dbeta partials amortise
@@ -773,10 +871,10 @@ int skf_layernorm_bwd(const float* dy, const float* s, const float* mean, const 
   if (grid < 1) grid = 1;
   const size_t sm = 2 * d * sizeof(float);
   cudaStream_t st = as_stream(stream);
-  if (d <= 128) ln_bwd_k<1><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32);
-  else if (d <= 256) ln_bwd_k<2><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32);
-  else if (d <= 512) ln_bwd_k<4><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32);
-  else ln_bwd_k<8><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32);
+  if (d <= 128) ln_bwd_k<1><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
+  else if (d <= 256) ln_bwd_k<2><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
+  else if (d <= 512) ln_bwd_k<4><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
+  else ln_bwd_k<8><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }

@@ -81,6 +81,7 @@ static int check_cfg(const skf_cfg* c) {
               "cfg: vocab size must be a positive multiple of 4");
   SKF_REQUIRE(!c->do_classification || c->C > 0, SKF_ERR_BAD_SHAPE, "cfg: n_classes");
   SKF_REQUIRE(c->T <= 1000, SKF_ERR_BAD_SHAPE, "cfg: max_seq_len > maximum_position_encoding (1000)");
+  SKF_REQUIRE(c->dropout_rate >= 0.f && c->dropout_rate < 1.f, SKF_ERR_BAD_ARG, "cfg: dropout_rate outside [0, 1)");
   return SKF_OK;
 }
 
@@ -252,6 +253,7 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
   W.add("g.a", Me * d * F);
   W.add("g.b", Me * d * F);
   W.add("g.c", Me * d * F);
+  W.add("g.d", Me * d * F);
   W.add("g.h", Me * f * F);
   W.add("g.qkv", Me * 3 * d * F);
   W.add("g.q2", Me * d * F);
@@ -277,6 +279,7 @@ struct skf_plan {
   int64_t launches = 0;
   bool round_ops = false;  // round GEMM operands to TF32 when they are produced
   const float* wc = nullptr;
+  bool training = false;   // inside skf_train_step: Dropout layers are active (training=True)
   int64_t gen_sos = 0, gen_eos = 0;   // greedy decode: start / stop token ids (utils/tokenizer.py:29-33)
   bool gen_ready = false;
 
@@ -398,6 +401,48 @@ struct Gemm {
   }
 };
 
+// Dropout sites (one independent mask stream each): the reference's Dropout layers in call order
+enum : uint32_t { SITE_ENC_X0 = 1, SITE_DEC_X0 = 2, SITE_ENC_L = 10, SITE_DEC_L = 100 };
+static inline bool dropping(const skf_plan* P) { return P->training && P->c.dropout_rate > 0.f; }
+
+// out = LN(resid + dropout(W-projection of `in`)) (transformer.py:217-218 etc.).  Without dropout the residual
+// add is fused into the GEMM epilogue; with dropout the GEMM writes the bare sublayer output into `tmp` and the
+// LayerNorm kernel applies mask and residual.  s receives the pre-LN sum (saved for backward).
+static int proj_resid_ln(skf_plan* P, const Gemm& G, const float* in, const std::string& w, const std::string& b,
+                         const std::string& ln, const float* resid, float* tmp, float* s, float* out, float* mean,
+                         float* rstd, int M, int N, int K, uint32_t site, cudaStream_t st) {
+  const int rnd = P->round_ops ? 1 : 0;
+  if (!dropping(P)) {
+    SKF_TRY(G.fwd(in, P->w(w), P->pw(b), s, M, N, K, SKF_ACT_NONE, resid, 0));
+    return skf_add_layernorm_fwd(s, nullptr, nullptr, P->pw(ln + ".g"), P->pw(ln + ".b"), nullptr, out, mean, rstd, M,
+                                 N, rnd, st);
+  }
+  SKF_TRY(G.fwd(in, P->w(w), P->pw(b), tmp, M, N, K, SKF_ACT_NONE, nullptr, 0));
+  return skf_add_dropout_layernorm_fwd(resid, tmp, nullptr, P->pw(ln + ".g"), P->pw(ln + ".b"), s, out, mean, rstd, M,
+                                       N, P->c.dropout_rate, P->c.dropout_seed, site, P->wsp<int64_t>("step"), st);
+}
+// backward of the LN of proj_resid_ln: ds -> gres (gradient of the residual input); returns in *gsub the
+// gradient of the sublayer output (== gres without dropout, the masked copy in gdrop with dropout)
+static int ln_bwd_any(skf_plan* P, const float* dy, const std::string& pfx, const std::string& idx, float* gres,
+                      float* gdrop, const float** gsub, int M, int d, uint32_t site, cudaStream_t st) {
+  const int rnd = P->round_ops ? 1 : 0;
+  const std::string ln = pfx + ".ln" + idx;
+  if (!dropping(P)) {
+    *gsub = gres;
+    return skf_layernorm_bwd(dy, P->wsf(pfx + ".s" + idx), P->wsf(pfx + ".mean" + idx), P->wsf(pfx + ".rstd" + idx),
+                             P->pw(ln + ".g"), gres, P->g(ln + ".g"), P->g(ln + ".b"), M, d, rnd, st);
+  }
+  *gsub = gdrop;
+  return skf_layernorm_dropout_bwd(dy, P->wsf(pfx + ".s" + idx), P->wsf(pfx + ".mean" + idx),
+                                   P->wsf(pfx + ".rstd" + idx), P->pw(ln + ".g"), gres, gdrop, P->g(ln + ".g"),
+                                   P->g(ln + ".b"), M, d, P->c.dropout_rate, P->c.dropout_seed, site,
+                                   P->wsp<int64_t>("step"), st);
+}
+static int embed_dropout(skf_plan* P, float* x, int64_t n, uint32_t site, cudaStream_t st) {
+  if (!dropping(P)) return SKF_OK;
+  return skf_dropout(x, x, n, P->c.dropout_rate, P->c.dropout_seed, site, P->wsp<int64_t>("step"), st);
+}
+
 static int attn_fwd_any(const skf_plan* P, const float* Q, int64_t ldq, const float* K, int64_t ldk,
                         const float* V, int64_t ldv, float* O, int64_t ldo, float* lse, const uint8_t* pad,
                         int Tq, int Tk, int mode, cudaStream_t st) {
@@ -466,6 +511,8 @@ static int forward_encoder(skf_plan* P, const void* tok, cudaStream_t st) {
   uint8_t* enc_pad = P->wsp<uint8_t>("enc_pad");
   float* x = P->wsf("enc.x0");
   SKF_TRY(embed_any(P, tok, "enc", enc_pad, x, T, st));
+  SKF_TRY(embed_dropout(P, x, (int64_t)Me * d, SITE_ENC_X0, st));            // transformer.py:296
+  float* tmp = P->wsf("g.c");                                                // forward scratch (free until backward)
   for (int i = 0; i < c.L; i++) {
     std::string p = "enc.l" + std::to_string(i);
     float* qkv = P->wsf(p + ".qkv");
@@ -473,18 +520,14 @@ static int forward_encoder(skf_plan* P, const void* tok, cudaStream_t st) {
     float* ctx = P->wsf(p + ".ctx");
     SKF_TRY(attn_fwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, ctx, d, P->wsf(p + ".lse"), enc_pad,
                          T, T, 1, st));
-    float* s1 = P->wsf(p + ".s1");
-    SKF_TRY(G.fwd(ctx, P->w(p + ".mha.wo.k"), P->pw(p + ".mha.wo.b"), s1, Me, d, d, SKF_ACT_NONE, x, 0));
     float* out1 = P->wsf(p + ".out1");
-    SKF_TRY(skf_add_layernorm_fwd(s1, nullptr, nullptr, P->pw(p + ".ln1.g"), P->pw(p + ".ln1.b"), nullptr, out1,
-                                  P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), Me, d, rnd, st));
+    SKF_TRY(proj_resid_ln(P, G, ctx, p + ".mha.wo.k", p + ".mha.wo.b", p + ".ln1", x, tmp, P->wsf(p + ".s1"), out1,
+                          P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), Me, d, d, SITE_ENC_L + 2 * i, st));
     float* hff = P->wsf(p + ".hff");
     SKF_TRY(G.fwd(out1, P->w(p + ".ffn.w1.k"), P->pw(p + ".ffn.w1.b"), hff, Me, f, d, SKF_ACT_RELU, nullptr, 1));
-    float* s2 = P->wsf(p + ".s2");
-    SKF_TRY(G.fwd(hff, P->w(p + ".ffn.w2.k"), P->pw(p + ".ffn.w2.b"), s2, Me, d, f, SKF_ACT_NONE, out1, 0));
     float* out2 = P->wsf(p + ".out2");
-    SKF_TRY(skf_add_layernorm_fwd(s2, nullptr, nullptr, P->pw(p + ".ln2.g"), P->pw(p + ".ln2.b"), nullptr, out2,
-                                  P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), Me, d, rnd, st));
+    SKF_TRY(proj_resid_ln(P, G, hff, p + ".ffn.w2.k", p + ".ffn.w2.b", p + ".ln2", out1, tmp, P->wsf(p + ".s2"), out2,
+                          P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), Me, d, f, SITE_ENC_L + 2 * i + 1, st));
     x = out2;
   }
   // bottleneck (SelfAttnV1.call transformer.py:61-74)
@@ -514,6 +557,8 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
   uint8_t* dec_pad = P->wsp<uint8_t>("dec_pad");
   float* x = P->wsf("dec.x0");
   SKF_TRY(embed_any(P, tok, "dec", dec_pad, x, Td, st));   // tar_inp = tar[:, :-1]
+  SKF_TRY(embed_dropout(P, x, (int64_t)Md * d, SITE_DEC_X0, st));            // transformer.py:334
+  float* tmp = P->wsf("g.c");
   const uint8_t* cross_pad = c.blind_decoder_mask ? nullptr : P->wsp<uint8_t>("enc_pad");
   const int cross_mode = c.blind_decoder_mask ? 0 : 1;
   for (int i = 0; i < c.L; i++) {
@@ -523,11 +568,9 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
     float* ctx1 = P->wsf(p + ".ctx1");
     SKF_TRY(attn_fwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, ctx1, d, P->wsf(p + ".lse1"), dec_pad,
                          Td, Td, 2, st));
-    float* s1 = P->wsf(p + ".s1");
-    SKF_TRY(G.fwd(ctx1, P->w(p + ".mha1.wo.k"), P->pw(p + ".mha1.wo.b"), s1, Md, d, d, SKF_ACT_NONE, x, 0));
     float* out1 = P->wsf(p + ".out1");
-    SKF_TRY(skf_add_layernorm_fwd(s1, nullptr, nullptr, P->pw(p + ".ln1.g"), P->pw(p + ".ln1.b"), nullptr, out1,
-                                  P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), Md, d, rnd, st));
+    SKF_TRY(proj_resid_ln(P, G, ctx1, p + ".mha1.wo.k", p + ".mha1.wo.b", p + ".ln1", x, tmp, P->wsf(p + ".s1"), out1,
+                          P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), Md, d, d, SITE_DEC_L + 3 * i, st));
     float* q2 = P->wsf(p + ".q2");
     SKF_TRY(G.fwd(out1, P->w(p + ".mha2.wq.k"), P->pw(p + ".mha2.wq.b"), q2, Md, d, d, SKF_ACT_NONE, nullptr, 0));
     float* kv2 = P->wsf(p + ".kv2");
@@ -535,18 +578,14 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
     float* ctx2 = P->wsf(p + ".ctx2");
     SKF_TRY(attn_fwd_any(P, q2, d, kv2, 2 * d, kv2 + d, 2 * d, ctx2, d, P->wsf(p + ".lse2"), cross_pad, Td, T,
                          cross_mode, st));
-    float* s2 = P->wsf(p + ".s2");
-    SKF_TRY(G.fwd(ctx2, P->w(p + ".mha2.wo.k"), P->pw(p + ".mha2.wo.b"), s2, Md, d, d, SKF_ACT_NONE, out1, 0));
     float* out2 = P->wsf(p + ".out2");
-    SKF_TRY(skf_add_layernorm_fwd(s2, nullptr, nullptr, P->pw(p + ".ln2.g"), P->pw(p + ".ln2.b"), nullptr, out2,
-                                  P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), Md, d, rnd, st));
+    SKF_TRY(proj_resid_ln(P, G, ctx2, p + ".mha2.wo.k", p + ".mha2.wo.b", p + ".ln2", out1, tmp, P->wsf(p + ".s2"), out2,
+                          P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), Md, d, d, SITE_DEC_L + 3 * i + 1, st));
     float* hff = P->wsf(p + ".hff");
     SKF_TRY(G.fwd(out2, P->w(p + ".ffn.w1.k"), P->pw(p + ".ffn.w1.b"), hff, Md, f, d, SKF_ACT_RELU, nullptr, 1));
-    float* s3 = P->wsf(p + ".s3");
-    SKF_TRY(G.fwd(hff, P->w(p + ".ffn.w2.k"), P->pw(p + ".ffn.w2.b"), s3, Md, d, f, SKF_ACT_NONE, out2, 0));
     float* out3 = P->wsf(p + ".out3");
-    SKF_TRY(skf_add_layernorm_fwd(s3, nullptr, nullptr, P->pw(p + ".ln3.g"), P->pw(p + ".ln3.b"), nullptr, out3,
-                                  P->wsf(p + ".mean3"), P->wsf(p + ".rstd3"), Md, d, rnd, st));
+    SKF_TRY(proj_resid_ln(P, G, hff, p + ".ffn.w2.k", p + ".ffn.w2.b", p + ".ln3", out2, tmp, P->wsf(p + ".s3"), out3,
+                          P->wsf(p + ".mean3"), P->wsf(p + ".rstd3"), Md, d, f, SITE_DEC_L + 3 * i + 2, st));
     x = out3;
   }
   if (c.continuous) {            // Dense(5), sketchformer.py:86 (5 columns: exact-fp32 SIMT GEMM, ld 8)
@@ -601,7 +640,8 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
   SKF_CUDA(cudaMemsetAsync(P->grads, 0, (size_t)P->PL.total * sizeof(float), st));
   float *gA = P->wsf("g.a"), *gB = P->wsf("g.b"), *gC = P->wsf("g.c"), *gH = P->wsf("g.h");
   float *gQKV = P->wsf("g.qkv"), *gQ2 = P->wsf("g.q2"), *gKV2 = P->wsf("g.kv2"), *gPre = P->wsf("g.pre");
-  float *gEmb = P->wsf("g.emb"), *gU = P->wsf("g.u"), *delta = P->wsf("g.delta");
+  float *gEmb = P->wsf("g.emb"), *gU = P->wsf("g.u"), *delta = P->wsf("g.delta"), *gD = P->wsf("g.d");
+  const float* gS = nullptr;       // gradient of the current sublayer output (behind its Dropout)
   const uint8_t* enc_pad = P->wsp<uint8_t>("enc_pad");
   bool have_demb = false;
 
@@ -629,17 +669,15 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
       std::string p = "dec.l" + std::to_string(i);
       const float* xin = i == 0 ? P->wsf("dec.x0") : P->wsf("dec.l" + std::to_string(i - 1) + ".out3");
       // LN3 + FFN
-      SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s3"), P->wsf(p + ".mean3"), P->wsf(p + ".rstd3"), P->pw(p + ".ln3.g"),
-                                gB, P->g(p + ".ln3.g"), P->g(p + ".ln3.b"), Md, d, rnd, st));
-      SKF_TRY(G.wgrad(P->wsf(p + ".hff"), gB, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Md, d, f));
-      SKF_TRY(G.dgrad(gB, P->w(p + ".ffn.w2.k"), gH, Md, d, f, P->wsf(p + ".hff"), nullptr, 1));
+      SKF_TRY(ln_bwd_any(P, gA, p, "3", gB, gD, &gS, Md, d, SITE_DEC_L + 3 * i + 2, st));
+      SKF_TRY(G.wgrad(P->wsf(p + ".hff"), gS, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Md, d, f));
+      SKF_TRY(G.dgrad(gS, P->w(p + ".ffn.w2.k"), gH, Md, d, f, P->wsf(p + ".hff"), nullptr, 1));
       SKF_TRY(G.wgrad(P->wsf(p + ".out2"), gH, P->g(p + ".ffn.w1.k"), P->g(p + ".ffn.w1.b"), Md, f, d));
       SKF_TRY(G.dgrad(gH, P->w(p + ".ffn.w1.k"), gA, Md, f, d, nullptr, gB, 0));
       // LN2 + cross attention
-      SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s2"), P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), P->pw(p + ".ln2.g"),
-                                gB, P->g(p + ".ln2.g"), P->g(p + ".ln2.b"), Md, d, rnd, st));
-      SKF_TRY(G.wgrad(P->wsf(p + ".ctx2"), gB, P->g(p + ".mha2.wo.k"), P->g(p + ".mha2.wo.b"), Md, d, d));
-      SKF_TRY(G.dgrad(gB, P->w(p + ".mha2.wo.k"), gC, Md, d, d, nullptr, nullptr, 0));
+      SKF_TRY(ln_bwd_any(P, gA, p, "2", gB, gD, &gS, Md, d, SITE_DEC_L + 3 * i + 1, st));
+      SKF_TRY(G.wgrad(P->wsf(p + ".ctx2"), gS, P->g(p + ".mha2.wo.k"), P->g(p + ".mha2.wo.b"), Md, d, d));
+      SKF_TRY(G.dgrad(gS, P->w(p + ".mha2.wo.k"), gC, Md, d, d, nullptr, nullptr, 0));
       float* kv2 = P->wsf(p + ".kv2");
       SKF_TRY(attn_bwd_any(P, P->wsf(p + ".q2"), d, kv2, 2 * d, kv2 + d, 2 * d, P->wsf(p + ".ctx2"), d, gC, d,
                            P->wsf(p + ".lse2"), delta, gQ2, d, gKV2, 2 * d, gKV2 + d, 2 * d, cross_pad, Td, T,
@@ -649,10 +687,9 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
       SKF_TRY(G.dgrad(gKV2, P->w(p + ".mha2.wkv.k"), gPre, Me, 2 * d, d, nullptr, i == c.L - 1 ? nullptr : gPre, 0));
       SKF_TRY(G.dgrad(gQ2, P->w(p + ".mha2.wq.k"), gA, Md, d, d, nullptr, gB, 0));
       // LN1 + masked self attention
-      SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s1"), P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), P->pw(p + ".ln1.g"),
-                                gB, P->g(p + ".ln1.g"), P->g(p + ".ln1.b"), Md, d, rnd, st));
-      SKF_TRY(G.wgrad(P->wsf(p + ".ctx1"), gB, P->g(p + ".mha1.wo.k"), P->g(p + ".mha1.wo.b"), Md, d, d));
-      SKF_TRY(G.dgrad(gB, P->w(p + ".mha1.wo.k"), gC, Md, d, d, nullptr, nullptr, 0));
+      SKF_TRY(ln_bwd_any(P, gA, p, "1", gB, gD, &gS, Md, d, SITE_DEC_L + 3 * i, st));
+      SKF_TRY(G.wgrad(P->wsf(p + ".ctx1"), gS, P->g(p + ".mha1.wo.k"), P->g(p + ".mha1.wo.b"), Md, d, d));
+      SKF_TRY(G.dgrad(gS, P->w(p + ".mha1.wo.k"), gC, Md, d, d, nullptr, nullptr, 0));
       float* qkv = P->wsf(p + ".qkv");
       SKF_TRY(attn_bwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, P->wsf(p + ".ctx1"), d, gC, d,
                            P->wsf(p + ".lse1"), delta, gQKV, 3 * d, gQKV + d, 3 * d, gQKV + 2 * d, 3 * d, dec_pad,
@@ -660,6 +697,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
       SKF_TRY(G.wgrad(xin, gQKV, P->g(p + ".mha1.wqkv.k"), P->g(p + ".mha1.wqkv.b"), Md, 3 * d, d));
       SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha1.wqkv.k"), gA, Md, 3 * d, d, nullptr, gB, 0));
     }
+    SKF_TRY(embed_dropout(P, gA, (int64_t)Md * d, SITE_DEC_X0, st));
     SKF_TRY(embed_any_bwd(P, tok, "dec", gA, Td, st));
     SKF_TRY(skf_expand_bwd(gPre, P->wsf("embedding"), P->pw("exp.k"), gEmb, 0, P->g("exp.k"),
                            P->g("exp.b"), B, T, d, st));
@@ -691,16 +729,14 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
   for (int i = c.L - 1; i >= 0; i--) {
     std::string p = "enc.l" + std::to_string(i);
     const float* xin = i == 0 ? P->wsf("enc.x0") : P->wsf("enc.l" + std::to_string(i - 1) + ".out2");
-    SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s2"), P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), P->pw(p + ".ln2.g"),
-                              gB, P->g(p + ".ln2.g"), P->g(p + ".ln2.b"), Me, d, rnd, st));
-    SKF_TRY(G.wgrad(P->wsf(p + ".hff"), gB, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Me, d, f));
-    SKF_TRY(G.dgrad(gB, P->w(p + ".ffn.w2.k"), gH, Me, d, f, P->wsf(p + ".hff"), nullptr, 1));
+    SKF_TRY(ln_bwd_any(P, gA, p, "2", gB, gD, &gS, Me, d, SITE_ENC_L + 2 * i + 1, st));
+    SKF_TRY(G.wgrad(P->wsf(p + ".hff"), gS, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Me, d, f));
+    SKF_TRY(G.dgrad(gS, P->w(p + ".ffn.w2.k"), gH, Me, d, f, P->wsf(p + ".hff"), nullptr, 1));
     SKF_TRY(G.wgrad(P->wsf(p + ".out1"), gH, P->g(p + ".ffn.w1.k"), P->g(p + ".ffn.w1.b"), Me, f, d));
     SKF_TRY(G.dgrad(gH, P->w(p + ".ffn.w1.k"), gA, Me, f, d, nullptr, gB, 0));
-    SKF_TRY(skf_layernorm_bwd(gA, P->wsf(p + ".s1"), P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), P->pw(p + ".ln1.g"),
-                              gB, P->g(p + ".ln1.g"), P->g(p + ".ln1.b"), Me, d, rnd, st));
-    SKF_TRY(G.wgrad(P->wsf(p + ".ctx"), gB, P->g(p + ".mha.wo.k"), P->g(p + ".mha.wo.b"), Me, d, d));
-    SKF_TRY(G.dgrad(gB, P->w(p + ".mha.wo.k"), gC, Me, d, d, nullptr, nullptr, 0));
+    SKF_TRY(ln_bwd_any(P, gA, p, "1", gB, gD, &gS, Me, d, SITE_ENC_L + 2 * i, st));
+    SKF_TRY(G.wgrad(P->wsf(p + ".ctx"), gS, P->g(p + ".mha.wo.k"), P->g(p + ".mha.wo.b"), Me, d, d));
+    SKF_TRY(G.dgrad(gS, P->w(p + ".mha.wo.k"), gC, Me, d, d, nullptr, nullptr, 0));
     float* qkv = P->wsf(p + ".qkv");
     SKF_TRY(attn_bwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, P->wsf(p + ".ctx"), d, gC, d,
                          P->wsf(p + ".lse"), delta, gQKV, 3 * d, gQKV + d, 3 * d, gQKV + 2 * d, 3 * d, enc_pad, T, T,
@@ -708,6 +744,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
     SKF_TRY(G.wgrad(xin, gQKV, P->g(p + ".mha.wqkv.k"), P->g(p + ".mha.wqkv.b"), Me, 3 * d, d));
     SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha.wqkv.k"), gA, Me, 3 * d, d, nullptr, gB, 0));
   }
+  SKF_TRY(embed_dropout(P, gA, (int64_t)Me * d, SITE_ENC_X0, st));
   SKF_TRY(embed_any_bwd(P, tok, "enc", gA, T, st));
   return SKF_OK;
 }
@@ -912,10 +949,13 @@ int skf_train_step(skf_plan* P, const void* tokens, const int64_t* labels, int a
   const void* tok = tokens;
   int64_t l0 = skf::g_launch_count;
   SKF_TRY(refresh_compute_weights(P, st));
-  SKF_TRY(forward_encoder(P, tok, st));
-  if (P->c.do_reconstruction) SKF_TRY(forward_decoder(P, tok, st));
-  SKF_TRY(losses(P, tok, labels, true, st));
-  SKF_TRY(backward(P, tok, st));
+  P->training = true;            // Dropout layers active (self.call(..., training=True), sketchformer.py:332)
+  int rc = forward_encoder(P, tok, st);
+  if (rc == SKF_OK && P->c.do_reconstruction) rc = forward_decoder(P, tok, st);
+  if (rc == SKF_OK) rc = losses(P, tok, labels, true, st);
+  if (rc == SKF_OK) rc = backward(P, tok, st);
+  P->training = false;
+  SKF_TRY(rc);
   P->launches += skf::g_launch_count - l0;
   if (apply_adam) SKF_TRY(skf_apply_adam(P, stream));
   return SKF_OK;

@@ -17,13 +17,14 @@ from ._lib import SkfCfg, SkfParamEntry, check
 
 def make_cfg(B, T, d, f, H, L, V, n_classes, lowerdim, *, continuous=False, blind_decoder_mask=True,
              do_classification=True, do_reconstruction=True, class_weight=1.0, recon_weight=1.0,
-             world_size=1, gemm_backend=0, attn_backend=0, gemm_precision=2) -> SkfCfg:
+             world_size=1, gemm_backend=0, attn_backend=0, gemm_precision=2, dropout_rate=0.0,
+             dropout_seed=0) -> SkfCfg:
     return SkfCfg(B=B, T=T, d=d, f=f, H=H, L=L, V=V, C=n_classes, u=lowerdim, continuous=int(continuous),
                   blind_decoder_mask=int(blind_decoder_mask), do_classification=int(do_classification),
                   do_reconstruction=int(do_reconstruction), warmup_steps=5000, class_weight=class_weight,
                   recon_weight=recon_weight, adam_beta1=0.9, adam_beta2=0.98, adam_eps=1e-9,
                   world_size=world_size, gemm_backend=gemm_backend, attn_backend=attn_backend,
-                  gemm_precision=gemm_precision)
+                  gemm_precision=gemm_precision, dropout_rate=float(dropout_rate), dropout_seed=int(dropout_seed))
 
 
 class Engine:

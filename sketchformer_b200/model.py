@@ -61,7 +61,7 @@ class Transformer:
 
     # ---- construction ----------------------------------------------------------------------
     def __init__(self, hps, dataset, out_dir=None, experiment_id="0", device="cuda:0", world_size=1, seed=0,
-                 gemm_precision=None, use_cuda_graph=True):
+                 gemm_precision=None, use_cuda_graph=True, rank=0):
         self.hps = hps if isinstance(hps, dict) else dict(hps.values())
         self.dataset = dataset
         self.experiment_id = experiment_id
@@ -81,6 +81,7 @@ class Transformer:
         self.current_step = 0
         self._device = torch.device(device)
         self._world = world_size
+        self._rank = rank
         self._seed = seed
         self._precision = gemm_precision
         self._use_graph = use_cuda_graph
@@ -121,7 +122,8 @@ class Transformer:
                         self.vocab_size or 0, self.dataset.n_classes, h["lowerdim"], continuous=self.continuous,
                         blind_decoder_mask=h["blind_decoder_mask"], do_classification=h["do_classification"],
                         do_reconstruction=h["do_reconstruction"], class_weight=h["class_weight"],
-                        recon_weight=h["recon_weight"], world_size=self._world, **kw)
+                        recon_weight=h["recon_weight"], world_size=self._world, dropout_rate=h["dropout_rate"],
+                        dropout_seed=(0x5EED + 7919 * self._seed + 104729 * self._rank) & 0xFFFFFFFF, **kw)
 
     def _engine(self, B, training=False):
         """One plan per batch size; all plans share the parameter arena of the training plan."""
@@ -186,8 +188,6 @@ class Transformer:
         data, labels = batch
         B = int(data.shape[0])
         eng = self._engine(B, training=True)
-        if self.hps["dropout_rate"] != 0.0:
-            raise NotImplementedError("dropout_rate != 0 is not built yet (parity runs use dropout_rate=0)")
         dt = torch.int64 if not self.continuous else torch.float32
         solo = self._world == 1           # data parallel: gradients are all-reduced before the optimizer
         if self._use_graph and eng is self._train_engine and self.current_step >= 2:

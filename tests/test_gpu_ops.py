@@ -93,6 +93,53 @@ def test_layernorm_fwd_bwd(lib, rows, d):
     assert rel_err(dg, p["ln.g"].grad) < TOL_EXACT and rel_err(db, p["ln.b"].grad) < TOL_EXACT
 
 
+def test_dropout_mask_matches_numpy_mirror(lib):
+    """skf_dropout: counter-based keep mask == oracle/dropout_rng.py bit for bit; keep fraction ~ 1 - rate."""
+    from oracle.dropout_rng import keep_mask
+    n, rate, seed, site = 257 * 129, 0.1, 1234567, 102
+    x = torch.randn(n)
+    step = torch.tensor([4321], dtype=torch.int64, device="cuda")
+    y = torch.empty(n, device="cuda")
+    xd = dev(x)
+    _lib.check(lib.skf_dropout(ptr(xd), ptr(y), n, rate, seed, site, ptr(step), stream()))
+    keep = torch.from_numpy(keep_mask((n,), rate, seed, site, 4321))
+    want = torch.where(keep, x * (torch.tensor(1.0) / (torch.tensor(1.0) - torch.tensor(rate))), torch.zeros(()))
+    assert torch.equal(y.cpu(), want)
+    assert abs(float(keep.float().mean()) - 0.9) < 0.01
+    step += 1
+    y2 = torch.empty(n, device="cuda")
+    _lib.check(lib.skf_dropout(ptr(xd), ptr(y2), n, rate, seed, site, ptr(step), stream()))
+    assert not torch.equal(y2, y)
+
+
+def test_layernorm_dropout_fwd_bwd(lib):
+    """s = a + dropout(b + bias); y = LN(s); backward returns ds (residual path) and mask(ds) (sublayer path)."""
+    from oracle.dropout_rng import keep_mask
+    rows, d, rate, seed, site = 300, 256, 0.25, 99, 11
+    g = torch.Generator().manual_seed(5)
+    a, b = torch.randn(rows, d, generator=g), torch.randn(rows, d, generator=g)
+    bias, gamma, beta = torch.randn(d, generator=g), torch.randn(d, generator=g), torch.randn(d, generator=g)
+    dy = torch.randn(rows, d, generator=g)
+    step = torch.tensor([7], dtype=torch.int64, device="cuda")
+    keep = torch.from_numpy(keep_mask((rows, d), rate, seed, site, 7)).double()
+    a64 = a.double().requires_grad_(True); b64 = b.double().requires_grad_(True)
+    s64 = a64 + (b64 + bias.double()) * keep / (1 - rate)
+    y64 = torch.nn.functional.layer_norm(s64, (d,), gamma.double(), beta.double(), 1e-6)
+    y64.backward(dy.double())
+    s, y = torch.empty(rows, d, device="cuda"), torch.empty(rows, d, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ad, bd, biasd, gd, bed, dyd = dev(a), dev(b), dev(bias), dev(gamma), dev(beta), dev(dy)   # keep the buffers alive
+    _lib.check(lib.skf_add_dropout_layernorm_fwd(ptr(ad), ptr(bd), ptr(biasd), ptr(gd), ptr(bed),
+                                                 ptr(s), ptr(y), ptr(mean), ptr(rstd), rows, d, rate, seed, site,
+                                                 ptr(step), stream()))
+    assert rel_err(s, s64) < 1e-6 and rel_err(y, y64) < 1e-5
+    ds, dsd = torch.empty(rows, d, device="cuda"), torch.empty(rows, d, device="cuda")
+    dg, db = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    _lib.check(lib.skf_layernorm_dropout_bwd(ptr(dyd), ptr(s), ptr(mean), ptr(rstd), ptr(gd), ptr(ds),
+                                             ptr(dsd), ptr(dg), ptr(db), rows, d, rate, seed, site, ptr(step), stream()))
+    assert rel_err(ds, a64.grad) < 1e-5 and rel_err(dsd, b64.grad) < 1e-5
+
+
 def test_colsum(lib):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(1234, 345, generator=g)

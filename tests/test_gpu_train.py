@@ -31,6 +31,7 @@ from sketchformer_b200.engine import Engine, make_cfg
 from tests.gpu_util import rel_err
 
 pytestmark = pytest.mark.gpu
+DROPOUT_SEED = 20260
 
 
 def build(cfg_kw, B, backend, precision=2, attn_backend=-1, **flags):
@@ -40,7 +41,8 @@ def build(cfg_kw, B, backend, precision=2, attn_backend=-1, **flags):
                  blind_decoder_mask=ocfg.blind_decoder_mask,
                  do_classification=ocfg.do_classification, do_reconstruction=ocfg.do_reconstruction,
                  class_weight=ocfg.class_weight, recon_weight=ocfg.recon_weight, gemm_backend=backend,
-                 attn_backend=backend if attn_backend < 0 else attn_backend, gemm_precision=precision)
+                 attn_backend=backend if attn_backend < 0 else attn_backend, gemm_precision=precision,
+                 dropout_rate=ocfg.dropout_rate, dropout_seed=DROPOUT_SEED)
     return ocfg, Engine(c)
 
 
@@ -258,3 +260,55 @@ def test_golden_tiny_continuous_losses(golden_dir):
         for k in ("recon_loss", "class_loss", "total_loss"):
             want = float(g[f"f64/step{s}/{k}"])
             assert abs(m[k] - want) <= 1e-3 * abs(want), (s, k, m[k], want)
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("name,cfg_kw,B,cont", [("tiny", TINY, 4, False), ("cfg1", CFG1, 8, False),
+                                                ("tiny-continuous", TINY, 4, True)], ids=["tiny", "cfg1", "tiny-cont"])
+def test_train_step_with_dropout_matches_oracle(name, cfg_kw, B, cont, backend):
+    """dropout_rate=0.1 (the reference default, models/sketchformer.py:31): every Dropout site of
+    Encoder/Decoder(.Layer).call is active in the train step.  The device masks are counter-based
+    (seed, site, optimizer step, element), regenerated in the backward pass; the oracle is given the same
+    masks (oracle/dropout_rng.py), so losses and gradients must agree to the usual tolerance — and a
+    second step must draw different masks."""
+    from oracle.dropout_rng import DeviceMasks
+    tol = 2e-4 if backend == 1 else 1e-3
+    ocfg, eng = build(cfg_kw, B, backend, dropout_rate=0.1, use_continuous_data=cont)
+    if cont:
+        x, y = synth.continuous_batch(B, ocfg.max_seq_len, ocfg.n_classes, 77)
+    else:
+        x, y = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 77, vocab=ocfg.vocab_size)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    p = O.init_params(ocfg, 0, torch.float64)
+    eng.load_params(p)
+    opt = O.AdamTF(p, ocfg.d_model)
+    first = None
+    for step in (0, 4000):
+        opt.iterations = step
+        eng.set_step(step)
+        eng.train_step(xt.cuda(), yt.cuda(), apply_adam=False)
+        torch.cuda.synchronize()
+        pattern = engine_relu_pattern(eng, ocfg, B)
+        with O.dropout_masks(DeviceMasks(0.1, DROPOUT_SEED, step)), O.relu_pattern(pattern):
+            p0 = {k: v.clone() for k, v in p.items()}
+            losses, grads = O.train_step(p0, O.AdamTF(p0, ocfg.d_model), xt, yt, ocfg, dtype=torch.float64)
+        m = eng.last_step_metrics()
+        for k in ("recon_loss", "class_loss", "total_loss"):
+            assert abs(m[k] - losses[k]) <= tol * abs(losses[k]), (step, k, m[k], losses[k])
+        got = eng.export_grads(grads)
+        G = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
+        bad = []
+        for k, ref in grads.items():
+            num = float((got[k].double() - ref.double()).norm())
+            if not num / max(float(ref.double().norm()), 1e-4 * G) < tol:
+                bad.append((k, num / max(float(ref.double().norm()), 1e-4 * G)))
+        assert not bad, f"step {step}: gradients off: {sorted(bad, key=lambda t: -t[1])[:8]}"
+        if first is None:
+            first = losses["total_loss"]
+        else:
+            assert abs(first - losses["total_loss"]) > 1e-6 * abs(first), "the mask did not change with the step"
+    # inference entry points never drop (training=False)
+    ocfg0, eng0 = build(cfg_kw, B, backend, use_continuous_data=cont)
+    eng0.load_params(p)
+    eng.encode(xt.cuda()); eng0.encode(xt.cuda())
+    assert torch.equal(eng.tensor("embedding", (B, ocfg.d_model)), eng0.tensor("embedding", (B, ocfg.d_model)))
