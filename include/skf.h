@@ -68,6 +68,10 @@ typedef struct skf_cfg {
                                  TF32 weight gradients                                        */
   float dropout_rate;         /* models/sketchformer.py:31; applied by skf_train_step only (training=True) */
   uint32_t dropout_seed;      /* seed of the counter-based dropout masks (see skf_dropout)   */
+  int32_t attn_version;       /* 1 = SelfAttnV1 (embedding width d_model), otherwise SelfAttnV2: W is (d,d) and a
+                                 Dense(lowerdim) follows the pooling, embedding width = lowerdim (0 is read as 1) */
+  int32_t class_buffer_layers;/* Dense(lowerdim, relu) + Dropout(class_dropout) blocks before the classifier      */
+  float class_dropout;        /* models/sketchformer.py:38                                   */
 } skf_cfg;
 
 const char* skf_last_error(void);

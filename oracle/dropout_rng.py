@@ -8,7 +8,7 @@ key = seed ^ (step * 0x632BE5AB), all in uint32 arithmetic.
 """
 import numpy as np
 
-SITE_ENC_X0, SITE_DEC_X0, SITE_ENC_L, SITE_DEC_L = 1, 2, 10, 100
+SITE_ENC_X0, SITE_DEC_X0, SITE_ENC_L, SITE_DEC_L, SITE_CBUF = 1, 2, 10, 100, 1000
 
 
 def _fmix32(h):
@@ -38,6 +38,8 @@ def site_id(name):
         return SITE_ENC_X0
     if name == "dec.x0":
         return SITE_DEC_X0
+    if name.startswith("cbuf"):
+        return SITE_CBUF + int(name[4:])
     side, layer, kind = name.split(".")
     i = int(layer[1:])
     if side == "enc":
@@ -48,8 +50,9 @@ def site_id(name):
 class DeviceMasks:
     """Mask provider for oracle.dropout_masks(): the masks the CUDA plan draws at optimizer step `step`."""
 
-    def __init__(self, rate, seed, step):
-        self.rate, self.seed, self.step = rate, seed, step
+    def __init__(self, rate, seed, step, class_rate=0.1):
+        self.rate, self.seed, self.step, self.class_rate = rate, seed, step, class_rate
 
     def __call__(self, site, shape):
-        return keep_mask(tuple(shape), self.rate, self.seed, site_id(site), self.step)
+        rate = self.class_rate if site.startswith("cbuf") else self.rate
+        return keep_mask(tuple(shape), rate, self.seed, site_id(site), self.step)

@@ -48,6 +48,7 @@ class OracleConfig:
     do_classification: bool = True
     class_weight: float = 1.0
     class_buffer_layers: int = 0
+    class_dropout: float = 0.1         # models/sketchformer.py:38
     do_reconstruction: bool = True
     recon_weight: float = 1.0
     blind_decoder_mask: bool = True
@@ -359,7 +360,7 @@ def classify_from_embedding(p, emb, cfg, training, gen):
     fc = emb
     for j in range(cfg.class_buffer_layers):
         fc = torch.relu(dense(p, f"cbuf{j}", fc))
-        fc = _dropout(fc, 0.1, training, gen)
+        fc = _dropout(fc, cfg.class_dropout, training, gen, f"cbuf{j}")
     logits = dense(p, "cls", fc)
     return torch.softmax(logits, dim=-1), logits
 

@@ -17,7 +17,8 @@ class SkfCfg(C.Structure):
                                          "warmup_steps")] + \
                [(n, C.c_float) for n in ("class_weight", "recon_weight", "adam_beta1", "adam_beta2", "adam_eps")] + \
                [(n, C.c_int32) for n in ("world_size", "gemm_backend", "attn_backend", "gemm_precision")] + \
-               [("dropout_rate", C.c_float), ("dropout_seed", C.c_uint32)]
+               [("dropout_rate", C.c_float), ("dropout_seed", C.c_uint32), ("attn_version", C.c_int32),
+                ("class_buffer_layers", C.c_int32), ("class_dropout", C.c_float)]
 
 
 class SkfParamEntry(C.Structure):

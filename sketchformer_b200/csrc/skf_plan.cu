@@ -82,8 +82,17 @@ static int check_cfg(const skf_cfg* c) {
   SKF_REQUIRE(!c->do_classification || c->C > 0, SKF_ERR_BAD_SHAPE, "cfg: n_classes");
   SKF_REQUIRE(c->T <= 1000, SKF_ERR_BAD_SHAPE, "cfg: max_seq_len > maximum_position_encoding (1000)");
   SKF_REQUIRE(c->dropout_rate >= 0.f && c->dropout_rate < 1.f, SKF_ERR_BAD_ARG, "cfg: dropout_rate outside [0, 1)");
+  SKF_REQUIRE(c->class_dropout >= 0.f && c->class_dropout < 1.f, SKF_ERR_BAD_ARG, "cfg: class_dropout outside [0, 1)");
+  SKF_REQUIRE(c->class_buffer_layers >= 0 && c->class_buffer_layers <= 8, SKF_ERR_BAD_SHAPE,
+              "cfg: class_buffer_layers outside [0, 8]");
   return SKF_OK;
 }
+
+// SelfAttnV1: pooling hidden width = lowerdim, embedding width = d_model;
+// SelfAttnV2: hidden width = d_model, Dense(lowerdim) after the pooling, embedding width = lowerdim.
+static inline bool pool_v2(const skf_cfg& c) { return c.attn_version != 0 && c.attn_version != 1; }
+static inline int emb_dim(const skf_cfg& c) { return pool_v2(c) ? c.u : c.d; }
+static inline int pool_dim(const skf_cfg& c) { return pool_v2(c) ? c.d : c.u; }
 
 static void add_mha_self(ParamLayout& L, const std::string& p, int d) {
   L.add(p + ".wqkv.k", d, 3 * d);
@@ -115,11 +124,21 @@ static ParamLayout build_layout(const skf_cfg& c) {
     add_mha_self(L, p + ".mha", c.d);
     add_ffn_ln(L, p, c.d, c.f, 2);
   }
-  L.add("pool.W", c.d, c.u);
-  L.add("pool.b", 1, c.u);
-  L.add("pool.V", 1, c.u);
-  if (c.do_classification) {
-    L.add("cls.k", c.d, c.C);
+  L.add("pool.W", c.d, pool_dim(c));
+  L.add("pool.b", 1, pool_dim(c));
+  L.add("pool.V", 1, pool_dim(c));
+  if (pool_v2(c)) {                       // SelfAttnV2.embeding_layer (transformer.py:99-100, 129-130)
+    L.add("pool.emb.k", c.d, c.u);
+    L.add("pool.emb.b", 1, c.u);
+  }
+  if (c.do_classification) {              // models/sketchformer.py:99-104
+    int fin = emb_dim(c);
+    for (int j = 0; j < c.class_buffer_layers; j++) {
+      L.add("cbuf" + std::to_string(j) + ".k", fin, c.u);
+      L.add("cbuf" + std::to_string(j) + ".b", 1, c.u);
+      fin = c.u;
+    }
+    L.add("cls.k", fin, c.C);
     L.add("cls.b", 1, c.C);
   }
   if (c.do_reconstruction) {
@@ -136,7 +155,7 @@ static ParamLayout build_layout(const skf_cfg& c) {
       add_mha_self(L, p + ".mha1", c.d);
       L.add(p + ".mha2.wq.k", c.d, c.d);
       L.add(p + ".mha2.wq.b", 1, c.d);
-      L.add(p + ".mha2.wkv.k", c.d, 2 * c.d);
+      L.add(p + ".mha2.wkv.k", emb_dim(c), 2 * c.d);   // keys / values come from the expanded embedding
       L.add(p + ".mha2.wkv.b", 1, 2 * c.d);
       L.add(p + ".mha2.wo.k", c.d, c.d);
       L.add(p + ".mha2.wo.b", 1, c.d);
@@ -193,16 +212,25 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
     W.add(p + ".rstd2", Me * F);
     W.add(p + ".out2", Me * d * F);
   }
-  W.add("pool.u", Me * c.u * F);
+  const size_t E = emb_dim(c);
+  W.add("pool.u", Me * pool_dim(c) * F);
   W.add("pool.a", Me * F);
-  W.add("embedding", (size_t)c.B * d * F);
+  W.add("pool.o", (size_t)c.B * d * F);            // pooled vector before SelfAttnV2's Dense
+  W.add("embedding", (size_t)c.B * E * F);
+  for (int j = 0; j < c.class_buffer_layers; j++) {
+    W.add("cbuf" + std::to_string(j) + ".h", (size_t)c.B * c.u * F);    // relu output
+    W.add("cbuf" + std::to_string(j) + ".hd", (size_t)c.B * c.u * F);   // after Dropout(class_dropout)
+  }
+  W.add("g.cb0", (size_t)c.B * c.u * F);
+  W.add("g.cb1", (size_t)c.B * c.u * F);
+  W.add("g.po", (size_t)c.B * d * F);
   size_t Cp = ((size_t)c.C + 3) & ~(size_t)3;
   W.add("cls.logits", (size_t)c.B * Cp * F);
   W.add("cls.dlogits", (size_t)c.B * Cp * F);
   W.add("cls.probs", (size_t)c.B * (c.C > 0 ? c.C : 1) * F);
   W.add("cls.argmax", (size_t)c.B * 4);
   if (c.do_reconstruction) {
-    W.add("pre_decoder", Me * d * F);
+    W.add("pre_decoder", Me * E * F);
     W.add("dec.x0", Md * d * F);
     for (int i = 0; i < c.L; i++) {
       std::string p = "dec.l" + std::to_string(i);
@@ -258,9 +286,9 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
   W.add("g.qkv", Me * 3 * d * F);
   W.add("g.q2", Me * d * F);
   W.add("g.kv2", Me * 2 * d * F);
-  W.add("g.pre", Me * d * F);
-  W.add("g.emb", (size_t)c.B * d * F);
-  W.add("g.u", Me * c.u * F);
+  W.add("g.pre", Me * E * F);
+  W.add("g.emb", (size_t)c.B * E * F);
+  W.add("g.u", Me * pool_dim(c) * F);
   W.add("g.delta", (size_t)c.B * H * c.T * F);
   W.total = (W.total + 255) & ~(size_t)255;
   return W;
@@ -503,6 +531,79 @@ static int embed_any_bwd(skf_plan* P, const void* in, const std::string& prefix,
   return skf_embed_bwd(reinterpret_cast<const int64_t*>(in), c.T, dx, P->g(prefix + ".emb"), c.B, rows, c.d, c.V, st);
 }
 
+// Transformer.classify_from_embedding (models/sketchformer.py:183-199): class_buffer_layers x
+// (Dense(lowerdim, relu) + Dropout(class_dropout)), then the Dense(n_classes) logits.  All of it is B rows
+// wide: exact-fp32 SIMT GEMMs (C = 345 columns are not 16-byte multiples).
+enum : uint32_t { SITE_CBUF = 1000 };
+static int classifier_fwd(skf_plan* P, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  const int B = c.B, Cp = (c.C + 3) & ~3;
+  const float* fc = P->wsf("embedding");
+  int fin = emb_dim(c);
+  skf_gemm_epilogue e;
+  for (int j = 0; j < c.class_buffer_layers; j++) {
+    const std::string n = "cbuf" + std::to_string(j);
+    memset(&e, 0, sizeof(e));
+    e.bias = P->pw(n + ".b");
+    e.act = SKF_ACT_RELU;
+    float* h = P->wsf(n + ".h");
+    SKF_TRY(gemm_simt(fc, fin, 1, P->pw(n + ".k"), c.u, 1, h, c.u, B, c.u, fin, &e, st));
+    fc = h;
+    if (P->training && c.class_dropout > 0.f) {
+      float* hd = P->wsf(n + ".hd");
+      SKF_TRY(skf_dropout(h, hd, (int64_t)B * c.u, c.class_dropout, c.dropout_seed, SITE_CBUF + j,
+                          P->wsp<int64_t>("step"), st));
+      fc = hd;
+    }
+    fin = c.u;
+  }
+  memset(&e, 0, sizeof(e));
+  e.bias = P->pw("cls.b");
+  return gemm_simt(fc, fin, 1, P->pw("cls.k"), c.C, 1, P->wsf("cls.logits"), Cp, B, c.C, fin, &e, st);
+}
+// gradient of the classification branch w.r.t. the embedding: gEmb (+)= ...
+static int classifier_bwd(skf_plan* P, float* gEmb, bool accumulate, cudaStream_t st) {
+  const skf_cfg& c = P->c;
+  const int B = c.B, Cp = (c.C + 3) & ~3, nb = c.class_buffer_layers;
+  const bool drop = P->training && c.class_dropout > 0.f;
+  auto layer_in = [&](int j) -> const float* {       // input of buffer layer j / of the classifier (j == nb)
+    if (j == 0) return P->wsf("embedding");
+    return P->wsf("cbuf" + std::to_string(j - 1) + (drop ? ".hd" : ".h"));
+  };
+  const float* dl = P->wsf("cls.dlogits");
+  int fin = nb ? c.u : emb_dim(c);
+  skf_gemm_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.accumulate = 1;
+  SKF_TRY(gemm_simt(layer_in(nb), 1, fin, dl, Cp, 1, P->g("cls.k"), c.C, fin, c.C, B, &e, st));
+  SKF_TRY(skf_colsum(dl, Cp, P->g("cls.b"), B, c.C, st));
+  const float* dy = dl;              // gradient of the current layer's output, [B, ncols] with row stride ldy
+  int ncols = c.C, ldy = Cp;
+  std::string wname = "cls.k";
+  float* buf[2] = {P->wsf("g.cb0"), P->wsf("g.cb1")};
+  for (int j = nb - 1; j >= -1; j--) {
+    // d(input of layer j+1) = dy * W^T; for a buffer layer's output also through Dropout and ReLU
+    const int kin = j >= 0 ? c.u : emb_dim(c);
+    float* dst = j >= 0 ? buf[j & 1] : gEmb;
+    memset(&e, 0, sizeof(e));
+    if (j >= 0) { e.mask = P->wsf("cbuf" + std::to_string(j) + ".h"); e.ld_mask = c.u; }
+    else if (accumulate) { e.resid = gEmb; e.ld_resid = kin; }
+    SKF_TRY(gemm_simt(dy, ldy, 1, P->pw(wname), 1, ncols, dst, kin, B, kin, ncols, &e, st));
+    if (j < 0) break;
+    if (drop)
+      SKF_TRY(skf_dropout(dst, dst, (int64_t)B * c.u, c.class_dropout, c.dropout_seed, SITE_CBUF + j,
+                          P->wsp<int64_t>("step"), st));
+    const std::string n = "cbuf" + std::to_string(j);
+    const int jin = j == 0 ? emb_dim(c) : c.u;
+    memset(&e, 0, sizeof(e));
+    e.accumulate = 1;
+    SKF_TRY(gemm_simt(layer_in(j), 1, jin, dst, c.u, 1, P->g(n + ".k"), c.u, jin, c.u, B, &e, st));
+    SKF_TRY(skf_colsum(dst, c.u, P->g(n + ".b"), B, c.u, st));
+    dy = dst; ncols = c.u; ldy = c.u; wname = n + ".k";
+  }
+  return SKF_OK;
+}
+
 static int forward_encoder(skf_plan* P, const void* tok, cudaStream_t st) {
   const skf_cfg& c = P->c;
   const int B = c.B, T = c.T, d = c.d, f = c.f, Me = B * T;
@@ -530,19 +631,19 @@ static int forward_encoder(skf_plan* P, const void* tok, cudaStream_t st) {
                           P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), Me, d, f, SITE_ENC_L + 2 * i + 1, st));
     x = out2;
   }
-  // bottleneck (SelfAttnV1.call transformer.py:61-74)
+  // bottleneck (SelfAttnV1.call transformer.py:61-74 / SelfAttnV2.call 116-131)
+  const int UP = pool_dim(c);
   float* u = P->wsf("pool.u");
-  SKF_TRY(G.fwd(x, P->w("pool.W"), P->pw("pool.b"), u, Me, c.u, d, SKF_ACT_TANH, nullptr, 0));
-  SKF_TRY(skf_pool_fwd(x, u, P->pw("pool.V"), P->wsf("pool.a"), P->wsf("embedding"), B, T, d, c.u, 0, st));
-  if (c.do_classification) {
-    int Cp = (c.C + 3) & ~3;
+  SKF_TRY(G.fwd(x, P->w("pool.W"), P->pw("pool.b"), u, Me, UP, d, SKF_ACT_TANH, nullptr, 0));
+  float* pooled = pool_v2(c) ? P->wsf("pool.o") : P->wsf("embedding");
+  SKF_TRY(skf_pool_fwd(x, u, P->pw("pool.V"), P->wsf("pool.a"), pooled, B, T, d, UP, 0, st));
+  if (pool_v2(c)) {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
-    e.bias = P->pw("cls.b");
-    // classifier runs in exact fp32 (C=345 rows are not 16-byte multiples; the op is tiny)
-    SKF_TRY(gemm_simt(P->wsf("embedding"), d, 1, P->pw("cls.k"), c.C, 1, P->wsf("cls.logits"), Cp,
-                      B, c.C, d, &e, st));
+    e.bias = P->pw("pool.emb.b");
+    SKF_TRY(gemm_simt(pooled, d, 1, P->pw("pool.emb.k"), c.u, 1, P->wsf("embedding"), c.u, B, c.u, d, &e, st));
   }
+  if (c.do_classification) SKF_TRY(classifier_fwd(P, st));
   return SKF_OK;
 }
 
@@ -552,8 +653,8 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
   const int rnd = P->round_ops ? 1 : 0;
   Gemm G{P, st};
   float* pre = P->wsf("pre_decoder");
-  SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre,
-                         B, T, d, rnd, st));
+  const int E = emb_dim(c);
+  SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, E, rnd, st));
   uint8_t* dec_pad = P->wsp<uint8_t>("dec_pad");
   float* x = P->wsf("dec.x0");
   SKF_TRY(embed_any(P, tok, "dec", dec_pad, x, Td, st));   // tar_inp = tar[:, :-1]
@@ -574,7 +675,7 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
     float* q2 = P->wsf(p + ".q2");
     SKF_TRY(G.fwd(out1, P->w(p + ".mha2.wq.k"), P->pw(p + ".mha2.wq.b"), q2, Md, d, d, SKF_ACT_NONE, nullptr, 0));
     float* kv2 = P->wsf(p + ".kv2");
-    SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), kv2, Me, 2 * d, d, SKF_ACT_NONE, nullptr, 0));
+    SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), kv2, Me, 2 * d, E, SKF_ACT_NONE, nullptr, 0));
     float* ctx2 = P->wsf(p + ".ctx2");
     SKF_TRY(attn_fwd_any(P, q2, d, kv2, 2 * d, kv2 + d, 2 * d, ctx2, d, P->wsf(p + ".lse2"), cross_pad, Td, T,
                          cross_mode, st));
@@ -683,8 +784,9 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
                            P->wsf(p + ".lse2"), delta, gQ2, d, gKV2, 2 * d, gKV2 + d, 2 * d, cross_pad, Td, T,
                            cross_mode, st));
       SKF_TRY(G.wgrad(P->wsf(p + ".out1"), gQ2, P->g(p + ".mha2.wq.k"), P->g(p + ".mha2.wq.b"), Md, d, d));
-      SKF_TRY(G.wgrad(pre, gKV2, P->g(p + ".mha2.wkv.k"), P->g(p + ".mha2.wkv.b"), Me, 2 * d, d));
-      SKF_TRY(G.dgrad(gKV2, P->w(p + ".mha2.wkv.k"), gPre, Me, 2 * d, d, nullptr, i == c.L - 1 ? nullptr : gPre, 0));
+      SKF_TRY(G.wgrad(pre, gKV2, P->g(p + ".mha2.wkv.k"), P->g(p + ".mha2.wkv.b"), Me, 2 * d, emb_dim(c)));
+      SKF_TRY(G.dgrad(gKV2, P->w(p + ".mha2.wkv.k"), gPre, Me, 2 * d, emb_dim(c), nullptr,
+                      i == c.L - 1 ? nullptr : gPre, 0));
       SKF_TRY(G.dgrad(gQ2, P->w(p + ".mha2.wq.k"), gA, Md, d, d, nullptr, gB, 0));
       // LN1 + masked self attention
       SKF_TRY(ln_bwd_any(P, gA, p, "1", gB, gD, &gS, Md, d, SITE_DEC_L + 3 * i, st));
@@ -700,20 +802,11 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
     SKF_TRY(embed_dropout(P, gA, (int64_t)Md * d, SITE_DEC_X0, st));
     SKF_TRY(embed_any_bwd(P, tok, "dec", gA, Td, st));
     SKF_TRY(skf_expand_bwd(gPre, P->wsf("embedding"), P->pw("exp.k"), gEmb, 0, P->g("exp.k"),
-                           P->g("exp.b"), B, T, d, st));
+                           P->g("exp.b"), B, T, emb_dim(c), st));
     have_demb = true;
   }
   if (c.do_classification) {
-    int Cp = (c.C + 3) & ~3;
-    float* dl = P->wsf("cls.dlogits");
-    skf_gemm_epilogue e;
-    memset(&e, 0, sizeof(e));
-    e.accumulate = 1;
-    SKF_TRY(gemm_simt(P->wsf("embedding"), 1, d, dl, Cp, 1, P->g("cls.k"), c.C, d, c.C, B, &e, st));
-    SKF_TRY(skf_colsum(dl, Cp, P->g("cls.b"), B, c.C, st));
-    memset(&e, 0, sizeof(e));
-    if (have_demb) { e.resid = gEmb; e.ld_resid = d; }
-    SKF_TRY(gemm_simt(dl, Cp, 1, P->pw("cls.k"), 1, c.C, gEmb, d, B, d, c.C, &e, st));
+    SKF_TRY(classifier_bwd(P, gEmb, have_demb, st));
     have_demb = true;
   }
   if (!have_demb) return SKF_OK;
@@ -721,10 +814,23 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
   {
     std::string last = "enc.l" + std::to_string(c.L - 1);
     const float* x = P->wsf(last + ".out2");
-    SKF_TRY(skf_pool_bwd(x, P->wsf("pool.u"), P->pw("pool.V"), P->wsf("pool.a"), gEmb, gA, 0, gU,
-                         P->g("pool.V"), B, T, d, c.u, rnd, st));
-    SKF_TRY(G.wgrad(x, gU, P->g("pool.W"), P->g("pool.b"), Me, c.u, d));
-    SKF_TRY(G.dgrad(gU, P->w("pool.W"), gA, Me, c.u, d, nullptr, gA, 0));
+    const int UP = pool_dim(c);
+    const float* gPool = gEmb;          // gradient of the pooled vector [B, d]
+    if (pool_v2(c)) {                   // through SelfAttnV2's Dense(lowerdim)
+      float* gO = P->wsf("g.po");
+      skf_gemm_epilogue e;
+      memset(&e, 0, sizeof(e));
+      e.accumulate = 1;
+      SKF_TRY(gemm_simt(P->wsf("pool.o"), 1, d, gEmb, c.u, 1, P->g("pool.emb.k"), c.u, d, c.u, B, &e, st));
+      SKF_TRY(skf_colsum(gEmb, c.u, P->g("pool.emb.b"), B, c.u, st));
+      memset(&e, 0, sizeof(e));
+      SKF_TRY(gemm_simt(gEmb, c.u, 1, P->pw("pool.emb.k"), 1, c.u, gO, d, B, d, c.u, &e, st));
+      gPool = gO;
+    }
+    SKF_TRY(skf_pool_bwd(x, P->wsf("pool.u"), P->pw("pool.V"), P->wsf("pool.a"), gPool, gA, 0, gU,
+                         P->g("pool.V"), B, T, d, UP, rnd, st));
+    SKF_TRY(G.wgrad(x, gU, P->g("pool.W"), P->g("pool.b"), Me, UP, d));
+    SKF_TRY(G.dgrad(gU, P->w("pool.W"), gA, Me, UP, d, nullptr, gA, 0));
   }
   for (int i = c.L - 1; i >= 0; i--) {
     std::string p = "enc.l" + std::to_string(i);
@@ -753,10 +859,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
 static int classify_embedding(skf_plan* P, cudaStream_t st) {
   const skf_cfg& c = P->c;
   int Cp = (c.C + 3) & ~3;
-  skf_gemm_epilogue e;
-  memset(&e, 0, sizeof(e));
-  e.bias = P->pw("cls.b");
-  SKF_TRY(gemm_simt(P->wsf("embedding"), c.d, 1, P->pw("cls.k"), c.C, 1, P->wsf("cls.logits"), Cp, c.B, c.C, c.d, &e, st));
+  SKF_TRY(classifier_fwd(P, st));
   return skf_class_ce(P->wsf("cls.logits"), Cp, nullptr, c.B, c.C, 0.f, nullptr, Cp, nullptr,
                       P->wsp<int32_t>("cls.argmax"), P->wsf("cls.probs"), st);
 }
@@ -768,14 +871,15 @@ static int decode_begin(skf_plan* P, const float* embedding, const int32_t* expe
   Gemm G{P, st};
   SKF_TRY(refresh_compute_weights(P, st));
   if (embedding && embedding != P->wsf("embedding"))
-    SKF_CUDA(cudaMemcpyAsync(P->wsf("embedding"), embedding, (size_t)B * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SKF_CUDA(cudaMemcpyAsync(P->wsf("embedding"), embedding, (size_t)B * emb_dim(c) * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
   if (c.do_classification) SKF_TRY(classify_embedding(P, st));     // sketchformer.py:307-310
   // the expanded embedding and every layer's cross-attention keys / values do not depend on the prefix
   float* pre = P->wsf("pre_decoder");
-  SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, d, rnd, st));
+  SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, emb_dim(c), rnd, st));
   for (int i = 0; i < c.L; i++) {
     std::string p = "dec.l" + std::to_string(i);
-    SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), P->wsf(p + ".kv2"), Me, 2 * d, d,
+    SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), P->wsf(p + ".kv2"), Me, 2 * d, emb_dim(c),
                   SKF_ACT_NONE, nullptr, 0));
   }
   SKF_TRY(decode_init(P->wsp<int64_t>("gen.tokens"), P->wsf("gen.strokes"), P->wsp<uint8_t>("gen.pad"),
@@ -996,7 +1100,7 @@ int skf_decode_begin(skf_plan* P, const float* embedding, const int32_t* expecte
     SKF_REQUIRE(P->c.do_classification, SKF_ERR_UNSUPPORTED, "decode: the model has neither decoder nor classifier");
     cudaStream_t st = as_stream(stream);
     if (embedding && embedding != P->wsf("embedding"))
-      SKF_CUDA(cudaMemcpyAsync(P->wsf("embedding"), embedding, (size_t)P->c.B * P->c.d * sizeof(float),
+      SKF_CUDA(cudaMemcpyAsync(P->wsf("embedding"), embedding, (size_t)P->c.B * emb_dim(P->c) * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
     return classify_embedding(P, st);
   }

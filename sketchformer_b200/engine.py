@@ -18,13 +18,15 @@ from ._lib import SkfCfg, SkfParamEntry, check
 def make_cfg(B, T, d, f, H, L, V, n_classes, lowerdim, *, continuous=False, blind_decoder_mask=True,
              do_classification=True, do_reconstruction=True, class_weight=1.0, recon_weight=1.0,
              world_size=1, gemm_backend=0, attn_backend=0, gemm_precision=2, dropout_rate=0.0,
-             dropout_seed=0) -> SkfCfg:
+             dropout_seed=0, attn_version=1, class_buffer_layers=0, class_dropout=0.1) -> SkfCfg:
     return SkfCfg(B=B, T=T, d=d, f=f, H=H, L=L, V=V, C=n_classes, u=lowerdim, continuous=int(continuous),
                   blind_decoder_mask=int(blind_decoder_mask), do_classification=int(do_classification),
                   do_reconstruction=int(do_reconstruction), warmup_steps=5000, class_weight=class_weight,
                   recon_weight=recon_weight, adam_beta1=0.9, adam_beta2=0.98, adam_eps=1e-9,
                   world_size=world_size, gemm_backend=gemm_backend, attn_backend=attn_backend,
-                  gemm_precision=gemm_precision, dropout_rate=float(dropout_rate), dropout_seed=int(dropout_seed))
+                  gemm_precision=gemm_precision, dropout_rate=float(dropout_rate), dropout_seed=int(dropout_seed),
+                  attn_version=int(attn_version), class_buffer_layers=int(class_buffer_layers),
+                  class_dropout=float(class_dropout))
 
 
 class Engine:
@@ -207,7 +209,8 @@ class Engine:
         B, T = self.cfg.B, self.cfg.T
         if embedding is not None:
             assert embedding.is_cuda and embedding.dtype == torch.float32 and embedding.is_contiguous()
-            assert tuple(embedding.shape) == (B, self.cfg.d), tuple(embedding.shape)
+            E = self.cfg.d if self.cfg.attn_version in (0, 1) else self.cfg.u
+            assert tuple(embedding.shape) == (B, E), tuple(embedding.shape)
         if expected_len is not None:
             expected_len = expected_len.to(device=self.device, dtype=torch.int32).contiguous()
             assert expected_len.numel() == B

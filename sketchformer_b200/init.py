@@ -14,6 +14,8 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
     do_class = hps.get("do_classification", True)
     do_recon = hps.get("do_reconstruction", True)
     continuous = bool(hps.get("use_continuous_data", False))
+    v2 = hps.get("attn_version", 1) != 1
+    nbuf = int(hps.get("class_buffer_layers", 0))
     gen = torch.Generator().manual_seed(seed)
     p: Dict[str, torch.Tensor] = {}
 
@@ -27,6 +29,8 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
     def dense(name, fin, fout):
         p[name + ".k"] = glorot(fin, fout, (fin, fout))
         p[name + ".b"] = torch.zeros(fout, dtype=torch.float64)
+
+    emb_dim = u if v2 else d
 
     def mha(name, kv_in):
         dense(name + ".wq", d, d)
@@ -51,18 +55,28 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
         dense(f"enc.l{i}.ffn.w2", f, d)
         ln(f"enc.l{i}.ln1")
         ln(f"enc.l{i}.ln2")
-    p["pool.W"] = torch.randn((d, u), generator=gen, dtype=torch.float64) * 0.05
-    p["pool.b"] = torch.zeros(u, dtype=torch.float64)
-    p["pool.V"] = uni05((u, 1))
-    if do_class:
-        dense("cls", d, C)
+    if not v2:                          # SelfAttnV1.build transformer.py:41-59
+        p["pool.W"] = torch.randn((d, u), generator=gen, dtype=torch.float64) * 0.05
+        p["pool.b"] = torch.zeros(u, dtype=torch.float64)
+        p["pool.V"] = uni05((u, 1))
+    else:                               # SelfAttnV2.build transformer.py:96-114
+        p["pool.W"] = torch.randn((d, d), generator=gen, dtype=torch.float64) * 0.05
+        p["pool.b"] = torch.zeros(d, dtype=torch.float64)
+        p["pool.V"] = uni05((d, 1))
+        dense("pool.emb", d, u)
+    if do_class:                        # models/sketchformer.py:99-104
+        fin = emb_dim
+        for j in range(nbuf):
+            dense(f"cbuf{j}", fin, u)
+            fin = u
+        dense("cls", fin, C)
     if do_recon:
         p["exp.k"] = glorot(1, T, (1, T))
         p["exp.b"] = torch.zeros(T, dtype=torch.float64)
         embed("dec")
         for i in range(L):
             mha(f"dec.l{i}.mha1", d)
-            mha(f"dec.l{i}.mha2", d)
+            mha(f"dec.l{i}.mha2", emb_dim)
             dense(f"dec.l{i}.ffn.w1", d, f)
             dense(f"dec.l{i}.ffn.w2", f, d)
             for j in (1, 2, 3):

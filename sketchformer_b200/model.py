@@ -90,17 +90,18 @@ class Transformer:
         self.build_model()
 
     @property
+    def embedding_dim(self):
+        """SelfAttnV1 pools to d_model; SelfAttnV2 adds Dense(lowerdim) (transformer.py:129-130)."""
+        return self.hps["d_model"] if self.hps["attn_version"] == 1 else self.hps["lowerdim"]
+
+    @property
     def identifier(self):
         return "{}-{}".format(self.name, self.experiment_id)
 
     def _unsupported(self):
         h = self.hps
-        if h["attn_version"] != 1:
-            return "attn_version=2 (SelfAttnV2 bottleneck)"
         if not h["lowerdim"]:
             return "lowerdim=0 (no bottleneck)"
-        if h["class_buffer_layers"]:
-            return "class_buffer_layers>0"
         if h["optimizer"].lower() != "adam":
             return "optimizer=%s (only Adam is built)" % h["optimizer"]
         if h["lr_scheduler"] not in ("WarmupDecay", "warmup-decay"):
@@ -122,7 +123,8 @@ class Transformer:
                         self.vocab_size or 0, self.dataset.n_classes, h["lowerdim"], continuous=self.continuous,
                         blind_decoder_mask=h["blind_decoder_mask"], do_classification=h["do_classification"],
                         do_reconstruction=h["do_reconstruction"], class_weight=h["class_weight"],
-                        recon_weight=h["recon_weight"], world_size=self._world, dropout_rate=h["dropout_rate"],
+                        recon_weight=h["recon_weight"], world_size=self._world, dropout_rate=h["dropout_rate"], attn_version=h["attn_version"],
+                        class_buffer_layers=h["class_buffer_layers"], class_dropout=h["class_dropout"],
                         dropout_seed=(0x5EED + 7919 * self._seed + 104729 * self._rank) & 0xFFFFFFFF, **kw)
 
     def _engine(self, B, training=False):
@@ -247,7 +249,7 @@ class Transformer:
         B = inp_seq.shape[0]
         eng = self._engine(B)
         eng.encode(self._to_device("x", inp_seq, torch.float32 if self.continuous else torch.int64))
-        out = {"embedding": eng.tensor("embedding", (B, self.hps["d_model"])).cpu().numpy(), "class": None}
+        out = {"embedding": eng.tensor("embedding", (B, self.embedding_dim)).cpu().numpy(), "class": None}
         if self.hps["do_classification"]:
             out["class"] = eng.tensor("cls.probs", (B, self.dataset.n_classes)).cpu().numpy()
             out["_argmax"] = eng.tensor("cls.argmax", dtype=torch.int32)[:B].cpu().numpy()

@@ -42,7 +42,8 @@ def build(cfg_kw, B, backend, precision=2, attn_backend=-1, **flags):
                  do_classification=ocfg.do_classification, do_reconstruction=ocfg.do_reconstruction,
                  class_weight=ocfg.class_weight, recon_weight=ocfg.recon_weight, gemm_backend=backend,
                  attn_backend=backend if attn_backend < 0 else attn_backend, gemm_precision=precision,
-                 dropout_rate=ocfg.dropout_rate, dropout_seed=DROPOUT_SEED)
+                 dropout_rate=ocfg.dropout_rate, dropout_seed=DROPOUT_SEED, attn_version=ocfg.attn_version,
+                 class_buffer_layers=ocfg.class_buffer_layers, class_dropout=ocfg.class_dropout)
     return ocfg, Engine(c)
 
 
@@ -312,3 +313,47 @@ def test_train_step_with_dropout_matches_oracle(name, cfg_kw, B, cont, backend):
     eng0.load_params(p)
     eng.encode(xt.cuda()); eng0.encode(xt.cuda())
     assert torch.equal(eng.tensor("embedding", (B, ocfg.d_model)), eng0.tensor("embedding", (B, ocfg.d_model)))
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("flags", [dict(attn_version=2), dict(class_buffer_layers=2),
+                                   dict(attn_version=2, class_buffer_layers=1, dropout_rate=0.1, class_dropout=0.2)],
+                         ids=["selfattn-v2", "class-buffer-2", "v2+buffer+dropout"])
+def test_bottleneck_variants_match_oracle(flags, backend):
+    """attn_version=2 (SelfAttnV2: (d,d) pooling attention + Dense(lowerdim), embedding / expander / cross
+    keys-values lowerdim wide, transformer.py:80-137) and class_buffer_layers (Dense(lowerdim, relu) +
+    Dropout(class_dropout) before the classifier, models/sketchformer.py:99-104, 183-199)."""
+    from oracle.dropout_rng import DeviceMasks
+    tol = 2e-4 if backend == 1 else 1e-3
+    B = 4
+    ocfg, eng = build(TINY, B, backend, **flags)
+    x, y = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 31, vocab=ocfg.vocab_size)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    p = O.init_params(ocfg, 0, torch.float64)
+    eng.load_params(p)
+    eng.train_step(xt.cuda(), yt.cuda(), apply_adam=False)
+    torch.cuda.synchronize()
+    pattern = engine_relu_pattern(eng, ocfg, B)
+    masks = DeviceMasks(ocfg.dropout_rate, DROPOUT_SEED, 0, class_rate=ocfg.class_dropout)
+    with O.dropout_masks(masks), O.relu_pattern(pattern):
+        losses, grads = O.train_step(p, O.AdamTF(p, ocfg.d_model), xt, yt, ocfg, dtype=torch.float64)
+    m = eng.last_step_metrics()
+    for k in ("recon_loss", "class_loss", "total_loss"):
+        assert abs(m[k] - losses[k]) <= tol * abs(losses[k]), (k, m[k], losses[k])
+    got = eng.export_grads(grads)
+    G = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
+    bad = []
+    for k, ref in grads.items():
+        num = float((got[k].double() - ref.double()).norm())
+        if not num / max(float(ref.double().norm()), 1e-4 * G) < tol:
+            bad.append((k, num / max(float(ref.double().norm()), 1e-4 * G)))
+    assert not bad, f"gradients off: {sorted(bad, key=lambda t: -t[1])[:8]}"
+    # inference: embedding width, class prediction and greedy decode through the same variants
+    E = ocfg.d_model if ocfg.attn_version == 1 else ocfg.lowerdim
+    want = O.predict(p, xt, ocfg, sos=ocfg.vocab_size - 2, eos=ocfg.vocab_size - 1, dtype=torch.float64)
+    eng.encode(xt.cuda())
+    assert rel_err(eng.tensor("embedding", (B, E)), want["embedding"]) < tol
+    assert torch.equal(eng.tensor("cls.argmax", dtype=torch.int32).cpu()[:B], want["class"])
+    got_tok = eng.decode(None, None, ocfg.vocab_size - 2, ocfg.vocab_size - 1).cpu().numpy()
+    from tests.test_gpu_decode import _assert_same_tokens
+    _assert_same_tokens(p, ocfg, want["embedding"], got_tok, want["recon"].numpy())

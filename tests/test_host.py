@@ -65,7 +65,7 @@ def test_bad_configs_are_rejected_with_a_message():
 
 
 def test_product_initialiser_equals_oracle():
-    for kw in (TINY, CFG1, dict(TINY, use_continuous_data=True)):
+    for kw in (TINY, CFG1, dict(TINY, use_continuous_data=True), dict(TINY, attn_version=2, class_buffer_layers=2)):
         a = init_params(kw, 0)
         b = O.init_params(O.OracleConfig(**kw), 0)
         assert list(a) == list(b)
