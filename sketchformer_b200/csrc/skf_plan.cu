@@ -75,8 +75,11 @@ static int check_cfg(const skf_cfg* c) {
   SKF_REQUIRE(c->d % 4 == 0 && c->f % 4 == 0, SKF_ERR_BAD_SHAPE, "cfg: d_model and dff must be multiples of 4");
   int dh = c->d / c->H;
   SKF_REQUIRE(dh == 16 || dh == 32 || dh == 64, SKF_ERR_UNSUPPORTED, "cfg: head dim %d not in {16,32,64}", dh);
-  SKF_REQUIRE(c->u > 0, SKF_ERR_UNSUPPORTED, "cfg: lowerdim=0 (no bottleneck) is not built yet");
-  SKF_REQUIRE(c->u % 4 == 0, SKF_ERR_BAD_SHAPE, "cfg: lowerdim must be a multiple of 4");
+  SKF_REQUIRE(c->u >= 0 && c->u % 4 == 0, SKF_ERR_BAD_SHAPE, "cfg: lowerdim must be a non-negative multiple of 4");
+  // lowerdim=0: no bottleneck / classifier / expander, the decoder attends to the encoder output
+  // (models/sketchformer.py:96-107, 157-158, 175-176); build_model() then creates no classify_layer
+  SKF_REQUIRE(c->u > 0 || (!c->do_classification && c->do_reconstruction), SKF_ERR_BAD_ARG,
+              "cfg: lowerdim=0 needs do_classification=0 and do_reconstruction=1");
   SKF_REQUIRE(c->continuous || (c->V > 0 && c->V % 4 == 0), SKF_ERR_BAD_SHAPE,
               "cfg: vocab size must be a positive multiple of 4");
   SKF_REQUIRE(!c->do_classification || c->C > 0, SKF_ERR_BAD_SHAPE, "cfg: n_classes");
@@ -90,7 +93,7 @@ static int check_cfg(const skf_cfg* c) {
 
 // SelfAttnV1: pooling hidden width = lowerdim, embedding width = d_model;
 // SelfAttnV2: hidden width = d_model, Dense(lowerdim) after the pooling, embedding width = lowerdim.
-static inline bool pool_v2(const skf_cfg& c) { return c.attn_version != 0 && c.attn_version != 1; }
+static inline bool pool_v2(const skf_cfg& c) { return c.u > 0 && c.attn_version != 0 && c.attn_version != 1; }
 static inline int emb_dim(const skf_cfg& c) { return pool_v2(c) ? c.u : c.d; }
 static inline int pool_dim(const skf_cfg& c) { return pool_v2(c) ? c.d : c.u; }
 
@@ -124,9 +127,11 @@ static ParamLayout build_layout(const skf_cfg& c) {
     add_mha_self(L, p + ".mha", c.d);
     add_ffn_ln(L, p, c.d, c.f, 2);
   }
-  L.add("pool.W", c.d, pool_dim(c));
-  L.add("pool.b", 1, pool_dim(c));
-  L.add("pool.V", 1, pool_dim(c));
+  if (c.u > 0) {
+    L.add("pool.W", c.d, pool_dim(c));
+    L.add("pool.b", 1, pool_dim(c));
+    L.add("pool.V", 1, pool_dim(c));
+  }
   if (pool_v2(c)) {                       // SelfAttnV2.embeding_layer (transformer.py:99-100, 129-130)
     L.add("pool.emb.k", c.d, c.u);
     L.add("pool.emb.b", 1, c.u);
@@ -142,8 +147,10 @@ static ParamLayout build_layout(const skf_cfg& c) {
     L.add("cls.b", 1, c.C);
   }
   if (c.do_reconstruction) {
-    L.add("exp.k", 1, c.T);
-    L.add("exp.b", 1, c.T);
+    if (c.u > 0) {
+      L.add("exp.k", 1, c.T);
+      L.add("exp.b", 1, c.T);
+    }
     if (c.continuous) {
       L.add("dec.emb.k", 5, c.d);
       L.add("dec.emb.b", 1, c.d);
@@ -631,6 +638,7 @@ static int forward_encoder(skf_plan* P, const void* tok, cudaStream_t st) {
                           P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), Me, d, f, SITE_ENC_L + 2 * i + 1, st));
     x = out2;
   }
+  if (c.u == 0) return SKF_OK;      // lowerdim=0: embedding = enc_output (sketchformer.py:157-158)
   // bottleneck (SelfAttnV1.call transformer.py:61-74 / SelfAttnV2.call 116-131)
   const int UP = pool_dim(c);
   float* u = P->wsf("pool.u");
@@ -652,9 +660,10 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
   const int B = c.B, T = c.T, Td = c.T - 1, d = c.d, f = c.f, Me = B * T, Md = B * Td;
   const int rnd = P->round_ops ? 1 : 0;
   Gemm G{P, st};
-  float* pre = P->wsf("pre_decoder");
   const int E = emb_dim(c);
-  SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, E, rnd, st));
+  float* pre = P->wsf("pre_decoder");
+  if (c.u > 0) SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, E, rnd, st));
+  else pre = P->wsf("enc.l" + std::to_string(c.L - 1) + ".out2");      // sketchformer.py:175-176
   uint8_t* dec_pad = P->wsp<uint8_t>("dec_pad");
   float* x = P->wsf("dec.x0");
   SKF_TRY(embed_any(P, tok, "dec", dec_pad, x, Td, st));   // tar_inp = tar[:, :-1]
@@ -750,7 +759,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
     const uint8_t* dec_pad = P->wsp<uint8_t>("dec_pad");
     const uint8_t* cross_pad = c.blind_decoder_mask ? nullptr : enc_pad;
     const int cross_mode = c.blind_decoder_mask ? 0 : 1;
-    float* pre = P->wsf("pre_decoder");
+    float* pre = c.u > 0 ? P->wsf("pre_decoder") : P->wsf("enc.l" + std::to_string(c.L - 1) + ".out2");
     float* dlog = P->wsf("recon.logits");  // holds dlogits after losses()
     std::string last = "dec.l" + std::to_string(c.L - 1);
     if (c.continuous) {
@@ -801,17 +810,23 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
     }
     SKF_TRY(embed_dropout(P, gA, (int64_t)Md * d, SITE_DEC_X0, st));
     SKF_TRY(embed_any_bwd(P, tok, "dec", gA, Td, st));
-    SKF_TRY(skf_expand_bwd(gPre, P->wsf("embedding"), P->pw("exp.k"), gEmb, 0, P->g("exp.k"),
-                           P->g("exp.b"), B, T, emb_dim(c), st));
-    have_demb = true;
+    if (c.u > 0) {
+      SKF_TRY(skf_expand_bwd(gPre, P->wsf("embedding"), P->pw("exp.k"), gEmb, 0, P->g("exp.k"),
+                             P->g("exp.b"), B, T, emb_dim(c), st));
+      have_demb = true;
+    }
   }
   if (c.do_classification) {
     SKF_TRY(classifier_bwd(P, gEmb, have_demb, st));
     have_demb = true;
   }
-  if (!have_demb) return SKF_OK;
-  // bottleneck backward
-  {
+  if (c.u == 0) {
+    // lowerdim=0: the encoder output reaches the loss only as the decoder's cross keys / values
+    SKF_CUDA(cudaMemcpyAsync(gA, gPre, (size_t)Me * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else if (!have_demb) {
+    return SKF_OK;
+  } else {
+    // bottleneck backward
     std::string last = "enc.l" + std::to_string(c.L - 1);
     const float* x = P->wsf(last + ".out2");
     const int UP = pool_dim(c);
@@ -870,13 +885,19 @@ static int decode_begin(skf_plan* P, const float* embedding, const int32_t* expe
   const int rnd = P->round_ops ? 1 : 0;
   Gemm G{P, st};
   SKF_TRY(refresh_compute_weights(P, st));
-  if (embedding && embedding != P->wsf("embedding"))
-    SKF_CUDA(cudaMemcpyAsync(P->wsf("embedding"), embedding, (size_t)B * emb_dim(c) * sizeof(float),
-                             cudaMemcpyDeviceToDevice, st));
-  if (c.do_classification) SKF_TRY(classify_embedding(P, st));     // sketchformer.py:307-310
-  // the expanded embedding and every layer's cross-attention keys / values do not depend on the prefix
   float* pre = P->wsf("pre_decoder");
-  SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, emb_dim(c), rnd, st));
+  if (c.u == 0) {
+    // lowerdim=0: the "embedding" IS the encoder output [B, T, d] and feeds the decoder unexpanded
+    const float* src = embedding ? embedding : P->wsf("enc.l" + std::to_string(c.L - 1) + ".out2");
+    SKF_CUDA(cudaMemcpyAsync(pre, src, (size_t)Me * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    if (embedding && embedding != P->wsf("embedding"))
+      SKF_CUDA(cudaMemcpyAsync(P->wsf("embedding"), embedding, (size_t)B * emb_dim(c) * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    if (c.do_classification) SKF_TRY(classify_embedding(P, st));     // sketchformer.py:307-310
+    // the expanded embedding and every layer's cross-attention keys / values do not depend on the prefix
+    SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, emb_dim(c), rnd, st));
+  }
   for (int i = 0; i < c.L; i++) {
     std::string p = "dec.l" + std::to_string(i);
     SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), P->wsf(p + ".kv2"), Me, 2 * d, emb_dim(c),

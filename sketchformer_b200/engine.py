@@ -209,8 +209,9 @@ class Engine:
         B, T = self.cfg.B, self.cfg.T
         if embedding is not None:
             assert embedding.is_cuda and embedding.dtype == torch.float32 and embedding.is_contiguous()
-            E = self.cfg.d if self.cfg.attn_version in (0, 1) else self.cfg.u
-            assert tuple(embedding.shape) == (B, E), tuple(embedding.shape)
+            E = self.cfg.d if (self.cfg.attn_version in (0, 1) or not self.cfg.u) else self.cfg.u
+            want = (B, E) if self.cfg.u else (B, T, E)       # lowerdim=0: the embedding is the encoder output
+            assert tuple(embedding.shape) == want, tuple(embedding.shape)
         if expected_len is not None:
             expected_len = expected_len.to(device=self.device, dtype=torch.int32).contiguous()
             assert expected_len.numel() == B

@@ -30,7 +30,7 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
         p[name + ".k"] = glorot(fin, fout, (fin, fout))
         p[name + ".b"] = torch.zeros(fout, dtype=torch.float64)
 
-    emb_dim = u if v2 else d
+    emb_dim = u if (v2 and u) else d
 
     def mha(name, kv_in):
         dense(name + ".wq", d, d)
@@ -55,7 +55,9 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
         dense(f"enc.l{i}.ffn.w2", f, d)
         ln(f"enc.l{i}.ln1")
         ln(f"enc.l{i}.ln2")
-    if not v2:                          # SelfAttnV1.build transformer.py:41-59
+    if not u:                           # lowerdim=0: no bottleneck, classifier or expander (sketchformer.py:96)
+        do_class = False
+    elif not v2:                        # SelfAttnV1.build transformer.py:41-59
         p["pool.W"] = torch.randn((d, u), generator=gen, dtype=torch.float64) * 0.05
         p["pool.b"] = torch.zeros(u, dtype=torch.float64)
         p["pool.V"] = uni05((u, 1))
@@ -71,8 +73,9 @@ def init_params(hps: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torc
             fin = u
         dense("cls", fin, C)
     if do_recon:
-        p["exp.k"] = glorot(1, T, (1, T))
-        p["exp.b"] = torch.zeros(T, dtype=torch.float64)
+        if u:
+            p["exp.k"] = glorot(1, T, (1, T))
+            p["exp.b"] = torch.zeros(T, dtype=torch.float64)
         embed("dec")
         for i in range(L):
             mha(f"dec.l{i}.mha1", d)

@@ -92,7 +92,7 @@ class Transformer:
     @property
     def embedding_dim(self):
         """SelfAttnV1 pools to d_model; SelfAttnV2 adds Dense(lowerdim) (transformer.py:129-130)."""
-        return self.hps["d_model"] if self.hps["attn_version"] == 1 else self.hps["lowerdim"]
+        return self.hps["d_model"] if (self.hps["attn_version"] == 1 or not self.hps["lowerdim"]) else self.hps["lowerdim"]
 
     @property
     def identifier(self):
@@ -100,8 +100,9 @@ class Transformer:
 
     def _unsupported(self):
         h = self.hps
-        if not h["lowerdim"]:
-            return "lowerdim=0 (no bottleneck)"
+        if not h["lowerdim"] and (h["do_classification"] or not h["do_reconstruction"]):
+            return ("lowerdim=0 with do_classification=True (the reference builds no classify_layer then, "
+                    "models/sketchformer.py:96-107)")
         if h["optimizer"].lower() != "adam":
             return "optimizer=%s (only Adam is built)" % h["optimizer"]
         if h["lr_scheduler"] not in ("WarmupDecay", "warmup-decay"):
@@ -249,6 +250,9 @@ class Transformer:
         B = inp_seq.shape[0]
         eng = self._engine(B)
         eng.encode(self._to_device("x", inp_seq, torch.float32 if self.continuous else torch.int64))
+        if not self.hps["lowerdim"]:      # embedding = enc_output (B, T, d), models/sketchformer.py:157-158
+            name = "enc.l%d.out2" % (self.hps["num_layers"] - 1)
+            return {"embedding": eng.tensor(name, (B, self.seq_len, self.hps["d_model"])).cpu().numpy(), "class": None}
         out = {"embedding": eng.tensor("embedding", (B, self.embedding_dim)).cpu().numpy(), "class": None}
         if self.hps["do_classification"]:
             out["class"] = eng.tensor("cls.probs", (B, self.dataset.n_classes)).cpu().numpy()
@@ -273,7 +277,7 @@ class Transformer:
         `expected_len` is ignored when blind_decoder_mask=True, exactly as the reference's decode() does.
         The per-step attention maps the reference returns are never materialised here."""
         emb = np.asarray(emb, dtype=np.float32)
-        if emb.ndim == 1:
+        if emb.ndim == (1 if self.hps["lowerdim"] else 2):
             emb = emb[None]
         B = emb.shape[0]
         eng = self._engine(B)

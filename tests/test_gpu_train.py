@@ -357,3 +357,36 @@ def test_bottleneck_variants_match_oracle(flags, backend):
     got_tok = eng.decode(None, None, ocfg.vocab_size - 2, ocfg.vocab_size - 1).cpu().numpy()
     from tests.test_gpu_decode import _assert_same_tokens
     _assert_same_tokens(p, ocfg, want["embedding"], got_tok, want["recon"].numpy())
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+def test_no_bottleneck_matches_oracle(backend):
+    """lowerdim=0 (models/sketchformer.py:96, 157-158, 175-176): no pooling / classifier / expander; the decoder's
+    cross-attention reads the encoder output and its gradient flows back into the encoder through it."""
+    tol = 2e-4 if backend == 1 else 1e-3
+    B = 4
+    ocfg, eng = build(dict(TINY, lowerdim=0), B, backend, do_classification=False)
+    x, y = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 41, vocab=ocfg.vocab_size)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    p = O.init_params(ocfg, 0, torch.float64)
+    assert "pool.W" not in p and "cls.k" not in p and "exp.k" not in p
+    eng.load_params(p)
+    eng.train_step(xt.cuda(), yt.cuda(), apply_adam=False)
+    torch.cuda.synchronize()
+    with O.relu_pattern(engine_relu_pattern(eng, ocfg, B)):
+        losses, grads = O.train_step(p, O.AdamTF(p, ocfg.d_model), xt, yt, ocfg, dtype=torch.float64)
+    m = eng.last_step_metrics()
+    assert abs(m["total_loss"] - losses["total_loss"]) <= tol * abs(losses["total_loss"])
+    got = eng.export_grads(grads)
+    G = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
+    bad = []
+    for k, ref in grads.items():
+        num = float((got[k].double() - ref.double()).norm())
+        if not num / max(float(ref.double().norm()), 1e-4 * G) < tol:
+            bad.append((k, num / max(float(ref.double().norm()), 1e-4 * G)))
+    assert not bad, f"gradients off: {sorted(bad, key=lambda t: -t[1])[:8]}"
+    want = O.predict(p, xt, ocfg, sos=ocfg.vocab_size - 2, eos=ocfg.vocab_size - 1, dtype=torch.float64)
+    eng.encode(xt.cuda())
+    got_tok = eng.decode(None, None, ocfg.vocab_size - 2, ocfg.vocab_size - 1).cpu().numpy()
+    from tests.test_gpu_decode import _assert_same_tokens
+    _assert_same_tokens(p, ocfg, want["embedding"], got_tok, want["recon"].numpy())
