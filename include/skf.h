@@ -278,6 +278,13 @@ int skf_forward(skf_plan* plan, const void* tokens, void* stream);
 int skf_decode_begin(skf_plan* plan, const float* embedding, const int32_t* expected_len,
                      int64_t sos_token, int64_t eos_token, void* stream);
 int skf_decode_steps(skf_plan* plan, int first_step, int n_steps, void* stream);
+/* DistributedStroke3DataLoader.preprocess + Tokenizer.encode for a batch of raw stroke-3 sketches
+ * (dataloaders/distributed_stroke3.py:90-125, 138-153; utils/tokenizer.py:35-64; utils/sketch.py:31-50).
+ * points: float [total, 3] rows (dx, dy, pen) of all sketches back to back; offsets: int64 [B+1] row ranges;
+ * centroids: float [K, 2] (KMeans cluster_centers_); out: int64 [B, T] = [SOS] ids.. (SEP after pen lifts) [EOS]
+ * PAD.., truncated to T.  Clip to +-limit, normalise by max(bbox_w, bbox_h, 1) of the absolute path.  */
+int skf_tokenize_strokes(const float* points, const int64_t* offsets, int B, const float* centroids, int K,
+                         float limit, int64_t* out, int T, void* stream);
 /* Number of kernels launched by this plan since creation (bench `gpu_launches`).           */
 int64_t skf_plan_launches(const skf_plan* plan);
 

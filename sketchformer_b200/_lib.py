@@ -77,6 +77,7 @@ SIGNATURES = {
     "skf_forward": (I, [P, P, P]),
     "skf_decode_begin": (I, [P, P, P, L, L, P]),
     "skf_decode_steps": (I, [P, I, I, P]),
+    "skf_tokenize_strokes": (I, [P, P, I, P, I, F, P, I, P]),
     "skf_plan_launches": (L, [P]),
 }
 

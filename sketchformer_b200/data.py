@@ -33,13 +33,14 @@ class SyntheticStroke3DataLoader:
             hps = hps.parse(params)
         return hps
 
-    def __init__(self, hps, data_directory=None, n_classes=345, n_samples=1 << 20, seed=1234, rank=0, world_size=1):
+    def __init__(self, hps, data_directory=None, n_classes=345, n_samples=1 << 20, seed=1234, rank=0, world_size=1,
+                 vocab=synth.VOCAB_SIZE):
         self.hps = hps if isinstance(hps, dict) else dict(hps.values())
         self.data_directory = data_directory
         self.tokenizer = None if self.hps["use_continuous_data"] else TokenizerInfo()
         self.n_classes, self.n_samples = n_classes, n_samples
         self.class_names = np.array([f"class_{i}" for i in range(n_classes)])
-        self.seed, self.rank, self.world_size = seed, rank, world_size
+        self.seed, self.rank, self.world_size, self.vocab = seed, rank, world_size, vocab
 
     def batch_iterator(self, split_name, batch_size, stop_at_end_of_split=False):
         """core/data.py:146-172: yields [x (B,T) int64 | (B,T,5) float32, y (B,1) int64].  With
@@ -49,13 +50,224 @@ class SyntheticStroke3DataLoader:
         gen = synth.continuous_batch if self.hps["use_continuous_data"] else synth.token_batch
         total = self.n_samples // (batch_size * self.world_size)
         while not (stop_at_end_of_split and step >= total):
-            x, y = gen(batch_size * self.world_size, T, self.n_classes, self.seed + step)
+            kw = {} if self.hps["use_continuous_data"] else {"vocab": self.vocab}
+            x, y = gen(batch_size * self.world_size, T, self.n_classes, self.seed + step, **kw)
             lo = self.rank * batch_size
             yield [x[lo:lo + batch_size], y[lo:lo + batch_size]]
             step += 1
 
 
-dataloaders_by_name = {SyntheticStroke3DataLoader.name: SyntheticStroke3DataLoader}
+def augment_strokes(strokes, prob, rng):
+    """utils/sketch.py:127-149: drop interior points of a stroke with probability `prob`, merging their
+    offsets into the next kept point (points next to a pen lift are never dropped)."""
+    result, prev, stroke, count = [], [0, 0, 1], [0, 0, 1], 0
+    for i in range(len(strokes)):
+        cand = [strokes[i][0], strokes[i][1], strokes[i][2]]
+        count = 0 if (cand[2] == 1 or prev[2] == 1) else count + 1
+        urnd = rng.random()
+        if cand[2] == 0 and prev[2] == 0 and count > 2 and urnd < prob:
+            stroke[0] += cand[0]
+            stroke[1] += cand[1]
+        else:
+            stroke = cand
+            prev = stroke
+            result.append(stroke)
+    return np.array(result, dtype=np.float32).reshape(-1, 3)
+
+
+class _Split:
+    """core/data.py:9-20 DatasetSplit."""
+
+    def __init__(self, name, filepaths):
+        self.name, self.filepaths, self.n_files = name, sorted(filepaths), len(filepaths)
+        self.current = self.next = None
+        self.current_index_shuffle, self.current_len, self.cursor = [], 0, 0
+        self.file_cursor, self.file_shuffle, self.thread = 0, [], None
+        self.did_load_first_megabatch = False
+
+
+class DistributedStroke3DataLoader:
+    """`stroke3-distributed` (dataloaders/distributed_stroke3.py:10-204 + core/data.py:33-254): the dataset is
+    a directory of .npz chunks (`meta*.npz`, `train*.npz`, `valid*.npz`, `test*.npz`, written by
+    prep_data/prepare-distributed-quickdraw.py:92-126) with `x` an object array of (n_i, 3) stroke-3 sketches
+    and `y` integer labels.  One prefetch thread per split loads and preprocesses the next chunk while the
+    current one is iterated; chunks are swapped when exhausted.
+
+    Data parallel (not in the reference): with world_size > 1 the train chunks are dealt
+    round-robin to the ranks (rank r reads files r, r + W, ...) when there are at least W of them, otherwise
+    every rank walks the same chunk in the same (seeded) order and keeps samples r, r + W, ...
+    """
+    name = "stroke3-distributed"
+
+    @classmethod
+    def default_hparams(cls):
+        return SyntheticStroke3DataLoader.default_hparams()
+
+    @classmethod
+    def parse_hparams(cls, params):
+        hps = cls.default_hparams()
+        if params is not None:
+            hps = hps.parse(params)
+        return hps
+
+    def __init__(self, hps, data_directory, rank=0, world_size=1, seed=None, tokenizer=None):
+        import glob
+        import os
+        import threading
+        self._threading = threading
+        self.hps = hps if isinstance(hps, dict) else dict(hps.values())
+        self.data_directory = data_directory
+        self.rank, self.world_size = rank, world_size
+        self.limit = 1000
+        self.rng = np.random.default_rng(seed)
+        self.tokenizer = tokenizer
+        if not self.hps["use_continuous_data"] and tokenizer is None:
+            if self.hps["token_type"] != "dictionary":
+                raise NotImplementedError("token_type=%s: only the dictionary tokenizer is built" % self.hps["token_type"])
+            from .tokenizer import Tokenizer
+            self.tokenizer = Tokenizer(self.hps["tokenizer_dict_file"], max_seq_len=0)
+        files = glob.glob(os.path.join(data_directory, "*"))
+        base = os.path.basename
+        meta = [f for f in files if base(f).startswith("meta")][0]
+        md = np.load(meta, allow_pickle=True)
+        self.n_classes = int(md["n_classes"])
+        self.n_samples = int(md["n_samples_train"])
+        self.class_names = md["class_names"]
+        self.scale_factor = float(md["std"])
+        self.splits = {n: _Split(n, [f for f in files if base(f).startswith(n)]) for n in ("train", "test", "valid")}
+        tr = self.splits["train"]
+        self._slice_samples = world_size > 1 and tr.n_files < world_size
+        if world_size > 1 and not self._slice_samples:
+            tr.filepaths = tr.filepaths[rank::world_size]
+            tr.n_files = len(tr.filepaths)
+        for s, split in self.splits.items():
+            if not split.n_files:
+                continue
+            split.file_shuffle = self.reshuffle_file_indices(s, split.filepaths)
+            self._start_load(split, split.filepaths[split.file_shuffle[0]])
+
+    # ---- chunk loading (core/data.py:44-50, 79-113; distributed_stroke3.py:77-88) -----------------
+    def _start_load(self, split, path):
+        split.thread = self._threading.Thread(target=self.load_next_megabatch, args=(split.name, path), daemon=True)
+        split.thread.start()
+
+    def reshuffle_file_indices(self, split_name, filenames):
+        return self.rng.permutation(len(filenames)) if split_name == "train" else list(range(len(filenames)))
+
+    def reshuffle_sample_indices(self, split_name, data):
+        if split_name != "train":
+            return list(range(len(data["x"])))
+        if self._slice_samples:      # every rank draws the same order, then keeps its residue class
+            order = np.random.default_rng(len(data["x"]) + 7919 * self.splits["train"].file_cursor).permutation(len(data["x"]))
+            return order[self.rank::self.world_size]
+        return self.rng.permutation(len(data["x"]))
+
+    def load_next_megabatch(self, split_name, selected_file):
+        loaded = np.load(selected_file, allow_pickle=True)
+        data = {"x": self.preprocess(loaded["x"], augment=split_name == "train"), "y": np.asarray(loaded["y"])}
+        self.splits[split_name].next = data
+
+    def _swap(self, split_name):
+        split = self.splits[split_name]
+        split.thread.join()
+        split.current = split.next
+        split.current_index_shuffle = self.reshuffle_sample_indices(split_name, split.current)
+        split.current_len = len(split.current_index_shuffle)
+        split.file_cursor += 1
+        done = split.file_cursor == split.n_files
+        if done:
+            split.file_cursor = 0
+            split.file_shuffle = self.reshuffle_file_indices(split_name, split.filepaths)
+        if split.n_files > 1:
+            self._start_load(split, split.filepaths[split.file_shuffle[split.file_cursor]])
+        return done
+
+    def _ready(self, split_name):
+        split = self.splits[split_name]
+        if not split.did_load_first_megabatch:
+            split.did_load_first_megabatch = True
+            self._swap(split_name)
+        return split
+
+    # ---- per-sketch preprocessing (distributed_stroke3.py:90-162) ---------------------------------
+    def preprocess(self, data, augment=False):
+        from .tokenizer import preprocess_sketch_host
+        T, out = self.hps["max_seq_len"], []
+        if self.hps["shuffle_stroke"] or self.hps["use_absolute_strokes"]:
+            raise NotImplementedError("shuffle_stroke / use_absolute_strokes are not built")
+        for sketch in data:
+            if not self.hps["use_continuous_data"]:
+                out.append(preprocess_sketch_host(sketch, self.tokenizer, T, self.limit))
+                continue
+            s = np.array(np.maximum(np.minimum(sketch, self.limit), -self.limit), dtype=np.float32).reshape(-1, 3)
+            if augment and self.hps["augment_stroke_prob"] > 0:
+                e = self.hps["random_scale_factor"]
+                s = s.copy()
+                s[:, 0] *= (self.rng.random() - 0.5) * 2 * e + 1.0
+                s[:, 1] *= (self.rng.random() - 0.5) * 2 * e + 1.0
+                s = augment_strokes(s, self.hps["augment_stroke_prob"], self.rng)
+            ax, ay = np.cumsum(s[:, 0].astype(np.float64)), np.cumsum(s[:, 1].astype(np.float64))
+            w = max(0.0, ax.max(initial=0.0)) - min(0.0, ax.min(initial=0.0))
+            h = max(0.0, ay.max(initial=0.0)) - min(0.0, ay.min(initial=0.0))
+            s[:, :2] /= max(w, h, 1)
+            s = s[:T]
+            conv = np.zeros((T, 5), dtype=np.float32)
+            n = len(s)
+            conv[:n, 0:2] = s[:, 0:2]
+            conv[:n, 3] = s[:, 2]
+            conv[:n, 2] = 1 - s[:, 2]
+            conv[n:, 4] = 1
+            conv[-1:, 4] = 1
+            out.append(conv)
+        return np.array(out)
+
+    def preprocess_on_device(self, sketches, device="cuda:0"):
+        """Token mode: the same preprocessing as `preprocess`, fused in one CUDA kernel (skf_tokenize_strokes);
+        returns int64 [B, max_seq_len] already in HBM."""
+        return self.tokenizer.encode_batch_device(sketches, self.hps["max_seq_len"], device, float(self.limit))
+
+    # ---- iteration (core/data.py:115-254) -----------------------------------------------------------
+    def get_sample(self, data, idx):
+        return [np.array(data["x"][idx]), np.expand_dims(data["y"][idx], axis=-1)]
+
+    def _collate(self, split, indices):
+        x = np.stack([split.current["x"][i] for i in indices])
+        y = np.stack([np.expand_dims(split.current["y"][i], -1) for i in indices]).astype(np.int64)
+        return [x, y]
+
+    def batch_iterator(self, split_name, batch_size, stop_at_end_of_split=False):
+        """core/data.py:115-172 (sample_iterator + batch_iterator): a batch continues across a chunk swap; when
+        the last file of the split is exhausted the running batch is cut short ('end_of_split')."""
+        split = self._ready(split_name)
+        status = "running"
+        while not stop_at_end_of_split or status != "end_of_split":
+            xs, ys, counter, status = [], [], 0, "running"
+            while status == "running":
+                counter += 1
+                status = "end_of_batch" if counter >= batch_size else "running"
+                if split.cursor >= split.current_len:
+                    end = self._swap(split_name)
+                    status = "end_of_split" if end else status
+                    split.cursor = 0
+                i = split.current_index_shuffle[split.cursor]
+                split.cursor += 1
+                xs.append(split.current["x"][i])
+                ys.append(np.expand_dims(split.current["y"][i], -1))
+            yield [np.stack(xs), np.stack(ys).astype(np.int64)]
+
+    def get_n_samples_from(self, split_name, n, shuffled=False, seeded=None, preprocess=False):
+        split = self._ready(split_name)
+        rng = np.random.default_rng(int(seeded)) if seeded is not None else self.rng
+        order = rng.permutation(split.current_len)[:n] if shuffled else list(range(min(n, split.current_len)))
+        return self._collate(split, [split.current_index_shuffle[i] for i in order])
+
+    def get_all_data_from(self, split_name):
+        split = self._ready(split_name)
+        return self.get_n_samples_from(split_name, split.current_len)
+
+
+dataloaders_by_name = {SyntheticStroke3DataLoader.name: SyntheticStroke3DataLoader,
+                       DistributedStroke3DataLoader.name: DistributedStroke3DataLoader}
 
 
 def get_dataloader_by_name(name):

@@ -313,17 +313,91 @@ class Transformer:
             out["attn_weights"] = None
         return out
 
+    # ---- training loop, reports, checkpoint cadence (core/models.py:163-223, 321-358) -----------------
+    def train(self, max_steps=None):
+        """core/models.py:163-197: total = batches_per_epoch * num_epochs steps from current_step; per step one
+        batch from dataset.batch_iterator('train', batch_size), train_on_batch, status report, checkpoint
+        cadence.  The slow-metric / Slack machinery of the reference is out of scope."""
+        total_steps = self.batches_per_epoch * self.hps["num_epochs"]
+        self.epoch = self.current_step // self.batches_per_epoch
+        it = self.dataset.batch_iterator("train", self.hps["batch_size"], stop_at_end_of_split=False)
+        todo = total_steps - self.current_step
+        if max_steps is not None:
+            todo = min(todo, max_steps)
+        self.quick_metrics_history = getattr(self, "quick_metrics_history", {k: [] for k in self.quick_metrics})
+        for _ in range(max(0, todo)):
+            # the reference increments current_step first (core/models.py:184); train_on_batch does it here
+            log_now = ((self.current_step + 1) % self.batches_per_epoch) % self.hps["log_every"] == 0
+            qm = self.train_on_batch(next(it), sync_metrics=True)
+            for k, v in qm.items():
+                self.quick_metrics_history.setdefault(k, []).append(v)
+            self.last_quick_metrics = qm
+            if log_now:
+                print(self.status_report())
+            self.save_checkpoint_if_its_time()
+            if self.current_step // self.batches_per_epoch > self.epoch:
+                self.epoch = self.current_step // self.batches_per_epoch
+                print(self.status_report())
+
+    def status_report(self, end_of_epoch=False):
+        """core/models.py:203-223 (log string only)."""
+        cur_iter = self.current_step % self.batches_per_epoch
+        s = "Epoch {} Batch {}/{}".format(getattr(self, "epoch", 0), cur_iter, self.batches_per_epoch)
+        for k, v in getattr(self, "last_quick_metrics", {}).items():
+            s = "{}|{}={:4.4f}".format(s, k, v)
+        return s
+
+    def save_checkpoint_if_its_time(self):
+        """core/models.py:346-358: rolling 'safety' checkpoints (the 2 newest are kept, like
+        CheckpointManager(max_to_keep=2)) every safety_save epochs and permanent ones every save_every."""
+        if getattr(self, "wgt_out_dir", None) is None:
+            return
+        cur = self.current_step
+        safety = max(1, int(self.hps["safety_save"] * self.batches_per_epoch))
+        every = max(1, int(self.hps["save_every"] * self.batches_per_epoch))
+        if (cur + 1) % safety == 0:
+            self.save_checkpoint(os.path.join(self.wgt_out_dir, "ckpt-{}.pt".format(cur)))
+            kept = sorted((f for f in os.listdir(self.wgt_out_dir) if f.startswith("ckpt-")),
+                          key=lambda f: int(f[5:-3]))
+            for f in kept[:-2]:
+                os.remove(os.path.join(self.wgt_out_dir, f))
+        if (cur + 1) % every == 0:
+            self.save_checkpoint(os.path.join(self.wgt_out_dir, "step{}.pt".format(cur)))
+
+    def save_checkpoint(self, path):
+        torch.save(self.state_dict(), path)
+        return path
+
+    def restore_checkpoint_if_exists(self, checkpoint):
+        """core/models.py:333-344: None -> nothing, 'latest' -> newest rolling checkpoint in weights/, else a path."""
+        if checkpoint is None:
+            return False
+        if checkpoint == "latest":
+            d = getattr(self, "wgt_out_dir", None)
+            cands = sorted((f for f in (os.listdir(d) if d else []) if f.endswith(".pt")),
+                           key=lambda f: os.path.getmtime(os.path.join(d, f)))
+            if not cands:
+                print("[Checkpoint] Not found")
+                return False
+            checkpoint = os.path.join(d, cands[-1])
+        self.load_state_dict(torch.load(checkpoint, map_location="cpu", weights_only=False))
+        print("[Checkpoint] Restored, step #{}".format(self.current_step))
+        return True
+
     # ---- checkpoints (own format: the flat arenas + step) ------------------------------------
     def state_dict(self):
         e = self._train_engine
         return {"params": e.params.cpu(), "adam_m": e.adam_m.cpu(), "adam_v": e.adam_v.cpu(),
-                "step": e.step_count(), "current_step": self.current_step, "table": dict(e.table)}
+                "step": e.step_count(), "current_step": self.current_step, "table": dict(e.table),
+                "metrics": e.tensor("stats_run", dtype=torch.float64).cpu().clone(), "hps": dict(self.hps)}
 
     def load_state_dict(self, sd):
         e = self._train_engine
         assert sd["table"] == e.table, "checkpoint was written for a different model layout"
         e.params.copy_(sd["params"]); e.adam_m.copy_(sd["adam_m"]); e.adam_v.copy_(sd["adam_v"])
         e.set_step(sd["step"])
+        if "metrics" in sd:
+            e.tensor("stats_run", dtype=torch.float64).copy_(sd["metrics"])
         self.current_step = sd["current_step"]
 
 

@@ -1,0 +1,76 @@
+"""Data-parallel host logic on CPU (gloo, world_size 2): the sharded loader hands every rank a disjoint slice
+of the same global batch, and summing per-rank gradients with the 1/world factor that the Adam kernel folds in
+(skf_adam_step grad_scale) reproduces the full-batch gradient of the oracle — the property the
+NCCL all-reduce of the flat gradient arena relies on.  No GPU: the per-rank gradients come from the oracle."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import sketchformer_oracle as O
+from oracle.make_golden import TINY
+from sketchformer_b200.data import get_dataloader_by_name
+
+WORLD = 2
+GLOBAL_B = 8
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    torch.set_num_threads(1)
+    try:
+        ocfg = O.OracleConfig(**TINY)
+        Loader = get_dataloader_by_name("stroke3-synthetic")
+        hps = Loader.parse_hparams(f"max_seq_len={ocfg.max_seq_len}")
+        ds = Loader(hps, None, n_classes=ocfg.n_classes, seed=99, rank=rank, world_size=WORLD, vocab=ocfg.vocab_size)
+        x, y = next(ds.batch_iterator("train", GLOBAL_B // WORLD))
+        # every rank sees the rows [rank*B, (rank+1)*B) of one global batch
+        xs = [torch.zeros(GLOBAL_B // WORLD, ocfg.max_seq_len, dtype=torch.int64) for _ in range(WORLD)]
+        dist.all_gather(xs, torch.from_numpy(x))
+        full = Loader(hps, None, n_classes=ocfg.n_classes, seed=99, rank=0, world_size=1, vocab=ocfg.vocab_size)
+        gx, gy = next(full.batch_iterator("train", GLOBAL_B))
+        assert np.array_equal(torch.cat(xs).numpy(), gx), "shards are not the slices of the global batch"
+        # replicated parameters, local gradients, all-reduce(sum) over a flat arena, 1/world in the optimizer
+        p = O.init_params(ocfg, 0, torch.float64)
+        _, grads = O.train_step({k: v.clone() for k, v in p.items()}, O.AdamTF(p, ocfg.d_model), torch.from_numpy(x),
+                                torch.from_numpy(y), ocfg, dtype=torch.float64)
+        names = sorted(grads)
+        arena = torch.cat([grads[k].reshape(-1) for k in names])
+        dist.all_reduce(arena)
+        arena /= WORLD
+        _, gfull = O.train_step({k: v.clone() for k, v in p.items()}, O.AdamTF(p, ocfg.d_model), torch.from_numpy(gx),
+                                torch.from_numpy(gy), ocfg, dtype=torch.float64)
+        want = torch.cat([gfull[k].reshape(-1) for k in names])
+        err = float((arena - want).norm() / want.norm())
+        assert err < 1e-12, err
+        if rank == 0:
+            out.put(("ok", err))
+    except Exception as e:      # noqa: BLE001
+        out.put(("fail", repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average_equals_full_batch():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, port, out)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    status, info = out.get(timeout=5)
+    assert status == "ok", info

@@ -149,3 +149,69 @@ def test_model_predict_api():
     # one sketch (1-D input) like the interpolation experiment does
     one = model.predict(x[0])
     assert one["recon"].shape[0] == 1
+
+
+def test_device_tokenizer_matches_host_preprocessing():
+    """skf_tokenize_strokes (clip, bbox normalise, nearest centre, SEP/SOS/EOS, cut, PAD in one kernel) against
+    the host restatement of DistributedStroke3DataLoader.preprocess + Tokenizer.encode: token ids bit-exact,
+    incl. empty-ish, single-point, overflowing and huge-offset sketches."""
+    from sketchformer_b200.tokenizer import Tokenizer, preprocess_sketch_host
+    rng = np.random.default_rng(5)
+    tok = Tokenizer(centroids=rng.uniform(-1, 1, size=(1000, 2)).astype(np.float32))
+    T = 200
+    sketches = []
+    for n in [1, 2, 3, 50, 120, 198, 199, 200, 260, 700] + list(rng.integers(5, 300, size=54)):
+        s = np.zeros((int(n), 3), np.float32)
+        s[:, :2] = rng.integers(-60, 60, size=(int(n), 2))
+        s[:, 2] = rng.random(int(n)) < 0.1
+        s[-1, 2] = 1
+        sketches.append(s)
+    sketches[3][5, 0] = 5000.0                     # clipped to +-1000 before the bounding box
+    sketches[4][:, :2] *= 0.001                    # bbox < 1: normalised by 1
+    got = tok.encode_batch_device(sketches, T).cpu().numpy()
+    want = np.stack([preprocess_sketch_host(s, tok, T) for s in sketches])
+    assert got.shape == want.shape == (len(sketches), T)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:5]
+
+
+def test_train_loop_checkpoint_resume(tmp_path):
+    """Transformer.train() cadence + restore (core/models.py:163-197, 333-358): 6 steps straight == 3 steps,
+    checkpoint, fresh model, restore 'latest', 3 more steps (weights, Adam state, step counter, metrics)."""
+    from sketchformer_b200.data import get_dataloader_by_name
+    from sketchformer_b200.model import get_model_by_name
+    Model, Loader = get_model_by_name("sketch-transformer-tf2"), get_dataloader_by_name("stroke3-synthetic")
+    spec = "num_layers=1,d_model=64,dff=128,num_heads=4,lowerdim=32,dropout_rate=0.1"
+
+    def make(out):
+        ds = Loader(Loader.parse_hparams("max_seq_len=24"), None, n_classes=10, n_samples=4 * 3, seed=3)
+        hps = Model.parse_hparams(base="batch_size=4,num_epochs=2,safety_save=1.0,save_every=1.0,log_every=1", specific=spec)
+        return Model(hps, ds, str(out), "r", seed=1)
+
+    a = make(tmp_path / "a")
+    assert a.batches_per_epoch == 3
+    a._train_engine.set_step(3000)              # a learning rate that moves the weights
+    a.train()                                   # 2 epochs x 3 batches
+    assert a.current_step == 6 and os.path.exists(a.config_filepath.replace("config.json", "weights"))
+    b = make(tmp_path / "b")
+    b._train_engine.set_step(3000)
+    b.train(max_steps=3)
+    files = sorted(os.listdir(b.wgt_out_dir))
+    assert "step2.pt" in files and "ckpt-2.pt" in files, files
+    c = make(tmp_path / "b")                    # same output dir: resumes from its weights/
+    # like the reference ((current_step + 1) % cadence == 0, core/models.py:346-353) the checkpoint of an epoch
+    # of 3 batches is written after batch 2
+    assert c.restore_checkpoint_if_exists("latest") and c.current_step == 2
+    c.dataset = b.dataset                       # keep drawing the same batch stream
+    it = b.dataset.batch_iterator("train", 4)
+    for _ in range(2):
+        next(it)                                # the checkpoint has seen 2 batches; c continues with batches 3..6
+    c.dataset.batch_iterator = lambda *args, **kw: it
+    c.train()
+    assert c.current_step == 6
+    pa, pc = a._train_engine.params.cpu(), c._train_engine.params.cpu()
+    # split-K weight gradients and the embedding scatter accumulate with atomics, so two runs agree to fp32
+    # rounding, not bit for bit; Adam turns a sign flip of a noise-level gradient into one +-lr step (lr ~ 1e-3)
+    assert float((pa - pc).norm() / pa.norm()) < 1e-3 and float((pa - pc).abs().max()) < 5e-3
+    assert a._train_engine.step_count() == c._train_engine.step_count() == 3006
+    ma, mc = a._train_engine.metrics(), c._train_engine.metrics()
+    assert all(abs(ma[k] - mc[k]) <= 1e-3 * max(abs(ma[k]), 1e-3) for k in ma), (ma, mc)

@@ -1,0 +1,132 @@
+"""Host tests of the loader side of the boundary: dictionary tokenizer (utils/tokenizer.py), the
+`stroke3-distributed` chunked-npz loader (dataloaders/distributed_stroke3.py + core/data.py) on a tiny
+dataset written here in the reference's on-disk format, and rank sharding."""
+import os
+
+import numpy as np
+import pytest
+
+from sketchformer_b200.data import get_dataloader_by_name
+from sketchformer_b200.tokenizer import Tokenizer, load_centroids, preprocess_sketch_host
+
+REF_PKL = "/root/reference/prep_data/sketch_token/token_dict.pkl"
+
+
+def _centroids(k=50, seed=0):
+    return np.random.default_rng(seed).uniform(-1, 1, size=(k, 2)).astype(np.float32)
+
+
+def _sketch(rng, n):
+    s = np.zeros((n, 3), np.float32)
+    s[:, :2] = rng.integers(-40, 40, size=(n, 2))
+    s[:, 2] = rng.random(n) < 0.15
+    s[-1, 2] = 1
+    return s
+
+
+def _write_dataset(d, n_chunks=3, per_chunk=40, seed=0):
+    rng = np.random.default_rng(seed)
+    def chunk(n):
+        x = np.empty(n, dtype=object)
+        for i in range(n):
+            x[i] = _sketch(rng, int(rng.integers(3, 60))).astype(np.int16)
+        return x, rng.integers(0, 7, size=n)
+    for c in range(n_chunks):
+        x, y = chunk(per_chunk)
+        np.savez(os.path.join(d, f"train_{c:03d}.npz"), x=x, y=y)
+    for name in ("valid", "test"):
+        x, y = chunk(25)
+        np.savez(os.path.join(d, f"{name}.npz"), x=x, y=y)
+    np.savez(os.path.join(d, "meta.npz"), n_classes=7, n_samples_train=n_chunks * per_chunk, n_samples_valid=25,
+             n_samples_test=25, class_names=np.array([f"c{i}" for i in range(7)]), std=1.0, mean=0.0)
+
+
+def test_tokenizer_known_answers():
+    """utils/tokenizer.py:35-64: ids shifted by one, SEP after pen lifts, SOS/EOS, padding / truncation fix-up."""
+    c = np.array([[0, 0], [1, 0], [0, 1], [-1, -1]], np.float32)
+    t = Tokenizer(centroids=c)
+    assert (t.PAD, t.SEP, t.SOS, t.EOS, t.VOCAB_SIZE) == (0, 5, 6, 7, 8)
+    s = np.array([[0.9, 0.1, 0], [0.1, 0.8, 1], [-0.7, -0.9, 0], [0.01, 0.02, 1]], np.float32)
+    assert t.encode(s).tolist() == [6, 2, 3, 5, 4, 1, 5, 7]
+    assert t.encode(s, seq_len=10).tolist() == [6, 2, 3, 5, 4, 1, 5, 7, 0, 0]
+    t6 = Tokenizer(centroids=c, max_seq_len=6)
+    assert t6.encode(s).tolist() == [6, 2, 3, 5, 5, 7]          # cut, last two forced to SEP, EOS
+    back = t.decode(t.encode(s))
+    assert back[:, 2].tolist() == [0, 1, 0, 1] and np.allclose(back[:, :2], c[[1, 2, 3, 0]])
+    # exact tie between centres 0 and 1 -> lowest index (sklearn argmin)
+    assert t.predict(np.array([[0.5, 0.0]], np.float32)).tolist() == [0]
+    assert t.decode([0, 0]).shape == (1, 3)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PKL), reason="reference dictionary not present on this box")
+def test_centroids_read_from_the_reference_pickle_without_unpickling():
+    c = load_centroids(REF_PKL)
+    assert c.shape == (1000, 2) and c.dtype == np.float32
+    raw = open(REF_PKL, "rb").read()
+    assert np.array_equal(c, np.frombuffer(raw[381:8381], "<f4").reshape(1000, 2))
+    t = Tokenizer(REF_PKL)
+    assert (t.SEP, t.SOS, t.EOS, t.VOCAB_SIZE) == (1001, 1002, 1003, 1004)
+
+
+def test_preprocess_matches_reference_steps():
+    """clip +-1000, normalise by max(bbox, 1) of the absolute path incl. the origin, tokenise, cut to T, PAD."""
+    t = Tokenizer(centroids=_centroids())
+    s = np.array([[2000, 0, 0], [-500, 300, 1], [10, 10, 0]], np.float32)
+    out = preprocess_sketch_host(s, t, 8)
+    # bbox: x path 1000 -> 500 -> 510 (with origin 0): width 1000; y path 0, 300, 310: height 310 -> max_dim 1000
+    want = t.encode(np.array([[1.0, 0, 0], [-0.5, 0.3, 1], [0.01, 0.01, 0]], np.float32))
+    assert out.tolist() == want.tolist() + [0] * (8 - len(want))
+    long = _sketch(np.random.default_rng(1), 30)
+    assert len(preprocess_sketch_host(long, t, 16)) == 16 and preprocess_sketch_host(long, t, 16)[0] == t.SOS
+
+
+def test_distributed_loader_iterates_chunks(tmp_path):
+    _write_dataset(str(tmp_path))
+    Loader = get_dataloader_by_name("stroke3-distributed")
+    hps = Loader.parse_hparams("max_seq_len=32")
+    ds = Loader(hps, str(tmp_path), seed=3, tokenizer=Tokenizer(centroids=_centroids()))
+    assert ds.n_classes == 7 and ds.n_samples == 120 and len(ds.class_names) == 7
+    it = ds.batch_iterator("train", 16, stop_at_end_of_split=False)
+    seen, short = 0, 0
+    for _ in range(14):                      # > one pass over the 3 chunks: swaps and wrap-around
+        x, y = next(it)
+        assert x.shape[1:] == (32,) and x.dtype == np.int64 and y.shape == (len(x), 1) and y.dtype == np.int64
+        assert (x[:, 0] == ds.tokenizer.SOS).all() and x.max() < ds.tokenizer.VOCAB_SIZE
+        short += len(x) < 16                 # like the reference, the batch that hits the end of the split is cut
+        seen += len(x)
+    assert seen > 120 and short <= 2
+    n = sum(len(x) for x, _ in ds.batch_iterator("valid", 10, stop_at_end_of_split=True))
+    assert n >= 25                           # the reference's iterator ends on the sample that wraps around
+    xa, ya = ds.get_all_data_from("test")
+    assert xa.shape == (25, 32) and ya.shape == (25, 1)
+    xs, _ = ds.get_n_samples_from("valid", 5, shuffled=True, seeded=14)
+    xs2, _ = ds.get_n_samples_from("valid", 5, shuffled=True, seeded=14)
+    assert np.array_equal(xs, xs2)
+
+
+def test_distributed_loader_continuous_rows(tmp_path):
+    _write_dataset(str(tmp_path), n_chunks=1)
+    Loader = get_dataloader_by_name("stroke3-distributed")
+    ds = Loader(Loader.parse_hparams("max_seq_len=24,use_continuous_data=True"), str(tmp_path), seed=1)
+    x, y = next(ds.batch_iterator("valid", 8))
+    assert x.shape == (8, 24, 5) and x.dtype == np.float32
+    assert np.allclose((x[..., 2] + x[..., 3] + x[..., 4])[:, :-1], 1.0)    # one-hot pen state ...
+    assert (x[:, -1, 4] == 1).all()                                          # ... the last row is always forced to pad
+    assert np.abs(x[..., :2]).max() <= 1.0 + 1e-6
+
+
+def test_distributed_loader_shards_by_rank(tmp_path):
+    _write_dataset(str(tmp_path), n_chunks=4, per_chunk=20)
+    Loader = get_dataloader_by_name("stroke3-distributed")
+    hps = Loader.parse_hparams("max_seq_len=16")
+    tok = Tokenizer(centroids=_centroids())
+    a = Loader(hps, str(tmp_path), rank=0, world_size=2, seed=5, tokenizer=tok)
+    b = Loader(hps, str(tmp_path), rank=1, world_size=2, seed=5, tokenizer=tok)
+    fa, fb = set(a.splits["train"].filepaths), set(b.splits["train"].filepaths)
+    assert len(fa) == 2 and len(fb) == 2 and not (fa & fb)            # chunk files dealt round-robin
+    _write_dataset(str(tmp_path / "one") if (tmp_path / "one").mkdir() is None else "", n_chunks=1, per_chunk=30)
+    a = Loader(hps, str(tmp_path / "one"), rank=0, world_size=2, seed=5, tokenizer=tok)
+    b = Loader(hps, str(tmp_path / "one"), rank=1, world_size=2, seed=5, tokenizer=tok)
+    a._ready("train"); b._ready("train")
+    ia, ib = set(a.splits["train"].current_index_shuffle), set(b.splits["train"].current_index_shuffle)
+    assert not (ia & ib) and len(ia | ib) == 30                        # one chunk: residue classes of one order
