@@ -35,20 +35,27 @@ int make_tmap_2d_typed(CUtensorMap* out, const float* ptr, uint64_t inner, uint6
                        uint32_t box_inner, uint32_t box_outer, bool mn_major, bool tf32_convert);
 
 constexpr int T3_BM = 128;                 // rows per CTA (256 per cluster)
-constexpr int T3_BN = 256;                 // columns per cluster tile
-constexpr int T3_BNH = 128;                // B columns staged per CTA
 constexpr int T3_BK = 32;
 constexpr int T3_A_BYTES = T3_BM * 128;    // 16 KB
-constexpr int T3_B_BYTES = T3_BNH * 128;   // 16 KB
-constexpr int T3_RAW = T3_A_BYTES + T3_B_BYTES;
-constexpr int T3_STAGE = 2 * T3_RAW;       // raw + lo tiles: 64 KB
-constexpr int T3_STAGES = 3;
 constexpr int T3_EPI_TILE = 32 * 128;
 constexpr int T3_EPI_BUFS = 2;
 constexpr int T3_EPI_BYTES = 4 * T3_EPI_BUFS * T3_EPI_TILE;   // 32 KB
-constexpr int T3_SMEM = T3_STAGES * T3_STAGE + T3_EPI_BYTES + 1024 + 256;
 constexpr int T3_THREADS = 320;
-constexpr int T3_TMEM_COLS = 512;          // two 256-column accumulators
+constexpr int T3_MAX_STAGES = 4;
+
+// BN = columns per cluster tile (256, or 128 for N <= 256: twice as many tiles for the 74 clusters and a
+// fourth pipeline stage); each CTA stages BN / 2 columns of B.
+template <int BN>
+struct Tc3Cfg {
+  static constexpr int BNH = BN / 2;
+  static constexpr int B_BYTES = BNH * 128;
+  static constexpr int RAW = T3_A_BYTES + B_BYTES;
+  static constexpr int STAGE = 2 * RAW;                 // raw + lo tiles: 64 KB / 48 KB
+  static constexpr int STAGES_RAW = (227 * 1024 - 2048 - T3_EPI_BYTES - 1024) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > T3_MAX_STAGES ? T3_MAX_STAGES : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE + T3_EPI_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN;              // two accumulators
+};
 
 struct Gemm3Params {
   int M, N, K;
@@ -71,15 +78,19 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Plain (release.cta) arrive on a barrier of another CTA of the cluster, as cutlass::arch::ClusterBarrier::arrive
+// does.  The data being published was written to THIS CTA's shared memory and made visible to the async proxy by
+// fence.proxy.async; a .release.cluster qualifier here costs a cluster-scope MEMBAR per arrive (measured: 37 % of
+// the splitter warps' time).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   for (uint32_t it = 0; it < (1u << 26); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -131,11 +142,13 @@ __device__ __forceinline__ void t3_bulk_wait_read() {
 }
 __device__ __forceinline__ float t3_trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-template <bool A_MN, bool B_MN>
+template <int T3_BN, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T3_THREADS, 1)
 gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
         const __grid_constant__ CUtensorMap tmY, const Gemm3Params p) {
-  constexpr int S = T3_STAGES;
+  using C = Tc3Cfg<T3_BN>;
+  constexpr int S = C::STAGES;
+  constexpr int T3_BNH = C::BNH, T3_RAW = C::RAW, T3_STAGE = C::STAGE, T3_TMEM_COLS = C::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;      // identical in both CTAs (same kernel, same layout)
@@ -409,11 +422,12 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 // ---- host side ---------------------------------------------------------------------------------
 static int g3_clusters = 0;
 
-template <bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t st) {
+  constexpr int T3_SMEM = Tc3Cfg<BN>::SMEM;
   static bool attr_done = false;
   if (!attr_done) {
-    SKF_CUDA(cudaFuncSetAttribute(gemm3_k<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
+    SKF_CUDA(cudaFuncSetAttribute(gemm3_k<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
     attr_done = true;
   }
   if (!g3_clusters) {
@@ -426,7 +440,7 @@ static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t 
     qc.blockDim = dim3(T3_THREADS);
     qc.dynamicSmemBytes = T3_SMEM;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, gemm3_k<A_MN, B_MN>, &qc) != cudaSuccess || nc <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&nc, gemm3_k<BN, A_MN, B_MN>, &qc) != cudaSuccess || nc <= 0) {
       cudaGetLastError();
       nc = sms / 2;
     }
@@ -434,17 +448,18 @@ static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t 
   }
   const int ntiles = p.mt * p.nt * p.splits;
   const int ncl = ntiles < g3_clusters ? ntiles : g3_clusters;
-  gemm3_k<A_MN, B_MN><<<2 * ncl, T3_THREADS, T3_SMEM, st>>>(tm[0], tm[1], tm[2], p);
+  gemm3_k<BN, A_MN, B_MN><<<2 * ncl, T3_THREADS, T3_SMEM, st>>>(tm[0], tm[1], tm[2], p);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
 
 int gemm_tc3_clusters() { return g3_clusters; }
 
-// The pair kernel is only built for the 256-column tile shape and needs at least one full 256-row cluster
-// tile.  Measured on B200 (tools/prof_ops.py, M = 25600): 4-7 % faster than the single-CTA kernel when the
-// weight matrix has >= 256 x 1024 elements (FFN, QKV), 7 % slower on the 256 x 256 projections.
-int gemm_tc3_wanted(int M, int N, int K) { return N > 128 && M > 128 && (long)N * K >= 256L * 768; }
+// The pair kernel needs more than one 128-row block and more than 64 columns; everything else stays on the
+// single-CTA kernel.  Measured on B200 (tools/prof_ops.py, M = 25600, 3xTF32): FFN-1 79 -> 61 us, FFN-2 dgrad
+// 76 -> 60 us, QKV wgrad 54 -> 44 us.
+int gemm_tc3_wanted(int M, int N, int K) { (void)K; return N > 64 && M > 128; }
+int gemm_tc3_bn(int N, int accumulate) { return (N <= 128 || (N <= 256 && !accumulate)) ? 128 : 256; }
 
 int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
              int64_t ldy, int M, int N, int K, const skf_gemm_epilogue* epi, cudaStream_t st) {
@@ -461,21 +476,28 @@ int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
   p.M = M; p.N = N; p.K = K;
   p.k_chunk = cdiv(cdiv(K, split), T3_BK) * T3_BK;
   p.splits = cdiv(K, p.k_chunk);
+  const int BN = gemm_tc3_bn(N, e.accumulate);
   p.mt = cdiv(M, 2 * T3_BM);
-  p.nt = cdiv(N, T3_BN);
+  p.nt = cdiv(N, BN);
   p.e = e;
   p.e.a_lo = p.e.b_lo = nullptr;
   CUtensorMap tm[3];
   // raw fp32 bits in shared memory (the splitter needs them): plain FLOAT32 maps
   if (!a_mn) SKF_TRY(make_tmap_2d_typed(&tm[0], A, (uint64_t)K, (uint64_t)M, (uint64_t)(M == 1 ? K : sa_m), T3_BK, T3_BM, false, false));
   else SKF_TRY(make_tmap_2d_typed(&tm[0], A, (uint64_t)M, (uint64_t)K, (uint64_t)sa_k, 32, T3_BK, true, false));
-  if (!b_mn) SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, T3_BK, (uint32_t)T3_BNH, false, false));
+  if (!b_mn) SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, T3_BK, (uint32_t)(BN / 2), false, false));
   else SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, T3_BK, true, false));
   SKF_TRY(make_tmap_2d_typed(&tm[2], Y, (uint64_t)N, (uint64_t)M, (uint64_t)ldy, 32, 32, false, false));
-  if (!a_mn && !b_mn) return launch_tc3<false, false>(tm, p, st);
-  if (!a_mn && b_mn) return launch_tc3<false, true>(tm, p, st);
-  if (a_mn && !b_mn) return launch_tc3<true, false>(tm, p, st);
-  return launch_tc3<true, true>(tm, p, st);
+  if (BN == 128) {
+    if (!a_mn && !b_mn) return launch_tc3<128, false, false>(tm, p, st);
+    if (!a_mn && b_mn) return launch_tc3<128, false, true>(tm, p, st);
+    if (a_mn && !b_mn) return launch_tc3<128, true, false>(tm, p, st);
+    return launch_tc3<128, true, true>(tm, p, st);
+  }
+  if (!a_mn && !b_mn) return launch_tc3<256, false, false>(tm, p, st);
+  if (!a_mn && b_mn) return launch_tc3<256, false, true>(tm, p, st);
+  if (a_mn && !b_mn) return launch_tc3<256, true, false>(tm, p, st);
+  return launch_tc3<256, true, true>(tm, p, st);
 }
 
 }  // namespace skf

@@ -412,7 +412,7 @@ def test_gemm_tcgen05_3xtf32(lib, name, a_mn, b_mn, M, N, K):
 
 
 PAIR_SHAPES = [(256, 256, 32), (512, 256, 64), (200, 1004, 96), (1600, 768, 256), (384, 512, 4000),
-               (3000, 1024, 256), (25472, 256, 1024)]
+               (3000, 1024, 256), (25472, 256, 1024), (300, 128, 160), (1000, 100, 256)]
 
 
 @pytest.mark.parametrize("name,a_mn,b_mn", MAJORS)
