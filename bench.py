@@ -132,7 +132,7 @@ def reference_main(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--backend", type=int, default=0, help="0 tcgen05 TF32 GEMMs, 1 SIMT fp32 (debug)")
@@ -168,7 +168,7 @@ def main():
                                     specific=f"num_layers={c['num_layers']},d_model={c['d_model']},dff={c['dff']},"
                                              f"num_heads={c['num_heads']},lowerdim={c['lowerdim']},dropout_rate=0.0")
     dataset = Loader(data_hps, None, n_classes=c["n_classes"], seed=1234 + 1000 * rank)
-    model = Model(model_hps, dataset, None, "bench", device=f"cuda:{local}", world_size=world, seed=0,
+    model = Model(model_hps, dataset, None, "bench", device=f"cuda:{local}", world_size=world, seed=0, rank=rank,
                   gemm_precision=None if args.precision < 0 else args.precision)
     eng = model._train_engine           # identical random-init weights on every rank (Keras initialisers, seed 0)
 
@@ -225,13 +225,14 @@ def main():
 
     # roofline of the dominant kernel (the persistent tcgen05 GEMM): CUDA events around launches of the FFN-1
     # shape through the C ABI, on this stream, after the timed region
-    roof = gemm_roofline(eng, c, peaks, peak_src, 2 if precision >= 1 else 0)
+    roof = gemm_roofline(eng, c, peaks, peak_src, 5 if precision >= 1 else 0)
     roof["step_core_tflops"] = value / world * core_flops_per_sketch() / 1e12
     roof["step_frac_of_tf32_peak"] = roof["step_core_tflops"] / (peaks["bf16_tflops_sustained"] / 2)
 
     if rank == 0:
         mode = {0: "tf32 single pass everywhere", 1: "3xTF32 forward, TF32 backward",
-                2: "3xTF32 (fp32-grade) forward and backward"}.get(precision, str(precision))
+                2: "3xTF32 (fp32-grade) forward and backward",
+                3: "3xTF32 forward and dgrad, TF32 weight gradients"}.get(precision, str(precision))
         line = {"metric": "sketches/sec", "value": value, "unit": "sketches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
@@ -255,10 +256,17 @@ def main():
         dist.destroy_process_group()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gemm3_k launch of this shape from the committed
+# `ncu --set full` capture (profiles/r1_ncu_full_gemm3_pair_ffn1.txt): 27.3 MB read + 45.3 MB written (part of the
+# 105 MB output is still in the 126 MB L2 when the kernel ends); algorithmic bytes are 132 MB.
+NCU_TRAFFIC_BYTES = {5: 72.6e6, 2: 72.2e6}
+
+
 def gemm_roofline(eng, c, peaks, peak_src, backend):
     """achieved TFLOP/s of the dominant kernel on its own stream (CUDA events), FFN-1 shape of cfg2:
     [B*T, d] x [d, dff] + bias + ReLU = 2*25600*256*1024 = 13.42 algorithmic GFLOP per launch.
-    backend 2 = 3xTF32 (three tensor-core passes per algorithmic FLOP), 0 = single-pass TF32."""
+    backend 5 = 3xTF32 on CTA pairs (gemm3_k, three tensor-core passes per algorithmic FLOP, what the plan
+    runs), 2 = the single-CTA 3xTF32 kernel, 0 = single-pass TF32."""
     import torch
     from sketchformer_b200.ops import gemm
     M, K, N = BATCH * c["max_seq_len"], c["d_model"], c["dff"]
@@ -280,10 +288,12 @@ def gemm_roofline(eng, c, peaks, peak_src, backend):
     flops = 2.0 * M * N * K
     achieved = flops / (us * 1e-6) / 1e12
     peak = peaks["bf16_tflops"] / 2
-    passes = 3 if backend == 2 else 1
-    return {"bound": "tensor", "kernel": f"gemm2_k<256,false,true,{'true' if backend == 2 else 'false'}> "
-                                         "(FFN-1: 25600x256x1024, bias+ReLU epilogue)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+    passes = 3 if backend in (2, 5) else 1
+    kname = {5: "gemm3_k<256,false,true> (cta_group::2 pair, 3xTF32)", 2: "gemm2_k<256,false,true,true> (3xTF32)",
+             0: "gemm2_k<256,false,true,false> (TF32)"}[backend]
+    return {"bound": "tensor", "kernel": kname + " FFN-1: 25600x256x1024, bias+ReLU epilogue",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": NCU_TRAFFIC_BYTES.get(backend),
             "us_per_launch": us, "flops_per_launch": flops, "mma_passes": passes,
             "tensor_pipe_tflops": achieved * passes, "tensor_pipe_frac": achieved * passes / peak,
             "peak_source": peak_src + "; TF32 = 1/2 of the bf16 burst figure",

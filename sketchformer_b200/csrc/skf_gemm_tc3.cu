@@ -1,12 +1,21 @@
 // 2-CTA (cta_group::2) variant of the persistent 3xTF32 tcgen05 GEMM in skf_gemm_tc2.cu.
 //
-// Why: in 3xTF32 mode the single-CTA kernel is SHARED-MEMORY-BANDWIDTH bound, not tensor bound.  Per 32-deep
-// k-block a CTA moves 48 KB of TMA writes + 96 KB of hi/lo splitter traffic + 12 MMAs x 12 KB of operand
-// reads = 288 KB through a 128 B/clk crossbar (2250 clk) while the 12 MMAs need only 1536 clk (measured: 62 %
-// of the TF32 peak).  A CTA pair shares the B operand: each CTA stages only HALF of the 256-column B tile
-// (its own 128 columns) and the pair's tensor cores exchange the halves, so per CTA the traffic drops to
-// 32 + 64 + 96 = 192 KB = 1500 clk < 1536 clk: tensor bound again.  The smaller stage (64 KB instead of
-// 96 KB) also buys a third pipeline stage.
+// A CTA pair shares the B operand: each CTA stages only HALF of the 256-column B tile (its own 128 columns)
+// and the pair's tensor cores exchange the halves, so per CTA and 32-deep k-block the shared-memory traffic
+// drops from 288 KB (48 TMA + 96 hi/lo splitter + 12 MMAs x 12 KB operand reads) to 192 KB and the L2 -> SM
+// traffic per FLOP by a third; the smaller stage (64 KB instead of 96 KB) buys a third pipeline stage.
+// Measured on B200 (FFN-1, 25600 x 256 x 1024, 3xTF32): 79.4 -> 61.4 us.  With the TMA loads and the splitter
+// disabled the same kernel takes 56 us: what remains is the tensor pipe itself at the power-limited clock
+// (~1.3 GHz under tensor load, the clock MEASURED_PEAKS.json's cuBLAS figure was taken at), i.e. the k-loop
+// runs at ~90 % of the pipe and the whole kernel at 79 % of the measured TF32 peak in MMA passes.
+//
+// Things tried here and dropped because they measured no better (round-1 notes, profiles/):
+//   * mbarrier.arrive.release.cluster for the cross-CTA "tiles ready" signal: a cluster-scope MEMBAR per
+//     arrive, 37 % of the splitter warps' samples (ncu) -> plain arrive, as CUTLASS's ClusterBarrier does;
+//   * decoupled raw / lo rings (4 x 32 KB of TMA in flight, 2 lo slots): 64 us (lo ring serialises the splitter);
+//   * A operand from tensor memory (tcgen05.mma TS form, 256 x 128 cluster tiles): correct, 70 us on FFN-1
+//     (more L2 traffic per FLOP), 1-3 % faster only for N = 256;
+//   * 8 splitter warps, TMA L2 prefetch of the next tile: no change.
 //
 //   cluster tile = 256 (M) x 256 (N); CTA r of the pair owns rows [128 r, 128 r + 128) of A and of the
 //   accumulator (its own TMEM) and stages columns [128 r, 128 r + 128) of B.
@@ -459,7 +468,9 @@ int gemm_tc3_clusters() { return g3_clusters; }
 // single-CTA kernel.  Measured on B200 (tools/prof_ops.py, M = 25600, 3xTF32): FFN-1 79 -> 61 us, FFN-2 dgrad
 // 76 -> 60 us, QKV wgrad 54 -> 44 us.
 int gemm_tc3_wanted(int M, int N, int K) { (void)K; return N > 64 && M > 128; }
-int gemm_tc3_bn(int N, int accumulate) { return (N <= 128 || (N <= 256 && !accumulate)) ? 128 : 256; }
+// 128-column cluster tiles only when the problem has no more than 128 columns: for N = 256 the 256-wide tile
+// (100 tiles on 74 clusters) measured 3 % faster than 2 x 128 (FFN-2 25600x1024x256: 69.6 vs 71.6 us).
+int gemm_tc3_bn(int N, int accumulate) { (void)accumulate; return N <= 128 ? 128 : 256; }
 
 int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
              int64_t ldy, int M, int N, int K, const skf_gemm_epilogue* epi, cudaStream_t st) {
