@@ -110,6 +110,34 @@ __device__ __forceinline__ void a2_mma_ts(uint32_t d, uint32_t a_tmem, uint32_t 
   }
 }
 
+// A [rows x 32 fp32] tile has the same 128-byte rows in both operand roles; only the intra-row swizzle differs
+// (pinned on B200 with tools/swz_probe.py): K-major tiles (CU_TENSOR_MAP_SWIZZLE_128B) keep logical 16-byte
+// chunk q of row r at chunk q ^ (r & 7), MN-major tiles (SWIZZLE_128B_ATOM_32B) at chunk q ^ ((r & 3) << 1).
+// Re-swizzling a tile in shared memory therefore replaces the second TMA load (and its ~2.5 us round trip)
+// the backward kernels used to issue for the MN-major copy of the same rows.
+__device__ __forceinline__ uint32_t a2_kchunk(int r, int q) { return (uint32_t)(q ^ (r & 7)) << 4; }
+__device__ __forceinline__ uint32_t a2_mnchunk(int r, int q) { return (uint32_t)(q ^ ((r & 3) << 1)) << 4; }
+
+// 64-row tile, 256 threads: thread t copies logical chunks 2g, 2g+1 (g = t >> 6) of row t & 63, raw and lo
+__device__ __forceinline__ void a2_kmajor_to_mnmajor_64(const uint8_t* src, const uint8_t* src_lo, uint8_t* dst,
+                                                        uint8_t* dst_lo, bool with_lo) {
+  const int r = threadIdx.x & 63, g = threadIdx.x >> 6;
+#pragma unroll
+  for (int q = 2 * g; q < 2 * g + 2; q++) {
+    const uint32_t so = r * 128 + a2_kchunk(r, q), dof = r * 128 + a2_mnchunk(r, q);
+    *reinterpret_cast<float4*>(dst + dof) = *reinterpret_cast<const float4*>(src + so);
+    if (with_lo) *reinterpret_cast<float4*>(dst_lo + dof) = *reinterpret_cast<const float4*>(src_lo + so);
+  }
+}
+// in place, one thread per row (all 8 chunks through registers); rows [0, 64) of one tile
+__device__ __forceinline__ void a2_row_kmajor_to_mnmajor_inplace(uint8_t* tile, int r) {
+  float4 c[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) c[q] = *reinterpret_cast<const float4*>(tile + r * 128 + a2_kchunk(r, q));
+#pragma unroll
+  for (int q = 0; q < 8; q++) *reinterpret_cast<float4*>(tile + r * 128 + a2_mnchunk(r, q)) = c[q];
+}
+
 struct A2Common {
   uint32_t base;   // 1024-aligned smem window
   uint8_t* gen;
@@ -419,13 +447,13 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    if (tid == 0) {                       // V and K (K-major) buffers are free
-      mbar_arrive_expect_tx(bar_x, A2_T64);
-      tma_load_2d(sX, &mKmn, bar_x, h * A2_DH, b * a.Tk + k0);
-      if (j + 1 < nblk) {
-        mbar_arrive_expect_tx(bar_k, A2_T64);
-        tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk + k0 + A2_BLK);
-      }
+    // the V block is dead: rebuild the key block (raw + lo) in its buffers with the MN-major swizzle for the
+    // dQ MMA, then hand the K-major buffers to the TMA for the next key block
+    a2_kmajor_to_mnmajor_64(gK, gK + A2_T64, gX, gX + A2_T64, X3);
+    __syncthreads();
+    if (tid == 0 && j + 1 < nblk) {
+      mbar_arrive_expect_tx(bar_k, A2_T64);
+      tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk + k0 + A2_BLK);
     }
     {
       uint32_t rs[32], rp[32];
@@ -446,8 +474,6 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
       tmem_st32(tdP + lane_off + wg * 32, rp);
     }
     tmem_st_wait();
-    mbar_wait(bar_x, ph);
-    if (X3) a2_split(gX, gX + A2_T64, A2_T64);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -557,10 +583,11 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    if (tid == 0) {                        // reload the same query block MN-major for the output MMAs
-      mbar_arrive_expect_tx(bar_b, 2 * A2_T64);
-      tma_load_2d(sA, &mQmn, bar_b, h * A2_DH, b * a.Tq + i0);
-      tma_load_2d(sB, &mdOmn, bar_b, h * A2_DH, b * a.Tq + i0);
+    // the score MMAs are done with the K-major Q / dO blocks: re-swizzle them in place (raw and lo tiles, one
+    // thread per 128-byte row) into the MN-major layout the output MMAs read
+    {
+      uint8_t* tile = gA + (tid >> 6) * A2_T64;      // gA, gA lo, gB, gB lo are contiguous 64-row tiles
+      if (X3 || ((tid >> 6) & 1) == 0) a2_row_kmajor_to_mnmajor_inplace(tile, tid & 63);
     }
     {
       uint32_t rs[32], rp[32];
@@ -583,11 +610,6 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
       tmem_st32(tdP + lane_off + wg * 32, rp);
     }
     tmem_st_wait();
-    mbar_wait(bar_b, ph);
-    if (X3) {
-      a2_split(gA, gA + A2_T64, A2_T64);
-      a2_split(gB, gB + A2_T64, A2_T64);
-    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -740,3 +762,31 @@ int attn2_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
 }
 
 }  // namespace skf
+
+// ---- debug: raw shared-memory image of one TMA box (used once to pin the 32B-atom swizzle pattern) --------
+namespace skf {
+__global__ void tma_dump_k(const __grid_constant__ CUtensorMap m, float* out, int bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t bar = base + bytes;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+    ptx::mbar_arrive_expect_tx(bar, bytes);
+    ptx::tma_load_2d(base, &m, bar, 0, 0);
+  }
+  __syncthreads();
+  ptx::mbar_wait(bar, 0);
+  for (int i = threadIdx.x; i < bytes / 4; i += blockDim.x) out[i] = reinterpret_cast<float*>(gen)[i];
+}
+}  // namespace skf
+extern "C" int skf_debug_tma_dump(const float* src, int rows, int mn, float* out, void* stream) {
+  CUtensorMap m;
+  SKF_TRY(skf::make_tmap_2d_typed(&m, src, 32, (uint64_t)rows, 32, 32, (uint32_t)rows, mn != 0, false));
+  const int bytes = rows * 128;
+  skf::tma_dump_k<<<1, 128, bytes + 1024 + 64, skf::as_stream(stream)>>>(m, out, bytes);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
