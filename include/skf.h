@@ -156,6 +156,9 @@ typedef struct skf_gemm_epilogue {
    * A*B ~= Ah*Bh + Ah*Bl + Al*Bh with Xl = X - tf32(X) from skf_split_lo(); same strides as A / B. */
   const float* a_lo;
   const float* b_lo;
+  /* Bias gradient fused into a weight-gradient product (pair backend 5, accumulate=1, B row-major [K, N]):
+   * colsum[n] += sum_k B[k, n], taken from the B tiles the CTAs stage anyway (row-block 0 only).          */
+  float* colsum;
 } skf_gemm_epilogue;
 /* lo[i] = x[i] - tf32(x[i])  (exact in fp32): the low half of the 3xTF32 operand split.     */
 int skf_split_lo(const float* x, float* lo, int64_t n, void* stream);

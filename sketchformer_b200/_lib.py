@@ -28,7 +28,7 @@ class SkfParamEntry(C.Structure):
 class SkfGemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("resid", C.c_void_p), ("ld_resid", C.c_int64), ("mask", C.c_void_p),
                 ("ld_mask", C.c_int64), ("act", C.c_int32), ("accumulate", C.c_int32), ("round_tf32", C.c_int32),
-                ("split_k", C.c_int32), ("a_lo", C.c_void_p), ("b_lo", C.c_void_p)]
+                ("split_k", C.c_int32), ("a_lo", C.c_void_p), ("b_lo", C.c_void_p), ("colsum", C.c_void_p)]
 
 
 P, I, L, F, SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t

@@ -173,7 +173,14 @@ __device__ __forceinline__ void a2_free(const A2Common& c) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// forward.  smem: Q | Ql | K | Kl | V | Vl | pad[256] | barriers     tmem: S/P [0,64)  O [64,96)
+// forward.  smem: Q | Ql | K | Kl | V | Vl | bias[256] | barriers     tmem: S/P [0,64)  O [64,96)
+//
+// Measured phase times of one CTA at cfg2 (clock64 stamps, 3 CTAs/SM, cycles per 64-key iteration of ~5400):
+// K split + sync 460, S MMAs (12 x 128x64x8) 1000, softmax + P store + O rescale 1900, V split + sync 470,
+// P V MMAs (16 x 128x32x8) 1300; prologue 2600, epilogue 1500.  Dependent small MMAs cost ~80 clk each whatever
+// their N (feeding [Vh | Vl] as ONE N=64 operand cut the P V phase to 850 clk but not the kernel time), so the
+// kernel is bound by the serial phase chain of each CTA, not by a pipe: the next step is a warp-specialised
+// two-tile ping-pong (softmax of one query tile under the MMAs of the other), not more tuning of this structure.
 // ---------------------------------------------------------------------------------------------------
 constexpr int A2F_DATA = 2 * A2_T128 + 4 * A2_T64 + A2_MAXT * 4;
 constexpr float A2_LOG2E = 1.4426950408889634f;

@@ -62,7 +62,7 @@ struct Tc3Cfg {
   static constexpr int STAGE = 2 * RAW;                 // raw + lo tiles: 64 KB / 48 KB
   static constexpr int STAGES_RAW = (227 * 1024 - 2048 - T3_EPI_BYTES - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > T3_MAX_STAGES ? T3_MAX_STAGES : STAGES_RAW;
-  static constexpr int SMEM = STAGES * STAGE + T3_EPI_BYTES + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE + T3_EPI_BYTES + 1024 + 256 + 512 /* column sums */;
   static constexpr int TMEM_COLS = 2 * BN;              // two accumulators
 };
 
@@ -395,9 +395,20 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     uint32_t xfull_leader[S];
 #pragma unroll
     for (int s = 0; s < S; s++) xfull_leader[s] = map_to_cta(xfull_bar(s), 0);
+    // Fused bias gradient (weight-gradient products, B = dY row-major => MN-major tiles): the splitter reads every
+    // element of the B tile anyway.  Thread `tid` always meets the same four columns of each 32-column box (chunk
+    // tid + 128 i' of the B region is row tid/8 + 16 (i' & 1), box i' / 2, logical 16-byte chunk
+    // q = (tid & 7) ^ (((tid >> 3) & 3) << 1) under the 32B-atom swizzle), so it keeps one float4 per box.
+    constexpr int NBOX = T3_BNH / 32;
+    float4 csum[NBOX];
+#pragma unroll
+    for (int j = 0; j < NBOX; j++) csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* colsum_s = reinterpret_cast<float*>(gen + S * T3_STAGE + T3_EPI_BYTES + 256);
+    const int cq = (tid & 7) ^ (((tid >> 3) & 3) << 1);
     for (int t = cluster_id; t < ntiles; t += nclusters) {
       int m0, n0, kb, nkb;
       tile_coords(t, m0, n0, kb, nkb);
+      const bool do_colsum = B_MN && p.e.colsum != nullptr && m0 == (int)rank * T3_BM;   // row-block 0 only
       for (int i = 0; i < nkb; i++, it++) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1u;
@@ -405,12 +416,24 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         const float4* src = reinterpret_cast<const float4*>(gen + s * T3_STAGE);
         float4* dst = reinterpret_cast<float4*>(gen + s * T3_STAGE + T3_RAW);
 #pragma unroll kSplitUnroll3
-        for (int k = tid; k < T3_RAW / 16; k += 128) {
+        for (int k = tid; k < T3_A_BYTES / 16; k += 128) {
           const float4 x = src[k];
           float4 l;
           l.x = x.x - t3_trunc_tf32(x.x); l.y = x.y - t3_trunc_tf32(x.y);
           l.z = x.z - t3_trunc_tf32(x.z); l.w = x.w - t3_trunc_tf32(x.w);
           dst[k] = l;
+        }
+#pragma unroll
+        for (int ib = 0; ib < 2 * NBOX; ib++) {
+          const int k = T3_A_BYTES / 16 + tid + 128 * ib;
+          const float4 x = src[k];
+          float4 l;
+          l.x = x.x - t3_trunc_tf32(x.x); l.y = x.y - t3_trunc_tf32(x.y);
+          l.z = x.z - t3_trunc_tf32(x.z); l.w = x.w - t3_trunc_tf32(x.w);
+          dst[k] = l;
+          if (B_MN && do_colsum) {
+            csum[ib >> 1].x += x.x; csum[ib >> 1].y += x.y; csum[ib >> 1].z += x.z; csum[ib >> 1].w += x.w;
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -420,6 +443,20 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           for (int ss = 1; ss < S; ss++) target = (s == ss) ? xfull_leader[ss] : target;
           mbar_arrive_cluster(target);
         }
+      }
+      if (B_MN && do_colsum) {
+        // 16 threads share each column: reduce in shared memory, then one global atomic per column and CTA
+        if (tid < T3_BNH) colsum_s[tid] = 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < NBOX; j++) {
+          float* cs = colsum_s + j * 32 + cq * 4;
+          atomicAdd(cs, csum[j].x); atomicAdd(cs + 1, csum[j].y); atomicAdd(cs + 2, csum[j].z); atomicAdd(cs + 3, csum[j].w);
+          csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int col = n0 + (int)rank * T3_BNH + tid;
+        if (tid < T3_BNH && col < p.N) atomicAdd(p.e.colsum + col, colsum_s[tid]);
       }
     }
   }
@@ -490,6 +527,8 @@ int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
   const int BN = gemm_tc3_bn(N, e.accumulate);
   p.mt = cdiv(M, 2 * T3_BM);
   p.nt = cdiv(N, BN);
+  SKF_REQUIRE(!e.colsum || (e.accumulate && b_mn), SKF_ERR_BAD_ARG,
+              "gemm: the fused column sum needs accumulate=1 and a row-major [K, N] B operand");
   p.e = e;
   p.e.a_lo = p.e.b_lo = nullptr;
   CUtensorMap tm[3];

@@ -430,8 +430,13 @@ struct Gemm {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
     e.accumulate = 1;
-    SKF_TRY(run(X, 1, K, dY, N, 1, dW, N, K, N, M, e, P->c.gemm_precision == 2));
-    if (db) SKF_TRY(skf_colsum(dY, N, db, M, N, st));
+    const bool x3 = P->c.gemm_precision == 2;
+    // the pair kernel sums the columns of dY (bias gradient) from the tiles it stages anyway
+    const bool fused = db && x3 && P->c.gemm_backend == 0 && g_gemm_pair && gemm_tc3_wanted(K, N, M) &&
+                       gemm_tc2_supported(X, 1, K, dY, N, 1, dW, N, K, N, M, &e);
+    if (fused) e.colsum = db;
+    SKF_TRY(run(X, 1, K, dY, N, 1, dW, N, K, N, M, e, x3));
+    if (db && !fused) SKF_TRY(skf_colsum(dY, N, db, M, N, st));
     return SKF_OK;
   }
 };
@@ -1153,6 +1158,8 @@ int64_t skf_plan_launches(const skf_plan* P) { return P ? P->launches : 0; }
 // ---- thin operator wrappers -------------------------------------------------------------------
 int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
              int64_t ldy, int M, int N, int K, const skf_gemm_epilogue* epi, int backend, void* stream) {
+  SKF_REQUIRE(!(epi && epi->colsum) || backend == 5, SKF_ERR_UNSUPPORTED,
+              "gemm: the fused column sum exists on the pair backend (5) only");
   if (backend == 0 || backend == 2)      // persistent tcgen05 kernel: single-pass TF32 / 3xTF32
     return gemm_tc2(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, backend == 2, as_stream(stream));
   if (backend == 3)                      // first-generation (one tile per CTA) tcgen05 kernel, kept for A/B runs

@@ -16,12 +16,12 @@ def stream():
 
 
 def gemm(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, backend=0, bias=None, resid=None, mask=None, act=0,
-         accumulate=0, round_tf32=0, split_k=0, a_lo=None, b_lo=None):
+         accumulate=0, round_tf32=0, split_k=0, a_lo=None, b_lo=None, colsum=None):
     """Y[M,N] = epilogue(op(A) op(B)); see skf_gemm in include/skf.h (Dense fwd / dgrad / wgrad)."""
     lib = _lib.load()
     e = SkfGemmEpilogue(bias=ptr(bias), resid=ptr(resid), ld_resid=(resid.stride(0) if resid is not None else 0),
                         mask=ptr(mask), ld_mask=(mask.stride(0) if mask is not None else 0), act=act,
-                        accumulate=accumulate, round_tf32=round_tf32, split_k=split_k, a_lo=ptr(a_lo), b_lo=ptr(b_lo))
+                        accumulate=accumulate, round_tf32=round_tf32, split_k=split_k, a_lo=ptr(a_lo), b_lo=ptr(b_lo), colsum=ptr(colsum))
     _lib.check(lib.skf_gemm(ptr(A), sa_m, sa_k, ptr(B), sb_k, sb_n, ptr(Y), ldy, M, N, K, C.byref(e), backend,
                             stream()), "skf_gemm")
 

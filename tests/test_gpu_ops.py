@@ -428,6 +428,22 @@ def test_gemm_tcgen05_pair_3xtf32(lib, name, a_mn, b_mn, M, N, K):
     assert _gemm_case(M, N, K, a_mn, b_mn, 5, 20, split_k=3) < TOL_X3
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 3000), (256, 1024, 25472), (512, 768, 1000), (300, 200, 517)])
+def test_gemm_pair_fused_bias_gradient(lib, M, N, K):
+    """weight-gradient product dW[M,N] += X^T dY with the bias gradient colsum(dY) fused into the same launch
+    (summed by the splitter warps from the B tiles of row-block 0, every split-K slice, ragged N and K)."""
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(K, M, generator=g)           # stored [K, M]: A = X^T is MN-major
+    dY = torch.randn(K, N, generator=g)
+    Xd, dYd = dev(X), dev(dY)
+    dW = torch.zeros(M, N, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    gemm(Xd, 1, M, dYd, N, 1, dW, N, M, N, K, 5, accumulate=1, split_k=7, colsum=db)
+    torch.cuda.synchronize()
+    assert rel_err(dW, X.double().T @ dY.double()) < TOL_X3
+    assert rel_err(db, dY.double().sum(0)) < 1e-5
+
+
 def test_gemm_tcgen05_3xtf32_beats_single_pass(lib):
     g = torch.Generator().manual_seed(13)
     for (M, N, K) in ((512, 256, 256), (300, 1024, 256), (256, 512, 1000)):
