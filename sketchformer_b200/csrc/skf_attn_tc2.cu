@@ -138,6 +138,20 @@ __device__ __forceinline__ void a2_row_kmajor_to_mnmajor_inplace(uint8_t* tile, 
   for (int q = 0; q < 8; q++) *reinterpret_cast<float4*>(tile + r * 128 + a2_mnchunk(r, q)) = c[q];
 }
 
+// D[128 x 64] (+)= A[tmem, 64 columns] * [Bh | Bl]: the raw tile and its lo tile (A2_T64 bytes apart in shared
+// memory) are read by ONE MMA as the two 32-wide N-chunks of an MN-major operand, so columns [0,32) of D
+// accumulate A*Bh and [32,64) A*Bl (summed by the reader).  Dependent 128x32x8 MMAs cost ~80-100 clk each whatever
+// their N (clock64 stamps: 16 of them 1300-1800 clk, 8 of N=64 850 clk), so half as many wider ones are cheaper.
+__device__ __forceinline__ void a2_mma_ts_cat(uint32_t d, uint32_t a_tmem, uint32_t bh, uint32_t idesc64,
+                                              uint32_t accumulate) {
+  uint32_t acc = accumulate;
+#pragma unroll
+  for (int k = 0; k < A2_BLK / 8; k++) {
+    mma_tf32_ts(d, a_tmem + k * 8, make_desc_mnmajor(bh + k * 1024, A2_T64), idesc64, acc);
+    acc = 1;
+  }
+}
+
 struct A2Common {
   uint32_t base;   // 1024-aligned smem window
   uint8_t* gen;
@@ -369,14 +383,18 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
 // ---------------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------------
 // backward, dQ.  smem: Q | Ql | dO | dOl | K | Kl | X | Xl | bias[256] | barriers   (X = V block, then the
-// MN-major copy of the K block).   tmem: S [0,64)  dP -> dS [64,128)  dQ [128,160)
+// MN-major copy of the K block).   tmem: S [0,64)  dP -> dS [64,128)  dQ [128,192) = dS*Kh | dS*Kl
+// Measured phases of one CTA before the two changes below (clock64, cycles): prologue 8500 (of which the
+// per-row global loads of O and dO for delta ~6000), per 64-key block S,dP MMAs 2200, re-swizzle 400-900,
+// row math 1400-2100, dQ MMAs (16 x N=32) 1200-1800, splits 500; epilogue 2200.  Now the O tile comes in by
+// TMA into the (not yet used) Q-lo buffer and delta is taken from shared memory, and dQ uses 8 N=64 MMAs.
 // ---------------------------------------------------------------------------------------------------
 constexpr int A2Q_DATA = 4 * A2_T128 + 4 * A2_T64 + A2_MAXT * 4;
 template <bool X3>
 __global__ void __launch_bounds__(256, 2)
 attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mdO,
                const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
-               const __grid_constant__ CUtensorMap mKmn, const Attn2Args a) {
+               const __grid_constant__ CUtensorMap mO, const Attn2Args a) {
   extern __shared__ uint8_t smem_raw[];
   A2Common c;
   a2_prologue<256>(c, smem_raw, A2Q_DATA);
@@ -398,6 +416,8 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
     mbar_arrive_expect_tx(bar_q, 2 * A2_T128);
     tma_load_2d(sQ, &mQ, bar_q, h * A2_DH, b * a.Tq + q0);
     tma_load_2d(sdO, &mdO, bar_q, h * A2_DH, b * a.Tq + q0);
+    mbar_arrive_expect_tx(bar_x, A2_T128);                      // O tile, parked in the Q-lo buffer
+    tma_load_2d(sQl, &mO, bar_x, h * A2_DH, b * a.Tq + q0);
     mbar_arrive_expect_tx(bar_k, A2_T64);
     tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk);
     mbar_arrive_expect_tx(bar_v, A2_T64);
@@ -409,21 +429,25 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
     else if (a.mode >= 1 && a.key_pad && a.key_pad[(int64_t)b * a.Tk + i]) bj = A2_MASK_NEG * A2_LOG2E;
     bias_s[i] = bj;
   }
-  // delta_i = sum_c dO[i,c] O[i,c]  (row per thread, 128 B each from global)
   const int qi = q0 + row;
   float delta = 0.f, lse2 = INFINITY;       // rows past the sequence: p = exp2(-inf) = 0
-  if (qi < a.Tq) {
-    const float4* o4 = reinterpret_cast<const float4*>(a.O + ((int64_t)b * a.Tq + qi) * a.ldO + h * A2_DH);
-    const float4* g4 = reinterpret_cast<const float4*>(a.dO + ((int64_t)b * a.Tq + qi) * a.lddO + h * A2_DH);
+  if (qi < a.Tq) lse2 = a.lse[((int64_t)b * a.H + h) * a.Tq + qi] * A2_LOG2E;
+  mbar_wait(bar_q, 0);
+  mbar_wait(bar_x, 0);
+  {
+    // delta_i = sum_c dO[i,c] O[i,c] from the two K-major tiles in shared memory (row per thread; rows past
+    // the sequence are TMA zero-fill)
+    const uint8_t* orow = gQ + A2_T128 + row * 128;
+    const uint8_t* grow = gdO + row * 128;
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      const float4 o = o4[jj], g = g4[jj];
+    for (int q = 0; q < 8; q++) {
+      const float4 o = *reinterpret_cast<const float4*>(orow + a2_kchunk(row, q));
+      const float4 g = *reinterpret_cast<const float4*>(grow + a2_kchunk(row, q));
       delta += (o.x * g.x + o.y * g.y) + (o.z * g.z + o.w * g.w);
     }
-    lse2 = a.lse[((int64_t)b * a.H + h) * a.Tq + qi] * A2_LOG2E;
-    if (wg == 0) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = delta;
+    if (wg == 0 && qi < a.Tq) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = delta;
   }
-  mbar_wait(bar_q, 0);
+  __syncthreads();                          // every thread has read the O tile: the Q-lo buffer may be overwritten
   if (X3) {
     a2_split(gQ, gQ + A2_T128, A2_T128);
     a2_split(gdO, gdO + A2_T128, A2_T128);
@@ -431,7 +455,7 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
   const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdQ = c.tmem + 128;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
-  const uint32_t idesc_o = make_idesc_tf32(128, A2_DH, 0, 1);
+  const uint32_t idesc_o = make_idesc_tf32(128, X3 ? 2 * A2_DH : A2_DH, 0, 1);
   const float c1 = a.scale * A2_LOG2E;
   const int qw = q0 + (warp & 3) * 32;      // first query row of this warp
 
@@ -486,7 +510,8 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      a2_mma_ts<X3>(tdQ, tdP, sX, sXl, idesc_o, j > 0 ? 1u : 0u);
+      if (X3) a2_mma_ts_cat(tdQ, tdP, sX, idesc_o, j > 0 ? 1u : 0u);
+      else a2_mma_ts<false>(tdQ, tdP, sX, sXl, idesc_o, j > 0 ? 1u : 0u);
       tc_commit(bar_o);
     }
     mbar_wait(bar_o, ph);
@@ -500,6 +525,13 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
     uint32_t r[32];
     __syncwarp();
     tmem_ld32(tdQ + lane_off, r);
+    if (X3) {
+      uint32_t rl[32];
+      tmem_ld32(tdQ + lane_off + 32, rl);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) r[jj] = __float_as_uint(__uint_as_float(r[jj]) + __uint_as_float(rl[jj]));
+    }
     tmem_ld_wait();
     if (qi < a.Tq) {
       float4* dst = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tq + qi) * a.ld0 + h * A2_DH);
@@ -515,7 +547,7 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------------
 // backward, dK / dV.  smem: K | Kl | V | Vl | A | Al | B | Bl | lse2[256] | delta[256] | barriers
 //   (A, B = Q block, dO block K-major for the score MMAs, then their MN-major copies for the output MMAs)
-// tmem: S^T -> P^T [0,64)  dP^T -> dS^T [64,128)  dV [128,160)  dK [160,192)
+// tmem: S^T -> P^T [0,64)  dP^T -> dS^T [64,128)  dV [128,192) = P^T dOh | P^T dOl   dK [192,256) likewise
 // ---------------------------------------------------------------------------------------------------
 constexpr int A2K_DATA = 4 * A2_T128 + 4 * A2_T64 + 2 * A2_MAXT * 4;
 template <bool X3>
@@ -564,10 +596,10 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
     a2_split(gK, gK + A2_T128, A2_T128);
     a2_split(gV, gV + A2_T128, A2_T128);
   }
-  const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdV = c.tmem + 128, tdK = c.tmem + 160;
+  const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdV = c.tmem + 128, tdK = c.tmem + 192;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
-  const uint32_t idesc_o = make_idesc_tf32(128, A2_DH, 0, 1);
+  const uint32_t idesc_o = make_idesc_tf32(128, X3 ? 2 * A2_DH : A2_DH, 0, 1);
   const float c1 = a.scale * A2_LOG2E;
   const int kw = j0 + (warp & 3) * 32;               // first key of this warp
 
@@ -622,8 +654,13 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      a2_mma_ts<X3>(tdV, tS, sB, sBl, idesc_o, it > 0 ? 1u : 0u);     // dV += P^T dO
-      a2_mma_ts<X3>(tdK, tdP, sA, sAl, idesc_o, it > 0 ? 1u : 0u);    // dK += dS^T Q
+      if (X3) {
+        a2_mma_ts_cat(tdV, tS, sB, idesc_o, it > 0 ? 1u : 0u);          // dV += P^T [dOh | dOl]
+        a2_mma_ts_cat(tdK, tdP, sA, idesc_o, it > 0 ? 1u : 0u);         // dK += dS^T [Qh | Ql]
+      } else {
+        a2_mma_ts<false>(tdV, tS, sB, sBl, idesc_o, it > 0 ? 1u : 0u);
+        a2_mma_ts<false>(tdK, tdP, sA, sAl, idesc_o, it > 0 ? 1u : 0u);
+      }
       tc_commit(bar_o);
     }
     mbar_wait(bar_o, ph);
@@ -640,6 +677,13 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
     __syncwarp();
     if (it > 0) {
       tmem_ld32((wg == 0 ? tdK : tdV) + lane_off, r);
+      if (X3) {
+        uint32_t rl[32];
+        tmem_ld32((wg == 0 ? tdK : tdV) + lane_off + 32, rl);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) r[jj] = __float_as_uint(__uint_as_float(r[jj]) + __uint_as_float(rl[jj]));
+      }
       tmem_ld_wait();
     } else {
 #pragma unroll
@@ -719,7 +763,8 @@ int attn2_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
                     reinterpret_cast<uintptr_t>(dV) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
               SKF_ERR_BAD_ALIGN, "attn2_bwd: alignment");
   const bool conv = !x3;
-  CUtensorMap mQ128, mdO128, mK64, mV64, mK64mn, mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn;
+  CUtensorMap mQ128, mdO128, mO128, mK64, mV64, mK64mn, mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn;
+  SKF_TRY(a2_map(&mO128, O, ldo, H, (int64_t)B * Tq, 128, false, false));
   SKF_TRY(a2_map(&mQ128, Q, ldq, H, (int64_t)B * Tq, 128, false, conv));
   SKF_TRY(a2_map(&mdO128, dO, lddo, H, (int64_t)B * Tq, 128, false, conv));
   SKF_TRY(a2_map(&mK64, K, ldk, H, (int64_t)B * Tk, A2_BLK, false, conv));
@@ -742,11 +787,11 @@ int attn2_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
     if (x3) {
       static bool done = false;
       if (!done) { SKF_TRY(a2_attr(attn2_bwd_dq_k<true>, smem)); done = true; }
-      attn2_bwd_dq_k<true><<<grid, 256, smem, st>>>(mQ128, mdO128, mK64, mV64, mK64mn, a);
+      attn2_bwd_dq_k<true><<<grid, 256, smem, st>>>(mQ128, mdO128, mK64, mV64, mO128, a);
     } else {
       static bool done = false;
       if (!done) { SKF_TRY(a2_attr(attn2_bwd_dq_k<false>, smem)); done = true; }
-      attn2_bwd_dq_k<false><<<grid, 256, smem, st>>>(mQ128, mdO128, mK64, mV64, mK64mn, a);
+      attn2_bwd_dq_k<false><<<grid, 256, smem, st>>>(mQ128, mdO128, mK64, mV64, mO128, a);
     }
     SKF_LAUNCH_CHECK();
   }
