@@ -494,12 +494,19 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
       tmem_ld32(tdP + lane_off + wg * 32, rp);
       tmem_ld_wait();
       const bool diag = a.mode == 2 && kc + 31 > qw;      // warp-uniform: some (q, k) pair has k > q
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s + kc);
 #pragma unroll
-      for (int jj = 0; jj < 32; jj++) {
-        float t = fmaf(__uint_as_float(rs[jj]), c1, bias_s[kc + jj]);
-        if (diag && kc + jj > qi) t += A2_MASK_NEG * A2_LOG2E;
-        const float p = exp2f(t - lse2);
-        rp[jj] = __float_as_uint(round_tf32(p * (__uint_as_float(rp[jj]) - delta)));
+      for (int j4 = 0; j4 < 8; j4++) {
+        const float4 bv = b4[j4];
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int jj = 4 * j4 + e;
+          float t = fmaf(__uint_as_float(rs[jj]), c1, bb[e] - lse2);
+          if (diag && kc + jj > qi) t += A2_MASK_NEG * A2_LOG2E;
+          const float p = a2_ex2(t);
+          rp[jj] = __float_as_uint(round_tf32(p * (__uint_as_float(rp[jj]) - delta)));
+        }
       }
       __syncwarp();
       tmem_st32(tdP + lane_off + wg * 32, rp);
@@ -636,13 +643,21 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
       tmem_ld32(tdP + lane_off + wg * 32, rp);
       tmem_ld_wait();
       const bool diag = a.mode == 2 && kw + 31 > qc;      // warp-uniform: some (q, k) pair has k > q
+      const float4* l4 = reinterpret_cast<const float4*>(lse_s + qc);
+      const float4* d4 = reinterpret_cast<const float4*>(del_s + qc);
 #pragma unroll
-      for (int jj = 0; jj < 32; jj++) {
-        float t = fmaf(__uint_as_float(rs[jj]), c1, bias);
-        if (diag && kj > qc + jj) t += A2_MASK_NEG * A2_LOG2E;
-        const float p = exp2f(t - lse_s[qc + jj]);
-        rs[jj] = __float_as_uint(round_tf32(p));
-        rp[jj] = __float_as_uint(round_tf32(p * (__uint_as_float(rp[jj]) - del_s[qc + jj])));
+      for (int j4 = 0; j4 < 8; j4++) {
+        const float4 lv = l4[j4], dv = d4[j4];
+        const float ll[4] = {lv.x, lv.y, lv.z, lv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int jj = 4 * j4 + e;
+          float t = fmaf(__uint_as_float(rs[jj]), c1, bias - ll[e]);
+          if (diag && kj > qc + jj) t += A2_MASK_NEG * A2_LOG2E;
+          const float p = a2_ex2(t);
+          rs[jj] = __float_as_uint(round_tf32(p));
+          rp[jj] = __float_as_uint(round_tf32(p * (__uint_as_float(rp[jj]) - dd[e])));
+        }
       }
       __syncwarp();
       tmem_st32(tS + lane_off + wg * 32, rs);
