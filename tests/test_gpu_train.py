@@ -390,3 +390,32 @@ def test_no_bottleneck_matches_oracle(backend):
     got_tok = eng.decode(None, None, ocfg.vocab_size - 2, ocfg.vocab_size - 1).cpu().numpy()
     from tests.test_gpu_decode import _assert_same_tokens
     _assert_same_tokens(p, ocfg, want["embedding"], got_tok, want["recon"].numpy())
+
+
+def test_cfg5_dimensions_match_oracle():
+    """BASELINE.json configs[4] dimensions (d_model=512, dff=2048, 8 heads of 64, max_seq_len=512) at 2 layers and
+    batch 2 so that the fp64 oracle finishes in seconds: head dim 64 and T > 256 take the SIMT attention kernels,
+    the GEMMs the tcgen05 pair kernel with 512 / 2048-wide tiles."""
+    kw = dict(num_layers=2, d_model=512, dff=2048, num_heads=8, lowerdim=256, max_seq_len=512, vocab_size=1004,
+              n_classes=345)
+    B = 2
+    ocfg, eng = build(kw, B, 0)
+    x, y = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 55, vocab=ocfg.vocab_size)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    p = O.init_params(ocfg, 0, torch.float64)
+    eng.load_params(p)
+    eng.train_step(xt.cuda(), yt.cuda(), apply_adam=False)
+    torch.cuda.synchronize()
+    with O.relu_pattern(engine_relu_pattern(eng, ocfg, B)):
+        losses, grads = O.train_step(p, O.AdamTF(p, ocfg.d_model), xt, yt, ocfg, dtype=torch.float64)
+    m = eng.last_step_metrics()
+    for k in ("recon_loss", "class_loss", "total_loss"):
+        assert abs(m[k] - losses[k]) <= 1e-3 * abs(losses[k]), (k, m[k], losses[k])
+    got = eng.export_grads(grads)
+    G = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
+    bad = []
+    for k, ref in grads.items():
+        num = float((got[k].double() - ref.double()).norm())
+        if not num / max(float(ref.double().norm()), 1e-4 * G) < 1e-3:
+            bad.append((k, num / max(float(ref.double().norm()), 1e-4 * G)))
+    assert not bad, f"gradients off: {sorted(bad, key=lambda t: -t[1])[:8]}"
