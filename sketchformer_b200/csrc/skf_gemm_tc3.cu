@@ -28,6 +28,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cuda_bf16.h>
+
 #include "skf_common.cuh"
 #include "skf_ptx.cuh"
 
@@ -127,6 +129,59 @@ __device__ __forceinline__ void mma2_tf32_ss(uint32_t tmem_d, uint64_t adesc, ui
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// bf16 x bf16 -> fp32 product of the mixed scheme (kind::f16), same accumulator as the tf32 MMAs
+__device__ __forceinline__ void mma2_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor for kind::f16 with bf16 operands, fp32 accumulate (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// bf16 operand tiles written by the splitter: 64-byte rows (32 elements) under the 64-byte swizzle
+// (cute Swizzle<2,4,3>: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)).
+//   K-major : rows = M/N index, 8-row groups 512 B apart (SBO), one MMA K = 16 elements = 32 bytes
+//   MN-major: rows = k, 32 MN elements per row, MN chunks of 32 `chunk` bytes apart (LBO), 8-k groups 512 B apart
+__device__ __forceinline__ uint64_t make_desc16_kmajor(uint32_t addr) { return make_smem_desc(addr, 16, 512, 4); }
+__device__ __forceinline__ uint64_t make_desc16_mnmajor(uint32_t addr, uint32_t chunk) {
+  return make_smem_desc(addr, chunk, 512, 4);
+}
+// 8 consecutive fp32 values -> 8 bf16 of x (hi) and 8 bf16 of x - trunc_tf32(x) (lo), 16 bytes each
+__device__ __forceinline__ void t3_to_bf16_pair(const float4& u, const float4& v, uint4& hi, uint4& lo) {
+  auto pk = [](float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+  };
+  hi = make_uint4(pk(u.x, u.y), pk(u.z, u.w), pk(v.x, v.y), pk(v.z, v.w));
+  auto l = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
+  lo = make_uint4(pk(l(u.x), l(u.y)), pk(l(u.z), l(u.w)), pk(l(v.x), l(v.y)), pk(l(v.z), l(v.w)));
+}
+// One operand tile of the mixed scheme: fp32 tile `src` (K-major: ROWS rows of 128 B under the 128B swizzle;
+// MN-major: ROWS/32 boxes of 32 k-rows under the 32B-atom swizzle) -> bf16 hi / lo tiles with 64-byte rows.
+// 128 threads, thread `tid`; tasks = ROWS * 4 groups of 8 elements.
+template <int ROWS, bool MN>
+__device__ __forceinline__ void t3_split_bf16(const uint8_t* src, uint8_t* hi16, uint8_t* lo16, int tid) {
+#pragma unroll
+  for (int task = tid; task < ROWS * 4; task += 128) {
+    const int r = task >> 2, g = task & 3;            // r: row inside the tile (box-major for MN), g: 8-element group
+    const int rs = MN ? (r & 31) : r;                 // row index the swizzles see (boxes are 4 KB / 2 KB aligned)
+    const uint32_t sx = MN ? (uint32_t)((rs & 3) << 1) : (uint32_t)(rs & 7);
+    const uint8_t* rowp = src + r * 128;
+    const float4 u = *reinterpret_cast<const float4*>(rowp + (((2 * g) ^ sx) << 4));
+    const float4 v = *reinterpret_cast<const float4*>(rowp + (((2 * g + 1) ^ sx) << 4));
+    uint4 h, l;
+    t3_to_bf16_pair(u, v, h, l);
+    const uint32_t dof = r * 64 + ((g ^ ((rs >> 1) & 3)) << 4);
+    *reinterpret_cast<uint4*>(hi16 + dof) = h;
+    *reinterpret_cast<uint4*>(lo16 + dof) = l;
+  }
+}
 // arrives (once the MMAs issued so far have completed) on the barrier at the same offset in BOTH CTAs
 __device__ __forceinline__ void tc_commit2(uint32_t bar) {
   asm volatile(
@@ -151,7 +206,12 @@ __device__ __forceinline__ void t3_bulk_wait_read() {
 }
 __device__ __forceinline__ float t3_trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-template <int T3_BN, bool A_MN, bool B_MN>
+// MIX: the two small cross terms of the 3xTF32 product run as bf16 MMAs (kind::f16, twice the TF32 rate):
+//   A*B ~= tf32(A)*tf32(B) [kind::tf32 on the raw tiles] + bf16(A)*bf16(Bl) + bf16(Al)*bf16(B) [kind::f16],
+// Xl = X - trunc_tf32(X).  A cross term is ~2^-11 of the product, so bf16's 2^-9 on its factors costs 2^-20:
+// the result keeps 3xTF32 accuracy for two TF32-pass equivalents instead of three.  The splitter writes four
+// bf16 tiles (hi/lo of A and of this CTA's B half, 32 KB) where the plain scheme keeps two fp32 lo tiles.
+template <int T3_BN, bool A_MN, bool B_MN, bool MIX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T3_THREADS, 1)
 gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
         const __grid_constant__ CUtensorMap tmY, const Gemm3Params p) {
@@ -270,6 +330,30 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           const uint32_t b_s = a_s + T3_A_BYTES;
           const uint32_t al_s = a_s + T3_RAW;
           const uint32_t bl_s = al_s + T3_A_BYTES;
+          if (MIX) {
+            constexpr uint32_t idesc16 = make_idesc_bf16(2 * T3_BM, T3_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            const uint32_t ah16 = a_s + T3_RAW, al16 = ah16 + T3_A_BYTES / 2;
+            const uint32_t bh16 = al16 + T3_A_BYTES / 2, bl16 = bh16 + C::B_BYTES / 2;
+#pragma unroll
+            for (int k2 = 0; k2 < T3_BK / 16; k2++) {                      // cross terms: bf16, K = 16 per MMA
+              const uint32_t ao = A_MN ? k2 * 1024 : k2 * 32;
+              const uint32_t bo = B_MN ? k2 * 1024 : k2 * 32;
+              const uint64_t ahd = A_MN ? make_desc16_mnmajor(ah16 + ao, 2048) : make_desc16_kmajor(ah16 + ao);
+              const uint64_t ald = A_MN ? make_desc16_mnmajor(al16 + ao, 2048) : make_desc16_kmajor(al16 + ao);
+              const uint64_t bhd = B_MN ? make_desc16_mnmajor(bh16 + bo, 2048) : make_desc16_kmajor(bh16 + bo);
+              const uint64_t bld = B_MN ? make_desc16_mnmajor(bl16 + bo, 2048) : make_desc16_kmajor(bl16 + bo);
+              mma2_bf16_ss(acc, ahd, bld, idesc16, (i | k2) != 0 ? 1u : 0u);
+              mma2_bf16_ss(acc, ald, bhd, idesc16, 1u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < T3_BK / 8; ks++) {                       // main term: tf32 on the raw tiles
+              const uint32_t ao = A_MN ? ks * 1024 : ks * 32;
+              const uint32_t bo = B_MN ? ks * 1024 : ks * 32;
+              const uint64_t ad = A_MN ? make_desc_mnmajor(a_s + ao, 4096) : make_desc_kmajor(a_s + ao);
+              const uint64_t bd = B_MN ? make_desc_mnmajor(b_s + bo, 4096) : make_desc_kmajor(b_s + bo);
+              mma2_tf32_ss(acc, ad, bd, idesc, 1u);
+            }
+          } else {
 #pragma unroll
           for (int ks = 0; ks < T3_BK / 8; ks++) {
             const uint32_t ao = A_MN ? ks * 1024 : ks * 32;
@@ -281,6 +365,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             mma2_tf32_ss(acc, ad, bld, idesc, (i | ks) != 0 ? 1u : 0u);   // small terms first
             mma2_tf32_ss(acc, ald, bd, idesc, 1u);
             mma2_tf32_ss(acc, ad, bd, idesc, 1u);
+          }
           }
           tc_commit2(empty_bar(s));
         }
@@ -415,6 +500,22 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         mbar_wait(full_bar(s), ph);
         const float4* src = reinterpret_cast<const float4*>(gen + s * T3_STAGE);
         float4* dst = reinterpret_cast<float4*>(gen + s * T3_STAGE + T3_RAW);
+        if (MIX) {
+          uint8_t* st8 = gen + s * T3_STAGE;
+          uint8_t* ah16 = st8 + T3_RAW;
+          uint8_t* al16 = ah16 + T3_A_BYTES / 2;
+          uint8_t* bh16 = al16 + T3_A_BYTES / 2;
+          uint8_t* bl16 = bh16 + C::B_BYTES / 2;
+          t3_split_bf16<T3_BM, A_MN>(st8, ah16, al16, tid);
+          t3_split_bf16<T3_BNH, B_MN>(st8 + T3_A_BYTES, bh16, bl16, tid);
+          if (B_MN && do_colsum) {
+#pragma unroll
+            for (int ib = 0; ib < 2 * NBOX; ib++) {
+              const float4 x = src[T3_A_BYTES / 16 + tid + 128 * ib];
+              csum[ib >> 1].x += x.x; csum[ib >> 1].y += x.y; csum[ib >> 1].z += x.z; csum[ib >> 1].w += x.w;
+            }
+          }
+        } else {
 #pragma unroll kSplitUnroll3
         for (int k = tid; k < T3_A_BYTES / 16; k += 128) {
           const float4 x = src[k];
@@ -434,6 +535,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           if (B_MN && do_colsum) {
             csum[ib >> 1].x += x.x; csum[ib >> 1].y += x.y; csum[ib >> 1].z += x.z; csum[ib >> 1].w += x.w;
           }
+        }
         }
         fence_proxy_async();
         __syncwarp();
@@ -467,13 +569,14 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 
 // ---- host side ---------------------------------------------------------------------------------
 static int g3_clusters = 0;
+int g_gemm_mix = 1;       // 1: cross terms of the 3xTF32 product as bf16 MMAs (see gemm3_k MIX)
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool MIX>
 static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t st) {
   constexpr int T3_SMEM = Tc3Cfg<BN>::SMEM;
   static bool attr_done = false;
   if (!attr_done) {
-    SKF_CUDA(cudaFuncSetAttribute(gemm3_k<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
+    SKF_CUDA(cudaFuncSetAttribute(gemm3_k<BN, A_MN, B_MN, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
     attr_done = true;
   }
   if (!g3_clusters) {
@@ -486,7 +589,7 @@ static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t 
     qc.blockDim = dim3(T3_THREADS);
     qc.dynamicSmemBytes = T3_SMEM;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, gemm3_k<BN, A_MN, B_MN>, &qc) != cudaSuccess || nc <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&nc, gemm3_k<BN, A_MN, B_MN, MIX>, &qc) != cudaSuccess || nc <= 0) {
       cudaGetLastError();
       nc = sms / 2;
     }
@@ -494,7 +597,7 @@ static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t 
   }
   const int ntiles = p.mt * p.nt * p.splits;
   const int ncl = ntiles < g3_clusters ? ntiles : g3_clusters;
-  gemm3_k<BN, A_MN, B_MN><<<2 * ncl, T3_THREADS, T3_SMEM, st>>>(tm[0], tm[1], tm[2], p);
+  gemm3_k<BN, A_MN, B_MN, MIX><<<2 * ncl, T3_THREADS, T3_SMEM, st>>>(tm[0], tm[1], tm[2], p);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -538,16 +641,20 @@ int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
   if (!b_mn) SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, T3_BK, (uint32_t)(BN / 2), false, false));
   else SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, T3_BK, true, false));
   SKF_TRY(make_tmap_2d_typed(&tm[2], Y, (uint64_t)N, (uint64_t)M, (uint64_t)ldy, 32, 32, false, false));
-  if (BN == 128) {
-    if (!a_mn && !b_mn) return launch_tc3<128, false, false>(tm, p, st);
-    if (!a_mn && b_mn) return launch_tc3<128, false, true>(tm, p, st);
-    if (a_mn && !b_mn) return launch_tc3<128, true, false>(tm, p, st);
-    return launch_tc3<128, true, true>(tm, p, st);
+#define SKF_T3_DISPATCH(BNV, MIXV)                                                          \
+  do {                                                                                     \
+    if (!a_mn && !b_mn) return launch_tc3<BNV, false, false, MIXV>(tm, p, st);             \
+    if (!a_mn && b_mn) return launch_tc3<BNV, false, true, MIXV>(tm, p, st);               \
+    if (a_mn && !b_mn) return launch_tc3<BNV, true, false, MIXV>(tm, p, st);               \
+    return launch_tc3<BNV, true, true, MIXV>(tm, p, st);                                   \
+  } while (0)
+  if (g_gemm_mix) {
+    if (BN == 128) SKF_T3_DISPATCH(128, true);
+    SKF_T3_DISPATCH(256, true);
   }
-  if (!a_mn && !b_mn) return launch_tc3<256, false, false>(tm, p, st);
-  if (!a_mn && b_mn) return launch_tc3<256, false, true>(tm, p, st);
-  if (a_mn && !b_mn) return launch_tc3<256, true, false>(tm, p, st);
-  return launch_tc3<256, true, true>(tm, p, st);
+  if (BN == 128) SKF_T3_DISPATCH(128, false);
+  SKF_T3_DISPATCH(256, false);
+#undef SKF_T3_DISPATCH
 }
 
 }  // namespace skf

@@ -25,7 +25,8 @@ int gemm_tc2(const float*, int64_t, int64_t, const float*, int64_t, int64_t, flo
 int gemm_tc3(const float*, int64_t, int64_t, const float*, int64_t, int64_t, float*, int64_t, int, int, int,
              const skf_gemm_epilogue*, cudaStream_t);
 int gemm_tc3_wanted(int, int, int);
-int g_gemm_pair = 1;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
+int g_gemm_pair = 1;
+extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
 int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
 int attn_fwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
                 const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
@@ -978,6 +979,10 @@ int skf_split_lo(const float* x, float* lo, int64_t n, void* stream) {
 }
 
 int skf_set_option(const char* name, int value) {
+  if (name && strcmp(name, "gemm_mix") == 0) {
+    skf::g_gemm_mix = value ? 1 : 0;
+    return SKF_OK;
+  }
   if (name && strcmp(name, "gemm_pair") == 0) {
     skf::g_gemm_pair = value ? 1 : 0;
     return SKF_OK;

@@ -444,6 +444,24 @@ def test_gemm_pair_fused_bias_gradient(lib, M, N, K):
     assert rel_err(db, dY.double().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("name,a_mn,b_mn", MAJORS)
+@pytest.mark.parametrize("M,N,K", [(256, 256, 32), (512, 256, 64), (200, 1004, 96), (1600, 768, 256), (384, 512, 4000),
+                                   (300, 128, 160)])
+def test_gemm_pair_mixed_bf16_cross_terms(lib, name, a_mn, b_mn, M, N, K):
+    """gemm_mix=1: tf32(A) tf32(B) + bf16(A) bf16(Bl) + bf16(Al) bf16(B); the bf16 operand tiles (64-byte-swizzled,
+    K-major and MN-major) are written by the splitter warps.  Same tolerance as the all-TF32 3-term product."""
+    errs = {}
+    for mix in (1, 0):          # 1 is the default; 0 = all three terms as TF32 MMAs (kept as the reference scheme)
+        _lib.check(lib.skf_set_option(b"gemm_mix", mix))
+        try:
+            errs[mix] = [_gemm_case(M, N, K, a_mn, b_mn, 5, 17),
+                         _gemm_case(M, N, K, a_mn, b_mn, 5, 18, bias=True, act=1, resid=True),
+                         _gemm_case(M, N, K, a_mn, b_mn, 5, 20, split_k=3)]
+        finally:
+            _lib.check(lib.skf_set_option(b"gemm_mix", 1))
+    assert max(errs[1]) < TOL_X3 and max(errs[0]) < TOL_X3, errs
+
+
 def test_gemm_tcgen05_3xtf32_beats_single_pass(lib):
     g = torch.Generator().manual_seed(13)
     for (M, N, K) in ((512, 256, 256), (300, 1024, 256), (256, 512, 1000)):
