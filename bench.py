@@ -231,7 +231,8 @@ def main():
 
     if rank == 0:
         mode = {0: "tf32 single pass everywhere", 1: "3xTF32 forward, TF32 backward",
-                2: "3xTF32 (fp32-grade) forward and backward",
+                2: "error-compensated 3-term products (fp32-grade) forward and backward: tf32 main term + two bf16 "
+                   "compensation terms in the pair GEMM, 3xTF32 in attention",
                 3: "3xTF32 forward and dgrad, TF32 weight gradients"}.get(precision, str(precision))
         line = {"metric": "sketches/sec", "value": value, "unit": "sketches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -288,9 +289,11 @@ def gemm_roofline(eng, c, peaks, peak_src, backend):
     flops = 2.0 * M * N * K
     achieved = flops / (us * 1e-6) / 1e12
     peak = peaks["bf16_tflops"] / 2
-    passes = 3 if backend in (2, 5) else 1
-    kname = {5: "gemm3_k<256,false,true> (cta_group::2 pair, 3xTF32)", 2: "gemm2_k<256,false,true,true> (3xTF32)",
-             0: "gemm2_k<256,false,true,false> (TF32)"}[backend]
+    # TF32-pass equivalents of tensor work per algorithmic FLOP: the pair kernel runs the main term as one TF32 MMA
+    # pass and the two error-compensation terms as bf16 MMAs (twice the TF32 rate) = 2; the single-CTA 3xTF32 kernel 3
+    passes = {5: 2, 2: 3}.get(backend, 1)
+    kname = {5: "gemm3_k<256,false,true,true> (cta_group::2 pair; tf32 main term + two bf16 compensation terms)",
+             2: "gemm2_k<256,false,true,true> (3xTF32)", 0: "gemm2_k<256,false,true,false> (TF32)"}[backend]
     return {"bound": "tensor", "kernel": kname + " FFN-1: 25600x256x1024, bias+ReLU epilogue",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": NCU_TRAFFIC_BYTES.get(backend),
