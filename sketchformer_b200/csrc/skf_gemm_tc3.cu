@@ -49,9 +49,11 @@ constexpr int T3_BM = 128;                 // rows per CTA (256 per cluster)
 constexpr int T3_BK = 32;
 constexpr int T3_A_BYTES = T3_BM * 128;    // 16 KB
 constexpr int T3_EPI_TILE = 32 * 128;
-constexpr int T3_EPI_BUFS = 2;
-constexpr int T3_EPI_BYTES = 4 * T3_EPI_BUFS * T3_EPI_TILE;   // 32 KB
-constexpr int T3_THREADS = 320;
+constexpr int T3_EPI_WARPS = 8;            // two warps per TMEM lane quarter: even / odd 32-column chunks
+constexpr int T3_EPI_BUFS = 1;
+constexpr int T3_EPI_BYTES = T3_EPI_WARPS * T3_EPI_BUFS * T3_EPI_TILE;   // 32 KB
+constexpr int T3_SPLIT_T0 = 32 * (2 + T3_EPI_WARPS);   // first splitter thread
+constexpr int T3_THREADS = T3_SPLIT_T0 + 128;          // 448
 constexpr int T3_MAX_STAGES = 4;
 
 // BN = columns per cluster tile (256, or 128 for N <= 256: twice as many tiles for the 74 clusters and a
@@ -251,7 +253,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 2 * T3_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -372,10 +374,13 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         tc_commit2(tfull_bar(a));
       }
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------------ epilogue (4 warps, both CTAs)
+  } else if (warp < 2 + T3_EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue (8 warps, both CTAs)
+    // With K = 256 a tile's k-loop (8 k-blocks) is shorter than draining its 128 x 256 accumulator through four
+    // warps, so two warps share each TMEM lane quarter and take alternate 32-column chunks.
     const int q = warp & 3;
     const int ew = warp - 2;
+    const int chalf = ew >> 2;             // warps 2..5 take even chunks, 6..9 odd chunks
     const uint32_t stg0 = epi0 + (uint32_t)(ew * T3_EPI_BUFS) * T3_EPI_TILE;
     uint8_t* stg0_gen = gen + S * T3_STAGE + (ew * T3_EPI_BUFS) * T3_EPI_TILE;
     const skf_gemm_epilogue& e = p.e;
@@ -394,7 +399,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T3_BN);
       constexpr int NCH = T3_BN / 32;
 #pragma unroll 1
-      for (int c = 0; c < NCH; c++) {
+      for (int c = chalf; c < NCH; c += 2) {
         const int nb = n0 + c * 32;
         const bool live = nb < p.N && mrow0 < p.M;
         uint32_t r[32];
@@ -402,7 +407,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           tmem_ld32(acc + (uint32_t)(c * 32), r);
           tmem_ld_wait();
         }
-        if (c == NCH - 1) {
+        if (c >= NCH - 2) {                // this warp's last chunk of the accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
@@ -475,7 +480,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     if (lane == 0) t3_bulk_wait_read<0>();
   } else {
     // ------------------------------------------------------------------ splitter (4 warps, both CTAs)
-    const int tid = threadIdx.x - 192;
+    const int tid = threadIdx.x - T3_SPLIT_T0;
     uint32_t it = 0;
     uint32_t xfull_leader[S];
 #pragma unroll
