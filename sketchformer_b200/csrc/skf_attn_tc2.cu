@@ -1,8 +1,10 @@
 // Scaled-dot-product attention (builders/utils.py:71-105, split_heads transformer.py:160-165) and its
-// backward on the 5th-gen tensor cores, head dim 32, flash-style: the (Tq,Tk) score matrix never
+// backward on the 5th-gen tensor cores, head dim 32 or 64 (template DH; a [rows x dh] tile is dh/32
+// chunk tiles of 128-byte rows), sequences up to 1024, flash-style: the (Tq,Tk) score matrix never
 // exists in HBM, masks come from per-key pad flags + indices, and the other sequence is streamed in
-// 64-row blocks so that a CTA needs only 64-96 KB of shared memory and 128-256 TMEM columns and
-// two or three CTAs share an SM (their TMA / MMA / softmax phases overlap each other).
+// 64-row blocks.  At head dim 32 a CTA needs 70-105 KB of shared memory and 128-256 TMEM columns and
+// two or three CTAs share an SM (their TMA / MMA / softmax phases overlap each other); at head dim 64
+// (cfg5: d 512, T 512) it is one CTA of 132-205 KB and up to 384 TMEM columns per SM.
 //
 //   fwd : per key block    S = Q K^T ; online softmax (running max / sum, O rescaled in TMEM) ; O += P V
 //   dq  : per key block    S, dP = dO V^T ; dS = P (dP - delta) / sqrt(dh) ; dQ += dS K      (lanes = queries)
@@ -26,11 +28,11 @@ using namespace ptx;
 int make_tmap_2d_typed(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
                        uint32_t box_inner, uint32_t box_outer, bool mn_major, bool tf32_convert);
 
-constexpr int A2_DH = 32;              // head dim (one 128-byte swizzle row)
+constexpr int A2_DH = 32;              // columns of one tile chunk (one 128-byte swizzle row); head dim = NC chunks
 constexpr int A2_BLK = 64;             // rows of the streamed operand per iteration
 constexpr int A2_T128 = 128 * 128;     // 128 rows x 128 B
 constexpr int A2_T64 = 64 * 128;       //  64 rows x 128 B
-constexpr int A2_MAXT = 256;           // longest sequence (pad / lse / delta staging)
+constexpr int A2_MAXT = 1024;          // longest sequence (bias / lse / delta staging); maximum_position_encoding = 1000
 constexpr float A2_MASK_NEG = -1e9f;
 
 struct Attn2Args {
@@ -69,29 +71,43 @@ __device__ __forceinline__ void a2_split(const uint8_t* raw, uint8_t* lo, int by
   }
 }
 
-// D[128 x N] = A B^T, both K-major smem tiles with dh = 32 (4 k-steps); X3: Ah*Bl + Al*Bh + Ah*Bh
-template <bool X3>
+// A [rows x dh] tile is NC = dh / 32 chunks of [rows x 32] (128-byte rows), chunk c at + c * rows * 128 bytes;
+// its lo tile follows the raw tile.  TMA: one box per chunk.
+template <int NC>
+__device__ __forceinline__ void a2_load(uint32_t dst, const CUtensorMap* m, uint32_t bar, int col0, int row0, int rows) {
+#pragma unroll
+  for (int c = 0; c < NC; c++) tma_load_2d(dst + c * rows * 128, m, bar, col0 + A2_DH * c, row0);
+}
+
+// D[128 x N] = A B^T, both K-major smem tiles of NC chunks (4 k-steps each); X3: Ah*Bl + Al*Bh + Ah*Bh.
+// ca / cb: chunk strides of the A / B tile in bytes (rows * 128).
+template <bool X3, int NC>
 __device__ __forceinline__ void a2_mma_ss(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl,
-                                          uint32_t idesc) {
+                                          uint32_t idesc, uint32_t ca, uint32_t cb) {
   uint32_t acc = 0;
   if (X3) {
 #pragma unroll
-    for (int ks = 0; ks < A2_DH / 8; ks++) {
-      mma_tf32_ss(d, make_desc_kmajor(ah + ks * 32), make_desc_kmajor(bl + ks * 32), idesc, acc);
+    for (int ks = 0; ks < NC * 4; ks++) {
+      const uint32_t ao = (ks >> 2) * ca + (ks & 3) * 32, bo = (ks >> 2) * cb + (ks & 3) * 32;
+      mma_tf32_ss(d, make_desc_kmajor(ah + ao), make_desc_kmajor(bl + bo), idesc, acc);
       acc = 1;
     }
 #pragma unroll
-    for (int ks = 0; ks < A2_DH / 8; ks++)
-      mma_tf32_ss(d, make_desc_kmajor(al + ks * 32), make_desc_kmajor(bh + ks * 32), idesc, 1u);
+    for (int ks = 0; ks < NC * 4; ks++) {
+      const uint32_t ao = (ks >> 2) * ca + (ks & 3) * 32, bo = (ks >> 2) * cb + (ks & 3) * 32;
+      mma_tf32_ss(d, make_desc_kmajor(al + ao), make_desc_kmajor(bh + bo), idesc, 1u);
+    }
   }
 #pragma unroll
-  for (int ks = 0; ks < A2_DH / 8; ks++) {
-    mma_tf32_ss(d, make_desc_kmajor(ah + ks * 32), make_desc_kmajor(bh + ks * 32), idesc, acc);
+  for (int ks = 0; ks < NC * 4; ks++) {
+    const uint32_t ao = (ks >> 2) * ca + (ks & 3) * 32, bo = (ks >> 2) * cb + (ks & 3) * 32;
+    mma_tf32_ss(d, make_desc_kmajor(ah + ao), make_desc_kmajor(bh + bo), idesc, acc);
     acc = 1;
   }
 }
 
-// D[128 x 32] (+)= A[tmem, 64 columns] * B[64 rows x 32, MN-major smem]; X3: A*Bl + A*Bh
+// D[128 x dh] (+)= A[tmem, 64 columns] * B[64 rows x dh, MN-major smem: NC 32-wide N-chunks A2_T64 bytes apart];
+// X3: A*Bl + A*Bh.  N comes from the instruction descriptor.
 template <bool X3>
 __device__ __forceinline__ void a2_mma_ts(uint32_t d, uint32_t a_tmem, uint32_t bh, uint32_t bl, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -99,13 +115,13 @@ __device__ __forceinline__ void a2_mma_ts(uint32_t d, uint32_t a_tmem, uint32_t 
   if (X3) {
 #pragma unroll
     for (int k = 0; k < A2_BLK / 8; k++) {
-      mma_tf32_ts(d, a_tmem + k * 8, make_desc_mnmajor(bl + k * 1024, 4096), idesc, acc);
+      mma_tf32_ts(d, a_tmem + k * 8, make_desc_mnmajor(bl + k * 1024, A2_T64), idesc, acc);
       acc = 1;
     }
   }
 #pragma unroll
   for (int k = 0; k < A2_BLK / 8; k++) {
-    mma_tf32_ts(d, a_tmem + k * 8, make_desc_mnmajor(bh + k * 1024, 4096), idesc, acc);
+    mma_tf32_ts(d, a_tmem + k * 8, make_desc_mnmajor(bh + k * 1024, A2_T64), idesc, acc);
     acc = 1;
   }
 }
@@ -138,9 +154,9 @@ __device__ __forceinline__ void a2_row_kmajor_to_mnmajor_inplace(uint8_t* tile, 
   for (int q = 0; q < 8; q++) *reinterpret_cast<float4*>(tile + r * 128 + a2_mnchunk(r, q)) = c[q];
 }
 
-// D[128 x 64] (+)= A[tmem, 64 columns] * [Bh | Bl]: the raw tile and its lo tile (A2_T64 bytes apart in shared
-// memory) are read by ONE MMA as the two 32-wide N-chunks of an MN-major operand, so columns [0,32) of D
-// accumulate A*Bh and [32,64) A*Bl (summed by the reader).  Dependent 128x32x8 MMAs cost ~80-100 clk each whatever
+// D[128 x 2 dh] (+)= A[tmem, 64 columns] * [Bh | Bl]: the raw tile and its lo tile (contiguous 32-wide chunks,
+// A2_T64 bytes apart in shared memory) are read by ONE MMA as the 2 NC N-chunks of an MN-major operand, so columns
+// [0,dh) of D accumulate A*Bh and [dh,2dh) A*Bl (summed by the reader).  Dependent 128x32x8 MMAs cost ~80-100 clk each whatever
 // their N (clock64 stamps: 16 of them 1300-1800 clk, 8 of N=64 850 clk), so half as many wider ones are cheaper.
 __device__ __forceinline__ void a2_mma_ts_cat(uint32_t d, uint32_t a_tmem, uint32_t bh, uint32_t idesc64,
                                               uint32_t accumulate) {
@@ -196,57 +212,58 @@ __device__ __forceinline__ void a2_free(const A2Common& c) {
 // kernel is bound by the serial phase chain of each CTA, not by a pipe: the next step is a warp-specialised
 // two-tile ping-pong (softmax of one query tile under the MMAs of the other), not more tuning of this structure.
 // ---------------------------------------------------------------------------------------------------
-constexpr int A2F_DATA = 2 * A2_T128 + 4 * A2_T64 + A2_MAXT * 4;
+__host__ __device__ constexpr int a2f_data(int nc) { return nc * (2 * A2_T128 + 4 * A2_T64) + A2_MAXT * 4; }
 constexpr float A2_LOG2E = 1.4426950408889634f;
 __device__ __forceinline__ float a2_ex2(float x) {      // 2^x, MUFU.EX2 (2 ulp; the result is rounded to TF32 anyway)
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-template <bool X3>
-__global__ void __launch_bounds__(128, 3)
+template <bool X3, int DH>
+__global__ void __launch_bounds__(128, DH == 32 ? 3 : 1)
 attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
             const __grid_constant__ CUtensorMap mV, const Attn2Args a) {
   extern __shared__ uint8_t smem_raw[];
   A2Common c;
-  a2_prologue<128>(c, smem_raw, A2F_DATA);
+  constexpr int NC = DH / A2_DH, T128 = NC * A2_T128, T64 = NC * A2_T64;
+  a2_prologue<128>(c, smem_raw, a2f_data(NC));
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t sQ = c.base, sQl = sQ + A2_T128, sK = sQl + A2_T128, sKl = sK + A2_T64, sV = sKl + A2_T64,
-                 sVl = sV + A2_T64;
+  const uint32_t sQ = c.base, sQl = sQ + T128, sK = sQl + T128, sKl = sK + T64, sV = sKl + T64,
+                 sVl = sV + T64;
   uint8_t* gQ = c.gen;
-  uint8_t* gK = gQ + 2 * A2_T128;
-  uint8_t* gV = gK + 2 * A2_T64;
-  float* bias_s = reinterpret_cast<float*>(gV + 2 * A2_T64);
+  uint8_t* gK = gQ + 2 * T128;
+  uint8_t* gV = gK + 2 * T64;
+  float* bias_s = reinterpret_cast<float*>(gV + 2 * T64);
   const uint32_t bar_q = c.bar0, bar_k = c.bar0 + 8, bar_v = c.bar0 + 16, bar_s = c.bar0 + 24, bar_o = c.bar0 + 32;
   const int kmax = a.mode == 2 ? min(a.Tk, q0 + 128) : a.Tk;   // causal: keys above the tile's last row never count
   const int nblk = (kmax + A2_BLK - 1) / A2_BLK;
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, A2_T128);
-    tma_load_2d(sQ, &mQ, bar_q, h * A2_DH, b * a.Tq + q0);
-    mbar_arrive_expect_tx(bar_k, A2_T64);
-    tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk);
-    mbar_arrive_expect_tx(bar_v, A2_T64);
-    tma_load_2d(sV, &mV, bar_v, h * A2_DH, b * a.Tk);
+    mbar_arrive_expect_tx(bar_q, T128);
+    a2_load<NC>(sQ, &mQ, bar_q, h * DH, b * a.Tq + q0, 128);
+    mbar_arrive_expect_tx(bar_k, T64);
+    a2_load<NC>(sK, &mK, bar_k, h * DH, b * a.Tk, A2_BLK);
+    mbar_arrive_expect_tx(bar_v, T64);
+    a2_load<NC>(sV, &mV, bar_v, h * DH, b * a.Tk, A2_BLK);
   }
   // logits are handled in the log2 domain: t = S * (scale*log2e) + bias[key]; bias carries the reference's
   // additive -1e9 mask (builders/utils.py:93-97) for padded keys and -inf for keys outside the sequence
-  for (int i = tid; i < A2_MAXT; i += 128) {
+  for (int i = tid; i < nblk * A2_BLK; i += 128) {
     float bj = 0.f;
     if (i >= a.Tk) bj = -INFINITY;
     else if (a.mode >= 1 && a.key_pad && a.key_pad[(int64_t)b * a.Tk + i]) bj = A2_MASK_NEG * A2_LOG2E;
     bias_s[i] = bj;
   }
   mbar_wait(bar_q, 0);
-  if (X3) a2_split(gQ, gQ + A2_T128, A2_T128);
+  if (X3) a2_split(gQ, gQ + T128, T128);
   const float c1 = a.scale * A2_LOG2E;
   const int qw = q0 + (tid & ~31);            // first query row of this warp
 
   const uint32_t tS = c.tmem, tO = c.tmem + 64;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
-  const uint32_t idesc_o = make_idesc_tf32(128, A2_DH, 0, 1);
+  const uint32_t idesc_o = make_idesc_tf32(128, DH, 0, 1);
   const int qi = q0 + tid;
   float m_run = -INFINITY, l_run = 0.f;
 
@@ -254,19 +271,19 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     const uint32_t ph = (uint32_t)j & 1u;
     const int k0 = j * A2_BLK;
     mbar_wait(bar_k, ph);
-    if (X3) a2_split(gK, gK + A2_T64, A2_T64);
+    if (X3) a2_split(gK, gK + T64, T64);
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      a2_mma_ss<X3>(tS, sQ, sQl, sK, sKl, idesc_s);
+      a2_mma_ss<X3, NC>(tS, sQ, sQl, sK, sKl, idesc_s, A2_T128, A2_T64);
       tc_commit(bar_s);
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
     if (tid == 0 && j + 1 < nblk) {     // K buffers are free again: prefetch the next key block
-      mbar_arrive_expect_tx(bar_k, A2_T64);
-      tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk + k0 + A2_BLK);
+      mbar_arrive_expect_tx(bar_k, T64);
+      a2_load<NC>(sK, &mK, bar_k, h * DH, b * a.Tk + k0 + A2_BLK, A2_BLK);
     }
     // ---- online softmax: this thread owns query row qi == TMEM lane tid ----------------------
     uint32_t r0[32], r1[32];
@@ -330,15 +347,18 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     tmem_st32(tS + lane_off, r0);
     tmem_st32(tS + lane_off + 32, r1);
     if (j > 0) {                                       // rescale the running output (previous P V has completed)
-      tmem_ld32(tO + lane_off, r0);
-      tmem_ld_wait();
 #pragma unroll
-      for (int jj = 0; jj < 32; jj++) r0[jj] = __float_as_uint(__uint_as_float(r0[jj]) * alpha);
-      tmem_st32(tO + lane_off, r0);
+      for (int cc = 0; cc < NC; cc++) {
+        tmem_ld32(tO + lane_off + 32 * cc, r0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) r0[jj] = __float_as_uint(__uint_as_float(r0[jj]) * alpha);
+        tmem_st32(tO + lane_off + 32 * cc, r0);
+      }
     }
     tmem_st_wait();
     mbar_wait(bar_v, ph);
-    if (X3) a2_split(gV, gV + A2_T64, A2_T64);
+    if (X3) a2_split(gV, gV + T64, T64);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -350,25 +370,28 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     mbar_wait(bar_o, ph);
     tc_fence_after();
     if (tid == 0 && j + 1 < nblk) {     // V buffers are free again
-      mbar_arrive_expect_tx(bar_v, A2_T64);
-      tma_load_2d(sV, &mV, bar_v, h * A2_DH, b * a.Tk + k0 + A2_BLK);
+      mbar_arrive_expect_tx(bar_v, T64);
+      a2_load<NC>(sV, &mV, bar_v, h * DH, b * a.Tk + k0 + A2_BLK, A2_BLK);
     }
   }
   {
     uint32_t r[32];
-    __syncwarp();
-    tmem_ld32(tO + lane_off, r);
-    tmem_ld_wait();
-    if (qi < a.Tq) {
-      const float inv = 1.0f / l_run;
-      float4* dst = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tq + qi) * a.ld0 + h * A2_DH);
+    const float inv = 1.0f / l_run;
 #pragma unroll
-      for (int jj = 0; jj < 8; jj++)
-        dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * inv, __uint_as_float(r[4 * jj + 1]) * inv,
-                              __uint_as_float(r[4 * jj + 2]) * inv, __uint_as_float(r[4 * jj + 3]) * inv);
-      // natural-log logsumexp of the masked scaled logits (m_run is in the log2 domain)
-      if (a.out1) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = m_run * 0.6931471805599453f + logf(l_run);
+    for (int cc = 0; cc < NC; cc++) {
+      __syncwarp();
+      tmem_ld32(tO + lane_off + 32 * cc, r);
+      tmem_ld_wait();
+      if (qi < a.Tq) {
+        float4* dst = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tq + qi) * a.ld0 + h * DH + 32 * cc);
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++)
+          dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * inv, __uint_as_float(r[4 * jj + 1]) * inv,
+                                __uint_as_float(r[4 * jj + 2]) * inv, __uint_as_float(r[4 * jj + 3]) * inv);
+      }
     }
+    // natural-log logsumexp of the masked scaled logits (m_run is in the log2 domain)
+    if (qi < a.Tq && a.out1) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = m_run * 0.6931471805599453f + logf(l_run);
   }
   a2_free<128>(c);
 }
@@ -389,41 +412,43 @@ attn2_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
 // row math 1400-2100, dQ MMAs (16 x N=32) 1200-1800, splits 500; epilogue 2200.  Now the O tile comes in by
 // TMA into the (not yet used) Q-lo buffer and delta is taken from shared memory, and dQ uses 8 N=64 MMAs.
 // ---------------------------------------------------------------------------------------------------
-constexpr int A2Q_DATA = 4 * A2_T128 + 4 * A2_T64 + A2_MAXT * 4;
-template <bool X3>
-__global__ void __launch_bounds__(256, 2)
+__host__ __device__ constexpr int a2q_data(int nc) { return nc * (4 * A2_T128 + 4 * A2_T64) + A2_MAXT * 4; }
+template <bool X3, int DH>
+__global__ void __launch_bounds__(256, DH == 32 ? 2 : 1)
 attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mdO,
                const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
                const __grid_constant__ CUtensorMap mO, const Attn2Args a) {
   extern __shared__ uint8_t smem_raw[];
   A2Common c;
-  a2_prologue<256>(c, smem_raw, A2Q_DATA);
+  constexpr int NC = DH / A2_DH, T128 = NC * A2_T128, T64 = NC * A2_T64;
+  constexpr int TCOLS = 256;                                      // S 64 + dP 64 + dQ (2) dh
+  a2_prologue<TCOLS>(c, smem_raw, a2q_data(NC));
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
   const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, row = tid & 127;
-  const uint32_t sQ = c.base, sQl = sQ + A2_T128, sdO = sQl + A2_T128, sdOl = sdO + A2_T128, sK = sdOl + A2_T128,
-                 sKl = sK + A2_T64, sX = sKl + A2_T64, sXl = sX + A2_T64;
+  const uint32_t sQ = c.base, sQl = sQ + T128, sdO = sQl + T128, sdOl = sdO + T128, sK = sdOl + T128,
+                 sKl = sK + T64, sX = sKl + T64, sXl = sX + T64;
   uint8_t* gQ = c.gen;
-  uint8_t* gdO = gQ + 2 * A2_T128;
-  uint8_t* gK = gdO + 2 * A2_T128;
-  uint8_t* gX = gK + 2 * A2_T64;
-  float* bias_s = reinterpret_cast<float*>(gX + 2 * A2_T64);
+  uint8_t* gdO = gQ + 2 * T128;
+  uint8_t* gK = gdO + 2 * T128;
+  uint8_t* gX = gK + 2 * T64;
+  float* bias_s = reinterpret_cast<float*>(gX + 2 * T64);
   const uint32_t bar_q = c.bar0, bar_k = c.bar0 + 8, bar_v = c.bar0 + 16, bar_x = c.bar0 + 24, bar_s = c.bar0 + 32,
                  bar_o = c.bar0 + 40;
   const int kmax = a.mode == 2 ? min(a.Tk, q0 + 128) : a.Tk;
   const int nblk = (kmax + A2_BLK - 1) / A2_BLK;
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, 2 * A2_T128);
-    tma_load_2d(sQ, &mQ, bar_q, h * A2_DH, b * a.Tq + q0);
-    tma_load_2d(sdO, &mdO, bar_q, h * A2_DH, b * a.Tq + q0);
-    mbar_arrive_expect_tx(bar_x, A2_T128);                      // O tile, parked in the Q-lo buffer
-    tma_load_2d(sQl, &mO, bar_x, h * A2_DH, b * a.Tq + q0);
-    mbar_arrive_expect_tx(bar_k, A2_T64);
-    tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk);
-    mbar_arrive_expect_tx(bar_v, A2_T64);
-    tma_load_2d(sX, &mV, bar_v, h * A2_DH, b * a.Tk);
+    mbar_arrive_expect_tx(bar_q, 2 * T128);
+    a2_load<NC>(sQ, &mQ, bar_q, h * DH, b * a.Tq + q0, 128);
+    a2_load<NC>(sdO, &mdO, bar_q, h * DH, b * a.Tq + q0, 128);
+    mbar_arrive_expect_tx(bar_x, T128);                      // O tile, parked in the Q-lo buffer
+    a2_load<NC>(sQl, &mO, bar_x, h * DH, b * a.Tq + q0, 128);
+    mbar_arrive_expect_tx(bar_k, T64);
+    a2_load<NC>(sK, &mK, bar_k, h * DH, b * a.Tk, A2_BLK);
+    mbar_arrive_expect_tx(bar_v, T64);
+    a2_load<NC>(sX, &mV, bar_v, h * DH, b * a.Tk, A2_BLK);
   }
-  for (int i = tid; i < A2_MAXT; i += 256) {
+  for (int i = tid; i < nblk * A2_BLK; i += 256) {
     float bj = 0.f;
     if (i >= a.Tk) bj = -INFINITY;
     else if (a.mode >= 1 && a.key_pad && a.key_pad[(int64_t)b * a.Tk + i]) bj = A2_MASK_NEG * A2_LOG2E;
@@ -437,25 +462,28 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
   {
     // delta_i = sum_c dO[i,c] O[i,c] from the two K-major tiles in shared memory (row per thread; rows past
     // the sequence are TMA zero-fill)
-    const uint8_t* orow = gQ + A2_T128 + row * 128;
-    const uint8_t* grow = gdO + row * 128;
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const float4 o = *reinterpret_cast<const float4*>(orow + a2_kchunk(row, q));
-      const float4 g = *reinterpret_cast<const float4*>(grow + a2_kchunk(row, q));
-      delta += (o.x * g.x + o.y * g.y) + (o.z * g.z + o.w * g.w);
+    for (int cc = 0; cc < NC; cc++) {
+      const uint8_t* orow = gQ + T128 + cc * A2_T128 + row * 128;
+      const uint8_t* grow = gdO + cc * A2_T128 + row * 128;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const float4 o = *reinterpret_cast<const float4*>(orow + a2_kchunk(row, q));
+        const float4 g = *reinterpret_cast<const float4*>(grow + a2_kchunk(row, q));
+        delta += (o.x * g.x + o.y * g.y) + (o.z * g.z + o.w * g.w);
+      }
     }
     if (wg == 0 && qi < a.Tq) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = delta;
   }
   __syncthreads();                          // every thread has read the O tile: the Q-lo buffer may be overwritten
   if (X3) {
-    a2_split(gQ, gQ + A2_T128, A2_T128);
-    a2_split(gdO, gdO + A2_T128, A2_T128);
+    a2_split(gQ, gQ + T128, T128);
+    a2_split(gdO, gdO + T128, T128);
   }
   const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdQ = c.tmem + 128;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
-  const uint32_t idesc_o = make_idesc_tf32(128, X3 ? 2 * A2_DH : A2_DH, 0, 1);
+  const uint32_t idesc_o = make_idesc_tf32(128, X3 ? 2 * DH : DH, 0, 1);
   const float c1 = a.scale * A2_LOG2E;
   const int qw = q0 + (warp & 3) * 32;      // first query row of this warp
 
@@ -465,26 +493,28 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
     mbar_wait(bar_k, ph);
     mbar_wait(bar_v, ph);
     if (X3) {
-      a2_split(gK, gK + A2_T64, A2_T64);
-      a2_split(gX, gX + A2_T64, A2_T64);
+      a2_split(gK, gK + T64, T64);
+      a2_split(gX, gX + T64, T64);
     }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      a2_mma_ss<X3>(tS, sQ, sQl, sK, sKl, idesc_s);
-      a2_mma_ss<X3>(tdP, sdO, sdOl, sX, sXl, idesc_s);
+      a2_mma_ss<X3, NC>(tS, sQ, sQl, sK, sKl, idesc_s, A2_T128, A2_T64);
+      a2_mma_ss<X3, NC>(tdP, sdO, sdOl, sX, sXl, idesc_s, A2_T128, A2_T64);
       tc_commit(bar_s);
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
     // the V block is dead: rebuild the key block (raw + lo) in its buffers with the MN-major swizzle for the
     // dQ MMA, then hand the K-major buffers to the TMA for the next key block
-    a2_kmajor_to_mnmajor_64(gK, gK + A2_T64, gX, gX + A2_T64, X3);
+#pragma unroll
+    for (int cc = 0; cc < NC; cc++)
+      a2_kmajor_to_mnmajor_64(gK + cc * A2_T64, gK + T64 + cc * A2_T64, gX + cc * A2_T64, gX + T64 + cc * A2_T64, X3);
     __syncthreads();
     if (tid == 0 && j + 1 < nblk) {
-      mbar_arrive_expect_tx(bar_k, A2_T64);
-      tma_load_2d(sK, &mK, bar_k, h * A2_DH, b * a.Tk + k0 + A2_BLK);
+      mbar_arrive_expect_tx(bar_k, T64);
+      a2_load<NC>(sK, &mK, bar_k, h * DH, b * a.Tk + k0 + A2_BLK, A2_BLK);
     }
     {
       uint32_t rs[32], rp[32];
@@ -524,31 +554,34 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
     mbar_wait(bar_o, ph);
     tc_fence_after();
     if (tid == 0 && j + 1 < nblk) {
-      mbar_arrive_expect_tx(bar_v, A2_T64);
-      tma_load_2d(sX, &mV, bar_v, h * A2_DH, b * a.Tk + k0 + A2_BLK);
+      mbar_arrive_expect_tx(bar_v, T64);
+      a2_load<NC>(sX, &mV, bar_v, h * DH, b * a.Tk + k0 + A2_BLK, A2_BLK);
     }
   }
   if (wg == 0) {
     uint32_t r[32];
-    __syncwarp();
-    tmem_ld32(tdQ + lane_off, r);
-    if (X3) {
-      uint32_t rl[32];
-      tmem_ld32(tdQ + lane_off + 32, rl);
+#pragma unroll
+    for (int cc = 0; cc < NC; cc++) {
+      __syncwarp();
+      tmem_ld32(tdQ + lane_off + 32 * cc, r);
+      if (X3) {
+        uint32_t rl[32];
+        tmem_ld32(tdQ + lane_off + DH + 32 * cc, rl);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) r[jj] = __float_as_uint(__uint_as_float(r[jj]) + __uint_as_float(rl[jj]));
+      }
       tmem_ld_wait();
+      if (qi < a.Tq) {
+        float4* dst = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tq + qi) * a.ld0 + h * DH + 32 * cc);
 #pragma unroll
-      for (int jj = 0; jj < 32; jj++) r[jj] = __float_as_uint(__uint_as_float(r[jj]) + __uint_as_float(rl[jj]));
-    }
-    tmem_ld_wait();
-    if (qi < a.Tq) {
-      float4* dst = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tq + qi) * a.ld0 + h * A2_DH);
-#pragma unroll
-      for (int jj = 0; jj < 8; jj++)
-        dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * a.scale, __uint_as_float(r[4 * jj + 1]) * a.scale,
-                              __uint_as_float(r[4 * jj + 2]) * a.scale, __uint_as_float(r[4 * jj + 3]) * a.scale);
+        for (int jj = 0; jj < 8; jj++)
+          dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * a.scale, __uint_as_float(r[4 * jj + 1]) * a.scale,
+                                __uint_as_float(r[4 * jj + 2]) * a.scale, __uint_as_float(r[4 * jj + 3]) * a.scale);
+      }
     }
   }
-  a2_free<256>(c);
+  a2_free<TCOLS>(c);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -556,41 +589,42 @@ attn2_bwd_dq_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ C
 //   (A, B = Q block, dO block K-major for the score MMAs, then their MN-major copies for the output MMAs)
 // tmem: S^T -> P^T [0,64)  dP^T -> dS^T [64,128)  dV [128,192) = P^T dOh | P^T dOl   dK [192,256) likewise
 // ---------------------------------------------------------------------------------------------------
-constexpr int A2K_DATA = 4 * A2_T128 + 4 * A2_T64 + 2 * A2_MAXT * 4;
-template <bool X3>
-__global__ void __launch_bounds__(256, 2)
+__host__ __device__ constexpr int a2k_data(int nc) { return nc * (4 * A2_T128 + 4 * A2_T64) + 2 * A2_MAXT * 4; }
+template <bool X3, int DH>
+__global__ void __launch_bounds__(256, DH == 32 ? 2 : 1)
 attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
                 const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mdO,
-                const __grid_constant__ CUtensorMap mQmn, const __grid_constant__ CUtensorMap mdOmn,
                 const Attn2Args a) {
   extern __shared__ uint8_t smem_raw[];
   A2Common c;
-  a2_prologue<256>(c, smem_raw, A2K_DATA);
+  constexpr int NC = DH / A2_DH, T128 = NC * A2_T128, T64 = NC * A2_T64;
+  constexpr int TCOLS = DH == 32 ? 256 : 512;                     // S 64 + dP 64 + dV 2 dh + dK 2 dh
+  a2_prologue<TCOLS>(c, smem_raw, a2k_data(NC));
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * 128;
   const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, row = tid & 127;
-  const uint32_t sK = c.base, sKl = sK + A2_T128, sV = sKl + A2_T128, sVl = sV + A2_T128, sA = sVl + A2_T128,
-                 sAl = sA + A2_T64, sB = sAl + A2_T64, sBl = sB + A2_T64;
+  const uint32_t sK = c.base, sKl = sK + T128, sV = sKl + T128, sVl = sV + T128, sA = sVl + T128,
+                 sAl = sA + T64, sB = sAl + T64, sBl = sB + T64;
   uint8_t* gK = c.gen;
-  uint8_t* gV = gK + 2 * A2_T128;
-  uint8_t* gA = gV + 2 * A2_T128;
-  uint8_t* gB = gA + 2 * A2_T64;
-  float* lse_s = reinterpret_cast<float*>(gB + 2 * A2_T64);     // lse * log2e, +inf for queries past the sequence
+  uint8_t* gV = gK + 2 * T128;
+  uint8_t* gA = gV + 2 * T128;
+  uint8_t* gB = gA + 2 * T64;
+  float* lse_s = reinterpret_cast<float*>(gB + 2 * T64);     // lse * log2e, +inf for queries past the sequence
   float* del_s = lse_s + A2_MAXT;
   const uint32_t bar_q = c.bar0, bar_a = c.bar0 + 8, bar_b = c.bar0 + 16, bar_s = c.bar0 + 24, bar_o = c.bar0 + 32;
   const int nqb = (a.Tq + A2_BLK - 1) / A2_BLK;
   const int ib0 = a.mode == 2 ? j0 / A2_BLK : 0;     // causal: queries before the tile's first key see none of it
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, 2 * A2_T128);
-    tma_load_2d(sK, &mK, bar_q, h * A2_DH, b * a.Tk + j0);
-    tma_load_2d(sV, &mV, bar_q, h * A2_DH, b * a.Tk + j0);
+    mbar_arrive_expect_tx(bar_q, 2 * T128);
+    a2_load<NC>(sK, &mK, bar_q, h * DH, b * a.Tk + j0, 128);
+    a2_load<NC>(sV, &mV, bar_q, h * DH, b * a.Tk + j0, 128);
     if (ib0 < nqb) {
-      mbar_arrive_expect_tx(bar_a, 2 * A2_T64);
-      tma_load_2d(sA, &mQ, bar_a, h * A2_DH, b * a.Tq + ib0 * A2_BLK);
-      tma_load_2d(sB, &mdO, bar_a, h * A2_DH, b * a.Tq + ib0 * A2_BLK);
+      mbar_arrive_expect_tx(bar_a, 2 * T64);
+      a2_load<NC>(sA, &mQ, bar_a, h * DH, b * a.Tq + ib0 * A2_BLK, A2_BLK);
+      a2_load<NC>(sB, &mdO, bar_a, h * DH, b * a.Tq + ib0 * A2_BLK, A2_BLK);
     }
   }
-  for (int i = tid; i < A2_MAXT; i += 256) {
+  for (int i = tid; i < nqb * A2_BLK; i += 256) {
     lse_s[i] = i < a.Tq ? a.lse[((int64_t)b * a.H + h) * a.Tq + i] * A2_LOG2E : INFINITY;
     del_s[i] = i < a.Tq ? a.delta[((int64_t)b * a.H + h) * a.Tq + i] : 0.f;
   }
@@ -600,13 +634,13 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
   else if (a.mode >= 1 && a.key_pad && a.key_pad[(int64_t)b * a.Tk + kj]) bias = A2_MASK_NEG * A2_LOG2E;
   mbar_wait(bar_q, 0);
   if (X3) {
-    a2_split(gK, gK + A2_T128, A2_T128);
-    a2_split(gV, gV + A2_T128, A2_T128);
+    a2_split(gK, gK + T128, T128);
+    a2_split(gV, gV + T128, T128);
   }
-  const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdV = c.tmem + 128, tdK = c.tmem + 192;
+  const uint32_t tS = c.tmem, tdP = c.tmem + 64, tdV = c.tmem + 128, tdK = c.tmem + 128 + 2 * DH;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t idesc_s = make_idesc_tf32(128, A2_BLK, 0, 0);
-  const uint32_t idesc_o = make_idesc_tf32(128, X3 ? 2 * A2_DH : A2_DH, 0, 1);
+  const uint32_t idesc_o = make_idesc_tf32(128, X3 ? 2 * DH : DH, 0, 1);
   const float c1 = a.scale * A2_LOG2E;
   const int kw = j0 + (warp & 3) * 32;               // first key of this warp
 
@@ -616,15 +650,15 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
     const int i0 = ib * A2_BLK;
     mbar_wait(bar_a, ph);
     if (X3) {
-      a2_split(gA, gA + A2_T64, A2_T64);
-      a2_split(gB, gB + A2_T64, A2_T64);
+      a2_split(gA, gA + T64, T64);
+      a2_split(gB, gB + T64, T64);
     }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      a2_mma_ss<X3>(tS, sK, sKl, sA, sAl, idesc_s);      // S^T  = K Q^T
-      a2_mma_ss<X3>(tdP, sV, sVl, sB, sBl, idesc_s);     // dP^T = V dO^T
+      a2_mma_ss<X3, NC>(tS, sK, sKl, sA, sAl, idesc_s, A2_T128, A2_T64);      // S^T  = K Q^T
+      a2_mma_ss<X3, NC>(tdP, sV, sVl, sB, sBl, idesc_s, A2_T128, A2_T64);     // dP^T = V dO^T
       tc_commit(bar_s);
     }
     mbar_wait(bar_s, ph);
@@ -632,8 +666,11 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
     // the score MMAs are done with the K-major Q / dO blocks: re-swizzle them in place (raw and lo tiles, one
     // thread per 128-byte row) into the MN-major layout the output MMAs read
     {
-      uint8_t* tile = gA + (tid >> 6) * A2_T64;      // gA, gA lo, gB, gB lo are contiguous 64-row tiles
-      if (X3 || ((tid >> 6) & 1) == 0) a2_row_kmajor_to_mnmajor_inplace(tile, tid & 63);
+#pragma unroll
+      for (int cc = 0; cc < NC; cc++) {
+        const int ti = (tid >> 6) + 4 * cc;          // gA, gA lo, gB, gB lo: 4 NC contiguous 64-row chunk tiles
+        if (X3 || ((ti / NC) & 1) == 0) a2_row_kmajor_to_mnmajor_inplace(gA + ti * A2_T64, tid & 63);
+      }
     }
     {
       uint32_t rs[32], rp[32];
@@ -681,46 +718,49 @@ attn2_bwd_dkv_k(const __grid_constant__ CUtensorMap mK, const __grid_constant__ 
     mbar_wait(bar_o, ph);
     tc_fence_after();
     if (tid == 0 && ib + 1 < nqb) {
-      mbar_arrive_expect_tx(bar_a, 2 * A2_T64);
-      tma_load_2d(sA, &mQ, bar_a, h * A2_DH, b * a.Tq + i0 + A2_BLK);
-      tma_load_2d(sB, &mdO, bar_a, h * A2_DH, b * a.Tq + i0 + A2_BLK);
+      mbar_arrive_expect_tx(bar_a, 2 * T64);
+      a2_load<NC>(sA, &mQ, bar_a, h * DH, b * a.Tq + i0 + A2_BLK, A2_BLK);
+      a2_load<NC>(sB, &mdO, bar_a, h * DH, b * a.Tq + i0 + A2_BLK, A2_BLK);
     }
   }
   {
     // warpgroup 0 stores dK (scaled by 1/sqrt(dh)), warpgroup 1 stores dV
     uint32_t r[32];
-    __syncwarp();
-    if (it > 0) {
-      tmem_ld32((wg == 0 ? tdK : tdV) + lane_off, r);
-      if (X3) {
-        uint32_t rl[32];
-        tmem_ld32((wg == 0 ? tdK : tdV) + lane_off + 32, rl);
+#pragma unroll
+    for (int cc = 0; cc < NC; cc++) {
+      __syncwarp();
+      if (it > 0) {
+        tmem_ld32((wg == 0 ? tdK : tdV) + lane_off + 32 * cc, r);
+        if (X3) {
+          uint32_t rl[32];
+          tmem_ld32((wg == 0 ? tdK : tdV) + lane_off + DH + 32 * cc, rl);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 32; jj++) r[jj] = __float_as_uint(__uint_as_float(r[jj]) + __uint_as_float(rl[jj]));
+        }
         tmem_ld_wait();
+      } else {
 #pragma unroll
-        for (int jj = 0; jj < 32; jj++) r[jj] = __float_as_uint(__uint_as_float(r[jj]) + __uint_as_float(rl[jj]));
+        for (int jj = 0; jj < 32; jj++) r[jj] = 0u;
       }
-      tmem_ld_wait();
-    } else {
+      if (kj < a.Tk) {
+        const float sc = wg == 0 ? a.scale : 1.0f;
+        float* base = wg == 0 ? a.out0 + ((int64_t)b * a.Tk + kj) * a.ld0 : a.out1 + ((int64_t)b * a.Tk + kj) * a.ld1;
+        float4* dst = reinterpret_cast<float4*>(base + h * DH + 32 * cc);
 #pragma unroll
-      for (int jj = 0; jj < 32; jj++) r[jj] = 0u;
-    }
-    if (kj < a.Tk) {
-      const float sc = wg == 0 ? a.scale : 1.0f;
-      float* base = wg == 0 ? a.out0 + ((int64_t)b * a.Tk + kj) * a.ld0 : a.out1 + ((int64_t)b * a.Tk + kj) * a.ld1;
-      float4* dst = reinterpret_cast<float4*>(base + h * A2_DH);
-#pragma unroll
-      for (int jj = 0; jj < 8; jj++)
-        dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * sc, __uint_as_float(r[4 * jj + 1]) * sc,
-                              __uint_as_float(r[4 * jj + 2]) * sc, __uint_as_float(r[4 * jj + 3]) * sc);
+        for (int jj = 0; jj < 8; jj++)
+          dst[jj] = make_float4(__uint_as_float(r[4 * jj]) * sc, __uint_as_float(r[4 * jj + 1]) * sc,
+                                __uint_as_float(r[4 * jj + 2]) * sc, __uint_as_float(r[4 * jj + 3]) * sc);
+      }
     }
   }
-  a2_free<256>(c);
+  a2_free<TCOLS>(c);
 }
 
 // ---- host --------------------------------------------------------------------------------------
 int attn2_supported(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, int Tq,
                     int Tk, int dh) {
-  if (dh != A2_DH) return 0;
+  if (dh != 32 && dh != 64) return 0;
   if (Tk > A2_MAXT || Tq > A2_MAXT || Tq < 1 || Tk < 1) return 0;
   if ((ldq | ldk | ldv) & 3) return 0;
   if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) | reinterpret_cast<uintptr_t>(V)) & 15) return 0;
@@ -728,16 +768,47 @@ int attn2_supported(const float* Q, int64_t ldq, const float* K, int64_t ldk, co
 }
 
 // rows: box height (128 for the lane-side operand, 64 for the streamed one); conv: TMA rounds to TF32
-static int a2_map(CUtensorMap* m, const float* p, int64_t ld, int H, int64_t nrows, int rows, bool mn, bool conv) {
-  return make_tmap_2d_typed(m, p, (uint64_t)H * A2_DH, (uint64_t)nrows, (uint64_t)ld, A2_DH, (uint32_t)rows, mn, conv);
-}
-
 template <class Kern>
 static int a2_attr(Kern k, int bytes) {
   SKF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   SKF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   return SKF_OK;
 }
+
+static int g_a2_dh = 32;   // head dim of the maps being built (set by attn2_fwd / attn2_bwd; host-side, single-threaded per call)
+static int a2_map(CUtensorMap* m, const float* p, int64_t ld, int H, int64_t nrows, int rows, bool mn, bool conv) {
+  return make_tmap_2d_typed(m, p, (uint64_t)H * g_a2_dh, (uint64_t)nrows, (uint64_t)ld, A2_DH, (uint32_t)rows, mn, conv);
+}
+
+template <class Kern, class... Args>
+static int a2_launch(Kern k, bool& attr_done, dim3 grid, int threads, int smem, cudaStream_t st, const Args&... args) {
+  if (!attr_done) { SKF_TRY(a2_attr(k, smem)); attr_done = true; }
+  k<<<grid, threads, smem, st>>>(args...);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+// one instantiation per (X3, DH); `done` flags are per instantiation
+template <bool X3, int DH>
+static int a2_fwd_launch(dim3 grid, cudaStream_t st, const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV,
+                         const Attn2Args& a) {
+  static bool done = false;
+  return a2_launch(attn2_fwd_k<X3, DH>, done, grid, 128, a2f_data(DH / A2_DH) + 1024 + 128, st, mQ, mK, mV, a);
+}
+template <bool X3, int DH>
+static int a2_dq_launch(dim3 grid, cudaStream_t st, const CUtensorMap& mQ, const CUtensorMap& mdO, const CUtensorMap& mK,
+                        const CUtensorMap& mV, const CUtensorMap& mO, const Attn2Args& a) {
+  static bool done = false;
+  return a2_launch(attn2_bwd_dq_k<X3, DH>, done, grid, 256, a2q_data(DH / A2_DH) + 1024 + 128, st, mQ, mdO, mK, mV, mO, a);
+}
+template <bool X3, int DH>
+static int a2_dkv_launch(dim3 grid, cudaStream_t st, const CUtensorMap& mK, const CUtensorMap& mV, const CUtensorMap& mQ,
+                         const CUtensorMap& mdO, const Attn2Args& a) {
+  static bool done = false;
+  return a2_launch(attn2_bwd_dkv_k<X3, DH>, done, grid, 256, a2k_data(DH / A2_DH) + 1024 + 128, st, mK, mV, mQ, mdO, a);
+}
+#define A2_DISPATCH(fn, ...)                                                        \
+  (dh == 32 ? (x3 ? fn<true, 32>(__VA_ARGS__) : fn<false, 32>(__VA_ARGS__))        \
+            : (x3 ? fn<true, 64>(__VA_ARGS__) : fn<false, 64>(__VA_ARGS__)))
 
 int attn2_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, float* O,
               int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh, int mode, int x3,
@@ -746,6 +817,7 @@ int attn2_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   SKF_REQUIRE((ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, SKF_ERR_BAD_ALIGN, "attn2_fwd: O");
   SKF_REQUIRE(mode == 0 || key_pad != nullptr || mode == 2, SKF_ERR_BAD_ARG, "attn2_fwd: mode 1 needs key_pad");
   CUtensorMap mQ, mK, mV;
+  g_a2_dh = dh;
   SKF_TRY(a2_map(&mQ, Q, ldq, H, (int64_t)B * Tq, 128, false, !x3));
   SKF_TRY(a2_map(&mK, K, ldk, H, (int64_t)B * Tk, A2_BLK, false, !x3));
   SKF_TRY(a2_map(&mV, V, ldv, H, (int64_t)B * Tk, A2_BLK, true, !x3));
@@ -753,19 +825,8 @@ int attn2_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   memset(&a, 0, sizeof(a));
   a.H = H; a.Tq = Tq; a.Tk = Tk; a.mode = mode; a.scale = 1.0f / sqrtf((float)dh);
   a.key_pad = key_pad; a.out0 = O; a.ld0 = ldo; a.out1 = lse;
-  const int smem = A2F_DATA + 1024 + 128;
   dim3 grid(cdiv(Tq, 128), H, B);
-  if (x3) {
-    static bool done = false;
-    if (!done) { SKF_TRY(a2_attr(attn2_fwd_k<true>, smem)); done = true; }
-    attn2_fwd_k<true><<<grid, 128, smem, st>>>(mQ, mK, mV, a);
-  } else {
-    static bool done = false;
-    if (!done) { SKF_TRY(a2_attr(attn2_fwd_k<false>, smem)); done = true; }
-    attn2_fwd_k<false><<<grid, 128, smem, st>>>(mQ, mK, mV, a);
-  }
-  SKF_LAUNCH_CHECK();
-  return SKF_OK;
+  return A2_DISPATCH(a2_fwd_launch, grid, st, mQ, mK, mV, a);
 }
 
 int attn2_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, const float* O,
@@ -778,52 +839,30 @@ int attn2_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
                     reinterpret_cast<uintptr_t>(dV) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
               SKF_ERR_BAD_ALIGN, "attn2_bwd: alignment");
   const bool conv = !x3;
-  CUtensorMap mQ128, mdO128, mO128, mK64, mV64, mK64mn, mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn;
+  CUtensorMap mQ128, mdO128, mO128, mK64, mV64, mK128, mV128, mQ64, mdO64;
+  g_a2_dh = dh;
   SKF_TRY(a2_map(&mO128, O, ldo, H, (int64_t)B * Tq, 128, false, false));
   SKF_TRY(a2_map(&mQ128, Q, ldq, H, (int64_t)B * Tq, 128, false, conv));
   SKF_TRY(a2_map(&mdO128, dO, lddo, H, (int64_t)B * Tq, 128, false, conv));
   SKF_TRY(a2_map(&mK64, K, ldk, H, (int64_t)B * Tk, A2_BLK, false, conv));
   SKF_TRY(a2_map(&mV64, V, ldv, H, (int64_t)B * Tk, A2_BLK, false, conv));
-  SKF_TRY(a2_map(&mK64mn, K, ldk, H, (int64_t)B * Tk, A2_BLK, true, conv));
   SKF_TRY(a2_map(&mK128, K, ldk, H, (int64_t)B * Tk, 128, false, conv));
   SKF_TRY(a2_map(&mV128, V, ldv, H, (int64_t)B * Tk, 128, false, conv));
   SKF_TRY(a2_map(&mQ64, Q, ldq, H, (int64_t)B * Tq, A2_BLK, false, conv));
   SKF_TRY(a2_map(&mdO64, dO, lddo, H, (int64_t)B * Tq, A2_BLK, false, conv));
-  SKF_TRY(a2_map(&mQ64mn, Q, ldq, H, (int64_t)B * Tq, A2_BLK, true, conv));
-  SKF_TRY(a2_map(&mdO64mn, dO, lddo, H, (int64_t)B * Tq, A2_BLK, true, conv));
   Attn2Args a;
   memset(&a, 0, sizeof(a));
   a.H = H; a.Tq = Tq; a.Tk = Tk; a.mode = mode; a.scale = 1.0f / sqrtf((float)dh); a.key_pad = key_pad;
   a.lse = lse; a.O = O; a.ldO = ldo; a.dO = dO; a.lddO = lddo;
   {
-    const int smem = A2Q_DATA + 1024 + 128;
     a.out0 = dQ; a.ld0 = lddq; a.out1 = delta;
     dim3 grid(cdiv(Tq, 128), H, B);
-    if (x3) {
-      static bool done = false;
-      if (!done) { SKF_TRY(a2_attr(attn2_bwd_dq_k<true>, smem)); done = true; }
-      attn2_bwd_dq_k<true><<<grid, 256, smem, st>>>(mQ128, mdO128, mK64, mV64, mO128, a);
-    } else {
-      static bool done = false;
-      if (!done) { SKF_TRY(a2_attr(attn2_bwd_dq_k<false>, smem)); done = true; }
-      attn2_bwd_dq_k<false><<<grid, 256, smem, st>>>(mQ128, mdO128, mK64, mV64, mO128, a);
-    }
-    SKF_LAUNCH_CHECK();
+    SKF_TRY(A2_DISPATCH(a2_dq_launch, grid, st, mQ128, mdO128, mK64, mV64, mO128, a));
   }
   {
-    const int smem = A2K_DATA + 1024 + 128;
     a.out0 = dK; a.ld0 = lddk; a.out1 = dV; a.ld1 = lddv; a.delta = delta;
     dim3 grid(cdiv(Tk, 128), H, B);
-    if (x3) {
-      static bool done = false;
-      if (!done) { SKF_TRY(a2_attr(attn2_bwd_dkv_k<true>, smem)); done = true; }
-      attn2_bwd_dkv_k<true><<<grid, 256, smem, st>>>(mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn, a);
-    } else {
-      static bool done = false;
-      if (!done) { SKF_TRY(a2_attr(attn2_bwd_dkv_k<false>, smem)); done = true; }
-      attn2_bwd_dkv_k<false><<<grid, 256, smem, st>>>(mK128, mV128, mQ64, mdO64, mQ64mn, mdO64mn, a);
-    }
-    SKF_LAUNCH_CHECK();
+    SKF_TRY(A2_DISPATCH(a2_dkv_launch, grid, st, mK128, mV128, mQ64, mdO64, a));
   }
   return SKF_OK;
 }

@@ -319,9 +319,17 @@ TC_ATTN = [(3, 8, 200, 200, 32, 1), (3, 8, 199, 199, 32, 2), (3, 8, 199, 200, 32
 TOL_ATTN_X3 = 3e-4
 
 
-@pytest.mark.parametrize("B,H,Tq,Tk,dh,mode", TC_ATTN + [(2, 8, 256, 256, 32, 2), (2, 2, 1, 200, 32, 1), (3, 4, 65, 64, 32, 0)])
+# head dim 64 (two 128-byte chunks per tile) and sequences up to 1024 (cfg5: d 512, 8 heads, T 512)
+TC_ATTN_WIDE = [(2, 8, 130, 131, 64, 2), (2, 2, 70, 257, 64, 1), (2, 3, 200, 200, 64, 0), (1, 8, 512, 512, 64, 2),
+                (1, 2, 512, 512, 64, 1), (1, 2, 1000, 1000, 32, 2), (1, 1, 300, 1024, 64, 1), (2, 2, 1, 65, 64, 1)]
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,mode", TC_ATTN + TC_ATTN_WIDE +
+                         [(2, 8, 256, 256, 32, 2), (2, 2, 1, 200, 32, 1), (3, 4, 65, 64, 32, 0)])
 def test_attention_tcgen05(lib, B, H, Tq, Tk, dh, mode):
     """flash-style tcgen05 kernels: fp32-grade (backend 2) and single-pass TF32 (backend 0)."""
+    if mode == 2 and Tq != Tk:
+        Tk = Tq
     errs = _attn_case(lib, B, H, Tq, Tk, dh, mode, 200 + Tq, fwd_backend=2, bwd_backend=2)
     assert max(errs) < TOL_ATTN_X3, errs
     errs = _attn_case(lib, B, H, Tq, Tk, dh, mode, 300 + Tq, fwd_backend=0, bwd_backend=0)
