@@ -112,11 +112,19 @@ class Engine:
 
     def load_params(self, named: Dict[str, torch.Tensor]):
         """Import tensors named as in oracle/sketchformer_oracle.py (Keras shapes, kernel=(in,out))."""
+        self._import(self.params, named)
+
+    def load_adam(self, m: Dict[str, torch.Tensor], v: Dict[str, torch.Tensor]):
+        """Adam first / second moments, same naming and shapes as load_params()."""
+        self._import(self.adam_m, m)
+        self._import(self.adam_v, v)
+
+    def _import(self, arena, named):
         seen = set()
         for name, val in named.items():
             tname, sl = self._map(name)
-            dst = self._view(self.params, tname)
-            v = val.detach().to(torch.float32)
+            dst = self._view(arena, tname)
+            v = torch.as_tensor(val).detach().to(torch.float32)
             if name == "pool.V" or v.dim() == 1:
                 v = v.reshape(1, -1)
             v = v.to(self.device)
@@ -141,6 +149,9 @@ class Engine:
 
     def export_params(self, like):
         return self._export(self.params, like)
+
+    def export_adam(self, like):
+        return self._export(self.adam_m, like), self._export(self.adam_v, like)
 
     def export_grads(self, like):
         return self._export(self.grads, like)

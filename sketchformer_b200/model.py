@@ -12,6 +12,7 @@ import os
 import numpy as np
 import torch
 
+from . import evaluation, tf_checkpoint
 from .engine import Engine, make_cfg
 from .hparams import HParams, combine_hparams_into_one
 from .init import init_params
@@ -128,6 +129,11 @@ class Transformer:
                         class_buffer_layers=h["class_buffer_layers"], class_dropout=h["class_dropout"],
                         dropout_seed=(0x5EED + 7919 * self._seed + 104729 * self._rank) & 0xFFFFFFFF, **kw)
 
+    def _layout_hps(self):
+        """model + data hparams that decide which variables exist and their shapes (init.py, tf_checkpoint.key_map)"""
+        return dict(self.hps, max_seq_len=self.seq_len, vocab_size=self.vocab_size, n_classes=self.dataset.n_classes,
+                    use_continuous_data=self.continuous)
+
     def _engine(self, B, training=False):
         """One plan per batch size; all plans share the parameter arena of the training plan."""
         if B in self._engines:
@@ -137,9 +143,7 @@ class Transformer:
                      share_from=None if first else self._train_engine)
         if first:
             self._train_engine = eng
-            eng.load_params(init_params(dict(self.hps, max_seq_len=self.seq_len, vocab_size=self.vocab_size,
-                                             n_classes=self.dataset.n_classes,
-                                             use_continuous_data=self.continuous), seed=self._seed))
+            eng.load_params(init_params(self._layout_hps(), seed=self._seed))
         self._engines[B] = eng
         return eng
 
@@ -376,13 +380,49 @@ class Transformer:
             d = getattr(self, "wgt_out_dir", None)
             cands = sorted((f for f in (os.listdir(d) if d else []) if f.endswith(".pt")),
                            key=lambda f: os.path.getmtime(os.path.join(d, f)))
-            if not cands:
+            tf_prefix = tf_checkpoint.latest_checkpoint(d) if d and not cands else None
+            if not cands and tf_prefix is None:
                 print("[Checkpoint] Not found")
                 return False
-            checkpoint = os.path.join(d, cands[-1])
+            checkpoint = os.path.join(d, cands[-1]) if cands else tf_prefix
+        if os.path.exists(checkpoint + ".index"):       # a TensorFlow tensor bundle written by the reference
+            self.load_tf_checkpoint(checkpoint)
+            print("[Checkpoint] Restored, step #{}".format(self.current_step))
+            return True
         self.load_state_dict(torch.load(checkpoint, map_location="cpu", weights_only=False))
         print("[Checkpoint] Restored, step #{}".format(self.current_step))
         return True
+
+    # ---- prediction sweeps for the slow metrics (models/evaluation_mixin.py:10-53) ----------------------
+    def compute_predictions_on_validation_set(self):
+        return evaluation.compute_predictions_on_set(self, "valid")
+
+    def compute_predictions_on_test_set(self):
+        return evaluation.compute_predictions_on_set(self, "test")
+
+    def compute_predictions_on_set(self, set_type):
+        return evaluation.compute_predictions_on_set(self, set_type)
+
+    # ---- TensorFlow checkpoints of the reference (core/models.py:321-344) ---------------------------
+    def load_tf_checkpoint(self, prefix):
+        """Weights, Adam moments and step counters from `tf.train.Checkpoint(transformer=, optimizer=)` files."""
+        params, m, v, info = tf_checkpoint.import_checkpoint(prefix, self._layout_hps())
+        e = self._train_engine
+        e.load_params(params)
+        if m and v:
+            e.load_adam(m, v)
+        if "optimizer_iter" in info:
+            e.set_step(info["optimizer_iter"])
+        self.current_step = info.get("current_step", info.get("optimizer_iter", self.current_step))
+
+    def save_tf_checkpoint(self, prefix):
+        e = self._train_engine
+        like = init_params(self._layout_hps(), 0)
+        m, v = e.export_adam(like)
+        tf_checkpoint.export_checkpoint(prefix, self._layout_hps(), {k: t.numpy() for k, t in e.export_params(like).items()},
+                                        {k: t.numpy() for k, t in m.items()}, {k: t.numpy() for k, t in v.items()},
+                                        current_step=self.current_step, optimizer_iter=e.step_count())
+        return prefix
 
     # ---- checkpoints (own format: the flat arenas + step) ------------------------------------
     def state_dict(self):

@@ -215,3 +215,40 @@ def test_train_loop_checkpoint_resume(tmp_path):
     assert a._train_engine.step_count() == c._train_engine.step_count() == 3006
     ma, mc = a._train_engine.metrics(), c._train_engine.metrics()
     assert all(abs(ma[k] - mc[k]) <= 1e-3 * max(abs(ma[k]), 1e-3) for k in ma), (ma, mc)
+
+
+@pytest.mark.gpu
+def test_tf_checkpoint_round_trip_through_the_model(tmp_path):
+    """save_tf_checkpoint -> fresh model -> restore_checkpoint_if_exists(prefix / 'latest'): weights, Adam moments
+    and both step counters come back under the reference's checkpoint keys (core/models.py:321-344)."""
+    from sketchformer_b200 import tf_checkpoint
+    from sketchformer_b200.data import get_dataloader_by_name
+    from sketchformer_b200.model import get_model_by_name
+    Model, Loader = get_model_by_name("sketch-transformer-tf2"), get_dataloader_by_name("stroke3-synthetic")
+    spec = "num_layers=2,d_model=64,dff=128,num_heads=4,lowerdim=32,dropout_rate=0.0"
+
+    def make(out, seed):
+        ds = Loader(Loader.parse_hparams("max_seq_len=24"), None, n_classes=10, n_samples=8, seed=3)
+        hps = Model.parse_hparams(base="batch_size=4,num_epochs=1,log_every=1", specific=spec)
+        return Model(hps, ds, str(out), "r", seed=seed)
+
+    a = make(tmp_path / "a", 1)
+    a._train_engine.set_step(3000)
+    batches = [b for _, b in zip(range(3), a.dataset.batch_iterator("train", 4))]
+    for b in batches[:2]:
+        a.train_on_batch(b)
+    a.current_step = 2
+    prefix = a.save_tf_checkpoint(os.path.join(a.wgt_out_dir, "ckpt-2"))
+    keys = tf_checkpoint.read_tensor_bundle(prefix)
+    assert "transformer/encoder/enc_layers/1/mha/wq/kernel/.ATTRIBUTES/VARIABLE_VALUE" in keys
+    assert "transformer/decoder/dec_layers/0/mha2/dense/bias/.OPTIMIZER_SLOT/optimizer/v/.ATTRIBUTES/VARIABLE_VALUE" in keys
+    assert int(keys["optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"]) == 3002
+    c = make(tmp_path / "a", 99)                         # different initial weights, same output directory
+    assert c.restore_checkpoint_if_exists("latest") and c.current_step == 2
+    ea, ec = a._train_engine, c._train_engine
+    assert torch.equal(ea.params, ec.params) and torch.equal(ea.adam_m, ec.adam_m) and torch.equal(ea.adam_v, ec.adam_v)
+    assert ec.step_count() == 3002
+    a.train_on_batch(batches[2]); c.train_on_batch(batches[2])     # (returned metrics are running means: not compared)
+    assert rel_err(ec.params, ea.params) < 1e-5
+    pa, pc = a.predict_class(batches[2][0]), c.predict_class(batches[2][0])
+    assert np.array_equal(pa["class"], pc["class"])

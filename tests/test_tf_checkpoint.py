@@ -1,0 +1,115 @@
+"""TensorFlow tensor-bundle reader / writer (sketchformer_b200/tf_checkpoint.py): table format known answers,
+round trips, and the reference's object-graph key layout (core/models.py:321-331)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from sketchformer_b200 import tf_checkpoint as T
+from sketchformer_b200.init import init_params
+
+HPS = dict(num_layers=2, d_model=32, dff=64, num_heads=4, lowerdim=16, max_seq_len=12, vocab_size=50, n_classes=7)
+
+
+def test_crc32c_known_answers():
+    # RFC 3720 B.4 test vectors
+    assert T.crc32c(b"123456789") == 0xE3069283
+    assert T.crc32c(b"\x00" * 32) == 0x8A9136AA
+    assert T.crc32c(b"\xff" * 32) == 0x62A8AB43
+    assert T.crc32c(bytes(range(32))) == 0x46DD794E
+    # LevelDB mask: rotate right 15, add constant
+    assert T.mask_crc(0) == 0xA282EAD8
+    assert T.mask_crc(0xE3069283) == ((((0xE3069283 >> 15) | (0xE3069283 << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def test_snappy_known_answers():
+    # literal "abcd", then copy (1-byte offset form) of 4 bytes from offset 4, then a self-overlapping run
+    assert T.snappy_uncompress(bytes([8, 0x0C]) + b"abcd" + bytes([0x01, 0x04])) == b"abcdabcd"
+    assert T.snappy_uncompress(bytes([9, 0x00]) + b"x" + bytes([(7 << 2) | 2, 1, 0])) == b"x" * 9
+    with pytest.raises(ValueError):
+        T.snappy_uncompress(bytes([4, 0x01, 0x09]))
+
+
+def test_hand_assembled_table(tmp_path):
+    """A table built byte by byte here (prefix compression, two data blocks), independent of write_table()."""
+    def block(entries, restarts):
+        b = b"".join(bytes([s, len(k), len(v)]) + k + v for s, k, v in entries)
+        return b + b"".join(struct.pack("<I", r) for r in restarts) + struct.pack("<I", len(restarts))
+
+    def framed(b):
+        return b + b"\x00" + struct.pack("<I", T.mask_crc(T.crc32c(b + b"\x00")))
+
+    b0 = block([(0, b"apple", b"1"), (3, b"ly", b"22"), (0, b"bar", b"")], [0, 15])   # apple, apply, bar
+    b1 = block([(0, b"cat", b"333")], [0])
+    meta = block([], [0])
+    out = framed(b0)
+    o1 = len(out); out += framed(b1)
+    om = len(out); out += framed(meta)
+    idx = block([(0, b"bar", bytes([0, len(b0)])), (0, b"d", bytes([o1, len(b1)]))], [0, 6])
+    oi = len(out); out += framed(idx)
+    foot = bytes([om, len(meta), oi, len(idx)])
+    out += foot + b"\x00" * (40 - len(foot)) + struct.pack("<Q", T.TABLE_MAGIC)
+    p = tmp_path / "t.index"
+    p.write_bytes(out)
+    assert T.read_table(str(p)) == [(b"apple", b"1"), (b"apply", b"22"), (b"bar", b""), (b"cat", b"333")]
+    bad = bytearray(out); bad[2] ^= 1
+    p.write_bytes(bytes(bad))
+    with pytest.raises(ValueError):
+        T.read_table(str(p))
+
+
+def test_bundle_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    tensors = {f"transformer/layer/{i}/kernel{T.SUFFIX}": rng.standard_normal((i + 1, 3)).astype(np.float32)
+               for i in range(300)}                                   # several index blocks
+    tensors["optimizer/iter" + T.SUFFIX] = np.asarray(1234567890123, dtype=np.int64)
+    tensors["scalar_f64"] = np.asarray(2.5)
+    tensors["empty"] = np.zeros((0, 4), dtype=np.float32)
+    prefix = str(tmp_path / "ckpt-3")
+    T.write_tensor_bundle(prefix, tensors)
+    back = T.read_tensor_bundle(prefix, verify_tensors=True)
+    assert sorted(back) == sorted(tensors)
+    for k, v in tensors.items():
+        assert back[k].dtype == v.dtype and back[k].shape == v.shape and np.array_equal(back[k], v), k
+    # the entry of one tensor, decoded by hand: dtype DT_FLOAT, dims, size
+    entries = dict(T.read_table(prefix + ".index"))
+    e = T._parse_entry(entries[f"transformer/layer/4/kernel{T.SUFFIX}".encode()])
+    assert e["dtype"] == 1 and e["shape"] == [5, 3] and e["size"] == 60 and e["shard_id"] == 0
+    # a flipped data byte is caught by the tensor crc
+    with open(prefix + ".data-00000-of-00001", "r+b") as f:
+        f.seek(5); b = f.read(1); f.seek(5); f.write(bytes([b[0] ^ 0x40]))
+    with pytest.raises(ValueError):
+        T.read_tensor_bundle(prefix, verify_tensors=True)
+
+
+@pytest.mark.parametrize("extra", [dict(), dict(use_continuous_data=True), dict(attn_version=2, class_buffer_layers=2),
+                                   dict(lowerdim=0, do_classification=False), dict(do_reconstruction=False)])
+def test_key_map_covers_every_variable(extra):
+    hps = dict(HPS, **extra)
+    params = init_params(hps, 0)
+    km = T.key_map(hps)
+    assert sorted(km) == sorted(params)
+    assert len(set(km.values())) == len(km)
+    if not extra:
+        assert km["enc.l1.mha.wo.k"] == "transformer/encoder/enc_layers/1/mha/dense/kernel"
+        assert km["dec.l0.ffn.w2.b"] == "transformer/decoder/dec_layers/0/ffn/layer_with_weights-1/bias"
+        assert km["dec.l1.ln3.g"] == "transformer/decoder/dec_layers/1/layernorm3/gamma"
+        assert km["pool.V"] == "transformer/bottleneck_layer/V"
+        assert km["exp.k"] == "transformer/expand_layer/expand_layer/kernel"
+        assert km["enc.emb"] == "transformer/encoder/embedding/embeddings"
+
+
+def test_checkpoint_export_import(tmp_path):
+    params = {k: v.numpy() for k, v in init_params(HPS, 3).items()}
+    m = {k: v * 0.5 for k, v in params.items()}
+    v = {k: v * v for k, v in params.items()}
+    prefix = str(tmp_path / "weights" / "ckpt-7")
+    T.export_checkpoint(prefix, HPS, params, m, v, current_step=699, optimizer_iter=700)
+    assert T.latest_checkpoint(str(tmp_path / "weights")) == prefix
+    p2, m2, v2, info = T.import_checkpoint(prefix, HPS)
+    assert info == {"current_step": 699, "optimizer_iter": 700}
+    for k in params:
+        assert np.array_equal(p2[k], params[k]) and np.array_equal(m2[k], m[k]) and np.array_equal(v2[k], v[k])
+    with pytest.raises(KeyError):
+        T.import_checkpoint(prefix, dict(HPS, num_layers=3))
