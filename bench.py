@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--precision", type=int, default=-1,
                     help="tensor-core GEMM passes: 0 TF32 everywhere, 1 3xTF32 forward, 2 3xTF32 everywhere (default: engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--set", action="append", default=[], metavar="NAME=INT",
+                    help="library switch for A/B runs (skf_set_option), e.g. --set wgrad_overlap=0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -151,6 +153,10 @@ def main():
     from sketchformer_b200.data import get_dataloader_by_name
     from sketchformer_b200.model import get_model_by_name
 
+    for kv in args.set:
+        from sketchformer_b200 import _lib
+        k, v = kv.split("=")
+        _lib.check(_lib.load().skf_set_option(k.encode(), int(v)), "skf_set_option")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

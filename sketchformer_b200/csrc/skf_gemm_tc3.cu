@@ -16,6 +16,9 @@
 //   * A operand from tensor memory (tcgen05.mma TS form, 256 x 128 cluster tiles): correct, 70 us on FFN-1
 //     (more L2 traffic per FLOP), 1-3 % faster only for N = 256;
 //   * 8 splitter warps, TMA L2 prefetch of the next tile: no change.
+//   * bf16 hi / lo images of the weights prepared once per step and TMA-loaded into the stage's bf16 B tiles
+//     (the splitter then converts only A): with the B conversion merely skipped the kernel is 8-13 % faster,
+//     but the extra 16 KB of TMA writes per stage give it back (FFN-1 58.4 -> 58.1 us, dgrads 2-7 %, step 0.5 %).
 //
 //   cluster tile = 256 (M) x 256 (N); CTA r of the pair owns rows [128 r, 128 r + 128) of A and of the
 //   accumulator (its own TMEM) and stages columns [128 r, 128 r + 128) of B.
@@ -175,8 +178,13 @@ __device__ __forceinline__ void t3_split_bf16(const uint8_t* src, uint8_t* hi16,
     const int rs = MN ? (r & 31) : r;                 // row index the swizzles see (boxes are 4 KB / 2 KB aligned)
     const uint32_t sx = MN ? (uint32_t)((rs & 3) << 1) : (uint32_t)(rs & 7);
     const uint8_t* rowp = src + r * 128;
-    const float4 u = *reinterpret_cast<const float4*>(rowp + (((2 * g) ^ sx) << 4));
-    const float4 v = *reinterpret_cast<const float4*>(rowp + (((2 * g + 1) ^ sx) << 4));
+    // the 4 lanes of a row read its 4 even chunks, then its 4 odd ones; under the 128B swizzle consecutive rows
+    // flip parity, but the 32B-atom swizzle keeps it, so there odd rows read their odd chunks first (two rows of a
+    // quarter-warp then never meet in a bank)
+    const uint32_t first = (MN && (r & 1)) ? 1u : 0u;
+    const float4 w0 = *reinterpret_cast<const float4*>(rowp + (((2 * g + first) ^ sx) << 4));
+    const float4 w1 = *reinterpret_cast<const float4*>(rowp + (((2 * g + 1 - first) ^ sx) << 4));
+    const float4 u = first ? w1 : w0, v = first ? w0 : w1;
     uint4 h, l;
     t3_to_bf16_pair(u, v, h, l);
     const uint32_t dof = r * 64 + ((g ^ ((rs >> 1) & 3)) << 4);
@@ -576,6 +584,8 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 static int g3_clusters = 0;
 int g_gemm_mix = 1;       // 1: cross terms of the 3xTF32 product as bf16 MMAs (see gemm3_k MIX)
 
+int g_t3_oversubscribe = 0;
+
 template <int BN, bool A_MN, bool B_MN, bool MIX>
 static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t st) {
   constexpr int T3_SMEM = Tc3Cfg<BN>::SMEM;
@@ -601,7 +611,10 @@ static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t 
     g3_clusters = nc < 1 ? 1 : nc;
   }
   const int ntiles = p.mt * p.nt * p.splits;
-  const int ncl = ntiles < g3_clusters ? ntiles : g3_clusters;
+  // g_t3_oversubscribe (set by the plan around launches on its low-priority side stream): one cluster per work
+  // unit instead of a persistent grid, so that the units are short and a higher-priority kernel waiting for SMs
+  // gets them after one unit, not after a cluster's whole share
+  const int ncl = (ntiles < g3_clusters || g_t3_oversubscribe) ? ntiles : g3_clusters;
   gemm3_k<BN, A_MN, B_MN, MIX><<<2 * ncl, T3_THREADS, T3_SMEM, st>>>(tm[0], tm[1], tm[2], p);
   SKF_LAUNCH_CHECK();
   return SKF_OK;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "skf_common.cuh"
@@ -26,6 +27,9 @@ int gemm_tc3(const float*, int64_t, int64_t, const float*, int64_t, int64_t, flo
              const skf_gemm_epilogue*, cudaStream_t);
 int gemm_tc3_wanted(int, int, int);
 int g_gemm_pair = 1;
+int g_wgrad_units = 1;     // side-stream wgrads: work units per cluster slot (finer units yield SMs sooner)
+extern int g_t3_oversubscribe;
+int g_wgrad_overlap = 1;   // weight-gradient GEMMs of the backward pass on a second stream (see SideQueue)
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
 int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
 int attn_fwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
@@ -290,6 +294,7 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
   W.add("g.b", Me * d * F);
   W.add("g.c", Me * d * F);
   W.add("g.d", Me * d * F);
+  for (const char* n : {"g.b1", "g.b2", "g.d1", "g.d2"}) W.add(n, Me * d * F);   // one (g.b, g.d) pair per LayerNorm site
   W.add("g.h", Me * f * F);
   W.add("g.qkv", Me * 3 * d * F);
   W.add("g.q2", Me * d * F);
@@ -318,6 +323,20 @@ struct skf_plan {
   bool training = false;   // inside skf_train_step: Dropout layers are active (training=True)
   int64_t gen_sos = 0, gen_eos = 0;   // greedy decode: start / stop token ids (utils/tokenizer.py:29-33)
   bool gen_ready = false;
+  // Backward pass, second stream: dW = X^T dY is off the critical path (nothing reads it before the optimizer),
+  // so it is issued on `side` behind an event and fills the SMs the main chain leaves idle in the last wave of its
+  // persistent GEMMs and attention kernels.  `pending` maps a gradient buffer to the event after which the side
+  // stream no longer reads it; the main chain waits on it before it overwrites the buffer.
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t ev_next = 0;
+  std::unordered_map<const void*, cudaEvent_t> pending;
+  bool side_active = false;
+  cudaEvent_t next_event() { return events[ev_next++ % events.size()]; }
+  ~skf_plan() {
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    if (side) cudaStreamDestroy(side);
+  }
 
   float* wsf(const std::string& n) const { return reinterpret_cast<float*>(ws + W.t.at(n).off); }
   template <class T>
@@ -402,6 +421,7 @@ struct Gemm {
                          : tc ? (long)cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256))
                               : (long)cdiv(M, 64) * cdiv(N, 64);
       int want = (int)((pair ? 74 : tc ? 148 : 2 * 148) / tiles);
+      if (pair && st == P->side && st != nullptr) want = (int)((long)74 * g_wgrad_units / tiles);
       int maxs = K / 256 > 0 ? K / 256 : 1;
       e.split_k = want < 1 ? 1 : (want > maxs ? maxs : want);
     }
@@ -438,6 +458,43 @@ struct Gemm {
     if (fused) e.colsum = db;
     SKF_TRY(run(X, 1, K, dY, N, 1, dW, N, K, N, M, e, x3));
     if (db && !fused) SKF_TRY(skf_colsum(dY, N, db, M, N, st));
+    return SKF_OK;
+  }
+  // wgrad on the plan's side stream, ordered after everything issued so far on `st`
+  int wgrad_async(const float* X, const float* dY, float* dW, float* db, int M, int N, int K) const {
+    skf_plan* Q = const_cast<skf_plan*>(P);
+    if (!Q->side_active) return wgrad(X, dY, dW, db, M, N, K);
+    cudaEvent_t ready = Q->next_event();
+    SKF_CUDA(cudaEventRecord(ready, st));
+    SKF_CUDA(cudaStreamWaitEvent(Q->side, ready, 0));
+    Gemm S{P, Q->side};
+    g_t3_oversubscribe = g_wgrad_units > 1;
+    const int rc = S.wgrad(X, dY, dW, db, M, N, K);
+    g_t3_oversubscribe = 0;
+    SKF_TRY(rc);
+    cudaEvent_t done = Q->next_event();
+    SKF_CUDA(cudaEventRecord(done, Q->side));
+    Q->pending[dY] = done;
+    return SKF_OK;
+  }
+  // the main chain is about to overwrite `buf`: wait until the side stream has read it
+  int before_write(const void* buf) const {
+    skf_plan* Q = const_cast<skf_plan*>(P);
+    auto it = Q->pending.find(buf);
+    if (it == Q->pending.end()) return SKF_OK;
+    SKF_CUDA(cudaStreamWaitEvent(st, it->second, 0));
+    Q->pending.erase(it);
+    return SKF_OK;
+  }
+  // rejoin: everything on the side stream completes before what follows on `st`
+  int join() const {
+    skf_plan* Q = const_cast<skf_plan*>(P);
+    if (!Q->side_active) return SKF_OK;
+    cudaEvent_t done = Q->next_event();
+    SKF_CUDA(cudaEventRecord(done, Q->side));
+    SKF_CUDA(cudaStreamWaitEvent(st, done, 0));
+    Q->pending.clear();
+    Q->side_active = false;
     return SKF_OK;
   }
 };
@@ -754,10 +811,18 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
   const int rnd = P->round_ops ? 1 : 0;
   Gemm G{P, st};
   SKF_CUDA(cudaMemsetAsync(P->grads, 0, (size_t)P->PL.total * sizeof(float), st));
-  float *gA = P->wsf("g.a"), *gB = P->wsf("g.b"), *gC = P->wsf("g.c"), *gH = P->wsf("g.h");
+  float *gA = P->wsf("g.a"), *gC = P->wsf("g.c"), *gH = P->wsf("g.h");
+  // gradient of the pre-LN sum (gBs) and its Dropout-masked copy (gDs), one pair per LayerNorm site of a layer:
+  // the weight-gradient GEMM that reads a pair runs on the side stream and may still be in flight when the next
+  // site's LayerNorm backward runs, so a pair is only reused one layer later (Gemm::before_write orders that)
+  float* gBs[3] = {P->wsf("g.b"), P->wsf("g.b1"), P->wsf("g.b2")};
+  float* gDs[3] = {P->wsf("g.d"), P->wsf("g.d1"), P->wsf("g.d2")};
+  P->pending.clear();
+  P->side_active = g_wgrad_overlap && P->side != nullptr;
   float *gQKV = P->wsf("g.qkv"), *gQ2 = P->wsf("g.q2"), *gKV2 = P->wsf("g.kv2"), *gPre = P->wsf("g.pre");
-  float *gEmb = P->wsf("g.emb"), *gU = P->wsf("g.u"), *delta = P->wsf("g.delta"), *gD = P->wsf("g.d");
+  float *gEmb = P->wsf("g.emb"), *gU = P->wsf("g.u"), *delta = P->wsf("g.delta");
   const float* gS = nullptr;       // gradient of the current sublayer output (behind its Dropout)
+  float *gB = gBs[0], *gD = gDs[0];
   const uint8_t* enc_pad = P->wsp<uint8_t>("enc_pad");
   bool have_demb = false;
 
@@ -778,40 +843,49 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
       memset(&e, 0, sizeof(e));
       SKF_TRY(gemm_simt(dlog, 8, 1, P->pw("out.k"), 1, 5, gA, d, Md, d, 5, &e, st));
     } else {
-      SKF_TRY(G.wgrad(P->wsf(last + ".out3"), dlog, P->g("out.k"), P->g("out.b"), Md, c.V, d));
+      SKF_TRY(G.wgrad_async(P->wsf(last + ".out3"), dlog, P->g("out.k"), P->g("out.b"), Md, c.V, d));
       SKF_TRY(G.dgrad(dlog, P->w("out.k"), gA, Md, c.V, d, nullptr, nullptr, 0));
     }
     for (int i = c.L - 1; i >= 0; i--) {
       std::string p = "dec.l" + std::to_string(i);
       const float* xin = i == 0 ? P->wsf("dec.x0") : P->wsf("dec.l" + std::to_string(i - 1) + ".out3");
       // LN3 + FFN
+      gB = gBs[2]; gD = gDs[2];
+      SKF_TRY(G.before_write(gB)); SKF_TRY(G.before_write(gD));
       SKF_TRY(ln_bwd_any(P, gA, p, "3", gB, gD, &gS, Md, d, SITE_DEC_L + 3 * i + 2, st));
-      SKF_TRY(G.wgrad(P->wsf(p + ".hff"), gS, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Md, d, f));
+      SKF_TRY(G.wgrad_async(P->wsf(p + ".hff"), gS, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Md, d, f));
+      SKF_TRY(G.before_write(gH));
       SKF_TRY(G.dgrad(gS, P->w(p + ".ffn.w2.k"), gH, Md, d, f, P->wsf(p + ".hff"), nullptr, 1));
-      SKF_TRY(G.wgrad(P->wsf(p + ".out2"), gH, P->g(p + ".ffn.w1.k"), P->g(p + ".ffn.w1.b"), Md, f, d));
+      SKF_TRY(G.wgrad_async(P->wsf(p + ".out2"), gH, P->g(p + ".ffn.w1.k"), P->g(p + ".ffn.w1.b"), Md, f, d));
       SKF_TRY(G.dgrad(gH, P->w(p + ".ffn.w1.k"), gA, Md, f, d, nullptr, gB, 0));
       // LN2 + cross attention
+      gB = gBs[1]; gD = gDs[1];
+      SKF_TRY(G.before_write(gB)); SKF_TRY(G.before_write(gD));
       SKF_TRY(ln_bwd_any(P, gA, p, "2", gB, gD, &gS, Md, d, SITE_DEC_L + 3 * i + 1, st));
-      SKF_TRY(G.wgrad(P->wsf(p + ".ctx2"), gS, P->g(p + ".mha2.wo.k"), P->g(p + ".mha2.wo.b"), Md, d, d));
+      SKF_TRY(G.wgrad_async(P->wsf(p + ".ctx2"), gS, P->g(p + ".mha2.wo.k"), P->g(p + ".mha2.wo.b"), Md, d, d));
       SKF_TRY(G.dgrad(gS, P->w(p + ".mha2.wo.k"), gC, Md, d, d, nullptr, nullptr, 0));
       float* kv2 = P->wsf(p + ".kv2");
+      SKF_TRY(G.before_write(gQ2)); SKF_TRY(G.before_write(gKV2));
       SKF_TRY(attn_bwd_any(P, P->wsf(p + ".q2"), d, kv2, 2 * d, kv2 + d, 2 * d, P->wsf(p + ".ctx2"), d, gC, d,
                            P->wsf(p + ".lse2"), delta, gQ2, d, gKV2, 2 * d, gKV2 + d, 2 * d, cross_pad, Td, T,
                            cross_mode, st));
-      SKF_TRY(G.wgrad(P->wsf(p + ".out1"), gQ2, P->g(p + ".mha2.wq.k"), P->g(p + ".mha2.wq.b"), Md, d, d));
-      SKF_TRY(G.wgrad(pre, gKV2, P->g(p + ".mha2.wkv.k"), P->g(p + ".mha2.wkv.b"), Me, 2 * d, emb_dim(c)));
+      SKF_TRY(G.wgrad_async(P->wsf(p + ".out1"), gQ2, P->g(p + ".mha2.wq.k"), P->g(p + ".mha2.wq.b"), Md, d, d));
+      SKF_TRY(G.wgrad_async(pre, gKV2, P->g(p + ".mha2.wkv.k"), P->g(p + ".mha2.wkv.b"), Me, 2 * d, emb_dim(c)));
       SKF_TRY(G.dgrad(gKV2, P->w(p + ".mha2.wkv.k"), gPre, Me, 2 * d, emb_dim(c), nullptr,
                       i == c.L - 1 ? nullptr : gPre, 0));
       SKF_TRY(G.dgrad(gQ2, P->w(p + ".mha2.wq.k"), gA, Md, d, d, nullptr, gB, 0));
       // LN1 + masked self attention
+      gB = gBs[0]; gD = gDs[0];
+      SKF_TRY(G.before_write(gB)); SKF_TRY(G.before_write(gD));
       SKF_TRY(ln_bwd_any(P, gA, p, "1", gB, gD, &gS, Md, d, SITE_DEC_L + 3 * i, st));
-      SKF_TRY(G.wgrad(P->wsf(p + ".ctx1"), gS, P->g(p + ".mha1.wo.k"), P->g(p + ".mha1.wo.b"), Md, d, d));
+      SKF_TRY(G.wgrad_async(P->wsf(p + ".ctx1"), gS, P->g(p + ".mha1.wo.k"), P->g(p + ".mha1.wo.b"), Md, d, d));
       SKF_TRY(G.dgrad(gS, P->w(p + ".mha1.wo.k"), gC, Md, d, d, nullptr, nullptr, 0));
       float* qkv = P->wsf(p + ".qkv");
+      SKF_TRY(G.before_write(gQKV));
       SKF_TRY(attn_bwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, P->wsf(p + ".ctx1"), d, gC, d,
                            P->wsf(p + ".lse1"), delta, gQKV, 3 * d, gQKV + d, 3 * d, gQKV + 2 * d, 3 * d, dec_pad,
                            Td, Td, 2, st));
-      SKF_TRY(G.wgrad(xin, gQKV, P->g(p + ".mha1.wqkv.k"), P->g(p + ".mha1.wqkv.b"), Md, 3 * d, d));
+      SKF_TRY(G.wgrad_async(xin, gQKV, P->g(p + ".mha1.wqkv.k"), P->g(p + ".mha1.wqkv.b"), Md, 3 * d, d));
       SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha1.wqkv.k"), gA, Md, 3 * d, d, nullptr, gB, 0));
     }
     SKF_TRY(embed_dropout(P, gA, (int64_t)Md * d, SITE_DEC_X0, st));
@@ -830,7 +904,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
     // lowerdim=0: the encoder output reaches the loss only as the decoder's cross keys / values
     SKF_CUDA(cudaMemcpyAsync(gA, gPre, (size_t)Me * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else if (!have_demb) {
-    return SKF_OK;
+    return G.join();
   } else {
     // bottleneck backward
     std::string last = "enc.l" + std::to_string(c.L - 1);
@@ -850,30 +924,36 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
     }
     SKF_TRY(skf_pool_bwd(x, P->wsf("pool.u"), P->pw("pool.V"), P->wsf("pool.a"), gPool, gA, 0, gU,
                          P->g("pool.V"), B, T, d, UP, rnd, st));
-    SKF_TRY(G.wgrad(x, gU, P->g("pool.W"), P->g("pool.b"), Me, UP, d));
+    SKF_TRY(G.wgrad_async(x, gU, P->g("pool.W"), P->g("pool.b"), Me, UP, d));
     SKF_TRY(G.dgrad(gU, P->w("pool.W"), gA, Me, UP, d, nullptr, gA, 0));
   }
   for (int i = c.L - 1; i >= 0; i--) {
     std::string p = "enc.l" + std::to_string(i);
     const float* xin = i == 0 ? P->wsf("enc.x0") : P->wsf("enc.l" + std::to_string(i - 1) + ".out2");
+    gB = gBs[1]; gD = gDs[1];
+    SKF_TRY(G.before_write(gB)); SKF_TRY(G.before_write(gD));
     SKF_TRY(ln_bwd_any(P, gA, p, "2", gB, gD, &gS, Me, d, SITE_ENC_L + 2 * i + 1, st));
-    SKF_TRY(G.wgrad(P->wsf(p + ".hff"), gS, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Me, d, f));
+    SKF_TRY(G.wgrad_async(P->wsf(p + ".hff"), gS, P->g(p + ".ffn.w2.k"), P->g(p + ".ffn.w2.b"), Me, d, f));
+    SKF_TRY(G.before_write(gH));
     SKF_TRY(G.dgrad(gS, P->w(p + ".ffn.w2.k"), gH, Me, d, f, P->wsf(p + ".hff"), nullptr, 1));
-    SKF_TRY(G.wgrad(P->wsf(p + ".out1"), gH, P->g(p + ".ffn.w1.k"), P->g(p + ".ffn.w1.b"), Me, f, d));
+    SKF_TRY(G.wgrad_async(P->wsf(p + ".out1"), gH, P->g(p + ".ffn.w1.k"), P->g(p + ".ffn.w1.b"), Me, f, d));
     SKF_TRY(G.dgrad(gH, P->w(p + ".ffn.w1.k"), gA, Me, f, d, nullptr, gB, 0));
+    gB = gBs[0]; gD = gDs[0];
+    SKF_TRY(G.before_write(gB)); SKF_TRY(G.before_write(gD));
     SKF_TRY(ln_bwd_any(P, gA, p, "1", gB, gD, &gS, Me, d, SITE_ENC_L + 2 * i, st));
-    SKF_TRY(G.wgrad(P->wsf(p + ".ctx"), gS, P->g(p + ".mha.wo.k"), P->g(p + ".mha.wo.b"), Me, d, d));
+    SKF_TRY(G.wgrad_async(P->wsf(p + ".ctx"), gS, P->g(p + ".mha.wo.k"), P->g(p + ".mha.wo.b"), Me, d, d));
     SKF_TRY(G.dgrad(gS, P->w(p + ".mha.wo.k"), gC, Me, d, d, nullptr, nullptr, 0));
     float* qkv = P->wsf(p + ".qkv");
+    SKF_TRY(G.before_write(gQKV));
     SKF_TRY(attn_bwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, P->wsf(p + ".ctx"), d, gC, d,
                          P->wsf(p + ".lse"), delta, gQKV, 3 * d, gQKV + d, 3 * d, gQKV + 2 * d, 3 * d, enc_pad, T, T,
                          1, st));
-    SKF_TRY(G.wgrad(xin, gQKV, P->g(p + ".mha.wqkv.k"), P->g(p + ".mha.wqkv.b"), Me, 3 * d, d));
+    SKF_TRY(G.wgrad_async(xin, gQKV, P->g(p + ".mha.wqkv.k"), P->g(p + ".mha.wqkv.b"), Me, 3 * d, d));
     SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha.wqkv.k"), gA, Me, 3 * d, d, nullptr, gB, 0));
   }
   SKF_TRY(embed_dropout(P, gA, (int64_t)Me * d, SITE_ENC_X0, st));
   SKF_TRY(embed_any_bwd(P, tok, "enc", gA, T, st));
-  return SKF_OK;
+  return G.join();
 }
 
 // ---- greedy decode (models/sketchformer.py:255-311) ----------------------------------------------
@@ -983,6 +1063,14 @@ int skf_set_option(const char* name, int value) {
     skf::g_gemm_mix = value ? 1 : 0;
     return SKF_OK;
   }
+  if (name && strcmp(name, "wgrad_units") == 0) {
+    skf::g_wgrad_units = value < 1 ? 1 : value;
+    return SKF_OK;
+  }
+  if (name && strcmp(name, "wgrad_overlap") == 0) {
+    skf::g_wgrad_overlap = value ? 1 : 0;
+    return SKF_OK;
+  }
   if (name && strcmp(name, "gemm_pair") == 0) {
     skf::g_gemm_pair = value ? 1 : 0;
     return SKF_OK;
@@ -1039,6 +1127,25 @@ int skf_plan_create(const skf_cfg* cfg, float* params, float* grads, float* adam
   P->ws = reinterpret_cast<uint8_t*>(workspace);
   P->round_ops = (cfg->gemm_backend == 0) && !skf::g_tma_tf32_type;
   P->wc = params;
+  {
+    // second stream + event pool for the backward pass; without them (no device) the plan runs single-stream
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess &&
+        cudaStreamCreateWithPriority(&P->side, cudaStreamNonBlocking, lo) == cudaSuccess) {
+      P->events.resize(512);
+      for (cudaEvent_t& e : P->events)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+          e = nullptr;
+          cudaStreamDestroy(P->side);
+          P->side = nullptr;
+          break;
+        }
+      if (!P->side) P->events.clear();
+    } else {
+      P->side = nullptr;
+      (void)cudaGetLastError();
+    }
+  }
   *out = P;
   return SKF_OK;
 }

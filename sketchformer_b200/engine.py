@@ -7,6 +7,7 @@ The arithmetic of the hot path (models/sketchformer.py:325-349 of the reference)
 the CUDA kernels behind include/skf.h; this file only moves pointers.
 """
 import ctypes as C
+import os
 from typing import Dict
 
 import torch
@@ -188,7 +189,10 @@ class Engine:
         torch.cuda.synchronize(self.device)
         l0 = self.launches()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # captured on a high-priority stream: the plan's side stream (weight gradients, lowest priority) then only
+        # takes SMs the critical path leaves idle
+        prio = int(os.environ.get("SKF_GRAPH_PRIORITY", "-1"))
+        with torch.cuda.graph(g, stream=torch.cuda.Stream(self.device, priority=prio)):
             self.train_step(self.graph_tokens, self.graph_labels, apply_adam)
         self.graph_launches = self.launches() - l0     # kernels per replay
         self._graph, self._graph_adam = g, bool(apply_adam)
