@@ -224,6 +224,19 @@ int skf_expand_bwd(const float* dpre, const float* emb, const float* w, float* d
                    int demb_accumulate, float* dw, float* dbeta, int B, int T, int d,
                    void* stream);
 
+/* Keys / values of the decoder's second attention block when they come from the expanded bottleneck
+ * (models/sketchformer.py:170-181: expand_layer, then mha2.wk / wv of builders/layers/transformer.py:155-156):
+ * pre[b,t,:] W + bias = w[t] U[b,:] + beta[t] s[:] + bias[:]  with U = emb W ([B,N]) and s = colsum(W) ([N]).
+ * fwd writes KV [B,T,N]; bwd reduces G = dKV: gU[b,:] += sum_t w[t] G[b,t,:], gs += sum beta[t] G,
+ * gbias += sum G, gw[t] += sum_{b,j} G U, gbeta[t] += sum_{b,j} G s   (N a multiple of 128 for bwd).          */
+int skf_kv_expand_fwd(const float* U, const float* s, const float* bias, const float* w, const float* beta,
+                      float* KV, int B, int T, int N, void* stream);
+int skf_kv_expand_bwd(const float* G, const float* U, const float* s, const float* w, const float* beta,
+                      float* gU, float* gs, float* gbias, float* gw, float* gbeta, int B, int T, int N,
+                      void* stream);
+/* Y[r,:] += v[:] for every row (the colsum(W) term of the weight gradient above)                              */
+int skf_add_row_broadcast(float* Y, const float* v, int rows, int N, void* stream);
+
 /* Token reconstruction loss + accuracy (builders/losses.py:26-41, sketchformer.py:335-339):
  * loss = sum_rows CE(z,tgt)*[tgt!=0] / rows ; correct = #(argmax z == tgt) over ALL rows.
  * dlogits (may alias logits) = (softmax(z) - onehot)*[tgt!=0]*scale.  tgt row stride tgt_ld;

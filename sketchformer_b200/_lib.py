@@ -63,6 +63,9 @@ SIGNATURES = {
     "skf_pool_bwd": (I, [P, P, P, P, P, P, I, P, P, I, I, I, I, I, P]),
     "skf_expand_fwd": (I, [P, P, P, P, I, I, I, I, P]),
     "skf_expand_bwd": (I, [P, P, P, P, I, P, P, I, I, I, P]),
+    "skf_kv_expand_fwd": (I, [P, P, P, P, P, P, I, I, I, P]),
+    "skf_kv_expand_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "skf_add_row_broadcast": (I, [P, P, I, I, P]),
     "skf_token_ce": (I, [P, L, P, L, I, I, I, F, P, L, P, P, I, P]),
     "skf_class_ce": (I, [P, L, P, I, I, F, P, L, P, P, P, P]),
     "skf_adam_step": (I, [P, P, P, P, L, P, I, I, F, F, F, F, P]),

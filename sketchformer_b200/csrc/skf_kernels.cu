@@ -725,6 +725,107 @@ __global__ void adam_k(float* __restrict__ p, const float* __restrict__ g, float
 }
 __global__ void step_inc_k(int64_t* step) { *step += 1; }
 
+// ---------------------------------------------------------------------------------------------
+// Cross-attention keys / values of the expanded bottleneck (models/sketchformer.py:170-181,
+// transformer.py:370-376 then MultiHeadAttention.wk / wv): pre[b,t,:] = emb[b,:] w[t] + beta[t] has rank
+// two in t, so  pre W + bias = w[t] (emb W)[b,:] + beta[t] colsum(W) + bias  needs a [B,E]x[E,N] product
+// instead of a [B T,E]x[E,N] one, and its backward is a reduction over the gradient rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void kv_expand_fwd_k(const float* __restrict__ U, const float* __restrict__ s, const float* __restrict__ bias,
+                                const float* __restrict__ w, const float* __restrict__ beta, float* __restrict__ KV,
+                                int T, int N, int rows_per_cta) {
+  const int b = blockIdx.x, t0 = blockIdx.y * rows_per_cta;
+  const int t1 = min(T, t0 + rows_per_cta);
+  for (int j = threadIdx.x * 4; j < N; j += blockDim.x * 4) {
+    const float4 u = *reinterpret_cast<const float4*>(U + (int64_t)b * N + j);
+    const float4 sv = *reinterpret_cast<const float4*>(s + j);
+    const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = t0; t < t1; t++) {
+      const float wt = __ldg(w + t), bt = __ldg(beta + t);
+      float4 o;
+      o.x = fmaf(wt, u.x, fmaf(bt, sv.x, bv.x)); o.y = fmaf(wt, u.y, fmaf(bt, sv.y, bv.y));
+      o.z = fmaf(wt, u.z, fmaf(bt, sv.z, bv.z)); o.w = fmaf(wt, u.w, fmaf(bt, sv.w, bv.w));
+      *reinterpret_cast<float4*>(KV + ((int64_t)b * T + t) * N + j) = o;
+    }
+  }
+}
+
+// One CTA = one sample x one slice of its T rows; a warp walks rows, a lane owns 4 columns of every 128-column
+// group (NV groups per 128 NV-column chunk).  Everything is accumulated with atomics into zeroed / running outputs.
+template <int NV>
+__global__ void __launch_bounds__(256)
+kv_expand_bwd_k(const float* __restrict__ G, const float* __restrict__ U, const float* __restrict__ s,
+                const float* __restrict__ w, const float* __restrict__ beta, float* __restrict__ gU,
+                float* __restrict__ gs, float* __restrict__ gbias, float* __restrict__ gw, float* __restrict__ gbeta,
+                int T, int N, int rows_per_cta) {
+  __shared__ float red[3][128 * NV];
+  const int b = blockIdx.x, t0 = blockIdx.y * rows_per_cta;
+  const int t1 = min(T, t0 + rows_per_cta);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c0 = 0; c0 < N; c0 += 128 * NV) {
+    float4 u[NV], sv[NV], aU[NV], aS[NV], aB[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const int j = c0 + 128 * v + 4 * lane;
+      u[v] = *reinterpret_cast<const float4*>(U + (int64_t)b * N + j);
+      sv[v] = *reinterpret_cast<const float4*>(s + j);
+      aU[v] = aS[v] = aB[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int t = t0 + warp; t < t1; t += nw) {
+      const float wt = __ldg(w + t), bt = __ldg(beta + t);
+      const float* row = G + ((int64_t)b * T + t) * N + c0 + 4 * lane;
+      float du = 0.f, ds = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        const float4 g = *reinterpret_cast<const float4*>(row + 128 * v);
+        du += (g.x * u[v].x + g.y * u[v].y) + (g.z * u[v].z + g.w * u[v].w);
+        ds += (g.x * sv[v].x + g.y * sv[v].y) + (g.z * sv[v].z + g.w * sv[v].w);
+        aU[v].x = fmaf(wt, g.x, aU[v].x); aU[v].y = fmaf(wt, g.y, aU[v].y);
+        aU[v].z = fmaf(wt, g.z, aU[v].z); aU[v].w = fmaf(wt, g.w, aU[v].w);
+        aS[v].x = fmaf(bt, g.x, aS[v].x); aS[v].y = fmaf(bt, g.y, aS[v].y);
+        aS[v].z = fmaf(bt, g.z, aS[v].z); aS[v].w = fmaf(bt, g.w, aS[v].w);
+        aB[v].x += g.x; aB[v].y += g.y; aB[v].z += g.z; aB[v].w += g.w;
+      }
+      du = warp_sum(du);
+      ds = warp_sum(ds);
+      if (lane == 0) {
+        atomicAdd(gw + t, du);
+        atomicAdd(gbeta + t, ds);
+      }
+    }
+    // column sums: the 8 warps meet in shared memory, then one global atomic per column and CTA
+    for (int i = threadIdx.x; i < 3 * 128 * NV; i += blockDim.x) (&red[0][0])[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const int j = 128 * v + 4 * lane;
+      atomicAdd(&red[0][j], aU[v].x); atomicAdd(&red[0][j + 1], aU[v].y);
+      atomicAdd(&red[0][j + 2], aU[v].z); atomicAdd(&red[0][j + 3], aU[v].w);
+      atomicAdd(&red[1][j], aS[v].x); atomicAdd(&red[1][j + 1], aS[v].y);
+      atomicAdd(&red[1][j + 2], aS[v].z); atomicAdd(&red[1][j + 3], aS[v].w);
+      atomicAdd(&red[2][j], aB[v].x); atomicAdd(&red[2][j + 1], aB[v].y);
+      atomicAdd(&red[2][j + 2], aB[v].z); atomicAdd(&red[2][j + 3], aB[v].w);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 128 * NV; j += blockDim.x) {
+      atomicAdd(gU + (int64_t)b * N + c0 + j, red[0][j]);
+      atomicAdd(gs + c0 + j, red[1][j]);
+      if (gbias) atomicAdd(gbias + c0 + j, red[2][j]);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void add_row_broadcast_k(float* __restrict__ Y, const float* __restrict__ r, int64_t rows, int N) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= rows * N) return;
+  const int j = (int)(i % N);
+  float4 y = *reinterpret_cast<float4*>(Y + i);
+  const float4 v = *reinterpret_cast<const float4*>(r + j);
+  y.x += v.x; y.y += v.y; y.z += v.z; y.w += v.w;
+  *reinterpret_cast<float4*>(Y + i) = y;
+}
+
 }  // namespace skf
 
 using namespace skf;
@@ -966,6 +1067,39 @@ int skf_expand_bwd(const float* dpre, const float* emb, const float* w, float* d
   expand_bwd_emb_k<<<B, 256, 0, as_stream(stream)>>>(dpre, w, demb, demb_accumulate, T, d);
   SKF_LAUNCH_CHECK();
   expand_bwd_w_k<<<T, 256, 0, as_stream(stream)>>>(dpre, emb, dw, dbeta, B, T, d);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_kv_expand_fwd(const float* U, const float* s, const float* bias, const float* w, const float* beta,
+                      float* KV, int B, int T, int N, void* stream) {
+  SKF_REQUIRE(U && s && w && beta && KV && B > 0 && T > 0 && N > 0 && N % 4 == 0, SKF_ERR_BAD_ARG,
+              "kv_expand_fwd: bad argument");
+  const int rows = 16;
+  kv_expand_fwd_k<<<dim3(B, cdiv(T, rows)), 128, 0, as_stream(stream)>>>(U, s, bias, w, beta, KV, T, N, rows);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_kv_expand_bwd(const float* G, const float* U, const float* s, const float* w, const float* beta,
+                      float* gU, float* gs, float* gbias, float* gw, float* gbeta, int B, int T, int N,
+                      void* stream) {
+  SKF_REQUIRE(G && U && s && w && beta && gU && gs && gw && gbeta && B > 0 && T > 0 && N > 0 && N % 128 == 0,
+              SKF_ERR_BAD_ARG, "kv_expand_bwd: bad argument (N must be a multiple of 128)");
+  const int slices = B >= 2 * 148 ? 1 : (2 * 148 + B - 1) / B;      // ~2 CTAs per SM
+  const int rows = cdiv(T, slices < 1 ? 1 : (slices > T ? T : slices));
+  dim3 grid(B, cdiv(T, rows));
+  cudaStream_t st = as_stream(stream);
+  if (N % 512 == 0) kv_expand_bwd_k<4><<<grid, 256, 0, st>>>(G, U, s, w, beta, gU, gs, gbias, gw, gbeta, T, N, rows);
+  else if (N % 256 == 0) kv_expand_bwd_k<2><<<grid, 256, 0, st>>>(G, U, s, w, beta, gU, gs, gbias, gw, gbeta, T, N, rows);
+  else kv_expand_bwd_k<1><<<grid, 256, 0, st>>>(G, U, s, w, beta, gU, gs, gbias, gw, gbeta, T, N, rows);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_add_row_broadcast(float* Y, const float* r, int rows, int N, void* stream) {
+  SKF_REQUIRE(Y && r && rows > 0 && N > 0 && N % 4 == 0, SKF_ERR_BAD_ARG, "add_row_broadcast: bad argument");
+  add_row_broadcast_k<<<cdiv((int64_t)rows * N / 4, 256), 256, 0, as_stream(stream)>>>(Y, r, rows, N);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }

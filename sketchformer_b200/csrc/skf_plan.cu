@@ -29,6 +29,7 @@ int gemm_tc3_wanted(int, int, int);
 int g_gemm_pair = 1;
 int g_wgrad_units = 1;     // side-stream wgrads: work units per cluster slot (finer units yield SMs sooner)
 extern int g_t3_oversubscribe;
+int g_kv_fold = 1;         // cross-attention K / V from the rank-2 form of the expanded bottleneck (see kv_fold())
 int g_wgrad_overlap = 1;   // weight-gradient GEMMs of the backward pass on a second stream (see SideQueue)
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
 int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
@@ -295,6 +296,14 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
   W.add("g.c", Me * d * F);
   W.add("g.d", Me * d * F);
   for (const char* n : {"g.b1", "g.b2", "g.d1", "g.d2"}) W.add(n, Me * d * F);   // one (g.b, g.d) pair per LayerNorm site
+  // rank-2 form of the cross-attention keys / values (kv_fold): U = emb Wkv per layer, s = colsum(Wkv), and the
+  // reduced gradients gU, gs
+  for (int i = 0; i < c.L; i++) {
+    W.add("dec.l" + std::to_string(i) + ".kvU", (size_t)c.B * 2 * d * F);
+    W.add("dec.l" + std::to_string(i) + ".kvs", (size_t)2 * d * F);
+  }
+  W.add("g.kvU", (size_t)c.B * 2 * d * F);
+  W.add("g.kvs", (size_t)2 * d * F);
   W.add("g.h", Me * f * F);
   W.add("g.qkv", Me * 3 * d * F);
   W.add("g.q2", Me * d * F);
@@ -460,24 +469,37 @@ struct Gemm {
     if (db && !fused) SKF_TRY(skf_colsum(dY, N, db, M, N, st));
     return SKF_OK;
   }
-  // wgrad on the plan's side stream, ordered after everything issued so far on `st`
-  int wgrad_async(const float* X, const float* dY, float* dW, float* db, int M, int N, int K) const {
+  // fork: a front-end on the plan's side stream, ordered after everything issued so far on `st` (or *this when
+  // the plan runs single-stream); merge: the side stream is done with `bufs` once it gets here
+  int fork(Gemm* S) const {
     skf_plan* Q = const_cast<skf_plan*>(P);
-    if (!Q->side_active) return wgrad(X, dY, dW, db, M, N, K);
+    *S = *this;
+    if (!Q->side_active || st == Q->side) return SKF_OK;
     cudaEvent_t ready = Q->next_event();
     SKF_CUDA(cudaEventRecord(ready, st));
     SKF_CUDA(cudaStreamWaitEvent(Q->side, ready, 0));
-    Gemm S{P, Q->side};
-    g_t3_oversubscribe = g_wgrad_units > 1;
+    S->st = Q->side;
+    return SKF_OK;
+  }
+  int merge(const Gemm& S, std::initializer_list<const void*> bufs) const {
+    skf_plan* Q = const_cast<skf_plan*>(P);
+    if (S.st == st) return SKF_OK;
+    cudaEvent_t done = Q->next_event();
+    SKF_CUDA(cudaEventRecord(done, S.st));
+    for (const void* b : bufs) Q->pending[b] = done;
+    return SKF_OK;
+  }
+  // wgrad on the side stream
+  int wgrad_async(const float* X, const float* dY, float* dW, float* db, int M, int N, int K) const {
+    Gemm S{P, st};
+    SKF_TRY(fork(&S));
+    g_t3_oversubscribe = S.st != st && g_wgrad_units > 1;
     const int rc = S.wgrad(X, dY, dW, db, M, N, K);
     g_t3_oversubscribe = 0;
     SKF_TRY(rc);
-    cudaEvent_t done = Q->next_event();
-    SKF_CUDA(cudaEventRecord(done, Q->side));
-    Q->pending[dY] = done;
-    return SKF_OK;
+    return merge(S, {dY});
   }
-  // the main chain is about to overwrite `buf`: wait until the side stream has read it
+  // the main chain is about to overwrite (or read a result in) `buf`: wait until the side stream is done with it
   int before_write(const void* buf) const {
     skf_plan* Q = const_cast<skf_plan*>(P);
     auto it = Q->pending.find(buf);
@@ -561,6 +583,14 @@ static int attn_bwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
                      c.H, Tq, Tk, c.d / c.H, mode, c.gemm_precision >= 2 ? 1 : 0, st);
   return attn_bwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad,
                        c.B, c.H, Tq, Tk, c.d / c.H, mode, P->round_ops ? 1 : 0, st);
+}
+
+// The decoder's cross-attention keys / values are Dense(2d) of pre[b,t,:] = emb[b,:] w[t] + beta[t]
+// (DenseExpander, transformer.py:370-376), i.e. w[t] (emb Wkv)[b,:] + beta[t] colsum(Wkv) + bias: a [B,E]x[E,2d]
+// product and an outer-product kernel replace the [B T,E]x[E,2d] GEMM, and a row reduction replaces its dgrad /
+// wgrad and the expander's backward (skf_kv_expand_fwd / _bwd).  Same arithmetic up to fp32 summation order.
+static bool kv_fold(const skf_plan* P) {
+  return g_kv_fold && P->c.u > 0 && !P->round_ops && (2 * P->c.d) % 128 == 0;
 }
 
 // ---- forward -----------------------------------------------------------------------------------
@@ -725,8 +755,22 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
   Gemm G{P, st};
   const int E = emb_dim(c);
   float* pre = P->wsf("pre_decoder");
-  if (c.u > 0) SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, E, rnd, st));
-  else pre = P->wsf("enc.l" + std::to_string(c.L - 1) + ".out2");      // sketchformer.py:175-176
+  const bool fold = kv_fold(P);
+  if (fold) {
+    for (int i = 0; i < c.L; i++) {
+      std::string p = "dec.l" + std::to_string(i);
+      float *U = P->wsf(p + ".kvU"), *sW = P->wsf(p + ".kvs");
+      SKF_TRY(G.fwd(P->wsf("embedding"), P->w(p + ".mha2.wkv.k"), nullptr, U, B, 2 * d, E, SKF_ACT_NONE, nullptr, 0));
+      SKF_CUDA(cudaMemsetAsync(sW, 0, (size_t)2 * d * sizeof(float), st));
+      SKF_TRY(skf_colsum(P->pw(p + ".mha2.wkv.k"), 2 * d, sW, E, 2 * d, st));
+      SKF_TRY(skf_kv_expand_fwd(U, sW, P->pw(p + ".mha2.wkv.b"), P->pw("exp.k"), P->pw("exp.b"), P->wsf(p + ".kv2"), B,
+                                T, 2 * d, st));
+    }
+  } else if (c.u > 0) {
+    SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, E, rnd, st));
+  } else {
+    pre = P->wsf("enc.l" + std::to_string(c.L - 1) + ".out2");      // sketchformer.py:175-176
+  }
   uint8_t* dec_pad = P->wsp<uint8_t>("dec_pad");
   float* x = P->wsf("dec.x0");
   SKF_TRY(embed_any(P, tok, "dec", dec_pad, x, Td, st));   // tar_inp = tar[:, :-1]
@@ -747,7 +791,8 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
     float* q2 = P->wsf(p + ".q2");
     SKF_TRY(G.fwd(out1, P->w(p + ".mha2.wq.k"), P->pw(p + ".mha2.wq.b"), q2, Md, d, d, SKF_ACT_NONE, nullptr, 0));
     float* kv2 = P->wsf(p + ".kv2");
-    SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), kv2, Me, 2 * d, E, SKF_ACT_NONE, nullptr, 0));
+    if (!fold)
+      SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), kv2, Me, 2 * d, E, SKF_ACT_NONE, nullptr, 0));
     float* ctx2 = P->wsf(p + ".ctx2");
     SKF_TRY(attn_fwd_any(P, q2, d, kv2, 2 * d, kv2 + d, 2 * d, ctx2, d, P->wsf(p + ".lse2"), cross_pad, Td, T,
                          cross_mode, st));
@@ -823,6 +868,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
   float *gEmb = P->wsf("g.emb"), *gU = P->wsf("g.u"), *delta = P->wsf("g.delta");
   const float* gS = nullptr;       // gradient of the current sublayer output (behind its Dropout)
   float *gB = gBs[0], *gD = gDs[0];
+  const bool fold = kv_fold(P);
   const uint8_t* enc_pad = P->wsp<uint8_t>("enc_pad");
   bool have_demb = false;
 
@@ -870,9 +916,25 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
                            P->wsf(p + ".lse2"), delta, gQ2, d, gKV2, 2 * d, gKV2 + d, 2 * d, cross_pad, Td, T,
                            cross_mode, st));
       SKF_TRY(G.wgrad_async(P->wsf(p + ".out1"), gQ2, P->g(p + ".mha2.wq.k"), P->g(p + ".mha2.wq.b"), Md, d, d));
-      SKF_TRY(G.wgrad_async(pre, gKV2, P->g(p + ".mha2.wkv.k"), P->g(p + ".mha2.wkv.b"), Me, 2 * d, emb_dim(c)));
-      SKF_TRY(G.dgrad(gKV2, P->w(p + ".mha2.wkv.k"), gPre, Me, 2 * d, emb_dim(c), nullptr,
-                      i == c.L - 1 ? nullptr : gPre, 0));
+      if (fold) {
+        // off the critical path (only the bottleneck gradient at the end of the decoder needs it): side stream
+        Gemm S{P, st};
+        SKF_TRY(G.fork(&S));
+        const int E = emb_dim(c);
+        float *gU = P->wsf("g.kvU"), *gs = P->wsf("g.kvs");
+        SKF_CUDA(cudaMemsetAsync(gU, 0, (size_t)B * 2 * d * sizeof(float), S.st));
+        SKF_CUDA(cudaMemsetAsync(gs, 0, (size_t)2 * d * sizeof(float), S.st));
+        SKF_TRY(skf_kv_expand_bwd(gKV2, P->wsf(p + ".kvU"), P->wsf(p + ".kvs"), P->pw("exp.k"), P->pw("exp.b"), gU, gs,
+                                  P->g(p + ".mha2.wkv.b"), P->g("exp.k"), P->g("exp.b"), B, T, 2 * d, S.st));
+        SKF_TRY(S.wgrad(P->wsf("embedding"), gU, P->g(p + ".mha2.wkv.k"), nullptr, B, 2 * d, E));
+        SKF_TRY(skf_add_row_broadcast(P->g(p + ".mha2.wkv.k"), gs, E, 2 * d, S.st));
+        SKF_TRY(S.dgrad(gU, P->w(p + ".mha2.wkv.k"), gEmb, B, 2 * d, E, nullptr, i == c.L - 1 ? nullptr : gEmb, 0));
+        SKF_TRY(G.merge(S, {gKV2, gEmb}));
+      } else {
+        SKF_TRY(G.wgrad_async(pre, gKV2, P->g(p + ".mha2.wkv.k"), P->g(p + ".mha2.wkv.b"), Me, 2 * d, emb_dim(c)));
+        SKF_TRY(G.dgrad(gKV2, P->w(p + ".mha2.wkv.k"), gPre, Me, 2 * d, emb_dim(c), nullptr,
+                        i == c.L - 1 ? nullptr : gPre, 0));
+      }
       SKF_TRY(G.dgrad(gQ2, P->w(p + ".mha2.wq.k"), gA, Md, d, d, nullptr, gB, 0));
       // LN1 + masked self attention
       gB = gBs[0]; gD = gDs[0];
@@ -890,7 +952,10 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
     }
     SKF_TRY(embed_dropout(P, gA, (int64_t)Md * d, SITE_DEC_X0, st));
     SKF_TRY(embed_any_bwd(P, tok, "dec", gA, Td, st));
-    if (c.u > 0) {
+    if (fold) {
+      SKF_TRY(G.before_write(gEmb));          // the side stream has finished accumulating the bottleneck gradient
+      have_demb = true;
+    } else if (c.u > 0) {
       SKF_TRY(skf_expand_bwd(gPre, P->wsf("embedding"), P->pw("exp.k"), gEmb, 0, P->g("exp.k"),
                              P->g("exp.b"), B, T, emb_dim(c), st));
       have_demb = true;
@@ -1061,6 +1126,10 @@ int skf_split_lo(const float* x, float* lo, int64_t n, void* stream) {
 int skf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_mix") == 0) {
     skf::g_gemm_mix = value ? 1 : 0;
+    return SKF_OK;
+  }
+  if (name && strcmp(name, "kv_fold") == 0) {
+    skf::g_kv_fold = value ? 1 : 0;
     return SKF_OK;
   }
   if (name && strcmp(name, "wgrad_units") == 0) {

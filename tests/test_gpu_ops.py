@@ -490,3 +490,40 @@ def test_gemm_tcgen05_unrounded_operands_within_tolerance(lib):
     Y = torch.zeros(M, N, device="cuda")
     gemm(dev(A), K, 1, dev(Bm), N, 1, Y, N, M, N, K, 0)
     assert rel_err(Y, A.double() @ Bm.double()) < TOL_TF32
+
+
+@pytest.mark.parametrize("B,T,E,N", [(3, 7, 16, 128), (5, 33, 64, 256), (4, 200, 32, 512), (2, 19, 16, 1024)])
+def test_kv_expand_rank2_form(lib, B, T, E, N):
+    """Cross-attention K/V of the expanded bottleneck (sketchformer.py:170-181, transformer.py:370-376, 155-156):
+    Dense(N)(emb[b,:] w[t] + beta[t]) == w[t] (emb W)[b,:] + beta[t] colsum(W) + bias, forward and backward."""
+    g = torch.Generator().manual_seed(B * T)
+    emb = torch.randn(B, E, generator=g).double().requires_grad_(True)
+    Wm = (torch.randn(E, N, generator=g) * 0.2).double().requires_grad_(True)
+    bias = torch.randn(N, generator=g).double().requires_grad_(True)
+    w = torch.randn(T, generator=g).double().requires_grad_(True)
+    beta = torch.randn(T, generator=g).double().requires_grad_(True)
+    pre = emb[:, None, :] * w[None, :, None] + beta[None, :, None]          # DenseExpander.call
+    kv = pre @ Wm + bias
+    G = torch.randn(B, T, N, generator=g)
+    kv.backward(G.double())
+    U = (emb.detach() @ Wm.detach()); s = Wm.detach().sum(0)
+    Ud, sd, wd, bd = dev(U.float()), dev(s.float()), dev(w.detach().float()), dev(beta.detach().float())
+    out = torch.empty(B, T, N, device="cuda")
+    _lib.check(lib.skf_kv_expand_fwd(ptr(Ud), ptr(sd), ptr(dev(bias.detach().float())), ptr(wd), ptr(bd), ptr(out),
+                                     B, T, N, stream()))
+    assert rel_err(out, kv.detach()) < TOL_EXACT
+    gU = torch.zeros(B, N, device="cuda"); gs = torch.zeros(N, device="cuda"); gb = torch.zeros(N, device="cuda")
+    gw = torch.zeros(T, device="cuda"); gbeta = torch.zeros(T, device="cuda")
+    Gd = dev(G)
+    _lib.check(lib.skf_kv_expand_bwd(ptr(Gd), ptr(Ud), ptr(sd), ptr(wd), ptr(bd), ptr(gU), ptr(gs), ptr(gb), ptr(gw),
+                                     ptr(gbeta), B, T, N, stream()))
+    assert rel_err(gb, bias.grad) < TOL_EXACT
+    assert rel_err(gw, w.grad) < TOL_EXACT and rel_err(gbeta, beta.grad) < TOL_EXACT
+    # chain rule through U = emb W and s = colsum(W)
+    gW = emb.detach().T @ gU.cpu().double() + gs.cpu().double()[None, :]
+    assert rel_err(gW, Wm.grad) < TOL_EXACT
+    assert rel_err(gU.cpu().double() @ Wm.detach().T, emb.grad) < TOL_EXACT
+    Y = torch.randn(E, N, generator=g)
+    Yd = dev(Y)
+    _lib.check(lib.skf_add_row_broadcast(ptr(Yd), ptr(gs), E, N, stream()))
+    assert rel_err(Yd, Y.double() + gs.cpu().double()[None, :]) < TOL_EXACT
