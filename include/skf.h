@@ -234,6 +234,17 @@ int skf_kv_expand_fwd(const float* U, const float* s, const float* bias, const f
 int skf_kv_expand_bwd(const float* G, const float* U, const float* s, const float* w, const float* beta,
                       float* gU, float* gs, float* gbias, float* gw, float* gbeta, int B, int T, int N,
                       void* stream);
+/* The whole second attention block of a decoder layer on that rank-2 form, no K / V / score tensors: per query and
+ * head a = Qh.UKh/sqrt(dh), c = Qh.sKh/sqrt(dh), e = Qh.bKh/sqrt(dh); P = softmax_t(a w[t] + c beta[t] + e - 1e9 pad[t]);
+ * O = (sum P w) UVh + (sum P beta) sVh + bVh.  U [B, 2 H dh] (keys then values), s / bias [2 H dh], key_pad [B,T] or
+ * NULL.  bwd: dQ, gU (overwritten), gs += , gbias += (value half; the key bias has zero gradient), gw += , gbeta += . */
+int skf_xattn_fold_fwd(const float* Q, int64_t ldq, const float* U, const float* s, const float* bias, const float* w,
+                       const float* beta, const uint8_t* key_pad, float* O, int64_t ldo, int B, int H, int Tq, int T,
+                       int dh, void* stream);
+int skf_xattn_fold_bwd(const float* Q, int64_t ldq, const float* U, const float* s, const float* bias, const float* w,
+                       const float* beta, const uint8_t* key_pad, const float* dO, int64_t lddo, float* dQ,
+                       int64_t lddq, float* gU, float* gs, float* gbias, float* gw, float* gbeta, int B, int H, int Tq,
+                       int T, int dh, void* stream);
 /* Y[r,:] += v[:] for every row (the colsum(W) term of the weight gradient above)                              */
 int skf_add_row_broadcast(float* Y, const float* v, int rows, int N, void* stream);
 

@@ -65,6 +65,8 @@ SIGNATURES = {
     "skf_expand_bwd": (I, [P, P, P, P, I, P, P, I, I, I, P]),
     "skf_kv_expand_fwd": (I, [P, P, P, P, P, P, I, I, I, P]),
     "skf_kv_expand_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "skf_xattn_fold_fwd": (I, [P, L, P, P, P, P, P, P, P, L, I, I, I, I, I, P]),
+    "skf_xattn_fold_bwd": (I, [P, L, P, P, P, P, P, P, P, L, P, L, P, P, P, P, P, I, I, I, I, I, P]),
     "skf_add_row_broadcast": (I, [P, P, I, I, P]),
     "skf_token_ce": (I, [P, L, P, L, I, I, I, F, P, L, P, P, I, P]),
     "skf_class_ce": (I, [P, L, P, I, I, F, P, L, P, P, P, P]),

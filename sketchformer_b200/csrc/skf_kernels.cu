@@ -826,6 +826,194 @@ __global__ void add_row_broadcast_k(float* __restrict__ Y, const float* __restri
   *reinterpret_cast<float4*>(Y + i) = y;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Cross-attention over the expanded bottleneck without materialising keys or values.  With
+// K[b,t,:] = w[t] UK[b,:] + beta[t] sK + bK and V likewise (see kv_expand above), a query's logits are
+// l[t] = a w[t] + c beta[t] + e  with the three per-(query, head) scalars a = Qh.UKh / sqrt(dh), c = Qh.sKh / sqrt(dh),
+// e = Qh.bKh / sqrt(dh), and its output is  m1 UVh + m2 sVh + bVh  with m1 = sum_t P[t] w[t], m2 = sum_t P[t] beta[t]:
+// scaled_dot_product_attention (builders/utils.py:71-105) of MultiHeadAttention.call (transformer.py:167-191)
+// reduced to T exponentials per query and head.  One CTA per (head, sample), one warp per query, lane j owns
+// elements j, j+32 of the head; additive -1e9 key-padding mask as in the reference.
+// ---------------------------------------------------------------------------------------------
+template <int DH>
+struct XFold {
+  static constexpr int EPL = (DH + 31) / 32;
+  float uk[EPL], sk[EPL], bk[EPL], uv[EPL], sv[EPL], bv[EPL];
+  __device__ __forceinline__ void load(const float* U, const float* s, const float* bias, int b, int h, int d, int lane) {
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int j = lane + 32 * e;
+      const bool ok = j < DH;
+      const int ck = h * DH + j, cv = d + h * DH + j;
+      uk[e] = ok ? U[(int64_t)b * 2 * d + ck] : 0.f;
+      uv[e] = ok ? U[(int64_t)b * 2 * d + cv] : 0.f;
+      sk[e] = ok ? s[ck] : 0.f;
+      sv[e] = ok ? s[cv] : 0.f;
+      bk[e] = ok && bias ? bias[ck] : 0.f;
+      bv[e] = ok && bias ? bias[cv] : 0.f;
+    }
+  }
+};
+
+template <int DH>
+__global__ void __launch_bounds__(256)
+xattn_fold_fwd_k(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ U, const float* __restrict__ s,
+                 const float* __restrict__ bias, const float* __restrict__ w, const float* __restrict__ beta,
+                 const uint8_t* __restrict__ key_pad, float* __restrict__ O, int64_t ldo, int Tq, int T, int d,
+                 float scale) {
+  extern __shared__ float sm[];          // w[T] | beta[T] | mask[T]
+  float* ws = sm;
+  float* bs = sm + T;
+  float* ms = sm + 2 * T;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    ws[t] = w[t];
+    bs[t] = beta[t];
+    ms[t] = (key_pad && key_pad[(int64_t)b * T + t]) ? -1e9f : 0.f;
+  }
+  XFold<DH> c;
+  c.load(U, s, bias, b, h, d, lane);
+  __syncthreads();
+  constexpr int EPL = XFold<DH>::EPL;
+  for (int q = blockIdx.z * nw + warp; q < Tq; q += nw * gridDim.z) {
+    const float* qr = Q + ((int64_t)b * Tq + q) * ldq + h * DH;
+    float a = 0.f, cb = 0.f, ce = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int j = lane + 32 * e;
+      const float qv = j < DH ? qr[j] : 0.f;
+      a = fmaf(qv, c.uk[e], a); cb = fmaf(qv, c.sk[e], cb); ce = fmaf(qv, c.bk[e], ce);
+    }
+    a = warp_sum(a) * scale; cb = warp_sum(cb) * scale; ce = warp_sum(ce) * scale;
+    float mx = -INFINITY;
+    for (int t = lane; t < T; t += 32) mx = fmaxf(mx, (fmaf(a, ws[t], fmaf(cb, bs[t], ce))) + ms[t]);
+    mx = warp_max(mx);
+    float sum = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float p = __expf((fmaf(a, ws[t], fmaf(cb, bs[t], ce)) + ms[t]) - mx);
+      sum += p; s1 = fmaf(p, ws[t], s1); s2 = fmaf(p, bs[t], s2);
+    }
+    sum = warp_sum(sum); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    const float inv = 1.0f / sum, m1 = s1 * inv, m2 = s2 * inv;
+    float* orow = O + ((int64_t)b * Tq + q) * ldo + h * DH;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int j = lane + 32 * e;
+      if (j < DH) orow[j] = fmaf(m1, c.uv[e], fmaf(m2, c.sv[e], c.bv[e]));
+    }
+  }
+}
+
+// Backward of the above for one (head, sample): dQ per query, and the sums over its queries of the gradients of
+// UKh / UVh (stored: this CTA owns those columns of gU), sKh / sVh / bVh (atomics over samples) and of w[t],
+// beta[t] (per-warp shared-memory rows, then atomics).  The key bias has zero gradient (softmax is shift-invariant).
+template <int DH>
+__global__ void __launch_bounds__(256)
+xattn_fold_bwd_k(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ U, const float* __restrict__ s,
+                 const float* __restrict__ bias, const float* __restrict__ w, const float* __restrict__ beta,
+                 const uint8_t* __restrict__ key_pad, const float* __restrict__ dO, int64_t lddo,
+                 float* __restrict__ dQ, int64_t lddq, float* __restrict__ gU, float* __restrict__ gs,
+                 float* __restrict__ gbias, float* __restrict__ gw, float* __restrict__ gbeta, int Tq, int T, int d,
+                 float scale) {
+  extern __shared__ float sm[];          // w[T] | beta[T] | mask[T] | gw rows [nw][T] | gbeta rows [nw][T] | red
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* ws = sm;
+  float* bs = sm + T;
+  float* ms = sm + 2 * T;
+  float* gwr = sm + 3 * T + warp * T;
+  float* gbr = sm + 3 * T + nw * T + warp * T;
+  float* red = sm + 3 * T + 2 * nw * T;  // [5][DH]
+  const int h = blockIdx.x, b = blockIdx.y;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    ws[t] = w[t];
+    bs[t] = beta[t];
+    ms[t] = (key_pad && key_pad[(int64_t)b * T + t]) ? -1e9f : 0.f;
+  }
+  for (int i = threadIdx.x; i < 2 * nw * T + 5 * DH; i += blockDim.x) sm[3 * T + i] = 0.f;
+  XFold<DH> c;
+  c.load(U, s, bias, b, h, d, lane);
+  __syncthreads();
+  constexpr int EPL = XFold<DH>::EPL;
+  float guk[EPL], gsk[EPL], guv[EPL], gsv[EPL], gbv[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; e++) guk[e] = gsk[e] = guv[e] = gsv[e] = gbv[e] = 0.f;
+  for (int q = warp; q < Tq; q += nw) {
+    const float* qr = Q + ((int64_t)b * Tq + q) * ldq + h * DH;
+    const float* gr = dO + ((int64_t)b * Tq + q) * lddo + h * DH;
+    float qv[EPL], gv[EPL];
+    float a = 0.f, cb = 0.f, ce = 0.f, dm1 = 0.f, dm2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int j = lane + 32 * e;
+      qv[e] = j < DH ? qr[j] : 0.f;
+      gv[e] = j < DH ? gr[j] : 0.f;
+      a = fmaf(qv[e], c.uk[e], a); cb = fmaf(qv[e], c.sk[e], cb); ce = fmaf(qv[e], c.bk[e], ce);
+      dm1 = fmaf(gv[e], c.uv[e], dm1); dm2 = fmaf(gv[e], c.sv[e], dm2);
+    }
+    a = warp_sum(a) * scale; cb = warp_sum(cb) * scale; ce = warp_sum(ce) * scale;
+    dm1 = warp_sum(dm1); dm2 = warp_sum(dm2);
+    float mx = -INFINITY;
+    for (int t = lane; t < T; t += 32) mx = fmaxf(mx, (fmaf(a, ws[t], fmaf(cb, bs[t], ce))) + ms[t]);
+    mx = warp_max(mx);
+    float sum = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float p = __expf((fmaf(a, ws[t], fmaf(cb, bs[t], ce)) + ms[t]) - mx);
+      sum += p; s1 = fmaf(p, ws[t], s1); s2 = fmaf(p, bs[t], s2);
+    }
+    sum = warp_sum(sum); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    const float inv = 1.0f / sum, m1 = s1 * inv, m2 = s2 * inv;
+    // dl[t] = P[t] (dm1 (w[t] - m1) + dm2 (beta[t] - m2)); da = sum dl w, dc = sum dl beta (centred: no cancellation)
+    float da = 0.f, dc = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float p = __expf((fmaf(a, ws[t], fmaf(cb, bs[t], ce)) + ms[t]) - mx) * inv;
+      const float dl = p * fmaf(dm1, ws[t] - m1, dm2 * (bs[t] - m2));
+      da = fmaf(dl, ws[t] - m1, da);
+      dc = fmaf(dl, bs[t] - m2, dc);
+      gwr[t] += fmaf(p, dm1, dl * a);
+      gbr[t] += fmaf(p, dm2, dl * cb);
+    }
+    da = warp_sum(da); dc = warp_sum(dc);
+    float* dqr = dQ + ((int64_t)b * Tq + q) * lddq + h * DH;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int j = lane + 32 * e;
+      if (j < DH) dqr[j] = scale * fmaf(da, c.uk[e], dc * c.sk[e]);
+      guk[e] = fmaf(scale * da, qv[e], guk[e]);
+      gsk[e] = fmaf(scale * dc, qv[e], gsk[e]);
+      guv[e] = fmaf(m1, gv[e], guv[e]);
+      gsv[e] = fmaf(m2, gv[e], gsv[e]);
+      gbv[e] += gv[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; e++) {
+    const int j = lane + 32 * e;
+    if (j < DH) {
+      atomicAdd(red + j, guk[e]); atomicAdd(red + DH + j, gsk[e]); atomicAdd(red + 2 * DH + j, guv[e]);
+      atomicAdd(red + 3 * DH + j, gsv[e]); atomicAdd(red + 4 * DH + j, gbv[e]);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < DH; j += blockDim.x) {
+    const int ck = h * DH + j, cv = d + h * DH + j;
+    gU[(int64_t)b * 2 * d + ck] = red[j];
+    gU[(int64_t)b * 2 * d + cv] = red[2 * DH + j];
+    atomicAdd(gs + ck, red[DH + j]);
+    atomicAdd(gs + cv, red[3 * DH + j]);
+    if (gbias) atomicAdd(gbias + cv, red[4 * DH + j]);
+  }
+  const float* gw_all = sm + 3 * T;
+  const float* gb_all = sm + 3 * T + nw * T;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float x = 0.f, y = 0.f;
+    for (int k = 0; k < nw; k++) { x += gw_all[k * T + t]; y += gb_all[k * T + t]; }
+    atomicAdd(gw + t, x);
+    atomicAdd(gbeta + t, y);
+  }
+}
+
 }  // namespace skf
 
 using namespace skf;
@@ -1096,6 +1284,54 @@ int skf_kv_expand_bwd(const float* G, const float* U, const float* s, const floa
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
+
+#define SKF_XFOLD_DISPATCH(K, ...)                                   \
+  do {                                                               \
+    if (dh == 16) K<16> __VA_ARGS__;                                 \
+    else if (dh == 32) K<32> __VA_ARGS__;                            \
+    else K<64> __VA_ARGS__;                                          \
+  } while (0)
+
+int skf_xattn_fold_fwd(const float* Q, int64_t ldq, const float* U, const float* s, const float* bias, const float* w,
+                       const float* beta, const uint8_t* key_pad, float* O, int64_t ldo, int B, int H, int Tq, int T,
+                       int dh, void* stream) {
+  SKF_REQUIRE(Q && U && s && w && beta && O && B > 0 && H > 0 && Tq > 0 && T > 0, SKF_ERR_BAD_ARG,
+              "xattn_fold_fwd: bad argument");
+  SKF_REQUIRE(dh == 16 || dh == 32 || dh == 64, SKF_ERR_UNSUPPORTED, "xattn_fold_fwd: head dim %d", dh);
+  const size_t smem = (size_t)3 * T * sizeof(float);
+  const int qz = Tq >= 64 && B * H < 2 * 148 ? 2 : 1;
+  const float scale = 1.0f / sqrtf((float)dh);
+  cudaStream_t st = as_stream(stream);
+  SKF_XFOLD_DISPATCH(xattn_fold_fwd_k, <<<dim3(H, B, qz), 256, smem, st>>>(Q, ldq, U, s, bias, w, beta, key_pad, O, ldo,
+                                                                            Tq, T, H * dh, scale));
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+int skf_xattn_fold_bwd(const float* Q, int64_t ldq, const float* U, const float* s, const float* bias, const float* w,
+                       const float* beta, const uint8_t* key_pad, const float* dO, int64_t lddo, float* dQ,
+                       int64_t lddq, float* gU, float* gs, float* gbias, float* gw, float* gbeta, int B, int H, int Tq,
+                       int T, int dh, void* stream) {
+  SKF_REQUIRE(Q && U && s && w && beta && dO && dQ && gU && gs && gw && gbeta && B > 0 && H > 0 && Tq > 0 && T > 0,
+              SKF_ERR_BAD_ARG, "xattn_fold_bwd: bad argument");
+  SKF_REQUIRE(dh == 16 || dh == 32 || dh == 64, SKF_ERR_UNSUPPORTED, "xattn_fold_bwd: head dim %d", dh);
+  const int nw = 8;
+  const size_t smem = ((size_t)3 * T + 2 * nw * T + 5 * dh) * sizeof(float);
+  SKF_REQUIRE(smem <= 200 * 1024, SKF_ERR_UNSUPPORTED, "xattn_fold_bwd: T = %d too long", T);
+  const float scale = 1.0f / sqrtf((float)dh);
+  cudaStream_t st = as_stream(stream);
+  if (smem > 48 * 1024) {
+    if (dh == 16) SKF_CUDA(cudaFuncSetAttribute(xattn_fold_bwd_k<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (dh == 32) SKF_CUDA(cudaFuncSetAttribute(xattn_fold_bwd_k<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else SKF_CUDA(cudaFuncSetAttribute(xattn_fold_bwd_k<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  SKF_XFOLD_DISPATCH(xattn_fold_bwd_k, <<<dim3(H, B), 32 * nw, smem, st>>>(Q, ldq, U, s, bias, w, beta, key_pad, dO, lddo,
+                                                                            dQ, lddq, gU, gs, gbias, gw, gbeta, Tq, T,
+                                                                            H * dh, scale));
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+#undef SKF_XFOLD_DISPATCH
 
 int skf_add_row_broadcast(float* Y, const float* r, int rows, int N, void* stream) {
   SKF_REQUIRE(Y && r && rows > 0 && N > 0 && N % 4 == 0, SKF_ERR_BAD_ARG, "add_row_broadcast: bad argument");

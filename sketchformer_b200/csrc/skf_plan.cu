@@ -29,7 +29,7 @@ int gemm_tc3_wanted(int, int, int);
 int g_gemm_pair = 1;
 int g_wgrad_units = 1;     // side-stream wgrads: work units per cluster slot (finer units yield SMs sooner)
 extern int g_t3_oversubscribe;
-int g_kv_fold = 1;         // cross-attention K / V from the rank-2 form of the expanded bottleneck (see kv_fold())
+int g_kv_fold = 2;         // rank-2 form of the expanded bottleneck (see kv_fold()): 1 K / V only, 2 whole cross attention
 int g_wgrad_overlap = 1;   // weight-gradient GEMMs of the backward pass on a second stream (see SideQueue)
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
 int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
@@ -589,8 +589,12 @@ static int attn_bwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
 // (DenseExpander, transformer.py:370-376), i.e. w[t] (emb Wkv)[b,:] + beta[t] colsum(Wkv) + bias: a [B,E]x[E,2d]
 // product and an outer-product kernel replace the [B T,E]x[E,2d] GEMM, and a row reduction replaces its dgrad /
 // wgrad and the expander's backward (skf_kv_expand_fwd / _bwd).  Same arithmetic up to fp32 summation order.
-static bool kv_fold(const skf_plan* P) {
-  return g_kv_fold && P->c.u > 0 && !P->round_ops && (2 * P->c.d) % 128 == 0;
+// Level 2 goes one step further: with such keys and values a query's logits are a w[t] + c beta[t] + const and its
+// output is a combination of three vectors, so the second attention block needs no K / V / score tensors at all
+// (skf_xattn_fold_fwd / _bwd); level 1 materialises K / V and runs the regular attention kernels.
+static int kv_fold(const skf_plan* P) {
+  if (!(g_kv_fold && P->c.u > 0 && !P->round_ops && (2 * P->c.d) % 128 == 0)) return 0;
+  return g_kv_fold;
 }
 
 // ---- forward -----------------------------------------------------------------------------------
@@ -755,7 +759,7 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
   Gemm G{P, st};
   const int E = emb_dim(c);
   float* pre = P->wsf("pre_decoder");
-  const bool fold = kv_fold(P);
+  const int fold = kv_fold(P);
   if (fold) {
     for (int i = 0; i < c.L; i++) {
       std::string p = "dec.l" + std::to_string(i);
@@ -763,8 +767,9 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
       SKF_TRY(G.fwd(P->wsf("embedding"), P->w(p + ".mha2.wkv.k"), nullptr, U, B, 2 * d, E, SKF_ACT_NONE, nullptr, 0));
       SKF_CUDA(cudaMemsetAsync(sW, 0, (size_t)2 * d * sizeof(float), st));
       SKF_TRY(skf_colsum(P->pw(p + ".mha2.wkv.k"), 2 * d, sW, E, 2 * d, st));
-      SKF_TRY(skf_kv_expand_fwd(U, sW, P->pw(p + ".mha2.wkv.b"), P->pw("exp.k"), P->pw("exp.b"), P->wsf(p + ".kv2"), B,
-                                T, 2 * d, st));
+      if (fold == 1)
+        SKF_TRY(skf_kv_expand_fwd(U, sW, P->pw(p + ".mha2.wkv.b"), P->pw("exp.k"), P->pw("exp.b"), P->wsf(p + ".kv2"),
+                                  B, T, 2 * d, st));
     }
   } else if (c.u > 0) {
     SKF_TRY(skf_expand_fwd(P->wsf("embedding"), P->pw("exp.k"), P->pw("exp.b"), pre, B, T, E, rnd, st));
@@ -794,8 +799,12 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
     if (!fold)
       SKF_TRY(G.fwd(pre, P->w(p + ".mha2.wkv.k"), P->pw(p + ".mha2.wkv.b"), kv2, Me, 2 * d, E, SKF_ACT_NONE, nullptr, 0));
     float* ctx2 = P->wsf(p + ".ctx2");
-    SKF_TRY(attn_fwd_any(P, q2, d, kv2, 2 * d, kv2 + d, 2 * d, ctx2, d, P->wsf(p + ".lse2"), cross_pad, Td, T,
-                         cross_mode, st));
+    if (fold == 2)
+      SKF_TRY(skf_xattn_fold_fwd(q2, d, P->wsf(p + ".kvU"), P->wsf(p + ".kvs"), P->pw(p + ".mha2.wkv.b"), P->pw("exp.k"),
+                                 P->pw("exp.b"), cross_pad, ctx2, d, B, c.H, Td, T, d / c.H, st));
+    else
+      SKF_TRY(attn_fwd_any(P, q2, d, kv2, 2 * d, kv2 + d, 2 * d, ctx2, d, P->wsf(p + ".lse2"), cross_pad, Td, T,
+                           cross_mode, st));
     float* out2 = P->wsf(p + ".out2");
     SKF_TRY(proj_resid_ln(P, G, ctx2, p + ".mha2.wo.k", p + ".mha2.wo.b", p + ".ln2", out1, tmp, P->wsf(p + ".s2"), out2,
                           P->wsf(p + ".mean2"), P->wsf(p + ".rstd2"), Md, d, d, SITE_DEC_L + 3 * i + 1, st));
@@ -868,7 +877,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
   float *gEmb = P->wsf("g.emb"), *gU = P->wsf("g.u"), *delta = P->wsf("g.delta");
   const float* gS = nullptr;       // gradient of the current sublayer output (behind its Dropout)
   float *gB = gBs[0], *gD = gDs[0];
-  const bool fold = kv_fold(P);
+  const int fold = kv_fold(P);
   const uint8_t* enc_pad = P->wsp<uint8_t>("enc_pad");
   bool have_demb = false;
 
@@ -911,25 +920,36 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
       SKF_TRY(G.wgrad_async(P->wsf(p + ".ctx2"), gS, P->g(p + ".mha2.wo.k"), P->g(p + ".mha2.wo.b"), Md, d, d));
       SKF_TRY(G.dgrad(gS, P->w(p + ".mha2.wo.k"), gC, Md, d, d, nullptr, nullptr, 0));
       float* kv2 = P->wsf(p + ".kv2");
+      float *gUkv = P->wsf("g.kvU"), *gskv = P->wsf("g.kvs");
       SKF_TRY(G.before_write(gQ2)); SKF_TRY(G.before_write(gKV2));
-      SKF_TRY(attn_bwd_any(P, P->wsf(p + ".q2"), d, kv2, 2 * d, kv2 + d, 2 * d, P->wsf(p + ".ctx2"), d, gC, d,
-                           P->wsf(p + ".lse2"), delta, gQ2, d, gKV2, 2 * d, gKV2 + d, 2 * d, cross_pad, Td, T,
-                           cross_mode, st));
+      if (fold == 2) {
+        SKF_TRY(G.before_write(gUkv));           // the side stream is done with the previous layer's gU / gs
+        SKF_CUDA(cudaMemsetAsync(gskv, 0, (size_t)2 * d * sizeof(float), st));
+        SKF_TRY(skf_xattn_fold_bwd(P->wsf(p + ".q2"), d, P->wsf(p + ".kvU"), P->wsf(p + ".kvs"), P->pw(p + ".mha2.wkv.b"),
+                                   P->pw("exp.k"), P->pw("exp.b"), cross_pad, gC, d, gQ2, d, gUkv, gskv,
+                                   P->g(p + ".mha2.wkv.b"), P->g("exp.k"), P->g("exp.b"), B, c.H, Td, T, d / c.H, st));
+      } else {
+        SKF_TRY(attn_bwd_any(P, P->wsf(p + ".q2"), d, kv2, 2 * d, kv2 + d, 2 * d, P->wsf(p + ".ctx2"), d, gC, d,
+                             P->wsf(p + ".lse2"), delta, gQ2, d, gKV2, 2 * d, gKV2 + d, 2 * d, cross_pad, Td, T,
+                             cross_mode, st));
+      }
       SKF_TRY(G.wgrad_async(P->wsf(p + ".out1"), gQ2, P->g(p + ".mha2.wq.k"), P->g(p + ".mha2.wq.b"), Md, d, d));
       if (fold) {
         // off the critical path (only the bottleneck gradient at the end of the decoder needs it): side stream
         Gemm S{P, st};
         SKF_TRY(G.fork(&S));
         const int E = emb_dim(c);
-        float *gU = P->wsf("g.kvU"), *gs = P->wsf("g.kvs");
-        SKF_CUDA(cudaMemsetAsync(gU, 0, (size_t)B * 2 * d * sizeof(float), S.st));
-        SKF_CUDA(cudaMemsetAsync(gs, 0, (size_t)2 * d * sizeof(float), S.st));
-        SKF_TRY(skf_kv_expand_bwd(gKV2, P->wsf(p + ".kvU"), P->wsf(p + ".kvs"), P->pw("exp.k"), P->pw("exp.b"), gU, gs,
-                                  P->g(p + ".mha2.wkv.b"), P->g("exp.k"), P->g("exp.b"), B, T, 2 * d, S.st));
+        float *gU = gUkv, *gs = gskv;
+        if (fold == 1) {
+          SKF_CUDA(cudaMemsetAsync(gU, 0, (size_t)B * 2 * d * sizeof(float), S.st));
+          SKF_CUDA(cudaMemsetAsync(gs, 0, (size_t)2 * d * sizeof(float), S.st));
+          SKF_TRY(skf_kv_expand_bwd(gKV2, P->wsf(p + ".kvU"), P->wsf(p + ".kvs"), P->pw("exp.k"), P->pw("exp.b"), gU, gs,
+                                    P->g(p + ".mha2.wkv.b"), P->g("exp.k"), P->g("exp.b"), B, T, 2 * d, S.st));
+        }
         SKF_TRY(S.wgrad(P->wsf("embedding"), gU, P->g(p + ".mha2.wkv.k"), nullptr, B, 2 * d, E));
         SKF_TRY(skf_add_row_broadcast(P->g(p + ".mha2.wkv.k"), gs, E, 2 * d, S.st));
         SKF_TRY(S.dgrad(gU, P->w(p + ".mha2.wkv.k"), gEmb, B, 2 * d, E, nullptr, i == c.L - 1 ? nullptr : gEmb, 0));
-        SKF_TRY(G.merge(S, {gKV2, gEmb}));
+        SKF_TRY(G.merge(S, {gKV2, gEmb, gU}));
       } else {
         SKF_TRY(G.wgrad_async(pre, gKV2, P->g(p + ".mha2.wkv.k"), P->g(p + ".mha2.wkv.b"), Me, 2 * d, emb_dim(c)));
         SKF_TRY(G.dgrad(gKV2, P->w(p + ".mha2.wkv.k"), gPre, Me, 2 * d, emb_dim(c), nullptr,
@@ -1129,7 +1149,7 @@ int skf_set_option(const char* name, int value) {
     return SKF_OK;
   }
   if (name && strcmp(name, "kv_fold") == 0) {
-    skf::g_kv_fold = value ? 1 : 0;
+    skf::g_kv_fold = value < 0 ? 0 : (value > 2 ? 2 : value);
     return SKF_OK;
   }
   if (name && strcmp(name, "wgrad_units") == 0) {

@@ -527,3 +527,48 @@ def test_kv_expand_rank2_form(lib, B, T, E, N):
     Yd = dev(Y)
     _lib.check(lib.skf_add_row_broadcast(ptr(Yd), ptr(gs), E, N, stream()))
     assert rel_err(Yd, Y.double() + gs.cpu().double()[None, :]) < TOL_EXACT
+
+
+@pytest.mark.parametrize("B,H,Tq,T,dh,masked", [(2, 4, 9, 10, 16, False), (3, 8, 33, 40, 32, True), (2, 8, 199, 200, 32, False),
+                                                 (2, 2, 70, 257, 64, True), (1, 8, 40, 512, 64, False)])
+def test_cross_attention_on_the_rank2_form(lib, B, H, Tq, T, dh, masked):
+    """skf_xattn_fold_fwd / _bwd against MultiHeadAttention's second block computed the long way (fp64): expand,
+    Dense keys / values, scaled_dot_product_attention with the additive -1e9 key-padding mask, autograd."""
+    g = torch.Generator().manual_seed(7 * T + dh)
+    d = H * dh
+    q = torch.randn(B, Tq, d, generator=g).double().requires_grad_(True)
+    U = torch.randn(B, 2 * d, generator=g).double().requires_grad_(True)
+    s = torch.randn(2 * d, generator=g).double().requires_grad_(True)
+    bias = torch.randn(2 * d, generator=g).double().requires_grad_(True)
+    w = torch.randn(T, generator=g).double().requires_grad_(True)
+    beta = torch.randn(T, generator=g).double().requires_grad_(True)
+    kv = w[None, :, None] * U[:, None, :] + beta[None, :, None] * s[None, None, :] + bias
+    k, v = kv[..., :d], kv[..., d:]
+    pad = None
+    mask = None
+    if masked:
+        lens = torch.randint(max(1, T // 3), T + 1, (B,), generator=g)
+        pad = (torch.arange(T)[None, :] >= lens[:, None])
+        mask = pad[:, None, None, :].double()
+    o, _ = O.scaled_dot_product_attention(O.split_heads(q, H), O.split_heads(k, H), O.split_heads(v, H), mask)
+    o = o.permute(0, 2, 1, 3).reshape(B, Tq, d)
+    do = torch.randn(B, Tq, d, generator=g)
+    o.backward(do.double())
+    f32 = lambda t: dev(t.detach().float())
+    qd, Ud, sd, bd, wd, btd, dod = f32(q), f32(U), f32(s), f32(bias), f32(w), f32(beta), dev(do)
+    padd = dev(pad.to(torch.uint8)) if masked else None
+    od = torch.empty(B, Tq, d, device="cuda")
+    _lib.check(lib.skf_xattn_fold_fwd(ptr(qd), d, ptr(Ud), ptr(sd), ptr(bd), ptr(wd), ptr(btd), ptr(padd), ptr(od), d,
+                                      B, H, Tq, T, dh, stream()))
+    assert rel_err(od, o.detach()) < 2e-5
+    dq = torch.empty_like(qd); gU = torch.full((B, 2 * d), 7.0, device="cuda")      # gU is overwritten, the rest add
+    gs = torch.zeros(2 * d, device="cuda"); gb = torch.zeros(2 * d, device="cuda")
+    gw = torch.zeros(T, device="cuda"); gbeta = torch.zeros(T, device="cuda")
+    _lib.check(lib.skf_xattn_fold_bwd(ptr(qd), d, ptr(Ud), ptr(sd), ptr(bd), ptr(wd), ptr(btd), ptr(padd), ptr(dod), d,
+                                      ptr(dq), d, ptr(gU), ptr(gs), ptr(gb), ptr(gw), ptr(gbeta), B, H, Tq, T, dh,
+                                      stream()))
+    tol = 5e-5
+    assert rel_err(dq, q.grad) < tol and rel_err(gU, U.grad) < tol and rel_err(gs, s.grad) < tol
+    assert rel_err(gw, w.grad) < tol and rel_err(gbeta, beta.grad) < tol
+    assert rel_err(gb[d:], bias.grad[d:]) < tol
+    assert float(gb[:d].abs().max()) == 0.0 and float(bias.grad[:d].abs().max()) < 1e-9 * float(bias.grad[d:].abs().max() + 1)

@@ -47,7 +47,7 @@ def build(cfg_kw, B, backend, precision=2, attn_backend=-1, **flags):
     return ocfg, Engine(c)
 
 
-def engine_activations(eng, ocfg, B, materialised_pre=False):
+def engine_activations(eng, ocfg, B, materialised_pre=False, materialised_kv=False):
     """Engine workspace tensors under the oracle's tape names."""
     T, d, L = ocfg.max_seq_len, ocfg.d_model, ocfg.num_layers
     out = {"enc.x0": eng.tensor("enc.x0", (B, T, d))}
@@ -69,8 +69,9 @@ def engine_activations(eng, ocfg, B, materialised_pre=False):
             out[f"dec.l{i}.mha1.q"], out[f"dec.l{i}.mha1.k"], out[f"dec.l{i}.mha1.v"] = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
             out[f"dec.l{i}.mha1.ctx"] = eng.tensor(f"dec.l{i}.ctx1", (B, T - 1, d))
             out[f"dec.l{i}.mha2.q"] = eng.tensor(f"dec.l{i}.q2", (B, T - 1, d))
-            kv = eng.tensor(f"dec.l{i}.kv2", (B, T, 2 * d))
-            out[f"dec.l{i}.mha2.k"], out[f"dec.l{i}.mha2.v"] = kv[..., :d], kv[..., d:]
+            if materialised_kv:      # not under kv_fold=2 (the default): mha2.ctx below covers the whole block
+                kv = eng.tensor(f"dec.l{i}.kv2", (B, T, 2 * d))
+                out[f"dec.l{i}.mha2.k"], out[f"dec.l{i}.mha2.v"] = kv[..., :d], kv[..., d:]
             out[f"dec.l{i}.mha2.ctx"] = eng.tensor(f"dec.l{i}.ctx2", (B, T - 1, d))
             for j in (1, 2, 3):
                 out[f"dec.l{i}.out{j}"] = eng.tensor(f"dec.l{i}.out{j}", (B, T - 1, d))
@@ -93,14 +94,15 @@ CFG2 = dict(num_layers=4, d_model=256, dff=1024, num_heads=8, lowerdim=256, max_
 CASES = [("tiny", TINY, 4), ("cfg1", CFG1, 8), ("cfg2-b6", CFG2, 6)]
 
 
-@pytest.fixture(params=[1, 0], ids=["kvfold", "kvgemm"])
+@pytest.fixture(params=[2, 1, 0], ids=["xfold", "kvfold", "kvgemm"])
 def kv_fold(request):
-    """1 (default): cross-attention K / V from the rank-2 form of the expanded bottleneck; 0: expander + GEMM."""
+    """2 (default): the decoder's second attention block on the rank-2 form of the expanded bottleneck, no K / V;
+    1: K / V from that form, regular attention kernels; 0: expander + Dense(2d) GEMM + attention kernels."""
     from sketchformer_b200 import _lib
     lib = _lib.load()
     _lib.check(lib.skf_set_option(b"kv_fold", request.param))
-    yield bool(request.param)
-    _lib.check(lib.skf_set_option(b"kv_fold", 1))
+    yield request.param
+    _lib.check(lib.skf_set_option(b"kv_fold", 2))
 
 
 @pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
@@ -126,7 +128,7 @@ def test_train_step_matches_oracle(name, cfg_kw, B, backend, kv_fold):
     assert flips <= 1e-3 * units, f"ReLU pattern differs on {flips} of {units} hidden units"
 
     bad = []
-    acts = engine_activations(eng, ocfg, B, materialised_pre=not kv_fold)
+    acts = engine_activations(eng, ocfg, B, materialised_pre=kv_fold == 0, materialised_kv=kv_fold < 2)
     for k, ref in tape.items():
         if k not in acts:
             continue
