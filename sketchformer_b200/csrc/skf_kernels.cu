@@ -836,79 +836,158 @@ __global__ void add_row_broadcast_k(float* __restrict__ Y, const float* __restri
 // reduced to T exponentials per query and head.  One CTA per (head, sample), one warp per query, lane j owns
 // elements j, j+32 of the head; additive -1e9 key-padding mask as in the reference.
 // ---------------------------------------------------------------------------------------------
-template <int DH>
-struct XFold {
-  static constexpr int EPL = (DH + 31) / 32;
-  float uk[EPL], sk[EPL], bk[EPL], uv[EPL], sv[EPL], bv[EPL];
-  __device__ __forceinline__ void load(const float* U, const float* s, const float* bias, int b, int h, int d, int lane) {
-#pragma unroll
-    for (int e = 0; e < EPL; e++) {
-      const int j = lane + 32 * e;
-      const bool ok = j < DH;
-      const int ck = h * DH + j, cv = d + h * DH + j;
-      uk[e] = ok ? U[(int64_t)b * 2 * d + ck] : 0.f;
-      uv[e] = ok ? U[(int64_t)b * 2 * d + cv] : 0.f;
-      sk[e] = ok ? s[ck] : 0.f;
-      sv[e] = ok ? s[cv] : 0.f;
-      bk[e] = ok && bias ? bias[ck] : 0.f;
-      bv[e] = ok && bias ? bias[cv] : 0.f;
-    }
-  }
+constexpr float XF_LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float xf_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Shared by the forward and backward kernels of one (head, sample): the key table, centred so that second moments
+// do not cancel, tab[t] = (w[t] - wbar, beta[t] - bbar, -1e9 log2e pad[t], 0), its extrema (for the softmax shift)
+// and the six head vectors UKh, sKh, bKh, UVh, sVh, bVh.
+struct XfShared {
+  float4* tab;     // [T]
+  float* vec;      // [6][DH]
+  float* stat;     // wbar, bbar, wmin', wmax', bmin', bmax'  (primes: centred)
 };
 
 template <int DH>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void xf_setup(const XfShared& S, const float* U, const float* s, const float* bias,
+                                         const float* w, const float* beta, const uint8_t* key_pad, int b, int h, int T,
+                                         int d) {
+  __shared__ float red[6][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float sw = 0.f, sb = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) { sw += w[t]; sb += beta[t]; }
+  sw = warp_sum(sw); sb = warp_sum(sb);
+  if (lane == 0) { red[0][warp] = sw; red[1][warp] = sb; }
+  __syncthreads();
+  float wbar = 0.f, bbar = 0.f;
+  for (int k = 0; k < nw; k++) { wbar += red[0][k]; bbar += red[1][k]; }
+  wbar /= (float)T; bbar /= (float)T;
+  float wmn = INFINITY, wmx = -INFINITY, bmn = INFINITY, bmx = -INFINITY;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float a = w[t] - wbar, c = beta[t] - bbar;
+    S.tab[t] = make_float4(a, c, (key_pad && key_pad[(int64_t)b * T + t]) ? -1e9f * XF_LOG2E : 0.f, 0.f);
+    wmn = fminf(wmn, a); wmx = fmaxf(wmx, a); bmn = fminf(bmn, c); bmx = fmaxf(bmx, c);
+  }
+  wmn = -warp_max(-wmn); wmx = warp_max(wmx); bmn = -warp_max(-bmn); bmx = warp_max(bmx);
+  if (lane == 0) { red[2][warp] = wmn; red[3][warp] = wmx; red[4][warp] = bmn; red[5][warp] = bmx; }
+  for (int j = threadIdx.x; j < DH; j += blockDim.x) {
+    const int ck = h * DH + j, cv = d + h * DH + j;
+    S.vec[j] = U[(int64_t)b * 2 * d + ck];
+    S.vec[DH + j] = s[ck];
+    S.vec[2 * DH + j] = bias ? bias[ck] : 0.f;
+    S.vec[3 * DH + j] = U[(int64_t)b * 2 * d + cv];
+    S.vec[4 * DH + j] = s[cv];
+    S.vec[5 * DH + j] = bias ? bias[cv] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = red[2][0], c = red[3][0], e = red[4][0], f = red[5][0];
+    for (int k = 1; k < nw; k++) {
+      a = fminf(a, red[2][k]); c = fmaxf(c, red[3][k]); e = fminf(e, red[4][k]); f = fmaxf(f, red[5][k]);
+    }
+    S.stat[0] = wbar; S.stat[1] = bbar; S.stat[2] = a; S.stat[3] = c; S.stat[4] = e; S.stat[5] = f;
+  }
+  __syncthreads();
+}
+
+// One query against the T keys: p[t] = 2^(a2 w'[t] + c2 b'[t] + e2 + mask[t] - shift); returns the sums of
+// p, p w', p b' (and p w'^2, p w' b', p b'^2 when MOM).  `shift` is an upper bound of the unmasked logits.
+template <bool MOM>
+__device__ __forceinline__ void xf_row(const float4* __restrict__ tab, int T, float a2, float c2, float e2s, float& sum,
+                                       float& s1, float& s2, float& s11, float& s12, float& s22) {
+  sum = s1 = s2 = s11 = s12 = s22 = 0.f;
+#pragma unroll 4
+  for (int t = 0; t < T; t++) {
+    const float4 k = tab[t];
+    const float p = xf_ex2(fmaf(a2, k.x, fmaf(c2, k.y, e2s)) + k.z);
+    const float pw = p * k.x, pb = p * k.y;
+    sum += p; s1 += pw; s2 += pb;
+    if (MOM) { s11 = fmaf(pw, k.x, s11); s12 = fmaf(pw, k.y, s12); s22 = fmaf(pb, k.y, s22); }
+  }
+}
+// Softmax statistics of one query.  The shift is the sum of the per-term maxima (no pass over the keys); if that
+// bound is so loose that everything underflows - or every key is masked, where the reference's additive -1e9 makes
+// the row uniform - the exact maximum is taken instead.
+template <bool MOM>
+__device__ __forceinline__ float xf_softmax(const XfShared& S, int T, float a2, float c2, float e2, float& sum, float& s1,
+                                            float& s2, float& s11, float& s12, float& s22) {
+  float shift = fmaxf(a2 * S.stat[2], a2 * S.stat[3]) + fmaxf(c2 * S.stat[4], c2 * S.stat[5]) + e2;
+  xf_row<MOM>(S.tab, T, a2, c2, e2 - shift, sum, s1, s2, s11, s12, s22);
+  if (!(sum > 1e-30f)) {
+    float mx = -INFINITY;
+    for (int t = 0; t < T; t++) {
+      const float4 k = S.tab[t];
+      mx = fmaxf(mx, fmaf(a2, k.x, fmaf(c2, k.y, e2)) + k.z);
+    }
+    // (x + mask) - mx in the order the reference adds them: a fully masked row collapses to p = 1 everywhere
+    shift = mx;
+    sum = s1 = s2 = s11 = s12 = s22 = 0.f;
+    for (int t = 0; t < T; t++) {
+      const float4 k = S.tab[t];
+      const float p = xf_ex2((fmaf(a2, k.x, fmaf(c2, k.y, e2)) + k.z) - mx);
+      const float pw = p * k.x, pb = p * k.y;
+      sum += p; s1 += pw; s2 += pb;
+      if (MOM) { s11 = fmaf(pw, k.x, s11); s12 = fmaf(pw, k.y, s12); s22 = fmaf(pb, k.y, s22); }
+    }
+  }
+  return shift;
+}
+
+// forward: one thread per query
+template <int DH>
+__global__ void __launch_bounds__(128)
 xattn_fold_fwd_k(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ U, const float* __restrict__ s,
                  const float* __restrict__ bias, const float* __restrict__ w, const float* __restrict__ beta,
                  const uint8_t* __restrict__ key_pad, float* __restrict__ O, int64_t ldo, int Tq, int T, int d,
                  float scale) {
-  extern __shared__ float sm[];          // w[T] | beta[T] | mask[T]
-  float* ws = sm;
-  float* bs = sm + T;
-  float* ms = sm + 2 * T;
+  extern __shared__ float4 sm4[];
+  XfShared S;
+  S.tab = sm4;
+  S.vec = reinterpret_cast<float*>(sm4 + T);
+  S.stat = S.vec + 6 * DH;
   const int h = blockIdx.x, b = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    ws[t] = w[t];
-    bs[t] = beta[t];
-    ms[t] = (key_pad && key_pad[(int64_t)b * T + t]) ? -1e9f : 0.f;
+  xf_setup<DH>(S, U, s, bias, w, beta, key_pad, b, h, T, d);
+  const int q = blockIdx.z * blockDim.x + threadIdx.x;
+  if (q >= Tq) return;
+  const float4* qr = reinterpret_cast<const float4*>(Q + ((int64_t)b * Tq + q) * ldq + h * DH);
+  const float4* uk = reinterpret_cast<const float4*>(S.vec);
+  const float4* sk = reinterpret_cast<const float4*>(S.vec + DH);
+  const float4* bk = reinterpret_cast<const float4*>(S.vec + 2 * DH);
+  float a = 0.f, c = 0.f, e = 0.f;
+#pragma unroll
+  for (int j = 0; j < DH / 4; j++) {
+    const float4 x = qr[j], u = uk[j], v = sk[j], z = bk[j];
+    a += (x.x * u.x + x.y * u.y) + (x.z * u.z + x.w * u.w);
+    c += (x.x * v.x + x.y * v.y) + (x.z * v.z + x.w * v.w);
+    e += (x.x * z.x + x.y * z.y) + (x.z * z.z + x.w * z.w);
   }
-  XFold<DH> c;
-  c.load(U, s, bias, b, h, d, lane);
-  __syncthreads();
-  constexpr int EPL = XFold<DH>::EPL;
-  for (int q = blockIdx.z * nw + warp; q < Tq; q += nw * gridDim.z) {
-    const float* qr = Q + ((int64_t)b * Tq + q) * ldq + h * DH;
-    float a = 0.f, cb = 0.f, ce = 0.f;
+  const float k2 = scale * XF_LOG2E;
+  const float a2 = a * k2, c2 = c * k2;
+  const float e2 = fmaf(a2, S.stat[0], fmaf(c2, S.stat[1], e * k2));     // centring constants folded into the offset
+  float sum, s1, s2, s11, s12, s22;
+  xf_softmax<false>(S, T, a2, c2, e2, sum, s1, s2, s11, s12, s22);
+  const float inv = 1.0f / sum, m1 = fmaf(s1, inv, S.stat[0]), m2 = fmaf(s2, inv, S.stat[1]);
+  float4* orow = reinterpret_cast<float4*>(O + ((int64_t)b * Tq + q) * ldo + h * DH);
+  const float4* uv = reinterpret_cast<const float4*>(S.vec + 3 * DH);
+  const float4* sv = reinterpret_cast<const float4*>(S.vec + 4 * DH);
+  const float4* bv = reinterpret_cast<const float4*>(S.vec + 5 * DH);
 #pragma unroll
-    for (int e = 0; e < EPL; e++) {
-      const int j = lane + 32 * e;
-      const float qv = j < DH ? qr[j] : 0.f;
-      a = fmaf(qv, c.uk[e], a); cb = fmaf(qv, c.sk[e], cb); ce = fmaf(qv, c.bk[e], ce);
-    }
-    a = warp_sum(a) * scale; cb = warp_sum(cb) * scale; ce = warp_sum(ce) * scale;
-    float mx = -INFINITY;
-    for (int t = lane; t < T; t += 32) mx = fmaxf(mx, (fmaf(a, ws[t], fmaf(cb, bs[t], ce))) + ms[t]);
-    mx = warp_max(mx);
-    float sum = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int t = lane; t < T; t += 32) {
-      const float p = __expf((fmaf(a, ws[t], fmaf(cb, bs[t], ce)) + ms[t]) - mx);
-      sum += p; s1 = fmaf(p, ws[t], s1); s2 = fmaf(p, bs[t], s2);
-    }
-    sum = warp_sum(sum); s1 = warp_sum(s1); s2 = warp_sum(s2);
-    const float inv = 1.0f / sum, m1 = s1 * inv, m2 = s2 * inv;
-    float* orow = O + ((int64_t)b * Tq + q) * ldo + h * DH;
-#pragma unroll
-    for (int e = 0; e < EPL; e++) {
-      const int j = lane + 32 * e;
-      if (j < DH) orow[j] = fmaf(m1, c.uv[e], fmaf(m2, c.sv[e], c.bv[e]));
-    }
+  for (int j = 0; j < DH / 4; j++) {
+    const float4 u = uv[j], v = sv[j], z = bv[j];
+    orow[j] = make_float4(fmaf(m1, u.x, fmaf(m2, v.x, z.x)), fmaf(m1, u.y, fmaf(m2, v.y, z.y)),
+                          fmaf(m1, u.z, fmaf(m2, v.z, z.z)), fmaf(m1, u.w, fmaf(m2, v.w, z.w)));
   }
 }
 
-// Backward of the above for one (head, sample): dQ per query, and the sums over its queries of the gradients of
-// UKh / UVh (stored: this CTA owns those columns of gU), sKh / sVh / bVh (atomics over samples) and of w[t],
-// beta[t] (per-warp shared-memory rows, then atomics).  The key bias has zero gradient (softmax is shift-invariant).
+// backward for one (head, sample), queries in chunks of blockDim:
+//   phase 1 (thread = query)  scalars a, c, dm1 = dO.UVh, dm2 = dO.sVh, softmax moments -> dQ, and a record per query
+//   phase 2 (thread = key t)  gw[t], gbeta[t] += sum_q p_q[t] (dm + coef (dm1 w'[t] + dm2 b'[t] - K_q))
+//   phase 3 (thread = column) sums over q of  da Q, dc Q, m1 dO, m2 dO, dO  -> gU (stored), gs, gbias (atomics)
+// The key bias has zero gradient (softmax is shift-invariant).
 template <int DH>
 __global__ void __launch_bounds__(256)
 xattn_fold_bwd_k(const float* __restrict__ Q, int64_t ldq, const float* __restrict__ U, const float* __restrict__ s,
@@ -917,86 +996,95 @@ xattn_fold_bwd_k(const float* __restrict__ Q, int64_t ldq, const float* __restri
                  float* __restrict__ dQ, int64_t lddq, float* __restrict__ gU, float* __restrict__ gs,
                  float* __restrict__ gbias, float* __restrict__ gw, float* __restrict__ gbeta, int Tq, int T, int d,
                  float scale) {
-  extern __shared__ float sm[];          // w[T] | beta[T] | mask[T] | gw rows [nw][T] | gbeta rows [nw][T] | red
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float* ws = sm;
-  float* bs = sm + T;
-  float* ms = sm + 2 * T;
-  float* gwr = sm + 3 * T + warp * T;
-  float* gbr = sm + 3 * T + nw * T + warp * T;
-  float* red = sm + 3 * T + 2 * nw * T;  // [5][DH]
-  const int h = blockIdx.x, b = blockIdx.y;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    ws[t] = w[t];
-    bs[t] = beta[t];
-    ms[t] = (key_pad && key_pad[(int64_t)b * T + t]) ? -1e9f : 0.f;
+  extern __shared__ float4 sm4[];
+  XfShared S;
+  S.tab = sm4;
+  float4* rec = sm4 + T;                                   // [3][blockDim]
+  const int Tp = (T + 3) & ~3;                             // keeps the float4 vectors below 16-byte aligned
+  float* gws = reinterpret_cast<float*>(rec + 3 * blockDim.x);   // [Tp]
+  float* gbs = gws + Tp;                                   // [Tp]
+  float* red = gbs + Tp;                                   // [5][DH]
+  S.vec = red + 5 * DH;
+  S.stat = S.vec + 6 * DH;
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+  for (int t = tid; t < T; t += nthr) gws[t] = gbs[t] = 0.f;
+  for (int i = tid; i < 5 * DH; i += nthr) red[i] = 0.f;
+  xf_setup<DH>(S, U, s, bias, w, beta, key_pad, b, h, T, d);
+  const float k2 = scale * XF_LOG2E;
+  for (int q0 = 0; q0 < Tq; q0 += nthr) {
+    const int q = q0 + tid, nq = min(nthr, Tq - q0);
+    // ---- phase 1
+    if (q < Tq) {
+      const float4* qr = reinterpret_cast<const float4*>(Q + ((int64_t)b * Tq + q) * ldq + h * DH);
+      const float4* gr = reinterpret_cast<const float4*>(dO + ((int64_t)b * Tq + q) * lddo + h * DH);
+      const float4* v4 = reinterpret_cast<const float4*>(S.vec);
+      float a = 0.f, c = 0.f, e = 0.f, dm1 = 0.f, dm2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < DH / 4; j++) {
+        const float4 x = qr[j], g = gr[j];
+        const float4 u = v4[j], v = v4[DH / 4 + j], z = v4[2 * DH / 4 + j], uv = v4[3 * DH / 4 + j], sv = v4[4 * DH / 4 + j];
+        a += (x.x * u.x + x.y * u.y) + (x.z * u.z + x.w * u.w);
+        c += (x.x * v.x + x.y * v.y) + (x.z * v.z + x.w * v.w);
+        e += (x.x * z.x + x.y * z.y) + (x.z * z.z + x.w * z.w);
+        dm1 += (g.x * uv.x + g.y * uv.y) + (g.z * uv.z + g.w * uv.w);
+        dm2 += (g.x * sv.x + g.y * sv.y) + (g.z * sv.z + g.w * sv.w);
+      }
+      const float a2 = a * k2, c2 = c * k2;
+      const float e2 = fmaf(a2, S.stat[0], fmaf(c2, S.stat[1], e * k2));
+      float sum, s1, s2, s11, s12, s22;
+      const float shift = xf_softmax<true>(S, T, a2, c2, e2, sum, s1, s2, s11, s12, s22);
+      const float inv = 1.0f / sum, m1 = s1 * inv, m2 = s2 * inv;          // centred means
+      const float v11 = fmaf(s11, inv, -m1 * m1), v12 = fmaf(s12, inv, -m1 * m2), v22 = fmaf(s22, inv, -m2 * m2);
+      const float da = fmaf(dm1, v11, dm2 * v12) * scale, dc = fmaf(dm1, v12, dm2 * v22) * scale;
+      // logits carry 1/sqrt(dh): a_true = a scale, so d(logit)/dw[t] = a scale
+      float4* dqr = reinterpret_cast<float4*>(dQ + ((int64_t)b * Tq + q) * lddq + h * DH);
+#pragma unroll
+      for (int j = 0; j < DH / 4; j++) {
+        const float4 u = v4[j], v = v4[DH / 4 + j];
+        dqr[j] = make_float4(fmaf(da, u.x, dc * v.x), fmaf(da, u.y, dc * v.y), fmaf(da, u.z, dc * v.z),
+                             fmaf(da, u.w, dc * v.w));
+      }
+      rec[tid] = make_float4(a2, c2, e2 - shift + log2f(inv), dm1);
+      rec[nthr + tid] = make_float4(dm2, fmaf(dm1, m1, dm2 * m2), a * scale, c * scale);
+      rec[2 * nthr + tid] = make_float4(da, dc, m1 + S.stat[0], m2 + S.stat[1]);
+    }
+    __syncthreads();
+    // ---- phase 2
+    for (int t = tid; t < T; t += nthr) {
+      const float4 k = S.tab[t];
+      float accw = 0.f, accb = 0.f;
+#pragma unroll 2
+      for (int i = 0; i < nq; i++) {
+        const float4 r0 = rec[i], r1 = rec[nthr + i];
+        const float p = xf_ex2(fmaf(r0.x, k.x, fmaf(r0.y, k.y, r0.z)) + k.z);
+        const float x = fmaf(r0.w, k.x, fmaf(r1.x, k.y, -r1.y));
+        accw = fmaf(p, fmaf(r1.z, x, r0.w), accw);
+        accb = fmaf(p, fmaf(r1.w, x, r1.x), accb);
+      }
+      gws[t] += accw;
+      gbs[t] += accb;
+    }
+    // ---- phase 3: a warp takes every (nthr/32)-th query of the chunk, a lane the columns j, j + 32, ...
+    {
+      const int lane = tid & 31, wp = tid >> 5, nwp = nthr >> 5;
+      const float* qb = Q + ((int64_t)b * Tq + q0) * ldq + h * DH;
+      const float* gb = dO + ((int64_t)b * Tq + q0) * lddo + h * DH;
+      for (int j = lane; j < DH; j += 32) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll 4
+        for (int i = wp; i < nq; i += nwp) {
+          const float4 r2 = rec[2 * nthr + i];
+          const float x = qb[(int64_t)i * ldq + j], g = gb[(int64_t)i * lddo + j];
+          a0 = fmaf(r2.x, x, a0); a1 = fmaf(r2.y, x, a1);
+          a2 = fmaf(r2.z, g, a2); a3 = fmaf(r2.w, g, a3); a4 += g;
+        }
+        atomicAdd(red + j, a0); atomicAdd(red + DH + j, a1); atomicAdd(red + 2 * DH + j, a2);
+        atomicAdd(red + 3 * DH + j, a3); atomicAdd(red + 4 * DH + j, a4);
+      }
+    }
+    __syncthreads();
   }
-  for (int i = threadIdx.x; i < 2 * nw * T + 5 * DH; i += blockDim.x) sm[3 * T + i] = 0.f;
-  XFold<DH> c;
-  c.load(U, s, bias, b, h, d, lane);
-  __syncthreads();
-  constexpr int EPL = XFold<DH>::EPL;
-  float guk[EPL], gsk[EPL], guv[EPL], gsv[EPL], gbv[EPL];
-#pragma unroll
-  for (int e = 0; e < EPL; e++) guk[e] = gsk[e] = guv[e] = gsv[e] = gbv[e] = 0.f;
-  for (int q = warp; q < Tq; q += nw) {
-    const float* qr = Q + ((int64_t)b * Tq + q) * ldq + h * DH;
-    const float* gr = dO + ((int64_t)b * Tq + q) * lddo + h * DH;
-    float qv[EPL], gv[EPL];
-    float a = 0.f, cb = 0.f, ce = 0.f, dm1 = 0.f, dm2 = 0.f;
-#pragma unroll
-    for (int e = 0; e < EPL; e++) {
-      const int j = lane + 32 * e;
-      qv[e] = j < DH ? qr[j] : 0.f;
-      gv[e] = j < DH ? gr[j] : 0.f;
-      a = fmaf(qv[e], c.uk[e], a); cb = fmaf(qv[e], c.sk[e], cb); ce = fmaf(qv[e], c.bk[e], ce);
-      dm1 = fmaf(gv[e], c.uv[e], dm1); dm2 = fmaf(gv[e], c.sv[e], dm2);
-    }
-    a = warp_sum(a) * scale; cb = warp_sum(cb) * scale; ce = warp_sum(ce) * scale;
-    dm1 = warp_sum(dm1); dm2 = warp_sum(dm2);
-    float mx = -INFINITY;
-    for (int t = lane; t < T; t += 32) mx = fmaxf(mx, (fmaf(a, ws[t], fmaf(cb, bs[t], ce))) + ms[t]);
-    mx = warp_max(mx);
-    float sum = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int t = lane; t < T; t += 32) {
-      const float p = __expf((fmaf(a, ws[t], fmaf(cb, bs[t], ce)) + ms[t]) - mx);
-      sum += p; s1 = fmaf(p, ws[t], s1); s2 = fmaf(p, bs[t], s2);
-    }
-    sum = warp_sum(sum); s1 = warp_sum(s1); s2 = warp_sum(s2);
-    const float inv = 1.0f / sum, m1 = s1 * inv, m2 = s2 * inv;
-    // dl[t] = P[t] (dm1 (w[t] - m1) + dm2 (beta[t] - m2)); da = sum dl w, dc = sum dl beta (centred: no cancellation)
-    float da = 0.f, dc = 0.f;
-    for (int t = lane; t < T; t += 32) {
-      const float p = __expf((fmaf(a, ws[t], fmaf(cb, bs[t], ce)) + ms[t]) - mx) * inv;
-      const float dl = p * fmaf(dm1, ws[t] - m1, dm2 * (bs[t] - m2));
-      da = fmaf(dl, ws[t] - m1, da);
-      dc = fmaf(dl, bs[t] - m2, dc);
-      gwr[t] += fmaf(p, dm1, dl * a);
-      gbr[t] += fmaf(p, dm2, dl * cb);
-    }
-    da = warp_sum(da); dc = warp_sum(dc);
-    float* dqr = dQ + ((int64_t)b * Tq + q) * lddq + h * DH;
-#pragma unroll
-    for (int e = 0; e < EPL; e++) {
-      const int j = lane + 32 * e;
-      if (j < DH) dqr[j] = scale * fmaf(da, c.uk[e], dc * c.sk[e]);
-      guk[e] = fmaf(scale * da, qv[e], guk[e]);
-      gsk[e] = fmaf(scale * dc, qv[e], gsk[e]);
-      guv[e] = fmaf(m1, gv[e], guv[e]);
-      gsv[e] = fmaf(m2, gv[e], gsv[e]);
-      gbv[e] += gv[e];
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < EPL; e++) {
-    const int j = lane + 32 * e;
-    if (j < DH) {
-      atomicAdd(red + j, guk[e]); atomicAdd(red + DH + j, gsk[e]); atomicAdd(red + 2 * DH + j, guv[e]);
-      atomicAdd(red + 3 * DH + j, gsv[e]); atomicAdd(red + 4 * DH + j, gbv[e]);
-    }
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < DH; j += blockDim.x) {
+  for (int j = tid; j < DH; j += nthr) {
     const int ck = h * DH + j, cv = d + h * DH + j;
     gU[(int64_t)b * 2 * d + ck] = red[j];
     gU[(int64_t)b * 2 * d + cv] = red[2 * DH + j];
@@ -1004,13 +1092,9 @@ xattn_fold_bwd_k(const float* __restrict__ Q, int64_t ldq, const float* __restri
     atomicAdd(gs + cv, red[3 * DH + j]);
     if (gbias) atomicAdd(gbias + cv, red[4 * DH + j]);
   }
-  const float* gw_all = sm + 3 * T;
-  const float* gb_all = sm + 3 * T + nw * T;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    float x = 0.f, y = 0.f;
-    for (int k = 0; k < nw; k++) { x += gw_all[k * T + t]; y += gb_all[k * T + t]; }
-    atomicAdd(gw + t, x);
-    atomicAdd(gbeta + t, y);
+  for (int t = tid; t < T; t += nthr) {
+    atomicAdd(gw + t, gws[t]);
+    atomicAdd(gbeta + t, gbs[t]);
   }
 }
 
@@ -1298,12 +1382,14 @@ int skf_xattn_fold_fwd(const float* Q, int64_t ldq, const float* U, const float*
   SKF_REQUIRE(Q && U && s && w && beta && O && B > 0 && H > 0 && Tq > 0 && T > 0, SKF_ERR_BAD_ARG,
               "xattn_fold_fwd: bad argument");
   SKF_REQUIRE(dh == 16 || dh == 32 || dh == 64, SKF_ERR_UNSUPPORTED, "xattn_fold_fwd: head dim %d", dh);
-  const size_t smem = (size_t)3 * T * sizeof(float);
-  const int qz = Tq >= 64 && B * H < 2 * 148 ? 2 : 1;
+  SKF_REQUIRE(((ldq | ldo) & 3) == 0 && ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(O)) & 15) == 0,
+              SKF_ERR_BAD_ALIGN, "xattn_fold_fwd: Q / O must be 16-byte aligned with row strides that are multiples of 4");
+  const size_t smem = (size_t)T * 16 + (6 * dh + 8) * sizeof(float);
+  SKF_REQUIRE(smem <= 48 * 1024, SKF_ERR_UNSUPPORTED, "xattn_fold_fwd: T = %d too long", T);
   const float scale = 1.0f / sqrtf((float)dh);
   cudaStream_t st = as_stream(stream);
-  SKF_XFOLD_DISPATCH(xattn_fold_fwd_k, <<<dim3(H, B, qz), 256, smem, st>>>(Q, ldq, U, s, bias, w, beta, key_pad, O, ldo,
-                                                                            Tq, T, H * dh, scale));
+  SKF_XFOLD_DISPATCH(xattn_fold_fwd_k, <<<dim3(H, B, cdiv(Tq, 128)), 128, smem, st>>>(Q, ldq, U, s, bias, w, beta, key_pad,
+                                                                                      O, ldo, Tq, T, H * dh, scale));
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -1315,19 +1401,17 @@ int skf_xattn_fold_bwd(const float* Q, int64_t ldq, const float* U, const float*
   SKF_REQUIRE(Q && U && s && w && beta && dO && dQ && gU && gs && gw && gbeta && B > 0 && H > 0 && Tq > 0 && T > 0,
               SKF_ERR_BAD_ARG, "xattn_fold_bwd: bad argument");
   SKF_REQUIRE(dh == 16 || dh == 32 || dh == 64, SKF_ERR_UNSUPPORTED, "xattn_fold_bwd: head dim %d", dh);
-  const int nw = 8;
-  const size_t smem = ((size_t)3 * T + 2 * nw * T + 5 * dh) * sizeof(float);
-  SKF_REQUIRE(smem <= 200 * 1024, SKF_ERR_UNSUPPORTED, "xattn_fold_bwd: T = %d too long", T);
+  SKF_REQUIRE(((ldq | lddo | lddq) & 3) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(dO) | reinterpret_cast<uintptr_t>(dQ)) & 15) == 0,
+              SKF_ERR_BAD_ALIGN, "xattn_fold_bwd: Q / dO / dQ must be 16-byte aligned with row strides that are multiples of 4");
+  const int nthr = 256;
+  const size_t smem = (size_t)T * 16 + (size_t)3 * nthr * 16 + ((size_t)2 * ((T + 3) & ~3) + 11 * dh + 8) * sizeof(float);
+  SKF_REQUIRE(smem <= 48 * 1024, SKF_ERR_UNSUPPORTED, "xattn_fold_bwd: T = %d too long", T);
   const float scale = 1.0f / sqrtf((float)dh);
   cudaStream_t st = as_stream(stream);
-  if (smem > 48 * 1024) {
-    if (dh == 16) SKF_CUDA(cudaFuncSetAttribute(xattn_fold_bwd_k<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else if (dh == 32) SKF_CUDA(cudaFuncSetAttribute(xattn_fold_bwd_k<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else SKF_CUDA(cudaFuncSetAttribute(xattn_fold_bwd_k<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  SKF_XFOLD_DISPATCH(xattn_fold_bwd_k, <<<dim3(H, B), 32 * nw, smem, st>>>(Q, ldq, U, s, bias, w, beta, key_pad, dO, lddo,
-                                                                            dQ, lddq, gU, gs, gbias, gw, gbeta, Tq, T,
-                                                                            H * dh, scale));
+  SKF_XFOLD_DISPATCH(xattn_fold_bwd_k, <<<dim3(H, B), nthr, smem, st>>>(Q, ldq, U, s, bias, w, beta, key_pad, dO, lddo, dQ,
+                                                                        lddq, gU, gs, gbias, gw, gbeta, Tq, T, H * dh,
+                                                                        scale));
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
