@@ -157,20 +157,31 @@ __device__ __forceinline__ uint64_t make_desc16_kmajor(uint32_t addr) { return m
 __device__ __forceinline__ uint64_t make_desc16_mnmajor(uint32_t addr, uint32_t chunk) {
   return make_smem_desc(addr, chunk, 512, 4);
 }
-// 8 consecutive fp32 values -> 8 bf16 of x (hi) and 8 bf16 of x - trunc_tf32(x) (lo), 16 bytes each
+// 8 consecutive fp32 values -> 8 bf16 of x (hi) and 8 bf16 of the residual (lo), 16 bytes each.
+//   BF3 = false: lo = x - trunc_tf32(x)   (the main term is a TF32 MMA on the raw tile)
+//   BF3 = true : lo = x - bf16(x)         (the main term is the bf16 MMA hi * hi)
+template <bool BF3>
 __device__ __forceinline__ void t3_to_bf16_pair(const float4& u, const float4& v, uint4& hi, uint4& lo) {
   auto pk = [](float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
   };
   hi = make_uint4(pk(u.x, u.y), pk(u.z, u.w), pk(v.x, v.y), pk(v.z, v.w));
-  auto l = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
-  lo = make_uint4(pk(l(u.x), l(u.y)), pk(l(u.z), l(u.w)), pk(l(v.x), l(v.y)), pk(l(v.z), l(v.w)));
+  if (BF3) {
+    // a bf16 is the top half of an fp32: the residuals x - float(bf16(x)) are exact in fp32
+    auto l2 = [&](float a, float b, uint32_t h) {
+      return pk(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xFFFF0000u));
+    };
+    lo = make_uint4(l2(u.x, u.y, hi.x), l2(u.z, u.w, hi.y), l2(v.x, v.y, hi.z), l2(v.z, v.w, hi.w));
+  } else {
+    auto l = [](float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); };
+    lo = make_uint4(pk(l(u.x), l(u.y)), pk(l(u.z), l(u.w)), pk(l(v.x), l(v.y)), pk(l(v.z), l(v.w)));
+  }
 }
 // One operand tile of the mixed scheme: fp32 tile `src` (K-major: ROWS rows of 128 B under the 128B swizzle;
 // MN-major: ROWS/32 boxes of 32 k-rows under the 32B-atom swizzle) -> bf16 hi / lo tiles with 64-byte rows.
 // 128 threads, thread `tid`; tasks = ROWS * 4 groups of 8 elements.
-template <int ROWS, bool MN>
+template <int ROWS, bool MN, bool BF3>
 __device__ __forceinline__ void t3_split_bf16(const uint8_t* src, uint8_t* hi16, uint8_t* lo16, int tid) {
 #pragma unroll
   for (int task = tid; task < ROWS * 4; task += 128) {
@@ -186,7 +197,7 @@ __device__ __forceinline__ void t3_split_bf16(const uint8_t* src, uint8_t* hi16,
     const float4 w1 = *reinterpret_cast<const float4*>(rowp + (((2 * g + 1 - first) ^ sx) << 4));
     const float4 u = first ? w1 : w0, v = first ? w0 : w1;
     uint4 h, l;
-    t3_to_bf16_pair(u, v, h, l);
+    t3_to_bf16_pair<BF3>(u, v, h, l);
     const uint32_t dof = r * 64 + ((g ^ ((rs >> 1) & 3)) << 4);
     *reinterpret_cast<uint4*>(hi16 + dof) = h;
     *reinterpret_cast<uint4*>(lo16 + dof) = l;
@@ -221,7 +232,13 @@ __device__ __forceinline__ float t3_trunc_tf32(float x) { return __uint_as_float
 // Xl = X - trunc_tf32(X).  A cross term is ~2^-11 of the product, so bf16's 2^-9 on its factors costs 2^-20:
 // the result keeps 3xTF32 accuracy for two TF32-pass equivalents instead of three.  The splitter writes four
 // bf16 tiles (hi/lo of A and of this CTA's B half, 32 KB) where the plain scheme keeps two fp32 lo tiles.
-template <int T3_BN, bool A_MN, bool B_MN, bool MIX>
+// MIX = 2 (bf16x3): all three terms as bf16 MMAs on the splitter's hi / lo tiles,
+//   A*B ~= bf16(A)*bf16(B) + bf16(A)*bf16(Bl) + bf16(Al)*bf16(B),  Xl = X - bf16(X)  (exact in fp32).
+// Dropped: Al*Bl and the bf16 rounding of the two residuals, each <= 2^-18 of the product (3 * 2^-18 = 1.1e-5 worst
+// case per product, random sign) -- far below the 1.4e-4 end-to-end floor set by attention's TF32-rounded P -- for
+// three bf16-rate passes instead of one TF32 + two bf16 (= four bf16-rate passes), and the tensor cores read only
+// the 32 KB of bf16 tiles per stage (the raw fp32 tiles feed the splitter alone).
+template <int T3_BN, bool A_MN, bool B_MN, int MIX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T3_THREADS, 1)
 gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
         const __grid_constant__ CUtensorMap tmY, const Gemm3Params p) {
@@ -354,9 +371,10 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
               const uint64_t bld = B_MN ? make_desc16_mnmajor(bl16 + bo, 2048) : make_desc16_kmajor(bl16 + bo);
               mma2_bf16_ss(acc, ahd, bld, idesc16, (i | k2) != 0 ? 1u : 0u);
               mma2_bf16_ss(acc, ald, bhd, idesc16, 1u);
+              if (MIX == 2) mma2_bf16_ss(acc, ahd, bhd, idesc16, 1u);      // bf16x3: main term on the hi tiles
             }
 #pragma unroll
-            for (int ks = 0; ks < T3_BK / 8; ks++) {                       // main term: tf32 on the raw tiles
+            for (int ks = 0; ks < (MIX == 2 ? 0 : T3_BK / 8); ks++) {      // main term: tf32 on the raw tiles
               const uint32_t ao = A_MN ? ks * 1024 : ks * 32;
               const uint32_t bo = B_MN ? ks * 1024 : ks * 32;
               const uint64_t ad = A_MN ? make_desc_mnmajor(a_s + ao, 4096) : make_desc_kmajor(a_s + ao);
@@ -519,8 +537,8 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           uint8_t* al16 = ah16 + T3_A_BYTES / 2;
           uint8_t* bh16 = al16 + T3_A_BYTES / 2;
           uint8_t* bl16 = bh16 + C::B_BYTES / 2;
-          t3_split_bf16<T3_BM, A_MN>(st8, ah16, al16, tid);
-          t3_split_bf16<T3_BNH, B_MN>(st8 + T3_A_BYTES, bh16, bl16, tid);
+          t3_split_bf16<T3_BM, A_MN, MIX == 2>(st8, ah16, al16, tid);
+          t3_split_bf16<T3_BNH, B_MN, MIX == 2>(st8 + T3_A_BYTES, bh16, bl16, tid);
           if (B_MN && do_colsum) {
 #pragma unroll
             for (int ib = 0; ib < 2 * NBOX; ib++) {
@@ -582,11 +600,11 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 
 // ---- host side ---------------------------------------------------------------------------------
 static int g3_clusters = 0;
-int g_gemm_mix = 1;       // 1: cross terms of the 3xTF32 product as bf16 MMAs (see gemm3_k MIX)
+int g_gemm_mix = 2;       // 1: cross terms of the 3xTF32 product as bf16 MMAs, 2: all three terms bf16 (see gemm3_k MIX)
 
 int g_t3_oversubscribe = 0;
 
-template <int BN, bool A_MN, bool B_MN, bool MIX>
+template <int BN, bool A_MN, bool B_MN, int MIX>
 static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t st) {
   constexpr int T3_SMEM = Tc3Cfg<BN>::SMEM;
   static bool attr_done = false;
@@ -666,12 +684,16 @@ int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
     if (a_mn && !b_mn) return launch_tc3<BNV, true, false, MIXV>(tm, p, st);               \
     return launch_tc3<BNV, true, true, MIXV>(tm, p, st);                                   \
   } while (0)
-  if (g_gemm_mix) {
-    if (BN == 128) SKF_T3_DISPATCH(128, true);
-    SKF_T3_DISPATCH(256, true);
+  if (g_gemm_mix == 2) {
+    if (BN == 128) SKF_T3_DISPATCH(128, 2);
+    SKF_T3_DISPATCH(256, 2);
   }
-  if (BN == 128) SKF_T3_DISPATCH(128, false);
-  SKF_T3_DISPATCH(256, false);
+  if (g_gemm_mix) {
+    if (BN == 128) SKF_T3_DISPATCH(128, 1);
+    SKF_T3_DISPATCH(256, 1);
+  }
+  if (BN == 128) SKF_T3_DISPATCH(128, 0);
+  SKF_T3_DISPATCH(256, 0);
 #undef SKF_T3_DISPATCH
 }
 

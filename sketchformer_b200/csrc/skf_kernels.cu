@@ -556,6 +556,179 @@ __global__ void pool_bwd_k(const float* __restrict__ x, const float* __restrict_
   }
 }
 
+// Cluster form of the two pooling kernels: one CTA per sample leaves 128 CTAs of serial T-loops on 148 SMs (68 us
+// forward / 131 us backward at cfg2, for 26 MB / 131 MB of traffic).  A thread-block cluster of POOL_CL CTAs shares a
+// sample: CTA r owns rows [r * ceil(T / POOL_CL), ...), the softmax statistics / the a.da dot product are exchanged
+// through distributed shared memory (every CTA stores its partial into slot r of every peer, one cluster barrier),
+// and the T-reductions (pooled vector, dV) are summed by the cluster's CTA 0 from partials stored into its smem.
+constexpr int POOL_CL = 8;
+__device__ __forceinline__ uint32_t pool_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void pool_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store v at the address of local shared variable `p` in CTA `rank` of the cluster
+__device__ __forceinline__ void pool_st_remote(float* p, uint32_t rank, float v) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+// block-wide reduction whose result every thread gets; `red` holds one float per warp
+__device__ __forceinline__ float pool_block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = is_max ? -INFINITY : 0.f;
+  for (int i = 0; i < nw; i++) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __cluster_dims__(POOL_CL, 1, 1) __launch_bounds__(256)
+pool_fwd_cl_k(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ vattn,
+              float* __restrict__ a_out, float* __restrict__ emb, int T, int d, int U, int rnd) {
+  extern __shared__ float sm[];   // sc[chunk] | red[32] | xmax[POOL_CL] | xsum[POOL_CL] | gather[POOL_CL * d]
+  const int chunk = (T + POOL_CL - 1) / POOL_CL;
+  float* sc = sm;
+  float* red = sc + chunk;
+  float* xmax = red + 32;
+  float* xsum = xmax + POOL_CL;
+  float* gather = xsum + POOL_CL;
+  const uint32_t r = pool_cta_rank();
+  const int b = blockIdx.x / POOL_CL;
+  const int t0 = min(T, (int)r * chunk), n = min(T, t0 + chunk) - t0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // scores of this CTA's rows: warp per row
+  for (int i = w; i < n; i += nw) {
+    const float* ur = u + ((int64_t)b * T + t0 + i) * U;
+    float acc = 0.f;
+    for (int j = lane; j < U; j += 32) acc += ur[j] * __ldg(vattn + j);
+    acc = warp_sum(acc);
+    if (lane == 0) sc[i] = acc;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, sc[i]);
+  mx = pool_block_reduce(mx, red, true);
+  if (threadIdx.x < POOL_CL) pool_st_remote(xmax + r, threadIdx.x, mx);
+  pool_cluster_sync();
+  mx = xmax[0];
+#pragma unroll
+  for (int i = 1; i < POOL_CL; i++) mx = fmaxf(mx, xmax[i]);
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float e = expf(sc[i] - mx);
+    sc[i] = e;
+    sum += e;
+  }
+  sum = pool_block_reduce(sum, red, false);
+  if (threadIdx.x < POOL_CL) pool_st_remote(xsum + r, threadIdx.x, sum);
+  pool_cluster_sync();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < POOL_CL; i++) sum += xsum[i];
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float pa = sc[i] * inv;
+    sc[i] = pa;
+    a_out[(int64_t)b * T + t0 + i] = pa;
+  }
+  __syncthreads();
+  // partial pooled vector over this CTA's rows -> slot r of CTA 0
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float* xb = x + ((int64_t)b * T + t0) * d + c;
+    float acc = 0.f;
+#pragma unroll 5
+    for (int i = 0; i < n; i++) acc += sc[i] * xb[(int64_t)i * d];
+    pool_st_remote(gather + r * d + c, 0, acc);
+  }
+  pool_cluster_sync();
+  if (r == 0) {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < POOL_CL; i++) acc += gather[i * d + c];
+      emb[(int64_t)b * d + c] = maybe_round(acc, rnd);
+    }
+  }
+}
+
+__global__ void __cluster_dims__(POOL_CL, 1, 1) __launch_bounds__(256)
+pool_bwd_cl_k(const float* __restrict__ x, const float* __restrict__ u, const float* __restrict__ vattn,
+              const float* __restrict__ a, const float* __restrict__ demb, float* __restrict__ dx, int dx_acc,
+              float* __restrict__ dupre, float* __restrict__ dvattn, int T, int d, int U, int rnd) {
+  extern __shared__ float sm[];   // da[chunk] | at[chunk] | red[32] | xdot[POOL_CL] | gather[POOL_CL * U]
+  const int chunk = (T + POOL_CL - 1) / POOL_CL;
+  float* da = sm;
+  float* at = da + chunk;
+  float* red = at + chunk;
+  float* xdot = red + 32;
+  float* gather = xdot + POOL_CL;
+  const uint32_t r = pool_cta_rank();
+  const int b = blockIdx.x / POOL_CL;
+  const int t0 = min(T, (int)r * chunk), n = min(T, t0 + chunk) - t0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* de = demb + (int64_t)b * d;
+  // da_t = demb . x_t for this CTA's rows
+  for (int i = w; i < n; i += nw) {
+    const float* xr = x + ((int64_t)b * T + t0 + i) * d;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc += xr[c] * de[c];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      da[i] = acc;
+      at[i] = a[(int64_t)b * T + t0 + i];
+    }
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dot += at[i] * da[i];
+  dot = pool_block_reduce(dot, red, false);
+  if (threadIdx.x < POOL_CL) pool_st_remote(xdot + r, threadIdx.x, dot);
+  pool_cluster_sync();
+  dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < POOL_CL; i++) dot += xdot[i];
+  // dscore_t = a_t (da_t - dot)   (softmax over t)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) da[i] = at[i] * (da[i] - dot);
+  __syncthreads();
+  // dx[b,t,c] (+)= a_t * demb_c
+  for (int i = w; i < n; i += nw) {
+    const float av = at[i];
+    float* dr = dx + ((int64_t)b * T + t0 + i) * d;
+    for (int c = lane; c < d; c += 32) {
+      const float v = av * de[c];
+      dr[c] = dx_acc ? dr[c] + v : v;
+    }
+  }
+  // dupre[b,t,j] = dscore_t * V_j * (1 - u^2);  dV_j += sum_t u[b,t,j] * dscore_t (partials summed by CTA 0)
+  for (int j = threadIdx.x; j < U; j += blockDim.x) {
+    const float vj = __ldg(vattn + j);
+    float acc = 0.f;
+#pragma unroll 5
+    for (int i = 0; i < n; i++) {
+      const int64_t o = ((int64_t)b * T + t0 + i) * U + j;
+      const float uu = u[o];
+      acc += uu * da[i];
+      dupre[o] = maybe_round(da[i] * vj * (1.0f - uu * uu), rnd);
+    }
+    pool_st_remote(gather + r * U + j, 0, acc);
+  }
+  pool_cluster_sync();
+  if (r == 0) {
+    for (int j = threadIdx.x; j < U; j += blockDim.x) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < POOL_CL; i++) acc += gather[i * U + j];
+      atomicAdd(dvattn + j, acc);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K8: DenseExpander (transformer.py:370-376): pre[b,t,c] = emb[b,c]*w[t] + beta[t]
 // ---------------------------------------------------------------------------------------------
@@ -1308,6 +1481,13 @@ int skf_colsum(const float* x, int64_t ldx, float* out, int M, int N, void* stre
 
 int skf_pool_fwd(const float* x, const float* u, const float* vattn, float* a, float* emb, int B,
                  int T, int d, int U, int round_tf32, void* stream) {
+  const int chunk = (T + POOL_CL - 1) / POOL_CL;
+  const size_t smc = (size_t)(chunk + 32 + 2 * POOL_CL + POOL_CL * d) * sizeof(float);
+  if (smc <= 48 * 1024) {
+    pool_fwd_cl_k<<<B * POOL_CL, 256, smc, as_stream(stream)>>>(x, u, vattn, a, emb, T, d, U, round_tf32);
+    SKF_LAUNCH_CHECK();
+    return SKF_OK;
+  }
   size_t sm = (T + 32) * sizeof(float);
   pool_fwd_k<<<B, 256, sm, as_stream(stream)>>>(x, u, vattn, a, emb, T, d, U, round_tf32);
   SKF_LAUNCH_CHECK();
@@ -1317,6 +1497,14 @@ int skf_pool_fwd(const float* x, const float* u, const float* vattn, float* a, f
 int skf_pool_bwd(const float* x, const float* u, const float* vattn, const float* a,
                  const float* demb, float* dx, int dx_accumulate, float* dupre, float* dvattn,
                  int B, int T, int d, int U, int round_tf32, void* stream) {
+  const int chunk = (T + POOL_CL - 1) / POOL_CL;
+  const size_t smc = (size_t)(2 * chunk + 32 + POOL_CL + POOL_CL * U) * sizeof(float);
+  if (smc <= 48 * 1024) {
+    pool_bwd_cl_k<<<B * POOL_CL, 256, smc, as_stream(stream)>>>(x, u, vattn, a, demb, dx, dx_accumulate, dupre,
+                                                                dvattn, T, d, U, round_tf32);
+    SKF_LAUNCH_CHECK();
+    return SKF_OK;
+  }
   size_t sm = (T + 32) * sizeof(float);
   pool_bwd_k<<<B, 256, sm, as_stream(stream)>>>(x, u, vattn, a, demb, dx, dx_accumulate, dupre, dvattn,
                                                T, d, U, round_tf32);

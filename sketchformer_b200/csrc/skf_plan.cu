@@ -1145,7 +1145,7 @@ int skf_split_lo(const float* x, float* lo, int64_t n, void* stream) {
 
 int skf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_mix") == 0) {
-    skf::g_gemm_mix = value ? 1 : 0;
+    skf::g_gemm_mix = value < 0 ? 0 : (value > 2 ? 2 : value);
     return SKF_OK;
   }
   if (name && strcmp(name, "kv_fold") == 0) {

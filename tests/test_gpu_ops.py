@@ -149,8 +149,11 @@ def test_colsum(lib):
     assert rel_err(out, x.double().sum(0)) < TOL_EXACT
 
 
-def test_pool_fwd_bwd(lib):
-    B, T, d, U = 6, 50, 128, 64
+@pytest.mark.parametrize("B,T,d,U", [(6, 50, 128, 64), (3, 5, 32, 16), (5, 200, 256, 256), (2, 64, 128, 128),
+                                     (2, 33, 2048, 64)])
+def test_pool_fwd_bwd(lib, B, T, d, U):
+    """SelfAttnV1 pooling (transformer.py:61-74) on clusters of 8 CTAs per sample (T not a multiple of 8, T < 8:
+    CTAs without rows) and, when the cluster's gather buffer would not fit (d = 2048), on one CTA per sample."""
     g = torch.Generator().manual_seed(2)
     x = torch.randn(B, T, d, generator=g).double().requires_grad_(True)
     p = {"pool.W": (torch.randn(d, U, generator=g) * 0.05).double().requires_grad_(True),
@@ -457,17 +460,18 @@ def test_gemm_pair_fused_bias_gradient(lib, M, N, K):
                                    (300, 128, 160)])
 def test_gemm_pair_mixed_bf16_cross_terms(lib, name, a_mn, b_mn, M, N, K):
     """gemm_mix=1: tf32(A) tf32(B) + bf16(A) bf16(Bl) + bf16(Al) bf16(B); the bf16 operand tiles (64-byte-swizzled,
-    K-major and MN-major) are written by the splitter warps.  Same tolerance as the all-TF32 3-term product."""
+    K-major and MN-major) are written by the splitter warps.  gemm_mix=2 (bf16x3): bf16(A) bf16(B) + the same two
+    cross terms with Xl = X - bf16(X).  Same tolerance as the all-TF32 3-term product."""
     errs = {}
-    for mix in (1, 0):          # 1 is the default; 0 = all three terms as TF32 MMAs (kept as the reference scheme)
+    for mix in (1, 2, 0):       # 0 = all three terms as TF32 MMAs (kept as the reference scheme)
         _lib.check(lib.skf_set_option(b"gemm_mix", mix))
         try:
             errs[mix] = [_gemm_case(M, N, K, a_mn, b_mn, 5, 17),
                          _gemm_case(M, N, K, a_mn, b_mn, 5, 18, bias=True, act=1, resid=True),
                          _gemm_case(M, N, K, a_mn, b_mn, 5, 20, split_k=3)]
         finally:
-            _lib.check(lib.skf_set_option(b"gemm_mix", 1))
-    assert max(errs[1]) < TOL_X3 and max(errs[0]) < TOL_X3, errs
+            _lib.check(lib.skf_set_option(b"gemm_mix", 2))     # back to the default
+    assert max(errs[1]) < TOL_X3 and max(errs[2]) < TOL_X3 and max(errs[0]) < TOL_X3, errs
 
 
 def test_gemm_tcgen05_3xtf32_beats_single_pass(lib):
