@@ -159,7 +159,15 @@ typedef struct skf_gemm_epilogue {
   /* Bias gradient fused into a weight-gradient product (pair backend 5, accumulate=1, B row-major [K, N]):
    * colsum[n] += sum_k B[k, n], taken from the B tiles the CTAs stage anyway (row-block 0 only).          */
   float* colsum;
+  /* Both non-NULL (pair backend 5 in bf16x3 mode): B is a weight whose bf16 images hi = bf16(B) and
+   * lo = bf16(B - hi) from skf_split_bf16() exist with the element layout and strides of B (base 16-byte aligned,
+   * row pitch a multiple of 8 elements); the kernel then TMA-loads the bf16 tiles instead of splitting B's fp32
+   * tiles in shared memory (Dense forward and dgrad: the same weights serve B*T rows).                       */
+  const void* b_hi16;
+  const void* b_lo16;
 } skf_gemm_epilogue;
+/* hi[i] = bf16(x[i]) (round to nearest even), lo[i] = bf16(x[i] - hi[i]): operand images of the bf16x3 product. */
+int skf_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
 /* lo[i] = x[i] - tf32(x[i])  (exact in fp32): the low half of the 3xTF32 operand split.     */
 int skf_split_lo(const float* x, float* lo, int64_t n, void* stream);
 int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,

@@ -28,7 +28,8 @@ class SkfParamEntry(C.Structure):
 class SkfGemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("resid", C.c_void_p), ("ld_resid", C.c_int64), ("mask", C.c_void_p),
                 ("ld_mask", C.c_int64), ("act", C.c_int32), ("accumulate", C.c_int32), ("round_tf32", C.c_int32),
-                ("split_k", C.c_int32), ("a_lo", C.c_void_p), ("b_lo", C.c_void_p), ("colsum", C.c_void_p)]
+                ("split_k", C.c_int32), ("a_lo", C.c_void_p), ("b_lo", C.c_void_p), ("colsum", C.c_void_p),
+                ("b_hi16", C.c_void_p), ("b_lo16", C.c_void_p)]
 
 
 P, I, L, F, SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
@@ -52,6 +53,7 @@ SIGNATURES = {
     "skf_cont_loss": (I, [P, L, P, L, I, I, F, P, L, P, P]),
     "skf_gemm": (I, [P, L, L, P, L, L, P, L, I, I, I, C.POINTER(SkfGemmEpilogue), I, P]),
     "skf_split_lo": (I, [P, P, L, P]),
+    "skf_split_bf16": (I, [P, P, P, L, P]),
     "skf_attn_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, P]),
     "skf_attn_bwd": (I, [P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, P]),
     "skf_add_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P]),

@@ -256,6 +256,25 @@ int make_tmap_2d_typed(CUtensorMap* out, const float* ptr, uint64_t inner, uint6
   return SKF_OK;
 }
 
+// 2-D bf16 tensor map with 64-byte rows in shared memory (box_inner = 32 elements) under the 64-byte swizzle: the
+// layout of the pair GEMM's bf16 operand tiles (skf_gemm_tc3.cu).
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  SKF_REQUIRE(enc != nullptr, SKF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SKF_REQUIRE(r == CUDA_SUCCESS, SKF_ERR_CUDA,
+              "cuTensorMapEncodeTiled (bf16) failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+  return SKF_OK;
+}
+
 int gemm_tc_supported(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,
                       int64_t sb_n, const float* Y, int64_t ldy, int M, int N, int K,
                       const skf_gemm_epilogue* epi) {

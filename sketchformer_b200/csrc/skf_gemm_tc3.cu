@@ -47,6 +47,8 @@ using namespace ptx;
 
 int make_tmap_2d_typed(CUtensorMap* out, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
                        uint32_t box_inner, uint32_t box_outer, bool mn_major, bool tf32_convert);
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer);
 
 constexpr int T3_BM = 128;                 // rows per CTA (256 per cluster)
 constexpr int T3_BK = 32;
@@ -61,12 +63,14 @@ constexpr int T3_MAX_STAGES = 4;
 
 // BN = columns per cluster tile (256, or 128 for N <= 256: twice as many tiles for the 74 clusters and a
 // fourth pipeline stage); each CTA stages BN / 2 columns of B.
-template <int BN>
+// WS (weights pre-split, bf16x3 only): the B operand arrives as bf16 hi / lo tiles straight from its HBM images, so
+// a stage holds A raw | A hi | A lo | B hi | B lo = 48 KB / 40 KB (four stages) and the splitter converts only A.
+template <int BN, bool WS = false>
 struct Tc3Cfg {
   static constexpr int BNH = BN / 2;
   static constexpr int B_BYTES = BNH * 128;
-  static constexpr int RAW = T3_A_BYTES + B_BYTES;
-  static constexpr int STAGE = 2 * RAW;                 // raw + lo tiles: 64 KB / 48 KB
+  static constexpr int RAW = T3_A_BYTES + B_BYTES;      // bytes the TMA delivers per stage (WS: B hi + B lo = B_BYTES)
+  static constexpr int STAGE = WS ? 2 * T3_A_BYTES + B_BYTES : 2 * RAW;   // raw + lo tiles: 64 KB / 48 KB
   static constexpr int STAGES_RAW = (227 * 1024 - 2048 - T3_EPI_BYTES - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > T3_MAX_STAGES ? T3_MAX_STAGES : STAGES_RAW;
   static constexpr int SMEM = STAGES * STAGE + T3_EPI_BYTES + 1024 + 256 + 512 /* column sums */;
@@ -238,11 +242,14 @@ __device__ __forceinline__ float t3_trunc_tf32(float x) { return __uint_as_float
 // case per product, random sign) -- far below the 1.4e-4 end-to-end floor set by attention's TF32-rounded P -- for
 // three bf16-rate passes instead of one TF32 + two bf16 (= four bf16-rate passes), and the tensor cores read only
 // the 32 KB of bf16 tiles per stage (the raw fp32 tiles feed the splitter alone).
-template <int T3_BN, bool A_MN, bool B_MN, int MIX>
+template <int T3_BN, bool A_MN, bool B_MN, int MIX, bool WS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T3_THREADS, 1)
 gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-        const __grid_constant__ CUtensorMap tmY, const Gemm3Params p) {
-  using C = Tc3Cfg<T3_BN>;
+        const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmY, const Gemm3Params p) {
+  static_assert(!WS || MIX == 2, "pre-split weights are bf16 images: bf16x3 mode only");
+  using C = Tc3Cfg<T3_BN, WS>;
+  // offset of the bf16 tiles (A hi | A lo | B hi | B lo) inside a stage
+  constexpr int T3_B16 = WS ? T3_A_BYTES : C::RAW;
   constexpr int S = C::STAGES;
   constexpr int T3_BNH = C::BNH, T3_RAW = C::RAW, T3_STAGE = C::STAGE, T3_TMEM_COLS = C::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
@@ -270,6 +277,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (WS) prefetch_tmap(&tmBl);
     prefetch_tmap(&tmY);
     for (int s = 0; s < S; s++) {
       mbar_init(full_bar(s), 1);
@@ -325,7 +333,21 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 #pragma unroll
             for (int j = 0; j < T3_BM / 32; j++) tma_load_2d(a_s + j * 4096, &tmA, full_bar(s), m0 + 32 * j, k0);
           }
-          if (!B_MN) {
+          if (WS) {
+            // bf16 images of the weight: hi / lo tiles with 64-byte rows (64B swizzle), where the splitter would
+            // have written them
+            const uint32_t bh16 = a_s + T3_B16 + T3_A_BYTES, bl16 = bh16 + C::B_BYTES / 2;
+            if (!B_MN) {
+              tma_load_2d(bh16, &tmB, full_bar(s), k0, nh);               // box {32 k, BNH n}
+              tma_load_2d(bl16, &tmBl, full_bar(s), k0, nh);
+            } else {
+#pragma unroll
+              for (int j = 0; j < T3_BNH / 32; j++) {                     // boxes {32 n, 32 k}, 2 KB each
+                tma_load_2d(bh16 + j * 2048, &tmB, full_bar(s), nh + 32 * j, k0);
+                tma_load_2d(bl16 + j * 2048, &tmBl, full_bar(s), nh + 32 * j, k0);
+              }
+            }
+          } else if (!B_MN) {
             tma_load_2d(b_s, &tmB, full_bar(s), k0, nh);
           } else {
 #pragma unroll
@@ -359,7 +381,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           const uint32_t bl_s = al_s + T3_A_BYTES;
           if (MIX) {
             constexpr uint32_t idesc16 = make_idesc_bf16(2 * T3_BM, T3_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-            const uint32_t ah16 = a_s + T3_RAW, al16 = ah16 + T3_A_BYTES / 2;
+            const uint32_t ah16 = a_s + T3_B16, al16 = ah16 + T3_A_BYTES / 2;
             const uint32_t bh16 = al16 + T3_A_BYTES / 2, bl16 = bh16 + C::B_BYTES / 2;
 #pragma unroll
             for (int k2 = 0; k2 < T3_BK / 16; k2++) {                      // cross terms: bf16, K = 16 per MMA
@@ -533,13 +555,13 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
         float4* dst = reinterpret_cast<float4*>(gen + s * T3_STAGE + T3_RAW);
         if (MIX) {
           uint8_t* st8 = gen + s * T3_STAGE;
-          uint8_t* ah16 = st8 + T3_RAW;
+          uint8_t* ah16 = st8 + T3_B16;
           uint8_t* al16 = ah16 + T3_A_BYTES / 2;
           uint8_t* bh16 = al16 + T3_A_BYTES / 2;
           uint8_t* bl16 = bh16 + C::B_BYTES / 2;
           t3_split_bf16<T3_BM, A_MN, MIX == 2>(st8, ah16, al16, tid);
-          t3_split_bf16<T3_BNH, B_MN, MIX == 2>(st8 + T3_A_BYTES, bh16, bl16, tid);
-          if (B_MN && do_colsum) {
+          if (!WS) t3_split_bf16<T3_BNH, B_MN, MIX == 2>(st8 + T3_A_BYTES, bh16, bl16, tid);
+          if (!WS && B_MN && do_colsum) {
 #pragma unroll
             for (int ib = 0; ib < 2 * NBOX; ib++) {
               const float4 x = src[T3_A_BYTES / 16 + tid + 128 * ib];
@@ -602,14 +624,16 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
 static int g3_clusters = 0;
 int g_gemm_mix = 2;       // 1: cross terms of the 3xTF32 product as bf16 MMAs, 2: all three terms bf16 (see gemm3_k MIX)
 
+int g_gemm_wsplit = 1;    // 1: the plan hands forward / dgrad products bf16 images of their weights (b_hi16 / b_lo16)
+
 int g_t3_oversubscribe = 0;
 
-template <int BN, bool A_MN, bool B_MN, int MIX>
+template <int BN, bool A_MN, bool B_MN, int MIX, bool WS = false>
 static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t st) {
-  constexpr int T3_SMEM = Tc3Cfg<BN>::SMEM;
+  constexpr int T3_SMEM = Tc3Cfg<BN, WS>::SMEM;
   static bool attr_done = false;
   if (!attr_done) {
-    SKF_CUDA(cudaFuncSetAttribute(gemm3_k<BN, A_MN, B_MN, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
+    SKF_CUDA(cudaFuncSetAttribute(gemm3_k<BN, A_MN, B_MN, MIX, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
     attr_done = true;
   }
   if (!g3_clusters) {
@@ -622,7 +646,7 @@ static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t 
     qc.blockDim = dim3(T3_THREADS);
     qc.dynamicSmemBytes = T3_SMEM;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, gemm3_k<BN, A_MN, B_MN, MIX>, &qc) != cudaSuccess || nc <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&nc, gemm3_k<BN, A_MN, B_MN, MIX, WS>, &qc) != cudaSuccess || nc <= 0) {
       cudaGetLastError();
       nc = sms / 2;
     }
@@ -633,7 +657,7 @@ static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t 
   // unit instead of a persistent grid, so that the units are short and a higher-priority kernel waiting for SMs
   // gets them after one unit, not after a cluster's whole share
   const int ncl = (ntiles < g3_clusters || g_t3_oversubscribe) ? ntiles : g3_clusters;
-  gemm3_k<BN, A_MN, B_MN, MIX><<<2 * ncl, T3_THREADS, T3_SMEM, st>>>(tm[0], tm[1], tm[2], p);
+  gemm3_k<BN, A_MN, B_MN, MIX, WS><<<2 * ncl, T3_THREADS, T3_SMEM, st>>>(tm[0], tm[1], tm[3], tm[2], p);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -670,12 +694,27 @@ int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
               "gemm: the fused column sum needs accumulate=1 and a row-major [K, N] B operand");
   p.e = e;
   p.e.a_lo = p.e.b_lo = nullptr;
-  CUtensorMap tm[3];
+  CUtensorMap tm[4];   // A, B (or B hi), Y, B lo
+  // pre-split weights: bf16 images of B with B's strides (bf16x3 mode, rows a multiple of 8 elements apart)
+  const bool ws = g_gemm_mix == 2 && e.b_hi16 && e.b_lo16 && !e.accumulate &&
+                  (((reinterpret_cast<uintptr_t>(e.b_hi16) | reinterpret_cast<uintptr_t>(e.b_lo16)) & 15) == 0) &&
+                  ((b_mn ? sb_k : sb_n) % 8 == 0);
   // raw fp32 bits in shared memory (the splitter needs them): plain FLOAT32 maps
   if (!a_mn) SKF_TRY(make_tmap_2d_typed(&tm[0], A, (uint64_t)K, (uint64_t)M, (uint64_t)(M == 1 ? K : sa_m), T3_BK, T3_BM, false, false));
   else SKF_TRY(make_tmap_2d_typed(&tm[0], A, (uint64_t)M, (uint64_t)K, (uint64_t)sa_k, 32, T3_BK, true, false));
-  if (!b_mn) SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, T3_BK, (uint32_t)(BN / 2), false, false));
-  else SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, T3_BK, true, false));
+  if (ws) {
+    if (!b_mn) {
+      SKF_TRY(make_tmap_2d_bf16(&tm[1], e.b_hi16, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, T3_BK, (uint32_t)(BN / 2)));
+      SKF_TRY(make_tmap_2d_bf16(&tm[3], e.b_lo16, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, T3_BK, (uint32_t)(BN / 2)));
+    } else {
+      SKF_TRY(make_tmap_2d_bf16(&tm[1], e.b_hi16, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, T3_BK));
+      SKF_TRY(make_tmap_2d_bf16(&tm[3], e.b_lo16, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, T3_BK));
+    }
+  } else {
+    if (!b_mn) SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)K, (uint64_t)N, (uint64_t)sb_n, T3_BK, (uint32_t)(BN / 2), false, false));
+    else SKF_TRY(make_tmap_2d_typed(&tm[1], B, (uint64_t)N, (uint64_t)K, (uint64_t)sb_k, 32, T3_BK, true, false));
+    tm[3] = tm[1];
+  }
   SKF_TRY(make_tmap_2d_typed(&tm[2], Y, (uint64_t)N, (uint64_t)M, (uint64_t)ldy, 32, 32, false, false));
 #define SKF_T3_DISPATCH(BNV, MIXV)                                                          \
   do {                                                                                     \
@@ -684,6 +723,18 @@ int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
     if (a_mn && !b_mn) return launch_tc3<BNV, true, false, MIXV>(tm, p, st);               \
     return launch_tc3<BNV, true, true, MIXV>(tm, p, st);                                   \
   } while (0)
+  if (ws) {
+#define SKF_T3_DISPATCH_WS(BNV)                                                            \
+  do {                                                                                     \
+    if (!a_mn && !b_mn) return launch_tc3<BNV, false, false, 2, true>(tm, p, st);          \
+    if (!a_mn && b_mn) return launch_tc3<BNV, false, true, 2, true>(tm, p, st);            \
+    if (a_mn && !b_mn) return launch_tc3<BNV, true, false, 2, true>(tm, p, st);            \
+    return launch_tc3<BNV, true, true, 2, true>(tm, p, st);                                \
+  } while (0)
+    if (BN == 128) SKF_T3_DISPATCH_WS(128);
+    SKF_T3_DISPATCH_WS(256);
+#undef SKF_T3_DISPATCH_WS
+  }
   if (g_gemm_mix == 2) {
     if (BN == 128) SKF_T3_DISPATCH(128, 2);
     SKF_T3_DISPATCH(256, 2);

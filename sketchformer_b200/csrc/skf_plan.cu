@@ -9,6 +9,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "skf_common.cuh"
 
 namespace skf {
@@ -31,6 +33,7 @@ int g_wgrad_units = 1;     // side-stream wgrads: work units per cluster slot (f
 extern int g_t3_oversubscribe;
 int g_kv_fold = 2;         // rank-2 form of the expanded bottleneck (see kv_fold()): 1 K / V only, 2 whole cross attention
 int g_wgrad_overlap = 1;   // weight-gradient GEMMs of the backward pass on a second stream (see SideQueue)
+extern int g_gemm_wsplit;   // 1: forward / dgrad products read pre-split bf16 images of the weights (skf_gemm_tc3.cu)
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
 int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
 int attn_fwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
@@ -64,7 +67,7 @@ struct ParamLayout {
   std::map<std::string, int> idx;
   int64_t total = 0;
   void add(const std::string& n, int rows, int cols) {
-    total = (total + 3) & ~(int64_t)3;  // 16-byte aligned tensors (TMA / float4)
+    total = (total + 7) & ~(int64_t)7;  // 32-byte aligned tensors: 16 bytes (TMA / float4) in the bf16 images too
     idx[n] = (int)e.size();
     e.push_back({n, total, rows, cols});
     total += (int64_t)rows * cols;
@@ -177,7 +180,7 @@ static ParamLayout build_layout(const skf_cfg& c) {
     L.add("out.k", c.d, c.continuous ? 5 : c.V);   // sketchformer.py:86 / 91
     L.add("out.b", 1, c.continuous ? 5 : c.V);
   }
-  L.total = (L.total + 3) & ~(int64_t)3;
+  L.total = (L.total + 7) & ~(int64_t)7;
   return L;
 }
 
@@ -207,6 +210,9 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
   W.add("stats_run", 16 * sizeof(double));
   W.add("pe", (size_t)c.T * d * F);
   W.add("wc", g_tma_tf32_type ? 256 : (size_t)PL.total * F);  // TF32-rounded copy of the weights (tma_tf32=0 only)
+  // bf16 images hi = bf16(w), lo = bf16(w - hi) of the parameter arena, same element offsets (pair GEMM, bf16x3)
+  W.add("w16h", (size_t)PL.total * 2);
+  W.add("w16l", (size_t)PL.total * 2);
   W.add("enc_pad", Me);
   W.add("dec_pad", Md);
   W.add("enc.x0", Me * d * F);
@@ -341,6 +347,7 @@ struct skf_plan {
   size_t ev_next = 0;
   std::unordered_map<const void*, cudaEvent_t> pending;
   bool side_active = false;
+  bool w16_valid = false;   // the "w16h" / "w16l" images match `params` (refresh_compute_weights)
   cudaEvent_t next_event() { return events[ev_next++ % events.size()]; }
   ~skf_plan() {
     for (cudaEvent_t e : events) cudaEventDestroy(e);
@@ -381,6 +388,35 @@ __global__ void split_lo_k(const float* __restrict__ x, float* __restrict__ lo, 
 }
 int split_lo(const float* x, float* lo, int64_t n, cudaStream_t st) {
   split_lo_k<<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(x, lo, n, g_tma_tf32_type);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
+// hi = bf16(x), lo = bf16(x - hi): operand images of the bf16x3 product (x - hi is exact in fp32)
+__global__ void split_bf16_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo, int64_t n) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+    const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+    uint2 ph, pl;
+    ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+    pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(hi + i) = ph;
+    *reinterpret_cast<uint2*>(lo + i) = pl;
+  } else {
+    for (; i < n; i++) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(x[i]);
+      hi[i] = h;
+      lo[i] = __float2bfloat16_rn(x[i] - __bfloat162float(h));
+    }
+  }
+}
+int split_bf16(const float* x, void* hi, void* lo, int64_t n, cudaStream_t st) {
+  split_bf16_k<<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                      reinterpret_cast<__nv_bfloat16*>(lo), n);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -439,11 +475,19 @@ struct Gemm {
     return tc ? gemm_tc2(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, x3 ? 1 : 0, st)
               : gemm_simt(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, st);
   }
+  // bf16 images of a weight inside the parameter arena (same element offset), when they are current
+  void weight_images(const float* W, skf_gemm_epilogue* e) const {
+    if (!P->w16_valid || W < P->params || W >= P->params + P->PL.total) return;
+    const size_t off = (size_t)(W - P->params);
+    e->b_hi16 = P->wsp<uint8_t>("w16h") + 2 * off;
+    e->b_lo16 = P->wsp<uint8_t>("w16l") + 2 * off;
+  }
   // Y[M,N] = act(X[M,K] * W[K,N] + bias) (+ resid)
   int fwd(const float* X, const float* W, const float* bias, float* Y, int M, int N, int K, int act,
           const float* resid, int rnd) const {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
+    weight_images(W, &e);
     e.bias = bias; e.act = act; e.resid = resid; e.ld_resid = N; e.round_tf32 = rnd;
     return run(X, K, 1, W, N, 1, Y, N, M, N, K, e, P->c.gemm_precision >= 1);
   }
@@ -452,6 +496,7 @@ struct Gemm {
             const float* resid, int rnd) const {
     skf_gemm_epilogue e;
     memset(&e, 0, sizeof(e));
+    weight_images(W, &e);
     e.mask = mask; e.ld_mask = K; e.resid = resid; e.ld_resid = K; e.round_tf32 = rnd;
     return run(dY, N, 1, W, 1, N, dX, K, M, K, N, e, P->c.gemm_precision >= 2);
   }
@@ -601,8 +646,15 @@ static int kv_fold(const skf_plan* P) {
 static int refresh_compute_weights(skf_plan* P, cudaStream_t st) {
   if (!P->round_ops) {
     P->wc = P->params;
+    // bf16 images of the weights for the pair GEMM (Gemm::weight_images): one pass over the arena per forward
+    P->w16_valid = false;
+    if (g_gemm_wsplit && g_gemm_mix == 2 && g_gemm_pair && P->c.gemm_backend == 0 && P->c.gemm_precision >= 1) {
+      SKF_TRY(split_bf16(P->params, P->wsp<uint8_t>("w16h"), P->wsp<uint8_t>("w16l"), P->PL.total, st));
+      P->w16_valid = true;
+    }
     return SKF_OK;
   }
+  P->w16_valid = false;
   float* dst = P->wsf("wc");
   round_copy_k<<<cdiv(P->PL.total, 256), 256, 0, st>>>(P->params, dst, P->PL.total);
   SKF_LAUNCH_CHECK();
@@ -1143,9 +1195,18 @@ int skf_split_lo(const float* x, float* lo, int64_t n, void* stream) {
   return skf::split_lo(x, lo, n, as_stream(stream));
 }
 
+int skf_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  SKF_REQUIRE(x && hi && lo && n > 0, SKF_ERR_BAD_ARG, "split_bf16: bad argument");
+  return skf::split_bf16(x, hi, lo, n, as_stream(stream));
+}
+
 int skf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_mix") == 0) {
     skf::g_gemm_mix = value < 0 ? 0 : (value > 2 ? 2 : value);
+    return SKF_OK;
+  }
+  if (name && strcmp(name, "gemm_wsplit") == 0) {
+    skf::g_gemm_wsplit = value ? 1 : 0;
     return SKF_OK;
   }
   if (name && strcmp(name, "kv_fold") == 0) {

@@ -9,6 +9,7 @@ import torch
 
 from oracle import sketchformer_oracle as O
 from sketchformer_b200 import _lib, synth
+from sketchformer_b200.ops import split_bf16
 from tests.gpu_util import gemm, ptr, rel_err, stream, to_tf32
 
 pytestmark = pytest.mark.gpu
@@ -375,6 +376,8 @@ def _gemm_case(M, N, K, a_mn, b_mn, backend, seed, **epi):
         rs = torch.randn(M, N, generator=g); kw["resid"] = dev(rs); want = want + rs.double()
     if epi.get("split_k"):
         kw["accumulate"] = 1; kw["split_k"] = epi["split_k"]
+    if epi.get("images"):        # B is a weight with bf16 images in its own layout (skf_split_bf16)
+        kw["b_hi16"], kw["b_lo16"] = split_bf16(Bst)
     gemm(Ast, sa[0], sa[1], Bst, sb[0], sb[1], Y, N, M, N, K, backend, **kw)
     torch.cuda.synchronize()
     return rel_err(Y, want)
@@ -472,6 +475,31 @@ def test_gemm_pair_mixed_bf16_cross_terms(lib, name, a_mn, b_mn, M, N, K):
         finally:
             _lib.check(lib.skf_set_option(b"gemm_mix", 2))     # back to the default
     assert max(errs[1]) < TOL_X3 and max(errs[2]) < TOL_X3 and max(errs[0]) < TOL_X3, errs
+
+
+def test_split_bf16_matches_torch(lib):
+    """hi = bf16(x) (round to nearest even), lo = bf16(x - hi), bit for bit; odd length exercises the scalar tail."""
+    g = torch.Generator().manual_seed(5)
+    x = dev(torch.randn(100003, generator=g) * torch.logspace(-6, 6, 100003))
+    hi, lo = split_bf16(x)
+    torch.cuda.synchronize()
+    h = x.bfloat16()
+    assert torch.equal(hi, h) and torch.equal(lo, (x - h.float()).bfloat16())
+    assert rel_err(hi.float() + lo.float(), x.double()) < 2e-5
+
+
+@pytest.mark.parametrize("name,a_mn,b_mn", MAJORS)
+@pytest.mark.parametrize("M,N,K", [(256, 256, 32), (512, 256, 64), (200, 1000, 96), (1600, 768, 256), (384, 512, 4000),
+                                   (300, 128, 160), (260, 1004, 100), (25600, 1024, 256)])
+def test_gemm_pair_presplit_weights(lib, name, a_mn, b_mn, M, N, K):
+    """bf16x3 with the B operand TMA-loaded from bf16 hi / lo images (Dense forward: B row-major [K, N]; dgrad: B
+    K-major), four-stage ring; ragged M / N / K; (260, 1004, 100) has a row pitch that is not a multiple of 8
+    elements in one of the majors and must fall back to the in-kernel split."""
+    if M > 20000 and name != "fwd":
+        pytest.skip("full-size schedule checked once")
+    assert _gemm_case(M, N, K, a_mn, b_mn, 5, 17, images=True) < TOL_X3
+    assert _gemm_case(M, N, K, a_mn, b_mn, 5, 18, bias=True, act=1, resid=True, images=True) < TOL_X3
+    assert _gemm_case(M, N, K, a_mn, b_mn, 5, 19, mask=True, images=True) < TOL_X3
 
 
 def test_gemm_tcgen05_3xtf32_beats_single_pass(lib):
