@@ -670,7 +670,8 @@ int gemm_tc3_clusters() { return g3_clusters; }
 int gemm_tc3_wanted(int M, int N, int K) { (void)K; return N > 64 && M > 128; }
 // 128-column cluster tiles only when the problem has no more than 128 columns: for N = 256 the 256-wide tile
 // (100 tiles on 74 clusters) measured 3 % faster than 2 x 128 (FFN-2 25600x1024x256: 69.6 vs 71.6 us).
-int gemm_tc3_bn(int N, int accumulate) { (void)accumulate; return N <= 128 ? 128 : 256; }
+int g_t3_bn128_max = 128;
+int gemm_tc3_bn(int N, int accumulate) { (void)accumulate; return N <= g_t3_bn128_max ? 128 : 256; }
 
 int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
              int64_t ldy, int M, int N, int K, const skf_gemm_epilogue* epi, cudaStream_t st) {

@@ -324,47 +324,78 @@ __global__ void __launch_bounds__(256) ln_bwd_k(const float* __restrict__ dy, co
   for (int k = 0; k < LN_NV; k++) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c = threadIdx.y * 32 + lane; c < 2 * d; c += nw * 32) sm[c] = 0.f;
   __syncthreads();
-  for (int row = blockIdx.x * nw + w; row < rows; row += gridDim.x * nw) {
-    float mu = mean[row], rs = rstd[row];
-    float4 g[LN_NV], xh[LN_NV];
-    float c1 = 0.f, c2 = 0.f;
+  // R rows per warp and iteration: their loads are issued together, so an SM keeps 16 warps x R x 2 rows of d
+  // floats in flight (64 KB at d = 256; one row per warp left the kernel at half the HBM rate)
+  constexpr int R = LN_NV <= 2 ? 2 : 1;
+  const int rstride = gridDim.x * nw;
+  for (int row0 = blockIdx.x * nw + w; row0 < rows; row0 += R * rstride) {
+    float4 g[R][LN_NV], xh[R][LN_NV];
+    float mu[R], rs[R], c1[R], c2[R];
 #pragma unroll
-    for (int k = 0; k < LN_NV; k++) {
-      int c = lane + k * 32;
-      if (c < nv) {
-        float4 dyv = reinterpret_cast<const float4*>(dy + (int64_t)row * d)[c];
-        float4 sv = reinterpret_cast<const float4*>(s + (int64_t)row * d)[c];
-        float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        xh[k] = make_float4((sv.x - mu) * rs, (sv.y - mu) * rs, (sv.z - mu) * rs, (sv.w - mu) * rs);
-        g[k] = make_float4(dyv.x * ga.x, dyv.y * ga.y, dyv.z * ga.z, dyv.w * ga.w);
-        c1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
-        c2 += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
-        ag[k].x += dyv.x * xh[k].x; ag[k].y += dyv.y * xh[k].y;
-        ag[k].z += dyv.z * xh[k].z; ag[k].w += dyv.w * xh[k].w;
-        ab[k].x += dyv.x; ab[k].y += dyv.y; ab[k].z += dyv.z; ab[k].w += dyv.w;
+    for (int r = 0; r < R; r++) {
+      const int row = row0 + r * rstride;
+      const bool live = row < rows;
+      mu[r] = live ? mean[row] : 0.f;
+      rs[r] = live ? rstd[row] : 0.f;
+#pragma unroll
+      for (int k = 0; k < LN_NV; k++) {
+        const int c = lane + k * 32;
+        g[r][k] = xh[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nv && live) {
+          g[r][k] = reinterpret_cast<const float4*>(dy + (int64_t)row * d)[c];     // dy for now
+          xh[r][k] = reinterpret_cast<const float4*>(s + (int64_t)row * d)[c];     // s for now
+        }
       }
     }
-    c1 = warp_sum(c1) / (float)d;
-    c2 = warp_sum(c2) / (float)d;
 #pragma unroll
-    for (int k = 0; k < LN_NV; k++) {
-      int c = lane + k * 32;
-      if (c < nv) {
-        float4 o;
-        o.x = maybe_round(rs * (g[k].x - c1 - xh[k].x * c2), rnd);
-        o.y = maybe_round(rs * (g[k].y - c1 - xh[k].y * c2), rnd);
-        o.z = maybe_round(rs * (g[k].z - c1 - xh[k].z * c2), rnd);
-        o.w = maybe_round(rs * (g[k].w - c1 - xh[k].w * c2), rnd);
-        reinterpret_cast<float4*>(ds + (int64_t)row * d)[c] = o;
-        if (ds_drop) {
-          if (dr.thresh) {
-            const uint32_t e0 = (uint32_t)row * (uint32_t)d + 4u * c;
-            o.x = skf_drop_apply(o.x, dkey, dr.site, e0, dr.thresh, dr.scale);
-            o.y = skf_drop_apply(o.y, dkey, dr.site, e0 + 1, dr.thresh, dr.scale);
-            o.z = skf_drop_apply(o.z, dkey, dr.site, e0 + 2, dr.thresh, dr.scale);
-            o.w = skf_drop_apply(o.w, dkey, dr.site, e0 + 3, dr.thresh, dr.scale);
+    for (int r = 0; r < R; r++) {
+      c1[r] = c2[r] = 0.f;
+#pragma unroll
+      for (int k = 0; k < LN_NV; k++) {
+        const int c = lane + k * 32;
+        if (c < nv) {
+          const float4 dyv = g[r][k], sv = xh[r][k];
+          const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+          xh[r][k] = make_float4((sv.x - mu[r]) * rs[r], (sv.y - mu[r]) * rs[r], (sv.z - mu[r]) * rs[r],
+                                 (sv.w - mu[r]) * rs[r]);
+          g[r][k] = make_float4(dyv.x * ga.x, dyv.y * ga.y, dyv.z * ga.z, dyv.w * ga.w);
+          c1[r] += (g[r][k].x + g[r][k].y) + (g[r][k].z + g[r][k].w);
+          c2[r] += (g[r][k].x * xh[r][k].x + g[r][k].y * xh[r][k].y) + (g[r][k].z * xh[r][k].z + g[r][k].w * xh[r][k].w);
+          ag[k].x += dyv.x * xh[r][k].x; ag[k].y += dyv.y * xh[r][k].y;
+          ag[k].z += dyv.z * xh[r][k].z; ag[k].w += dyv.w * xh[r][k].w;
+          ab[k].x += dyv.x; ab[k].y += dyv.y; ab[k].z += dyv.z; ab[k].w += dyv.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      c1[r] = warp_sum(c1[r]) / (float)d;
+      c2[r] = warp_sum(c2[r]) / (float)d;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int row = row0 + r * rstride;
+      if (row >= rows) continue;
+#pragma unroll
+      for (int k = 0; k < LN_NV; k++) {
+        int c = lane + k * 32;
+        if (c < nv) {
+          float4 o;
+          o.x = maybe_round(rs[r] * (g[r][k].x - c1[r] - xh[r][k].x * c2[r]), rnd);
+          o.y = maybe_round(rs[r] * (g[r][k].y - c1[r] - xh[r][k].y * c2[r]), rnd);
+          o.z = maybe_round(rs[r] * (g[r][k].z - c1[r] - xh[r][k].z * c2[r]), rnd);
+          o.w = maybe_round(rs[r] * (g[r][k].w - c1[r] - xh[r][k].w * c2[r]), rnd);
+          reinterpret_cast<float4*>(ds + (int64_t)row * d)[c] = o;
+          if (ds_drop) {
+            if (dr.thresh) {
+              const uint32_t e0 = (uint32_t)row * (uint32_t)d + 4u * c;
+              o.x = skf_drop_apply(o.x, dkey, dr.site, e0, dr.thresh, dr.scale);
+              o.y = skf_drop_apply(o.y, dkey, dr.site, e0 + 1, dr.thresh, dr.scale);
+              o.z = skf_drop_apply(o.z, dkey, dr.site, e0 + 2, dr.thresh, dr.scale);
+              o.w = skf_drop_apply(o.w, dkey, dr.site, e0 + 3, dr.thresh, dr.scale);
+            }
+            reinterpret_cast<float4*>(ds_drop + (int64_t)row * d)[c] = o;
           }
-          reinterpret_cast<float4*>(ds_drop + (int64_t)row * d)[c] = o;
         }
       }
     }

@@ -33,6 +33,7 @@ int g_wgrad_units = 1;     // side-stream wgrads: work units per cluster slot (f
 extern int g_t3_oversubscribe;
 int g_kv_fold = 2;         // rank-2 form of the expanded bottleneck (see kv_fold()): 1 K / V only, 2 whole cross attention
 int g_wgrad_overlap = 1;   // weight-gradient GEMMs of the backward pass on a second stream (see SideQueue)
+extern int g_t3_bn128_max;  // pair GEMM: 128-column cluster tiles for N up to this
 extern int g_gemm_wsplit;   // 1: forward / dgrad products read pre-split bf16 images of the weights (skf_gemm_tc3.cu)
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
 int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
@@ -1203,6 +1204,10 @@ int skf_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) 
 int skf_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_mix") == 0) {
     skf::g_gemm_mix = value < 0 ? 0 : (value > 2 ? 2 : value);
+    return SKF_OK;
+  }
+  if (name && strcmp(name, "gemm_bn128_max") == 0) {
+    skf::g_t3_bn128_max = value;
     return SKF_OK;
   }
   if (name && strcmp(name, "gemm_wsplit") == 0) {
