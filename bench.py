@@ -276,20 +276,23 @@ def gemm_roofline(eng, c, peaks, peak_src, backend):
     backend 5 = 3xTF32 on CTA pairs (gemm3_k, three tensor-core passes per algorithmic FLOP, what the plan
     runs), 2 = the single-CTA 3xTF32 kernel, 0 = single-pass TF32."""
     import torch
-    from sketchformer_b200.ops import gemm
+    from sketchformer_b200.ops import gemm, split_bf16
     M, K, N = BATCH * c["max_seq_len"], c["d_model"], c["dff"]
     X = torch.randn(M, K, device="cuda")
     W = torch.randn(K, N, device="cuda")
     bias = torch.zeros(N, device="cuda")
     Ys = [torch.empty(M, N, device="cuda") for _ in range(4)]    # 4 x 105 MB outputs: > L2
+    # as in the plan's forward pass: the weight's bf16 hi / lo images exist (one split pass per step) and the pair
+    # kernel TMA-loads its B tiles from them
+    img = dict(zip(("b_hi16", "b_lo16"), split_bf16(W))) if backend == 5 else {}
     for i in range(3):
-        gemm(X, K, 1, W, N, 1, Ys[i % 4], N, M, N, K, backend, bias=bias, act=1)
+        gemm(X, K, 1, W, N, 1, Ys[i % 4], N, M, N, K, backend, bias=bias, act=1, **img)
     torch.cuda.synchronize()
     n = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n):
-        gemm(X, K, 1, W, N, 1, Ys[i % 4], N, M, N, K, backend, bias=bias, act=1)
+        gemm(X, K, 1, W, N, 1, Ys[i % 4], N, M, N, K, backend, bias=bias, act=1, **img)
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / n
@@ -299,8 +302,8 @@ def gemm_roofline(eng, c, peaks, peak_src, backend):
     # burst peak; the single-CTA kernels run TF32 MMAs (half the bf16 rate), three passes in 3xTF32 mode.
     peak = peaks["bf16_tflops"] if backend == 5 else peaks["bf16_tflops"] / 2
     passes = {5: 3, 2: 3}.get(backend, 1)
-    kname = {5: "gemm3_k<256,false,true,2> (cta_group::2 pair; bf16x3: three kind::f16 MMA passes on splitter-written "
-                "bf16 hi/lo tiles)",
+    kname = {5: "gemm3_k<256,false,true,2,true> (cta_group::2 pair; bf16x3: three kind::f16 MMA passes; A split into "
+                "bf16 hi/lo tiles in shared memory, B TMA-loaded from the pre-split weight images)",
              2: "gemm2_k<256,false,true,true> (3xTF32)", 0: "gemm2_k<256,false,true,false> (TF32)"}[backend]
     return {"bound": "tensor", "kernel": kname + " FFN-1: 25600x256x1024, bias+ReLU epilogue",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

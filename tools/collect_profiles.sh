@@ -11,7 +11,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --c
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
 python tools/launch_summary.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches.summary.txt
 head -30 $OUT/${TAG}_launches.summary.txt
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm3_k -s 3 -c 1 -o $OUT/${TAG}_gemm3 -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm3_k -s 2 -c 1 -o $OUT/${TAG}_gemm3 -f \
   python tools/prof_ops.py gemm 2 > $OUT/${TAG}_ncu_gemm.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn2_ -s 6 -c 3 -o $OUT/${TAG}_attn2 -f \
   python tools/prof_ops.py attn 2 > $OUT/${TAG}_ncu_attn.log 2>&1

@@ -53,6 +53,8 @@ if __name__ == "__main__":
     acts = engine_activations(eng, ocfg, B)
     worst = 0.0
     for k, ref in tape.items():
+        if k not in acts:          # not materialised by the engine (folded cross attention: pre_decoder, kv2, ...)
+            continue
         e = rel_err(acts[k], ref)
         worst = max(worst, e)
         if a.all or (e > 1e-4 and not a.quiet):

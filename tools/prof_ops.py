@@ -8,7 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sketchformer_b200 import _lib                              # noqa: E402
-from sketchformer_b200.ops import gemm, ptr, stream             # noqa: E402
+from sketchformer_b200.ops import gemm, ptr, split_bf16, stream  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
@@ -21,6 +21,18 @@ if what in ("gemm", "all"):
     b = torch.zeros(N, device="cuda")
     Y = torch.empty(M, N, device="cuda")
     import time
+    # the plan's forward products read the weight's pre-split bf16 images (gemm3_k<..., WS = true>)
+    img = dict(zip(("b_hi16", "b_lo16"), split_bf16(W)))
+    for _ in range(reps):
+        gemm(X, K, 1, W, N, 1, Y, N, M, N, K, 5, bias=b, act=1, **img)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        gemm(X, K, 1, W, N, 1, Y, N, M, N, K, 5, bias=b, act=1, **img)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"FFN-1 gemm backend 5 + weight images: {e0.elapsed_time(e1) * 1e3 / 20:.1f} us")
     for backend in (2, 5, 0, 3):
         for _ in range(reps):
             gemm(X, K, 1, W, N, 1, Y, N, M, N, K, backend, bias=b, act=1)
