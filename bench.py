@@ -162,6 +162,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL's version / warning lines go to stderr: stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     assert world == args.gpus or world == 1 and args.gpus == 1, "launch with torchrun for --gpus > 1"
 
