@@ -55,10 +55,17 @@ constexpr int T3_BK = 32;
 constexpr int T3_A_BYTES = T3_BM * 128;    // 16 KB
 constexpr int T3_EPI_TILE = 32 * 128;
 constexpr int T3_EPI_WARPS = 8;            // two warps per TMEM lane quarter: even / odd 32-column chunks
-constexpr int T3_EPI_BUFS = 1;
+#ifndef SKF_T3_EPI_BUFS
+#define SKF_T3_EPI_BUFS 1
+#endif
+#ifndef SKF_T3_SPLIT_WARPS
+#define SKF_T3_SPLIT_WARPS 4
+#endif
+constexpr int T3_EPI_BUFS = SKF_T3_EPI_BUFS;
+constexpr int T3_SPLIT_WARPS = SKF_T3_SPLIT_WARPS;     // splitter warps per CTA (the fused column sum assumes 4)
 constexpr int T3_EPI_BYTES = T3_EPI_WARPS * T3_EPI_BUFS * T3_EPI_TILE;   // 32 KB
 constexpr int T3_SPLIT_T0 = 32 * (2 + T3_EPI_WARPS);   // first splitter thread
-constexpr int T3_THREADS = T3_SPLIT_T0 + 128;          // 448
+constexpr int T3_THREADS = T3_SPLIT_T0 + 32 * T3_SPLIT_WARPS;   // 448
 constexpr int T3_MAX_STAGES = 4;
 
 // BN = columns per cluster tile (256, or 128 for N <= 256: twice as many tiles for the 74 clusters and a
@@ -184,11 +191,11 @@ __device__ __forceinline__ void t3_to_bf16_pair(const float4& u, const float4& v
 }
 // One operand tile of the mixed scheme: fp32 tile `src` (K-major: ROWS rows of 128 B under the 128B swizzle;
 // MN-major: ROWS/32 boxes of 32 k-rows under the 32B-atom swizzle) -> bf16 hi / lo tiles with 64-byte rows.
-// 128 threads, thread `tid`; tasks = ROWS * 4 groups of 8 elements.
+// 32 * T3_SPLIT_WARPS threads, thread `tid`; tasks = ROWS * 4 groups of 8 elements.
 template <int ROWS, bool MN, bool BF3>
 __device__ __forceinline__ void t3_split_bf16(const uint8_t* src, uint8_t* hi16, uint8_t* lo16, int tid) {
 #pragma unroll
-  for (int task = tid; task < ROWS * 4; task += 128) {
+  for (int task = tid; task < ROWS * 4; task += 32 * T3_SPLIT_WARPS) {
     const int r = task >> 2, g = task & 3;            // r: row inside the tile (box-major for MN), g: 8-element group
     const int rs = MN ? (r & 31) : r;                 // row index the swizzles see (boxes are 4 KB / 2 KB aligned)
     const uint32_t sx = MN ? (uint32_t)((rs & 3) << 1) : (uint32_t)(rs & 7);
@@ -282,7 +289,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     for (int s = 0; s < S; s++) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(xfull_bar(s), 8);
+      mbar_init(xfull_bar(s), 2 * T3_SPLIT_WARPS);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull_bar(a), 1);

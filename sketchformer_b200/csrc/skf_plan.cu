@@ -34,6 +34,7 @@ extern int g_t3_oversubscribe;
 int g_kv_fold = 2;         // rank-2 form of the expanded bottleneck (see kv_fold()): 1 K / V only, 2 whole cross attention
 int g_wgrad_overlap = 1;   // weight-gradient GEMMs of the backward pass on a second stream (see SideQueue)
 extern int g_t3_bn128_max;  // pair GEMM: 128-column cluster tiles for N up to this
+int g_gemm_tiny_simt = 0;   // 1: products with M <= 128 and few column tiles run on the small-tile SIMT kernel (no gain measured: 9.04 vs 9.01 ms)
 extern int g_gemm_wsplit;   // 1: forward / dgrad products read pre-split bf16 images of the weights (skf_gemm_tc3.cu)
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
 int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
@@ -458,7 +459,12 @@ struct Gemm {
   // 0 means the operand is a weight (its low half lives in the "wlo" arena at the same offset).
   int run(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
           int64_t ldy, int M, int N, int K, skf_gemm_epilogue e, bool x3 = false) const {
-    const bool tc = P->c.gemm_backend == 0 && gemm_tc2_supported(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e);
+    // One 128-row block and a handful of column tiles (the [B, E] x [E, 2d] products of the folded cross attention,
+    // the per-token products of the greedy decode at batch <= 128): a persistent tensor-core kernel would run its
+    // whole k-loop on 2-4 SMs (18-20 us measured for 128 x 512 x 256); the small-tile fp32 kernel spreads it out.
+    const bool tiny = g_gemm_tiny_simt && M <= 128 && !e.accumulate && (long)cdiv(M, 64) * cdiv(N, 64) <= 37;
+    const bool tc = !tiny && P->c.gemm_backend == 0 &&
+                    gemm_tc2_supported(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e);
     if (!P->round_ops) e.round_tf32 = 0;
     if (e.accumulate) {
       // split-K so that the persistent grid (one CTA per SM) has about one tile per SM
@@ -1208,6 +1214,10 @@ int skf_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "gemm_bn128_max") == 0) {
     skf::g_t3_bn128_max = value;
+    return SKF_OK;
+  }
+  if (name && strcmp(name, "gemm_tiny_simt") == 0) {
+    skf::g_gemm_tiny_simt = value ? 1 : 0;
     return SKF_OK;
   }
   if (name && strcmp(name, "gemm_wsplit") == 0) {

@@ -91,6 +91,70 @@ gemm_simt_k(const float* __restrict__ A, int64_t sa_m, int64_t sa_k, const float
   }
 }
 
+// Small problems (a handful of 64x64 tiles: the classifier head at batch 128, the [B, E] x [E, 2d] products of the
+// folded cross attention): 32x32 tiles put 4x as many CTAs on the machine, and 64-deep k-steps with all of a step's
+// global loads in flight cut the serial load -> sync -> FMA chain to K / 64 rounds.
+constexpr int SS_M = 32, SS_N = 32, SS_K = 64;
+__global__ void __launch_bounds__(256)
+gemm_simt_small_k(const float* __restrict__ A, int64_t sa_m, int64_t sa_k, const float* __restrict__ B,
+                  int64_t sb_k, int64_t sb_n, float* __restrict__ Y, int64_t ldy, int M, int N, int K,
+                  skf_gemm_epilogue e, int k_chunk) {
+  __shared__ float As[SS_K][SS_M + 1];
+  __shared__ float Bs[SS_K][SS_N + 1];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SS_M, n0 = blockIdx.x * SS_N;
+  const int k_begin = blockIdx.z * k_chunk;
+  const int k_end = min(K, k_begin + k_chunk);
+  const int ty = tid / 16, tx = tid % 16;          // 2 x 2 outputs per thread: rows ty, ty + 16; columns tx, tx + 16
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = k_begin; k0 < k_end; k0 += SS_K) {
+    float av[8], bv[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {                  // 32 x 64 elements of each operand, 8 per thread, all in flight
+      const int idx = tid + r * 256;
+      int mm, kk;
+      if (sa_k == 1) { kk = idx % SS_K; mm = idx / SS_K; } else { mm = idx % SS_M; kk = idx / SS_M; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      av[r] = (gm < M && gk < k_end) ? A[(int64_t)gm * sa_m + (int64_t)gk * sa_k] : 0.f;
+      int nn, k2;
+      if (sb_k == 1) { k2 = idx % SS_K; nn = idx / SS_K; } else { nn = idx % SS_N; k2 = idx / SS_N; }
+      const int gn = n0 + nn, gk2 = k0 + k2;
+      bv[r] = (gn < N && gk2 < k_end) ? B[(int64_t)gk2 * sb_k + (int64_t)gn * sb_n] : 0.f;
+    }
+    __syncthreads();                               // the previous step's reads of As / Bs are done
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int idx = tid + r * 256;
+      int mm, kk;
+      if (sa_k == 1) { kk = idx % SS_K; mm = idx / SS_K; } else { mm = idx % SS_M; kk = idx / SS_M; }
+      As[kk][mm] = av[r];
+      int nn, k2;
+      if (sb_k == 1) { k2 = idx % SS_K; nn = idx / SS_K; } else { nn = idx % SS_N; k2 = idx / SS_N; }
+      Bs[k2][nn] = bv[r];
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int kk = 0; kk < SS_K; kk++) {
+      const float a0 = As[kk][ty], a1 = As[kk][ty + 16], b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const int m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      float* dst = Y + (int64_t)m * ldy + n;
+      if (e.accumulate) atomicAdd(dst, acc[i][j]);
+      else *dst = epi_apply(acc[i][j], m, n, e);
+    }
+  }
+}
+
 int gemm_simt(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,
               int64_t sb_n, float* Y, int64_t ldy, int M, int N, int K,
               const skf_gemm_epilogue* epi, cudaStream_t st) {
@@ -102,6 +166,14 @@ int gemm_simt(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_
   SKF_REQUIRE(!(e.accumulate && (e.bias || e.resid || e.mask || e.act)), SKF_ERR_BAD_ARG,
               "gemm: accumulate excludes other epilogue terms");
   SKF_REQUIRE(M > 0 && N > 0 && K > 0, SKF_ERR_BAD_SHAPE, "gemm: empty problem %d %d %d", M, N, K);
+  if ((long)cdiv(M, SB_M) * cdiv(N, SB_N) * split <= 37) {     // fewer 64x64 tiles than a quarter of the SMs
+    int kc = cdiv(cdiv(K, split), SS_K) * SS_K;
+    split = cdiv(K, kc);
+    dim3 grid_s(cdiv(N, SS_N), cdiv(M, SS_M), split);
+    gemm_simt_small_k<<<grid_s, 256, 0, st>>>(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, e, kc);
+    SKF_LAUNCH_CHECK();
+    return SKF_OK;
+  }
   int k_chunk = cdiv(cdiv(K, split), SB_K) * SB_K;
   split = cdiv(K, k_chunk);
   dim3 grid(cdiv(N, SB_N), cdiv(M, SB_M), split);
