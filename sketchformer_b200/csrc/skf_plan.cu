@@ -1195,6 +1195,8 @@ static int decode_step(skf_plan* P, int i, bool cross_masked, cudaStream_t st) {
 // =============================================================================================
 // C ABI
 // =============================================================================================
+extern int g_ln_bwd_bpsm;
+
 extern "C" {
 
 int skf_split_lo(const float* x, float* lo, int64_t n, void* stream) {
@@ -1214,6 +1216,10 @@ int skf_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "gemm_bn128_max") == 0) {
     skf::g_t3_bn128_max = value;
+    return SKF_OK;
+  }
+  if (name && strcmp(name, "ln_bwd_bpsm") == 0) {
+    g_ln_bwd_bpsm = value < 1 ? 1 : value;
     return SKF_OK;
   }
   if (name && strcmp(name, "gemm_tiny_simt") == 0) {
