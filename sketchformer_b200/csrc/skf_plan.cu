@@ -1350,6 +1350,7 @@ int skf_apply_adam(skf_plan* P, void* stream) {
   const skf_cfg& c = P->c;
   SKF_TRY(skf_adam_step(P->params, P->grads, P->am, P->av, P->PL.total, P->wsp<int64_t>("step"), c.d,
                         c.warmup_steps, c.adam_beta1, c.adam_beta2, c.adam_eps, 1.0f / (float)c.world_size, stream));
+  P->w16_valid = false;          // the bf16 weight images are stale until the next refresh_compute_weights()
   P->launches += skf::g_launch_count - l0;
   return SKF_OK;
 }
