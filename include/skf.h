@@ -79,6 +79,9 @@ const char* skf_last_error(void);
  * unit converts fp32->tf32 on load) instead of pre-rounded operands.  Set before creating plans. */
 int skf_set_option(const char* name, int value);
 int skf_version(void);
+/* sizeof() of the ABI structs as this library was compiled: which = 0 skf_cfg, 1 skf_gemm_epilogue,
+ * 2 skf_param_entry; 0 for anything else.  A binding checks its own struct layouts against these at load time. */
+size_t skf_abi_sizeof(int which);
 /* 1 if the current device can run the sm_100a kernels. */
 int skf_device_ok(void);
 

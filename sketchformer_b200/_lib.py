@@ -39,6 +39,7 @@ SIGNATURES = {
     "skf_last_error": (C.c_char_p, []),
     "skf_set_option": (I, [C.c_char_p, I]),
     "skf_version": (I, []),
+    "skf_abi_sizeof": (SZ, [I]),
     "skf_device_ok": (I, []),
     "skf_param_count": (L, [C.POINTER(SkfCfg)]),
     "skf_param_table": (I, [C.POINTER(SkfCfg), C.POINTER(SkfParamEntry), I]),
@@ -104,6 +105,10 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
+    for which, struct in enumerate((SkfCfg, SkfGemmEpilogue, SkfParamEntry)):
+        if lib.skf_abi_sizeof(which) != C.sizeof(struct):
+            raise SkfError(f"{struct.__name__}: ctypes layout ({C.sizeof(struct)} bytes) does not match libskf.so "
+                           f"({lib.skf_abi_sizeof(which)} bytes): rebuild the library or update _lib.py")
     _lib = lib
     return lib
 

@@ -1314,6 +1314,9 @@ extern "C" {
 
 const char* skf_last_error(void) { return skf::err_buf(); }
 int skf_version(void) { return 1; }
+size_t skf_abi_sizeof(int which) {
+  return which == 0 ? sizeof(skf_cfg) : which == 1 ? sizeof(skf_gemm_epilogue) : which == 2 ? sizeof(skf_param_entry) : 0;
+}
 int skf_device_ok(void) {
   int dev = 0;
   cudaDeviceProp prop;

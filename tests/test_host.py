@@ -31,6 +31,15 @@ def test_library_exports_every_declared_symbol():
     assert lib.skf_version() == 1
 
 
+def test_ctypes_struct_layouts_match_the_library():
+    """include/skf.h structs as compiled vs their ctypes mirrors (also enforced by _lib.load())."""
+    lib = _lib.load()
+    assert lib.skf_abi_sizeof(0) == C.sizeof(_lib.SkfCfg)
+    assert lib.skf_abi_sizeof(1) == C.sizeof(_lib.SkfGemmEpilogue)
+    assert lib.skf_abi_sizeof(2) == C.sizeof(_lib.SkfParamEntry)
+    assert lib.skf_abi_sizeof(99) == 0
+
+
 def test_param_table_matches_oracle_param_count():
     lib = _lib.load()
     for kw, B, want in ((CFG1, 8, 2272630), (dict(num_layers=4, d_model=256, dff=1024, num_heads=8, lowerdim=256,
