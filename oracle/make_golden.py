@@ -73,10 +73,11 @@ def run(cfg_kw, batch, seed, continuous, full, steps=3):
                     out[f"p_after/{k}"] = v.numpy().astype(np.float32)
             # inference: class prediction + greedy decode from the trained-3-steps weights
             xi = torch.from_numpy(x)
-            pc = O.predict_class(p, xi, cfg, dt)
-            out["pred/embedding"] = pc["embedding"].numpy().astype(np.float32)
-            out["pred/class"] = pc["class"].numpy()
-            if full:
+            if cfg.do_classification:
+                pc = O.predict_class(p, xi, cfg, dt)
+                out["pred/embedding"] = pc["embedding"].numpy().astype(np.float32)
+                out["pred/class"] = pc["class"].numpy()
+            if full and cfg.do_classification:
                 pr = O.predict(p, xi[:2], cfg, sos=cfg.vocab_size - 2, eos=cfg.vocab_size - 1, dtype=dt)
                 out["pred/recon"] = pr["recon"].numpy()
     for k, v in cfg.to_dict().items():
@@ -84,15 +85,28 @@ def run(cfg_kw, batch, seed, continuous, full, steps=3):
     return out
 
 
-def main():
+# hparam variants of models/sketchformer.py:24-53 that change the graph: SelfAttnV2 + one class buffer layer,
+# no bottleneck (lowerdim=0: the decoder attends to the encoder output), decoder cross mask = encoder padding mask
+TINY_V2 = dict(TINY, attn_version=2, class_buffer_layers=1, class_dropout=0.0)   # dropout off: replayable
+TINY_LOWERDIM0 = dict(TINY, lowerdim=0, do_classification=False)
+TINY_NOTBLIND = dict(TINY, blind_decoder_mask=False)
+FIXTURES = [("tiny_tokens.npz", TINY, 4, False, True), ("tiny_continuous.npz", TINY, 4, True, True),
+            ("cfg1_tokens.npz", CFG1, 8, False, False), ("tiny_v2.npz", TINY_V2, 4, False, False),
+            ("tiny_lowerdim0.npz", TINY_LOWERDIM0, 4, False, False), ("tiny_notblind.npz", TINY_NOTBLIND, 4, False, False)]
+
+
+def main(force=False):
+    """Writes the fixtures that do not exist yet (all of them with --force: the zip container is not
+    byte-reproducible, so existing files are left alone unless asked)."""
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    np.savez_compressed(os.path.join(GOLD, "tiny_tokens.npz"), **run(TINY, 4, 1234, False, True))
-    np.savez_compressed(os.path.join(GOLD, "tiny_continuous.npz"), **run(TINY, 4, 1234, True, True))
-    np.savez_compressed(os.path.join(GOLD, "cfg1_tokens.npz"), **run(CFG1, 8, 1234, False, False))
+    for name, kw, batch, cont, full in FIXTURES:
+        path = os.path.join(GOLD, name)
+        if force or not os.path.exists(path):
+            np.savez_compressed(path, **run(kw, batch, 1234, cont, full))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 
 
 if __name__ == "__main__":
-    main()
+    main(force="--force" in sys.argv)

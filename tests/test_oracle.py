@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import sketchformer_oracle as O
-from oracle.make_golden import TINY, CFG1
+from oracle.make_golden import CFG1, TINY, TINY_LOWERDIM0, TINY_NOTBLIND, TINY_V2
 from sketchformer_b200 import synth
 
 
@@ -25,7 +25,10 @@ def _load(golden_dir, name):
 
 @pytest.mark.parametrize("name,kw,cont,B", [("tiny_tokens.npz", TINY, False, 4),
                                             ("tiny_continuous.npz", TINY, True, 4),
-                                            ("cfg1_tokens.npz", CFG1, False, 8)])
+                                            ("cfg1_tokens.npz", CFG1, False, 8),
+                                            ("tiny_v2.npz", TINY_V2, False, 4),
+                                            ("tiny_lowerdim0.npz", TINY_LOWERDIM0, False, 4),
+                                            ("tiny_notblind.npz", TINY_NOTBLIND, False, 4)])
 def test_golden_replay(golden_dir, name, kw, cont, B):
     g = _load(golden_dir, name)
     cfg = O.OracleConfig(use_continuous_data=cont, **kw)
