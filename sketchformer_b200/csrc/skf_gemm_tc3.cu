@@ -566,7 +566,10 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           uint8_t* al16 = ah16 + T3_A_BYTES / 2;
           uint8_t* bh16 = al16 + T3_A_BYTES / 2;
           uint8_t* bl16 = bh16 + C::B_BYTES / 2;
+#ifndef SKF_T3_DEBUG_SKIP_ASPLIT   // timing experiment only (wrong results): upper bound of what activation images
+                                   // written by the producing kernels would buy
           t3_split_bf16<T3_BM, A_MN, MIX == 2>(st8, ah16, al16, tid);
+#endif
           if (!WS) t3_split_bf16<T3_BNH, B_MN, MIX == 2>(st8 + T3_A_BYTES, bh16, bl16, tid);
           if (!WS && B_MN && do_colsum) {
 #pragma unroll
