@@ -245,7 +245,7 @@ def main():
                 3: "3xTF32 forward and dgrad, TF32 weight gradients"}.get(precision, str(precision))
         line = {"metric": "sketches/sec", "value": value, "unit": "sketches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 via split products (bf16x3 GEMMs, 3xTF32 attention)",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tensor-core split products: bf16x3 GEMMs, 3xTF32 attention; fp32 accumulate and storage)",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "parallelism": f"dp{world}", "global_batch": BATCH * world,
                            "l2": "per-step working set 3.5 GB (activations saved for backward) >> 126 MB L2; 8 distinct batches",
