@@ -115,6 +115,80 @@ def test_sdpa_against_torch_functional():
     assert torch.allclose(wf, torch.full_like(wf, 1 / 9), atol=1e-6)
 
 
+def _load_mha(m, p, name):
+    """oracle Dense kernels are (in, out); torch.nn.MultiheadAttention packs (out, in) rows of q | k | v."""
+    with torch.no_grad():
+        m.in_proj_weight.copy_(torch.cat([p[name + ".wq.k"].T, p[name + ".wk.k"].T, p[name + ".wv.k"].T]))
+        m.in_proj_bias.copy_(torch.cat([p[name + ".wq.b"], p[name + ".wk.b"], p[name + ".wv.b"]]))
+        m.out_proj.weight.copy_(p[name + ".wo.k"].T)
+        m.out_proj.bias.copy_(p[name + ".wo.b"])
+
+
+def _load_ffn_ln(layer, p, n, nln):
+    with torch.no_grad():
+        layer.linear1.weight.copy_(p[n + ".ffn.w1.k"].T); layer.linear1.bias.copy_(p[n + ".ffn.w1.b"])
+        layer.linear2.weight.copy_(p[n + ".ffn.w2.k"].T); layer.linear2.bias.copy_(p[n + ".ffn.w2.b"])
+        for i in range(1, nln + 1):
+            getattr(layer, f"norm{i}").weight.copy_(p[f"{n}.ln{i}.g"])
+            getattr(layer, f"norm{i}").bias.copy_(p[f"{n}.ln{i}.b"])
+
+
+def _randomise(p, seed):
+    """Keras initialisers leave biases 0 and LayerNorm at (1, 0): perturb everything so that no term hides."""
+    g = torch.Generator().manual_seed(seed)
+    for k in p:
+        if k.endswith(".b") or k.endswith(".g"):
+            p[k] = p[k] + 0.1 * torch.randn(p[k].shape, generator=g, dtype=p[k].dtype)
+    return p
+
+
+def test_encoder_and_decoder_stacks_against_torch_nn_transformer_layers():
+    """Independent pin of the layer wiring (the reference cannot run here): the oracle's Encoder / Decoder stacks
+    (builders/layers/transformer.py:215-224, 245-262: post-LN residual blocks, LayerNorm eps 1e-6, ReLU FFN,
+    additive -1e9 masks) against torch.nn.TransformerEncoderLayer / TransformerDecoderLayer carrying the same
+    weights, in float64, on a padded batch."""
+    cfg = O.OracleConfig(**TINY)
+    d, H, f, L = cfg.d_model, cfg.num_heads, cfg.dff, cfg.num_layers
+    p = _randomise(O.init_params(cfg, 3, torch.float64), 4)
+    x, _ = synth.token_batch(5, cfg.max_seq_len, cfg.n_classes, 77, vocab=cfg.vocab_size)
+    x = torch.from_numpy(x)
+    tar = x[:, :-1]
+    enc_mask, combined, _ = O.create_masks(x, tar, torch.float64)
+    assert bool((x == 0).any()), "the batch must contain padding"
+
+    # ---- encoder
+    got = O.encoder(p, x, enc_mask, cfg, False, None, None, torch.float64)
+    h = O.embed_input(p, "enc", x, cfg, torch.float64)
+    for i in range(L):
+        lay = torch.nn.TransformerEncoderLayer(d, H, f, dropout=0.0, activation="relu", layer_norm_eps=1e-6,
+                                               batch_first=True, norm_first=False, dtype=torch.float64)
+        lay.train()                      # no inference fast path (it zeroes padded rows); dropout is 0
+        _load_mha(lay.self_attn, p, f"enc.l{i}.mha")
+        _load_ffn_ln(lay, p, f"enc.l{i}", 2)
+        h = lay(h, src_key_padding_mask=(x == 0))
+    assert torch.allclose(got, h, atol=1e-10), float((got - h).abs().max())
+
+    # ---- decoder: causal + target padding on block 1, memory padding on block 2
+    g = torch.Generator().manual_seed(9)
+    memory = torch.randn(5, cfg.max_seq_len, d, generator=g, dtype=torch.float64)
+    for mem_mask in (torch.zeros_like(enc_mask), enc_mask):        # blind_decoder_mask True / False
+        got, _ = O.decoder(p, tar, memory, combined, mem_mask, cfg, False, None, None, torch.float64)
+        h = O.embed_input(p, "dec", tar, cfg, torch.float64)
+        Td = tar.shape[1]
+        causal = torch.triu(torch.ones(Td, Td, dtype=torch.bool), diagonal=1)
+        for i in range(L):
+            lay = torch.nn.TransformerDecoderLayer(d, H, f, dropout=0.0, activation="relu", layer_norm_eps=1e-6,
+                                                   batch_first=True, norm_first=False, dtype=torch.float64)
+            lay.train()
+            _load_mha(lay.self_attn, p, f"dec.l{i}.mha1")
+            _load_mha(lay.multihead_attn, p, f"dec.l{i}.mha2")
+            _load_ffn_ln(lay, p, f"dec.l{i}", 3)
+            h = lay(h, memory, tgt_mask=causal, tgt_key_padding_mask=(tar == 0),
+                    memory_key_padding_mask=(mem_mask[:, 0, 0, :] > 0))
+        # rows whose every key is masked (a PAD query never is: key 0 is SOS) do not occur; compare everything
+        assert torch.allclose(got, h, atol=1e-10), float((got - h).abs().max())
+
+
 def test_layernorm_and_losses_against_functional():
     g = torch.Generator().manual_seed(2)
     x = torch.randn(3, 5, 32, generator=g, dtype=torch.float64)
