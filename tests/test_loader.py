@@ -68,6 +68,27 @@ def test_centroids_read_from_the_reference_pickle_without_unpickling():
     assert (t.SEP, t.SOS, t.EOS, t.VOCAB_SIZE) == (1001, 1002, 1003, 1004)
 
 
+@pytest.mark.skipif(not os.path.exists(REF_PKL), reason="reference dictionary not present on this box")
+def test_nearest_centre_agrees_with_sklearn_kmeans_predict():
+    """utils/tokenizer.py:38 calls KMeans.predict of the pickled estimator; here a scikit-learn KMeans carrying the
+    reference's 1000 centres (lifted from the pickle) against Tokenizer.predict on 40 k points spread like
+    normalised sketch deltas.  Disagreements are only tolerated between centres that are tied to 1e-6."""
+    from sklearn.cluster import KMeans
+    t = Tokenizer(REF_PKL)
+    km = KMeans(n_clusters=t.n_clusters)
+    km.cluster_centers_ = t.centroids.astype(np.float32)
+    km._n_threads = 1
+    km.n_features_in_ = 2
+    rng = np.random.default_rng(0)
+    X = np.concatenate([rng.normal(0, 0.05, size=(20000, 2)), rng.uniform(-1, 1, size=(20000, 2))]).astype(np.float32)
+    want, got = km.predict(X), t.predict(X)
+    c = t.centroids.astype(np.float64)
+    for i in np.nonzero(want != got)[0]:
+        da, db = ((X[i] - c[want[i]]) ** 2).sum(), ((X[i] - c[got[i]]) ** 2).sum()
+        assert abs(da - db) <= 1e-6 * max(da, db), (i, want[i], got[i], da, db)
+    assert (want != got).mean() < 1e-3
+
+
 def test_preprocess_matches_reference_steps():
     """clip +-1000, normalise by max(bbox, 1) of the absolute path incl. the origin, tokenise, cut to T, PAD."""
     t = Tokenizer(centroids=_centroids())
