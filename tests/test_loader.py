@@ -68,6 +68,46 @@ def test_centroids_read_from_the_reference_pickle_without_unpickling():
     assert (t.SEP, t.SOS, t.EOS, t.VOCAB_SIZE) == (1001, 1002, 1003, 1004)
 
 
+GOLDEN_TOK = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tokenizer_ref.npz")
+
+
+def test_tokenizer_matches_vectors_made_by_the_reference_code():
+    """tests/golden/tokenizer_ref.npz was written by oracle/make_tokenizer_golden.py, which EXECUTES the reference's
+    utils/tokenizer.py (encode / decode, every max_seq_len regime: variable length, padding, truncation with the
+    SEP / EOS fix-up) on seeded float32 sketches with the pickled centroids.  Bit-exact ids, exact decoded rows."""
+    g = np.load(GOLDEN_TOK)
+    cen, n = g["centroids"], int(g["n"])
+    assert cen.shape == (1000, 2)
+    for L in g["seq_lens"].tolist():
+        t = Tokenizer(centroids=cen, max_seq_len=L)
+        for i in range(n):
+            want = g[f"enc/{L}/{i}"]
+            got = t.encode(g[f"in/{i}"].copy())
+            assert got.dtype.kind == "i" and np.array_equal(got, want), (L, i)
+            if L:
+                assert len(got) == L
+            if f"dec/{L}/{i}" in g:
+                assert np.array_equal(np.asarray(t.decode(want), np.float64), g[f"dec/{L}/{i}"]), (L, i)
+    t0 = Tokenizer(centroids=cen)
+    assert np.array_equal(t0.encode(g["in/1"].copy(), seq_len=300), g["enc_pad/0"])
+    lens = {len(g[f"enc/0/{i}"]) for i in range(n)}
+    assert min(lens) < 16 and max(lens) > 200          # the fixture covers padding and truncation at every length
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PKL), reason="/root/reference is not present on this box")
+def test_tokenizer_golden_is_reproducible_from_the_reference():
+    """Re-runs the reference code here and compares with the committed fixture (guards against a stale file)."""
+    from oracle.make_tokenizer_golden import SEQ_LENS, reference_tokenizer, sketches
+    g = np.load(GOLDEN_TOK)
+    sk = sketches()
+    assert len(sk) == int(g["n"]) and tuple(g["seq_lens"].tolist()) == SEQ_LENS
+    for L in (0, 64):
+        t = reference_tokenizer(g["centroids"], L)
+        for i in range(0, len(sk), 5):
+            assert np.array_equal(sk[i], g[f"in/{i}"])
+            assert np.array_equal(np.asarray(t.encode(sk[i].copy())), g[f"enc/{L}/{i}"])
+
+
 @pytest.mark.skipif(not os.path.exists(REF_PKL), reason="reference dictionary not present on this box")
 def test_nearest_centre_agrees_with_sklearn_kmeans_predict():
     """utils/tokenizer.py:38 calls KMeans.predict of the pickled estimator; here a scikit-learn KMeans carrying the
@@ -87,6 +127,45 @@ def test_nearest_centre_agrees_with_sklearn_kmeans_predict():
         da, db = ((X[i] - c[want[i]]) ** 2).sum(), ((X[i] - c[got[i]]) ** 2).sum()
         assert abs(da - db) <= 1e-6 * max(da, db), (i, want[i], got[i], da, db)
     assert (want != got).mean() < 1e-3
+
+
+GOLDEN_LOADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loader_ref.npz")
+
+
+def test_preprocess_matches_vectors_made_by_the_reference_code(tmp_path):
+    """tests/golden/loader_ref.npz was written by oracle/make_loader_golden.py, which EXECUTES the reference's
+    DistributedStroke3DataLoader.preprocess (clip, get_bounds normalisation, tokenizer, cut, PAD / stroke-5 rows) on
+    seeded raw sketches: clipped gaps, sub-unit bounding boxes, sketches longer than max_seq_len.  Token ids are
+    compared bit for bit, stroke-5 rows to float32 rounding (the reference divides in float32 too)."""
+    g = np.load(GOLDEN_LOADER)
+    n = int(g["n"])
+    raw = [g[f"in/{i}"] for i in range(n)]
+    _write_dataset(str(tmp_path), n_chunks=1, per_chunk=4)
+    Loader = get_dataloader_by_name("stroke3-distributed")
+    tok = Tokenizer(centroids=g["centroids"])
+    for L in g["seq_lens"].tolist():
+        ds = Loader(Loader.parse_hparams(f"max_seq_len={L}"), str(tmp_path), seed=0, tokenizer=tok)
+        got = ds.preprocess([r.copy() for r in raw])
+        assert got.shape == (n, L) and np.array_equal(got, g[f"tok/{L}"]), L
+        for i in range(n):                      # the single-sketch host path is the same function
+            assert np.array_equal(preprocess_sketch_host(raw[i].copy(), tok, L), g[f"tok/{L}"][i])
+        dc = Loader(Loader.parse_hparams(f"max_seq_len={L},use_continuous_data=True"), str(tmp_path), seed=0)
+        gc = dc.preprocess([r.copy() for r in raw], augment=False)
+        want = g[f"cont/{L}"]
+        assert gc.shape == want.shape == (n, L, 5)
+        assert np.array_equal(gc[..., 2:], want[..., 2:])                       # pen / pad flags exactly
+        assert np.allclose(gc[..., :2], want[..., :2], rtol=0, atol=1e-7)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PKL), reason="/root/reference is not present on this box")
+def test_loader_golden_is_reproducible_from_the_reference():
+    from oracle.make_loader_golden import BASE_HPS, raw_sketches, reference_loader
+    from oracle.make_tokenizer_golden import reference_tokenizer
+    g = np.load(GOLDEN_LOADER)
+    sk = raw_sketches()
+    assert all(np.array_equal(sk[i], g[f"in/{i}"]) for i in range(len(sk)))
+    ld = reference_loader(dict(BASE_HPS, max_seq_len=64, use_continuous_data=False), reference_tokenizer(g["centroids"], 0))
+    assert np.array_equal(np.asarray(ld.preprocess([s.copy() for s in sk[:10]])), g["tok/64"][:10])
 
 
 def test_preprocess_matches_reference_steps():
