@@ -2,9 +2,11 @@
 
     python -m oracle.make_golden
 
-PARITY UNPINNED: these vectors freeze the *oracle's* outputs (the reference cannot run in this
-image and ships no fixtures); they guard the restatement against drift and give the CUDA parity
-tests byte-identical inputs/expected values on the GPU box, where /root/reference is absent.
+These vectors freeze the *oracle's* outputs (TensorFlow cannot run in this image and the reference ships
+no fixtures); they guard the restatement against drift and give the CUDA parity tests byte-identical
+inputs/expected values on the GPU box, where /root/reference is absent.  The vectors made by the
+REFERENCE's own code are written by make_reference_golden.py / make_tokenizer_golden.py /
+make_loader_golden.py; against TensorFlow's kernels parity stays unpinned (see sketchformer_oracle.py).
 """
 import os
 import sys

@@ -280,3 +280,30 @@ def test_greedy_decode_runs_and_starts_with_sos(golden_dir):
     rec = g["pred/recon"]
     assert rec.shape[0] == 2 and rec.shape[1] <= TINY["max_seq_len"] + 1
     assert (rec[:, 0] == TINY["vocab_size"] - 2).all()
+
+
+def test_oracle_matches_vectors_made_by_the_reference_model_code(golden_dir):
+    """tests/golden/reference_model_tiny.npz holds what the reference's own models/sketchformer.py + builders/* code
+    computed (oracle/make_reference_golden.py runs it from /root/reference on oracle/tf_shim.py): forward outputs,
+    both losses and the greedy decode for five graph-changing hparam variants.  This test needs no /root/reference."""
+    from oracle.make_reference_golden import VARIANTS, inputs, params
+    g = np.load(os.path.join(golden_dir, "reference_model_tiny.npz"))
+    for name, kw in VARIANTS:
+        cfg = O.OracleConfig(**kw)
+        p = params(cfg)
+        x, y = inputs(cfg)
+        assert np.array_equal(x.numpy(), g[f"{name}/x"]) and np.array_equal(y.numpy(), g[f"{name}/y"])
+        tar_inp, tar_real = x[:, :-1], x[:, 1:]
+        out = O.call(p, x, tar_inp, cfg, False, O.create_masks(x, tar_inp, torch.float64), dtype=torch.float64)
+        assert np.allclose(out["embedding"].numpy(), g[f"{name}/embedding"], atol=1e-12), name
+        assert np.allclose(out["recon"].numpy(), g[f"{name}/recon"], atol=1e-11), name
+        lo = O.compute_losses(out, tar_real, y, cfg)
+        assert float(lo["recon_loss"]) == pytest.approx(float(g[f"{name}/recon_loss"]), rel=1e-12)
+        if f"{name}/class" in g:
+            assert np.allclose(out["class"].numpy(), g[f"{name}/class"], atol=1e-12)
+            assert float(lo["class_loss"]) == pytest.approx(float(g[f"{name}/class_loss"]), rel=1e-9)
+        if f"{name}/greedy" in g:
+            pr = O.predict(p, x, cfg, sos=cfg.vocab_size - 2, eos=cfg.vocab_size - 1, dtype=torch.float64)
+            assert pr["recon"].numpy().tolist() == g[f"{name}/greedy"].tolist(), name
+            if f"{name}/pred_class" in g:
+                assert pr["class"].numpy().tolist() == g[f"{name}/pred_class"].tolist()
