@@ -9,12 +9,17 @@ not the other way round.
 import json
 import re
 
-_PAIR = re.compile(r"\s*(?P<name>[A-Za-z_][\w.]*)\s*(\[\s*(?P<index>\d+)\s*\])?\s*=\s*"
-                   r"((?P<list>\[[^\]]*\])|(?P<scalar>[^,\[\]]*))\s*(,|$)")
+# One `name=value` clause.  As in the reference's grammar (utils/hparams.py:33-40): the name starts with a letter and
+# follows the previous clause's comma (and optional blanks) directly - leading blanks at the very start are malformed;
+# blanks around `=` are skipped; a scalar runs up to the next comma or `[` and KEEPS its trailing blanks.
+_PAIR = re.compile(r"(?P<name>[A-Za-z][\w.]*)(\[\s*(?P<index>\d+)\s*\])?\s*=\s*"
+                   r"((?P<scalar>[^,\[]*)|(?P<list>\[[^\]]*\]))($|,\s*)")
 
 
 def _parse_scalar(name, typ, text, whole):
-    text = text.strip()
+    """utils/hparams.py:101-148, 313-328: bools are true / True / false / False or an integer; everything else goes
+    through the type's constructor on the text as matched (int() and float() tolerate the trailing blanks, a string
+    keeps them and may be empty)."""
     try:
         if typ is bool:
             if text in ("true", "True"):
@@ -22,12 +27,6 @@ def _parse_scalar(name, typ, text, whole):
             if text in ("false", "False"):
                 return False
             return bool(int(text))
-        if typ is int:
-            return int(text)
-        if typ is float:
-            return float(text)
-        if text == "":
-            raise ValueError
         return typ(text)
     except ValueError:
         raise ValueError(f"Could not parse hparam '{name}' of type '{typ.__name__}' with value '{text}' in {whole}")
@@ -116,21 +115,18 @@ class HParams:
                 raise ValueError(f"Multiple assignments to variable '{name}' in {values}")
             seen.add((name, None))
             if m.group("list") is not None:
+                # utils/hparams.py:174-181: elements are separated by commas and / or blanks, empty ones are dropped
                 body = m.group("list")[1:-1]
-                out[name] = [_parse_scalar(name, typ, t, values) for t in body.split(",")] if body.strip() else []
+                out[name] = [_parse_scalar(name, typ, t, values) for t in re.split("[ ,]", body) if t]
             else:
                 out[name] = _parse_scalar(name, typ, m.group("scalar"), values)
         return self.override_from_dict(out)
 
     def override_from_dict(self, values):
+        # An index assignment `a[1]=x` reaches this point as {1: x}, exactly as in the reference
+        # (utils/hparams.py:232-344 builds the dict, 552-567 hands it to set_hparam), where it is then refused:
+        # "Must pass a list" for a list hparam, "Could not cast" for a scalar one.  Same here.
         for name, v in values.items():
-            if isinstance(v, dict):                       # index assignments a[1]=..
-                cur = list(getattr(self, name))
-                for i, x in v.items():
-                    if i >= len(cur):
-                        raise ValueError(f"Index {i} out of range for hparam '{name}'")
-                    cur[i] = x
-                v = cur
             self.set_hparam(name, v)
         return self
 
