@@ -167,3 +167,27 @@ def test_default_hparam_sets_come_from_the_reference_code():
     D = get_dataloader_by_name("stroke3-distributed")
     assert type(ld).name == D.name == "stroke3-distributed"
     assert ref_defaults == D.default_hparams().values()
+
+
+@needs_ref
+def test_config_json_is_byte_identical_to_the_reference(tmp_path):
+    """save_config / load_config / combine_hparams_into_one (utils/hparams.py:49-84; train.py:76-77 writes
+    config.json, evaluate-metrics.py reads it): the file the reference code writes for the merged model + data
+    hparams, byte for byte, and each side loads the other's file."""
+    ref = _reference_hparams_module()
+    M, D = get_model_by_name("sketch-transformer-tf2"), get_dataloader_by_name("stroke3-distributed")
+    ours = combine_hparams_into_one(M.parse_hparams("batch_size=64", "d_model=256,dff=1024,lr=0.001"),
+                                    D.parse_hparams("max_seq_len=64,use_continuous_data=True"))
+    theirs = ref.combine_hparams_into_one(ref.HParams(**M.default_hparams().values()).parse("batch_size=64,d_model=256,dff=1024,lr=0.001"),
+                                          ref.HParams(**D.default_hparams().values()).parse("max_seq_len=64,use_continuous_data=True"))
+    assert list(ours.values().items()) == list(theirs.values().items())          # same keys, same order, same values
+    a, b = tmp_path / "ours.json", tmp_path / "ref.json"
+    save_config(str(a), ours)
+    ref.save_config(str(b), theirs, verbose=False)
+    assert a.read_bytes() == b.read_bytes()
+    fresh = combine_hparams_into_one(M.default_hparams(), D.default_hparams())
+    load_config(fresh, str(b))
+    assert fresh.values() == ours.values()
+    fresh_ref = ref.combine_hparams_into_one(ref.HParams(**M.default_hparams().values()), ref.HParams(**D.default_hparams().values()))
+    ref.load_config(fresh_ref, str(a), verbose=False)
+    assert fresh_ref.values() == theirs.values()
