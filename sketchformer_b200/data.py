@@ -256,10 +256,18 @@ class DistributedStroke3DataLoader:
             yield [np.stack(xs), np.stack(ys).astype(np.int64)]
 
     def get_n_samples_from(self, split_name, n, shuffled=False, seeded=None, preprocess=False):
+        """core/data.py:174-209: the first n samples of the loaded chunk in FILE order, or n of a permutation of it.
+        `seeded` seeds numpy's legacy global generator in the reference (np.random.seed(int(seeded)) followed by
+        np.random.permutation), so the same MT19937 stream is used here: seeded=True picks the very samples the
+        reference's evaluation picks (models/evaluation_mixin.py:25-27)."""
         split = self._ready(split_name)
-        rng = np.random.default_rng(int(seeded)) if seeded is not None else self.rng
-        order = rng.permutation(split.current_len)[:n] if shuffled else list(range(min(n, split.current_len)))
-        return self._collate(split, [split.current_index_shuffle[i] for i in order])
+        if shuffled:
+            perm = (np.random.RandomState(int(seeded)).permutation(split.current_len) if seeded is not None
+                    else self.rng.permutation(split.current_len))
+            order = perm[:n]
+        else:
+            order = list(range(min(n, split.current_len)))
+        return self._collate(split, order)
 
     def get_all_data_from(self, split_name):
         split = self._ready(split_name)

@@ -230,3 +230,25 @@ def test_distributed_loader_shards_by_rank(tmp_path):
     a._ready("train"); b._ready("train")
     ia, ib = set(a.splits["train"].current_index_shuffle), set(b.splits["train"].current_index_shuffle)
     assert not (ia & ib) and len(ia | ib) == 30                        # one chunk: residue classes of one order
+
+
+def test_get_n_samples_picks_the_reference_indices(tmp_path):
+    """core/data.py:174-209: file order for shuffled=False (whatever the train shuffle is), and for seeded=True the
+    permutation numpy's legacy global generator produces after np.random.seed(1)."""
+    _write_dataset(str(tmp_path))
+    Loader = get_dataloader_by_name("stroke3-distributed")
+    ds = Loader(Loader.parse_hparams("max_seq_len=32"), str(tmp_path), seed=5, tokenizer=Tokenizer(centroids=_centroids()))
+    for split in ("valid", "train"):
+        allx, ally = ds.get_all_data_from(split)
+        n = len(allx)
+        cur = ds.splits[split].current
+        assert np.array_equal(allx, np.stack(list(cur["x"]))) and np.array_equal(ally[:, 0], cur["y"])   # file order
+        x5, y5 = ds.get_n_samples_from(split, 5)
+        assert np.array_equal(x5, allx[:5]) and np.array_equal(y5, ally[:5])
+        np.random.seed(1)
+        want = np.random.permutation(n)[:7]
+        np.random.seed()
+        xs, ys = ds.get_n_samples_from(split, 7, shuffled=True, seeded=True)
+        assert np.array_equal(xs, allx[want]) and np.array_equal(ys, ally[want])
+        xs2, _ = ds.get_n_samples_from(split, 7, shuffled=True, seeded=True)
+        assert np.array_equal(xs, xs2)
