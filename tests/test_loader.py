@@ -252,3 +252,64 @@ def test_get_n_samples_picks_the_reference_indices(tmp_path):
         assert np.array_equal(xs, allx[want]) and np.array_equal(ys, ally[want])
         xs2, _ = ds.get_n_samples_from(split, 7, shuffled=True, seeded=True)
         assert np.array_equal(xs, xs2)
+
+
+REF_PREP = "/root/reference/prep_data/prepare-distributed-quickdraw.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PREP), reason="/root/reference is not present on this box")
+def test_loader_reads_a_dataset_written_by_the_reference_script(tmp_path, monkeypatch):
+    """prep_data/prepare-distributed-quickdraw.py (the writer of the chunked on-disk format: train_XXX.npz, valid.npz,
+    test.npz, meta.npz) is RUN from the reference on three synthetic QuickDraw class files; our loader must read its
+    output: metadata, every test / valid sample in file order with the right label, every train sample once per
+    epoch."""
+    import runpy
+    rng = np.random.default_rng(4)
+    raw = tmp_path / "raw"; raw.mkdir()
+    names = ["cat", "dog", "tree"]
+    (tmp_path / "classes.txt").write_text("\n".join(names + ["unused"]) + "\n")
+    per_class = {}
+    for c in names:
+        def sketches(n):
+            out = np.empty(n, dtype=object)
+            for i in range(n):
+                out[i] = _sketch(rng, int(rng.integers(3, 40))).astype(np.int16)
+            return out
+        per_class[c] = {"train": sketches(12), "valid": sketches(4), "test": sketches(6)}
+        np.savez(raw / f"{c}.npz", **per_class[c])
+    target = tmp_path / "chunked"
+    monkeypatch.setattr("sys.argv", ["prepare-distributed-quickdraw.py", "--dataset-dir", str(raw), "--class-list",
+                                     str(tmp_path / "classes.txt"), "--n-chunks", "3", "--n-classes", "3",
+                                     "--target-dir", str(target)])
+    runpy.run_path(REF_PREP, run_name="__main__")
+    assert sorted(os.listdir(target)) == ["meta.npz", "test.npz", "train_000.npz", "train_001.npz", "train_002.npz", "valid.npz"]
+
+    tok = Tokenizer(centroids=_centroids())
+    Loader = get_dataloader_by_name("stroke3-distributed")
+    T = 24
+    ds = Loader(Loader.parse_hparams(f"max_seq_len={T}"), str(target), seed=0, tokenizer=tok)
+    meta = np.load(target / "meta.npz", allow_pickle=True)
+    assert ds.n_classes == 3 and ds.n_samples == 36 == int(meta["n_samples_train"])
+    assert list(ds.class_names) == names and ds.scale_factor == float(meta["std"])
+    for split, n_per in (("test", 6), ("valid", 4)):
+        x, y = ds.get_all_data_from(split)
+        want_x = [preprocess_sketch_host(s, tok, T) for c in names for s in per_class[c][split]]
+        assert x.shape == (3 * n_per, T) and np.array_equal(x, np.stack(want_x))
+        assert y[:, 0].tolist() == [i for i in range(3) for _ in range(n_per)]
+    # "one epoch" over the three train chunks as core/data.py:79-106 counts it: 'end_of_split' is raised when the LAST
+    # chunk is swapped in (file_cursor reaches n_files at that moment), so the sweep covers the first two chunks and the
+    # one sample that completes the running batch - 12 + 12 + 1 - and never a sample twice
+    from collections import Counter
+    seen = []
+    for bx, by in ds.batch_iterator("train", 5, stop_at_end_of_split=True):
+        seen += [(tuple(r.tolist()), int(l)) for r, l in zip(bx, by[:, 0])]
+    want = Counter((tuple(preprocess_sketch_host(s, tok, T).tolist()), i) for i, c in enumerate(names)
+                   for s in per_class[c]["train"])
+    assert len(seen) == 25 and not (Counter(seen) - want)
+    # an endless iterator does reach every training sketch
+    it = ds.batch_iterator("train", 6, stop_at_end_of_split=False)
+    pool = Counter()
+    for _ in range(18):
+        bx, by = next(it)
+        pool.update((tuple(r.tolist()), int(l)) for r, l in zip(bx, by[:, 0]))
+    assert set(pool) == set(want)
