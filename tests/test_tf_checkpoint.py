@@ -113,3 +113,66 @@ def test_checkpoint_export_import(tmp_path):
         assert np.array_equal(p2[k], params[k]) and np.array_equal(m2[k], m[k]) and np.array_equal(v2[k], v[k])
     with pytest.raises(KeyError):
         T.import_checkpoint(prefix, dict(HPS, num_layers=3))
+
+
+# ---- checkpoint keys against the reference's attribute structure ---------------------------------------------------
+def _tracked_variables(obj, prefix=""):
+    """TF object-graph naming restated (tf.train.Checkpoint: a variable's key is the chain of attribute names that
+    leads to it, list elements by index, the layers of a keras Sequential as `layer_with_weights-N`), applied to an
+    object built by the REFERENCE's code on oracle/tf_shim.py: attribute names and nesting are the reference's."""
+    import torch
+    from oracle import tf_shim
+    out = {}
+    if isinstance(obj, tf_shim.Sequential):
+        for n, lay in enumerate(obj.layers):
+            out.update(_tracked_variables(lay, f"{prefix}/layer_with_weights-{n}"))
+        return out
+    for name, val in vars(obj).items():
+        if name in ("pos_encoding",):                       # a constant tensor, not a variable
+            continue
+        path = f"{prefix}/{name}" if prefix else name
+        if isinstance(val, torch.Tensor):
+            out[path] = tuple(val.shape)
+        elif isinstance(val, tf_shim.Layer):
+            out.update(_tracked_variables(val, path))
+        elif isinstance(val, list) and val and all(isinstance(v, tf_shim.Layer) for v in val):
+            for i, v in enumerate(val):
+                out.update(_tracked_variables(v, f"{path}/{i}"))
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/sketchformer.py"),
+                    reason="/root/reference is not present on this box")
+@pytest.mark.parametrize("variant", ["default", "v2_classbuffer", "lowerdim0", "continuous", "no_recon"])
+def test_checkpoint_keys_follow_the_reference_attribute_structure(variant):
+    """key_map() against the variables of a model that the reference's build_model() created (models/sketchformer.py
+    :63-107 on the TF-API shim): same attribute paths under the `transformer/` root (core/models.py:322-323), same
+    shapes as our parameters."""
+    import torch
+    from oracle import sketchformer_oracle as O
+    from oracle import tf_shim
+    from oracle.make_golden import TINY, TINY_LOWERDIM0, TINY_V2
+    from oracle.reference_model import build_reference
+    from sketchformer_b200 import synth
+    kw = {"default": TINY, "v2_classbuffer": dict(TINY_V2), "lowerdim0": TINY_LOWERDIM0,
+          "continuous": dict(TINY, use_continuous_data=True), "no_recon": dict(TINY, do_reconstruction=False)}[variant]
+    cfg = O.OracleConfig(**kw)
+    p = O.init_params(cfg, 0, torch.float64)
+    if cfg.use_continuous_data:
+        x = torch.from_numpy(synth.continuous_batch(2, cfg.max_seq_len, cfg.n_classes, 1)[0]).double()
+    else:
+        x = torch.from_numpy(synth.token_batch(2, cfg.max_seq_len, cfg.n_classes, 1, vocab=cfg.vocab_size)[0])
+    m = build_reference(tf_shim.load_reference_model(), cfg, p, x)
+    layers = {k: v for k, v in vars(m).items() if isinstance(v, (tf_shim.Layer, list))}
+    holder = type("Holder", (), {})()
+    holder.__dict__.update(layers)
+    ref_vars = {"transformer/" + k: v for k, v in _tracked_variables(holder).items()}
+    hps = dict(num_layers=cfg.num_layers, lowerdim=cfg.lowerdim, attn_version=cfg.attn_version,
+               do_classification=cfg.do_classification, do_reconstruction=cfg.do_reconstruction,
+               class_buffer_layers=cfg.class_buffer_layers, use_continuous_data=cfg.use_continuous_data)
+    km = T.key_map(hps)
+    assert set(km) == set(p), (set(km) ^ set(p))
+    ours = {key: tuple(p[name].shape) for name, key in km.items()}
+    assert set(ours) == set(ref_vars), sorted(set(ours) ^ set(ref_vars))
+    for key in ours:
+        assert ours[key] == ref_vars[key], key
