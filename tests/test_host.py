@@ -88,3 +88,88 @@ def test_engine_refuses_to_run_without_cuda():
     from sketchformer_b200.engine import Engine
     with pytest.raises(_lib.SkfError):
         Engine(make_cfg(4, 24, 64, 128, 4, 2, 68, 10, 32))
+
+
+# ---- checkpoint cadence and model-side defaults against the reference's core/models.py ------------------------------
+import importlib.util   # noqa: E402
+import os               # noqa: E402
+import sys              # noqa: E402
+import types            # noqa: E402
+
+import pytest           # noqa: E402
+
+REF_CORE_MODELS = "/root/reference/core/models.py"
+
+
+def _reference_base_model():
+    """core/models.py executed from the reference with stand-ins for what its imports need at class-definition time
+    (tf.keras.Model as a plain base class, the utils / metrics / notifier packages): the methods under test are pure
+    Python."""
+    names = ["tensorflow", "utils", "utils.hparams", "metrics", "core", "core.metrics", "core.notifyier", "ref_core_models"]
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        tf = types.ModuleType("tensorflow")
+        tf.keras = types.SimpleNamespace(Model=type("Model", (), {}))
+        sys.modules["tensorflow"] = tf
+        spec = importlib.util.spec_from_file_location("utils.hparams", "/root/reference/utils/hparams.py")
+        hp = importlib.util.module_from_spec(spec); spec.loader.exec_module(hp)
+        utils = types.ModuleType("utils"); utils.hparams = hp
+        sys.modules["utils"], sys.modules["utils.hparams"] = utils, hp
+        sys.modules["metrics"] = types.ModuleType("metrics")
+        core = types.ModuleType("core"); core.__path__ = []
+        sys.modules["core"] = core
+        m = types.ModuleType("core.metrics"); m.QuickMetric = object; sys.modules["core.metrics"] = m
+        m = types.ModuleType("core.notifyier"); m.Notifyier = object; sys.modules["core.notifyier"] = m
+        spec = importlib.util.spec_from_file_location("ref_core_models", REF_CORE_MODELS)
+        mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+        return mod.BaseModel
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CORE_MODELS), reason="/root/reference is not present on this box")
+def test_base_hparams_paths_and_checkpoint_cadence_match_the_reference(tmp_path):
+    """BaseModel.base_default_hparams / get_config_filepath / save_checkpoint_if_its_time (core/models.py:17-30,
+    109-112, 346-358) executed from the reference, against sketchformer_b200.model.Transformer."""
+    from sketchformer_b200.model import Transformer
+    Base = _reference_base_model()
+    assert list(Base.base_default_hparams().values().items()) == list(Transformer.base_default_hparams().values().items())
+
+    class RefNamed(Base):
+        name = Transformer.name
+    assert RefNamed.get_config_filepath("/out", "x1") == Transformer.get_config_filepath("/out", "x1")
+
+    class Step:                      # tf.Variable stand-in: .numpy() and `+ 1` are all the method uses
+        def __init__(self, v):
+            self.v = v
+
+        def numpy(self):
+            return self.v
+
+        def __add__(self, o):
+            return self.v + o
+
+    for safety_save, save_every, bpe in ((.5, 1., 10), (1., 1., 7), (.25, 2., 8), (.5, 1., 3)):
+        ref_saves, our_saves = [], []
+        ref = types.SimpleNamespace(hps=dict(safety_save=safety_save, save_every=save_every), batches_per_epoch=bpe,
+                                    wgt_out_dir="W",
+                                    ckpt_manager=types.SimpleNamespace(save=lambda: ref_saves.append(("safety", ref.current_step.v)) or "p"),
+                                    ckpt=types.SimpleNamespace(save=lambda file_prefix: ref_saves.append(("fixed", file_prefix))))
+        ours = object.__new__(Transformer)
+        ours.hps, ours.batches_per_epoch, ours.wgt_out_dir = dict(ref.hps), bpe, str(tmp_path)
+        ours.save_checkpoint = lambda path: our_saves.append(path)
+        for step in range(1, 4 * bpe + 1):
+            ref.current_step = Step(step)
+            Base.save_checkpoint_if_its_time(ref)
+            ours.current_step = step
+            ours.save_checkpoint_if_its_time()
+        ref_safety = [s for k, s in ref_saves if k == "safety"]
+        ref_fixed = [p for k, p in ref_saves if k == "fixed"]
+        our_safety = [int(os.path.basename(p)[5:-3]) for p in our_saves if os.path.basename(p).startswith("ckpt-")]
+        our_fixed = [os.path.basename(p)[:-3] for p in our_saves if os.path.basename(p).startswith("step")]
+        assert our_safety == ref_safety and ref_safety, (safety_save, save_every, bpe)
+        assert our_fixed == [os.path.basename(p) for p in ref_fixed] and ref_fixed      # 'step<N>' file stems
