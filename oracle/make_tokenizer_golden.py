@@ -27,21 +27,32 @@ OUT = os.path.join(ROOT, "tests", "golden", "tokenizer_ref.npz")
 SEQ_LENS = (0, 16, 64, 200)
 
 
-def load_reference_tokenizer_class():
+def load_reference_tokenizer_class(which="Tokenizer"):
+    """utils/tokenizer.py executed from the reference.  `utils.skt_tools` (strokes_to_lines / lines_to_strokes, used
+    by GridTokenizer) is the reference's own file too, loaded with empty stand-ins for the drawing libraries it
+    imports at the top (svgwrite, PIL, rdp, svgpathtools)."""
     pkg = types.ModuleType("utils")
     pkg.__path__ = [os.path.join(REF, "utils")]
     helpers = types.ModuleType("utils.helpers")
     helpers.load_pickle = lambda path: (_ for _ in ()).throw(RuntimeError("not used"))
-    skt = types.ModuleType("utils.skt_tools")
-    skt.strokes_to_lines = skt.lines_to_strokes = None
-    saved = {k: sys.modules.get(k) for k in ("utils", "utils.helpers", "utils.skt_tools", "utils.tokenizer")}
-    sys.modules.update({"utils": pkg, "utils.helpers": helpers, "utils.skt_tools": skt})
+    names = ("utils", "utils.helpers", "utils.skt_tools", "utils.tokenizer", "svgwrite", "PIL", "rdp", "svgpathtools")
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update({"utils": pkg, "utils.helpers": helpers})
     try:
+        sys.modules["svgwrite"] = types.ModuleType("svgwrite")
+        pil = types.ModuleType("PIL"); pil.Image = pil.ImageDraw = None; sys.modules["PIL"] = pil
+        rdp = types.ModuleType("rdp"); rdp.rdp = None; sys.modules["rdp"] = rdp
+        svp = types.ModuleType("svgpathtools"); svp.real = svp.imag = svp.svg2paths = svp.wsvg = None
+        sys.modules["svgpathtools"] = svp
+        spec = importlib.util.spec_from_file_location("utils.skt_tools", os.path.join(REF, "utils", "skt_tools.py"))
+        skt = importlib.util.module_from_spec(spec)
+        sys.modules["utils.skt_tools"] = skt
+        spec.loader.exec_module(skt)
         spec = importlib.util.spec_from_file_location("utils.tokenizer", os.path.join(REF, "utils", "tokenizer.py"))
         mod = importlib.util.module_from_spec(spec)
         sys.modules["utils.tokenizer"] = mod
         spec.loader.exec_module(mod)
-        return mod.Tokenizer
+        return getattr(mod, which)
     finally:
         for k, v in saved.items():
             if v is None:
@@ -81,6 +92,28 @@ def sketches(n=48, seed=7):
     return out
 
 
+def grid_sketches(n=30, seed=19):
+    """Normalised sketches whose absolute path stays inside the canvas most of the time; some end without a pen lift
+    (their tail is dropped by the reference), some have none at all, some touch the upper edge exactly."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        m = int(rng.integers(2, 30))
+        s = np.zeros((m, 3), np.float32)
+        s[:, :2] = rng.normal(0, 0.12, size=(m, 2))
+        s[0, :2] = rng.uniform(-0.5, 0.5, size=2)
+        s[:, 2] = rng.random(m) < 0.2
+        if i % 3 == 0:
+            s[-1, 2] = 1
+        if i % 7 == 0:
+            s[:, 2] = 0
+        if i % 10 == 0:
+            s[:, :2] = 0
+            s[0, :2] = (1.0, -1.0)          # lands exactly on the upper x edge and the lower y edge
+        out.append(s)
+    return out
+
+
 def main():
     from sketchformer_b200.tokenizer import load_centroids
     cen = load_centroids(PKL)
@@ -99,6 +132,21 @@ def main():
     # seq_len argument (padding of a variable-length tokenizer) and list decoding
     t0 = reference_tokenizer(cen, 0)
     data["enc_pad/0"] = np.asarray(t0.encode(sk[1].copy(), seq_len=300), np.int64)
+    # token_type='grid' (utils/tokenizer.py:103-200).  Inputs go in as float64: the reference accumulates the absolute
+    # path in Python floats (NumPy 1.17 promotes float32 + int to float64), which NumPy 2 would otherwise do in float32
+    Grid = load_reference_tokenizer_class("GridTokenizer")
+    gsk = grid_sketches()
+    data["grid/n"] = np.array(len(gsk))
+    for i, s in enumerate(gsk):
+        data[f"grid/in/{i}"] = s
+    for res in (100, 16):
+        for L in (0, 32):
+            t = Grid(resolution=res, max_seq_len=L)
+            for i, s in enumerate(gsk):
+                enc = np.asarray(t.encode(s.astype(np.float64)), np.int64)
+                data[f"grid/enc/{res}/{L}/{i}"] = enc
+                if L == 0:
+                    data[f"grid/dec/{res}/{i}"] = np.asarray(t.decode(enc), np.float64)
     np.savez_compressed(OUT, **data)
     print(OUT, os.path.getsize(OUT), "bytes;", len(sk), "sketches x", len(SEQ_LENS), "max_seq_len settings")
 

@@ -121,11 +121,14 @@ class DistributedStroke3DataLoader:
         self.limit = 1000
         self.rng = np.random.default_rng(seed)
         self.tokenizer = tokenizer
-        if not self.hps["use_continuous_data"] and tokenizer is None:
-            if self.hps["token_type"] != "dictionary":
-                raise NotImplementedError("token_type=%s: only the dictionary tokenizer is built" % self.hps["token_type"])
-            from .tokenizer import Tokenizer
-            self.tokenizer = Tokenizer(self.hps["tokenizer_dict_file"], max_seq_len=0)
+        if not self.hps["use_continuous_data"] and tokenizer is None:      # distributed_stroke3.py:32-36
+            from .tokenizer import GridTokenizer, Tokenizer
+            if self.hps["token_type"] == "dictionary":
+                self.tokenizer = Tokenizer(self.hps["tokenizer_dict_file"], max_seq_len=0)
+            elif self.hps["token_type"] == "grid":
+                self.tokenizer = GridTokenizer(resolution=100)            # the reference ignores tokenizer_resolution
+            else:
+                raise ValueError("token_type=%s: 'dictionary' or 'grid'" % self.hps["token_type"])
         files = glob.glob(os.path.join(data_directory, "*"))
         base = os.path.basename
         meta = [f for f in files if base(f).startswith("meta")][0]
@@ -224,6 +227,9 @@ class DistributedStroke3DataLoader:
     def preprocess_on_device(self, sketches, device="cuda:0"):
         """Token mode: the same preprocessing as `preprocess`, fused in one CUDA kernel (skf_tokenize_strokes);
         returns int64 [B, max_seq_len] already in HBM."""
+        if not hasattr(self.tokenizer, "encode_batch_device"):
+            raise NotImplementedError("device-side tokenisation exists for the dictionary tokenizer only "
+                                      "(token_type=grid is tokenised on the host: preprocess())")
         return self.tokenizer.encode_batch_device(sketches, self.hps["max_seq_len"], device, float(self.limit))
 
     # ---- iteration (core/data.py:115-254) -----------------------------------------------------------

@@ -140,6 +140,82 @@ class Tokenizer:
         return out
 
 
+class GridTokenizer:
+    """`token_type='grid'` (utils/tokenizer.py:103-200): a point of the ABSOLUTE polyline is the id of the grid cell
+    it falls in, cells numbered row-major over [-1, 1)^2 with `resolution` cells per axis (+1: id 0 is PAD); SEP closes
+    every stroke, SOS / EOS frame the sketch; padding / truncation as in the dictionary tokenizer.  Host path only
+    (the reference builds it with resolution=100: vocabulary 10004).
+
+    Kept quirks of the reference: coordinates are NOT clamped to the canvas (only the exact upper edge 1.0 is folded
+    into the last cell; np.int64() truncates toward zero), and the points after the last pen lift are dropped unless
+    the sketch has no pen lift at all (utils/skt_tools.py:71-96)."""
+
+    def __init__(self, resolution=100, max_seq_len=0):
+        self.max_seq_len = max_seq_len
+        self.r = int(resolution / 2)
+        self.resolution = 2 * self.r
+        self.half_pixel = 1 / self.resolution
+        self.PAD = 0
+        self.SEP = self.resolution ** 2 + 1
+        self.SOS = self.SEP + 1
+        self.EOS = self.SEP + 2
+        self.VOCAB_SIZE = self.resolution ** 2 + 4
+
+    def _cells(self, v):
+        c = np.int64((v + 1) * self.r)
+        c[c == self.resolution] = self.resolution - 1
+        return c
+
+    def encode(self, stroke3, seq_len=0):
+        s = np.asarray(stroke3, np.float64).reshape(-1, 3)
+        xy = np.cumsum(s[:, :2], axis=0)                     # running sum in float64, point by point
+        ends = np.flatnonzero(s[:, 2] == 1)
+        bounds = [(0, len(s))] if len(ends) == 0 else list(zip(np.concatenate(([0], ends[:-1] + 1)), ends + 1))
+        out = [self.SOS]
+        for a, b in bounds:
+            ids = self._cells(xy[a:b, 0]) + self._cells(xy[a:b, 1]) * self.resolution + 1
+            out.extend(ids.tolist())
+            out.append(self.SEP)
+        out.append(self.EOS)
+        if self.max_seq_len:
+            npad = self.max_seq_len - len(out)
+            if npad > 0:
+                out += [self.PAD] * npad
+            else:
+                out = out[:self.max_seq_len]
+                out[-2:] = [self.SEP, self.EOS]
+        if len(out) < seq_len:
+            out += [self.PAD] * (seq_len - len(out))
+        return np.array(out, dtype=np.int64)
+
+    def decode(self, seqs):
+        if len(seqs) > 0 and isinstance(seqs[0], (list, tuple, np.ndarray)):
+            return [self.decode_single(np.squeeze(s)) for s in seqs]
+        return self.decode_single(seqs)
+
+    def decode_single(self, tokens):
+        """tokens -> stroke-3 whose first row is the absolute position of the first cell centre
+        (lines_to_strokes(..., omit_first_point=False), utils/skt_tools.py:55-68)."""
+        pts, pen = [], []
+        for t in np.asarray(tokens).reshape(-1).tolist():
+            if 0 < t < self.SEP:
+                cy, cx = divmod(t - 1, self.resolution)
+                pts.append((cx / self.r - 1 + self.half_pixel, cy / self.r - 1 + self.half_pixel))
+                pen.append(0)
+            elif t == self.SEP and pen and pen[-1] == 0:
+                pen[-1] = 1
+            elif t == self.EOS:
+                break
+        if not pts:
+            pts, pen = [(0.0, 0.0)], [0]
+        pen[-1] = 1                                          # the last point of the last line always closes it
+        out = np.zeros((len(pts), 3), np.float64)
+        out[:, :2] = np.asarray(pts, np.float64)
+        out[:, 2] = pen
+        out[1:, :2] -= out[:-1, :2].copy()
+        return out
+
+
 def preprocess_sketch_host(sketch, tokenizer, max_seq_len, limit=1000.0):
     """Host restatement of DistributedStroke3DataLoader.preprocess for one token-mode sketch
     (distributed_stroke3.py:90-125 + _cap_pad_and_convert_sketch 138-153, utils/sketch.py:31-50)."""

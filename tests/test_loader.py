@@ -313,3 +313,49 @@ def test_loader_reads_a_dataset_written_by_the_reference_script(tmp_path, monkey
         bx, by = next(it)
         pool.update((tuple(r.tolist()), int(l)) for r, l in zip(bx, by[:, 0]))
     assert set(pool) == set(want)
+
+
+def test_grid_tokenizer_matches_vectors_made_by_the_reference_code():
+    """token_type='grid' (utils/tokenizer.py:103-200 + utils/skt_tools.py:55-96, executed by
+    oracle/make_tokenizer_golden.py): encode for two resolutions and two max_seq_len regimes, decode of the encoded
+    sequences; sketches that end without a pen lift, have none, or sit exactly on the canvas edge."""
+    from sketchformer_b200.tokenizer import GridTokenizer
+    g = np.load(GOLDEN_TOK)
+    n = int(g["grid/n"])
+    t100 = GridTokenizer(resolution=100)
+    assert (t100.PAD, t100.SEP, t100.SOS, t100.EOS, t100.VOCAB_SIZE) == (0, 10001, 10002, 10003, 10004)
+    for res in (100, 16):
+        for L in (0, 32):
+            t = GridTokenizer(resolution=res, max_seq_len=L)
+            for i in range(n):
+                s = g[f"grid/in/{i}"]
+                want = g[f"grid/enc/{res}/{L}/{i}"]
+                assert np.array_equal(t.encode(s.copy()), want), (res, L, i)
+                if L == 0:
+                    dec = t.decode(want)
+                    assert dec.shape == g[f"grid/dec/{res}/{i}"].shape and np.allclose(dec, g[f"grid/dec/{res}/{i}"], atol=1e-12)
+    # a decoded sketch re-encodes to the same tokens (cell centres stay in their cells) - for sketches that stay on
+    # the canvas: the reference does not clamp, a point outside gets an id outside the vocabulary and decode drops it
+    inside = 0
+    for i in range(n):
+        enc = g[f"grid/enc/100/0/{i}"]
+        if enc.min() > 0 and enc.max() <= t100.EOS:
+            inside += 1
+            assert np.array_equal(t100.encode(t100.decode(enc)), enc)
+    assert inside >= n // 2
+
+
+def test_distributed_loader_with_the_grid_tokenizer(tmp_path):
+    """token_type=grid: the loader builds GridTokenizer(resolution=100) (distributed_stroke3.py:35-36) and its batches
+    are the per-sketch preprocessing with that tokenizer (vocabulary 10004)."""
+    from sketchformer_b200.tokenizer import GridTokenizer
+    _write_dataset(str(tmp_path), n_chunks=1, per_chunk=6)
+    Loader = get_dataloader_by_name("stroke3-distributed")
+    ds = Loader(Loader.parse_hparams("max_seq_len=40,token_type=grid"), str(tmp_path), seed=0)
+    assert isinstance(ds.tokenizer, GridTokenizer) and ds.tokenizer.VOCAB_SIZE == 10004
+    x, y = ds.get_all_data_from("test")
+    raw = np.load(tmp_path / "test.npz", allow_pickle=True)["x"]
+    assert x.shape == (25, 40) and x.dtype.kind == "i" and int(x.max()) <= ds.tokenizer.EOS
+    for i in (0, 7, 24):
+        assert np.array_equal(x[i], preprocess_sketch_host(raw[i], ds.tokenizer, 40))
+    assert (x[:, 0] == ds.tokenizer.SOS).all()
