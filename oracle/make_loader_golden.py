@@ -39,7 +39,8 @@ def _load(name, path):
 def reference_loader(hps, tokenizer):
     """An instance of the reference's DistributedStroke3DataLoader that can run preprocess()."""
     names = ["tensorflow", "svgwrite", "svglib", "svglib.svglib", "reportlab", "reportlab.graphics", "utils",
-             "utils.sketch", "core", "core.data", "dataloaders_ref_stroke3"]
+             "utils.sketch", "utils.skt_tools", "PIL", "rdp", "svgpathtools", "core", "core.data",
+             "dataloaders_ref_stroke3"]
     saved = {k: sys.modules.get(k) for k in names}
     try:
         for n in ("tensorflow", "svgwrite", "svglib", "reportlab"):
@@ -50,6 +51,11 @@ def reference_loader(hps, tokenizer):
         utils.__path__ = [os.path.join(REF, "utils")]
         sys.modules["utils"] = utils
         utils.sketch = _load("utils.sketch", os.path.join(REF, "utils", "sketch.py"))
+        pil = types.ModuleType("PIL"); pil.Image = pil.ImageDraw = None; sys.modules["PIL"] = pil
+        m = types.ModuleType("rdp"); m.rdp = None; sys.modules["rdp"] = m
+        m = types.ModuleType("svgpathtools"); m.real = m.imag = m.svg2paths = m.wsvg = None; sys.modules["svgpathtools"] = m
+        # utils/__init__.py:5 imports skt_tools under this name; preprocess uses it for shuffle_stroke
+        utils.tu_sketch_tools = _load("utils.skt_tools", os.path.join(REF, "utils", "skt_tools.py"))
         core = types.ModuleType("core"); core.__path__ = []
         data = types.ModuleType("core.data")
         data.BaseDataLoader = type("BaseDataLoader", (), {})

@@ -194,13 +194,14 @@ class DistributedStroke3DataLoader:
 
     # ---- per-sketch preprocessing (distributed_stroke3.py:90-162) ---------------------------------
     def preprocess(self, data, augment=False):
-        from .tokenizer import preprocess_sketch_host
+        """distributed_stroke3.py:90-125: clip, (continuous + train: random scale and point dropout), bbox
+        normalisation, optional stroke shuffle / absolute coordinates, tokenizer, cut to max_seq_len, PAD / stroke-5."""
+        from .tokenizer import convert_to_absolute, preprocess_sketch_host, shuffle_strokes
         T, out = self.hps["max_seq_len"], []
-        if self.hps["shuffle_stroke"] or self.hps["use_absolute_strokes"]:
-            raise NotImplementedError("shuffle_stroke / use_absolute_strokes are not built")
+        shuffle, absolute = bool(self.hps["shuffle_stroke"]), bool(self.hps["use_absolute_strokes"])
         for sketch in data:
             if not self.hps["use_continuous_data"]:
-                out.append(preprocess_sketch_host(sketch, self.tokenizer, T, self.limit))
+                out.append(preprocess_sketch_host(sketch, self.tokenizer, T, self.limit, shuffle, absolute, self.rng))
                 continue
             s = np.array(np.maximum(np.minimum(sketch, self.limit), -self.limit), dtype=np.float32).reshape(-1, 3)
             if augment and self.hps["augment_stroke_prob"] > 0:
@@ -213,6 +214,10 @@ class DistributedStroke3DataLoader:
             w = max(0.0, ax.max(initial=0.0)) - min(0.0, ax.min(initial=0.0))
             h = max(0.0, ay.max(initial=0.0)) - min(0.0, ay.min(initial=0.0))
             s[:, :2] /= max(w, h, 1)
+            if shuffle:
+                s = shuffle_strokes(s, self.rng)
+            if absolute:
+                s = convert_to_absolute(s)
             s = s[:T]
             conv = np.zeros((T, 5), dtype=np.float32)
             n = len(s)

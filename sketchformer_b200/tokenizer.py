@@ -216,16 +216,59 @@ class GridTokenizer:
         return out
 
 
-def preprocess_sketch_host(sketch, tokenizer, max_seq_len, limit=1000.0):
-    """Host restatement of DistributedStroke3DataLoader.preprocess for one token-mode sketch
-    (distributed_stroke3.py:90-125 + _cap_pad_and_convert_sketch 138-153, utils/sketch.py:31-50)."""
+def shuffle_strokes(sketch, rng=None, perm=None):
+    """`shuffle_stroke=True` (distributed_stroke3.py:107-110 with utils/skt_tools.py:55-96): the sketch as absolute
+    polylines starting from the origin, the polylines in a new order (`perm`, or a permutation drawn from `rng`), back
+    to stroke-3 deltas with the first point (the origin of the new first line) dropped.  float64, like the reference's
+    Python-float accumulation; the points after the last pen lift are lost unless the sketch has no pen lift."""
+    s = np.asarray(sketch).reshape(-1, 3)
+    xy = np.cumsum(s[:, :2].astype(np.float64), axis=0)
+    ends = np.flatnonzero(s[:, 2] == 1)
+    if len(ends) == 0:
+        lines = [np.vstack(([[0.0, 0.0]], xy))]
+    else:
+        starts = np.concatenate(([0], ends[:-1] + 1))
+        lines = [xy[a:b + 1] for a, b in zip(starts, ends)]
+        lines[0] = np.vstack(([[0.0, 0.0]], lines[0]))
+    if perm is None:
+        perm = (rng or np.random.default_rng()).permutation(len(lines))
+    lines = [lines[i] for i in perm]
+    out = np.zeros((sum(len(ln) for ln in lines), 3), np.float64)
+    out[:, :2] = np.concatenate(lines)
+    out[np.cumsum([len(ln) for ln in lines]) - 1, 2] = 1
+    out[1:, :2] -= out[:-1, :2].copy()
+    return out[1:]
+
+
+def convert_to_absolute(sketch):
+    """`use_absolute_strokes=True` (utils/sketch.py:169-175): running sum of the offsets in the array's own dtype,
+    pen column unchanged."""
+    s = np.array(sketch)
+    s[:, :2] = np.cumsum(s[:, :2], axis=0, dtype=s.dtype)
+    return s
+
+
+def normalise_sketch(sketch, limit=1000.0, shuffle_rng=None, absolute=False, shuffle=False):
+    """The part of DistributedStroke3DataLoader.preprocess shared by token and continuous mode
+    (distributed_stroke3.py:93-112): clip to +-limit, float32, divide by max(bbox_w, bbox_h, 1) of the absolute path
+    (origin included, utils/sketch.py:31-50), then the optional stroke shuffle and absolute conversion."""
     s = np.array(np.maximum(np.minimum(sketch, limit), -limit), dtype=np.float32).reshape(-1, 3)
     ax = np.cumsum(s[:, 0].astype(np.float64))
     ay = np.cumsum(s[:, 1].astype(np.float64))
     min_x, max_x = min(0.0, ax.min(initial=0.0)), max(0.0, ax.max(initial=0.0))
     min_y, max_y = min(0.0, ay.min(initial=0.0)), max(0.0, ay.max(initial=0.0))
-    max_dim = max(max_x - min_x, max_y - min_y, 1)
-    s[:, :2] /= max_dim
+    s[:, :2] /= max(max_x - min_x, max_y - min_y, 1)
+    if shuffle:
+        s = shuffle_strokes(s, shuffle_rng)
+    if absolute:
+        s = convert_to_absolute(s)
+    return s
+
+
+def preprocess_sketch_host(sketch, tokenizer, max_seq_len, limit=1000.0, shuffle=False, absolute=False, rng=None):
+    """Host restatement of DistributedStroke3DataLoader.preprocess for one token-mode sketch
+    (distributed_stroke3.py:90-125 + _cap_pad_and_convert_sketch 138-153, utils/sketch.py:31-50)."""
+    s = normalise_sketch(sketch, limit, rng, absolute, shuffle)
     tok = tokenizer.encode(s)
     tok = tok[:max_seq_len]
     out = np.full(max_seq_len, tokenizer.PAD, np.int64)

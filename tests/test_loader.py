@@ -359,3 +359,53 @@ def test_distributed_loader_with_the_grid_tokenizer(tmp_path):
     for i in (0, 7, 24):
         assert np.array_equal(x[i], preprocess_sketch_host(raw[i], ds.tokenizer, 40))
     assert (x[:, 0] == ds.tokenizer.SOS).all()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PKL), reason="/root/reference is not present on this box")
+def test_absolute_and_shuffled_strokes_match_the_reference(tmp_path):
+    """use_absolute_strokes / shuffle_stroke (distributed_stroke3.py:107-112) through the reference's own preprocess,
+    helper by helper and end to end.  np.random.shuffle of the reference is replayed by seeding numpy's global
+    generator and shuffling an index list of the same length (same swaps)."""
+    from oracle.make_loader_golden import BASE_HPS, raw_sketches, reference_loader
+    from oracle.make_tokenizer_golden import reference_tokenizer
+    from sketchformer_b200.tokenizer import convert_to_absolute, normalise_sketch, shuffle_strokes
+    cen = np.load(GOLDEN_LOADER)["centroids"]
+    raw = raw_sketches()[:24]
+    ld = reference_loader(dict(BASE_HPS, max_seq_len=64, use_continuous_data=True), None)
+    import sys
+    sk_mod = type(ld).preprocess.__globals__["utils"].sketch
+    tu = type(ld).preprocess.__globals__["utils"].tu_sketch_tools
+    for s in raw:
+        n = normalise_sketch(s)
+        assert np.array_equal(sk_mod.convert_to_absolute(n.copy()), convert_to_absolute(n))
+        lines = tu.strokes_to_lines(n.astype(np.float64), scale=1.0, start_from_origin=True)
+        perm = np.random.default_rng(len(s)).permutation(len(lines))
+        want = tu.lines_to_strokes([lines[i] for i in perm])
+        got = shuffle_strokes(n, perm=perm)
+        assert got.shape == want.shape and np.allclose(got, want, rtol=0, atol=1e-15)
+    # end to end, absolute coordinates: stroke-5 rows and dictionary tokens
+    _write_dataset(str(tmp_path), n_chunks=1, per_chunk=4)
+    Loader = get_dataloader_by_name("stroke3-distributed")
+    tok = Tokenizer(centroids=cen)
+    for cont in (True, False):
+        hp = dict(BASE_HPS, max_seq_len=64, use_continuous_data=cont, use_absolute_strokes=True)
+        ref = reference_loader(hp, None if cont else reference_tokenizer(cen, 0))
+        want = np.asarray(ref.preprocess([s.copy() for s in raw], augment=False))
+        spec = "max_seq_len=64,use_absolute_strokes=True" + (",use_continuous_data=True" if cont else "")
+        ours = Loader(Loader.parse_hparams(spec), str(tmp_path), seed=0, tokenizer=None if cont else tok)
+        got = ours.preprocess([s.copy() for s in raw])
+        assert got.shape == want.shape
+        assert np.allclose(got, want, rtol=0, atol=1e-6) if cont else np.array_equal(got, want)
+    # end to end, shuffled strokes (continuous rows): same permutation on both sides, sketch by sketch
+    ref = reference_loader(dict(BASE_HPS, max_seq_len=64, use_continuous_data=True, shuffle_stroke=True), None)
+    for k, s in enumerate(raw):
+        np.random.seed(100 + k)
+        want = np.asarray(ref.preprocess([s.copy()], augment=False))[0]
+        n_lines = max(1, int((s[:, 2] == 1).sum()))
+        np.random.seed(100 + k)
+        idx = list(range(n_lines))
+        np.random.shuffle(idx)
+        np.random.seed()
+        n = shuffle_strokes(normalise_sketch(s), perm=idx)[:64]
+        assert np.allclose(n[:, :2], want[:len(n), :2], rtol=0, atol=1e-6) and np.array_equal(n[:, 2], want[:len(n), 3])
+        assert (want[len(n):, 4] == 1).all()
