@@ -409,3 +409,24 @@ def test_absolute_and_shuffled_strokes_match_the_reference(tmp_path):
         n = shuffle_strokes(normalise_sketch(s), perm=idx)[:64]
         assert np.allclose(n[:, :2], want[:len(n), :2], rtol=0, atol=1e-6) and np.array_equal(n[:, 2], want[:len(n), 3])
         assert (want[len(n):, 4] == 1).all()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PKL), reason="/root/reference is not present on this box")
+def test_point_dropout_augmentation_matches_the_reference():
+    """augment_strokes (utils/sketch.py:127-149; train-time augmentation of continuous data): same kept points and
+    merged offsets when both sides draw the same uniform numbers (numpy's legacy generator, one draw per point)."""
+    from types import SimpleNamespace
+    from oracle.make_loader_golden import BASE_HPS, raw_sketches, reference_loader
+    from sketchformer_b200.data import augment_strokes
+    ld = reference_loader(dict(BASE_HPS, max_seq_len=64, use_continuous_data=True), None)
+    ref_aug = type(ld).preprocess.__globals__["utils"].sketch.augment_strokes
+    dropped = 0
+    for k, s in enumerate(raw_sketches()):
+        s = s.astype(np.float32)
+        np.random.seed(k)
+        want = ref_aug(s.copy(), 0.3)
+        np.random.seed()
+        got = augment_strokes(s.copy(), 0.3, SimpleNamespace(random=np.random.RandomState(k).rand))
+        assert got.shape == want.shape and np.array_equal(got, want.astype(np.float32))
+        dropped += len(s) - len(got)
+    assert dropped > 50
