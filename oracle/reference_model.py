@@ -36,7 +36,7 @@ def set_ffn(seq, p, name):
     set_dense(seq.layers[1], p, name + ".w2")
 
 
-def build_reference(ref_model, cfg, p, x):
+def build_reference(ref_model, cfg, p, x, dropout_rate=0.1):
     """An instance of the reference's Transformer with the oracle's weights (BaseModel.__init__ is replaced by
     setting the attributes it would: hps, dataset; then the reference's build_model runs)."""
     Transformer, builders = ref_model
@@ -44,7 +44,7 @@ def build_reference(ref_model, cfg, p, x):
     m.losses_manager = builders.losses.LossManager()                 # models/sketchformer.py:56-57
     m.metrics_manager = builders.keras_metrics.MetricManager()
     m.hps = dict(num_layers=cfg.num_layers, d_model=cfg.d_model, dff=cfg.dff, num_heads=cfg.num_heads,
-                 dropout_rate=0.1, lowerdim=cfg.lowerdim, attn_version=cfg.attn_version,
+                 dropout_rate=dropout_rate, lowerdim=cfg.lowerdim, attn_version=cfg.attn_version,
                  do_classification=cfg.do_classification, class_weight=cfg.class_weight,
                  class_buffer_layers=cfg.class_buffer_layers, class_dropout=cfg.class_dropout,
                  do_reconstruction=cfg.do_reconstruction, recon_weight=cfg.recon_weight,
@@ -99,3 +99,36 @@ def m_masks(ref_model, inp, tar):
     return ref_model[1].utils.create_masks(inp, tar)
 
 
+
+
+def trainable_variables(m):
+    """Every weight tensor of a reference model built by build_reference, as torch leaves that require gradients
+    (what `self.trainable_variables` of a tf.keras.Model would list); also stored on the instance."""
+    out = []
+
+    def walk(obj):
+        if isinstance(obj, tf_shim.Sequential):
+            for lay in obj.layers:
+                walk(lay)
+            return
+        for name, val in list(vars(obj).items()):
+            if name == "pos_encoding":
+                continue
+            if isinstance(val, torch.Tensor):
+                val = val.detach().clone().requires_grad_(True)
+                setattr(obj, name, val)
+                out.append(val)
+            elif isinstance(val, tf_shim.Layer):
+                walk(val)
+            elif isinstance(val, list) and val and all(isinstance(v, tf_shim.Layer) for v in val):
+                for v in val:
+                    walk(v)
+
+    for name, val in list(vars(m).items()):
+        if isinstance(val, tf_shim.Layer):
+            walk(val)
+        elif isinstance(val, list) and val and all(isinstance(v, tf_shim.Layer) for v in val):
+            for v in val:
+                walk(v)
+    m.trainable_variables = out
+    return out

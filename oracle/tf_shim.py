@@ -3,9 +3,9 @@
 
 TensorFlow cannot be installed in this image, so the reference's model cannot run as shipped.  Its *layer code*
 (`builders/utils.py`, `builders/layers/transformer.py`, `builders/schedulers.py`) however only calls a few dozen TF
-primitives with textbook semantics.  `install()` puts modules named `tensorflow`, `tensorflow.keras` and
-`tensorflow.keras.backend` into `sys.modules` that implement exactly those primitives on torch tensors, and
-`load_reference_builders()` then EXECUTES the reference's own files from /root/reference against them.  What this
+primitives with textbook semantics.  `build_modules()` makes modules named `tensorflow`, `tensorflow.keras` and
+`tensorflow.keras.backend` that implement exactly those primitives on torch tensors; `load_reference_builders()` /
+`load_reference_model()` put them into `sys.modules` (restored afterwards) and EXECUTE the reference's own files from /root/reference against them.  What this
 pins is the wiring of the reference (argument order v/k/q, which mask goes where and with which polarity, residual /
 LayerNorm order, sqrt(d_model) scaling, the transposes of split_heads and DenseExpander, the softmax axes of the
 pooling layer, the schedule's formula); what it cannot pin is TensorFlow's own kernels, whose semantics are restated
@@ -210,9 +210,46 @@ class _SparseCategoricalAccuracy(_Mean):
         self.total += float(hit.sum()); self.count += hit.numel()
 
 
+class GradientTape:
+    """tf.GradientTape as used by model_trainer (models/sketchformer.py:331-347): gradients of a scalar with respect
+    to a list of variables - here torch leaf tensors with requires_grad."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def gradient(self, target, sources):
+        return torch.autograd.grad(target, list(sources), allow_unused=True)
+
+
 class _RecordedOptimizer:
+    """tf.keras.optimizers.Adam: records the constructor arguments build_model() passes, and implements
+    apply_gradients with the update rule TensorFlow documents for Adam (training_ops ApplyAdam):
+        t = iterations + 1;  lr_t = lr(iterations) * sqrt(1 - beta_2^t) / (1 - beta_1^t)
+        m = beta_1 m + (1 - beta_1) g;  v = beta_2 v + (1 - beta_2) g^2;  var -= lr_t * m / (sqrt(v) + epsilon)
+    (the schedule is evaluated at `iterations` BEFORE the increment).  This restates TensorFlow, not the reference."""
+
     def __init__(self, *args, **kwargs):
         self.args, self.kwargs = args, kwargs
+        self.iterations, self.slots = 0, {}
+
+    def apply_gradients(self, grads_and_vars):
+        lr = self.args[0]
+        b1, b2, eps = self.kwargs["beta_1"], self.kwargs["beta_2"], self.kwargs["epsilon"]
+        lr = float(lr(torch.tensor(float(self.iterations), dtype=torch.float32))) if callable(lr) else float(lr)
+        t = self.iterations + 1
+        lr_t = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+        with torch.no_grad():
+            for g, var in grads_and_vars:
+                if g is None:
+                    continue
+                m, v = self.slots.setdefault(id(var), (torch.zeros_like(var), torch.zeros_like(var)))
+                m.mul_(b1).add_(g, alpha=1 - b1)
+                v.mul_(b2).addcmul_(g, g, value=1 - b2)
+                var.sub_(lr_t * m / (v.sqrt() + eps))
+        self.iterations = t
 
 
 # ---- tf.keras -------------------------------------------------------------------------------------------------------
@@ -341,7 +378,8 @@ def build_modules():
                  cast=cast, shape=shape, reshape=reshape, transpose=transpose, matmul=matmul, expand_dims=expand_dims,
                  ones=ones, maximum=maximum, squeeze=squeeze, reduce_mean=reduce_mean, argmax=argmax,
                  constant=constant, custom_gradient=custom_gradient, math=math, linalg=linalg, nn=nn, losses=losses,
-                 zeros_like=zeros_like, concat=concat, reduce_sum=reduce_sum, function=function, TensorSpec=TensorSpec)
+                 zeros_like=zeros_like, concat=concat, reduce_sum=reduce_sum, function=function, TensorSpec=TensorSpec,
+                 GradientTape=GradientTape)
     return {"tensorflow": tf, "tensorflow.keras": keras, "tensorflow.keras.backend": kback,
             "tensorflow.keras.layers": layers}
 

@@ -99,3 +99,35 @@ def test_continuous_greedy_decode_matches_the_reference_model(ref_model):
     assert got["recon"].shape == want["recon"].shape
     assert got["recon"][:, 0].tolist() == [[0., 0., 1., 0., 0.]] * 3
     assert torch.allclose(got["recon"].to(F64), want["recon"], atol=1e-5)       # float32-rounded embedding on one side
+
+
+def test_train_steps_match_the_reference_trainer(ref_model):
+    """model_trainer / train_on_batch (models/sketchformer.py:313-359) executed from the reference for three steps
+    with dropout 0: `inp = tar = data`, the slicing of the target, both weighted losses and their sum under the
+    gradient tape, apply_gradients over every variable, the running-mean quick metrics.  Gradients are torch
+    autograd on both sides and the Adam rule is restated from TensorFlow on both sides (tf_shim.py says so); what is
+    pinned is the trainer's wiring and the metric definitions (accuracy over ALL positions, pads included)."""
+    from oracle.reference_model import trainable_variables
+    cfg = O.OracleConfig(**dict(TINY, class_weight=0.7, recon_weight=1.3))
+    p = _randomise(O.init_params(cfg, 19, F64), 20)
+    x, y = _batch(cfg, B=4, seed=8)
+    m = build_reference(ref_model, cfg, {k: v.clone() for k, v in p.items()}, x, dropout_rate=0.0)
+    trainable_variables(m)
+    assert sum(v.numel() for v in m.trainable_variables) == O.count_params(p)
+    opt = O.AdamTF(p, cfg.d_model)
+    run = O.RunningMetrics()
+    for step in range(3):
+        xb, yb = _batch(cfg, B=4, seed=8 + step)
+        got = m.train_on_batch((xb, yb))
+        losses, _ = O.train_step(p, opt, xb, yb, cfg, dtype=F64)
+        run.update(losses)
+        want = run.result()
+        assert set(got) == set(want) == {"recon_loss", "recon_acc", "class_loss", "class_acc", "total_loss"}
+        for k in want:
+            assert float(got[k]) == pytest.approx(float(want[k]), rel=1e-6, abs=1e-9), (step, k)
+    # after three optimizer steps (lr(0) = 0, so two effective ones) the weights agree
+    out_ref = m.call(x, x[:, :-1], False, *m_masks(ref_model, x, x[:, :-1]))
+    out_orc = O.call(p, x, x[:, :-1], cfg, False, O.create_masks(x, x[:, :-1], F64), dtype=F64)
+    assert torch.allclose(out_ref["recon"], out_orc["recon"], atol=1e-9)
+    assert torch.allclose(out_ref["class"], out_orc["class"], atol=1e-10)
+    assert m.optimizer.iterations == 3
