@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 from oracle import sketchformer_oracle as O                                  # noqa: E402
 from oracle import tf_shim                                                    # noqa: E402
 from oracle.make_golden import TINY, TINY_LOWERDIM0, TINY_NOTBLIND, TINY_V2   # noqa: E402
-from oracle.reference_model import build_reference, m_masks, randomise        # noqa: E402
+from oracle.reference_model import build_reference, m_masks, randomise, trainable_variables   # noqa: E402
 from sketchformer_b200 import synth                                           # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "reference_model_tiny.npz")
@@ -35,6 +35,14 @@ def inputs(cfg):
         x, y = synth.continuous_batch(BATCH, cfg.max_seq_len, cfg.n_classes, BATCH_SEED)
         return torch.from_numpy(x).to(F64), torch.from_numpy(y)
     x, y = synth.token_batch(BATCH, cfg.max_seq_len, cfg.n_classes, BATCH_SEED, vocab=cfg.vocab_size)
+    return torch.from_numpy(x), torch.from_numpy(y)
+
+
+TRAIN_KW = dict(TINY, class_weight=0.7, recon_weight=1.3)
+
+
+def train_inputs(cfg, step):
+    x, y = synth.token_batch(BATCH, cfg.max_seq_len, cfg.n_classes, BATCH_SEED + 100 + step, vocab=cfg.vocab_size)
     return torch.from_numpy(x), torch.from_numpy(y)
 
 
@@ -64,6 +72,19 @@ def main():
             data[f"{name}/greedy"] = pr["recon"].numpy().astype(np.int64)
             if "class" in pr and pr["class"] is not None:
                 data[f"{name}/pred_class"] = pr["class"].numpy().astype(np.int64)
+    # three steps of the reference's trainer (models/sketchformer.py:313-359) with dropout 0 and unequal loss weights
+    cfg = O.OracleConfig(**TRAIN_KW)
+    p = params(cfg)
+    x, y = inputs(cfg)
+    m = build_reference(ref_model, cfg, {k: v.clone() for k, v in p.items()}, x, dropout_rate=0.0)
+    trainable_variables(m)
+    for step in range(3):
+        xb, yb = train_inputs(cfg, step)
+        qm = m.train_on_batch((xb, yb))
+        for k, v in qm.items():
+            data[f"train/step{step}/{k}"] = np.float64(v)
+    out = m.call(x, x[:, :-1], False, *m_masks(ref_model, x, x[:, :-1]))
+    data["train/recon_after"] = out["recon"].detach().numpy()
     np.savez_compressed(OUT, **data)
     print(OUT, os.path.getsize(OUT), "bytes;", len(data), "arrays")
 

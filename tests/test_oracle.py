@@ -307,3 +307,24 @@ def test_oracle_matches_vectors_made_by_the_reference_model_code(golden_dir):
             assert pr["recon"].numpy().tolist() == g[f"{name}/greedy"].tolist(), name
             if f"{name}/pred_class" in g:
                 assert pr["class"].numpy().tolist() == g[f"{name}/pred_class"].tolist()
+
+
+def test_train_steps_match_vectors_made_by_the_reference_trainer(golden_dir):
+    """Three steps of the reference's model_trainer / train_on_batch (frozen by oracle/make_reference_golden.py from
+    the reference's code on oracle/tf_shim.py): running-mean quick metrics after every step and the logits of the
+    updated model.  Needs no /root/reference."""
+    from oracle.make_reference_golden import TRAIN_KW, inputs, params, train_inputs
+    g = np.load(os.path.join(golden_dir, "reference_model_tiny.npz"))
+    cfg = O.OracleConfig(**TRAIN_KW)
+    p = params(cfg)
+    opt = O.AdamTF(p, cfg.d_model)
+    run = O.RunningMetrics()
+    for step in range(3):
+        xb, yb = train_inputs(cfg, step)
+        losses, _ = O.train_step(p, opt, xb, yb, cfg, dtype=torch.float64)
+        run.update(losses)
+        for k, v in run.result().items():
+            assert float(v) == pytest.approx(float(g[f"train/step{step}/{k}"]), rel=1e-6, abs=1e-9), (step, k)
+    x, _ = inputs(cfg)
+    out = O.call(p, x, x[:, :-1], cfg, False, O.create_masks(x, x[:, :-1], torch.float64), dtype=torch.float64)
+    assert np.allclose(out["recon"].detach().numpy(), g["train/recon_after"], atol=1e-9)
