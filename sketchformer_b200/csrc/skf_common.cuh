@@ -94,12 +94,5 @@ __device__ __forceinline__ float skf_drop_apply(float x, uint32_t key, uint32_t 
 int gemm_simt(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,
               int64_t sb_n, float* Y, int64_t ldy, int M, int N, int K,
               const skf_gemm_epilogue* epi, cudaStream_t st);
-int gemm_tc(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,
-            int64_t sb_n, float* Y, int64_t ldy, int M, int N, int K,
-            const skf_gemm_epilogue* epi, cudaStream_t st);
-// returns 1 when the tcgen05 path can take this problem (alignment / stride constraints)
-int gemm_tc_supported(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k,
-                      int64_t sb_n, const float* Y, int64_t ldy, int M, int N, int K,
-                      const skf_gemm_epilogue* epi);
 
 }  // namespace skf

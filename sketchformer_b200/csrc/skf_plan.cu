@@ -20,7 +20,8 @@ int attn_fwd_simt(const float*, int64_t, const float*, int64_t, const float*, in
 int attn_bwd_simt(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
                   const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
                   const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
-extern int g_tma_tf32_type;
+// 1 = tensor maps of the single-pass TF32 GEMM use CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 (the TMA unit rounds on load)
+int g_tma_tf32_type = 1;
 int gemm_tc2_supported(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const float*, int64_t, int, int,
                        int, const skf_gemm_epilogue*);
 int gemm_tc2(const float*, int64_t, int64_t, const float*, int64_t, int64_t, float*, int64_t, int, int, int,
@@ -37,12 +38,6 @@ extern int g_t3_bn128_max;  // pair GEMM: 128-column cluster tiles for N up to t
 int g_gemm_tiny_simt = 0;   // 1: products with M <= 128 and few column tiles run on the small-tile SIMT kernel (no gain measured: 9.04 vs 9.01 ms)
 extern int g_gemm_wsplit;   // 1: forward / dgrad products read pre-split bf16 images of the weights (skf_gemm_tc3.cu)
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
-int attn_tc_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
-int attn_fwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
-                const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
-int attn_bwd_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
-                const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
-                const uint8_t*, int, int, int, int, int, int, cudaStream_t);
 int attn2_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
 int attn2_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
               const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
@@ -1409,10 +1404,15 @@ int skf_decode_begin(skf_plan* P, const float* embedding, const int32_t* expecte
   if (!P->c.do_reconstruction) {        // classification of a given embedding only (sketchformer.py:307-310)
     SKF_REQUIRE(P->c.do_classification, SKF_ERR_UNSUPPORTED, "decode: the model has neither decoder nor classifier");
     cudaStream_t st = as_stream(stream);
+    int64_t l0 = skf::g_launch_count;
+    SKF_TRY(refresh_compute_weights(P, st));    // like every other entry point: host-side weight-image flags are stale
+                                                // after a CUDA-graph replay or a parameter load through torch
     if (embedding && embedding != P->wsf("embedding"))
       SKF_CUDA(cudaMemcpyAsync(P->wsf("embedding"), embedding, (size_t)P->c.B * emb_dim(P->c) * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
-    return classify_embedding(P, st);
+    SKF_TRY(classify_embedding(P, st));
+    P->launches += skf::g_launch_count - l0;
+    return SKF_OK;
   }
   SKF_REQUIRE(P->c.blind_decoder_mask || expected_len != nullptr, SKF_ERR_UNSUPPORTED,
               "decode: blind_decoder_mask=False needs expected_len (the i+1 cross mask of the reference changes "
@@ -1446,8 +1446,6 @@ int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
               "gemm: the fused column sum exists on the pair backend (5) only");
   if (backend == 0 || backend == 2)      // persistent tcgen05 kernel: single-pass TF32 / 3xTF32
     return gemm_tc2(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, backend == 2, as_stream(stream));
-  if (backend == 3)                      // first-generation (one tile per CTA) tcgen05 kernel, kept for A/B runs
-    return gemm_tc(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
   if (backend == 5) {                    // 3xTF32 on CTA pairs (cta_group::2), 256 x 256 cluster tiles
     SKF_REQUIRE(gemm_tc2_supported(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi), SKF_ERR_BAD_ALIGN,
                 "gemm (pair): operand strides/alignment not TMA-compatible");
@@ -1460,13 +1458,10 @@ int skf_attn_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
                  int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh,
                  int mask_mode, int round_tf32, int backend, void* stream) {
   // backend: 0 = tcgen05 flash kernels, single-pass TF32; 2 = the same with the 3xTF32 split (fp32-grade);
-  //          1 = SIMT fp32; 3 / 4 = first-generation one-shot tcgen05 kernel (TF32 / 3xTF32), kept for A/B runs
+  //          1 = SIMT fp32
   if (backend == 0 || backend == 2)
     return attn2_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, backend == 2,
                      as_stream(stream));
-  if (backend == 3 || backend == 4)
-    return attn_fwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, backend == 4,
-                       as_stream(stream));
   return attn_fwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, round_tf32,
                        as_stream(stream));
 }
@@ -1478,9 +1473,6 @@ int skf_attn_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
   if (backend == 0 || backend == 2)
     return attn2_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B,
                      H, Tq, Tk, dh, mask_mode, backend == 2, as_stream(stream));
-  if (backend == 3)
-    return attn_bwd_tc(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B,
-                       H, Tq, Tk, dh, mask_mode, as_stream(stream));
   return attn_bwd_simt(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad,
                        B, H, Tq, Tk, dh, mask_mode, round_tf32, as_stream(stream));
 }

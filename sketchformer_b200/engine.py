@@ -74,6 +74,7 @@ class Engine:
                                        ptr(self.adam_v), ptr(self.workspace), wsb, C.byref(self._plan)),
               "skf_plan_create")
         check(self.lib.skf_plan_init(self._plan, self._stream()), "skf_plan_init")
+        self.eager_train_steps = 0      # train steps this engine has run outside a CUDA graph (capture needs >= 1)
 
     def __del__(self):
         try:
@@ -171,6 +172,8 @@ class Engine:
         assert labels.is_cuda and labels.dtype == torch.int64 and labels.numel() == self.cfg.B
         check(self.lib.skf_train_step(self._plan, C.c_void_p(tokens.data_ptr()), C.c_void_p(labels.data_ptr()),
                                       int(apply_adam), self._stream()), "skf_train_step")
+        if not torch.cuda.is_current_stream_capturing():
+            self.eager_train_steps += 1
 
     # ---- CUDA-graph replay of the whole step ------------------------------------------------------
     def capture_train_step(self, apply_adam=True):
@@ -256,6 +259,16 @@ class Engine:
 
     def step_count(self):
         return int(self.tensor("step", dtype=torch.int64)[0].item())
+
+    def merge_metrics_into(self, main):
+        """Fold this plan's running sums into `main`'s and clear them (device-side, no synchronisation): the
+        reference has ONE MetricManager whatever the batch size of a step (builders/keras_metrics.py:13-42)."""
+        if main is self:
+            return
+        mine, theirs = self.tensor("stats_run", dtype=torch.float64), main.tensor("stats_run", dtype=torch.float64)
+        theirs[:8] += mine[:8]
+        theirs[8:13] = mine[8:13]
+        mine.zero_()
 
     def reset_metrics(self):
         """MetricManager.reset (builders/keras_metrics.py): zero the running sums."""

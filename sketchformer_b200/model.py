@@ -8,6 +8,7 @@ this class only stages host batches into HBM and reads results back.  There is n
 a B200 and the built library the constructor raises.
 """
 import os
+import re
 
 import numpy as np
 import torch
@@ -18,10 +19,14 @@ from .hparams import HParams, combine_hparams_into_one
 from .init import init_params
 
 
+_ROLLING = re.compile(r"^ckpt-(\d+)\.pt$")
+
+
 class Transformer:
     name = "sketch-transformer-tf2"                                   # models/sketchformer.py:18
     quick_metrics = ["recon_loss", "recon_acc", "class_loss", "class_acc", "total_loss"]
     slow_metrics = ["sketch-reconstruction", "val-clas-acc", "tsne", "tsne-predicted"]
+    MAX_EXTRA_PLANS = 4      # plans (workspaces) kept for batch sizes other than hps['batch_size']
 
     # ---- hparams (names, types and defaults are the reference's) ---------------------------
     @classmethod
@@ -70,7 +75,9 @@ class Transformer:
         self.continuous = bool(dhps["use_continuous_data"])
         self.vocab_size = None if self.continuous else dataset.tokenizer.VOCAB_SIZE   # sketchformer.py:59
         self.seq_len = dhps["max_seq_len"]                                            # sketchformer.py:60
-        self.batches_per_epoch = max(1, getattr(dataset, "n_samples", 0) // self.hps["batch_size"])
+        # core/models.py:60: n_samples // batch_size.  Under data parallelism a step consumes world_size batches
+        # (one per rank), so an epoch is world_size times fewer steps and the checkpoint cadence follows it.
+        self.batches_per_epoch = max(1, getattr(dataset, "n_samples", 0) // (self.hps["batch_size"] * max(1, world_size)))
         if out_dir is not None:                                                       # core/models.py:68-81
             self.out_dir = os.path.join(out_dir, self.identifier)
             self.plots_out_dir = os.path.join(self.out_dir, "plots")
@@ -137,8 +144,15 @@ class Transformer:
     def _engine(self, B, training=False):
         """One plan per batch size; all plans share the parameter arena of the training plan."""
         if B in self._engines:
-            return self._engines[B]
+            eng = self._engines.pop(B)
+            self._engines[B] = eng            # most recently used last
+            return eng
         first = not self._engines
+        # batch_iterator cuts the running batch short at every end of split and the cut size varies with the chunk
+        # order: keep the training plan plus the few most recently used other sizes, not one workspace per size
+        others = [b for b, e in self._engines.items() if e is not self._train_engine]
+        while len(others) >= self.MAX_EXTRA_PLANS:
+            del self._engines[others.pop(0)]
         eng = Engine(self._cfg(B), device=self._device, training=training or first,
                      share_from=None if first else self._train_engine)
         if first:
@@ -197,7 +211,9 @@ class Transformer:
         eng = self._engine(B, training=True)
         dt = torch.int64 if not self.continuous else torch.float32
         solo = self._world == 1           # data parallel: gradients are all-reduced before the optimizer
-        if self._use_graph and eng is self._train_engine and self.current_step >= 2:
+        if self._use_graph and eng is self._train_engine and eng.eager_train_steps >= 1:
+            # (one eager step first — also right after restore_checkpoint_if_exists(), when current_step is already
+            # large: function attributes and tensor-map encoders are initialised lazily, engine.py capture_train_step)
             # steady state: pinned host -> static device buffers -> one cudaGraphLaunch for the whole step
             eng.capture_train_step(apply_adam=solo)
             self._h2d_into("x", data, dt, eng.graph_tokens)
@@ -211,10 +227,12 @@ class Transformer:
             eng.train_step(x, y, apply_adam=solo)
             if eng is not self._train_engine and solo:
                 self._train_engine.set_step(eng.step_count())
+        # one running mean over all steps, whatever plan ran them
+        eng.merge_metrics_into(self._train_engine)
         if not solo:
             self._allreduce_and_step(eng)
         self.current_step += 1
-        return self._quick_metrics(eng) if sync_metrics else None
+        return self._quick_metrics(self._train_engine) if sync_metrics else None
 
     def _quick_metrics(self, eng):
         """Only the metrics build_model() registers (models/sketchformer.py:85-107): no recon_acc with
@@ -361,9 +379,11 @@ class Transformer:
         every = max(1, int(self.hps["save_every"] * self.batches_per_epoch))
         if (cur + 1) % safety == 0:
             self.save_checkpoint(os.path.join(self.wgt_out_dir, "ckpt-{}.pt".format(cur)))
-            kept = sorted((f for f in os.listdir(self.wgt_out_dir) if f.startswith("ckpt-")),
-                          key=lambda f: int(f[5:-3]))
-            for f in kept[:-2]:
+            # rotate only the files this method wrote: the reference's CheckpointManager keeps `ckpt-N.index` /
+            # `ckpt-N.data-*` tensor bundles in the same directory (core/models.py:326-331) and they are not ours
+            mine = [(int(m.group(1)), f) for f in os.listdir(self.wgt_out_dir)
+                    for m in [_ROLLING.match(f)] if m]
+            for _, f in sorted(mine)[:-2]:
                 os.remove(os.path.join(self.wgt_out_dir, f))
         if (cur + 1) % every == 0:
             self.save_checkpoint(os.path.join(self.wgt_out_dir, "step{}.pt".format(cur)))
@@ -389,7 +409,8 @@ class Transformer:
             self.load_tf_checkpoint(checkpoint)
             print("[Checkpoint] Restored, step #{}".format(self.current_step))
             return True
-        self.load_state_dict(torch.load(checkpoint, map_location="cpu", weights_only=False))
+        # tensors, ints and dicts / tuples of primitives only: the safe loader (no arbitrary unpickling)
+        self.load_state_dict(torch.load(checkpoint, map_location="cpu", weights_only=True))
         print("[Checkpoint] Restored, step #{}".format(self.current_step))
         return True
 
@@ -428,12 +449,17 @@ class Transformer:
     def state_dict(self):
         e = self._train_engine
         return {"params": e.params.cpu(), "adam_m": e.adam_m.cpu(), "adam_v": e.adam_v.cpu(),
-                "step": e.step_count(), "current_step": self.current_step, "table": dict(e.table),
-                "metrics": e.tensor("stats_run", dtype=torch.float64).cpu().clone(), "hps": dict(self.hps)}
+                "step": e.step_count(), "current_step": self.current_step,
+                "table": {k: list(v) for k, v in e.table.items()},
+                "metrics": e.tensor("stats_run", dtype=torch.float64).cpu().clone(),
+                "hps": {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in self.hps.items()}}
 
     def load_state_dict(self, sd):
         e = self._train_engine
-        assert sd["table"] == e.table, "checkpoint was written for a different model layout"
+        table = {k: tuple(int(i) for i in v) for k, v in sd["table"].items()}
+        if table != e.table:
+            raise ValueError("checkpoint was written for a different model layout (parameter table mismatch: "
+                             f"{len(table)} tensors in the file, {len(e.table)} in this model)")
         e.params.copy_(sd["params"]); e.adam_m.copy_(sd["adam_m"]); e.adam_v.copy_(sd["adam_v"])
         e.set_step(sd["step"])
         if "metrics" in sd:

@@ -40,8 +40,15 @@ def _assert_same_tokens(p, ocfg, emb, got, want, expected_len=None):
         assert gap <= 1e-3 * float(zb.max() - zb.min()), f"row {b} step {j}: {got[b, j]} vs {want[b, j]}, gap {gap}"
 
 
+# cfg2 dimensions (d_model 256, 8 heads of 32, dff 1024, max_seq_len 200; 2 layers and batch 2 so that the oracle's
+# O(T^2) re-evaluation of the decoder on the growing prefix, models/sketchformer.py:274-301, finishes in seconds)
+CFG2_L2 = dict(num_layers=2, d_model=256, dff=1024, num_heads=8, lowerdim=256, max_seq_len=200, vocab_size=1004,
+               n_classes=345)
+
+
 @pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
-@pytest.mark.parametrize("name,cfg_kw,B", [("tiny", TINY, 4), ("cfg1", CFG1, 8)], ids=["tiny", "cfg1"])
+@pytest.mark.parametrize("name,cfg_kw,B", [("tiny", TINY, 4), ("cfg1", CFG1, 8), ("cfg2-l2", CFG2_L2, 2)],
+                         ids=["tiny", "cfg1", "cfg2-l2"])
 def test_greedy_decode_tokens(name, cfg_kw, B, backend):
     ocfg, eng = build(cfg_kw, B, backend)
     p = O.init_params(ocfg, 3, torch.float64)

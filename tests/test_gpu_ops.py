@@ -340,14 +340,6 @@ def test_attention_tcgen05(lib, B, H, Tq, Tk, dh, mode):
     assert max(errs) < TOL_TF32, errs
 
 
-@pytest.mark.parametrize("B,H,Tq,Tk,dh,mode", TC_ATTN)
-def test_attention_tcgen05_legacy(lib, B, H, Tq, Tk, dh, mode):
-    # first-generation one-shot kernels (kept for A/B runs): forward 3xTF32, backward single-pass TF32
-    e_o, e_q, e_k, e_v = _attn_case(lib, B, H, Tq, Tk, dh, mode, 200 + Tq, fwd_backend=4, bwd_backend=3)
-    assert e_o < TOL_EXACT, e_o
-    assert max(e_q, e_k, e_v) < TOL_TF32, (e_q, e_k, e_v)
-
-
 MAJORS = [("fwd", False, True), ("dgrad", False, False), ("wgrad", True, True), ("tn", True, False)]
 
 
@@ -355,7 +347,7 @@ def _gemm_case(M, N, K, a_mn, b_mn, backend, seed, **epi):
     g = torch.Generator().manual_seed(seed)
     A = torch.randn(M, K, generator=g)
     Bm = torch.randn(K, N, generator=g)
-    if backend in (0, 3):
+    if backend == 0:
         A, Bm = to_tf32(A), to_tf32(Bm)      # exactly TF32-representable operands: only accumulation order differs
     Ast = dev(A.T) if a_mn else dev(A)        # MN-major: stored [K, M]
     Bst = dev(Bm) if b_mn else dev(Bm.T)      # K-major: stored [N, K]
@@ -396,7 +388,7 @@ TC_SHAPES = [(128, 256, 32), (128, 64, 256), (256, 128, 64), (200, 100, 96), (16
              (256, 256, 4000), (3000, 1024, 256)]
 
 
-@pytest.mark.parametrize("backend", [0, 3], ids=["persistent", "legacy"])
+@pytest.mark.parametrize("backend", [0], ids=["persistent"])
 @pytest.mark.parametrize("name,a_mn,b_mn", MAJORS)
 @pytest.mark.parametrize("M,N,K", TC_SHAPES)
 def test_gemm_tcgen05(lib, name, a_mn, b_mn, M, N, K, backend):

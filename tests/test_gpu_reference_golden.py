@@ -1,10 +1,7 @@
 """The CUDA engine against vectors made by the REFERENCE'S OWN model code (tests/golden/reference_model_tiny.npz,
 written by oracle/make_reference_golden.py from /root/reference on oracle/tf_shim.py): embedding, class prediction,
 both losses and the greedy token sequences for the graph-changing hparam variants.  The other GPU tests compare the
-engine with the oracle and the CPU tests compare the oracle with these vectors; this file closes the chain directly.
-
-Written after the round's GPU budget was spent, so it has not run on a B200 yet: it is skipped unless
-SKF_RUN_UNVERIFIED_GPU_TESTS=1 so that it cannot turn the suite red unseen.  Enable it once it has been seen green."""
+engine with the oracle and the CPU tests compare the oracle with these vectors; this file closes the chain directly."""
 import os
 
 import numpy as np
@@ -14,9 +11,7 @@ import torch
 from oracle import sketchformer_oracle as O
 from oracle.make_reference_golden import VARIANTS, inputs, params
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SKF_RUN_UNVERIFIED_GPU_TESTS") != "1",
-                                 reason="not yet verified on a GPU (set SKF_RUN_UNVERIFIED_GPU_TESTS=1)")]
+pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_model_tiny.npz")
 
 

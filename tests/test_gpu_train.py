@@ -205,24 +205,41 @@ def test_encode_matches_oracle_predict_class():
     assert torch.equal(eng.tensor("cls.argmax", dtype=torch.int32).cpu()[:8], want["class"])
 
 
-def test_ablation_flags():
-    """do_classification / do_reconstruction / blind_decoder_mask variants of build_model()."""
-    for flags in (dict(do_classification=False), dict(do_reconstruction=False), dict(blind_decoder_mask=False),
-                  dict(class_weight=0.5, recon_weight=2.0)):
-        ocfg, eng = build(TINY, 4, 1, **flags)
-        x, y = synth.token_batch(4, ocfg.max_seq_len, ocfg.n_classes, 5, vocab=ocfg.vocab_size)
-        p = O.init_params(ocfg, 0, torch.float64)
-        eng.load_params(p)
-        opt = O.AdamTF(p, ocfg.d_model)
-        losses, grads = O.train_step(p, opt, torch.from_numpy(x), torch.from_numpy(y), ocfg, dtype=torch.float64)
-        eng.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), True)
-        m = eng.last_step_metrics()
-        assert abs(m["total_loss"] - losses["total_loss"]) <= 2e-4 * abs(losses["total_loss"]), (flags, m, losses)
-        got = eng.export_grads(grads)
-        G = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
-        for k, ref in grads.items():
-            num = float((got[k].double() - ref.double()).norm())
-            assert num / max(float(ref.norm()), 1e-4 * G) < 2e-4, (flags, k)
+ABLATIONS = [dict(do_classification=False), dict(do_reconstruction=False), dict(blind_decoder_mask=False),
+             dict(class_weight=0.5, recon_weight=2.0)]
+# TINY runs the SIMT attention (head dim 16); the small cfg2-shaped case (head dim 32, T=200) runs the tcgen05
+# attention and pair-GEMM kernels through the same flags
+CFG2_L1 = dict(num_layers=1, d_model=256, dff=1024, num_heads=8, lowerdim=256, max_seq_len=200, vocab_size=1004,
+               n_classes=345)
+
+
+@pytest.mark.parametrize("name,cfg_kw,B,backend", [("tiny", TINY, 4, 1), ("tiny", TINY, 4, 0), ("cfg2-l1", CFG2_L1, 3, 0)],
+                         ids=["tiny-simt", "tiny-tcgen05", "cfg2l1-tcgen05"])
+@pytest.mark.parametrize("flags", ABLATIONS, ids=["no-class", "no-recon", "not-blind", "weights"])
+def test_ablation_flags(flags, name, cfg_kw, B, backend):
+    """do_classification / do_reconstruction / blind_decoder_mask / loss-weight variants of build_model()
+    (models/sketchformer.py:63-129) on both backends."""
+    tol = 2e-4 if backend == 1 else 1e-3
+    ocfg, eng = build(cfg_kw, B, backend, **flags)
+    x, y = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 5, vocab=ocfg.vocab_size)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    p = O.init_params(ocfg, 0, torch.float64)
+    eng.load_params(p)
+    opt = O.AdamTF(p, ocfg.d_model)
+    eng.train_step(xt.cuda(), yt.cuda(), True)
+    torch.cuda.synchronize()
+    with O.relu_pattern(engine_relu_pattern(eng, ocfg, B)):
+        losses, grads = O.train_step(p, opt, xt, yt, ocfg, dtype=torch.float64)
+    m = eng.last_step_metrics()
+    assert abs(m["total_loss"] - losses["total_loss"]) <= tol * abs(losses["total_loss"]), (flags, m, losses)
+    got = eng.export_grads(grads)
+    G = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
+    bad = []
+    for k, ref in grads.items():
+        num = float((got[k].double() - ref.double()).norm())
+        if not num / max(float(ref.double().norm()), 1e-4 * G) < tol:
+            bad.append((k, num / max(float(ref.double().norm()), 1e-4 * G)))
+    assert not bad, f"{flags}: gradients off: {sorted(bad, key=lambda t: -t[1])[:8]}"
 
 
 CONT_CASES = [("tiny", TINY, 4), ("cfg4-b4", CFG2, 4)]
@@ -411,8 +428,8 @@ def test_no_bottleneck_matches_oracle(backend):
 
 def test_cfg5_dimensions_match_oracle():
     """BASELINE.json configs[4] dimensions (d_model=512, dff=2048, 8 heads of 64, max_seq_len=512) at 2 layers and
-    batch 2 so that the fp64 oracle finishes in seconds: head dim 64 and T > 256 take the SIMT attention kernels,
-    the GEMMs the tcgen05 pair kernel with 512 / 2048-wide tiles."""
+    batch 2 so that the fp64 oracle finishes in seconds: head dim 64 and T = 512 run the tcgen05 attention kernels
+    (one CTA per SM at this head dim), the GEMMs the tcgen05 pair kernel with 512 / 2048-wide tiles."""
     kw = dict(num_layers=2, d_model=512, dff=2048, num_heads=8, lowerdim=256, max_seq_len=512, vocab_size=1004,
               n_classes=345)
     B = 2

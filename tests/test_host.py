@@ -173,3 +173,21 @@ def test_base_hparams_paths_and_checkpoint_cadence_match_the_reference(tmp_path)
         our_fixed = [os.path.basename(p)[:-3] for p in our_saves if os.path.basename(p).startswith("step")]
         assert our_safety == ref_safety and ref_safety, (safety_save, save_every, bpe)
         assert our_fixed == [os.path.basename(p) for p in ref_fixed] and ref_fixed      # 'step<N>' file stems
+
+
+def test_rolling_checkpoints_leave_tensorflow_bundles_alone(tmp_path):
+    """weights/ may also hold the reference's own `ckpt-N.index` / `ckpt-N.data-*` tensor bundles (CheckpointManager,
+    core/models.py:326-331; the supported flow is restore('latest') from one and keep training): the rotation of our
+    rolling `ckpt-N.pt` files must neither choke on those names nor delete them."""
+    from sketchformer_b200.model import Transformer
+    for f in ("ckpt-5.index", "ckpt-5.data-00000-of-00001", "checkpoint", "ckpt-old.pt.bak"):
+        (tmp_path / f).write_bytes(b"tf")
+    ours = object.__new__(Transformer)
+    ours.hps, ours.batches_per_epoch, ours.wgt_out_dir = dict(safety_save=.5, save_every=100.), 4, str(tmp_path)
+    ours.save_checkpoint = lambda path: open(path, "wb").close()
+    for step in range(1, 13):
+        ours.current_step = step
+        ours.save_checkpoint_if_its_time()
+    left = sorted(os.listdir(tmp_path))
+    assert [f for f in left if f.endswith(".pt")] == ["ckpt-11.pt", "ckpt-9.pt"]
+    assert {"ckpt-5.index", "ckpt-5.data-00000-of-00001", "checkpoint", "ckpt-old.pt.bak"} <= set(left)

@@ -33,7 +33,7 @@ if what in ("gemm", "all"):
     e1.record()
     torch.cuda.synchronize()
     print(f"FFN-1 gemm backend 5 + weight images: {e0.elapsed_time(e1) * 1e3 / 20:.1f} us")
-    for backend in (2, 5, 0, 3):
+    for backend in (2, 5, 0):
         for _ in range(reps):
             gemm(X, K, 1, W, N, 1, Y, N, M, N, K, backend, bias=b, act=1)
         torch.cuda.synchronize()
@@ -104,7 +104,7 @@ if what in ("attn", "all"):
                                         ptr(dqkv[:, 2 * d:]), 3 * d, ptr(pad), B, H, T, T, dh, mode, 0, bb, stream()))
 
     for name, fb, bb in (("flash x3 fwd", 2, -1), ("flash x3 fwd+bwd", 2, 2), ("flash tf32 fwd", 0, -1),
-                         ("flash tf32 fwd+bwd", 0, 0), ("legacy x3 fwd", 4, -1), ("legacy fwd+bwd tf32", 3, 3)):
+                         ("flash tf32 fwd+bwd", 0, 0)):
         for mode in (1, 2):
             for _ in range(reps):
                 run(fb, bb, mode)
