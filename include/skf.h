@@ -326,6 +326,32 @@ int skf_tokenize_strokes(const float* points, const int64_t* offsets, int B, con
 /* Number of kernels launched by this plan since creation (bench `gpu_launches`).           */
 int64_t skf_plan_launches(const skf_plan* plan);
 
+/* ---------------- data-parallel exchange --------------------------------------------------------
+ * The reference is single-device (utils/gpu.py:4-15, train.py:41,69): these entry points are new work the north
+ * star asks for.  One process per GPU; the only exchange of a step is a sum of the flat gradient arena over the
+ * ranks (1/world is folded into the optimizer kernel, skf_cfg.world_size).  NCCL is bound at run time; every
+ * failure of it is reported as SKF_ERR_NCCL with NCCL's own message.
+ *  skf_nccl_version     : NCCL version code (e.g. 22809), or SKF_ERR_NCCL when no libnccl.so.2 can be loaded.
+ *  skf_comm_unique_id   : rank 0 fills a 128-byte ncclUniqueId; the caller broadcasts it to the other ranks by any
+ *                         means (torch.distributed, a file, the environment).
+ *  skf_comm_create      : ncclCommInitRank on the current CUDA device; *comm is an opaque handle.
+ *  skf_allreduce_bucket : in-place ncclAllReduce(sum, fp32) of `count` floats at `ptr` on `stream`; asynchronous and
+ *                         CUDA-graph capturable.
+ *  skf_grad_buckets     : the contiguous arena ranges [lo[i], hi[i]) (in floats) a plan with `n_buckets` (1..4) reduces,
+ *                         in the order in which the backward pass completes them (output layer and decoder first,
+ *                         encoder embedding last); returns how many ranges were written (<= n_buckets).
+ *  skf_plan_set_comm    : from now on skf_train_step all-reduces those buckets on a high-priority communication stream
+ *                         as soon as the backward pass (main chain and weight-gradient side stream) has produced
+ *                         them, and the optimizer waits for the last one — all inside the step, so a CUDA graph of
+ *                         the step contains the exchange.  comm = NULL turns it off.                              */
+int skf_nccl_version(void);
+int skf_comm_unique_id(void* id128);
+int skf_comm_create(const void* id128, int world_size, int rank, void** comm);
+int skf_comm_destroy(void* comm);
+int skf_allreduce_bucket(float* ptr, int64_t count, void* comm, void* stream);
+int skf_grad_buckets(const skf_cfg* cfg, int n_buckets, int64_t* lo, int64_t* hi);
+int skf_plan_set_comm(skf_plan* plan, void* comm, int n_buckets);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,13 @@ SIGNATURES = {
     "skf_decode_steps": (I, [P, I, I, P]),
     "skf_tokenize_strokes": (I, [P, P, I, P, I, F, P, I, P]),
     "skf_plan_launches": (L, [P]),
+    "skf_nccl_version": (I, []),
+    "skf_comm_unique_id": (I, [P]),
+    "skf_comm_create": (I, [P, I, I, C.POINTER(P)]),
+    "skf_comm_destroy": (I, [P]),
+    "skf_allreduce_bucket": (I, [P, L, P, P]),
+    "skf_grad_buckets": (I, [C.POINTER(SkfCfg), I, C.POINTER(L), C.POINTER(L)]),
+    "skf_plan_set_comm": (I, [P, P, I]),
 }
 
 _lib = None

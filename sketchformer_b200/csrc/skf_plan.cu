@@ -44,6 +44,7 @@ int attn2_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_
 int attn2_bwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
               const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
               const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
+int allreduce_sum_f32(float*, int64_t, void*, cudaStream_t);       // skf_dp.cu (NCCL, bound at run time)
 int decode_attn(const float*, int64_t, const float*, const float*, int64_t, float*, float*, int64_t, int64_t, int, int,
                 const uint8_t*, int64_t, int, float*, int64_t, int, int, int, cudaStream_t);
 int decode_init(int64_t*, float*, uint8_t*, uint8_t*, uint8_t*, int32_t*, const int32_t*, int, int, int64_t, int,
@@ -179,6 +180,41 @@ static ParamLayout build_layout(const skf_cfg& c) {
   }
   L.total = (L.total + 7) & ~(int64_t)7;
   return L;
+}
+
+// Gradient buckets of the data-parallel exchange: contiguous arena ranges listed in the order in which
+// the backward pass completes them.  The arena is laid out in forward order (encoder, bottleneck, classifier,
+// expander, decoder, output layer), so the ranges are cut from its END: [second half of the decoder + output layer],
+// [rest of the decoder + expander], [second half of the encoder + bottleneck + classifier], [rest of the encoder +
+// its embedding].  stage[k] names the point of backward() after which bucket k is final:
+//   0 = decoder layer L/2 done, 1 = decoder done, 2 = encoder layer L/2 done, 3 = everything done.
+struct Buckets {
+  int n = 0;
+  int64_t lo[4], hi[4];
+  int stage[4];
+};
+static Buckets build_buckets(const skf_cfg& c, const ParamLayout& PL, int want) {
+  Buckets b;
+  if (want < 1) want = 1;
+  if (want > 4) want = 4;
+  const int half = c.L / 2;
+  std::vector<std::pair<int64_t, int>> cuts;        // (arena offset where a bucket starts, stage that completes it)
+  if (c.do_reconstruction) {
+    const int64_t dec_start = PL.off(c.u > 0 ? "exp.k" : (c.continuous ? "dec.emb.k" : "dec.emb"));
+    if (want >= 4 && half > 0) cuts.push_back({PL.off("dec.l" + std::to_string(half) + ".mha1.wqkv.k"), 0});
+    if (want >= 2) cuts.push_back({dec_start, 1});
+  }
+  if ((want >= 3 || (!c.do_reconstruction && want >= 2)) && half > 0)
+    cuts.push_back({PL.off("enc.l" + std::to_string(half) + ".mha.wqkv.k"), 2});
+  cuts.push_back({0, 3});
+  int64_t end = PL.total;
+  for (auto& ct : cuts) {
+    if (ct.first >= end) continue;
+    b.lo[b.n] = ct.first; b.hi[b.n] = end; b.stage[b.n] = ct.second;
+    end = ct.first;
+    b.n++;
+  }
+  return b;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -345,10 +381,17 @@ struct skf_plan {
   std::unordered_map<const void*, cudaEvent_t> pending;
   bool side_active = false;
   bool w16_valid = false;   // the "w16h" / "w16l" images match `params` (refresh_compute_weights)
+  // Data parallel (skf_plan_set_comm): gradient buckets are all-reduced on `comm_stream` as soon as the backward pass
+  // has finished them, behind an event of the main chain and one of the side stream; the optimizer waits for the last
+  void* comm = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  Buckets buckets;
+  int buckets_sent = 0;
   cudaEvent_t next_event() { return events[ev_next++ % events.size()]; }
   ~skf_plan() {
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     if (side) cudaStreamDestroy(side);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
   }
 
   float* wsf(const std::string& n) const { return reinterpret_cast<float*>(ws + W.t.at(n).off); }
@@ -912,6 +955,35 @@ static int losses(skf_plan* P, const void* in, const int64_t* labels, bool want_
   return SKF_OK;
 }
 
+// ---- data-parallel exchange ---------------------------------------------------------------------
+// Stage `stage` of the backward pass is complete on the main chain (everything issued so far on `st`) and on the
+// weight-gradient side stream: all-reduce every bucket that stage finishes, on the communication stream.
+static int buckets_ready(skf_plan* P, int stage, cudaStream_t st) {
+  if (!P->comm || P->c.world_size <= 1) return SKF_OK;
+  while (P->buckets_sent < P->buckets.n && P->buckets.stage[P->buckets_sent] <= stage) {
+    const int k = P->buckets_sent++;
+    cudaEvent_t e_main = P->next_event();
+    SKF_CUDA(cudaEventRecord(e_main, st));
+    SKF_CUDA(cudaStreamWaitEvent(P->comm_stream, e_main, 0));
+    if (P->side_active && P->side != st) {
+      cudaEvent_t e_side = P->next_event();
+      SKF_CUDA(cudaEventRecord(e_side, P->side));
+      SKF_CUDA(cudaStreamWaitEvent(P->comm_stream, e_side, 0));
+    }
+    SKF_TRY(allreduce_sum_f32(P->grads + P->buckets.lo[k], P->buckets.hi[k] - P->buckets.lo[k], P->comm, P->comm_stream));
+  }
+  return SKF_OK;
+}
+// the main chain continues (optimizer) only after every bucket has been reduced
+static int buckets_join(skf_plan* P, cudaStream_t st) {
+  if (!P->comm || P->c.world_size <= 1) return SKF_OK;
+  SKF_TRY(buckets_ready(P, 3, st));
+  cudaEvent_t done = P->next_event();
+  SKF_CUDA(cudaEventRecord(done, P->comm_stream));
+  SKF_CUDA(cudaStreamWaitEvent(st, done, 0));
+  return SKF_OK;
+}
+
 // ---- backward ----------------------------------------------------------------------------------
 static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
   const skf_cfg& c = P->c;
@@ -927,6 +999,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
   float* gDs[3] = {P->wsf("g.d"), P->wsf("g.d1"), P->wsf("g.d2")};
   P->pending.clear();
   P->side_active = g_wgrad_overlap && P->side != nullptr;
+  P->buckets_sent = 0;
   float *gQKV = P->wsf("g.qkv"), *gQ2 = P->wsf("g.q2"), *gKV2 = P->wsf("g.kv2"), *gPre = P->wsf("g.pre");
   float *gEmb = P->wsf("g.emb"), *gU = P->wsf("g.u"), *delta = P->wsf("g.delta");
   const float* gS = nullptr;       // gradient of the current sublayer output (behind its Dropout)
@@ -1023,6 +1096,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
                            Td, Td, 2, st));
       SKF_TRY(G.wgrad_async(xin, gQKV, P->g(p + ".mha1.wqkv.k"), P->g(p + ".mha1.wqkv.b"), Md, 3 * d, d));
       SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha1.wqkv.k"), gA, Md, 3 * d, d, nullptr, gB, 0));
+      if (i == c.L / 2 && i > 0) SKF_TRY(buckets_ready(P, 0, st));    // decoder layers L/2.. and the output layer are final
     }
     SKF_TRY(embed_dropout(P, gA, (int64_t)Md * d, SITE_DEC_X0, st));
     SKF_TRY(embed_any_bwd(P, tok, "dec", gA, Td, st));
@@ -1035,6 +1109,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
       have_demb = true;
     }
   }
+  if (c.do_reconstruction) SKF_TRY(buckets_ready(P, 1, st));          // decoder, its embedding and the expander are final
   if (c.do_classification) {
     SKF_TRY(classifier_bwd(P, gEmb, have_demb, st));
     have_demb = true;
@@ -1043,7 +1118,8 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
     // lowerdim=0: the encoder output reaches the loss only as the decoder's cross keys / values
     SKF_CUDA(cudaMemcpyAsync(gA, gPre, (size_t)Me * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else if (!have_demb) {
-    return G.join();
+    SKF_TRY(G.join());
+    return buckets_join(P, st);
   } else {
     // bottleneck backward
     std::string last = "enc.l" + std::to_string(c.L - 1);
@@ -1089,10 +1165,12 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
                          1, st));
     SKF_TRY(G.wgrad_async(xin, gQKV, P->g(p + ".mha.wqkv.k"), P->g(p + ".mha.wqkv.b"), Me, 3 * d, d));
     SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha.wqkv.k"), gA, Me, 3 * d, d, nullptr, gB, 0));
+    if (i == c.L / 2 && i > 0) SKF_TRY(buckets_ready(P, 2, st));      // encoder layers L/2.., bottleneck and classifier are final
   }
   SKF_TRY(embed_dropout(P, gA, (int64_t)Me * d, SITE_ENC_X0, st));
   SKF_TRY(embed_any_bwd(P, tok, "enc", gA, T, st));
-  return G.join();
+  SKF_TRY(G.join());
+  return buckets_join(P, st);
 }
 
 // ---- greedy decode (models/sketchformer.py:255-311) ----------------------------------------------
@@ -1438,6 +1516,30 @@ int skf_decode_steps(skf_plan* P, int first_step, int n_steps, void* stream) {
 }
 
 int64_t skf_plan_launches(const skf_plan* P) { return P ? P->launches : 0; }
+
+int skf_grad_buckets(const skf_cfg* cfg, int n_buckets, int64_t* lo, int64_t* hi) {
+  SKF_TRY(check_cfg(cfg));
+  SKF_REQUIRE(lo != nullptr && hi != nullptr && n_buckets >= 1, SKF_ERR_BAD_ARG, "grad_buckets: bad argument");
+  ParamLayout L = build_layout(*cfg);
+  Buckets b = build_buckets(*cfg, L, n_buckets);
+  for (int i = 0; i < b.n; i++) { lo[i] = b.lo[i]; hi[i] = b.hi[i]; }
+  return b.n;
+}
+
+int skf_plan_set_comm(skf_plan* P, void* comm, int n_buckets) {
+  SKF_REQUIRE(P != nullptr, SKF_ERR_BAD_ARG, "plan_set_comm: plan is NULL");
+  P->comm = comm;
+  if (!comm) return SKF_OK;
+  SKF_REQUIRE(P->grads != nullptr, SKF_ERR_BAD_ARG, "plan_set_comm: plan created without a gradient arena");
+  SKF_REQUIRE(!P->events.empty(), SKF_ERR_CUDA, "plan_set_comm: the plan has no event pool (no CUDA device?)");
+  if (!P->comm_stream) {
+    int lo = 0, hi = 0;
+    SKF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SKF_CUDA(cudaStreamCreateWithPriority(&P->comm_stream, cudaStreamNonBlocking, hi));
+  }
+  P->buckets = build_buckets(P->c, P->PL, n_buckets);
+  return SKF_OK;
+}
 
 // ---- thin operator wrappers -------------------------------------------------------------------
 int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,

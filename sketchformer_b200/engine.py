@@ -16,6 +16,25 @@ from . import _lib
 from ._lib import SkfCfg, SkfParamEntry, check
 
 
+def create_comm(world_size, rank, device):
+    """NCCL communicator for the gradient exchange, through the C ABI (skf_comm_unique_id / skf_comm_create): rank 0
+    draws the 128-byte id and the default torch.distributed group (any backend) carries it to the other ranks.
+    Returns the opaque handle skf_plan_set_comm / skf_allreduce_bucket take."""
+    import torch.distributed as dist
+    lib = _lib.load()
+    torch.cuda.set_device(device)
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        check(lib.skf_comm_unique_id(C.c_void_p(uid.data_ptr())), "skf_comm_unique_id")
+    on_gpu = dist.get_backend() == "nccl"
+    buf = uid.to(device) if on_gpu else uid
+    dist.broadcast(buf, src=0)
+    uid = buf.cpu().contiguous()
+    comm = C.c_void_p()
+    check(lib.skf_comm_create(C.c_void_p(uid.data_ptr()), int(world_size), int(rank), C.byref(comm)), "skf_comm_create")
+    return comm.value
+
+
 def make_cfg(B, T, d, f, H, L, V, n_classes, lowerdim, *, continuous=False, blind_decoder_mask=True,
              do_classification=True, do_reconstruction=True, class_weight=1.0, recon_weight=1.0,
              world_size=1, gemm_backend=0, attn_backend=0, gemm_precision=2, dropout_rate=0.0,
@@ -249,6 +268,27 @@ class Engine:
         if self.cfg.continuous:
             return self.tensor("gen.strokes", (B, T + 1, 5))[:, :cols].clone()
         return self.tensor("gen.tokens", (B, T + 1), dtype=torch.int64)[:, :cols].to(torch.int32)
+
+    # ---- data parallel (include/skf.h "data-parallel exchange") -----------------------------------
+    def set_comm(self, comm, n_buckets=4):
+        """From now on train_step() all-reduces the gradient arena over the ranks of `comm` (an opaque handle from
+        `create_comm`) in `n_buckets` buckets overlapped with the backward pass, before the optimizer.  A captured
+        graph of the old step is dropped."""
+        check(self.lib.skf_plan_set_comm(self._plan, C.c_void_p(comm) if comm else None, int(n_buckets)),
+              "skf_plan_set_comm")
+        self._graph = None
+
+    def grad_buckets(self, n_buckets=4):
+        lo, hi = (C.c_int64 * 4)(), (C.c_int64 * 4)()
+        n = self.lib.skf_grad_buckets(C.byref(self.cfg), int(n_buckets), lo, hi)
+        if n < 0:
+            check(n, "skf_grad_buckets")
+        return [(int(lo[i]), int(hi[i])) for i in range(n)]
+
+    def allreduce_grads(self, comm):
+        """One in-place NCCL sum of the whole gradient arena on the current stream (tests, the dp check of bench.py)."""
+        check(self.lib.skf_allreduce_bucket(C.c_void_p(self.grads.data_ptr()), self.grads.numel(), C.c_void_p(comm),
+                                            self._stream()), "skf_allreduce_bucket")
 
     def launches(self):
         return int(self.lib.skf_plan_launches(self._plan))

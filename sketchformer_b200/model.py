@@ -67,7 +67,7 @@ class Transformer:
 
     # ---- construction ----------------------------------------------------------------------
     def __init__(self, hps, dataset, out_dir=None, experiment_id="0", device="cuda:0", world_size=1, seed=0,
-                 gemm_precision=None, use_cuda_graph=True, rank=0):
+                 gemm_precision=None, use_cuda_graph=True, rank=0, dp_buckets=4):
         self.hps = hps if isinstance(hps, dict) else dict(hps.values())
         self.dataset = dataset
         self.experiment_id = experiment_id
@@ -95,6 +95,10 @@ class Transformer:
         self._use_graph = use_cuda_graph
         self._engines = {}
         self._stage = {}
+        # data parallel: dp_buckets >= 1 -> bucketed NCCL all-reduce inside the step, overlapped with the backward pass
+        # and captured in the CUDA graph (skf_plan_set_comm); 0 -> one torch.distributed all_reduce after the step
+        self._dp_buckets = int(dp_buckets) if world_size > 1 else 0
+        self._comm = None
         self.build_model()
 
     @property
@@ -158,6 +162,11 @@ class Transformer:
         if first:
             self._train_engine = eng
             eng.load_params(init_params(self._layout_hps(), seed=self._seed))
+        if self._dp_buckets and eng.grads is not None:
+            if self._comm is None:
+                from .engine import create_comm
+                self._comm = create_comm(self._world, self._rank, self._device)
+            eng.set_comm(self._comm, self._dp_buckets)
         self._engines[B] = eng
         return eng
 
@@ -210,7 +219,8 @@ class Transformer:
         B = int(data.shape[0])
         eng = self._engine(B, training=True)
         dt = torch.int64 if not self.continuous else torch.float32
-        solo = self._world == 1           # data parallel: gradients are all-reduced before the optimizer
+        # the optimizer runs inside the step unless the gradients still have to be all-reduced by torch afterwards
+        solo = self._world == 1 or self._dp_buckets > 0
         if self._use_graph and eng is self._train_engine and eng.eager_train_steps >= 1:
             # (one eager step first — also right after restore_checkpoint_if_exists(), when current_step is already
             # large: function attributes and tensor-map encoders are initialised lazily, engine.py capture_train_step)

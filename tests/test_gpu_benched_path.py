@@ -47,13 +47,19 @@ def test_train_on_batch_cfg2_b128_graph_replay_matches_oracle():
     p = O.init_params(ocfg, 0, torch.float64)
     eng.load_params(p)
     opt = O.AdamTF(p, ocfg.d_model)
-    # inside the warm-up ramp (lr ~ 1e-3) so that the optimizer of every step moves the weights measurably
-    opt.iterations = 4000
-    eng.set_step(4000)
     it = dataset.batch_iterator("train", B)
     batches = [next(it) for _ in range(4)]
 
     for s, (x, y) in enumerate(batches):
+        if s == 2:
+            # Steps 0 and 1 run at optimizer iterations 0 and 1: lr(0) = 0 (builders/schedulers.py:25-29) leaves the
+            # weights bit-identical on both sides, so the gradients of step 1 — the first REPLAYED step — are
+            # compared at identical weights.  (At lr ~ 1e-3 Adam's first updates are ~lr * sign(g): every element
+            # whose gradient is rounding noise would move the two sides 1e-3 apart before the comparison.)  From
+            # here on both sides jump into the warm-up ramp so that the in-graph optimizer moves the weights
+            # measurably; the graph reads the iteration counter from device memory, so this needs no re-capture.
+            opt.iterations = 4000
+            eng.set_step(4000)
         assert isinstance(x, np.ndarray) and x.shape == (B, ocfg.max_seq_len)       # host buffers, as bench's e2e
         got = model.train_on_batch((x, y))
         torch.cuda.synchronize()
@@ -79,6 +85,9 @@ def test_train_on_batch_cfg2_b128_graph_replay_matches_oracle():
                 if not num / den < TOL:
                     bad.append((k, num / den))
             assert not bad, f"gradients of the replayed step off: {sorted(bad, key=lambda t: -t[1])[:8]}"
+            worst = max(float((gg[k].double() - ref.double()).norm()) / max(float(ref.double().norm()), 1e-4 * G)
+                        for k, ref in grads.items())
+            print(f"cfg2 B=128 graph replay: worst gradient rel. L2 error {worst:.2e}, ReLU flips {flips}/{units}")
         else:
             want, _ = O.train_step(p, opt, xt, yt, ocfg, dtype=torch.float64)
         for k in ("recon_loss", "class_loss", "total_loss"):
@@ -89,7 +98,7 @@ def test_train_on_batch_cfg2_b128_graph_replay_matches_oracle():
         assert abs(last["recon_acc"] - want["recon_acc"]) <= 1.0 / (B * (ocfg.max_seq_len - 1)) + 1e-12
         assert last["class_acc"] == pytest.approx(want["class_acc"], abs=1e-12)
         assert set(got) == {"recon_loss", "recon_acc", "class_loss", "class_acc", "total_loss"}
-    assert eng.step_count() == 4004 and model.current_step == 4
+    assert eng.step_count() == 4002 and model.current_step == 4
     # the optimizer ran inside the graph: weights left their initial values by about lr per element
     moved = eng.export_params({"enc.l0.ffn.w1.k": p["enc.l0.ffn.w1.k"]})["enc.l0.ffn.w1.k"]
     init = O.init_params(ocfg, 0, torch.float64)["enc.l0.ffn.w1.k"]
