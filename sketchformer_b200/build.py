@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libskf.so")
-SOURCES = ["skf_kernels.cu", "skf_simt.cu", "skf_tmap.cu", "skf_gemm_tc2.cu", "skf_gemm_tc3.cu", "skf_attn_tc2.cu", "skf_decode.cu", "skf_tokenize.cu", "skf_dp.cu", "skf_plan.cu"]
+SOURCES = ["skf_kernels.cu", "skf_simt.cu", "skf_tmap.cu", "skf_gemm_tc2.cu", "skf_gemm_tc3.cu", "skf_attn_tc2.cu", "skf_attn_tc3.cu", "skf_decode.cu", "skf_tokenize.cu", "skf_dp.cu", "skf_plan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-v"]
 

@@ -38,6 +38,14 @@ extern int g_t3_bn128_max;  // pair GEMM: 128-column cluster tiles for N up to t
 int g_gemm_tiny_simt = 0;   // 1: products with M <= 128 and few column tiles run on the small-tile SIMT kernel (no gain measured: 9.04 vs 9.01 ms)
 extern int g_gemm_wsplit;   // 1: forward / dgrad products read pre-split bf16 images of the weights (skf_gemm_tc3.cu)
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
+int attn3_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
+int attn3_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
+              const uint8_t*, int, int, int, int, int, int, cudaStream_t);
+int attn3_bwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
+              const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
+              const uint8_t*, int, int, int, int, int, int, cudaStream_t);
+int g_attn3 = 3;           // bit 0 / bit 1: head dim 32 and sequences up to 224 run the warp-specialised whole-row forward /
+                           // backward kernels (skf_attn_tc3.cu)
 int attn2_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
 int attn2_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
               const uint8_t*, int, int, int, int, int, int, int, cudaStream_t);
@@ -657,6 +665,8 @@ static int attn_fwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
                         const float* V, int64_t ldv, float* O, int64_t ldo, float* lse, const uint8_t* pad,
                         int Tq, int Tk, int mode, cudaStream_t st) {
   const skf_cfg& c = P->c;
+  if (c.attn_backend == 0 && (g_attn3 & 1) && c.gemm_precision >= 1 && attn3_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
+    return attn3_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode, st);
   if (c.attn_backend == 0 && attn2_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
     return attn2_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode,
                      c.gemm_precision >= 1 ? 1 : 0, st);
@@ -668,6 +678,9 @@ static int attn_bwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
                         const float* lse, float* delta, float* dQ, int64_t lddq, float* dK, int64_t lddk,
                         float* dV, int64_t lddv, const uint8_t* pad, int Tq, int Tk, int mode, cudaStream_t st) {
   const skf_cfg& c = P->c;
+  if (c.attn_backend == 0 && (g_attn3 & 2) && c.gemm_precision >= 2 && attn3_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
+    return attn3_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad, c.B, c.H,
+                     Tq, Tk, c.d / c.H, mode, st);
   if (c.attn_backend == 0 && attn2_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
     return attn2_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad, c.B,
                      c.H, Tq, Tk, c.d / c.H, mode, c.gemm_precision >= 2 ? 1 : 0, st);
@@ -1303,6 +1316,10 @@ int skf_set_option(const char* name, int value) {
     skf::g_gemm_wsplit = value ? 1 : 0;
     return SKF_OK;
   }
+  if (name && strcmp(name, "attn3") == 0) {
+    skf::g_attn3 = value & 3;
+    return SKF_OK;
+  }
   if (name && strcmp(name, "kv_fold") == 0) {
     skf::g_kv_fold = value < 0 ? 0 : (value > 2 ? 2 : value);
     return SKF_OK;
@@ -1561,6 +1578,8 @@ int skf_attn_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
                  int mask_mode, int round_tf32, int backend, void* stream) {
   // backend: 0 = tcgen05 flash kernels, single-pass TF32; 2 = the same with the 3xTF32 split (fp32-grade);
   //          1 = SIMT fp32
+  if (backend == 6)                      // warp-specialised whole-row kernels (head dim 32, T <= 224), bf16x3
+    return attn3_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, as_stream(stream));
   if (backend == 0 || backend == 2)
     return attn2_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, backend == 2,
                      as_stream(stream));
@@ -1572,6 +1591,9 @@ int skf_attn_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
                  const float* O, int64_t ldo, const float* dO, int64_t lddo, const float* lse, float* delta,
                  float* dQ, int64_t lddq, float* dK, int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad,
                  int B, int H, int Tq, int Tk, int dh, int mask_mode, int round_tf32, int backend, void* stream) {
+  if (backend == 6)
+    return attn3_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B, H,
+                     Tq, Tk, dh, mask_mode, as_stream(stream));
   if (backend == 0 || backend == 2)
     return attn2_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B,
                      H, Tq, Tk, dh, mask_mode, backend == 2, as_stream(stream));

@@ -45,6 +45,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   __trap();
 }
 
+// The same with a suspend-time hint: the thread sleeps in hardware (up to the hint, in ns) instead of re-issuing
+// try_wait — for warps that share an SM sub-partition with warps doing real work (warp-specialised kernels).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+    if (ok) return;
+    uint64_t now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) __trap();      // 4 s: a lost arrival traps instead of hanging the GPU box
+  }
+}
+
 // ---- TMA ----------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -49,6 +49,60 @@ def make_cfg(B, T, d, f, H, L, V, n_classes, lowerdim, *, continuous=False, blin
                   class_dropout=float(class_dropout))
 
 
+def param_table(cfg: SkfCfg):
+    """skf_param_table(): name -> (offset in floats, rows, cols) of the flat parameter / gradient arena, and its size.
+    Pure host code (no device needed)."""
+    lib = _lib.load()
+    n = lib.skf_param_count(C.byref(cfg))
+    if n <= 0:
+        check(int(n) if n < 0 else -1, "skf_param_count")
+    ent = (SkfParamEntry * 512)()
+    cnt = lib.skf_param_table(C.byref(cfg), ent, 512)
+    if cnt < 0:
+        check(cnt, "skf_param_table")
+    return {ent[i].name.decode(): (int(ent[i].offset), int(ent[i].rows), int(ent[i].cols)) for i in range(cnt)}, int(n)
+
+
+def arena_name(name, d):
+    """oracle / Keras variable name -> (arena tensor name, column slice or None): wq|wk|wv of a self-attention block
+    are fused column-wise into wqkv, the cross-attention wk|wv into wkv (include/skf.h "parameter arena")."""
+    for tag, fused, order in ((".mha.", "wqkv", ("wq", "wk", "wv")), (".mha1.", "wqkv", ("wq", "wk", "wv")),
+                              (".mha2.", "wkv", ("wk", "wv"))):
+        if tag in name:
+            head, rest = name.split(tag)
+            w, kind = rest.split(".")
+            if w in order:
+                i = order.index(w)
+                return f"{head}{tag}{fused}.{kind}", slice(i * d, (i + 1) * d)
+    return name, None
+
+
+def fill_arena(arena, table, d, named):
+    """Write tensors named as in oracle/sketchformer_oracle.py into a flat arena laid out by `table` (any device)."""
+    for name, val in named.items():
+        tname, sl = arena_name(name, d)
+        off, r, c = table[tname]
+        dst = arena[off: off + r * c].view(r, c)
+        v = torch.as_tensor(val).detach().to(arena.dtype)
+        if name == "pool.V" or v.dim() == 1:
+            v = v.reshape(1, -1)
+        if sl is None:
+            dst.copy_(v)
+        else:
+            dst[:, sl].copy_(v)
+    return arena
+
+
+def grad_buckets(cfg: SkfCfg, n_buckets=4):
+    """skf_grad_buckets(): [(lo, hi)] arena ranges in backward-completion order.  Pure host code."""
+    lib = _lib.load()
+    lo, hi = (C.c_int64 * 4)(), (C.c_int64 * 4)()
+    n = lib.skf_grad_buckets(C.byref(cfg), int(n_buckets), lo, hi)
+    if n < 0:
+        check(n, "skf_grad_buckets")
+    return [(int(lo[i]), int(hi[i])) for i in range(n)]
+
+
 class Engine:
     METRIC_NAMES = ("recon_loss", "recon_acc", "class_loss", "class_acc", "total_loss")
 
@@ -120,16 +174,7 @@ class Engine:
 
     def _map(self, name):
         """oracle name -> (arena tensor name, column slice or None)"""
-        d = self.cfg.d
-        for tag, fused, order in ((".mha.", "wqkv", ("wq", "wk", "wv")), (".mha1.", "wqkv", ("wq", "wk", "wv")),
-                                  (".mha2.", "wkv", ("wk", "wv"))):
-            if tag in name:
-                head, rest = name.split(tag)
-                w, kind = rest.split(".")
-                if w in order:
-                    i = order.index(w)
-                    return f"{head}{tag}{fused}.{kind}", slice(i * d, (i + 1) * d)
-        return name, None
+        return arena_name(name, self.cfg.d)
 
     def load_params(self, named: Dict[str, torch.Tensor]):
         """Import tensors named as in oracle/sketchformer_oracle.py (Keras shapes, kernel=(in,out))."""
@@ -279,11 +324,7 @@ class Engine:
         self._graph = None
 
     def grad_buckets(self, n_buckets=4):
-        lo, hi = (C.c_int64 * 4)(), (C.c_int64 * 4)()
-        n = self.lib.skf_grad_buckets(C.byref(self.cfg), int(n_buckets), lo, hi)
-        if n < 0:
-            check(n, "skf_grad_buckets")
-        return [(int(lo[i]), int(hi[i])) for i in range(n)]
+        return grad_buckets(self.cfg, n_buckets)
 
     def allreduce_grads(self, comm):
         """One in-place NCCL sum of the whole gradient arena on the current stream (tests, the dp check of bench.py)."""

@@ -1,7 +1,8 @@
 """Data-parallel host logic on CPU (gloo, world_size 2): the sharded loader hands every rank a disjoint slice
 of the same global batch, and summing per-rank gradients with the 1/world factor that the Adam kernel folds in
 (skf_adam_step grad_scale) reproduces the full-batch gradient of the oracle — the property the
-NCCL all-reduce of the flat gradient arena relies on.  No GPU: the per-rank gradients come from the oracle."""
+NCCL all-reduce of the flat gradient arena relies on.  The arena layout and the gradient buckets are the library's own
+(skf_param_table / skf_grad_buckets, host code); no GPU: the per-rank gradients come from the oracle."""
 import os
 import socket
 
@@ -44,15 +45,30 @@ def _worker(rank, port, out):
         p = O.init_params(ocfg, 0, torch.float64)
         _, grads = O.train_step({k: v.clone() for k, v in p.items()}, O.AdamTF(p, ocfg.d_model), torch.from_numpy(x),
                                 torch.from_numpy(y), ocfg, dtype=torch.float64)
-        names = sorted(grads)
-        arena = torch.cat([grads[k].reshape(-1) for k in names])
-        dist.all_reduce(arena)
-        arena /= WORLD
+        # the library's own arena layout (skf_param_table) and bucket ranges (skf_grad_buckets: what skf_train_step
+        # all-reduces, bucket by bucket, in backward-completion order) — host code of libskf.so, no GPU involved
+        from sketchformer_b200.engine import fill_arena, grad_buckets, make_cfg, param_table
+        cfg = make_cfg(GLOBAL_B // WORLD, ocfg.max_seq_len, ocfg.d_model, ocfg.dff, ocfg.num_heads, ocfg.num_layers,
+                       ocfg.vocab_size, ocfg.n_classes, ocfg.lowerdim, world_size=WORLD)
+        table, total = param_table(cfg)
+        arena = fill_arena(torch.zeros(total, dtype=torch.float64), table, ocfg.d_model, grads)
         _, gfull = O.train_step({k: v.clone() for k, v in p.items()}, O.AdamTF(p, ocfg.d_model), torch.from_numpy(gx),
                                 torch.from_numpy(gy), ocfg, dtype=torch.float64)
-        want = torch.cat([gfull[k].reshape(-1) for k in names])
-        err = float((arena - want).norm() / want.norm())
-        assert err < 1e-12, err
+        want = fill_arena(torch.zeros(total, dtype=torch.float64), table, ocfg.d_model, gfull)
+        for nb in (1, 2, 3, 4):
+            buckets = grad_buckets(cfg, nb)
+            assert len(buckets) == nb and buckets[0][1] == total and buckets[-1][0] == 0
+            assert all(buckets[i][0] == buckets[i + 1][1] for i in range(nb - 1)), buckets   # contiguous, end -> start
+            assert all(lo % 8 == 0 for lo, _ in buckets)                                     # 32-byte aligned ranges
+            red = arena.clone()
+            for lo, hi in buckets:
+                dist.all_reduce(red[lo:hi])
+            red /= WORLD
+            err = float((red - want).norm() / want.norm())
+            assert err < 1e-12, (nb, err)
+        # the output layer / decoder come first (backward order), the encoder embedding last
+        b4 = grad_buckets(cfg, 4)
+        assert b4[0][0] <= table["out.k"][0] < b4[0][1] and b4[-1][0] <= table["enc.emb"][0] < b4[-1][1]
         if rank == 0:
             out.put(("ok", err))
     except Exception as e:      # noqa: BLE001

@@ -321,6 +321,7 @@ TC_ATTN = [(3, 8, 200, 200, 32, 1), (3, 8, 199, 199, 32, 2), (3, 8, 199, 200, 32
 # 3xTF32 score products; P / dS rounded once to TF32 (rel. 2^-12 per weight, does not average out against
 # random V) with compensated V / K / Q / dO: 1.6e-4 forward, 2.2e-4 backward measured on B200
 TOL_ATTN_X3 = 3e-4
+ATTN3_BWD = 6       # backward kernels the whole-row forward is paired with in the op test (6 once they exist)
 
 
 # head dim 64 (two 128-byte chunks per tile) and sequences up to 1024 (cfg5: d 512, 8 heads, T 512)
@@ -338,6 +339,22 @@ def test_attention_tcgen05(lib, B, H, Tq, Tk, dh, mode):
     assert max(errs) < TOL_ATTN_X3, errs
     errs = _attn_case(lib, B, H, Tq, Tk, dh, mode, 300 + Tq, fwd_backend=0, bwd_backend=0)
     assert max(errs) < TOL_TF32, errs
+
+
+# warp-specialised whole-row kernels (skf_attn_tc3.cu, backend 6): head dim 32, sequences up to 224; every product is
+# the bf16x3 error-compensated sum (16 mantissa bits per operand): 1e-5-grade
+TOL_ATTN3 = 5e-5
+TC_ATTN3 = TC_ATTN + [(5, 8, 200, 200, 32, 1), (40, 8, 199, 199, 32, 2), (2, 3, 128, 128, 32, 2), (2, 3, 129, 129, 32, 2),
+                      (1, 1, 1, 1, 32, 0), (2, 2, 1, 200, 32, 1), (2, 2, 224, 17, 32, 1), (3, 4, 65, 64, 32, 0)]
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,mode", TC_ATTN3)
+def test_attention_tcgen05_whole_row(lib, B, H, Tq, Tk, dh, mode):
+    if mode == 2 and Tq != Tk:
+        Tk = Tq
+    e_o, e_q, e_k, e_v = _attn_case(lib, B, H, Tq, Tk, dh, mode, 400 + Tq, fwd_backend=6, bwd_backend=ATTN3_BWD)
+    assert e_o < TOL_ATTN3, e_o
+    assert max(e_q, e_k, e_v) < (TOL_ATTN3 if ATTN3_BWD == 6 else TOL_ATTN_X3), (e_q, e_k, e_v)
 
 
 MAJORS = [("fwd", False, True), ("dgrad", False, False), ("wgrad", True, True), ("tn", True, False)]

@@ -236,6 +236,10 @@ def test_ablation_flags(flags, name, cfg_kw, B, backend):
     G = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
     bad = []
     for k, ref in grads.items():
+        if k.endswith(".wk.b"):
+            continue      # identically-zero gradient (softmax is shift-invariant): rounding noise on both sides, whose
+                          # size relative to G depends on which loss terms are switched on; test_train_step_matches_oracle
+                          # bounds it at the default flags
         num = float((got[k].double() - ref.double()).norm())
         if not num / max(float(ref.double().norm()), 1e-4 * G) < tol:
             bad.append((k, num / max(float(ref.double().norm()), 1e-4 * G)))
