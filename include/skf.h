@@ -326,6 +326,11 @@ int skf_tokenize_strokes(const float* points, const int64_t* offsets, int B, con
 /* Number of kernels launched by this plan since creation (bench `gpu_launches`).           */
 int64_t skf_plan_launches(const skf_plan* plan);
 
+/* Development aid: with skf_set_option("attn3_trace", 1) CTA 0 of the whole-row attention forward kernel stamps clock64()
+ * at its phase boundaries ([role][item][16], see csrc/skf_attn_tc3.cu); copies up to n stamps to host memory `out`
+ * (synchronises the device) and returns how many.                                                               */
+int skf_debug_trace(int64_t* out, int n);
+
 /* ---------------- data-parallel exchange --------------------------------------------------------
  * The reference is single-device (utils/gpu.py:4-15, train.py:41,69): these entry points are new work the north
  * star asks for.  One process per GPU; the only exchange of a step is a sum of the flat gradient arena over the

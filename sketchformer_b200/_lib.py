@@ -87,6 +87,7 @@ SIGNATURES = {
     "skf_decode_steps": (I, [P, I, I, P]),
     "skf_tokenize_strokes": (I, [P, P, I, P, I, F, P, I, P]),
     "skf_plan_launches": (L, [P]),
+    "skf_debug_trace": (I, [P, I]),
     "skf_nccl_version": (I, []),
     "skf_comm_unique_id": (I, [P]),
     "skf_comm_create": (I, [P, I, I, C.POINTER(P)]),

@@ -6,7 +6,7 @@
 //
 //   warp 0        TMA producer   fp32 [64 rows x 32] boxes of Q / K / V (/ dO / O) -> a 4-stage ring (3-D tensor maps
 //                                [B][T][H*dh]: rows past the sequence are zero-filled, never the next sample's rows)
-//   warps 2..7    converters     ring stage -> bf16 hi / lo operand tiles (64-byte rows, 64B swizzle); operands whose
+//   warps 2..5    converters     ring stage -> bf16 hi / lo operand tiles (64-byte rows, 64B swizzle); operands whose
 //                                last reader runs late in an item are double-buffered, so the next item's operands
 //                                land while this item's math runs
 //   warp 1        MMA issuer     tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), SS form for the score products
@@ -45,10 +45,11 @@ namespace a3 {
 constexpr int DH = 32;
 constexpr int MAXT = 224;                 // 2 S tiles of MAXT columns + 64 accumulator columns = 512 TMEM columns
 constexpr int HALF = MAXT / 2;            // backward: columns per warpgroup
-constexpr int NST = 4;                    // ring stages
+constexpr int NST = 8;                    // ring stages at most (barrier slots); Args::nst are used
 constexpr int STAGE_BYTES = 64 * 128;     // 64 rows x 32 fp32
-constexpr int NCONV = 6;                  // converter warps
-constexpr int THREADS = 512;
+constexpr int NCONV = 4;                  // converter warps (warps 2..5); 256 % (32 NCONV) == 0
+constexpr int MATH0 = 8;                  // first math warp (a multiple of 4: warp % 4 == TMEM lane quarter); 6, 7 idle
+constexpr int THREADS = 32 * (MATH0 + 8);
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float MASK_NEG = -1e9f;
 
@@ -80,6 +81,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                : "r"(taddr)
                : "memory");
 }
+// 16 columns into the first half of a 32-register buffer (no address-of: the buffer stays in registers)
+__device__ __forceinline__ void tmem_ld16_lo(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
                ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
@@ -95,10 +104,19 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
   hi = pack_bf16(a, b);
   lo = pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
 }
+// The same split on the integer pipe for the math warps (F2FP shares the quarter-rate conversion / MUFU path with ex2,
+// which bounds those warps): hi = x truncated to bf16 (top 16 bits), lo = bf16(x - hi) rounded half-up; x - hi is
+// exact and has the sign of x, so hi + lo = x (1 +- 2^-17), unbiased.
+__device__ __forceinline__ void split_pair_int(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  hi = __byte_perm(ua, ub, 0x7632);
+  const float la = a - __uint_as_float(ua & 0xFFFF0000u), lb = b - __uint_as_float(ub & 0xFFFF0000u);
+  lo = __byte_perm(__float_as_uint(la) + 0x8000u, __float_as_uint(lb) + 0x8000u, 0x7632);
+}
 // 16 fp32 values -> 8 packed hi words followed by 8 packed lo words (the A operand of one K = 16 MMA step, twice)
 __device__ __forceinline__ void split16(const float (&p)[16], uint32_t (&w)[16]) {
 #pragma unroll
-  for (int j = 0; j < 8; j++) split_pair(p[2 * j], p[2 * j + 1], w[j], w[8 + j]);
+  for (int j = 0; j < 8; j++) split_pair_int(p[2 * j], p[2 * j + 1], w[j], w[8 + j]);
 }
 
 // One ring stage (64 rows x 32 fp32, 128-byte rows under the TMA's 128B swizzle) -> rows [row0, row0 + 64) of a bf16
@@ -110,14 +128,14 @@ template <bool WITH_DOT>
 __device__ __forceinline__ void convert_stage(const uint8_t* stage, uint8_t* hi, uint8_t* lo, int row0, int rows_alloc,
                                               int ct, const uint8_t* other = nullptr, float* dot_out = nullptr,
                                               float* dot_glob = nullptr, int rows_valid = 0) {
-  // 256 tasks = 64 rows x 4 groups of 8 columns; WITH_DOT needs the 4 lanes of a row in one warp at the same time, so
-  // the loop runs a uniform number of rounds (ct < 192: round 0 covers tasks 0..191, round 1 tasks 192..255)
-  for (int round = 0; round < 2; round++) {
+  // 256 tasks = 64 rows x 4 groups of 8 columns, NCONV * 32 per round; the 4 lanes of a quad share a row
+  static_assert(256 % (NCONV * 32) == 0, "converter rounds");
+#pragma unroll 1
+  for (int round = 0; round < 256 / (NCONV * 32); round++) {
     const int task = ct + round * NCONV * 32;
-    const bool live = task < 256;
-    const int r = (task >> 2) & 63, g = task & 3, R = row0 + r;
+    const int r = task >> 2, g = task & 3, R = row0 + r;
     float dot = 0.f;
-    if (live && R < rows_alloc) {
+    if (R < rows_alloc) {
       const uint32_t sx = (uint32_t)(r & 7);
       const uint32_t o0 = r * 128 + (((2 * g) ^ sx) << 4), o1 = r * 128 + (((2 * g + 1) ^ sx) << 4);
       const float4 u = *reinterpret_cast<const float4*>(stage + o0);
@@ -137,10 +155,9 @@ __device__ __forceinline__ void convert_stage(const uint8_t* stage, uint8_t* hi,
       *reinterpret_cast<uint4*>(lo + dof) = l;
     }
     if (WITH_DOT) {
-      if (round == 1 && ct >= 64) continue;              // warp-uniform: warps 2.. have no task in round 1
       dot += __shfl_xor_sync(0xffffffffu, dot, 1);
       dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-      if (live && g == 0 && R < rows_alloc) {
+      if (g == 0 && R < rows_alloc) {
         dot_out[R] = dot;
         if (dot_glob && R < rows_valid) dot_glob[R] = dot;
       }
@@ -148,8 +165,17 @@ __device__ __forceinline__ void convert_stage(const uint8_t* stage, uint8_t* hi,
   }
 }
 
+// Optional phase trace (skf_set_option("attn3_trace", 1)): CTA 0 stamps clock64() at the phase boundaries of its first
+// 8 items, role by role; tools/attn_trace.py prints the deltas.  [role][item][16 stamps]
+__device__ long long g_trace[4 * 8 * 16];
+__device__ __forceinline__ void stamp(int on, int role, uint32_t li, int k) {
+  if (on && blockIdx.x == 0 && li < 8) g_trace[(role * 8 + li) * 16 + k] = clock64();
+}
+
 struct Args {
+  int trace;
   int B, H, Tq, Tk, mode;
+  int nst;                    // ring stages in use (<= NST): as many as shared memory leaves room for
   float scale;
   const uint8_t* key_pad;     // [B, Tk] or nullptr
   float* out0;                // fwd: O      dq: dQ     dkv: dK
@@ -205,10 +231,10 @@ struct Smem {
   uint32_t tile_bytes;          // one bf16 tile: TP x 64 bytes
   uint32_t total;
 };
-__host__ __device__ inline Smem smem_plan(int TP, int ntiles, int nvec) {
+__host__ __device__ inline Smem smem_plan(int TP, int ntiles, int nvec, int nst) {
   Smem s;
   s.ring = 0;
-  s.tiles = NST * STAGE_BYTES;
+  s.tiles = nst * STAGE_BYTES;
   s.tile_bytes = (uint32_t)TP * 64;
   s.vec = s.tiles + s.tile_bytes * ntiles + 4096;   // 4 KB pad: M = 128 / N reads past the last tile stay inside
   s.bars = s.vec + nvec * 256 * 4;
@@ -249,8 +275,8 @@ __device__ __forceinline__ void epilogue_free(const Ctx& c) {
 // ---------------------------------------------------------------------------------------------------
 namespace fw {
 enum { RING_FULL = 0, RING_EMPTY = NST, OP_FULL = 2 * NST /* [2 bufs][4] */, OP_EMPTY = 2 * NST + 8 /* [2] */,
-       S_FULL = 2 * NST + 10 /* [2] */, P_FULL = 2 * NST + 12 /* [2] */, O_FULL = 2 * NST + 14 /* [2] */,
-       O_FREE = 2 * NST + 16, COUNT = 2 * NST + 17 };
+       S_FULL = 2 * NST + 10 /* [2] */, P_FULL = 2 * NST + 12 /* [2 tiles][2 column parts] */, O_FULL = 2 * NST + 16 /* [2] */,
+       O_FREE = 2 * NST + 18, COUNT = 2 * NST + 19 };
 }
 
 template <bool CAUSAL>
@@ -262,7 +288,7 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
   Ctx c;
   prologue(c, smem_raw);
   const int QP = (a.Tq + 15) & ~15, KP = (a.Tk + 15) & ~15, TP = QP > KP ? QP : KP;
-  const Smem L = smem_plan(TP, 12, 2);
+  const Smem L = smem_plan(TP, 12, 2, a.nst);
   const uint32_t buf_bytes = 6 * L.tile_bytes;
   const int tid = c.tid, warp = c.warp, lane = c.lane;
   const uint32_t base = c.base;
@@ -284,7 +310,8 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       mbar_init(bar(OP_FULL + 4 * b + 3), 1);
       mbar_init(bar(OP_EMPTY + b), 1);
       mbar_init(bar(S_FULL + b), 1);
-      mbar_init(bar(P_FULL + b), 4);
+      mbar_init(bar(P_FULL + 2 * b), 4);
+      mbar_init(bar(P_FULL + 2 * b + 1), 4);
       mbar_init(bar(O_FULL + b), 1);
     }
     mbar_init(bar(O_FREE), 4);
@@ -300,6 +327,9 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     if (CAUSAL) n = min(n, 128 * t + 128);
     return (n + 15) & ~15;
   };
+  // P is handed to the tensor core in two column parts so that the first part's P V MMAs run under the softmax of
+  // the second: part 0 = columns [0, split(t)), a multiple of 32
+  auto split = [&](int t) { return min(ncols(t), ((ncols(t) + 63) >> 6) << 5); };
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -312,8 +342,8 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           const CUtensorMap* m = op == 0 ? &mQ : (op == 1 ? &mK : &mV);
           const int nch = op == 0 ? nq_ch : nk_ch;
           for (int ch = 0; ch < nch; ch++, n++) {
-            const int st = n % NST;
-            mbar_wait_sleep(bar(RING_EMPTY + st), ((n / NST) & 1u) ^ 1u);
+            const int st = n % a.nst;
+            mbar_wait_sleep(bar(RING_EMPTY + st), ((n / a.nst) & 1u) ^ 1u);
             mbar_arrive_expect_tx(bar(RING_FULL + st), STAGE_BYTES);
             tma_load_3d(base + L.ring + st * STAGE_BYTES, m, bar(RING_FULL + st), h * DH, 64 * ch, b);
           }
@@ -329,9 +359,10 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       uint8_t* tiles = gen + L.tiles + buf * buf_bytes;
       // the MMAs of the item that used this buffer two items ago have completed
       mbar_wait_sleep(bar(OP_EMPTY + buf), ((li >> 1) & 1u) ^ 1u);
+      if (ct == 0) stamp(a.trace, 3, li, 0);
       // key bias of this item (log2 domain): -inf past the sequence, the reference's additive -1e9 on padded keys
       float* bias_s = reinterpret_cast<float*>(gen + L.vec) + buf * 256;
-      for (int j = ct; j < KP; j += NCONV * 32) {
+      for (int j = ct; j < 256; j += NCONV * 32) {
         float bj = 0.f;
         if (j >= a.Tk) bj = -INFINITY;
         else if (a.mode >= 1 && a.key_pad && a.key_pad[(int64_t)b * a.Tk + j]) bj = MASK_NEG * LOG2E;
@@ -342,8 +373,8 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         uint8_t* hi = tiles + (2 * op) * L.tile_bytes;
         uint8_t* lo = hi + L.tile_bytes;
         for (int ch = 0; ch < nch; ch++, n++) {
-          const int st = n % NST;
-          mbar_wait_sleep(bar(RING_FULL + st), (n / NST) & 1u);
+          const int st = n % a.nst;
+          mbar_wait_sleep(bar(RING_FULL + st), (n / a.nst) & 1u);
           convert_stage<false>(gen + L.ring + st * STAGE_BYTES, hi, lo, 64 * ch, TP, ct);
           fence_proxy_async();             // the tensor core reads the tiles through the async proxy
           __syncwarp();
@@ -352,6 +383,7 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
             mbar_arrive(bar(RING_EMPTY + st));
           }
         }
+        if (ct == 0) stamp(a.trace, 3, li, 1 + op);
       }
     }
   } else if (warp == 1) {
@@ -378,12 +410,22 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         const uint32_t tiles = base + L.tiles + buf * buf_bytes;
         const bool more = it + (int)gridDim.x < n_items;
         mbar_wait_sleep(bar(OP_FULL + 4 * buf + 2), par);                     // V of this item
+        stamp(a.trace, 0, li, 0);
         for (int t = 0; t < ntiles; t++, uses++) {
-          mbar_wait_sleep(bar(P_FULL + t), li & 1u);
+          const int k1 = split(t) >> 4, k2 = ncols(t) >> 4;
+          mbar_wait_sleep(bar(P_FULL + 2 * t), li & 1u);
+          stamp(a.trace, 0, li, 1 + 6 * t);
           if (uses > 0) mbar_wait_sleep(bar(O_FREE), (uses - 1) & 1u);        // the previous tile's epilogue has drained O
+          stamp(a.trace, 0, li, 2 + 6 * t);
           tc_fence_after();
-          mma_av_cat(tO, tS[t], tiles + 4 * L.tile_bytes, L.tile_bytes, 0, ncols(t) >> 4, idesc64, 0);
+          mma_av_cat(tO, tS[t], tiles + 4 * L.tile_bytes, L.tile_bytes, 0, k1, idesc64, 0);
+          stamp(a.trace, 0, li, 3 + 6 * t);
+          mbar_wait_sleep(bar(P_FULL + 2 * t + 1), li & 1u);
+          stamp(a.trace, 0, li, 4 + 6 * t);
+          tc_fence_after();
+          if (k2 > k1) mma_av_cat(tO, tS[t] + 16 * k1, tiles + 4 * L.tile_bytes, L.tile_bytes, 16 * k1, k2 - k1, idesc64, 1);
           tc_commit(bar(O_FULL + t));
+          stamp(a.trace, 0, li, 5 + 6 * t);
           if (more) {
             // the S tile is free as soon as the product above has consumed P (in-order execution): next item's scores
             if (t == 0) {
@@ -395,14 +437,15 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
             }
             issue_scores(li + 1, t);
           }
+          stamp(a.trace, 0, li, 6 + 6 * t);
         }
         tc_commit(bar(OP_EMPTY + buf));        // every MMA that reads this item's operand buffer has been issued
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= MATH0) {
     // ================= softmax + epilogue: warpgroup t owns query tile t =================
-    const int t = (warp - 8) >> 2;
-    const int row = tid - 256 - 128 * t;            // TMEM lane
+    const int t = (warp - MATH0) >> 2;
+    const int row = tid - 32 * MATH0 - 128 * t;     // TMEM lane
     const int qi = 128 * t + row;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const float c1 = a.scale * LOG2E;
@@ -417,11 +460,16 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         mbar_wait_sleep(bar(OP_FULL + 4 * buf + 1), (li >> 1) & 1u);     // K converted => the key bias is written
         mbar_wait_sleep(bar(S_FULL + t), li & 1u);
         tc_fence_after();
+        if (row == 0) stamp(a.trace, 1 + t, li, 0);
         float m = -INFINITY, l = 0.f;
         if (!idle) {
-          // pass 1: row maximum of the masked, scaled logits (log2 domain).  Two register buffers alternate so that
-          // the next chunk's TMEM load is in flight while this one is reduced.
+          // TMEM -> register reads run at 64 B/clk per SM (B300_MICROARCH.md "LDTM throughput"; confirmed by the phase
+          // trace profiles/r2_a8_trace.log: 32-column loads with two in flight took exactly as long as 16-column ones),
+          // i.e. 1.7 k clk per 128 x 208 fp32 tile and pass whatever the access pattern: the passes below are bound by
+          // that, not by latency or issue slots.  16-column chunks, two register buffers alternating.
+          const uint32_t tRow = tS[t] + lane_off;
           uint32_t ra[16], rb[16];
+          // pass 1: row maximum of the masked, scaled logits (log2 domain)
           auto max16 = [&](const uint32_t (&r)[16], int c0) {
             if (CAUSAL && c0 + 15 > qw) {
 #pragma unroll
@@ -435,17 +483,18 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
               for (int j = 0; j < 16; j++) m = fmaxf(m, fmaf(__uint_as_float(r[j]), c1, bias_s[c0 + j]));
             }
           };
-          tmem_ld16(tS[t] + lane_off, ra);
+          tmem_ld16(tRow, ra);
           for (int c0 = 0; c0 < nc; c0 += 32) {
             tmem_ld_wait();
-            if (c0 + 16 < nc) tmem_ld16(tS[t] + lane_off + c0 + 16, rb);
+            if (c0 + 16 < nc) tmem_ld16(tRow + c0 + 16, rb);
             max16(ra, c0);
             if (c0 + 16 < nc) {
               tmem_ld_wait();
-              if (c0 + 32 < nc) tmem_ld16(tS[t] + lane_off + c0 + 32, ra);
+              if (c0 + 32 < nc) tmem_ld16(tRow + c0 + 32, ra);
               max16(rb, c0 + 16);
             }
           }
+          if (row == 0) stamp(a.trace, 1 + t, li, 1);
           // pass 2: p = 2^(t - m), row sum, P -> packed bf16 hi / lo over the S columns of the same 16 keys
           auto soft16 = [&](const uint32_t (&r)[16], int c0) {
             float p[16];
@@ -466,27 +515,45 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
               }
             }
             split16(p, w);
-            tmem_st16(tS[t] + lane_off + c0, w);
+            tmem_st16(tRow + c0, w);
           };
-          tmem_ld16(tS[t] + lane_off, ra);
+          const int sp = split(t);
+          tmem_ld16(tRow, ra);
           for (int c0 = 0; c0 < nc; c0 += 32) {
+            if (c0 == sp) {                 // part 0 is complete: hand it to the tensor core
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(P_FULL + 2 * t));
+            }
             tmem_ld_wait();
-            if (c0 + 16 < nc) tmem_ld16(tS[t] + lane_off + c0 + 16, rb);
+            if (c0 + 16 < nc) tmem_ld16(tRow + c0 + 16, rb);
             soft16(ra, c0);
             if (c0 + 16 < nc) {
               tmem_ld_wait();
-              if (c0 + 32 < nc) tmem_ld16(tS[t] + lane_off + c0 + 32, ra);
+              if (c0 + 32 < nc) tmem_ld16(tRow + c0 + 32, ra);
               soft16(rb, c0 + 16);
             }
           }
           tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (sp >= nc) mbar_arrive(bar(P_FULL + 2 * t));
+            mbar_arrive(bar(P_FULL + 2 * t + 1));
+          }
+        } else {
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar(P_FULL + 2 * t));
+            mbar_arrive(bar(P_FULL + 2 * t + 1));
+          }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(P_FULL + t));
         // epilogue: O = (P Vh + P Vl) / l
+        if (row == 0) stamp(a.trace, 1 + t, li, 2);
         mbar_wait_sleep(bar(O_FULL + t), li & 1u);
         tc_fence_after();
+        if (row == 0) stamp(a.trace, 1 + t, li, 3);
         uint32_t o0[32], o1[32];
         if (!idle) {
           tmem_ld32(tO + lane_off, o0);
@@ -507,6 +574,7 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
                                  (__uint_as_float(o0[4 * j + 3]) + __uint_as_float(o1[4 * j + 3])) * inv);
           if (a.out1) a.out1[((int64_t)b * a.H + h) * a.Tq + qi] = m * 0.6931471805599453f + logf(l);
         }
+        if (row == 0) stamp(a.trace, 1 + t, li, 4);
       }
     }
   }
@@ -546,7 +614,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
   prologue(c, smem_raw);
   const int QP = (a.Tq + 15) & ~15, KP = (a.Tk + 15) & ~15, TP = QP > KP ? QP : KP;
   constexpr int NTILES = DKV ? 12 : 10;
-  const Smem L = smem_plan(TP, NTILES, DKV ? 6 : 4);
+  const Smem L = smem_plan(TP, NTILES, DKV ? 6 : 4, a.nst);
   const int tid = c.tid, warp = c.warp, lane = c.lane;
   const uint32_t base = c.base;
   uint8_t* gen = c.gen;
@@ -609,8 +677,8 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       if (!DKV) prefetch_tmap(&mO);
       uint32_t n = 0;
       auto load = [&](const CUtensorMap* m, int h, int row, int b) {
-        const int st = n % NST;
-        mbar_wait_sleep(bar(RING_EMPTY + st), ((n / NST) & 1u) ^ 1u);
+        const int st = n % a.nst;
+        mbar_wait_sleep(bar(RING_EMPTY + st), ((n / a.nst) & 1u) ^ 1u);
         mbar_arrive_expect_tx(bar(RING_FULL + st), STAGE_BYTES);
         tma_load_3d(base + L.ring + st * STAGE_BYTES, m, bar(RING_FULL + st), h * DH, row, b);
         n++;
@@ -666,8 +734,8 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         for (int ch = 0; ch < nch; ch++, n++) {
           // single-buffered operands: the previous item's score MMAs (their only readers) have completed
           if (first_sb && ch == 0) mbar_wait_sleep(bar(SB_EMPTY), (li & 1u) ^ 1u);
-          const int st = n % NST;
-          mbar_wait_sleep(bar(RING_FULL + st), (n / NST) & 1u);
+          const int st = n % a.nst;
+          mbar_wait_sleep(bar(RING_FULL + st), (n / a.nst) & 1u);
           convert_stage<false>(gen + L.ring + st * STAGE_BYTES, hi, lo, 64 * ch, TP, ct);
           fence_proxy_async();
           __syncwarp();
@@ -686,9 +754,9 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         uint8_t* hi = gen + L.tiles + slot(3, buf) * L.tile_bytes;
         uint8_t* lo = hi + L.tile_bytes;
         for (int ch = 0; ch < nq_ch; ch++, n += 2) {
-          const int s0 = n % NST, s1 = (n + 1) % NST;
-          mbar_wait_sleep(bar(RING_FULL + s0), (n / NST) & 1u);
-          mbar_wait_sleep(bar(RING_FULL + s1), ((n + 1) / NST) & 1u);
+          const int s0 = n % a.nst, s1 = (n + 1) % a.nst;
+          mbar_wait_sleep(bar(RING_FULL + s0), (n / a.nst) & 1u);
+          mbar_wait_sleep(bar(RING_FULL + s1), ((n + 1) / a.nst) & 1u);
           convert_stage<true>(gen + L.ring + s1 * STAGE_BYTES, hi, lo, 64 * ch, TP, ct, gen + L.ring + s0 * STAGE_BYTES,
                               del_s, a.out1 ? a.out1 + bh * a.Tq : nullptr, a.Tq);
           fence_proxy_async();
@@ -769,10 +837,10 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= MATH0) {
     // ================= math: warpgroup w owns column half w =================
-    const int w = (warp - 8) >> 2;
-    const int row = tid - 256 - 128 * w;            // TMEM lane
+    const int w = (warp - MATH0) >> 2;
+    const int row = tid - 32 * MATH0 - 128 * w;     // TMEM lane
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const float c1 = a.scale * LOG2E;
     const uint32_t tS = tmem + MAXT * w, tP = tS + HALF;
@@ -918,6 +986,13 @@ int attn3_supported(const float* Q, int64_t ldq, const float* K, int64_t ldk, co
   return 1;
 }
 
+int g_a3_trace = 0;
+int attn3_trace_dump(long long* out, int n) {
+  if (n > 4 * 8 * 16) n = 4 * 8 * 16;
+  SKF_CUDA(cudaMemcpyFromSymbol(out, a3::g_trace, sizeof(long long) * n));
+  return n;
+}
+
 static int a3_sm_count() {
   static int n = 0;
   if (!n) {
@@ -927,6 +1002,14 @@ static int a3_sm_count() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+// as many ring stages (8 KB each, 4..NST) as fit beside the operand tiles in 227 KB of shared memory: the ring is the
+// only data in flight from HBM, and at ~2 us per TMA round trip under load 32 KB per SM starve the kernels
+static int a3_ring_stages(int TP, int ntiles, int nvec) {
+  const int limit = 227 * 1024 - 1024;
+  int nst = a3::NST;
+  while (nst > 4 && (int)a3::smem_plan(TP, ntiles, nvec, nst).total > limit) nst--;
+  return nst;
 }
 template <class Kern>
 static int a3_attr(Kern k, int bytes) {
@@ -951,9 +1034,11 @@ int attn3_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   a3::Args a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.mode = mode; a.scale = 1.0f / sqrtf((float)dh);
+  a.trace = g_a3_trace;
   a.key_pad = key_pad; a.out0 = O; a.ld0 = ldo; a.out1 = lse;
   const int QP = (Tq + 15) & ~15, KP = (Tk + 15) & ~15, TP = QP > KP ? QP : KP;
-  const int smem = (int)a3::smem_plan(TP, 12, 2).total + 1024;
+  a.nst = a3_ring_stages(TP, 12, 2);
+  const int smem = (int)a3::smem_plan(TP, 12, 2, a.nst).total + 1024;
   const int grid = B * H < a3_sm_count() ? B * H : a3_sm_count();
   if (mode == 2) {
     SKF_TRY(a3_attr(a3::attn3_fwd_k<true>, smem));
@@ -992,7 +1077,8 @@ int attn3_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   const int grid = B * H < a3_sm_count() ? B * H : a3_sm_count();
   {
     a.out0 = dQ; a.ld0 = lddq; a.out1 = delta; a.delta = nullptr;
-    const int smem = (int)a3::smem_plan(TP, 10, 4).total + 1024;
+    a.nst = a3_ring_stages(TP, 10, 4);
+    const int smem = (int)a3::smem_plan(TP, 10, 4, a.nst).total + 1024;
     if (mode == 2) {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<false, true>, smem));
       a3::attn3_bwd_k<false, true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, a);
@@ -1004,7 +1090,8 @@ int attn3_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   }
   {
     a.out0 = dK; a.ld0 = lddk; a.out1 = dV; a.ld1 = lddv; a.delta = delta;
-    const int smem = (int)a3::smem_plan(TP, 12, 6).total + 1024;
+    a.nst = a3_ring_stages(TP, 12, 6);
+    const int smem = (int)a3::smem_plan(TP, 12, 6, a.nst).total + 1024;
     if (mode == 2) {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<true, true>, smem));
       a3::attn3_bwd_k<true, true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, a);

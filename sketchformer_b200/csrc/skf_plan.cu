@@ -44,6 +44,8 @@ int attn3_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_
 int attn3_bwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
               const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
               const uint8_t*, int, int, int, int, int, int, cudaStream_t);
+extern int g_a3_trace;
+int attn3_trace_dump(long long*, int);
 int g_attn3 = 3;           // bit 0 / bit 1: head dim 32 and sequences up to 224 run the warp-specialised whole-row forward /
                            // backward kernels (skf_attn_tc3.cu)
 int attn2_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
@@ -1316,6 +1318,10 @@ int skf_set_option(const char* name, int value) {
     skf::g_gemm_wsplit = value ? 1 : 0;
     return SKF_OK;
   }
+  if (name && strcmp(name, "attn3_trace") == 0) {
+    skf::g_a3_trace = value;
+    return SKF_OK;
+  }
   if (name && strcmp(name, "attn3") == 0) {
     skf::g_attn3 = value & 3;
     return SKF_OK;
@@ -1533,6 +1539,11 @@ int skf_decode_steps(skf_plan* P, int first_step, int n_steps, void* stream) {
 }
 
 int64_t skf_plan_launches(const skf_plan* P) { return P ? P->launches : 0; }
+
+int skf_debug_trace(int64_t* out, int n) {
+  SKF_REQUIRE(out != nullptr && n > 0, SKF_ERR_BAD_ARG, "debug_trace: bad argument");
+  return skf::attn3_trace_dump(reinterpret_cast<long long*>(out), n);
+}
 
 int skf_grad_buckets(const skf_cfg* cfg, int n_buckets, int64_t* lo, int64_t* hi) {
   SKF_TRY(check_cfg(cfg));
