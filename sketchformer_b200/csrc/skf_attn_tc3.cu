@@ -113,6 +113,14 @@ __device__ __forceinline__ void split_pair_int(float a, float b, uint32_t& hi, u
   const float la = a - __uint_as_float(ua & 0xFFFF0000u), lb = b - __uint_as_float(ub & 0xFFFF0000u);
   lo = __byte_perm(__float_as_uint(la) + 0x8000u, __float_as_uint(lb) + 0x8000u, 0x7632);
 }
+// Operand tiles (converter warps): the same on the integer pipe with hi ROUNDED (half-up on the magnitude), so that the
+// residual is unbiased and at most 2^-9 |x| and the dropped lo * lo term stays at 2^-18 of a product.
+__device__ __forceinline__ void split_pair_rn(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
+  hi = __byte_perm(ua, ub, 0x7632);
+  const float la = a - __uint_as_float(ua & 0xFFFF0000u), lb = b - __uint_as_float(ub & 0xFFFF0000u);
+  lo = __byte_perm(__float_as_uint(la) + 0x8000u, __float_as_uint(lb) + 0x8000u, 0x7632);
+}
 // 16 fp32 values -> 8 packed hi words followed by 8 packed lo words (the A operand of one K = 16 MMA step, twice)
 __device__ __forceinline__ void split16(const float (&p)[16], uint32_t (&w)[16]) {
 #pragma unroll
@@ -146,10 +154,10 @@ __device__ __forceinline__ void convert_stage(const uint8_t* stage, uint8_t* hi,
         dot = (u.x * p.x + u.y * p.y) + (u.z * p.z + u.w * p.w) + (v.x * q.x + v.y * q.y) + (v.z * q.z + v.w * q.w);
       }
       uint4 h, l;
-      split_pair(u.x, u.y, h.x, l.x);
-      split_pair(u.z, u.w, h.y, l.y);
-      split_pair(v.x, v.y, h.z, l.z);
-      split_pair(v.z, v.w, h.w, l.w);
+      split_pair_rn(u.x, u.y, h.x, l.x);
+      split_pair_rn(u.z, u.w, h.y, l.y);
+      split_pair_rn(v.x, v.y, h.z, l.z);
+      split_pair_rn(v.z, v.w, h.w, l.w);
       const uint32_t dof = R * 64 + ((g ^ ((R >> 1) & 3)) << 4);
       *reinterpret_cast<uint4*>(hi + dof) = h;
       *reinterpret_cast<uint4*>(lo + dof) = l;
@@ -165,11 +173,36 @@ __device__ __forceinline__ void convert_stage(const uint8_t* stage, uint8_t* hi,
   }
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONV * 32) : "memory"); }
+
 // Optional phase trace (skf_set_option("attn3_trace", 1)): CTA 0 stamps clock64() at the phase boundaries of its first
 // 8 items, role by role; tools/attn_trace.py prints the deltas.  [role][item][16 stamps]
 __device__ long long g_trace[4 * 8 * 16];
 __device__ __forceinline__ void stamp(int on, int role, uint32_t li, int k) {
   if (on && blockIdx.x == 0 && li < 8) g_trace[(role * 8 + li) * 16 + k] = clock64();
+}
+
+// Effective key length of an item: 1 + the index of its last unpadded key (Tk without a padding mask, or when every
+// key is padded — then the reference's softmax over equally shifted logits is uniform and no column may be dropped).
+// Keys past it get exactly zero weight in fp32 (exp(x - 1e9 - max) with a finite max), so the kernels skip their
+// columns (fwd / dq) and their lane tiles (dkv) altogether; padded keys BEFORE it keep the additive -1e9.
+// Computed redundantly by every converter warp (a handful of byte loads per lane); returns the warp-uniform value.
+__device__ __forceinline__ int effective_klen(const uint8_t* key_pad, int mode, int64_t row_off, int Tk, int lane) {
+  if (mode < 1 || key_pad == nullptr) return Tk;
+  int last = 0;
+  for (int j = lane; j < Tk; j += 32)
+    if (!key_pad[row_off + j]) last = j + 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  return last == 0 ? Tk : last;
 }
 
 struct Args {
@@ -184,6 +217,11 @@ struct Args {
   int64_t ld1;
   const float* lse;           // dq / dkv: logsumexp of the forward pass [B, H, Tq]
   const float* delta;         // dkv: rowsum(dO * O) [B, H, Tq] (written by dq)
+  // bf16 hi / lo operand images in HBM, one contiguous [TP x 32] tile per (operand, hi|lo, item): the forward kernel
+  // writes those of Q, K, V from its shared-memory tiles (img != 0), dq writes those of dO (img_do != 0), and the
+  // backward kernels TMA-load them straight into their operand slots instead of pulling fp32 rows through the ring and
+  // the converter warps again (direct != 0).  Tile row of (op, hl, item) in the image map: ((2 op + hl) n_items + item) TP
+  int img, img_do, direct;
 };
 
 // D[128 x N] = Ah Bh^T + Ah Bl^T + Al Bh^T: A rows [a_row0, +128) of the K-major tiles (ah, al), B rows [b_row0, +N)
@@ -202,11 +240,12 @@ __device__ __forceinline__ void mma_scores(uint32_t d, uint32_t ah, uint32_t al,
 // second MMA is 2^-18 of the product and harmless
 __device__ __forceinline__ void mma_av_cat(uint32_t d, uint32_t a_tmem, uint32_t bh, uint32_t chunk, int b_row0,
                                            int ksteps, uint32_t idesc64, uint32_t accumulate) {
-  uint32_t acc = accumulate;
-  for (int s = 0; s < ksteps; s++) {
-    const uint64_t bd = desc16_mn(bh + (uint32_t)(b_row0 + 16 * s) * 64, chunk);
-    mma_ts(d, a_tmem + 16 * s, bd, idesc64, acc);
-    mma_ts(d, a_tmem + 16 * s + 8, bd, idesc64, 1);
+  // the start-address field of a descriptor counts 16-byte units: one k-step (16 rows x 64 B) further = + 64
+  uint64_t bd = desc16_mn(bh + (uint32_t)b_row0 * 64, chunk);
+  uint32_t acc = accumulate, ta = a_tmem;
+  for (int s = 0; s < ksteps; s++, bd += 64, ta += 16) {
+    mma_ts(d, ta, bd, idesc64, acc);
+    mma_ts(d, ta + 8, bd, idesc64, 1);
     acc = 1;
   }
 }
@@ -214,20 +253,19 @@ __device__ __forceinline__ void mma_av_cat(uint32_t d, uint32_t a_tmem, uint32_t
 // concatenated form)
 __device__ __forceinline__ void mma_av_32(uint32_t d, uint32_t a_tmem, uint32_t bh, uint32_t bl, int b_row0, int ksteps,
                                           uint32_t idesc32, uint32_t accumulate) {
-  uint32_t acc = accumulate;
-  for (int s = 0; s < ksteps; s++) {
-    const uint32_t off = (uint32_t)(b_row0 + 16 * s) * 64;
-    const uint64_t bhd = desc16_mn(bh + off, 0), bld = desc16_mn(bl + off, 0);
-    mma_ts(d, a_tmem + 16 * s, bhd, idesc32, acc);
-    mma_ts(d, a_tmem + 16 * s + 8, bhd, idesc32, 1);
-    mma_ts(d, a_tmem + 16 * s, bld, idesc32, 1);
+  uint64_t bhd = desc16_mn(bh + (uint32_t)b_row0 * 64, 0), bld = desc16_mn(bl + (uint32_t)b_row0 * 64, 0);
+  uint32_t acc = accumulate, ta = a_tmem;
+  for (int s = 0; s < ksteps; s++, bhd += 64, bld += 64, ta += 16) {
+    mma_ts(d, ta, bhd, idesc32, acc);
+    mma_ts(d, ta + 8, bhd, idesc32, 1);
+    mma_ts(d, ta, bld, idesc32, 1);
     acc = 1;
   }
 }
 
 // shared-memory plan (offsets from the 1024-aligned base): ring | ntiles operand tiles | 1 KB zero pad | vectors | barriers
 struct Smem {
-  uint32_t ring, tiles, vec, bars;
+  uint32_t ring, tiles, vec, meta, bars;
   uint32_t tile_bytes;          // one bf16 tile: TP x 64 bytes
   uint32_t total;
 };
@@ -237,7 +275,8 @@ __host__ __device__ inline Smem smem_plan(int TP, int ntiles, int nvec, int nst)
   s.tiles = nst * STAGE_BYTES;
   s.tile_bytes = (uint32_t)TP * 64;
   s.vec = s.tiles + s.tile_bytes * ntiles + 4096;   // 4 KB pad: M = 128 / N reads past the last tile stay inside
-  s.bars = s.vec + nvec * 256 * 4;
+  s.meta = s.vec + nvec * 256 * 4;                  // per-buffer item facts (effective key length)
+  s.bars = s.meta + 64;
   s.total = s.bars + 64 * 8 + 16;
   return s;
 }
@@ -282,7 +321,7 @@ enum { RING_FULL = 0, RING_EMPTY = NST, OP_FULL = 2 * NST /* [2 bufs][4] */, OP_
 template <bool CAUSAL>
 __global__ void __launch_bounds__(THREADS, 1)
 attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
-            const __grid_constant__ CUtensorMap mV, const Args a) {
+            const __grid_constant__ CUtensorMap mV, const __grid_constant__ CUtensorMap mImg, const Args a) {
   using namespace fw;
   extern __shared__ uint8_t smem_raw[];
   Ctx c;
@@ -322,14 +361,15 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
   const uint32_t tmem = c.tmem;
   const uint32_t tS[2] = {tmem, tmem + MAXT}, tO = tmem + 2 * MAXT;
   // key columns a query tile needs: causal tiles never look past their last row
-  auto ncols = [&](int t) {
-    int n = a.Tk;
+  volatile int* klen_s = reinterpret_cast<volatile int*>(gen + L.meta);      // [2 buffers]
+  auto ncols = [&](int t, int klen) {
+    int n = klen;
     if (CAUSAL) n = min(n, 128 * t + 128);
     return (n + 15) & ~15;
   };
   // P is handed to the tensor core in two column parts so that the first part's P V MMAs run under the softmax of
-  // the second: part 0 = columns [0, split(t)), a multiple of 32
-  auto split = [&](int t) { return min(ncols(t), ((ncols(t) + 63) >> 6) << 5); };
+  // the second: part 0 = columns [0, split(nc)), a multiple of 32
+  auto split = [&](int nc) { return min(nc, ((nc + 63) >> 6) << 5); };
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -359,7 +399,15 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       uint8_t* tiles = gen + L.tiles + buf * buf_bytes;
       // the MMAs of the item that used this buffer two items ago have completed
       mbar_wait_sleep(bar(OP_EMPTY + buf), ((li >> 1) & 1u) ^ 1u);
+      if (a.img) {                 // ... and the image stores of the earlier items have read their tiles
+        if (ct == 0) bulk_wait_read0();
+        conv_bar_sync();
+      }
       if (ct == 0) stamp(a.trace, 3, li, 0);
+      {
+        const int kl = effective_klen(a.key_pad, a.mode, (int64_t)b * a.Tk, a.Tk, lane);
+        if (ct == 0) klen_s[buf] = kl;
+      }
       // key bias of this item (log2 domain): -inf past the sequence, the reference's additive -1e9 on padded keys
       float* bias_s = reinterpret_cast<float*>(gen + L.vec) + buf * 256;
       for (int j = ct; j < 256; j += NCONV * 32) {
@@ -384,8 +432,17 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           }
         }
         if (ct == 0) stamp(a.trace, 3, li, 1 + op);
+        if (a.img && ct == 0) {
+          // every converter warp has finished (and fenced) this operand's tiles: write them out for the backward pass
+          mbar_wait_sleep(bar(OP_FULL + 4 * buf + op), (li >> 1) & 1u);
+          const int fop = op == 0 ? 1 : (op == 1 ? 0 : 2);          // image order K, Q, V (the backward kernels' op index)
+          tma_store_2d(&mImg, smem_u32(hi), 0, ((2 * fop) * n_items + it) * TP);
+          tma_store_2d(&mImg, smem_u32(lo), 0, ((2 * fop + 1) * n_items + it) * TP);
+          bulk_commit();
+        }
       }
     }
+    if (a.img && ct == 0) bulk_wait0();
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
@@ -394,7 +451,7 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       auto issue_scores = [&](uint32_t item_li, int t) {
         const uint32_t tiles = base + L.tiles + (item_li & 1) * buf_bytes;
         mma_scores(tS[t], tiles, tiles + L.tile_bytes, tiles + 2 * L.tile_bytes, tiles + 3 * L.tile_bytes, 128 * t, 0,
-                   idesc_bf16(128, ncols(t), 0));
+                   idesc_bf16(128, ncols(t, klen_s[item_li & 1]), 0));
         tc_commit(bar(S_FULL + t));
       };
       const int first = blockIdx.x;
@@ -411,8 +468,9 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         const bool more = it + (int)gridDim.x < n_items;
         mbar_wait_sleep(bar(OP_FULL + 4 * buf + 2), par);                     // V of this item
         stamp(a.trace, 0, li, 0);
+        const int klen = klen_s[buf];
         for (int t = 0; t < ntiles; t++, uses++) {
-          const int k1 = split(t) >> 4, k2 = ncols(t) >> 4;
+          const int k1 = split(ncols(t, klen)) >> 4, k2 = ncols(t, klen) >> 4;
           mbar_wait_sleep(bar(P_FULL + 2 * t), li & 1u);
           stamp(a.trace, 0, li, 1 + 6 * t);
           if (uses > 0) mbar_wait_sleep(bar(O_FREE), (uses - 1) & 1u);        // the previous tile's epilogue has drained O
@@ -449,7 +507,6 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     const int qi = 128 * t + row;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const float c1 = a.scale * LOG2E;
-    const int nc = ncols(t);
     const int qw = 128 * t + (warp & 3) * 32;       // first query row of this warp
     const bool idle = qw >= a.Tq;                   // no valid row in this warp: only the barrier protocol
     if (t < ntiles) {
@@ -457,7 +514,8 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, li++) {
         const int b = it / a.H, h = it % a.H, buf = li & 1;
         const float* bias_s = reinterpret_cast<const float*>(gen + L.vec) + buf * 256;
-        mbar_wait_sleep(bar(OP_FULL + 4 * buf + 1), (li >> 1) & 1u);     // K converted => the key bias is written
+        mbar_wait_sleep(bar(OP_FULL + 4 * buf + 1), (li >> 1) & 1u);     // K converted => key bias and length are written
+        const int nc = ncols(t, klen_s[buf]);
         mbar_wait_sleep(bar(S_FULL + t), li & 1u);
         tc_fence_after();
         if (row == 0) stamp(a.trace, 1 + t, li, 0);
@@ -517,7 +575,7 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
             split16(p, w);
             tmem_st16(tRow + c0, w);
           };
-          const int sp = split(t);
+          const int sp = split(nc);
           tmem_ld16(tRow, ra);
           for (int c0 = 0; c0 < nc; c0 += 32) {
             if (c0 == sp) {                 // part 0 is complete: hand it to the tensor core
@@ -600,14 +658,15 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
 namespace bw {
 enum { RING_FULL = 0, RING_EMPTY = NST, OP_FULL = 2 * NST /* [2 bufs][4 ops] */, DB_EMPTY = 2 * NST + 8 /* [2] */,
        SB_EMPTY = 2 * NST + 10, SP_FULL = 2 * NST + 11 /* [2] */, DS_FULL = 2 * NST + 13 /* [2] */,
-       ACC_FULL = 2 * NST + 15, ACC_FREE = 2 * NST + 16, COUNT = 2 * NST + 17 };
+       ACC_FULL = 2 * NST + 15, ACC_FREE = 2 * NST + 16, VEC_FULL = 2 * NST + 17 /* [2] */, COUNT = 2 * NST + 19 };
 }
 
 template <bool DKV, bool CAUSAL>
 __global__ void __launch_bounds__(THREADS, 1)
 attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK,
             const __grid_constant__ CUtensorMap mV, const __grid_constant__ CUtensorMap mdO,
-            const __grid_constant__ CUtensorMap mO, const Args a) {
+            const __grid_constant__ CUtensorMap mO, const __grid_constant__ CUtensorMap mImg,
+            const __grid_constant__ CUtensorMap mImgDo, const Args a) {
   using namespace bw;
   extern __shared__ uint8_t smem_raw[];
   Ctx c;
@@ -643,8 +702,12 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       mbar_init(bar(RING_FULL + i), 1);
       mbar_init(bar(RING_EMPTY + i), NCONV);
     }
-    for (int b = 0; b < 2; b++)
-      for (int op = 0; op < 4; op++) mbar_init(bar(OP_FULL + 4 * b + op), NCONV * nch_of(op));
+    // operands that arrive as images by one TMA transaction (direct mode: all but dO in dq) count a single arrival
+    for (int b = 0; b < 2; b++) {
+      for (int op = 0; op < 4; op++)
+        mbar_init(bar(OP_FULL + 4 * b + op), (a.direct && (DKV || op != 3)) ? 1 : NCONV * nch_of(op));
+      mbar_init(bar(VEC_FULL + b), NCONV);
+    }
     mbar_init(bar(DB_EMPTY + 0), 1);
     mbar_init(bar(DB_EMPTY + 1), 1);
     mbar_init(bar(SB_EMPTY), 1);
@@ -661,14 +724,18 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
   const uint32_t tmem = c.tmem;
   const uint32_t tAcc = tmem + 2 * MAXT;
   // columns unit (lane tile t, half w) covers: [HALF w, HALF w + ncols)
-  auto ncols = [&](int t, int w) {
-    int hi = TC;
+  volatile int* klen_s = reinterpret_cast<volatile int*>(gen + L.meta);      // [2 buffers]
+  auto ncols = [&](int t, int w, int klen) {
+    int hi = DKV ? TC : min(TC, klen);                   // dq: key columns past the effective length carry p = 0
     if (CAUSAL && !DKV) hi = min(hi, 128 * t + 128);     // queries of tile t see keys <= their own index
     int n = hi - HALF * w;
     n = n < 0 ? 0 : (n > HALF ? HALF : n);
     n = (n + 15) & ~15;
     return n < 16 ? 16 : n;
   };
+
+  // dkv: key tile 1 (keys 128..) of an item whose effective length is <= 128 has zero gradients: not computed
+  auto tiles_of = [&](int klen) { return (DKV && klen <= 128) ? 1 : ntiles; };
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -683,8 +750,37 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         tma_load_3d(base + L.ring + st * STAGE_BYTES, m, bar(RING_FULL + st), h * DH, row, b);
         n++;
       };
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      uint32_t pli = 0;
+      // direct mode: one [TP x 32] hi tile and one lo tile per operand, straight into the operand slot
+      auto load_img = [&](const CUtensorMap* m, int op, int buf, int it, int tile_op) {
+        const uint32_t dst = base + L.tiles + slot(op, buf) * L.tile_bytes;
+        mbar_arrive_expect_tx(bar(OP_FULL + 4 * buf + op), 2 * L.tile_bytes);
+        tma_load_2d(dst, m, bar(OP_FULL + 4 * buf + op), 0, ((2 * tile_op) * n_items + it) * TP);
+        tma_load_2d(dst + L.tile_bytes, m, bar(OP_FULL + 4 * buf + op), 0, ((2 * tile_op + 1) * n_items + it) * TP);
+      };
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, pli++) {
         const int b = it / a.H, h = it % a.H;
+        if (a.direct) {
+          const int buf = pli & 1;
+          mbar_wait_sleep(bar(DB_EMPTY + buf), ((pli >> 1) & 1u) ^ 1u);
+          if (!DKV) {
+            load_img(&mImg, 0, buf, it, 0);                                  // K (double-buffered)
+            mbar_wait_sleep(bar(SB_EMPTY), (pli & 1u) ^ 1u);
+            load_img(&mImg, 1, buf, it, 1);                                  // Q
+            load_img(&mImg, 2, buf, it, 2);                                  // V
+            for (int ch = 0; ch < nq_ch; ch++) {                             // (O, dO) pairs through the ring
+              load(&mO, h, 64 * ch, b);
+              load(&mdO, h, 64 * ch, b);
+            }
+          } else {
+            load_img(&mImg, 1, buf, it, 1);                                  // Q  (double-buffered)
+            load_img(&mImgDo, 3, buf, it, 0);                                // dO (double-buffered)
+            mbar_wait_sleep(bar(SB_EMPTY), (pli & 1u) ^ 1u);
+            load_img(&mImg, 0, buf, it, 0);                                  // K
+            load_img(&mImg, 2, buf, it, 2);                                  // V
+          }
+          continue;
+        }
         // order = order of first use: dq K, Q, V, (O, dO) pairs; dkv Q, dO, K, V
         if (!DKV) {
           for (int ch = 0; ch < nk_ch; ch++) load(&mK, h, 64 * ch, b);
@@ -711,6 +807,11 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       const int64_t bh = (int64_t)b * a.H + h;
       // double-buffered operands + vectors of buffer `buf`: free once the item two back has issued its last MMA
       mbar_wait_sleep(bar(DB_EMPTY + buf), ((li >> 1) & 1u) ^ 1u);
+      if (ct == 0) stamp(a.trace, 3, li, 0);
+      {
+        const int kl = effective_klen(a.key_pad, a.mode, (int64_t)b * a.Tk, a.Tk, lane);
+        if (ct == 0) klen_s[buf] = kl;
+      }
       float* bias_s = vec + buf * 256;
       for (int j = ct; j < KP; j += NCONV * 32) {
         float bj = 0.f;
@@ -727,13 +828,19 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           del_s[j] = j < a.Tq ? a.delta[bh * a.Tq + j] : 0.f;
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(VEC_FULL + buf));
       auto conv = [&](int op, bool first_sb) {
         const int nch = nch_of(op);
         uint8_t* hi = gen + L.tiles + slot(op, buf) * L.tile_bytes;
         uint8_t* lo = hi + L.tile_bytes;
         for (int ch = 0; ch < nch; ch++, n++) {
           // single-buffered operands: the previous item's score MMAs (their only readers) have completed
-          if (first_sb && ch == 0) mbar_wait_sleep(bar(SB_EMPTY), (li & 1u) ^ 1u);
+          if (first_sb && ch == 0) {
+            if (ct == 0) stamp(a.trace, 3, li, 5);
+            mbar_wait_sleep(bar(SB_EMPTY), (li & 1u) ^ 1u);
+            if (ct == 0) stamp(a.trace, 3, li, 6);
+          }
           const int st = n % a.nst;
           mbar_wait_sleep(bar(RING_FULL + st), (n / a.nst) & 1u);
           convert_stage<false>(gen + L.ring + st * STAGE_BYTES, hi, lo, 64 * ch, TP, ct);
@@ -744,11 +851,22 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
             mbar_arrive(bar(RING_EMPTY + st));
           }
         }
+        if (ct == 0) stamp(a.trace, 3, li, 1 + op);
       };
+      if (DKV && a.direct) continue;          // every operand arrives as an image: only the vectors above
       if (!DKV) {
-        conv(0, false);          // K (double-buffered)
-        conv(1, true);           // Q
-        conv(2, false);          // V
+        if (!a.direct) {
+          conv(0, false);          // K (double-buffered)
+          conv(1, true);           // Q
+          conv(2, false);          // V
+        } else {
+          // dO is single-buffered: the previous item's score MMAs have completed, and its image store has read the tile
+          mbar_wait_sleep(bar(SB_EMPTY), (li & 1u) ^ 1u);
+          if (a.img_do) {
+            if (ct == 0) bulk_wait_read0();
+            conv_bar_sync();
+          }
+        }
         // (O, dO) chunk pairs: delta = rowsum(dO * O) from the fp32 values, dO -> tiles
         float* del_s = vec + 512 + buf * 256;
         uint8_t* hi = gen + L.tiles + slot(3, buf) * L.tile_bytes;
@@ -767,6 +885,13 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
             mbar_arrive(bar(RING_EMPTY + s1));
           }
         }
+        if (ct == 0) stamp(a.trace, 3, li, 4);
+        if (a.img_do && ct == 0) {             // dO images for dkv
+          mbar_wait_sleep(bar(OP_FULL + 4 * buf + 3), (li >> 1) & 1u);
+          tma_store_2d(&mImgDo, smem_u32(hi), 0, it * TP);
+          tma_store_2d(&mImgDo, smem_u32(lo), 0, (n_items + it) * TP);
+          bulk_commit();
+        }
       } else {
         conv(1, false);          // Q  (double-buffered)
         conv(3, false);          // dO (double-buffered)
@@ -774,6 +899,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         conv(2, false);          // V
       }
     }
+    if (!DKV && a.img_do && ct == 0) bulk_wait0();
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
@@ -782,7 +908,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       // score products of unit (item li, lane tile t, half w): S_w = L C^T, dP_w = Lg Cg^T
       auto issue_scores = [&](uint32_t item_li, int t, int w) {
         const int buf = item_li & 1;
-        const uint32_t idesc = idesc_bf16(128, ncols(t, w), 0);
+        const uint32_t idesc = idesc_bf16(128, ncols(t, w, klen_s[buf]), 0);
         const int opL = DKV ? 0 : 1, opLg = DKV ? 2 : 3, opC = DKV ? 1 : 0, opCg = DKV ? 3 : 2;
         const uint32_t Lh = tile_addr(opL, buf), Lgh = tile_addr(opLg, buf), Ch = tile_addr(opC, buf), Cgh = tile_addr(opCg, buf);
         mma_scores(tmem + MAXT * w, Lh, Lh + L.tile_bytes, Ch, Ch + L.tile_bytes, 128 * t, HALF * w, idesc);
@@ -793,6 +919,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         const int buf = item_li & 1;
         const uint32_t par = (item_li >> 1) & 1u;
         for (int op = 0; op < 4; op++) mbar_wait_sleep(bar(OP_FULL + 4 * buf + op), par);
+        mbar_wait_sleep(bar(VEC_FULL + buf), par);       // effective key length
         tc_fence_after();
       };
       const int first = blockIdx.x;
@@ -800,21 +927,25 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       if (first < n_items) {
         wait_item(0);
         for (int w = 0; w < nhalf; w++) issue_scores(0, 0, w);
-        if (ntiles == 1) tc_commit(bar(SB_EMPTY));
+        if (tiles_of(klen_s[0]) == 1) tc_commit(bar(SB_EMPTY));
       }
       for (int it = first; it < n_items; it += gridDim.x, li++) {
         const int buf = li & 1;
         const bool more = it + (int)gridDim.x < n_items;
-        for (int t = 0; t < ntiles; t++, u++) {
-          const bool last_tile = t + 1 == ntiles;
+        const int klen = klen_s[buf];
+        const int nt_item = tiles_of(klen);
+        for (int t = 0; t < nt_item; t++, u++) {
+          const bool last_tile = t + 1 == nt_item;
           const bool has_next = !last_tile || more;
           const uint32_t nli = last_tile ? li + 1 : li;
           const int nt = last_tile ? 0 : t + 1;
           for (int w = 0; w < nhalf; w++) {
             mbar_wait_sleep(bar(DS_FULL + w), u & 1u);
+            stamp(a.trace, 0, li, 6 * t + 3 * w);
             if (w == 0 && u > 0) mbar_wait_sleep(bar(ACC_FREE), (u - 1) & 1u);      // previous epilogue drained the accumulators
+            stamp(a.trace, 0, li, 6 * t + 3 * w + 1);
             tc_fence_after();
-            const int ks = ncols(t, w) >> 4;
+            const int ks = ncols(t, w, klen) >> 4;
             if (!DKV) {
               const uint32_t Kh = tile_addr(0, buf);
               mma_av_cat(tAcc, tmem + MAXT * w + HALF, Kh, L.tile_bytes, HALF * w, ks, idesc64, w > 0);
@@ -831,8 +962,9 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
               if (w == 0 && last_tile) wait_item(nli);
               issue_scores(nli, nt, w);
               // the single-buffered operands are free once the item's last score MMAs have completed
-              if (w == nhalf - 1 && nt == ntiles - 1) tc_commit(bar(SB_EMPTY));
+              if (w == nhalf - 1 && nt == tiles_of(klen_s[nli & 1]) - 1) tc_commit(bar(SB_EMPTY));
             }
+            stamp(a.trace, 0, li, 6 * t + 3 * w + 2);
           }
         }
       }
@@ -851,12 +983,32 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         const int64_t bh = (int64_t)b * a.H + h;
         const float* bias_s = vec + buf * 256;
         // vectors of this item are written before the converters arrive on these barriers
-        mbar_wait_sleep(bar(OP_FULL + 4 * buf + (DKV ? 1 : 0)), (li >> 1) & 1u);
+        mbar_wait_sleep(bar(VEC_FULL + buf), (li >> 1) & 1u);
         if (!DKV) mbar_wait_sleep(bar(OP_FULL + 4 * buf + 3), (li >> 1) & 1u);      // delta (with dO)
-        for (int t = 0; t < ntiles; t++, u++) {
+        const int klen = klen_s[buf];
+        const int nt_item = tiles_of(klen);
+        if (DKV && nt_item < ntiles) {
+          // skipped key tile: its dK / dV rows are exactly zero (warpgroup 0 writes dK, warpgroup 1 dV; with one
+          // column half, warpgroup 0 writes both)
+          const int kr = 128 + row;
+          if (kr < a.Tk) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (w == 0) {
+              float4* dst = reinterpret_cast<float4*>(a.out0 + ((int64_t)b * a.Tk + kr) * a.ld0 + h * DH);
+#pragma unroll
+              for (int j = 0; j < 8; j++) dst[j] = z;
+            }
+            if (w == 1 || nhalf == 1) {
+              float4* dst = reinterpret_cast<float4*>(a.out1 + ((int64_t)b * a.Tk + kr) * a.ld1 + h * DH);
+#pragma unroll
+              for (int j = 0; j < 8; j++) dst[j] = z;
+            }
+          }
+        }
+        for (int t = 0; t < nt_item; t++, u++) {
           const int li_row = 128 * t + row;           // sequence index of this lane (query for dq, key for dkv)
           const int lw = 128 * t + (warp & 3) * 32;   // first lane index of this warp
-          const int nc = ncols(t, w);
+          const int nc = ncols(t, w, klen);
           const int col0 = HALF * w;
           const bool idle = lw >= TL;
           float lane_bias = 0.f, lane_delta = 0.f, lane_lse2 = INFINITY;
@@ -872,6 +1024,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           const float* del_s = lse_s + 256;
           mbar_wait_sleep(bar(SP_FULL + w), u & 1u);
           tc_fence_after();
+          if (row == 0) stamp(a.trace, 1 + w, li, 4 * t);
           if (!idle) {
             uint32_t rs[16], rp[16];
             for (int c0 = 0; c0 < nc; c0 += 16) {
@@ -912,12 +1065,14 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(DS_FULL + w));
+          if (row == 0) stamp(a.trace, 1 + w, li, 4 * t + 1);
           // epilogue.  dq: warpgroup (t & 1) stores dQ of tile t; dkv: warpgroup 0 stores dK, warpgroup 1 dV
           // (with one column half, warpgroup 0 stores both)
           const bool my_epi = DKV ? true : (nhalf == 1 || (t & 1) == w);
           if (my_epi) {
             mbar_wait_sleep(bar(ACC_FULL), u & 1u);
             tc_fence_after();
+            if (row == 0) stamp(a.trace, 1 + w, li, 4 * t + 2);
             if (!DKV) {
               uint32_t o0[32], o1[32];
               if (!idle) {
@@ -1020,9 +1175,21 @@ static int a3_map(CUtensorMap* m, const float* p, int64_t ld, int H, int T, int 
   return make_tmap_3d_f32(m, p, (uint64_t)H * a3::DH, (uint64_t)T, (uint64_t)B, (uint64_t)ld, (uint64_t)T * ld, 32, 64);
 }
 
+int make_tmap_2d_any(CUtensorMap* out, const void* ptr, int dtype, int esize, uint64_t inner, uint64_t outer,
+                     uint64_t ld, uint32_t box_inner, uint32_t box_outer, int swizzle);
+// bytes of the image buffer of one attention site (Q, K, V: 6 tiles per item) / of the dO images (2 tiles per item)
+size_t attn3_image_bytes(int B, int H, int Tq, int Tk, int ntiles) {
+  const int QP = (Tq + 15) & ~15, KP = (Tk + 15) & ~15, TP = QP > KP ? QP : KP;
+  return (size_t)ntiles * B * H * TP * 64;
+}
+static int a3_img_map(CUtensorMap* m, const void* img, int ntiles, int n_items, int TP) {
+  return make_tmap_2d_any(m, img, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 32, (uint64_t)ntiles * n_items * TP, 32, 32,
+                          (uint32_t)TP, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
 int attn3_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, float* O,
               int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh, int mode,
-              cudaStream_t st) {
+              void* img, cudaStream_t st) {
   SKF_REQUIRE(attn3_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, dh), SKF_ERR_UNSUPPORTED, "attn3_fwd: shape");
   SKF_REQUIRE((ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, SKF_ERR_BAD_ALIGN, "attn3_fwd: O");
   SKF_REQUIRE(mode == 0 || key_pad != nullptr || mode == 2, SKF_ERR_BAD_ARG, "attn3_fwd: mode 1 needs key_pad");
@@ -1034,18 +1201,21 @@ int attn3_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   a3::Args a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.mode = mode; a.scale = 1.0f / sqrtf((float)dh);
-  a.trace = g_a3_trace;
+  a.trace = g_a3_trace == 1;
   a.key_pad = key_pad; a.out0 = O; a.ld0 = ldo; a.out1 = lse;
   const int QP = (Tq + 15) & ~15, KP = (Tk + 15) & ~15, TP = QP > KP ? QP : KP;
+  CUtensorMap mImg = mQ;
+  a.img = img != nullptr;
+  if (img) SKF_TRY(a3_img_map(&mImg, img, 6, B * H, TP));
   a.nst = a3_ring_stages(TP, 12, 2);
   const int smem = (int)a3::smem_plan(TP, 12, 2, a.nst).total + 1024;
   const int grid = B * H < a3_sm_count() ? B * H : a3_sm_count();
   if (mode == 2) {
     SKF_TRY(a3_attr(a3::attn3_fwd_k<true>, smem));
-    a3::attn3_fwd_k<true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, a);
+    a3::attn3_fwd_k<true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mImg, a);
   } else {
     SKF_TRY(a3_attr(a3::attn3_fwd_k<false>, smem));
-    a3::attn3_fwd_k<false><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, a);
+    a3::attn3_fwd_k<false><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mImg, a);
   }
   SKF_LAUNCH_CHECK();
   return SKF_OK;
@@ -1054,7 +1224,7 @@ int attn3_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
 int attn3_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, const float* O,
               int64_t ldo, const float* dO, int64_t lddo, const float* lse, float* delta, float* dQ, int64_t lddq,
               float* dK, int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad, int B, int H, int Tq, int Tk,
-              int dh, int mode, cudaStream_t st) {
+              int dh, int mode, const void* img, void* img_do, cudaStream_t st) {
   SKF_REQUIRE(attn3_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, dh), SKF_ERR_UNSUPPORTED, "attn3_bwd: shape");
   SKF_REQUIRE(((lddo | lddq | lddk | lddv | ldo) & 3) == 0 &&
                   ((reinterpret_cast<uintptr_t>(dO) | reinterpret_cast<uintptr_t>(dQ) | reinterpret_cast<uintptr_t>(dK) |
@@ -1075,29 +1245,38 @@ int attn3_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   a.key_pad = key_pad; a.lse = lse;
   const int QP = (Tq + 15) & ~15, KP = (Tk + 15) & ~15, TP = QP > KP ? QP : KP;
   const int grid = B * H < a3_sm_count() ? B * H : a3_sm_count();
+  // with the forward kernel's operand images (and room for dO's) the backward kernels load bf16 tiles directly
+  CUtensorMap mImg = mQ, mImgDo = mQ;
+  a.direct = img != nullptr && img_do != nullptr;
+  if (a.direct) {
+    SKF_TRY(a3_img_map(&mImg, img, 6, B * H, TP));
+    SKF_TRY(a3_img_map(&mImgDo, img_do, 2, B * H, TP));
+  }
   {
-    a.out0 = dQ; a.ld0 = lddq; a.out1 = delta; a.delta = nullptr;
+    a.img_do = a.direct;
+    a.out0 = dQ; a.ld0 = lddq; a.out1 = delta; a.delta = nullptr; a.trace = g_a3_trace == 2;
     a.nst = a3_ring_stages(TP, 10, 4);
     const int smem = (int)a3::smem_plan(TP, 10, 4, a.nst).total + 1024;
     if (mode == 2) {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<false, true>, smem));
-      a3::attn3_bwd_k<false, true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, a);
+      a3::attn3_bwd_k<false, true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
     } else {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<false, false>, smem));
-      a3::attn3_bwd_k<false, false><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, a);
+      a3::attn3_bwd_k<false, false><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
     }
     SKF_LAUNCH_CHECK();
   }
   {
-    a.out0 = dK; a.ld0 = lddk; a.out1 = dV; a.ld1 = lddv; a.delta = delta;
+    a.img_do = 0;
+    a.out0 = dK; a.ld0 = lddk; a.out1 = dV; a.ld1 = lddv; a.delta = delta; a.trace = g_a3_trace == 3;
     a.nst = a3_ring_stages(TP, 12, 6);
     const int smem = (int)a3::smem_plan(TP, 12, 6, a.nst).total + 1024;
     if (mode == 2) {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<true, true>, smem));
-      a3::attn3_bwd_k<true, true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, a);
+      a3::attn3_bwd_k<true, true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
     } else {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<true, false>, smem));
-      a3::attn3_bwd_k<true, false><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, a);
+      a3::attn3_bwd_k<true, false><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
     }
     SKF_LAUNCH_CHECK();
   }

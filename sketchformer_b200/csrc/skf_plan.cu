@@ -40,12 +40,14 @@ extern int g_gemm_wsplit;   // 1: forward / dgrad products read pre-split bf16 i
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
 int attn3_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
 int attn3_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, float*, int64_t, float*,
-              const uint8_t*, int, int, int, int, int, int, cudaStream_t);
+              const uint8_t*, int, int, int, int, int, int, void*, cudaStream_t);
 int attn3_bwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, const float*, int64_t,
               const float*, int64_t, const float*, float*, float*, int64_t, float*, int64_t, float*, int64_t,
-              const uint8_t*, int, int, int, int, int, int, cudaStream_t);
+              const uint8_t*, int, int, int, int, int, int, const void*, void*, cudaStream_t);
+size_t attn3_image_bytes(int, int, int, int, int);
 extern int g_a3_trace;
 int attn3_trace_dump(long long*, int);
+int g_attn3_img = 1;       // 1: the backward kernels read the bf16 operand images the forward kernel wrote (training only)
 int g_attn3 = 3;           // bit 0 / bit 1: head dim 32 and sequences up to 224 run the warp-specialised whole-row forward /
                            // backward kernels (skf_attn_tc3.cu)
 int attn2_supported(const float*, int64_t, const float*, int64_t, const float*, int64_t, int, int, int);
@@ -243,6 +245,12 @@ struct Workspace {
   }
 };
 
+// operand images of the whole-row attention kernels (skf_attn_tc3.cu): only for head dim 32 and sequences <= 224
+static size_t attn_image_bytes(const skf_cfg& c, int T, int ntiles) {
+  if (c.d / c.H != 32 || T > 224 || c.gemm_backend != 0 || c.attn_backend != 0) return 256;
+  return attn3_image_bytes(c.B, c.H, T, T, ntiles);
+}
+
 static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
   Workspace W;
   const size_t F = sizeof(float);
@@ -264,6 +272,7 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
     W.add(p + ".qkv", Me * 3 * d * F);
     W.add(p + ".ctx", Me * d * F);
     W.add(p + ".lse", (size_t)c.B * H * c.T * F);
+    W.add(p + ".img", attn_image_bytes(c, c.T, 6));        // bf16 hi / lo images of q, k, v (whole-row attention)
     W.add(p + ".s1", Me * d * F);
     W.add(p + ".mean1", Me * F);
     W.add(p + ".rstd1", Me * F);
@@ -299,6 +308,7 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
       W.add(p + ".qkv", Md * 3 * d * F);
       W.add(p + ".ctx1", Md * d * F);
       W.add(p + ".lse1", (size_t)c.B * H * (c.T - 1) * F);
+      W.add(p + ".img1", attn_image_bytes(c, c.T - 1, 6));
       W.add(p + ".s1", Md * d * F);
       W.add(p + ".mean1", Md * F);
       W.add(p + ".rstd1", Md * F);
@@ -361,6 +371,7 @@ static Workspace build_workspace(const skf_cfg& c, const ParamLayout& PL) {
   W.add("g.emb", (size_t)c.B * E * F);
   W.add("g.u", Me * pool_dim(c) * F);
   W.add("g.delta", (size_t)c.B * H * c.T * F);
+  W.add("g.img_do", attn_image_bytes(c, c.T, 2));          // bf16 hi / lo images of dO (written by dq, read by dkv)
   W.total = (W.total + 255) & ~(size_t)255;
   return W;
 }
@@ -663,12 +674,18 @@ static int embed_dropout(skf_plan* P, float* x, int64_t n, uint32_t site, cudaSt
   return skf_dropout(x, x, n, P->c.dropout_rate, P->c.dropout_seed, site, P->wsp<int64_t>("step"), st);
 }
 
+// img: workspace buffer for the operand images of this attention site (nullptr: none, e.g. cross attention)
+static bool attn3_images(const skf_plan* P, const void* img, int Tq, int Tk) {
+  return img != nullptr && P->training && (g_attn3 & 3) == 3 && (g_attn3_img != 0) && Tq == Tk &&
+         P->c.gemm_precision >= 2;
+}
 static int attn_fwd_any(const skf_plan* P, const float* Q, int64_t ldq, const float* K, int64_t ldk,
                         const float* V, int64_t ldv, float* O, int64_t ldo, float* lse, const uint8_t* pad,
-                        int Tq, int Tk, int mode, cudaStream_t st) {
+                        int Tq, int Tk, int mode, cudaStream_t st, void* img = nullptr) {
   const skf_cfg& c = P->c;
   if (c.attn_backend == 0 && (g_attn3 & 1) && c.gemm_precision >= 1 && attn3_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
-    return attn3_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode, st);
+    return attn3_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode,
+                     attn3_images(P, img, Tq, Tk) ? img : nullptr, st);
   if (c.attn_backend == 0 && attn2_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
     return attn2_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, pad, c.B, c.H, Tq, Tk, c.d / c.H, mode,
                      c.gemm_precision >= 1 ? 1 : 0, st);
@@ -678,11 +695,14 @@ static int attn_fwd_any(const skf_plan* P, const float* Q, int64_t ldq, const fl
 static int attn_bwd_any(const skf_plan* P, const float* Q, int64_t ldq, const float* K, int64_t ldk,
                         const float* V, int64_t ldv, const float* O, int64_t ldo, const float* dO, int64_t lddo,
                         const float* lse, float* delta, float* dQ, int64_t lddq, float* dK, int64_t lddk,
-                        float* dV, int64_t lddv, const uint8_t* pad, int Tq, int Tk, int mode, cudaStream_t st) {
+                        float* dV, int64_t lddv, const uint8_t* pad, int Tq, int Tk, int mode, cudaStream_t st,
+                        const void* img = nullptr) {
   const skf_cfg& c = P->c;
-  if (c.attn_backend == 0 && (g_attn3 & 2) && c.gemm_precision >= 2 && attn3_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
+  if (c.attn_backend == 0 && (g_attn3 & 2) && c.gemm_precision >= 2 && attn3_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H)) {
+    const bool direct = attn3_images(P, img, Tq, Tk);
     return attn3_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad, c.B, c.H,
-                     Tq, Tk, c.d / c.H, mode, st);
+                     Tq, Tk, c.d / c.H, mode, direct ? img : nullptr, direct ? P->wsp<void>("g.img_do") : nullptr, st);
+  }
   if (c.attn_backend == 0 && attn2_supported(Q, ldq, K, ldk, V, ldv, Tq, Tk, c.d / c.H))
     return attn2_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, pad, c.B,
                      c.H, Tq, Tk, c.d / c.H, mode, c.gemm_precision >= 2 ? 1 : 0, st);
@@ -836,7 +856,7 @@ static int forward_encoder(skf_plan* P, const void* tok, cudaStream_t st) {
     SKF_TRY(G.fwd(x, P->w(p + ".mha.wqkv.k"), P->pw(p + ".mha.wqkv.b"), qkv, Me, 3 * d, d, SKF_ACT_NONE, nullptr, 0));
     float* ctx = P->wsf(p + ".ctx");
     SKF_TRY(attn_fwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, ctx, d, P->wsf(p + ".lse"), enc_pad,
-                         T, T, 1, st));
+                         T, T, 1, st, P->wsp<void>(p + ".img")));
     float* out1 = P->wsf(p + ".out1");
     SKF_TRY(proj_resid_ln(P, G, ctx, p + ".mha.wo.k", p + ".mha.wo.b", p + ".ln1", x, tmp, P->wsf(p + ".s1"), out1,
                           P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), Me, d, d, SITE_ENC_L + 2 * i, st));
@@ -901,7 +921,7 @@ static int forward_decoder(skf_plan* P, const void* tok, cudaStream_t st) {
     SKF_TRY(G.fwd(x, P->w(p + ".mha1.wqkv.k"), P->pw(p + ".mha1.wqkv.b"), qkv, Md, 3 * d, d, SKF_ACT_NONE, nullptr, 0));
     float* ctx1 = P->wsf(p + ".ctx1");
     SKF_TRY(attn_fwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, ctx1, d, P->wsf(p + ".lse1"), dec_pad,
-                         Td, Td, 2, st));
+                         Td, Td, 2, st, P->wsp<void>(p + ".img1")));
     float* out1 = P->wsf(p + ".out1");
     SKF_TRY(proj_resid_ln(P, G, ctx1, p + ".mha1.wo.k", p + ".mha1.wo.b", p + ".ln1", x, tmp, P->wsf(p + ".s1"), out1,
                           P->wsf(p + ".mean1"), P->wsf(p + ".rstd1"), Md, d, d, SITE_DEC_L + 3 * i, st));
@@ -1108,7 +1128,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
       SKF_TRY(G.before_write(gQKV));
       SKF_TRY(attn_bwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, P->wsf(p + ".ctx1"), d, gC, d,
                            P->wsf(p + ".lse1"), delta, gQKV, 3 * d, gQKV + d, 3 * d, gQKV + 2 * d, 3 * d, dec_pad,
-                           Td, Td, 2, st));
+                           Td, Td, 2, st, P->wsp<void>(p + ".img1")));
       SKF_TRY(G.wgrad_async(xin, gQKV, P->g(p + ".mha1.wqkv.k"), P->g(p + ".mha1.wqkv.b"), Md, 3 * d, d));
       SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha1.wqkv.k"), gA, Md, 3 * d, d, nullptr, gB, 0));
       if (i == c.L / 2 && i > 0) SKF_TRY(buckets_ready(P, 0, st));    // decoder layers L/2.. and the output layer are final
@@ -1177,7 +1197,7 @@ static int backward(skf_plan* P, const void* tok, cudaStream_t st) {
     SKF_TRY(G.before_write(gQKV));
     SKF_TRY(attn_bwd_any(P, qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, P->wsf(p + ".ctx"), d, gC, d,
                          P->wsf(p + ".lse"), delta, gQKV, 3 * d, gQKV + d, 3 * d, gQKV + 2 * d, 3 * d, enc_pad, T, T,
-                         1, st));
+                         1, st, P->wsp<void>(p + ".img")));
     SKF_TRY(G.wgrad_async(xin, gQKV, P->g(p + ".mha.wqkv.k"), P->g(p + ".mha.wqkv.b"), Me, 3 * d, d));
     SKF_TRY(G.dgrad(gQKV, P->w(p + ".mha.wqkv.k"), gA, Me, 3 * d, d, nullptr, gB, 0));
     if (i == c.L / 2 && i > 0) SKF_TRY(buckets_ready(P, 2, st));      // encoder layers L/2.., bottleneck and classifier are final
@@ -1316,6 +1336,10 @@ int skf_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "gemm_wsplit") == 0) {
     skf::g_gemm_wsplit = value ? 1 : 0;
+    return SKF_OK;
+  }
+  if (name && strcmp(name, "attn3_img") == 0) {
+    skf::g_attn3_img = value ? 1 : 0;
     return SKF_OK;
   }
   if (name && strcmp(name, "attn3_trace") == 0) {
@@ -1590,7 +1614,7 @@ int skf_attn_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
   // backend: 0 = tcgen05 flash kernels, single-pass TF32; 2 = the same with the 3xTF32 split (fp32-grade);
   //          1 = SIMT fp32
   if (backend == 6)                      // warp-specialised whole-row kernels (head dim 32, T <= 224), bf16x3
-    return attn3_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, as_stream(stream));
+    return attn3_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, nullptr, as_stream(stream));
   if (backend == 0 || backend == 2)
     return attn2_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, backend == 2,
                      as_stream(stream));
@@ -1604,7 +1628,7 @@ int skf_attn_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
                  int B, int H, int Tq, int Tk, int dh, int mask_mode, int round_tf32, int backend, void* stream) {
   if (backend == 6)
     return attn3_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B, H,
-                     Tq, Tk, dh, mask_mode, as_stream(stream));
+                     Tq, Tk, dh, mask_mode, nullptr, nullptr, as_stream(stream));
   if (backend == 0 || backend == 2)
     return attn2_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B,
                      H, Tq, Tk, dh, mask_mode, backend == 2, as_stream(stream));

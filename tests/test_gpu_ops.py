@@ -269,7 +269,7 @@ def test_adam_matches_oracle(lib):
     assert rel_err(m, opt.m["a"]) < 1e-5 and rel_err(v, opt.v["a"]) < 1e-5
 
 
-def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed, fwd_backend=1, bwd_backend=1):
+def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed, fwd_backend=1, bwd_backend=1, pad_edit=None):
     g = torch.Generator().manual_seed(seed)
     d = H * dh
     q = torch.randn(B, Tq, d, generator=g).double().requires_grad_(True)
@@ -277,6 +277,8 @@ def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed, fwd_backend=1, bwd_backend=1):
     v = torch.randn(B, Tk, d, generator=g).double().requires_grad_(True)
     lens = torch.randint(max(1, Tk // 3), Tk + 1, (B,), generator=g)
     pad = (torch.arange(Tk)[None, :] >= lens[:, None])
+    if pad_edit is not None:
+        pad = pad_edit(pad.clone())
     mask = None
     if mode >= 1:
         mask = pad[:, None, None, :].double()
@@ -355,6 +357,28 @@ def test_attention_tcgen05_whole_row(lib, B, H, Tq, Tk, dh, mode):
     e_o, e_q, e_k, e_v = _attn_case(lib, B, H, Tq, Tk, dh, mode, 400 + Tq, fwd_backend=6, bwd_backend=ATTN3_BWD)
     assert e_o < TOL_ATTN3, e_o
     assert max(e_q, e_k, e_v) < (TOL_ATTN3 if ATTN3_BWD == 6 else TOL_ATTN_X3), (e_q, e_k, e_v)
+
+
+def test_attention_whole_row_padding_patterns(lib):
+    """The whole-row kernels drop the key columns (dK / dV: key tiles) past an item's last unpadded key.  Masks that
+    are not a padded tail must still follow the reference's additive -1e9 exactly (builders/utils.py:93-97): padded
+    keys in the MIDDLE of a sequence, real keys only at the very end, very short effective lengths, and lengths at the
+    tile / half boundaries of the kernels."""
+    def edit(pad):
+        pad[:] = False
+        pad[0, 3:40] = True                 # hole before the tail
+        pad[1, :-2] = True                  # only the last two keys are real
+        pad[2, 2:] = True                   # effective length 2
+        pad[3, 128:] = True                 # effective length 128: key tile 1 skipped exactly at the tile edge
+        pad[4, 100:] = True                 # effective length 100: key tile 1 skipped, key half 1 of dq empty
+        pad[5, 113:] = True; pad[5, 7] = True
+        return pad
+    # (Not here: a single real key makes dQ = dK = 0 identically, and with EVERY key padded the fp32 reference is
+    # uniform over the keys — 1e9 swallows the logits — while the fp64 oracle still sees them: neither has a
+    # meaningful relative error.  DESIGN.md section 3.)
+    for Tq, Tk in ((200, 200), (70, 200), (200, 131)):
+        e_o, e_q, e_k, e_v = _attn_case(lib, 6, 2, Tq, Tk, 32, 1, 900 + Tq + Tk, fwd_backend=6, bwd_backend=6, pad_edit=edit)
+        assert max(e_o, e_q, e_k, e_v) < TOL_ATTN3, (Tq, Tk, e_o, e_q, e_k, e_v)
 
 
 MAJORS = [("fwd", False, True), ("dgrad", False, False), ("wgrad", True, True), ("tn", True, False)]
