@@ -198,8 +198,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="cfg2", choices=sorted(BATCHES))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--dp-buckets", type=int, default=4,
-                    help="gradient buckets all-reduced inside the step (0: one torch all_reduce after the step)")
+    ap.add_argument("--dp-buckets", type=int, default=-1,
+                    help="gradient buckets all-reduced inside the step (0: one torch all_reduce after the step; "
+                         "-1: the plugin's default, in-step on 2 ranks and the torch path on more)")
     ap.add_argument("--precision", type=int, default=-1,
                     help="tensor-core GEMM passes: 0 TF32 everywhere, 1 3xTF32 forward, 2 3xTF32 everywhere (default: engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -251,7 +252,9 @@ def main():
     else:
         dataset = Loader(data_hps, None, n_classes=c["n_classes"], seed=1234 + 1000 * rank)
     model = Model(model_hps, dataset, None, "bench", device=f"cuda:{local}", world_size=world, seed=0, rank=rank,
-                  gemm_precision=None if args.precision < 0 else args.precision, dp_buckets=args.dp_buckets)
+                  gemm_precision=None if args.precision < 0 else args.precision,
+                  dp_buckets=None if args.dp_buckets < 0 else args.dp_buckets)
+    args.dp_buckets = model._dp_buckets
     eng = model._train_engine           # identical random-init weights on every rank (Keras initialisers, seed 0)
 
     NB = 8   # distinct synthetic batches per rank: resident in HBM (value) / host numpy arrays (e2e)

@@ -67,7 +67,7 @@ class Transformer:
 
     # ---- construction ----------------------------------------------------------------------
     def __init__(self, hps, dataset, out_dir=None, experiment_id="0", device="cuda:0", world_size=1, seed=0,
-                 gemm_precision=None, use_cuda_graph=True, rank=0, dp_buckets=4):
+                 gemm_precision=None, use_cuda_graph=True, rank=0, dp_buckets=None):
         self.hps = hps if isinstance(hps, dict) else dict(hps.values())
         self.dataset = dataset
         self.experiment_id = experiment_id
@@ -97,6 +97,11 @@ class Transformer:
         self._stage = {}
         # data parallel: dp_buckets >= 1 -> bucketed NCCL all-reduce inside the step, overlapped with the backward pass
         # and captured in the CUDA graph (skf_plan_set_comm); 0 -> one torch.distributed all_reduce after the step
+        # Default: the in-step exchange on 2 ranks (measured: same step time as the torch path, exchange inside the
+        # graph), the torch path on more — the in-step exchange ran at 8 ranks with 16 sketches per rank but did not
+        # finish within the time limit at 128 per rank (profiles/r2_dp8_*), so it is opt-in there.
+        if dp_buckets is None:
+            dp_buckets = 4 if world_size == 2 else 0
         self._dp_buckets = int(dp_buckets) if world_size > 1 else 0
         self._comm = None
         self.build_model()
