@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--precision", type=int, default=-1,
                     help="tensor-core GEMM passes: 0 TF32 everywhere, 1 3xTF32 forward, 2 3xTF32 everywhere (default: engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-loader", action="store_true", help="skip the stroke3-distributed loader measurement")
     ap.add_argument("--set", action="append", default=[], metavar="NAME=INT",
                     help="library switch for A/B runs (skf_set_option), e.g. --set wgrad_overlap=0")
     args = ap.parse_args()
@@ -313,7 +314,10 @@ def main():
         return float(ms.item())
 
     steps = args.steps if cfg != "decode" else min(args.steps, 10)
-    for i in range(args.warmup):          # >= 3: one eager step, then the CUDA graph is captured and replayed
+    lw = eng.launches()
+    step(0)                               # eager: its launch count is what a (graph-replayed) call executes
+    launches_per_call = eng.launches() - lw
+    for i in range(1, args.warmup):       # >= 3: one eager step, then the CUDA graph is captured and replayed
         step(i)
     l0 = eng.launches()
     sampler = ClockSampler(local)
@@ -331,7 +335,7 @@ def main():
     if train:
         launches = (getattr(eng, "graph_launches", 0) + (0 if world == 1 or args.dp_buckets else 2)) * steps
     else:
-        launches = eager_launches
+        launches = max(eager_launches, launches_per_call * steps)
 
     value = world * B * steps / (ms / 1e3)
     e2e_value = world * B * steps / (ms_e2e / 1e3)
@@ -388,6 +392,8 @@ def main():
             line["decode_steps_per_call"] = tok_dev / steps / B
         if dp_check is not None:
             line["dp_grad_rel_err"] = dp_check
+        if cfg == "cfg2" and world == 1 and not args.no_loader:
+            line["e2e_loader"] = loader_bench(model, c, steps)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_steps(cfg, 2 if cfg != "decode" else 1, 1 if cfg not in ("cfg5", "decode") else 0,
                                     budget_s=25.0)
@@ -399,6 +405,80 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def loader_bench(model, c, steps):
+    """the real `stroke3-distributed` iterator (chunked .npz files, prefetch thread, whole-chunk
+    tokenisation on the device, batches cut by fancy indexing) over a synthetic chunk directory in the reference's
+    on-disk format, alone and feeding train_on_batch.  Reference: dataloaders/distributed_stroke3.py:77-125,
+    core/data.py:79-172 (a per-sketch Python loop and per-sample appends)."""
+    import shutil
+    import tempfile
+    import numpy as np
+    import torch
+    from sketchformer_b200.data import get_dataloader_by_name
+    from sketchformer_b200.tokenizer import Tokenizer
+    root = tempfile.mkdtemp(prefix="bench_loader_", dir=ROOT)
+    try:
+        rng = np.random.default_rng(7)
+        per_chunk, n_chunks = 8192, 4
+
+        def chunk(n):
+            lens = rng.integers(20, 121, size=n)
+            flat = np.zeros((int(lens.sum()), 3), np.int16)
+            flat[:, :2] = rng.integers(-40, 41, size=(len(flat), 2))
+            flat[:, 2] = rng.random(len(flat)) < 0.08
+            ends = np.cumsum(lens)
+            flat[ends - 1, 2] = 1
+            x = np.empty(n, dtype=object)
+            for i, part in enumerate(np.split(flat, ends[:-1])):
+                x[i] = part
+            return x, rng.integers(0, c["n_classes"], size=n)
+        for i in range(n_chunks):
+            x, y = chunk(per_chunk)
+            np.savez(os.path.join(root, f"train_{i:03d}.npz"), x=x, y=y)
+        for name in ("valid", "test"):
+            x, y = chunk(256)
+            np.savez(os.path.join(root, f"{name}.npz"), x=x, y=y)
+        np.savez(os.path.join(root, "meta.npz"), n_classes=c["n_classes"], n_samples_train=per_chunk * n_chunks,
+                 n_samples_valid=256, n_samples_test=256, class_names=np.array([f"c{i}" for i in range(c["n_classes"])]),
+                 std=1.0, mean=0.0)
+        Loader = get_dataloader_by_name("stroke3-distributed")
+        hps = Loader.parse_hparams(f"max_seq_len={c['max_seq_len']}")
+        cents = np.random.default_rng(0).uniform(-1, 1, size=(1000, 2)).astype(np.float32)
+        ds = Loader(hps, root, seed=5, tokenizer=Tokenizer(centroids=cents))
+        out = {"unit": "sketches/s", "chunks": n_chunks, "sketches_per_chunk": per_chunk,
+               "device_tokenizer": bool(ds._device_path())}
+        # one chunk through preprocess(): device path, and the host restatement on a sample of it
+        raw = np.load(os.path.join(root, "train_000.npz"), allow_pickle=True)["x"]
+        ds.preprocess(raw[:256])
+        t0 = time.perf_counter(); ds.preprocess(raw); dt = time.perf_counter() - t0
+        out["preprocess_sketches_per_s"] = len(raw) / dt
+        dev, ds.device = ds.device, None
+        t0 = time.perf_counter(); ds.preprocess(raw[:512]); dt = time.perf_counter() - t0
+        out["preprocess_host_loop_sketches_per_s"] = 512 / dt
+        ds.device = dev
+        # the iterator alone (2.3 passes over the chunks: swaps and the wrap-around included)
+        it = ds.batch_iterator("train", BATCH)
+        for _ in range(3):
+            next(it)
+        nb = 600
+        t0 = time.perf_counter()
+        for _ in range(nb):
+            next(it)
+        out["loader_sketches_per_s"] = nb * BATCH / (time.perf_counter() - t0)
+        # and feeding the train step through the plugin API
+        for _ in range(3):
+            model.train_on_batch(next(it))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            model.train_on_batch(next(it), sync_metrics=False)
+        torch.cuda.synchronize()
+        out["value"] = steps * BATCH / (time.perf_counter() - t0)
+        return out
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
 
 
 def dp_gradient_check(model, world, rank, full, c, cfg):

@@ -110,7 +110,13 @@ class DistributedStroke3DataLoader:
             hps = hps.parse(params)
         return hps
 
-    def __init__(self, hps, data_directory, rank=0, world_size=1, seed=None, tokenizer=None):
+    def __init__(self, hps, data_directory, rank=0, world_size=1, seed=None, tokenizer=None, device="auto",
+                 device_batches=False):
+        """device: where whole chunks are preprocessed in dictionary-token mode — "auto" = the current CUDA device when
+        there is one (skf_tokenize_strokes, one launch per chunk: the reference's per-sketch Python loop,
+        distributed_stroke3.py:90-125, caps a 15 k sketches/s train step), None = the host restatement.
+        device_batches: yield batches as CUDA tensors cut from the device-resident chunk (no per-step host->device
+        copy); the default yields numpy arrays exactly like the reference."""
         import glob
         import os
         import threading
@@ -120,7 +126,17 @@ class DistributedStroke3DataLoader:
         self.rank, self.world_size = rank, world_size
         self.limit = 1000
         self.rng = np.random.default_rng(seed)
+        # sample-slicing mode needs the SAME file order on every rank: a rank-independent generator for it
+        self._file_rng = np.random.default_rng(0x5EED if seed is None else seed)
         self.tokenizer = tokenizer
+        self.device, self.device_batches, self._loader_stream = None, bool(device_batches), None
+        if device == "auto":
+            try:
+                import torch
+                device = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else None
+            except Exception:      # noqa: BLE001
+                device = None
+        self.device = device
         if not self.hps["use_continuous_data"] and tokenizer is None:      # distributed_stroke3.py:32-36
             from .tokenizer import GridTokenizer, Tokenizer
             if self.hps["token_type"] == "dictionary":
@@ -155,7 +171,10 @@ class DistributedStroke3DataLoader:
         split.thread.start()
 
     def reshuffle_file_indices(self, split_name, filenames):
-        return self.rng.permutation(len(filenames)) if split_name == "train" else list(range(len(filenames)))
+        if split_name != "train":
+            return list(range(len(filenames)))
+        # every rank walks the same chunk when the ranks slice samples instead of files
+        return (self._file_rng if getattr(self, "_slice_samples", False) else self.rng).permutation(len(filenames))
 
     def reshuffle_sample_indices(self, split_name, data):
         if split_name != "train":
@@ -169,6 +188,13 @@ class DistributedStroke3DataLoader:
         loaded = np.load(selected_file, allow_pickle=True)
         data = {"x": self.preprocess(loaded["x"], augment=split_name == "train"), "y": np.asarray(loaded["y"])}
         self.splits[split_name].next = data
+
+    def _device_path(self):
+        """Whole-chunk preprocessing on the device: dictionary tokens, relative strokes in file order (the options
+        that reorder or re-reference the points, and the grid tokenizer, stay on the host restatement)."""
+        return (self.device is not None and not self.hps["use_continuous_data"] and
+                not self.hps["shuffle_stroke"] and not self.hps["use_absolute_strokes"] and
+                hasattr(self.tokenizer, "encode_batch_device"))
 
     def _swap(self, split_name):
         split = self.splits[split_name]
@@ -197,6 +223,18 @@ class DistributedStroke3DataLoader:
         """distributed_stroke3.py:90-125: clip, (continuous + train: random scale and point dropout), bbox
         normalisation, optional stroke shuffle / absolute coordinates, tokenizer, cut to max_seq_len, PAD / stroke-5."""
         from .tokenizer import convert_to_absolute, preprocess_sketch_host, shuffle_strokes
+        if self._device_path() and len(data):
+            # one kernel launch for the whole chunk, on the loader's own stream (this runs in the prefetch thread while
+            # the train step owns the device's other streams); bit-identical to the host loop below
+            import torch
+            with torch.cuda.device(self.device):
+                if self._loader_stream is None:
+                    self._loader_stream = torch.cuda.Stream(self.device)
+                with torch.cuda.stream(self._loader_stream):
+                    tok = self.preprocess_on_device(list(data), self.device)
+                    out = tok if self.device_batches else tok.cpu().numpy()
+                    self._loader_stream.synchronize()
+            return out
         T, out = self.hps["max_seq_len"], []
         shuffle, absolute = bool(self.hps["shuffle_stroke"]), bool(self.hps["use_absolute_strokes"])
         for sketch in data:
@@ -241,10 +279,21 @@ class DistributedStroke3DataLoader:
     def get_sample(self, data, idx):
         return [np.array(data["x"][idx]), np.expand_dims(data["y"][idx], axis=-1)]
 
+    def _take(self, split, indices):
+        """Samples `indices` of the loaded chunk as one stacked batch (fancy indexing: no per-sample Python work)."""
+        idx = np.asarray(indices, dtype=np.int64)
+        x = split.current["x"]
+        if isinstance(x, np.ndarray):
+            bx = x[idx]
+        else:                      # device-resident chunk (device_batches=True)
+            import torch
+            bx = x.index_select(0, torch.as_tensor(idx, device=x.device))
+        by = np.asarray(split.current["y"])[idx].reshape(len(idx), -1)[:, :1].astype(np.int64)
+        return bx, by
+
     def _collate(self, split, indices):
-        x = np.stack([split.current["x"][i] for i in indices])
-        y = np.stack([np.expand_dims(split.current["y"][i], -1) for i in indices]).astype(np.int64)
-        return [x, y]
+        bx, by = self._take(split, indices)
+        return [bx, by]
 
     def batch_iterator(self, split_name, batch_size, stop_at_end_of_split=False):
         """core/data.py:115-172 (sample_iterator + batch_iterator): a batch continues across a chunk swap; when
@@ -252,19 +301,31 @@ class DistributedStroke3DataLoader:
         split = self._ready(split_name)
         status = "running"
         while not stop_at_end_of_split or status != "end_of_split":
-            xs, ys, counter, status = [], [], 0, "running"
+            # The reference draws one sample at a time (core/data.py:115-172); the same sequence in slices: take what
+            # the loaded chunk still has, swap chunks when it is exhausted, and when that swap wrapped the split the
+            # batch ends with the single sample drawn right after it.
+            xs, ys, need, status = [], [], batch_size, "running"
             while status == "running":
-                counter += 1
-                status = "end_of_batch" if counter >= batch_size else "running"
                 if split.cursor >= split.current_len:
                     end = self._swap(split_name)
-                    status = "end_of_split" if end else status
                     split.cursor = 0
-                i = split.current_index_shuffle[split.cursor]
-                split.cursor += 1
-                xs.append(split.current["x"][i])
-                ys.append(np.expand_dims(split.current["y"][i], -1))
-            yield [np.stack(xs), np.stack(ys).astype(np.int64)]
+                    if end:
+                        status, need = "end_of_split", 1
+                take = min(need, split.current_len - split.cursor)
+                bx, by = self._take(split, split.current_index_shuffle[split.cursor:split.cursor + take])
+                split.cursor += take
+                need -= take
+                xs.append(bx)
+                ys.append(by)
+                if status == "running" and need == 0:
+                    status = "end_of_batch"
+            if len(xs) == 1:
+                yield [xs[0], ys[0]]
+            elif isinstance(xs[0], np.ndarray):
+                yield [np.concatenate(xs), np.concatenate(ys)]
+            else:
+                import torch
+                yield [torch.cat(xs), np.concatenate(ys)]
 
     def get_n_samples_from(self, split_name, n, shuffled=False, seeded=None, preprocess=False):
         """core/data.py:174-209: the first n samples of the loaded chunk in FILE order, or n of a permutation of it.

@@ -304,11 +304,30 @@ class Engine:
             return None                      # classification of the embedding only ("cls.argmax")
         state = self.tensor("gen.state", dtype=torch.int32)
         cols, i = 0, 0
+        # The ~50 small launches of a decoder position are replayed as CUDA graphs, one per chunk of positions
+        # (captured on the second decode of this plan with the same chunking: the first runs eagerly, which also
+        # initialises function attributes and tensor-map encoders).  The reference re-runs the whole decoder on the
+        # growing prefix and synchronises with the host at every token (models/sketchformer.py:274-301).
+        graphs = getattr(self, "_decode_graphs", None)
+        if graphs is None:
+            graphs = self._decode_graphs = {"warm": False}
+        use_graphs = graphs["warm"] and os.environ.get("SKF_DECODE_GRAPHS", "1") != "0"
         while i < T and cols == 0:
             n = min(chunk, T - i)
-            check(self.lib.skf_decode_steps(self._plan, i, n, self._stream()), "skf_decode_steps")
+            if use_graphs:
+                g = graphs.get((i, n, int(sos), int(eos)))
+                if g is None:
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize(self.device)
+                    with torch.cuda.graph(g, stream=self._graph_stream()):
+                        check(self.lib.skf_decode_steps(self._plan, i, n, self._stream()), "skf_decode_steps")
+                    graphs[(i, n, int(sos), int(eos))] = g
+                g.replay()
+            else:
+                check(self.lib.skf_decode_steps(self._plan, i, n, self._stream()), "skf_decode_steps")
             i += n
             cols = int(state[0].item())
+        graphs["warm"] = True
         cols = cols or T + 1
         if self.cfg.continuous:
             return self.tensor("gen.strokes", (B, T + 1, 5))[:, :cols].clone()
@@ -330,6 +349,11 @@ class Engine:
         """One in-place NCCL sum of the whole gradient arena on the current stream (tests, the dp check of bench.py)."""
         check(self.lib.skf_allreduce_bucket(C.c_void_p(self.grads.data_ptr()), self.grads.numel(), C.c_void_p(comm),
                                             self._stream()), "skf_allreduce_bucket")
+
+    def _graph_stream(self):
+        if getattr(self, "_gstream", None) is None:
+            self._gstream = torch.cuda.Stream(self.device)
+        return self._gstream
 
     def launches(self):
         return int(self.lib.skf_plan_launches(self._plan))

@@ -430,3 +430,29 @@ def test_point_dropout_augmentation_matches_the_reference():
         assert got.shape == want.shape and np.array_equal(got, want.astype(np.float32))
         dropped += len(s) - len(got)
     assert dropped > 50
+
+
+@pytest.mark.gpu
+def test_device_chunk_preprocessing_equals_the_host_loop(tmp_path):
+    """load_next_megabatch tokenises whole chunks with skf_tokenize_strokes (one launch per chunk) and the iterator cuts
+    batches by fancy indexing: same token ids, bit for bit, and the same batch sequence as the host restatement that is
+    pinned to the reference's vectors (tests/golden/loader_ref.npz)."""
+    _write_dataset(str(tmp_path), n_chunks=3, per_chunk=70)
+    Loader = get_dataloader_by_name("stroke3-distributed")
+    hps = Loader.parse_hparams("max_seq_len=48")
+    cents = np.random.default_rng(1).uniform(-1, 1, size=(1000, 2)).astype(np.float32)
+    dev = Loader(hps, str(tmp_path), seed=11, tokenizer=Tokenizer(centroids=cents))
+    host = Loader(hps, str(tmp_path), seed=11, tokenizer=Tokenizer(centroids=cents), device=None)
+    assert dev._device_path() and not host._device_path()
+    raw = np.load(os.path.join(str(tmp_path), "train_000.npz"), allow_pickle=True)["x"]
+    assert np.array_equal(dev.preprocess(raw), host.preprocess(raw))
+    a, b = dev.batch_iterator("train", 16), host.batch_iterator("train", 16)
+    for _ in range(40):                       # three passes: chunk swaps, the cut batch at the end of the split
+        (xa, ya), (xb, yb) = next(a), next(b)
+        assert xa.dtype == np.int64 and np.array_equal(xa, xb) and np.array_equal(ya, yb)
+    # device-resident batches: the same ids as CUDA tensors
+    import torch
+    res = Loader(hps, str(tmp_path), seed=11, tokenizer=Tokenizer(centroids=cents), device_batches=True)
+    xr, yr = next(res.batch_iterator("train", 16))
+    xh, yh = next(Loader(hps, str(tmp_path), seed=11, tokenizer=Tokenizer(centroids=cents), device=None).batch_iterator("train", 16))
+    assert torch.is_tensor(xr) and xr.is_cuda and np.array_equal(xr.cpu().numpy(), xh) and np.array_equal(yr, yh)
