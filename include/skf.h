@@ -195,6 +195,20 @@ int skf_attn_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const
                  int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad, int B, int H,
                  int Tq, int Tk, int dh, int mask_mode, int round_tf32, int backend, void* stream);
 
+/* The whole-row kernels (backend 6: head dim 32, Tq, Tk <= 224) with operand images: the forward pass also writes the
+ * bf16 hi / lo tiles of Q, K, V it built in shared memory to `img` (skf_attn_image_bytes(.., 0) bytes), and the backward
+ * pass TMA-loads them straight into its operand slots instead of converting the fp32 rows again; `img_do`
+ * (skf_attn_image_bytes(.., 1) bytes) carries the images of dO from the dQ kernel to the dK / dV kernel.  Same
+ * arithmetic as skf_attn_fwd / skf_attn_bwd with backend 6; Tq == Tk.  This is what the plan runs in training.   */
+size_t skf_attn_image_bytes(int B, int H, int Tq, int Tk, int which);
+int skf_attn_fwd_img(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, float* O,
+                     int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh,
+                     int mask_mode, void* img, void* stream);
+int skf_attn_bwd_img(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv,
+                     const float* O, int64_t ldo, const float* dO, int64_t lddo, const float* lse, float* delta,
+                     float* dQ, int64_t lddq, float* dK, int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad,
+                     int B, int H, int Tq, int Tk, int dh, int mask_mode, const void* img, void* img_do, void* stream);
+
 /* x + sublayer -> LayerNormalization(eps=1e-6) (transformer.py:209-224): s = a + b (+bias);
  * y = LN(s)*gamma+beta.  s, mean, rstd are saved for backward (any may be NULL).           */
 int skf_add_layernorm_fwd(const float* a, const float* b, const float* bias, const float* gamma,

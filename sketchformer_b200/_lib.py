@@ -57,6 +57,9 @@ SIGNATURES = {
     "skf_split_bf16": (I, [P, P, P, L, P]),
     "skf_attn_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, P]),
     "skf_attn_bwd": (I, [P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, P]),
+    "skf_attn_image_bytes": (SZ, [I, I, I, I, I]),
+    "skf_attn_fwd_img": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, P, P]),
+    "skf_attn_bwd_img": (I, [P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, P, I, I, I, I, I, I, P, P, P]),
     "skf_add_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "skf_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, P]),
     "skf_add_dropout_layernorm_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, F, C.c_uint32, C.c_uint32, P, P]),

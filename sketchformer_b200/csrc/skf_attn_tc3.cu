@@ -130,16 +130,18 @@ __device__ __forceinline__ void split16(const float (&p)[16], uint32_t (&w)[16])
 // One ring stage (64 rows x 32 fp32, 128-byte rows under the TMA's 128B swizzle) -> rows [row0, row0 + 64) of a bf16
 // hi / lo operand tile pair (64-byte rows under the 64B swizzle: 16-byte chunk g of row R at chunk g ^ ((R >> 1) & 3)).
 // Rows >= rows_alloc are not stored.  `ct` = thread index among the NCONV * 32 converter threads.
-// WITH_DOT: `other` is the ring stage holding the same rows of O; writes rowsum(x * other) of every row into dot_out
-// (shared, indexed by sequence row) and dot_glob (global, may be nullptr; rows >= rows_valid are skipped).
+// WITH_DOT: other[round][0..1] hold this thread's 8 values of O for the task of each round (prefetched from HBM by
+// prefetch_rows(): a quad of lanes covers one 128-byte row segment); writes rowsum(x * O) of every row into dot_out
+// (shared, indexed by sequence row) and dot_glob (global, may be nullptr; rows >= rows_valid are not written).
+constexpr int CONV_ROUNDS = 256 / (NCONV * 32);
 template <bool WITH_DOT>
 __device__ __forceinline__ void convert_stage(const uint8_t* stage, uint8_t* hi, uint8_t* lo, int row0, int rows_alloc,
-                                              int ct, const uint8_t* other = nullptr, float* dot_out = nullptr,
+                                              int ct, const float4 (*other)[2] = nullptr, float* dot_out = nullptr,
                                               float* dot_glob = nullptr, int rows_valid = 0) {
   // 256 tasks = 64 rows x 4 groups of 8 columns, NCONV * 32 per round; the 4 lanes of a quad share a row
   static_assert(256 % (NCONV * 32) == 0, "converter rounds");
-#pragma unroll 1
-  for (int round = 0; round < 256 / (NCONV * 32); round++) {
+#pragma unroll
+  for (int round = 0; round < CONV_ROUNDS; round++) {
     const int task = ct + round * NCONV * 32;
     const int r = task >> 2, g = task & 3, R = row0 + r;
     float dot = 0.f;
@@ -149,8 +151,7 @@ __device__ __forceinline__ void convert_stage(const uint8_t* stage, uint8_t* hi,
       const float4 u = *reinterpret_cast<const float4*>(stage + o0);
       const float4 v = *reinterpret_cast<const float4*>(stage + o1);
       if (WITH_DOT) {
-        const float4 p = *reinterpret_cast<const float4*>(other + o0);
-        const float4 q = *reinterpret_cast<const float4*>(other + o1);
+        const float4 p = other[round][0], q = other[round][1];
         dot = (u.x * p.x + u.y * p.y) + (u.z * p.z + u.w * p.w) + (v.x * q.x + v.y * q.y) + (v.z * q.z + v.w * q.w);
       }
       uint4 h, l;
@@ -190,6 +191,22 @@ __device__ __forceinline__ void stamp(int on, int role, uint32_t li, int k) {
   if (on && blockIdx.x == 0 && li < 8) g_trace[(role * 8 + li) * 16 + k] = clock64();
 }
 
+// This thread's O values for the conversion tasks of rows [row0, row0 + 64) (zeros past rows_valid)
+__device__ __forceinline__ void prefetch_rows(float4 (*dst)[2], const float* src, int64_t ld, int row0, int rows_valid,
+                                              int ct) {
+#pragma unroll
+  for (int round = 0; round < CONV_ROUNDS; round++) {
+    const int task = ct + round * NCONV * 32;
+    const int R = row0 + (task >> 2), g = task & 3;
+    dst[round][0] = dst[round][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (R < rows_valid) {
+      const float4* p = reinterpret_cast<const float4*>(src + (int64_t)R * ld + 8 * g);
+      dst[round][0] = __ldg(p);
+      dst[round][1] = __ldg(p + 1);
+    }
+  }
+}
+
 // Effective key length of an item: 1 + the index of its last unpadded key (Tk without a padding mask, or when every
 // key is padded — then the reference's softmax over equally shifted logits is uniform and no column may be dropped).
 // Keys past it get exactly zero weight in fp32 (exp(x - 1e9 - max) with a finite max), so the kernels skip their
@@ -215,6 +232,8 @@ struct Args {
   int64_t ld0;
   float* out1;                // fwd: lse    dq: delta  dkv: dV
   int64_t ld1;
+  const float* O;             // dq: forward output [B*Tq, ldO] (for delta = rowsum(dO * O))
+  int64_t ldO;
   const float* lse;           // dq / dkv: logsumexp of the forward pass [B, H, Tq]
   const float* delta;         // dkv: rowsum(dO * O) [B, H, Tq] (written by dq)
   // bf16 hi / lo operand images in HBM, one contiguous [TP x 32] tile per (operand, hi|lo, item): the forward kernel
@@ -716,7 +735,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       mbar_init(bar(DS_FULL + w), 4);
     }
     mbar_init(bar(ACC_FULL), 1);
-    mbar_init(bar(ACC_FREE), DKV ? 8 : 4);
+    mbar_init(bar(ACC_FREE), 4);
     fence_barrier_init();
   }
   for (int i = tid; i < 1024; i += THREADS) reinterpret_cast<uint32_t*>(gen + L.vec - 4096)[i] = 0u;
@@ -741,7 +760,6 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     // ================= TMA producer =================
     if (lane == 0) {
       prefetch_tmap(&mQ); prefetch_tmap(&mK); prefetch_tmap(&mV); prefetch_tmap(&mdO);
-      if (!DKV) prefetch_tmap(&mO);
       uint32_t n = 0;
       auto load = [&](const CUtensorMap* m, int h, int row, int b) {
         const int st = n % a.nst;
@@ -768,10 +786,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
             mbar_wait_sleep(bar(SB_EMPTY), (pli & 1u) ^ 1u);
             load_img(&mImg, 1, buf, it, 1);                                  // Q
             load_img(&mImg, 2, buf, it, 2);                                  // V
-            for (int ch = 0; ch < nq_ch; ch++) {                             // (O, dO) pairs through the ring
-              load(&mO, h, 64 * ch, b);
-              load(&mdO, h, 64 * ch, b);
-            }
+            for (int ch = 0; ch < nq_ch; ch++) load(&mdO, h, 64 * ch, b);    // dO through the ring (fp32 -> tiles)
           } else {
             load_img(&mImg, 1, buf, it, 1);                                  // Q  (double-buffered)
             load_img(&mImgDo, 3, buf, it, 0);                                // dO (double-buffered)
@@ -786,10 +801,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           for (int ch = 0; ch < nk_ch; ch++) load(&mK, h, 64 * ch, b);
           for (int ch = 0; ch < nq_ch; ch++) load(&mQ, h, 64 * ch, b);
           for (int ch = 0; ch < nk_ch; ch++) load(&mV, h, 64 * ch, b);
-          for (int ch = 0; ch < nq_ch; ch++) {
-            load(&mO, h, 64 * ch, b);
-            load(&mdO, h, 64 * ch, b);
-          }
+          for (int ch = 0; ch < nq_ch; ch++) load(&mdO, h, 64 * ch, b);
         } else {
           for (int ch = 0; ch < nq_ch; ch++) load(&mQ, h, 64 * ch, b);
           for (int ch = 0; ch < nq_ch; ch++) load(&mdO, h, 64 * ch, b);
@@ -806,6 +818,14 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       const int b = it / a.H, h = it % a.H, buf = li & 1;
       const int64_t bh = (int64_t)b * a.H + h;
       // double-buffered operands + vectors of buffer `buf`: free once the item two back has issued its last MMA
+      // dq: this thread's share of O (for delta) does not depend on any buffer: in flight during the waits below
+      float4 oval[4][CONV_ROUNDS][2];
+      if (!DKV) {
+        const float* Og = a.O + (int64_t)b * a.Tq * a.ldO + h * DH;
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++)
+          if (ch < nq_ch) prefetch_rows(oval[ch], Og, a.ldO, 64 * ch, a.Tq, ct);
+      }
       mbar_wait_sleep(bar(DB_EMPTY + buf), ((li >> 1) & 1u) ^ 1u);
       if (ct == 0) stamp(a.trace, 3, li, 0);
       {
@@ -871,19 +891,20 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         float* del_s = vec + 512 + buf * 256;
         uint8_t* hi = gen + L.tiles + slot(3, buf) * L.tile_bytes;
         uint8_t* lo = hi + L.tile_bytes;
-        for (int ch = 0; ch < nq_ch; ch++, n += 2) {
-          const int s0 = n % a.nst, s1 = (n + 1) % a.nst;
-          mbar_wait_sleep(bar(RING_FULL + s0), (n / a.nst) & 1u);
-          mbar_wait_sleep(bar(RING_FULL + s1), ((n + 1) / a.nst) & 1u);
-          convert_stage<true>(gen + L.ring + s1 * STAGE_BYTES, hi, lo, 64 * ch, TP, ct, gen + L.ring + s0 * STAGE_BYTES,
-                              del_s, a.out1 ? a.out1 + bh * a.Tq : nullptr, a.Tq);
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+          if (ch >= nq_ch) break;
+          const int st = n % a.nst;
+          mbar_wait_sleep(bar(RING_FULL + st), (n / a.nst) & 1u);
+          convert_stage<true>(gen + L.ring + st * STAGE_BYTES, hi, lo, 64 * ch, TP, ct, oval[ch], del_s,
+                              a.out1 ? a.out1 + bh * a.Tq : nullptr, a.Tq);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(bar(OP_FULL + 4 * buf + 3));
-            mbar_arrive(bar(RING_EMPTY + s0));
-            mbar_arrive(bar(RING_EMPTY + s1));
+            mbar_arrive(bar(RING_EMPTY + st));
           }
+          n++;
         }
         if (ct == 0) stamp(a.trace, 3, li, 4);
         if (a.img_do && ct == 0) {             // dO images for dkv
@@ -976,6 +997,34 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const float c1 = a.scale * LOG2E;
     const uint32_t tS = tmem + MAXT * w, tP = tS + HALF;
+    // dkv: accumulator columns [0,32) = dV, [32,64) = dK of key row `krow` of item (eb, eh), unit parity eu
+    auto dkv_epilogue = [&](int eb, int eh, int krow, bool eidle, uint32_t eu) {
+      mbar_wait_sleep(bar(ACC_FULL), eu & 1u);
+      tc_fence_after();
+      uint32_t ov[32], ok[32];
+      if (!eidle) {
+        tmem_ld32(tAcc + lane_off, ov);
+        tmem_ld32(tAcc + lane_off + 32, ok);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(ACC_FREE));
+      if (!eidle && krow < a.Tk) {
+        float4* dk = reinterpret_cast<float4*>(a.out0 + ((int64_t)eb * a.Tk + krow) * a.ld0 + eh * DH);
+        float4* dv = reinterpret_cast<float4*>(a.out1 + ((int64_t)eb * a.Tk + krow) * a.ld1 + eh * DH);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          dv[j] = make_float4(__uint_as_float(ov[4 * j]), __uint_as_float(ov[4 * j + 1]), __uint_as_float(ov[4 * j + 2]),
+                              __uint_as_float(ov[4 * j + 3]));
+          dk[j] = make_float4(__uint_as_float(ok[4 * j]) * a.scale, __uint_as_float(ok[4 * j + 1]) * a.scale,
+                              __uint_as_float(ok[4 * j + 2]) * a.scale, __uint_as_float(ok[4 * j + 3]) * a.scale);
+        }
+      }
+    };
+    bool have_prev = false, pidle = false;
+    int pb = 0, ph = 0, prow = 0;
+    uint32_t pu = 0;
     if (w < nhalf) {
       uint32_t li = 0, u = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, li++) {
@@ -1066,14 +1115,15 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(DS_FULL + w));
           if (row == 0) stamp(a.trace, 1 + w, li, 4 * t + 1);
-          // epilogue.  dq: warpgroup (t & 1) stores dQ of tile t; dkv: warpgroup 0 stores dK, warpgroup 1 dV
-          // (with one column half, warpgroup 0 stores both)
-          const bool my_epi = DKV ? true : (nhalf == 1 || (t & 1) == w);
-          if (my_epi) {
-            mbar_wait_sleep(bar(ACC_FULL), u & 1u);
-            tc_fence_after();
-            if (row == 0) stamp(a.trace, 1 + w, li, 4 * t + 2);
-            if (!DKV) {
+          // epilogue.  dq: warpgroup (t & 1) stores dQ of tile t, right away.  dkv: warpgroup 0 stores dV and dK of a
+          // key tile AFTER its math of the next unit: the accumulators are final only when the other warpgroup's half
+          // has been consumed, and waiting for that here would keep this warpgroup from the next unit's scores, which
+          // the tensor core finished long before (phase trace profiles/r2_a13_trace_dkv.log).
+          if (!DKV) {
+            if (nhalf == 1 || (t & 1) == w) {
+              mbar_wait_sleep(bar(ACC_FULL), u & 1u);
+              tc_fence_after();
+              if (row == 0) stamp(a.trace, 1 + w, li, 4 * t + 2);
               uint32_t o0[32], o1[32];
               if (!idle) {
                 tmem_ld32(tAcc + lane_off, o0);
@@ -1092,38 +1142,14 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
                                        (__uint_as_float(o0[4 * j + 2]) + __uint_as_float(o1[4 * j + 2])) * a.scale,
                                        (__uint_as_float(o0[4 * j + 3]) + __uint_as_float(o1[4 * j + 3])) * a.scale);
               }
-            } else {
-              // accumulator columns [0,32) = dV, [32,64) = dK
-              const int nsel = nhalf == 1 ? 2 : 1;
-              for (int sel = 0; sel < nsel; sel++) {
-                const bool is_dk = nhalf == 1 ? sel == 1 : w == 0;
-                uint32_t o[32];
-                if (!idle) {
-                  tmem_ld32(tAcc + lane_off + (is_dk ? 32 : 0), o);
-                  tmem_ld_wait();
-                }
-                if (sel == nsel - 1) {
-                  tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) {
-                    mbar_arrive(bar(ACC_FREE));
-                    if (nhalf == 1) mbar_arrive(bar(ACC_FREE));      // the idle warpgroup's share of the count
-                  }
-                }
-                if (!idle && li_row < a.Tk) {
-                  const float sc = is_dk ? a.scale : 1.0f;
-                  float* obase = is_dk ? a.out0 + ((int64_t)b * a.Tk + li_row) * a.ld0 : a.out1 + ((int64_t)b * a.Tk + li_row) * a.ld1;
-                  float4* dst = reinterpret_cast<float4*>(obase + h * DH);
-#pragma unroll
-                  for (int j = 0; j < 8; j++)
-                    dst[j] = make_float4(__uint_as_float(o[4 * j]) * sc, __uint_as_float(o[4 * j + 1]) * sc,
-                                         __uint_as_float(o[4 * j + 2]) * sc, __uint_as_float(o[4 * j + 3]) * sc);
-                }
-              }
             }
+          } else if (w == 0) {
+            if (have_prev) dkv_epilogue(pb, ph, prow, pidle, pu);
+            have_prev = true; pb = b; ph = h; prow = li_row; pidle = idle; pu = u;
           }
         }
       }
+      if (DKV && w == 0 && have_prev) dkv_epilogue(pb, ph, prow, pidle, pu);
     }
   }
   epilogue_free(c);
@@ -1242,7 +1268,7 @@ int attn3_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   a3::Args a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.mode = mode; a.scale = 1.0f / sqrtf((float)dh);
-  a.key_pad = key_pad; a.lse = lse;
+  a.key_pad = key_pad; a.lse = lse; a.O = O; a.ldO = ldo;
   const int QP = (Tq + 15) & ~15, KP = (Tk + 15) & ~15, TP = QP > KP ? QP : KP;
   const int grid = B * H < a3_sm_count() ? B * H : a3_sm_count();
   // with the forward kernel's operand images (and room for dO's) the backward kernels load bf16 tiles directly

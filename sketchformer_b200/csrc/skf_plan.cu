@@ -1564,6 +1564,24 @@ int skf_decode_steps(skf_plan* P, int first_step, int n_steps, void* stream) {
 
 int64_t skf_plan_launches(const skf_plan* P) { return P ? P->launches : 0; }
 
+size_t skf_attn_image_bytes(int B, int H, int Tq, int Tk, int which) {
+  return skf::attn3_image_bytes(B, H, Tq, Tk, which == 0 ? 6 : 2);
+}
+
+int skf_attn_fwd_img(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, float* O,
+                     int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh,
+                     int mask_mode, void* img, void* stream) {
+  return attn3_fwd(Q, ldq, K, ldk, V, ldv, O, ldo, lse, key_pad, B, H, Tq, Tk, dh, mask_mode, img, as_stream(stream));
+}
+
+int skf_attn_bwd_img(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv,
+                     const float* O, int64_t ldo, const float* dO, int64_t lddo, const float* lse, float* delta,
+                     float* dQ, int64_t lddq, float* dK, int64_t lddk, float* dV, int64_t lddv, const uint8_t* key_pad,
+                     int B, int H, int Tq, int Tk, int dh, int mask_mode, const void* img, void* img_do, void* stream) {
+  return attn3_bwd(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, key_pad, B, H,
+                   Tq, Tk, dh, mask_mode, img, img_do, as_stream(stream));
+}
+
 int skf_debug_trace(int64_t* out, int n) {
   SKF_REQUIRE(out != nullptr && n > 0, SKF_ERR_BAD_ARG, "debug_trace: bad argument");
   return skf::attn3_trace_dump(reinterpret_cast<long long*>(out), n);

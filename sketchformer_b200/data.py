@@ -137,6 +137,9 @@ class DistributedStroke3DataLoader:
             except Exception:      # noqa: BLE001
                 device = None
         self.device = device
+        # the prefetch threads of the three splits share one stream and one centre table on the device: chunks are
+        # tokenised one at a time (tensors allocated, used and freed on that stream only)
+        self._device_lock = threading.Lock()
         if not self.hps["use_continuous_data"] and tokenizer is None:      # distributed_stroke3.py:32-36
             from .tokenizer import GridTokenizer, Tokenizer
             if self.hps["token_type"] == "dictionary":
@@ -227,13 +230,16 @@ class DistributedStroke3DataLoader:
             # one kernel launch for the whole chunk, on the loader's own stream (this runs in the prefetch thread while
             # the train step owns the device's other streams); bit-identical to the host loop below
             import torch
-            with torch.cuda.device(self.device):
+            with self._device_lock, torch.cuda.device(self.device):
                 if self._loader_stream is None:
                     self._loader_stream = torch.cuda.Stream(self.device)
                 with torch.cuda.stream(self._loader_stream):
                     tok = self.preprocess_on_device(list(data), self.device)
                     out = tok if self.device_batches else tok.cpu().numpy()
                     self._loader_stream.synchronize()
+                if self.device_batches:
+                    # the chunk outlives this stream context: the train step reads it from its own stream
+                    out.record_stream(torch.cuda.current_stream(self.device))
             return out
         T, out = self.hps["max_seq_len"], []
         shuffle, absolute = bool(self.hps["shuffle_stroke"]), bool(self.hps["use_absolute_strokes"])

@@ -291,8 +291,15 @@ def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed, fwd_backend=1, bwd_backend=1, 
     qd, kd, vd = dev(q.detach().float()), dev(k.detach().float()), dev(v.detach().float())
     od = torch.empty(B, Tq, d, device="cuda"); lse = torch.empty(B, H, Tq, device="cuda")
     padd = dev(pad.to(torch.uint8)) if mode >= 1 else None
-    _lib.check(lib.skf_attn_fwd(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(lse), ptr(padd), B, H, Tq, Tk, dh,
-                                mode, 0, fwd_backend, stream()))
+    img = img_do = None
+    if fwd_backend == 7:          # whole-row kernels with operand images (what the plan runs in training)
+        img = torch.empty(lib.skf_attn_image_bytes(B, H, Tq, Tk, 0), dtype=torch.uint8, device="cuda")
+        img_do = torch.empty(lib.skf_attn_image_bytes(B, H, Tq, Tk, 1), dtype=torch.uint8, device="cuda")
+        _lib.check(lib.skf_attn_fwd_img(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(lse), ptr(padd), B, H, Tq, Tk,
+                                        dh, mode, ptr(img), stream()))
+    else:
+        _lib.check(lib.skf_attn_fwd(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(lse), ptr(padd), B, H, Tq, Tk, dh,
+                                    mode, 0, fwd_backend, stream()))
     e_o = rel_err(od, o)
     e_lse = rel_err(lse, torch.logsumexp((O.split_heads(q, H) @ O.split_heads(k, H).transpose(-1, -2)).detach() / dh ** 0.5
                                          + (mask * -1e9 if mask is not None else 0), -1))
@@ -300,8 +307,13 @@ def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed, fwd_backend=1, bwd_backend=1, 
     dq = torch.empty_like(qd); dk = torch.empty_like(kd); dv = torch.empty_like(vd)
     delta = torch.empty(B, H, Tq, device="cuda")
     do_d = dev(do)
-    _lib.check(lib.skf_attn_bwd(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(do_d), d, ptr(lse), ptr(delta),
-                                ptr(dq), d, ptr(dk), d, ptr(dv), d, ptr(padd), B, H, Tq, Tk, dh, mode, 0, bwd_backend, stream()))
+    if fwd_backend == 7:
+        _lib.check(lib.skf_attn_bwd_img(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(do_d), d, ptr(lse), ptr(delta),
+                                        ptr(dq), d, ptr(dk), d, ptr(dv), d, ptr(padd), B, H, Tq, Tk, dh, mode, ptr(img),
+                                        ptr(img_do), stream()))
+    else:
+        _lib.check(lib.skf_attn_bwd(ptr(qd), d, ptr(kd), d, ptr(vd), d, ptr(od), d, ptr(do_d), d, ptr(lse), ptr(delta),
+                                    ptr(dq), d, ptr(dk), d, ptr(dv), d, ptr(padd), B, H, Tq, Tk, dh, mode, 0, bwd_backend, stream()))
     return e_o, rel_err(dq, q.grad), rel_err(dk, k.grad), rel_err(dv, v.grad)
 
 
@@ -359,6 +371,16 @@ def test_attention_tcgen05_whole_row(lib, B, H, Tq, Tk, dh, mode):
     assert max(e_q, e_k, e_v) < (TOL_ATTN3 if ATTN3_BWD == 6 else TOL_ATTN_X3), (e_q, e_k, e_v)
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,mode", [c for c in TC_ATTN3 if c[2] == c[3] or c[5] == 2])
+def test_attention_tcgen05_whole_row_with_images(lib, B, H, Tq, Tk, dh, mode):
+    """The training configuration of the whole-row kernels: the forward pass writes the bf16 operand images, the
+    backward kernels load them directly (skf_attn_fwd_img / skf_attn_bwd_img)."""
+    if mode == 2 and Tq != Tk:
+        Tk = Tq
+    errs = _attn_case(lib, B, H, Tq, Tk, dh, mode, 500 + Tq, fwd_backend=7, bwd_backend=7)
+    assert max(errs) < TOL_ATTN3, errs
+
+
 def test_attention_whole_row_padding_patterns(lib):
     """The whole-row kernels drop the key columns (dK / dV: key tiles) past an item's last unpadded key.  Masks that
     are not a padded tail must still follow the reference's additive -1e9 exactly (builders/utils.py:93-97): padded
@@ -379,6 +401,8 @@ def test_attention_whole_row_padding_patterns(lib):
     for Tq, Tk in ((200, 200), (70, 200), (200, 131)):
         e_o, e_q, e_k, e_v = _attn_case(lib, 6, 2, Tq, Tk, 32, 1, 900 + Tq + Tk, fwd_backend=6, bwd_backend=6, pad_edit=edit)
         assert max(e_o, e_q, e_k, e_v) < TOL_ATTN3, (Tq, Tk, e_o, e_q, e_k, e_v)
+    e_o, e_q, e_k, e_v = _attn_case(lib, 6, 2, 200, 200, 32, 1, 1300, fwd_backend=7, bwd_backend=7, pad_edit=edit)
+    assert max(e_o, e_q, e_k, e_v) < TOL_ATTN3, ("images", e_o, e_q, e_k, e_v)
 
 
 MAJORS = [("fwd", False, True), ("dgrad", False, False), ("wgrad", True, True), ("tn", True, False)]

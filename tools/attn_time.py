@@ -13,7 +13,7 @@ from sketchformer_b200.ops import ptr, stream
 lib = _lib.load()
 B, H, dh = 128, 8, 32
 d = H * dh
-backends = [int(x) for x in sys.argv[1:]] or [2, 6]
+backends = [int(x) for x in sys.argv[1:]] or [2, 6, 7]        # 7 = whole-row kernels with operand images
 for (T, mode) in ((200, 1), (199, 2)):
     g = torch.Generator(device="cuda").manual_seed(0)
     qkv = torch.randn(B * T, 3 * d, device="cuda", generator=g)
@@ -22,11 +22,22 @@ for (T, mode) in ((200, 1), (199, 2)):
     dqkv = torch.empty_like(qkv)
     pad = (torch.arange(T, device="cuda")[None, :] >= torch.randint(T // 3, T + 1, (B, 1), device="cuda")).to(torch.uint8).contiguous()
 
+    img = torch.empty(lib.skf_attn_image_bytes(B, H, T, T, 0), dtype=torch.uint8, device="cuda")
+    img_do = torch.empty(lib.skf_attn_image_bytes(B, H, T, T, 1), dtype=torch.uint8, device="cuda")
+
     def fwd(be):
+        if be == 7:
+            return _lib.check(lib.skf_attn_fwd_img(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d,
+                                                   ptr(lse), ptr(pad), B, H, T, T, dh, mode, ptr(img), stream()))
         _lib.check(lib.skf_attn_fwd(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d, ptr(lse),
                                     ptr(pad), B, H, T, T, dh, mode, 0, be, stream()))
 
     def bwd(be):
+        if be == 7:
+            return _lib.check(lib.skf_attn_bwd_img(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d,
+                                                   ptr(dO), d, ptr(lse), ptr(delta), ptr(dqkv), 3 * d, ptr(dqkv[:, d:]), 3 * d,
+                                                   ptr(dqkv[:, 2 * d:]), 3 * d, ptr(pad), B, H, T, T, dh, mode, ptr(img),
+                                                   ptr(img_do), stream()))
         _lib.check(lib.skf_attn_bwd(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d, ptr(dO), d,
                                     ptr(lse), ptr(delta), ptr(dqkv), 3 * d, ptr(dqkv[:, d:]), 3 * d, ptr(dqkv[:, 2 * d:]), 3 * d,
                                     ptr(pad), B, H, T, T, dh, mode, 0, be, stream()))

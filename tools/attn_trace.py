@@ -18,15 +18,17 @@ pad = (torch.arange(T, device="cuda")[None, :] >= torch.randint(T // 3, T + 1, (
 which = sys.argv[3] if len(sys.argv) > 3 else "fwd"
 dO = torch.randn(B * T, d, device="cuda") * 1e-3
 delta = torch.empty(B, H, T, device="cuda"); dqkv = torch.empty_like(qkv)
+img = torch.empty(lib.skf_attn_image_bytes(B, H, T, T, 0), dtype=torch.uint8, device="cuda")
+img_do = torch.empty(lib.skf_attn_image_bytes(B, H, T, T, 1), dtype=torch.uint8, device="cuda")
 for i in range(3):
     if i == 2:
         _lib.check(lib.skf_set_option(b"attn3_trace", 1 if which == "fwd" else (2 if which == "dq" else 3)))
-    _lib.check(lib.skf_attn_fwd(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d, ptr(lse),
-                                ptr(pad), B, H, T, T, dh, mode, 0, 6, stream()))
+    _lib.check(lib.skf_attn_fwd_img(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d, ptr(lse),
+                                    ptr(pad), B, H, T, T, dh, mode, ptr(img), stream()))
     if which != "fwd":
-        _lib.check(lib.skf_attn_bwd(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d, ptr(dO), d,
-                                    ptr(lse), ptr(delta), ptr(dqkv), 3 * d, ptr(dqkv[:, d:]), 3 * d, ptr(dqkv[:, 2 * d:]), 3 * d,
-                                    ptr(pad), B, H, T, T, dh, mode, 0, 6, stream()))
+        _lib.check(lib.skf_attn_bwd_img(ptr(qkv), 3 * d, ptr(qkv[:, d:]), 3 * d, ptr(qkv[:, 2 * d:]), 3 * d, ptr(O), d, ptr(dO), d,
+                                        ptr(lse), ptr(delta), ptr(dqkv), 3 * d, ptr(dqkv[:, d:]), 3 * d, ptr(dqkv[:, 2 * d:]), 3 * d,
+                                        ptr(pad), B, H, T, T, dh, mode, ptr(img), ptr(img_do), stream()))
 torch.cuda.synchronize()
 print("key lengths of CTA 0's items:", [(int((pad[(i * 148) // H] == 0).sum())) for i in range(7)])
 buf = (C.c_int64 * 512)()
