@@ -691,7 +691,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
   Ctx c;
   prologue(c, smem_raw);
   const int QP = (a.Tq + 15) & ~15, KP = (a.Tk + 15) & ~15, TP = QP > KP ? QP : KP;
-  constexpr int NTILES = DKV ? 12 : 10;
+  constexpr int NTILES = 12;
   const Smem L = smem_plan(TP, NTILES, DKV ? 6 : 4, a.nst);
   const int tid = c.tid, warp = c.warp, lane = c.lane;
   const uint32_t base = c.base;
@@ -704,13 +704,13 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
   const int ntiles = TL > 128 ? 2 : 1;
   const int nhalf = TC > HALF ? 2 : 1;
   // operand slots.  op index: 0 = K, 1 = Q, 2 = V, 3 = dO.  Double-buffered ops get two slot pairs.
-  //   dq : K -> slots {0, 2} (+buf*2)   Q -> 4   V -> 6   dO -> 8
+  //   dq : K -> slots {0, 2} (+buf*2)   Q -> 4   V -> 6   dO -> {8, 10}
   //   dkv: Q -> slots {0, 2}            dO -> {4, 6}      K -> 8   V -> 10
   auto slot = [&](int op, int buf) -> int {
-    if (!DKV) return op == 0 ? 2 * buf : (op == 1 ? 4 : (op == 2 ? 6 : 8));
+    if (!DKV) return op == 0 ? 2 * buf : (op == 1 ? 4 : (op == 2 ? 6 : 8 + 2 * buf));
     return op == 1 ? 2 * buf : (op == 3 ? 4 + 2 * buf : (op == 0 ? 8 : 10));
   };
-  auto is_db = [&](int op) { return DKV ? (op == 1 || op == 3) : op == 0; };
+  auto is_db = [&](int op) { return DKV ? (op == 1 || op == 3) : (op == 0 || op == 3); };
   auto nch_of = [&](int op) { return (op == 0 || op == 2) ? nk_ch : nq_ch; };
   // vectors: [0,256) / [256,512): per-item bias of the keys (dq: column side, dkv: lane side), double-buffered;
   // [512,768) / [768,1024): dq: delta of the item's queries; dkv: interleaved (lse2, delta) pairs need 2 x 256 x 2
@@ -780,13 +780,16 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         const int b = it / a.H, h = it % a.H;
         if (a.direct) {
           const int buf = pli & 1;
-          mbar_wait_sleep(bar(DB_EMPTY + buf), ((pli >> 1) & 1u) ^ 1u);
+          if (DKV) mbar_wait_sleep(bar(DB_EMPTY + buf), ((pli >> 1) & 1u) ^ 1u);
           if (!DKV) {
+            // dO through the ring (fp32 -> tiles) first: the ring does not depend on any operand buffer, so these
+            // rows are in flight a whole item ahead
+            for (int ch = 0; ch < nq_ch; ch++) load(&mdO, h, 64 * ch, b);
+            mbar_wait_sleep(bar(DB_EMPTY + buf), ((pli >> 1) & 1u) ^ 1u);
             load_img(&mImg, 0, buf, it, 0);                                  // K (double-buffered)
             mbar_wait_sleep(bar(SB_EMPTY), (pli & 1u) ^ 1u);
             load_img(&mImg, 1, buf, it, 1);                                  // Q
             load_img(&mImg, 2, buf, it, 2);                                  // V
-            for (int ch = 0; ch < nq_ch; ch++) load(&mdO, h, 64 * ch, b);    // dO through the ring (fp32 -> tiles)
           } else {
             load_img(&mImg, 1, buf, it, 1);                                  // Q  (double-buffered)
             load_img(&mImgDo, 3, buf, it, 0);                                // dO (double-buffered)
@@ -798,10 +801,10 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         }
         // order = order of first use: dq K, Q, V, (O, dO) pairs; dkv Q, dO, K, V
         if (!DKV) {
+          for (int ch = 0; ch < nq_ch; ch++) load(&mdO, h, 64 * ch, b);
           for (int ch = 0; ch < nk_ch; ch++) load(&mK, h, 64 * ch, b);
           for (int ch = 0; ch < nq_ch; ch++) load(&mQ, h, 64 * ch, b);
           for (int ch = 0; ch < nk_ch; ch++) load(&mV, h, 64 * ch, b);
-          for (int ch = 0; ch < nq_ch; ch++) load(&mdO, h, 64 * ch, b);
         } else {
           for (int ch = 0; ch < nq_ch; ch++) load(&mQ, h, 64 * ch, b);
           for (int ch = 0; ch < nq_ch; ch++) load(&mdO, h, 64 * ch, b);
@@ -875,19 +878,11 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       };
       if (DKV && a.direct) continue;          // every operand arrives as an image: only the vectors above
       if (!DKV) {
-        if (!a.direct) {
-          conv(0, false);          // K (double-buffered)
-          conv(1, true);           // Q
-          conv(2, false);          // V
-        } else {
-          // dO is single-buffered: the previous item's score MMAs have completed, and its image store has read the tile
-          mbar_wait_sleep(bar(SB_EMPTY), (li & 1u) ^ 1u);
-          if (a.img_do) {
-            if (ct == 0) bulk_wait_read0();
-            conv_bar_sync();
-          }
+        if (a.img_do) {            // the image stores of the earlier items have read their dO tiles
+          if (ct == 0) bulk_wait_read0();
+          conv_bar_sync();
         }
-        // (O, dO) chunk pairs: delta = rowsum(dO * O) from the fp32 values, dO -> tiles
+        // dO chunks first (double-buffered tile): delta = rowsum(dO * O) from the fp32 values, dO -> tiles
         float* del_s = vec + 512 + buf * 256;
         uint8_t* hi = gen + L.tiles + slot(3, buf) * L.tile_bytes;
         uint8_t* lo = hi + L.tile_bytes;
@@ -912,6 +907,11 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           tma_store_2d(&mImgDo, smem_u32(hi), 0, it * TP);
           tma_store_2d(&mImgDo, smem_u32(lo), 0, (n_items + it) * TP);
           bulk_commit();
+        }
+        if (!a.direct) {
+          conv(0, false);          // K (double-buffered)
+          conv(1, true);           // Q
+          conv(2, false);          // V
         }
       } else {
         conv(1, false);          // Q  (double-buffered)
@@ -1281,8 +1281,8 @@ int attn3_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   {
     a.img_do = a.direct;
     a.out0 = dQ; a.ld0 = lddq; a.out1 = delta; a.delta = nullptr; a.trace = g_a3_trace == 2;
-    a.nst = a3_ring_stages(TP, 10, 4);
-    const int smem = (int)a3::smem_plan(TP, 10, 4, a.nst).total + 1024;
+    a.nst = a3_ring_stages(TP, 12, 4);
+    const int smem = (int)a3::smem_plan(TP, 12, 4, a.nst).total + 1024;
     if (mode == 2) {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<false, true>, smem));
       a3::attn3_bwd_k<false, true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
