@@ -677,7 +677,8 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
 namespace bw {
 enum { RING_FULL = 0, RING_EMPTY = NST, OP_FULL = 2 * NST /* [2 bufs][4 ops] */, DB_EMPTY = 2 * NST + 8 /* [2] */,
        SB_EMPTY = 2 * NST + 10, SP_FULL = 2 * NST + 11 /* [2] */, DS_FULL = 2 * NST + 13 /* [2] */,
-       ACC_FULL = 2 * NST + 15, ACC_FREE = 2 * NST + 16, VEC_FULL = 2 * NST + 17 /* [2] */, COUNT = 2 * NST + 19 };
+       ACC_FULL = 2 * NST + 15 /* [2]: one per epilogue warpgroup */, ACC_FREE = 2 * NST + 17,
+       VEC_FULL = 2 * NST + 18 /* [2] */, COUNT = 2 * NST + 20 };
 }
 
 template <bool DKV, bool CAUSAL>
@@ -734,7 +735,12 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
       mbar_init(bar(SP_FULL + w), 1);
       mbar_init(bar(DS_FULL + w), 4);
     }
+    // dq: the warpgroups take turns at the epilogue, so each gets its OWN "accumulator ready" barrier and sees every
+    // phase of it.  (With one barrier a warpgroup waited on every other phase; a warpgroup that ran ahead — short
+    // sequences make a unit's math shorter than the MMA issue — found the parity of the phase before last already
+    // complete and read the accumulators of a unit that had not finished.)
     mbar_init(bar(ACC_FULL), 1);
+    mbar_init(bar(ACC_FULL + 1), 1);
     mbar_init(bar(ACC_FREE), 4);
     fence_barrier_init();
   }
@@ -976,7 +982,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
               mma_av_32(tAcc + 32, tmem + MAXT * w + HALF, Qh, Qh + L.tile_bytes, HALF * w, ks, idesc32, w > 0);  // dK += dS^T Q
             }
             if (w == nhalf - 1) {
-              tc_commit(bar(ACC_FULL));
+              tc_commit(bar(ACC_FULL + ((DKV || nhalf == 1) ? 0 : (t & 1))));
               if (last_tile) tc_commit(bar(DB_EMPTY + buf));     // last reader of the double-buffered operands
             }
             if (has_next) {
@@ -1026,7 +1032,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     int pb = 0, ph = 0, prow = 0;
     uint32_t pu = 0;
     if (w < nhalf) {
-      uint32_t li = 0, u = 0;
+      uint32_t li = 0, u = 0, nepi = 0;           // nepi: dq epilogues this warpgroup has done
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, li++) {
         const int b = it / a.H, h = it % a.H, buf = li & 1;
         const int64_t bh = (int64_t)b * a.H + h;
@@ -1121,7 +1127,8 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           // the tensor core finished long before (phase trace profiles/r2_a13_trace_dkv.log).
           if (!DKV) {
             if (nhalf == 1 || (t & 1) == w) {
-              mbar_wait_sleep(bar(ACC_FULL), u & 1u);
+              mbar_wait_sleep(bar(ACC_FULL + w), nepi & 1u);
+              nepi++;
               tc_fence_after();
               if (row == 0) stamp(a.trace, 1 + w, li, 4 * t + 2);
               uint32_t o0[32], o1[32];

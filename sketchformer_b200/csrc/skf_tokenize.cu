@@ -12,9 +12,10 @@ namespace skf {
 
 constexpr int TK_MAX_T = 1024;
 
+// The inputs are read with plain (coherent) loads, not through the read-only path: they are uploaded by the loader's
+// prefetch thread right before the launch and the buffers are recycled from chunk to chunk.
 __global__ void __launch_bounds__(256)
-tokenize_strokes_k(const float* __restrict__ pts, const int64_t* __restrict__ offs, const float* __restrict__ cent,
-                   int K, float limit, int64_t* __restrict__ out, int T) {
+tokenize_strokes_k(const float* pts, const int64_t* offs, const float* cent, int K, float limit, int64_t* out, int T) {
   extern __shared__ float sm_c[];                 // K x 2 centres
   __shared__ int s_pos[TK_MAX_T];                 // token position of point i (i < T)
   __shared__ float s_inv[2];                      // max_dim (as float), unused slot
@@ -23,16 +24,16 @@ tokenize_strokes_k(const float* __restrict__ pts, const int64_t* __restrict__ of
   const int64_t p0 = offs[b];
   const int n = (int)(offs[b + 1] - p0);
   const float* P = pts + p0 * 3;
-  for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) sm_c[i] = cent[i];
+  for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) sm_c[i] = __ldcg(cent + i);
   int64_t* row = out + (int64_t)b * T;
   for (int t = threadIdx.x; t < T; t += blockDim.x) row[t] = 0;   // PAD
   if (threadIdx.x == 0) {
     double ax = 0.0, ay = 0.0, mnx = 0.0, mxx = 0.0, mny = 0.0, mxy = 0.0;
     int lifts = 0;
     for (int i = 0; i < n; i++) {
-      const float x = fminf(fmaxf(P[3 * i], -limit), limit);
-      const float y = fminf(fmaxf(P[3 * i + 1], -limit), limit);
-      const float pen = fminf(fmaxf(P[3 * i + 2], -limit), limit);
+      const float x = fminf(fmaxf(__ldcg(P + 3 * i), -limit), limit);
+      const float y = fminf(fmaxf(__ldcg(P + 3 * i + 1), -limit), limit);
+      const float pen = fminf(fmaxf(__ldcg(P + 3 * i + 2), -limit), limit);
       ax += (double)x; ay += (double)y;
       mnx = fmin(mnx, ax); mxx = fmax(mxx, ax); mny = fmin(mny, ay); mxy = fmax(mxy, ay);
       if (i < T) s_pos[i] = 1 + i + lifts;
@@ -52,9 +53,9 @@ tokenize_strokes_k(const float* __restrict__ pts, const int64_t* __restrict__ of
   for (int i = threadIdx.x; i < np; i += blockDim.x) {
     const int pos = s_pos[i];
     if (pos >= T) continue;
-    const float x = __fdiv_rn(fminf(fmaxf(P[3 * i], -limit), limit), md);
-    const float y = __fdiv_rn(fminf(fmaxf(P[3 * i + 1], -limit), limit), md);
-    const float pen = fminf(fmaxf(P[3 * i + 2], -limit), limit);
+    const float x = __fdiv_rn(fminf(fmaxf(__ldcg(P + 3 * i), -limit), limit), md);
+    const float y = __fdiv_rn(fminf(fmaxf(__ldcg(P + 3 * i + 1), -limit), limit), md);
+    const float pen = fminf(fmaxf(__ldcg(P + 3 * i + 2), -limit), limit);
     float best = INFINITY;
     int arg = 0;
     for (int k = 0; k < K; k++) {

@@ -157,6 +157,15 @@ class DistributedStroke3DataLoader:
         self.class_names = md["class_names"]
         self.scale_factor = float(md["std"])
         self.splits = {n: _Split(n, [f for f in files if base(f).startswith(n)]) for n in ("train", "test", "valid")}
+        if self._device_path():
+            # before any prefetch thread exists: the centre table is uploaded and the tokeniser kernel has run once
+            # (module load, function attributes) on this thread, with the device idle afterwards
+            import torch
+            with torch.cuda.device(self.device):
+                self.tokenizer.prepare_device(self.device)
+                self.tokenizer.encode_batch_device([np.zeros((1, 3), np.float32)], int(self.hps["max_seq_len"]),
+                                                   self.device, float(self.limit))
+                torch.cuda.synchronize()
         tr = self.splits["train"]
         self._slice_samples = world_size > 1 and tr.n_files < world_size
         if world_size > 1 and not self._slice_samples:

@@ -112,6 +112,16 @@ class Tokenizer:
         return np.c_[dxy, np.asarray(pens, np.float32)]
 
     # ---- device path -----------------------------------------------------------------------
+    def prepare_device(self, device="cuda:0"):
+        """Uploads the centre table once and waits for the device: the table outlives every stream that will read it,
+        so its upload is not left to whichever prefetch thread happens to tokenise first."""
+        import torch
+        dev = torch.device(device)
+        if self._dev_centroids is None or self._dev_centroids.device != dev:
+            self._dev_centroids = torch.from_numpy(np.ascontiguousarray(self.centroids, np.float32)).to(dev).contiguous()
+            torch.cuda.synchronize(dev)
+        return self._dev_centroids
+
     def encode_batch_device(self, sketches, max_seq_len, device="cuda:0", limit=1000.0):
         """dataloaders/distributed_stroke3.py:90-125, 138-153 for a list of raw stroke-3 arrays, fused on the
         device: clip to +-limit, normalise by max(bbox_w, bbox_h, 1), nearest centre, SEP / SOS / EOS, truncate
@@ -127,8 +137,7 @@ class Tokenizer:
         flat = (np.concatenate([np.asarray(s, np.float32).reshape(-1, 3) for s in sketches]) if len(sketches)
                 else np.zeros((0, 3), np.float32))
         dev = torch.device(device)
-        if self._dev_centroids is None or self._dev_centroids.device != dev:
-            self._dev_centroids = torch.from_numpy(self.centroids).to(dev).contiguous()
+        self.prepare_device(dev)
         pts = torch.from_numpy(np.ascontiguousarray(flat)).to(dev)
         off_d = torch.from_numpy(offs).to(dev)
         out = torch.empty(len(sketches), max_seq_len, dtype=torch.int64, device=dev)

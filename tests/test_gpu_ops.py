@@ -269,13 +269,14 @@ def test_adam_matches_oracle(lib):
     assert rel_err(m, opt.m["a"]) < 1e-5 and rel_err(v, opt.v["a"]) < 1e-5
 
 
-def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed, fwd_backend=1, bwd_backend=1, pad_edit=None):
+def _attn_case(lib, B, H, Tq, Tk, dh, mode, seed, fwd_backend=1, bwd_backend=1, pad_edit=None, len_range=None):
     g = torch.Generator().manual_seed(seed)
     d = H * dh
     q = torch.randn(B, Tq, d, generator=g).double().requires_grad_(True)
     k = torch.randn(B, Tk, d, generator=g).double().requires_grad_(True)
     v = torch.randn(B, Tk, d, generator=g).double().requires_grad_(True)
-    lens = torch.randint(max(1, Tk // 3), Tk + 1, (B,), generator=g)
+    lo, hi = len_range or (max(1, Tk // 3), Tk)
+    lens = torch.randint(lo, hi + 1, (B,), generator=g)
     pad = (torch.arange(Tk)[None, :] >= lens[:, None])
     if pad_edit is not None:
         pad = pad_edit(pad.clone())
@@ -403,6 +404,18 @@ def test_attention_whole_row_padding_patterns(lib):
         assert max(e_o, e_q, e_k, e_v) < TOL_ATTN3, (Tq, Tk, e_o, e_q, e_k, e_v)
     e_o, e_q, e_k, e_v = _attn_case(lib, 6, 2, 200, 200, 32, 1, 1300, fwd_backend=7, bwd_backend=7, pad_edit=edit)
     assert max(e_o, e_q, e_k, e_v) < TOL_ATTN3, ("images", e_o, e_q, e_k, e_v)
+
+
+@pytest.mark.parametrize("backend", [6, 7])
+@pytest.mark.parametrize("T,mode", [(200, 1), (199, 2)])
+@pytest.mark.parametrize("len_range", [(2, 40), (23, 140), (100, 135)])
+def test_attention_whole_row_short_sequences_many_items(lib, backend, T, mode, len_range):
+    """Several (sample, head) items per CTA with SHORT sequences (the lengths the stroke3-distributed loader yields;
+    the synthetic batches never go below T / 4): a unit's row math is then shorter than the MMA issue, the regime in
+    which the dq kernel's warpgroups once read each other's accumulator phases."""
+    errs = _attn_case(lib, 64, 8, T, T, 32, mode, 1700 + T + len_range[0], fwd_backend=backend, bwd_backend=backend,
+                      len_range=len_range)
+    assert max(errs) < TOL_ATTN3, errs
 
 
 MAJORS = [("fwd", False, True), ("dgrad", False, False), ("wgrad", True, True), ("tn", True, False)]
