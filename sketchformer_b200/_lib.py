@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libskf.so")
+LIB_PATH = os.environ.get("SKF_LIB") or os.path.join(HERE, "libskf.so")     # SKF_LIB: a timing-experiment build (tools/)
 
 
 class SkfError(RuntimeError):
@@ -120,6 +120,11 @@ def load():
         if lib.skf_abi_sizeof(which) != C.sizeof(struct):
             raise SkfError(f"{struct.__name__}: ctypes layout ({C.sizeof(struct)} bytes) does not match libskf.so "
                            f"({lib.skf_abi_sizeof(which)} bytes): rebuild the library or update _lib.py")
+    # A/B switches for measurement runs: SKF_OPTIONS="pdl=0,attn3=3" -> skf_set_option(name, value) once at load
+    for clause in filter(None, os.environ.get("SKF_OPTIONS", "").split(",")):
+        name, _, value = clause.partition("=")
+        if lib.skf_set_option(name.strip().encode(), int(value)) != 0:
+            raise SkfError(f"SKF_OPTIONS: unknown option {name!r}")
     _lib = lib
     return lib
 

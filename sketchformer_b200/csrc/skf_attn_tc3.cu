@@ -241,6 +241,7 @@ struct Args {
   // backward kernels TMA-load them straight into their operand slots instead of pulling fp32 rows through the ring and
   // the converter warps again (direct != 0).  Tile row of (op, hl, item) in the image map: ((2 op + hl) n_items + item) TP
   int img, img_do, direct;
+  int pdl_late;               // the TMA producer releases the next kernel after its last load instead of after the prologue
 };
 
 // D[128 x N] = Ah Bh^T + Ah Bl^T + Al Bh^T: A rows [a_row0, +128) of the K-major tiles (ah, al), B rows [b_row0, +N)
@@ -312,7 +313,7 @@ __device__ __forceinline__ void prologue(Ctx& c, uint8_t* smem_raw) {
   c.gen = smem_raw + (c.base - raw);
   c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
 }
-__device__ __forceinline__ void alloc_tmem(Ctx& c, uint32_t slot_off) {
+__device__ __forceinline__ void alloc_tmem(Ctx& c, uint32_t slot_off, int pdl_late) {
   if (c.warp == 1) {
     tmem_alloc(c.base + slot_off, 512);
     tmem_relinquish();
@@ -321,6 +322,10 @@ __device__ __forceinline__ void alloc_tmem(Ctx& c, uint32_t slot_off) {
   __syncthreads();
   tc_fence_after();
   c.tmem = *reinterpret_cast<volatile uint32_t*>(c.gen + slot_off);
+  // tensor memory is ours: the next kernel of the stream may become resident (programmatic dependent launch); this
+  // one touches global memory only from here on
+  if (!pdl_late) pdl_trigger();
+  pdl_wait();
 }
 __device__ __forceinline__ void epilogue_free(const Ctx& c) {
   tc_fence_before();
@@ -376,7 +381,7 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     fence_barrier_init();
   }
   for (int i = tid; i < 1024; i += THREADS) reinterpret_cast<uint32_t*>(gen + L.vec - 4096)[i] = 0u;
-  alloc_tmem(c, L.bars + 8u * COUNT);
+  alloc_tmem(c, L.bars + 8u * COUNT, a.pdl_late);
   const uint32_t tmem = c.tmem;
   const uint32_t tS[2] = {tmem, tmem + MAXT}, tO = tmem + 2 * MAXT;
   // key columns a query tile needs: causal tiles never look past their last row
@@ -408,6 +413,7 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           }
         }
       }
+      if (a.pdl_late) pdl_trigger();
     }
   } else if (warp >= 2 && warp < 2 + NCONV) {
     // ================= converters =================
@@ -745,7 +751,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
     fence_barrier_init();
   }
   for (int i = tid; i < 1024; i += THREADS) reinterpret_cast<uint32_t*>(gen + L.vec - 4096)[i] = 0u;
-  alloc_tmem(c, L.bars + 8u * COUNT);
+  alloc_tmem(c, L.bars + 8u * COUNT, a.pdl_late);
   const uint32_t tmem = c.tmem;
   const uint32_t tAcc = tmem + 2 * MAXT;
   // columns unit (lane tile t, half w) covers: [HALF w, HALF w + ncols)
@@ -818,6 +824,7 @@ attn3_bwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
           for (int ch = 0; ch < nk_ch; ch++) load(&mV, h, 64 * ch, b);
         }
       }
+      if (a.pdl_late) pdl_trigger();
     }
   } else if (warp >= 2 && warp < 2 + NCONV) {
     // ================= converters =================
@@ -1235,6 +1242,7 @@ int attn3_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   memset(&a, 0, sizeof(a));
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.mode = mode; a.scale = 1.0f / sqrtf((float)dh);
   a.trace = g_a3_trace == 1;
+  a.pdl_late = (g_pdl & PDL_LATE) != 0;
   a.key_pad = key_pad; a.out0 = O; a.ld0 = ldo; a.out1 = lse;
   const int QP = (Tq + 15) & ~15, KP = (Tk + 15) & ~15, TP = QP > KP ? QP : KP;
   CUtensorMap mImg = mQ;
@@ -1245,10 +1253,10 @@ int attn3_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   const int grid = B * H < a3_sm_count() ? B * H : a3_sm_count();
   if (mode == 2) {
     SKF_TRY(a3_attr(a3::attn3_fwd_k<true>, smem));
-    a3::attn3_fwd_k<true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mImg, a);
+    launch_k(a3::attn3_fwd_k<true>, dim3(grid), dim3(a3::THREADS), smem, st, PDL_ATTN, mQ, mK, mV, mImg, a);
   } else {
     SKF_TRY(a3_attr(a3::attn3_fwd_k<false>, smem));
-    a3::attn3_fwd_k<false><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mImg, a);
+    launch_k(a3::attn3_fwd_k<false>, dim3(grid), dim3(a3::THREADS), smem, st, PDL_ATTN, mQ, mK, mV, mImg, a);
   }
   SKF_LAUNCH_CHECK();
   return SKF_OK;
@@ -1276,6 +1284,7 @@ int attn3_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
   memset(&a, 0, sizeof(a));
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.mode = mode; a.scale = 1.0f / sqrtf((float)dh);
   a.key_pad = key_pad; a.lse = lse; a.O = O; a.ldO = ldo;
+  a.pdl_late = (g_pdl & PDL_LATE) != 0;
   const int QP = (Tq + 15) & ~15, KP = (Tk + 15) & ~15, TP = QP > KP ? QP : KP;
   const int grid = B * H < a3_sm_count() ? B * H : a3_sm_count();
   // with the forward kernel's operand images (and room for dO's) the backward kernels load bf16 tiles directly
@@ -1292,10 +1301,10 @@ int attn3_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
     const int smem = (int)a3::smem_plan(TP, 12, 4, a.nst).total + 1024;
     if (mode == 2) {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<false, true>, smem));
-      a3::attn3_bwd_k<false, true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
+      launch_k(a3::attn3_bwd_k<false, true>, dim3(grid), dim3(a3::THREADS), smem, st, PDL_ATTN, mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
     } else {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<false, false>, smem));
-      a3::attn3_bwd_k<false, false><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
+      launch_k(a3::attn3_bwd_k<false, false>, dim3(grid), dim3(a3::THREADS), smem, st, PDL_ATTN, mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
     }
     SKF_LAUNCH_CHECK();
   }
@@ -1306,10 +1315,10 @@ int attn3_bwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const fl
     const int smem = (int)a3::smem_plan(TP, 12, 6, a.nst).total + 1024;
     if (mode == 2) {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<true, true>, smem));
-      a3::attn3_bwd_k<true, true><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
+      launch_k(a3::attn3_bwd_k<true, true>, dim3(grid), dim3(a3::THREADS), smem, st, PDL_ATTN, mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
     } else {
       SKF_TRY(a3_attr(a3::attn3_bwd_k<true, false>, smem));
-      a3::attn3_bwd_k<true, false><<<grid, a3::THREADS, smem, st>>>(mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
+      launch_k(a3::attn3_bwd_k<true, false>, dim3(grid), dim3(a3::THREADS), smem, st, PDL_ATTN, mQ, mK, mV, mdO, mO, mImg, mImgDo, a);
     }
     SKF_LAUNCH_CHECK();
   }

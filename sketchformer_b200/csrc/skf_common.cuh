@@ -46,6 +46,48 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch ---------------------------------------------------------
+// A kernel launched through launch_k(..., pdl = true) may become resident while the previous kernel of its stream is
+// still running: its prologue (barrier init, tensor-memory allocation, tensor-map prefetch, block scheduling)
+// overlaps that kernel's tail.  It must not touch global memory before pdl_wait() returns — the previous grid has
+// then completed and its writes are visible (this also covers write-after-read on reused buffers).  A kernel lets its
+// successor start early with pdl_trigger(), issued by every CTA AFTER it has taken the resources it needs (tensor
+// memory above all: a successor that allocated first would hold them while it waits for this grid).  Both are no-ops
+// when the launch carried no programmatic attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
+
+// skf_set_option("pdl", mask): which launches carry the attribute — 1 the SIMT kernels (LayerNorm, losses, embeddings,
+// folded cross attention ...), 2 the tcgen05 GEMMs, 4 the tcgen05 attention kernels; 8: the tcgen05 kernels trigger
+// LATE (their TMA producer, once it has issued its last load) instead of right after their prologue, so that a
+// successor does not sit on SMs the low-priority weight-gradient stream could have used during the tail.
+extern int g_pdl;
+constexpr int PDL_SIMT = 1, PDL_GEMM = 2, PDL_ATTN = 4, PDL_LATE = 8;
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialisation attribute when the option has the bit `pdl`.
+// Only kernels that call pdl_wait() / pdl_enter() before their first global access may pass a non-zero class.
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int pdl,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  if (pdl & g_pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // the error is picked up by SKF_LAUNCH_CHECK()
+}
+
 // ---- warp helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -135,6 +135,7 @@ gemm2_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_enter();      // tensor memory is ours: the next kernel may become resident; nothing global was touched yet
 
   // tile t -> (split z, row block, column block), n fastest
   auto tile_coords = [&](int t, int& m0, int& n0, int& kb, int& nkb) {
@@ -409,7 +410,7 @@ static int launch_tc2(const CUtensorMap* tm, const Gemm2Params& p, cudaStream_t 
   }
   const int ntiles = p.mt * p.nt * p.splits;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  gemm2_k<BN, A_MN, B_MN, X3><<<grid, C::THREADS, C::SMEM, st>>>(tm[0], tm[1], tm[2], p);
+  launch_k(gemm2_k<BN, A_MN, B_MN, X3>, dim3(grid), dim3(C::THREADS), C::SMEM, st, PDL_GEMM, tm[0], tm[1], tm[2], p);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }

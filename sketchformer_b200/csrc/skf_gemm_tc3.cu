@@ -88,6 +88,11 @@ struct Gemm3Params {
   int M, N, K;
   int k_chunk;
   int mt, nt, splits;   // cluster-tile grid (mt counts 256-row blocks)
+  int pdl_late;         // the TMA producer releases the next kernel after its last load instead of after the prologue
+  // Tail split: the last `ntiles - tail_first` cluster tiles are done as two half-width units each (columns
+  // [n0, n0 + BN/2) and [n0 + BN/2, n0 + BN)), so that e.g. 100 tiles on 74 clusters are 74 full units and one SHORT
+  // wave of 52 half units instead of two full waves; units = tail_first + 2 (ntiles - tail_first).
+  int tail_first, nunits;
   skf_gemm_epilogue e;
 };
 
@@ -279,7 +284,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int nclusters = gridDim.x >> 1;
-  const int ntiles = p.mt * p.nt * p.splits;
+  const int ntiles = p.nunits;          // work units: whole cluster tiles, then the half-width units of the tail
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -305,14 +310,22 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // tensor memory is ours: the next kernel of the stream may become resident (programmatic dependent launch); this
+  // one touches global memory only from here on
+  if (!p.pdl_late) pdl_trigger();
+  pdl_wait();
 
-  auto tile_coords = [&](int t, int& m0, int& n0, int& kb, int& nkb) {
+  // unit u -> rows, first column, k range and width (BN, or BN / 2 for a unit of the split tail)
+  auto tile_coords = [&](int u, int& m0, int& n0, int& kb, int& nkb, int& ncols) {
+    const int half = u < p.tail_first ? -1 : ((u - p.tail_first) & 1);
+    const int t = u < p.tail_first ? u : p.tail_first + ((u - p.tail_first) >> 1);
     const int n = t % p.nt;
     const int r = t / p.nt;
     const int m = r % p.mt;
     const int z = r / p.mt;
     m0 = m * (2 * T3_BM) + (int)rank * T3_BM;     // this CTA's rows
-    n0 = n * T3_BN;
+    n0 = n * T3_BN + (half > 0 ? T3_BN / 2 : 0);
+    ncols = half < 0 ? T3_BN : T3_BN / 2;
     kb = z * p.k_chunk;
     const int ke = min(p.K, kb + p.k_chunk);
     nkb = (ke - kb + T3_BK - 1) / T3_BK;
@@ -323,9 +336,11 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = cluster_id; t < ntiles; t += nclusters) {
-        int m0, n0, kb, nkb;
-        tile_coords(t, m0, n0, kb, nkb);
-        const int nh = n0 + (int)rank * T3_BNH;   // this CTA's half of the B tile
+        int m0, n0, kb, nkb, ncols;
+        tile_coords(t, m0, n0, kb, nkb, ncols);
+        // this CTA's half of the unit's B columns; a half-width unit still loads whole boxes (the MMA reads the
+        // first ncols / 2 rows of each CTA's tile)
+        const int nh = n0 + (int)rank * (ncols >> 1);
         for (int i = 0; i < nkb; i++, it++) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
@@ -362,16 +377,19 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           }
         }
       }
+      if (p.pdl_late) pdl_trigger();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(2 * T3_BM, T3_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_full = make_idesc_tf32(2 * T3_BM, T3_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_half = make_idesc_tf32(2 * T3_BM, T3_BN / 2, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t it = 0;
       int ti = 0;
       for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
-        int m0, n0, kb, nkb;
-        tile_coords(t, m0, n0, kb, nkb);
+        int m0, n0, kb, nkb, ncols;
+        tile_coords(t, m0, n0, kb, nkb, ncols);
+        const bool halfw = ncols != T3_BN;
         const int a = ti & 1;
         const uint32_t aph = (ti >> 1) & 1u;
         mbar_wait_cluster(tempty_bar(a), aph ^ 1u);     // both CTAs' epilogues have drained this accumulator
@@ -386,8 +404,10 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           const uint32_t b_s = a_s + T3_A_BYTES;
           const uint32_t al_s = a_s + T3_RAW;
           const uint32_t bl_s = al_s + T3_A_BYTES;
+          const uint32_t idesc = halfw ? idesc_half : idesc_full;
           if (MIX) {
-            constexpr uint32_t idesc16 = make_idesc_bf16(2 * T3_BM, T3_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            const uint32_t idesc16 = halfw ? make_idesc_bf16(2 * T3_BM, T3_BN / 2, A_MN ? 1 : 0, B_MN ? 1 : 0)
+                                           : make_idesc_bf16(2 * T3_BM, T3_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
             const uint32_t ah16 = a_s + T3_B16, al16 = ah16 + T3_A_BYTES / 2;
             const uint32_t bh16 = al16 + T3_A_BYTES / 2, bl16 = bh16 + C::B_BYTES / 2;
 #pragma unroll
@@ -442,8 +462,8 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     int ti = 0;
     uint32_t nstore = 0;
     for (int t = cluster_id; t < ntiles; t += nclusters, ti++) {
-      int m0, n0, kb, nkb;
-      tile_coords(t, m0, n0, kb, nkb);
+      int m0, n0, kb, nkb, ncols;
+      tile_coords(t, m0, n0, kb, nkb, ncols);
       const int a = ti & 1;
       const uint32_t aph = (ti >> 1) & 1u;
       mbar_wait(tfull_bar(a), aph);
@@ -452,7 +472,7 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
       const int m = mrow0 + lane;
       const bool row_ok = m < p.M;
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * T3_BN);
-      constexpr int NCH = T3_BN / 32;
+      const int NCH = ncols / 32;
 #pragma unroll 1
       for (int c = chalf; c < NCH; c += 2) {
         const int nb = n0 + c * 32;
@@ -551,8 +571,8 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
     float* colsum_s = reinterpret_cast<float*>(gen + S * T3_STAGE + T3_EPI_BYTES + 256);
     const int cq = (tid & 7) ^ (((tid >> 3) & 3) << 1);
     for (int t = cluster_id; t < ntiles; t += nclusters) {
-      int m0, n0, kb, nkb;
-      tile_coords(t, m0, n0, kb, nkb);
+      int m0, n0, kb, nkb, ncols;
+      tile_coords(t, m0, n0, kb, nkb, ncols);
       const bool do_colsum = B_MN && p.e.colsum != nullptr && m0 == (int)rank * T3_BM;   // row-block 0 only
       for (int i = 0; i < nkb; i++, it++) {
         const int s = it % S;
@@ -637,6 +657,7 @@ int g_gemm_mix = 2;       // 1: cross terms of the 3xTF32 product as bf16 MMAs, 
 int g_gemm_wsplit = 1;    // 1: the plan hands forward / dgrad products bf16 images of their weights (b_hi16 / b_lo16)
 
 int g_t3_oversubscribe = 0;
+int g_t3_tail_split = 1;  // 1: the tiles of a partial last wave are done as two half-width units each (Gemm3Params::tail_first)
 
 template <int BN, bool A_MN, bool B_MN, int MIX, bool WS = false>
 static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t st) {
@@ -662,12 +683,22 @@ static int launch_tc3(const CUtensorMap* tm, const Gemm3Params& p, cudaStream_t 
     }
     g3_clusters = nc < 1 ? 1 : nc;
   }
-  const int ntiles = p.mt * p.nt * p.splits;
+  int ntiles = p.mt * p.nt * p.splits;
+  Gemm3Params q = p;
+  q.tail_first = ntiles;
+  // a partial last wave of whole tiles costs a full tile time: when its tiles, halved, still fit one wave, halve them
+  // (forward / dgrad products only: split-K and the fused column sum keep whole tiles)
+  if (g_t3_tail_split && !g_t3_oversubscribe && p.splits == 1 && !p.e.accumulate && ntiles > g3_clusters) {
+    const int rem = ntiles % g3_clusters;
+    if (rem > 0 && 2 * rem <= g3_clusters) q.tail_first = ntiles - rem;
+  }
+  q.nunits = q.tail_first + 2 * (ntiles - q.tail_first);
+  ntiles = q.nunits;
   // g_t3_oversubscribe (set by the plan around launches on its low-priority side stream): one cluster per work
   // unit instead of a persistent grid, so that the units are short and a higher-priority kernel waiting for SMs
   // gets them after one unit, not after a cluster's whole share
   const int ncl = (ntiles < g3_clusters || g_t3_oversubscribe) ? ntiles : g3_clusters;
-  gemm3_k<BN, A_MN, B_MN, MIX, WS><<<2 * ncl, T3_THREADS, T3_SMEM, st>>>(tm[0], tm[1], tm[3], tm[2], p);
+  launch_k(gemm3_k<BN, A_MN, B_MN, MIX, WS>, dim3(2 * ncl), dim3(T3_THREADS), T3_SMEM, st, g_t3_oversubscribe ? 0 : PDL_GEMM, tm[0], tm[1], tm[3], tm[2], q);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -705,6 +736,7 @@ int gemm_tc3(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
               "gemm: the fused column sum needs accumulate=1 and a row-major [K, N] B operand");
   p.e = e;
   p.e.a_lo = p.e.b_lo = nullptr;
+  p.pdl_late = (g_pdl & PDL_LATE) != 0;
   CUtensorMap tm[4];   // A, B (or B hi), Y, B lo
   // pre-split weights: bf16 images of B with B's strides (bf16x3 mode, rows a multiple of 8 elements apart)
   const bool ws = g_gemm_mix == 2 && e.b_hi16 && e.b_lo16 && !e.accumulate &&

@@ -11,6 +11,7 @@ namespace skf {
 
 thread_local char g_err[512] = {0};
 thread_local int64_t g_launch_count = 0;
+int g_pdl = 0;
 char* err_buf() { return g_err; }
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -30,6 +31,7 @@ __global__ void embed_fwd_k(const int64_t* __restrict__ tok, int64_t tok_ld,
                             const float* __restrict__ table, const float* __restrict__ pe,
                             float* __restrict__ out, int B, int T, int d, int V, float scale,
                             int rnd) {
+  pdl_enter();
   int row = blockIdx.x * blockDim.y + threadIdx.y;
   if (row >= B * T) return;
   int b = row / T, t = row - b * T;
@@ -58,6 +60,7 @@ template <int NV>        // d <= 128 * NV
 __global__ void embed_bwd_k(const int64_t* __restrict__ tok, int64_t tok_ld,
                             const float* __restrict__ dout, float* __restrict__ dtable, int B,
                             int T, int d, int V, float scale) {
+  pdl_enter();
   const int chunks = (T + EMB_RUN - 1) / EMB_RUN;
   const int w = blockIdx.x * blockDim.y + threadIdx.y;
   if (w >= B * chunks) return;
@@ -243,6 +246,7 @@ __global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restric
                              const float* __restrict__ beta, float* __restrict__ s_out,
                              float* __restrict__ y, float* __restrict__ mean_out,
                              float* __restrict__ rstd_out, int rows, int d, int rnd, DropSpec dr) {
+  pdl_enter();
   int row = blockIdx.x * blockDim.y + threadIdx.y;
   if (row >= rows) return;
   int lane = threadIdx.x;
@@ -310,12 +314,13 @@ __global__ void add_ln_fwd_k(const float* __restrict__ a, const float* __restric
 
 // LayerNorm backward.  Each block walks rows blockIdx.x, +gridDim.x, ...; one warp per row;
 // dgamma/dbeta partials stay in registers across the walk, then smem -> one atomic per column.
-template <int LN_NV>
+template <int LN_NV, int R>
 __global__ void __launch_bounds__(256) ln_bwd_k(const float* __restrict__ dy, const float* __restrict__ s,
                          const float* __restrict__ mean, const float* __restrict__ rstd,
                          const float* __restrict__ gamma, float* __restrict__ ds,
                          float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d,
                          int rnd, float* __restrict__ ds_drop, DropSpec dr) {
+  pdl_enter();
   extern __shared__ float sm[];  // [2][d]
   const uint32_t dkey = (ds_drop && dr.thresh) ? skf_drop_key(dr) : 0u;
   int lane = threadIdx.x, w = threadIdx.y, nw = blockDim.y;
@@ -326,8 +331,7 @@ __global__ void __launch_bounds__(256) ln_bwd_k(const float* __restrict__ dy, co
   for (int c = threadIdx.y * 32 + lane; c < 2 * d; c += nw * 32) sm[c] = 0.f;
   __syncthreads();
   // R rows per warp and iteration: their loads are issued together, so an SM keeps 16 warps x R x 2 rows of d
-  // floats in flight (64 KB at d = 256; one row per warp left the kernel at half the HBM rate)
-  constexpr int R = LN_NV <= 2 ? 2 : 1;
+  // floats in flight (R = 2: 64 KB at d = 256; one row per warp left the kernel at half the HBM rate)
   const int rstride = gridDim.x * nw;
   for (int row0 = blockIdx.x * nw + w; row0 < rows; row0 += R * rstride) {
     float4 g[R][LN_NV], xh[R][LN_NV];
@@ -439,6 +443,7 @@ __global__ void dropout_k(const float* x, float* y, int64_t n, DropSpec dr) {
 // per block; partial sums go through shared memory to one atomic per column per block.
 __global__ void __launch_bounds__(256) colsum_k(const float* __restrict__ x, int64_t ldx, float* __restrict__ out,
                                                 int M, int N) {
+  pdl_enter();
   __shared__ float4 sm[8][32];
   const int lane = threadIdx.x, w = threadIdx.y;
   const int col = blockIdx.x * 128 + lane * 4;
@@ -827,6 +832,7 @@ __global__ void softmax_ce_k(const float* __restrict__ logits, int64_t ldl,
                              int64_t lddl, float* __restrict__ probs, int64_t ldp,
                              int32_t* __restrict__ argmax_out, double* __restrict__ stats,
                              int rnd) {
+  pdl_enter();
   __shared__ float s_loss[8];
   __shared__ int s_corr[8];
   int lane = threadIdx.x, w = threadIdx.y;
@@ -1022,6 +1028,7 @@ kv_expand_bwd_k(const float* __restrict__ G, const float* __restrict__ U, const 
 }
 
 __global__ void add_row_broadcast_k(float* __restrict__ Y, const float* __restrict__ r, int64_t rows, int N) {
+  pdl_enter();
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= rows * N) return;
   const int j = (int)(i % N);
@@ -1149,6 +1156,7 @@ xattn_fold_fwd_k(const float* __restrict__ Q, int64_t ldq, const float* __restri
                  const float* __restrict__ bias, const float* __restrict__ w, const float* __restrict__ beta,
                  const uint8_t* __restrict__ key_pad, float* __restrict__ O, int64_t ldo, int Tq, int T, int d,
                  float scale) {
+  pdl_enter();
   extern __shared__ float4 sm4[];
   XfShared S;
   S.tab = sm4;
@@ -1201,6 +1209,7 @@ xattn_fold_bwd_k(const float* __restrict__ Q, int64_t ldq, const float* __restri
                  float* __restrict__ dQ, int64_t lddq, float* __restrict__ gU, float* __restrict__ gs,
                  float* __restrict__ gbias, float* __restrict__ gw, float* __restrict__ gbeta, int Tq, int T, int d,
                  float scale) {
+  pdl_enter();
   extern __shared__ float4 sm4[];
   XfShared S;
   S.tab = sm4;
@@ -1329,7 +1338,7 @@ int skf_embed_fwd(const int64_t* tok, int64_t tok_ld, const float* table, const 
                   float* out, int B, int T, int d, int V, int round_tf32, void* stream) {
   SKF_REQUIRE(d % 4 == 0 && B > 0 && T > 0, SKF_ERR_BAD_SHAPE, "embed_fwd: d %% 4 != 0 or empty");
   dim3 blk(32, 8);
-  embed_fwd_k<<<cdiv((long)B * T, 8), blk, 0, as_stream(stream)>>>(tok, tok_ld, table, pe, out, B, T,
+  launch_k(embed_fwd_k, dim3(cdiv((long)B * T, 8)), dim3(blk), 0, as_stream(stream), PDL_SIMT, tok, tok_ld, table, pe, out, B, T,
                                                                   d, V, sqrtf((float)d), round_tf32);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
@@ -1342,10 +1351,10 @@ int skf_embed_bwd(const int64_t* tok, int64_t tok_ld, const float* dout, float* 
   const int grid = cdiv((long)B * cdiv(T, EMB_RUN), 8);
   const float sc = sqrtf((float)d);
   cudaStream_t st = as_stream(stream);
-  if (d <= 128) embed_bwd_k<1><<<grid, blk, 0, st>>>(tok, tok_ld, dout, dtable, B, T, d, V, sc);
-  else if (d <= 256) embed_bwd_k<2><<<grid, blk, 0, st>>>(tok, tok_ld, dout, dtable, B, T, d, V, sc);
-  else if (d <= 512) embed_bwd_k<4><<<grid, blk, 0, st>>>(tok, tok_ld, dout, dtable, B, T, d, V, sc);
-  else embed_bwd_k<8><<<grid, blk, 0, st>>>(tok, tok_ld, dout, dtable, B, T, d, V, sc);
+  if (d <= 128) launch_k(embed_bwd_k<1>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, tok, tok_ld, dout, dtable, B, T, d, V, sc);
+  else if (d <= 256) launch_k(embed_bwd_k<2>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, tok, tok_ld, dout, dtable, B, T, d, V, sc);
+  else if (d <= 512) launch_k(embed_bwd_k<4>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, tok, tok_ld, dout, dtable, B, T, d, V, sc);
+  else launch_k(embed_bwd_k<8>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, tok, tok_ld, dout, dtable, B, T, d, V, sc);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -1438,10 +1447,10 @@ int skf_add_dropout_layernorm_fwd(const float* a, const float* b, const float* b
   const int grid = cdiv(rows, 8);
   cudaStream_t st = as_stream(stream);
   DropSpec dr = make_dropout(rate, seed, site, step);
-  if (d <= 128) add_ln_fwd_k<1><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
-  else if (d <= 256) add_ln_fwd_k<2><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
-  else if (d <= 512) add_ln_fwd_k<4><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
-  else add_ln_fwd_k<8><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
+  if (d <= 128) launch_k(add_ln_fwd_k<1>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
+  else if (d <= 256) launch_k(add_ln_fwd_k<2>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
+  else if (d <= 512) launch_k(add_ln_fwd_k<4>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
+  else launch_k(add_ln_fwd_k<8>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, 0, dr);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -1454,14 +1463,15 @@ int skf_add_layernorm_fwd(const float* a, const float* b, const float* bias, con
   const int grid = cdiv(rows, 8);
   cudaStream_t st = as_stream(stream);
   DropSpec dr = make_dropout(0.f, 0, 0, nullptr);
-  if (d <= 128) add_ln_fwd_k<1><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
-  else if (d <= 256) add_ln_fwd_k<2><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
-  else if (d <= 512) add_ln_fwd_k<4><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
-  else add_ln_fwd_k<8><<<grid, blk, 0, st>>>(a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
+  if (d <= 128) launch_k(add_ln_fwd_k<1>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
+  else if (d <= 256) launch_k(add_ln_fwd_k<2>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
+  else if (d <= 512) launch_k(add_ln_fwd_k<4>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
+  else launch_k(add_ln_fwd_k<8>, dim3(grid), dim3(blk), 0, st, PDL_SIMT, a, b, bias, gamma, beta, s, y, mean, rstd, rows, d, round_tf32, dr);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
 
+int g_ln_bwd_rows = 2;   // rows per warp and iteration of the LayerNorm backward for d <= 256 (skf_set_option "ln_bwd_rows": 2 | 4)
 int g_ln_bwd_bpsm = 2;   // blocks per SM of the LayerNorm backward grid (skf_set_option "ln_bwd_bpsm")
 static int ln_bwd_launch(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
                          float* ds, float* ds_drop, float* dgamma, float* dbeta, int rows, int d, int round_tf32,
@@ -1495,10 +1505,16 @@ static int ln_bwd_launch(const float* dy, const float* s, const float* mean, con
   if (grid < 1) grid = 1;
   const size_t sm = 2 * d * sizeof(float);
   cudaStream_t st = as_stream(stream);
-  if (d <= 128) ln_bwd_k<1><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
-  else if (d <= 256) ln_bwd_k<2><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
-  else if (d <= 512) ln_bwd_k<4><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
-  else ln_bwd_k<8><<<grid, blk, sm, st>>>(dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
+  if (d <= 128) {
+    if (g_ln_bwd_rows >= 4) launch_k(ln_bwd_k<1, 4>, dim3(grid), dim3(blk), sm, st, PDL_SIMT, dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
+    else launch_k(ln_bwd_k<1, 2>, dim3(grid), dim3(blk), sm, st, PDL_SIMT, dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
+  }
+  else if (d <= 256) {
+    if (g_ln_bwd_rows >= 4) launch_k(ln_bwd_k<2, 4>, dim3(grid), dim3(blk), sm, st, PDL_SIMT, dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
+    else launch_k(ln_bwd_k<2, 2>, dim3(grid), dim3(blk), sm, st, PDL_SIMT, dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
+  }
+  else if (d <= 512) launch_k(ln_bwd_k<4, 1>, dim3(grid), dim3(blk), sm, st, PDL_SIMT, dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
+  else launch_k(ln_bwd_k<8, 1>, dim3(grid), dim3(blk), sm, st, PDL_SIMT, dy, s, mean, rstd, gamma, ds, dgamma, dbeta, rows, d, round_tf32, ds_drop, dr);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -1510,7 +1526,7 @@ int skf_colsum(const float* x, int64_t ldx, float* out, int M, int N, void* stre
   const int maxy = cdiv(M, 8 * 4);
   if (gy > maxy) gy = maxy;
   if (gy < 1) gy = 1;
-  colsum_k<<<dim3(gx, gy), blk, 0, as_stream(stream)>>>(x, ldx, out, M, N);
+  launch_k(colsum_k, dim3(dim3(gx, gy)), dim3(blk), 0, as_stream(stream), PDL_SIMT, x, ldx, out, M, N);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -1593,11 +1609,11 @@ int skf_kv_expand_bwd(const float* G, const float* U, const float* s, const floa
   return SKF_OK;
 }
 
-#define SKF_XFOLD_DISPATCH(K, ...)                                   \
-  do {                                                               \
-    if (dh == 16) K<16> __VA_ARGS__;                                 \
-    else if (dh == 32) K<32> __VA_ARGS__;                            \
-    else K<64> __VA_ARGS__;                                          \
+#define SKF_XFOLD_DISPATCH(K, GRID, BLK, SMEM, ST, ...)                             \
+  do {                                                                              \
+    if (dh == 16) launch_k(K<16>, GRID, dim3(BLK), SMEM, ST, PDL_SIMT, __VA_ARGS__);    \
+    else if (dh == 32) launch_k(K<32>, GRID, dim3(BLK), SMEM, ST, PDL_SIMT, __VA_ARGS__); \
+    else launch_k(K<64>, GRID, dim3(BLK), SMEM, ST, PDL_SIMT, __VA_ARGS__);             \
   } while (0)
 
 int skf_xattn_fold_fwd(const float* Q, int64_t ldq, const float* U, const float* s, const float* bias, const float* w,
@@ -1612,8 +1628,8 @@ int skf_xattn_fold_fwd(const float* Q, int64_t ldq, const float* U, const float*
   SKF_REQUIRE(smem <= 48 * 1024, SKF_ERR_UNSUPPORTED, "xattn_fold_fwd: T = %d too long", T);
   const float scale = 1.0f / sqrtf((float)dh);
   cudaStream_t st = as_stream(stream);
-  SKF_XFOLD_DISPATCH(xattn_fold_fwd_k, <<<dim3(H, B, cdiv(Tq, 128)), 128, smem, st>>>(Q, ldq, U, s, bias, w, beta, key_pad,
-                                                                                      O, ldo, Tq, T, H * dh, scale));
+  SKF_XFOLD_DISPATCH(xattn_fold_fwd_k, dim3(H, B, cdiv(Tq, 128)), 128, smem, st, Q, ldq, U, s, bias, w, beta, key_pad, O, ldo,
+                     Tq, T, H * dh, scale);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -1633,9 +1649,8 @@ int skf_xattn_fold_bwd(const float* Q, int64_t ldq, const float* U, const float*
   SKF_REQUIRE(smem <= 48 * 1024, SKF_ERR_UNSUPPORTED, "xattn_fold_bwd: T = %d too long", T);
   const float scale = 1.0f / sqrtf((float)dh);
   cudaStream_t st = as_stream(stream);
-  SKF_XFOLD_DISPATCH(xattn_fold_bwd_k, <<<dim3(H, B), nthr, smem, st>>>(Q, ldq, U, s, bias, w, beta, key_pad, dO, lddo, dQ,
-                                                                        lddq, gU, gs, gbias, gw, gbeta, Tq, T, H * dh,
-                                                                        scale));
+  SKF_XFOLD_DISPATCH(xattn_fold_bwd_k, dim3(H, B), nthr, smem, st, Q, ldq, U, s, bias, w, beta, key_pad, dO, lddo, dQ, lddq,
+                     gU, gs, gbias, gw, gbeta, Tq, T, H * dh, scale);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -1643,7 +1658,7 @@ int skf_xattn_fold_bwd(const float* Q, int64_t ldq, const float* U, const float*
 
 int skf_add_row_broadcast(float* Y, const float* r, int rows, int N, void* stream) {
   SKF_REQUIRE(Y && r && rows > 0 && N > 0 && N % 4 == 0, SKF_ERR_BAD_ARG, "add_row_broadcast: bad argument");
-  add_row_broadcast_k<<<cdiv((int64_t)rows * N / 4, 256), 256, 0, as_stream(stream)>>>(Y, r, rows, N);
+  launch_k(add_row_broadcast_k, dim3(cdiv((int64_t)rows * N / 4, 256)), dim3(256), 0, as_stream(stream), PDL_SIMT, Y, r, rows, N);
   SKF_LAUNCH_CHECK();
   return SKF_OK;
 }
@@ -1653,7 +1668,7 @@ int skf_token_ce(const float* logits, int64_t ldl, const int64_t* tgt, int64_t t
                  int32_t* argmax_out, int round_tf32, void* stream) {
   dim3 blk(32, 8);
   int rows = B * Td;
-  softmax_ce_k<<<cdiv(rows, 8), blk, 0, as_stream(stream)>>>(logits, ldl, tgt, tgt_ld, rows, Td, V, 1,
+  launch_k(softmax_ce_k, dim3(cdiv(rows, 8)), dim3(blk), 0, as_stream(stream), PDL_SIMT, logits, ldl, tgt, tgt_ld, rows, Td, V, 1,
                                                             grad_scale, dlogits, lddl, nullptr, 0,
                                                             argmax_out, stats, round_tf32);
   SKF_LAUNCH_CHECK();
@@ -1664,7 +1679,7 @@ int skf_class_ce(const float* logits, int64_t ldl, const int64_t* labels, int B,
                  float grad_scale, float* dlogits, int64_t lddl, double* stats,
                  int32_t* argmax_out, float* probs, void* stream) {
   dim3 blk(32, 8);
-  softmax_ce_k<<<cdiv(B, 8), blk, 0, as_stream(stream)>>>(logits, ldl, labels, 1, B, 1, C, 0, grad_scale,
+  launch_k(softmax_ce_k, dim3(cdiv(B, 8)), dim3(blk), 0, as_stream(stream), PDL_SIMT, logits, ldl, labels, 1, B, 1, C, 0, grad_scale,
                                                          dlogits, lddl, probs, C, argmax_out, stats, 0);
   SKF_LAUNCH_CHECK();
   return SKF_OK;

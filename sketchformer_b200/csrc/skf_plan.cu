@@ -34,7 +34,8 @@ int g_wgrad_units = 1;     // side-stream wgrads: work units per cluster slot (f
 extern int g_t3_oversubscribe;
 int g_kv_fold = 2;         // rank-2 form of the expanded bottleneck (see kv_fold()): 1 K / V only, 2 whole cross attention
 int g_wgrad_overlap = 1;   // weight-gradient GEMMs of the backward pass on a second stream (see SideQueue)
-extern int g_t3_bn128_max;  // pair GEMM: 128-column cluster tiles for N up to this
+extern int g_t3_bn128_max;
+extern int g_t3_tail_split;  // pair GEMM: 128-column cluster tiles for N up to this
 int g_gemm_tiny_simt = 0;   // 1: products with M <= 128 and few column tiles run on the small-tile SIMT kernel (no gain measured: 9.04 vs 9.01 ms)
 extern int g_gemm_wsplit;   // 1: forward / dgrad products read pre-split bf16 images of the weights (skf_gemm_tc3.cu)
 extern int g_gemm_mix;   // 1: 3xTF32 GEMMs with N > 128 run on CTA pairs (skf_gemm_tc3.cu)
@@ -1304,6 +1305,7 @@ static int decode_step(skf_plan* P, int i, bool cross_masked, cudaStream_t st) {
 // C ABI
 // =============================================================================================
 extern int g_ln_bwd_bpsm;
+extern int g_ln_bwd_rows;
 
 extern "C" {
 
@@ -1322,8 +1324,20 @@ int skf_set_option(const char* name, int value) {
     skf::g_gemm_mix = value < 0 ? 0 : (value > 2 ? 2 : value);
     return SKF_OK;
   }
+  if (name && strcmp(name, "pdl") == 0) {
+    skf::g_pdl = value & 15;        // programmatic dependent launch: bit mask of kernel classes (skf_common.cuh)
+    return SKF_OK;
+  }
+  if (name && strcmp(name, "gemm_tail_split") == 0) {
+    skf::g_t3_tail_split = value ? 1 : 0;     // pair GEMM: tiles of a partial last wave as two half-width units
+    return SKF_OK;
+  }
   if (name && strcmp(name, "gemm_bn128_max") == 0) {
     skf::g_t3_bn128_max = value;
+    return SKF_OK;
+  }
+  if (name && strcmp(name, "ln_bwd_rows") == 0) {
+    g_ln_bwd_rows = value >= 4 ? 4 : 2;
     return SKF_OK;
   }
   if (name && strcmp(name, "ln_bwd_bpsm") == 0) {

@@ -572,6 +572,25 @@ def test_gemm_pair_presplit_weights(lib, name, a_mn, b_mn, M, N, K):
     assert _gemm_case(M, N, K, a_mn, b_mn, 5, 19, mask=True, images=True) < TOL_X3
 
 
+@pytest.mark.parametrize("name,a_mn,b_mn", MAJORS)
+@pytest.mark.parametrize("M,N,K", [(25600, 256, 256), (19100, 1004, 64), (19200, 768, 96), (40000, 128, 64)])
+def test_gemm_pair_tail_split(lib, name, a_mn, b_mn, M, N, K):
+    """More cluster tiles than clusters with a partial last wave (100, 300, 225 and 157 tiles on 74 clusters): the tail
+    tiles run as two half-width units (gemm_tail_split, the default).  Every epilogue, weights pre-split or not, a
+    ragged last column tile (N = 1004), the 128-column tile variant (N = 128), against float64 — and the same
+    launches with the split switched off."""
+    if name not in ("fwd", "dgrad") and M != 19200:
+        pytest.skip("large schedules checked for the forward / dgrad majors; all majors at one shape")
+    for split in (1, 0):
+        _lib.check(lib.skf_set_option(b"gemm_tail_split", split))
+        try:
+            assert _gemm_case(M, N, K, a_mn, b_mn, 5, 17, images=True) < TOL_X3
+            assert _gemm_case(M, N, K, a_mn, b_mn, 5, 18, bias=True, act=1, resid=True, images=True) < TOL_X3
+            assert _gemm_case(M, N, K, a_mn, b_mn, 5, 19, mask=True) < TOL_X3
+        finally:
+            _lib.check(lib.skf_set_option(b"gemm_tail_split", 1))
+
+
 def test_gemm_tcgen05_3xtf32_beats_single_pass(lib):
     g = torch.Generator().manual_seed(13)
     for (M, N, K) in ((512, 256, 256), (300, 1024, 256), (256, 512, 1000)):

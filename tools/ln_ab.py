@@ -32,16 +32,18 @@ sets = [(torch.randn(rows, d, device="cuda"), torch.randn(rows, d, device="cuda"
         for _ in range(4)]
 mean = torch.zeros(rows, device="cuda"); rstd = torch.ones(rows, device="cuda")
 gamma = torch.ones(d, device="cuda"); dg = torch.zeros(d, device="cuda"); db = torch.zeros(d, device="cuda")
-for bpsm in (2, 3, 4, 6, 8):
+for nrows, bpsm in ((2, 2), (2, 3), (2, 4), (4, 1), (4, 2), (4, 3)):
     _lib.check(lib.skf_set_option(b"ln_bwd_bpsm", bpsm))
+    _lib.check(lib.skf_set_option(b"ln_bwd_rows", nrows))
 
     def f(i):
         dy, s, ds = sets[i % 4]
         _lib.check(lib.skf_layernorm_bwd(ptr(dy), ptr(s), ptr(mean), ptr(rstd), ptr(gamma), ptr(ds), ptr(dg), ptr(db),
                                          rows, d, 0, stream()))
     us = timed(f)
-    print(f"ln_bwd bpsm={bpsm}: {us:.1f} us  {3 * rows * d * 4 / us / 1e6:.2f} TB/s", flush=True)
+    print(f"ln_bwd rows/warp={nrows} bpsm={bpsm}: {us:.1f} us  {3 * rows * d * 4 / us / 1e6:.2f} TB/s", flush=True)
 _lib.check(lib.skf_set_option(b"ln_bwd_bpsm", 2))
+_lib.check(lib.skf_set_option(b"ln_bwd_rows", 2))
 
 x, _ = synth.token_batch(128, 200, 345, 1234, vocab=1004)
 tok = torch.from_numpy(x).cuda()

@@ -24,4 +24,4 @@ e0.record()
 for _ in range(n): eng.train_step(xd, yd, True)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
-print(f"{name} B={B}: {ms:.1f} ms/step, {B / ms * 1e3:.0f} sketches/s")
+print(f"{name} B={B} [{os.environ.get('SKF_OPTIONS', '')}]: {ms:.2f} ms/step, {B / ms * 1e3:.0f} sketches/s")
