@@ -439,6 +439,83 @@ class Transformer:
     def compute_predictions_on_set(self, set_type):
         return evaluation.compute_predictions_on_set(self, set_type)
 
+    # ---- slow-metric plumbing of evaluate-metrics.py:53-61 (core/models.py:249-320) ----------------------
+    def compute_metrics_from(self, chosen_metrics):
+        """core/models.py:254-257: for every metric object gather the data its `input_type` names and run its
+        `computation_worker` on it (synchronously).  The metric objects are the caller's: the reference's own
+        `metrics.build_metric_by_name(...)` instances work unchanged (tests/test_integration_stub.py)."""
+        for _, metric in chosen_metrics.items():
+            input_data = self.gather_data_for_metric(metric.input_type)
+            metric.computation_worker(input_data)
+
+    def gather_data_for_metric(self, data_type):
+        """core/models.py:280-292: `compute_<data_type>()` once per time window, cached."""
+        data = self.load_precomputed_features_if_they_exist(data_type)
+        if not data:
+            try:
+                gather_func = getattr(self, "compute_{}".format(data_type))
+            except AttributeError:
+                raise AttributeError("One of your metrics requires a compute_{} method".format(data_type))
+            data = gather_func()
+            self.save_precomputed_features(data_type, data)
+            data = self.load_precomputed_features_if_they_exist(data_type)
+        return data
+
+    @staticmethod
+    def _time_id_str():
+        """utils/helpers.py:23-30: DDHHM with the minutes cut to the tens — the reference's cache window."""
+        import datetime
+        now = datetime.datetime.now()
+        return "{:02d}{:02d}{:02d}".format(now.day, now.hour, now.minute)[:-1]
+
+    def load_precomputed_features_if_they_exist(self, feature_type):
+        """core/models.py:294-308.  The reference re-reads `tmp/precomputed_<type>_<time id>.pickle`; here the tuple
+        stays in memory for the same ten-minute window and the file is only written (nothing is unpickled)."""
+        hit = getattr(self, "_precomputed", {}).get(feature_type)
+        return hit[1] if hit and hit[0] == self._time_id_str() else False
+
+    def save_precomputed_features(self, feature_type, data):
+        """core/models.py:310-319: one `precomputed_<type>_<time id>.pickle` per feature type in tmp/."""
+        import glob
+        import pickle
+        self._precomputed = getattr(self, "_precomputed", {})
+        self._precomputed[feature_type] = (self._time_id_str(), data)
+        d = getattr(self, "tmp_out_dir", None)
+        if d is None:
+            return
+        for old in glob.glob(os.path.join(d, "precomputed_{}*".format(feature_type))):
+            os.remove(old)
+        with open(os.path.join(d, "precomputed_{}_{}.pickle".format(feature_type, self._time_id_str())), "wb") as f:
+            pickle.dump(data, f)
+
+    def plot_and_send_notification_for(self, metrics_list):
+        """core/models.py:259-269 draws `plots/evaluation_plots.png` and posts it to Slack; plotting and the notifier are
+        outside the hot-path scope, so the same per-metric plot data goes to
+        `plots/evaluation_metrics.json` instead.  Returns the file path."""
+        import json
+        report = {}
+        for m, metric in metrics_list.items():
+            data = metric.get_data_for_plot()
+            report[m] = {"plot_type": getattr(metric, "plot_type", None),
+                         "data": np.asarray(data).tolist() if not isinstance(data, dict) else
+                                 {k: np.asarray(v).tolist() for k, v in data.items()},
+                         "last_value": getattr(metric, "last_value_repr", None)}
+        path = os.path.join(getattr(self, "plots_out_dir", None) or ".", "evaluation_metrics.json")
+        with open(path, "w") as f:
+            json.dump(report, f, indent=2, sort_keys=True, default=str)
+        print("[Metrics] {}".format(", ".join("{}={}".format(m, r["last_value"]) for m, r in report.items())))
+        return path
+
+    def clean_up_tmp_dir(self):
+        """core/models.py:271-278: remove the files (not the directories) under tmp/."""
+        for the_file in os.listdir(self.tmp_out_dir):
+            file_path = os.path.join(self.tmp_out_dir, the_file)
+            try:
+                if os.path.isfile(file_path):
+                    os.unlink(file_path)
+            except Exception as e:      # noqa: BLE001 — the reference prints and carries on
+                print(e)
+
     # ---- TensorFlow checkpoints of the reference (core/models.py:321-344) ---------------------------
     def load_tf_checkpoint(self, prefix):
         """Weights, Adam moments and step counters from `tf.train.Checkpoint(transformer=, optimizer=)` files."""
