@@ -15,9 +15,10 @@ Format restated from the published TensorFlow / LevelDB specifications (tensor_b
                  shard_id, offset, size, crc32c}
 There is no TensorFlow in this image and no reference checkpoint on disk, so the reader is checked against the
 writer below and against hand-assembled blocks (tests/test_tf_checkpoint.py), not against a file TF wrote:
-"parity unpinned" like the oracle.  String tensors (the `_CHECKPOINTABLE_OBJECT_GRAPH` entry) are skipped on read
-and not produced on write, so TF itself can load a bundle written here by name (`tf.train.load_checkpoint`), not
-through object-based `Checkpoint.restore`."""
+"parity unpinned" like the oracle.  The one string tensor of such a bundle, `_CHECKPOINTABLE_OBJECT_GRAPH` (a
+serialized TrackableObjectGraph: the tree of attribute names `tf.train.Checkpoint.restore` walks to find each
+variable's key, plus the optimizer's slot-variable table), is written by export_checkpoint() and parsed by
+read_object_graph(); the numeric reader does not need it (keys are looked up by name)."""
 import os
 import struct
 from typing import Dict, Iterable, List, Tuple
@@ -327,6 +328,12 @@ def write_tensor_bundle(prefix: str, tensors: Dict[str, np.ndarray]):
     off = 0
     with open(_data_path(prefix, 0, 1), "wb") as f:
         for name in sorted(tensors):
+            if isinstance(tensors[name], (bytes, bytearray)):                       # scalar DT_STRING tensor
+                raw, crc = _string_tensor_bytes([bytes(tensors[name])])
+                f.write(raw)
+                items.append((name.encode(), _entry_proto(DT_STRING, (), off, len(raw), crc)))
+                off += len(raw)
+                continue
             a = np.asarray(tensors[name], order="C")       # (ascontiguousarray would turn scalars into [1])
             dt = a.dtype.newbyteorder("<") if a.dtype.byteorder == ">" else a.dtype
             a = a.astype(dt, copy=False)
@@ -336,6 +343,165 @@ def write_tensor_bundle(prefix: str, tensors: Dict[str, np.ndarray]):
                                                       mask_crc(crc32c(raw)))))
             off += len(raw)
     write_table(prefix + ".index", items)
+
+
+# ---- string tensors and the object graph -----------------------------------------------------------------------
+OBJECT_GRAPH_KEY = "_CHECKPOINTABLE_OBJECT_GRAPH"
+
+
+def _string_tensor_bytes(values: List[bytes]) -> Tuple[bytes, int]:
+    """DT_STRING layout of tensor_bundle.cc (WriteStringTensor): [varint64 length]* | masked crc32c of the lengths
+    (each taken as a little-endian uint32) | the strings.  Returns (bytes, crc32c over lengths-as-uint32, the 4
+    checksum bytes and the string bytes) — the value BundleEntryProto.crc32c stores, masked."""
+    lengths = b"".join(_put_varint(len(v)) for v in values)
+    crc = 0
+    for v in values:
+        crc = crc32c(struct.pack("<I", len(v)), crc)
+    cks = struct.pack("<I", mask_crc(crc))
+    crc = crc32c(cks, crc)
+    for v in values:
+        crc = crc32c(v, crc)
+    return lengths + cks + b"".join(values), mask_crc(crc)
+
+
+def _parse_string_tensor(raw: bytes, count: int) -> List[bytes]:
+    pos, lens = 0, []
+    for _ in range(count):
+        n, pos = _get_varint(raw, pos)
+        lens.append(n)
+    crc = 0
+    for n in lens:
+        crc = crc32c(struct.pack("<I", n), crc)
+    if struct.unpack("<I", raw[pos: pos + 4])[0] != mask_crc(crc):
+        raise ValueError("string tensor: checksum of the lengths does not match")
+    pos += 4
+    out = []
+    for n in lens:
+        out.append(bytes(raw[pos: pos + n]))
+        pos += n
+    return out
+
+
+def _pb_str(field: int, v: bytes) -> bytes:
+    return _put_varint(field << 3 | 2) + _put_varint(len(v)) + v
+
+
+def _pb_int(field: int, v: int) -> bytes:
+    return _put_varint(field << 3) + _put_varint(v) if v else b""        # proto3: zero is the default, not written
+
+
+def build_object_graph(keys: Iterable[str]) -> bytes:
+    """Serialized TrackableObjectGraph (tensorflow/core/protobuf/trackable_object_graph.proto) for the variables whose
+    checkpoint keys are `keys` (with the /.ATTRIBUTES/VARIABLE_VALUE suffix).  Node 0 is the root
+    (`tf.train.Checkpoint(transformer=..., optimizer=...)`, core/models.py:322-323); every path component of a key is
+    a child edge named like the Python attribute / list index; the object a key ends at carries
+    SerializedTensor{name: 'VARIABLE_VALUE', full_name, checkpoint_key}.  Adam's moments
+    (`<variable path>/.OPTIMIZER_SLOT/optimizer/<m|v>`) are nodes of their own, reachable only through the optimizer
+    node's slot_variables table, as TensorFlow writes them."""
+    nodes = [{"children": {}, "attrs": [], "slots": []}]
+
+    def walk(path):
+        n = 0
+        for part in path:
+            kids = nodes[n]["children"]
+            if part not in kids:
+                nodes.append({"children": {}, "attrs": [], "slots": []})
+                kids[part] = len(nodes) - 1
+            n = kids[part]
+        return n
+
+    slots = []
+    for key in sorted(keys):
+        assert key.endswith(SUFFIX), key
+        path = key[: -len(SUFFIX)]
+        if "/.OPTIMIZER_SLOT/" in path:
+            slots.append((path, key))
+            continue
+        n = walk(path.split("/"))
+        nodes[n]["attrs"].append(("VARIABLE_VALUE", path.split("/", 1)[-1], key))
+    for path, key in slots:
+        var_path, rest = path.split("/.OPTIMIZER_SLOT/")
+        opt_name, slot_name = rest.split("/")
+        var_node, opt_node = walk(var_path.split("/")), walk([opt_name])
+        nodes.append({"children": {}, "attrs": [("VARIABLE_VALUE", f"{var_path.split('/', 1)[-1]}/{slot_name}", key)],
+                      "slots": []})
+        nodes[opt_node]["slots"].append((var_node, slot_name, len(nodes) - 1))
+    out = b""
+    for nd in nodes:
+        body = b""
+        for name, nid in nd["children"].items():
+            body += _pb_str(1, _pb_int(1, nid) + _pb_str(2, name.encode()))
+        for name, full, key in nd["attrs"]:
+            body += _pb_str(2, _pb_str(1, name.encode()) + _pb_str(2, full.encode()) + _pb_str(3, key.encode()))
+        for orig, slot_name, snode in nd["slots"]:
+            body += _pb_str(3, _pb_int(1, orig) + _pb_str(2, slot_name.encode()) + _pb_int(3, snode))
+        out += _pb_str(1, body)
+    return out
+
+
+def parse_object_graph(buf: bytes) -> List[dict]:
+    """-> [{'children': {local_name: node_id}, 'attributes': [(name, full_name, checkpoint_key)],
+            'slot_variables': [(original_variable_node_id, slot_name, slot_variable_node_id)]}] in node order."""
+    nodes = []
+    for f, _, v in _pb_fields(buf):
+        if f != 1:
+            continue
+        nd = {"children": {}, "attributes": [], "slot_variables": []}
+        for f2, _, v2 in _pb_fields(v):
+            fields = {f3: v3 for f3, _, v3 in _pb_fields(v2)}
+            if f2 == 1:
+                nd["children"][bytes(fields.get(2, b"")).decode()] = int(fields.get(1, 0))
+            elif f2 == 2:
+                nd["attributes"].append(tuple(bytes(fields.get(i, b"")).decode() for i in (1, 2, 3)))
+            elif f2 == 3:
+                nd["slot_variables"].append((int(fields.get(1, 0)), bytes(fields.get(2, b"")).decode(), int(fields.get(3, 0))))
+        nodes.append(nd)
+    return nodes
+
+
+def read_object_graph(prefix: str) -> List[dict]:
+    """The parsed `_CHECKPOINTABLE_OBJECT_GRAPH` entry of a bundle, or [] when it has none."""
+    for key, val in read_table(prefix + ".index"):
+        if key.decode() == OBJECT_GRAPH_KEY:
+            e = _parse_entry(val)
+            if e["dtype"] != DT_STRING:
+                raise ValueError("object graph entry is not a string tensor")
+            with open(_data_path(prefix, e["shard_id"], _num_shards(prefix)), "rb") as f:
+                f.seek(e["offset"])
+                raw = f.read(e["size"])
+            count = int(np.prod(e["shape"])) if e["shape"] else 1
+            return parse_object_graph(_parse_string_tensor(raw, count)[0])
+    return []
+
+
+def _num_shards(prefix: str) -> int:
+    for key, val in read_table(prefix + ".index"):
+        if key == b"":
+            for f, _, v in _pb_fields(val):
+                if f == 1:
+                    return int(v)
+    return 1
+
+
+def object_graph_variables(nodes: List[dict]) -> Dict[str, str]:
+    """{attribute path from the root ('transformer/encoder/embedding/embeddings'): checkpoint_key} — what
+    `Checkpoint.restore` finds by walking the children; slot variables appear as
+    '<variable path>/.OPTIMIZER_SLOT/<optimizer child name>/<slot>'."""
+    out, paths = {}, {0: ""}
+    todo = [0]
+    while todo:
+        n = todo.pop()
+        for name, nid in nodes[n]["children"].items():
+            if nid not in paths:
+                paths[nid] = (paths[n] + "/" + name).lstrip("/")
+                todo.append(nid)
+    for n, path in paths.items():
+        for name, _, key in nodes[n]["attributes"]:
+            out[path] = key
+        for orig, slot_name, snode in nodes[n]["slot_variables"]:
+            for _, _, key in nodes[snode]["attributes"]:
+                out[f"{paths[orig]}/.OPTIMIZER_SLOT/{path}/{slot_name}"] = key
+    return out
 
 
 def latest_checkpoint(directory: str):
@@ -460,6 +626,7 @@ def export_checkpoint(prefix: str, hps: dict, params: dict, adam_m: dict = None,
         out[STEP_KEYS[0] + SUFFIX] = np.asarray(current_step, dtype=np.int32)
     if optimizer_iter is not None:
         out[STEP_KEYS[1] + SUFFIX] = np.asarray(optimizer_iter, dtype=np.int64)
+    out[OBJECT_GRAPH_KEY] = build_object_graph(out.keys())
     write_tensor_bundle(prefix, out)
     with open(os.path.join(os.path.dirname(os.path.abspath(prefix)), "checkpoint"), "w") as f:
         base = os.path.basename(prefix)

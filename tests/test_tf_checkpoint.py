@@ -115,6 +115,96 @@ def test_checkpoint_export_import(tmp_path):
         T.import_checkpoint(prefix, dict(HPS, num_layers=3))
 
 
+def test_string_tensor_layout():
+    """tensor_bundle.cc WriteStringTensor: varint lengths | masked crc32c of the lengths as uint32 | bytes."""
+    vals = [b"", b"abc", b"x" * 300]
+    raw, crc = T._string_tensor_bytes(vals)
+    assert raw[:4] == b"\x00\x03\xac\x02"                                     # 0, 3, 300 as varints
+    want = 0
+    for n in (0, 3, 300):
+        want = T.crc32c(struct.pack("<I", n), want)
+    assert struct.unpack("<I", raw[4:8])[0] == T.mask_crc(want)
+    assert raw[8:] == b"abc" + b"x" * 300
+    assert T._parse_string_tensor(raw, 3) == vals
+    assert crc == T.mask_crc(T.crc32c(raw[8:], T.crc32c(raw[4:8], want)))
+    with pytest.raises(ValueError):
+        T._parse_string_tensor(raw[:4] + b"\0\0\0\0" + raw[8:], 3)
+
+
+def _graph_message_class():
+    """TrackableObjectGraph declared to the protobuf runtime (schema restated from
+    tensorflow/core/protobuf/trackable_object_graph.proto): an encoder independent of tf_checkpoint's hand-rolled one."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="tog_test.proto", package="togtest", syntax="proto3")
+    g = fd.message_type.add(name="TrackableObjectGraph")
+    o = g.nested_type.add(name="TrackableObject")
+    r = o.nested_type.add(name="ObjectReference")
+    r.field.add(name="node_id", number=1, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+    r.field.add(name="local_name", number=2, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+    t = o.nested_type.add(name="SerializedTensor")
+    for i, n in enumerate(("name", "full_name", "checkpoint_key"), 1):
+        t.field.add(name=n, number=i, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+    v = o.nested_type.add(name="SlotVariableReference")
+    v.field.add(name="original_variable_node_id", number=1, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+    v.field.add(name="slot_name", number=2, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+    v.field.add(name="slot_variable_node_id", number=3, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+    pre = ".togtest.TrackableObjectGraph.TrackableObject."
+    o.field.add(name="children", number=1, type=F.TYPE_MESSAGE, label=F.LABEL_REPEATED, type_name=pre + "ObjectReference")
+    o.field.add(name="attributes", number=2, type=F.TYPE_MESSAGE, label=F.LABEL_REPEATED, type_name=pre + "SerializedTensor")
+    o.field.add(name="slot_variables", number=3, type=F.TYPE_MESSAGE, label=F.LABEL_REPEATED,
+                type_name=pre + "SlotVariableReference")
+    g.field.add(name="nodes", number=1, type=F.TYPE_MESSAGE, label=F.LABEL_REPEATED,
+                type_name=".togtest.TrackableObjectGraph.TrackableObject")
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    return message_factory.GetMessageClass(pool.FindMessageTypeByName("togtest.TrackableObjectGraph"))
+
+
+def test_object_graph_entry(tmp_path):
+    """export_checkpoint writes `_CHECKPOINTABLE_OBJECT_GRAPH`: walking its children from the root
+    (`transformer` / `optimizer`, core/models.py:322-323) reaches every variable of the bundle under its own key, the
+    Adam moments hang off the optimizer node's slot table, and the protobuf runtime reads the same message."""
+    params = {k: v.numpy() for k, v in init_params(HPS, 3).items()}
+    m = {k: v * 0.5 for k, v in params.items()}
+    v = {k: v * v for k, v in params.items()}
+    prefix = str(tmp_path / "w" / "ckpt-3")
+    T.export_checkpoint(prefix, HPS, params, m, v, current_step=12, optimizer_iter=13)
+    bundle = T.read_tensor_bundle(prefix, verify_tensors=True)            # the string entry does not disturb the numeric reader
+    assert T.OBJECT_GRAPH_KEY not in bundle
+    nodes = T.read_object_graph(prefix)
+    assert set(nodes[0]["children"]) == {"transformer", "optimizer"}
+    found = T.object_graph_variables(nodes)
+    assert {k + T.SUFFIX for k in found} == set(bundle) and all(found[k] == k + T.SUFFIX for k in found)
+    tr = nodes[nodes[0]["children"]["transformer"]]
+    enc = nodes[tr["children"]["encoder"]]
+    assert sorted(nodes[enc["children"]["enc_layers"]]["children"]) == [str(i) for i in range(HPS["num_layers"])]
+    opt = nodes[nodes[0]["children"]["optimizer"]]
+    assert set(opt["children"]) == {"iter"} and len(opt["slot_variables"]) == 2 * len(params)
+    assert {s for _, s, _ in opt["slot_variables"]} == {"m", "v"}
+    # the same bytes through google.protobuf
+    raw = None
+    for key, val in T.read_table(prefix + ".index"):
+        if key.decode() == T.OBJECT_GRAPH_KEY:
+            e = T._parse_entry(val)
+            assert e["dtype"] == T.DT_STRING and e["shape"] == []
+            data = open(T._data_path(prefix, 0, 1), "rb").read()[e["offset"]: e["offset"] + e["size"]]
+            raw = T._parse_string_tensor(data, 1)[0]
+            assert T.mask_crc(T.crc32c(data[-len(raw):], T.crc32c(data[:len(data) - len(raw)][-4:],
+                              T.crc32c(struct.pack("<I", len(raw)))))) == e["crc32c"]
+    msg = _graph_message_class()()
+    msg.ParseFromString(raw)
+    assert len(msg.nodes) == len(nodes)
+    for a, b in zip(msg.nodes, nodes):
+        assert {c.local_name: c.node_id for c in a.children} == b["children"]
+        assert [(t.name, t.full_name, t.checkpoint_key) for t in a.attributes] == b["attributes"]
+        assert [(x.original_variable_node_id, x.slot_name, x.slot_variable_node_id) for x in a.slot_variables] == b["slot_variables"]
+    assert msg.SerializeToString() == raw             # canonical field order: byte-identical re-encoding
+    # a bundle without the entry (e.g. one written by name only) parses to an empty graph
+    T.write_tensor_bundle(str(tmp_path / "plain"), {"a": np.zeros(3, np.float32)})
+    assert T.read_object_graph(str(tmp_path / "plain")) == []
+
+
 # ---- checkpoint keys against the reference's attribute structure ---------------------------------------------------
 def _tracked_variables(obj, prefix=""):
     """TF object-graph naming restated (tf.train.Checkpoint: a variable's key is the chain of attribute names that
