@@ -177,6 +177,38 @@ int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
              int64_t sb_n, float* Y, int64_t ldy, int M, int N, int K,
              const skf_gemm_epilogue* epi, int backend, void* stream);
 
+/* ---- sublayer entry points: the operator groups SURVEY.md 8(b) names `skf_ffn_*` and `skf_logits_ce_*` ----------
+ * Each is the sequence of launches the plan runs for that group, on caller-owned buffers.  They are NOT single
+ * kernels: the hidden tensor / the logits go through HBM between the launches (DESIGN.md section 9 has the measured
+ * reasons).  Products run as the plan's default: the bf16x3 pair GEMM where the shape allows it, with the weights'
+ * bf16 images when all of them are given (skf_split_bf16; NULL = split in shared memory).
+ *
+ * Position-wise feed-forward sublayer with its residual (builders/layers/transformer.py:194-198, 220-222, 258-260):
+ *   h = relu(x W1 + b1) [M, f] (an output: the backward pass needs it);  y = resid + h W2 + b2 [M, d]
+ * x, resid (may be NULL), y: [M, d] row-major; W1 [d, f], W2 [f, d] Keras kernels.  Two launches.            */
+int skf_ffn_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                const float* resid, float* h, float* y, int M, int d, int f, const void* w1_hi16,
+                const void* w1_lo16, const void* w2_hi16, const void* w2_lo16, void* stream);
+/* Its gradients from dy = dL/dy [M, d] (the residual branch passes dy through and stays with the caller):
+ *   dW2 += h^T dy, db2 += colsum(dy);  dh = (dy W2^T) * [h > 0] [M, f] (scratch / output);
+ *   dW1 += x^T dh, db1 += colsum(dh);  dx = dh W1^T (+ dx_resid when non-NULL) [M, d].
+ * The weight gradients ACCUMULATE (zero them first); four GEMM launches, bias gradients fused where the shape
+ * allows, else one column-sum launch each.                                                                   */
+int skf_ffn_bwd(const float* x, const float* h, const float* dy, const float* W1, const float* W2, float* dh,
+                float* dx, const float* dx_resid, float* dW1, float* db1, float* dW2, float* db2, int M, int d,
+                int f, const void* w1_hi16, const void* w1_lo16, const void* w2_hi16, const void* w2_lo16,
+                void* stream);
+/* Output layer + token loss (models/sketchformer.py:179 `final_layer`; builders/losses.py:26-41; accuracy 335-339):
+ *   logits = x W + b [B*Td, V] (row pitch ldl >= V, a multiple of 4), then skf_token_ce IN PLACE: stats[0] += CE sum,
+ *   stats[1] += correct, argmax_out[row], and `logits` leaves as dlogits = (softmax - onehot) [tgt != 0] grad_scale.
+ * Two launches.                                                                                               */
+int skf_logits_ce_fwd(const float* x, const float* W, const float* b, const int64_t* tgt, int64_t tgt_ld, int B,
+                      int Td, int d, int V, float grad_scale, float* logits, int64_t ldl, double* stats,
+                      int32_t* argmax_out, const void* w_hi16, const void* w_lo16, void* stream);
+/* dx = dlogits W^T [B*Td, d];  dW += x^T dlogits [d, V];  db += colsum(dlogits) [V].                           */
+int skf_logits_ce_bwd(const float* x, const float* dlogits, int64_t ldl, const float* W, float* dx, float* dW,
+                      float* db, int B, int Td, int d, int V, const void* w_hi16, const void* w_lo16, void* stream);
+
 /* builders/utils.py:71-105 + split_heads (transformer.py:160-165), fused.
  * Q rows are b*Tq+i, K/V rows b*Tk+j; head h occupies columns [h*dh,(h+1)*dh) of each.
  * mask_mode: 0 none, 1 key padding (key_pad[b,j]!=0 masked), 2 causal | key padding.

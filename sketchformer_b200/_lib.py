@@ -53,6 +53,10 @@ SIGNATURES = {
     "skf_embed_cont_bwd": (I, [P, L, P, P, P, I, I, I, P]),
     "skf_cont_loss": (I, [P, L, P, L, I, I, F, P, L, P, P]),
     "skf_gemm": (I, [P, L, L, P, L, L, P, L, I, I, I, C.POINTER(SkfGemmEpilogue), I, P]),
+    "skf_ffn_fwd": (I, [P, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P]),
+    "skf_ffn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P]),
+    "skf_logits_ce_fwd": (I, [P, P, P, P, L, I, I, I, I, F, P, L, P, P, P, P, P]),
+    "skf_logits_ce_bwd": (I, [P, P, L, P, P, P, P, I, I, I, I, P, P, P]),
     "skf_split_lo": (I, [P, P, L, P]),
     "skf_split_bf16": (I, [P, P, P, L, P]),
     "skf_attn_fwd": (I, [P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, P]),

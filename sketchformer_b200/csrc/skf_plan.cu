@@ -1640,6 +1640,105 @@ int skf_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t
   return gemm_simt(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, epi, as_stream(stream));
 }
 
+// ---- sublayer entry points (include/skf.h): the plan's launch sequences on caller-owned buffers --------------------
+// the plan's choice of kernel for one product (Gemm::run without a plan): bf16x3 on CTA pairs where the shape is worth
+// it, the single-CTA tcgen05 kernel (3xTF32) for the other TMA-compatible shapes, the fp32 SIMT kernel otherwise
+static int gemm_auto(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* Y,
+                     int64_t ldy, int M, int N, int K, skf_gemm_epilogue e, cudaStream_t st) {
+  const bool tc = gemm_tc2_supported(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e) != 0;
+  const bool pair = tc && gemm_tc3_wanted(M, N, K);
+  if (e.accumulate) {            // split-K so that the persistent grid has about one unit per cluster / SM
+    const long tiles = pair ? (long)cdiv(M, 256) * cdiv(N, 256)
+                       : tc ? (long)cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256))
+                            : (long)cdiv(M, 64) * cdiv(N, 64);
+    const int want = (int)((pair ? 74 : tc ? 148 : 2 * 148) / tiles);
+    const int maxs = K / 256 > 0 ? K / 256 : 1;
+    e.split_k = want < 1 ? 1 : (want > maxs ? maxs : want);
+  }
+  if (!pair) e.colsum = nullptr, e.b_hi16 = e.b_lo16 = nullptr;
+  if (pair) return gemm_tc3(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, st);
+  return tc ? gemm_tc2(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, 1, st)
+            : gemm_simt(A, sa_m, sa_k, B, sb_k, sb_n, Y, ldy, M, N, K, &e, st);
+}
+// dW[K,N] += X[M,K]^T dY[M,N]; db[N] += colsum(dY) (fused into the pair kernel when it runs, else its own launch)
+static int wgrad_auto(const float* X, const float* dY, int64_t ldy, float* dW, float* db, int M, int N, int K,
+                      cudaStream_t st) {
+  skf_gemm_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.accumulate = 1;
+  const bool fused = db && ldy == N && gemm_tc3_wanted(K, N, M) &&
+                     gemm_tc2_supported(X, 1, K, dY, ldy, 1, dW, N, K, N, M, &e);
+  if (fused) e.colsum = db;
+  SKF_TRY(gemm_auto(X, 1, K, dY, ldy, 1, dW, N, K, N, M, e, st));
+  if (db && !fused) SKF_TRY(skf_colsum(dY, ldy, db, M, N, st));
+  return SKF_OK;
+}
+
+int skf_ffn_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                const float* resid, float* h, float* y, int M, int d, int f, const void* w1_hi16,
+                const void* w1_lo16, const void* w2_hi16, const void* w2_lo16, void* stream) {
+  SKF_REQUIRE(x && W1 && W2 && h && y && M > 0 && d > 0 && f > 0, SKF_ERR_BAD_ARG, "ffn_fwd: bad argument");
+  cudaStream_t st = as_stream(stream);
+  const bool img = w1_hi16 && w1_lo16 && w2_hi16 && w2_lo16;
+  skf_gemm_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.bias = b1; e.act = SKF_ACT_RELU;
+  if (img) e.b_hi16 = w1_hi16, e.b_lo16 = w1_lo16;
+  SKF_TRY(gemm_auto(x, d, 1, W1, f, 1, h, f, M, f, d, e, st));            // transformer.py:196
+  memset(&e, 0, sizeof(e));
+  e.bias = b2; e.resid = resid; e.ld_resid = d;
+  if (img) e.b_hi16 = w2_hi16, e.b_lo16 = w2_lo16;
+  return gemm_auto(h, f, 1, W2, d, 1, y, d, M, d, f, e, st);               // transformer.py:197 + the residual of 222
+}
+
+int skf_ffn_bwd(const float* x, const float* h, const float* dy, const float* W1, const float* W2, float* dh,
+                float* dx, const float* dx_resid, float* dW1, float* db1, float* dW2, float* db2, int M, int d,
+                int f, const void* w1_hi16, const void* w1_lo16, const void* w2_hi16, const void* w2_lo16,
+                void* stream) {
+  SKF_REQUIRE(x && h && dy && W1 && W2 && dh && dx && dW1 && dW2 && M > 0 && d > 0 && f > 0, SKF_ERR_BAD_ARG,
+              "ffn_bwd: bad argument");
+  cudaStream_t st = as_stream(stream);
+  const bool img = w1_hi16 && w1_lo16 && w2_hi16 && w2_lo16;
+  SKF_TRY(wgrad_auto(h, dy, d, dW2, db2, M, d, f, st));                    // dW2 += h^T dy, db2 += colsum(dy)
+  skf_gemm_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.mask = h; e.ld_mask = f;                                               // ReLU backward: * [h > 0]
+  if (img) e.b_hi16 = w2_hi16, e.b_lo16 = w2_lo16;
+  SKF_TRY(gemm_auto(dy, d, 1, W2, 1, d, dh, f, M, f, d, e, st));          // dh = (dy W2^T) * [h > 0]
+  SKF_TRY(wgrad_auto(x, dh, f, dW1, db1, M, f, d, st));                    // dW1 += x^T dh, db1 += colsum(dh)
+  memset(&e, 0, sizeof(e));
+  e.resid = dx_resid; e.ld_resid = d;
+  if (img) e.b_hi16 = w1_hi16, e.b_lo16 = w1_lo16;
+  return gemm_auto(dh, f, 1, W1, 1, f, dx, d, M, d, f, e, st);             // dx = dh W1^T (+ dx_resid)
+}
+
+int skf_logits_ce_fwd(const float* x, const float* W, const float* b, const int64_t* tgt, int64_t tgt_ld, int B,
+                      int Td, int d, int V, float grad_scale, float* logits, int64_t ldl, double* stats,
+                      int32_t* argmax_out, const void* w_hi16, const void* w_lo16, void* stream) {
+  SKF_REQUIRE(x && W && tgt && logits && stats && B > 0 && Td > 0 && d > 0 && V > 0 && ldl >= V, SKF_ERR_BAD_ARG,
+              "logits_ce_fwd: bad argument");
+  cudaStream_t st = as_stream(stream);
+  skf_gemm_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.bias = b;
+  if (w_hi16 && w_lo16) e.b_hi16 = w_hi16, e.b_lo16 = w_lo16;
+  SKF_TRY(gemm_auto(x, d, 1, W, V, 1, logits, ldl, B * Td, V, d, e, st));  // models/sketchformer.py:179
+  return skf_token_ce(logits, ldl, tgt, tgt_ld, B, Td, V, grad_scale, logits, ldl, stats, argmax_out, 0, stream);
+}
+
+int skf_logits_ce_bwd(const float* x, const float* dlogits, int64_t ldl, const float* W, float* dx, float* dW,
+                      float* db, int B, int Td, int d, int V, const void* w_hi16, const void* w_lo16, void* stream) {
+  SKF_REQUIRE(x && dlogits && W && dx && dW && B > 0 && Td > 0 && d > 0 && V > 0 && ldl >= V, SKF_ERR_BAD_ARG,
+              "logits_ce_bwd: bad argument");
+  cudaStream_t st = as_stream(stream);
+  const int M = B * Td;
+  SKF_TRY(wgrad_auto(x, dlogits, ldl, dW, db, M, V, d, st));               // dW += x^T dlogits, db += colsum
+  skf_gemm_epilogue e;
+  memset(&e, 0, sizeof(e));
+  if (w_hi16 && w_lo16) e.b_hi16 = w_hi16, e.b_lo16 = w_lo16;
+  return gemm_auto(dlogits, ldl, 1, W, 1, V, dx, d, M, d, V, e, st);       // dx = dlogits W^T
+}
+
 int skf_attn_fwd(const float* Q, int64_t ldq, const float* K, int64_t ldk, const float* V, int64_t ldv, float* O,
                  int64_t ldo, float* lse, const uint8_t* key_pad, int B, int H, int Tq, int Tk, int dh,
                  int mask_mode, int round_tf32, int backend, void* stream) {

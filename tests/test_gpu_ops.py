@@ -693,3 +693,75 @@ def test_cross_attention_on_the_rank2_form(lib, B, H, Tq, T, dh, masked):
     assert rel_err(gw, w.grad) < tol and rel_err(gbeta, beta.grad) < tol
     assert rel_err(gb[d:], bias.grad[d:]) < tol
     assert float(gb[:d].abs().max()) == 0.0 and float(bias.grad[:d].abs().max()) < 1e-9 * float(bias.grad[d:].abs().max() + 1)
+
+
+# ---- sublayer entry points (skf_ffn_*, skf_logits_ce_*) against torch autograd in float64 ----------------------------
+@pytest.mark.parametrize("images", [True, False])
+@pytest.mark.parametrize("M,d,f", [(25600, 256, 1024), (1592, 128, 512), (300, 64, 96)])
+def test_ffn_sublayer_fwd_bwd(lib, M, d, f, images):
+    """skf_ffn_fwd / skf_ffn_bwd = point_wise_feed_forward_network with its residual
+    (builders/layers/transformer.py:194-198, 220-222) and its gradients: cfg2's full size (pair GEMM with the tail
+    split), a mid size, and a shape that falls to the single-CTA / SIMT kernels."""
+    from sketchformer_b200.ops import ffn_bwd, ffn_fwd
+    g = torch.Generator().manual_seed(M + d)
+    x = torch.randn(M, d, generator=g).double().requires_grad_()
+    resid = torch.randn(M, d, generator=g).double()
+    W1 = (torch.randn(d, f, generator=g) / math.sqrt(d)).double().requires_grad_()
+    b1 = (0.1 * torch.randn(f, generator=g)).double().requires_grad_()
+    W2 = (torch.randn(f, d, generator=g) / math.sqrt(f)).double().requires_grad_()
+    b2 = (0.1 * torch.randn(d, generator=g)).double().requires_grad_()
+    dy = torch.randn(M, d, generator=g).double()
+    h_ref = torch.relu(x @ W1 + b1)
+    y_ref = resid + h_ref @ W2 + b2
+    f32 = lambda t: dev(t.detach().float())
+    xd, W1d, b1d, W2d, b2d = f32(x), f32(W1), f32(b1), f32(W2), f32(b2)
+    h, y = ffn_fwd(xd, W1d, b1d, W2d, b2d, resid=f32(resid), images=images)
+    torch.cuda.synchronize()
+    assert rel_err(h, h_ref.detach()) < TOL_X3 and rel_err(y, y_ref.detach()) < TOL_X3
+    # gradients at the device's own activation pattern (ReLU is not differentiable at 0: a forward difference of 3e-5
+    # flips ~2e-5 of the hidden units and each flip moves dW1 by that unit's whole contribution, DESIGN.md section 3)
+    mask = (h > 0).cpu()
+    assert float((mask != (h_ref > 0)).double().mean()) < 1e-3
+    with torch.no_grad():
+        dW2_ref, db2_ref = h_ref.T @ dy, dy.sum(0)
+        dh_ref = (dy @ W2.T) * mask
+        dW1_ref, db1_ref, dx_ref = x.T @ dh_ref, dh_ref.sum(0), dh_ref @ W1.T
+    extra = dev(torch.randn(M, d, generator=g))
+    dx, dW1, db1, dW2, db2 = ffn_bwd(xd, h, f32(dy), W1d, W2d, dx_resid=extra, images=images)
+    torch.cuda.synchronize()
+    assert rel_err(dW2, dW2_ref) < 2e-4 and rel_err(db2, db2_ref) < 2e-4
+    assert rel_err(dW1, dW1_ref) < 2e-4 and rel_err(db1, db1_ref) < 2e-4
+    assert rel_err(dx - extra, dx_ref) < 2e-4
+
+
+@pytest.mark.parametrize("images", [True, False])
+@pytest.mark.parametrize("B,Td,d,V", [(128, 199, 256, 1004), (5, 31, 64, 52)])
+def test_logits_ce_sublayer_fwd_bwd(lib, B, Td, d, V, images):
+    """skf_logits_ce_fwd / _bwd = final_layer + masked token CE + accuracy (models/sketchformer.py:179, 335-339;
+    builders/losses.py:26-41): loss sum and dlogits against float64, argmax / correct count exactly."""
+    from sketchformer_b200.ops import logits_ce_bwd, logits_ce_fwd
+    g = torch.Generator().manual_seed(B * Td)
+    x = torch.randn(B * Td, d, generator=g).double().requires_grad_()
+    W = (torch.randn(d, V, generator=g) / math.sqrt(d)).double().requires_grad_()
+    b = (0.1 * torch.randn(V, generator=g)).double().requires_grad_()
+    tgt = torch.randint(1, V, (B, Td), generator=g)
+    tgt[:, Td - Td // 4:] = 0                                      # PAD tail: masked in the loss, counted in the mean
+    z = x @ W + b
+    ce = torch.nn.functional.cross_entropy(z, tgt.reshape(-1), reduction="none") * (tgt.reshape(-1) != 0)
+    scale = 1.0 / (B * Td)
+    (ce.sum() * scale).backward()
+    f32 = lambda t: dev(t.detach().float())
+    xd, Wd = f32(x), f32(W)
+    dlog, stats, am = logits_ce_fwd(xd, Wd, f32(b), dev(tgt), scale, images=images)
+    torch.cuda.synchronize()
+    assert abs(float(stats[0]) - float(ce.sum())) < 1e-4 * float(ce.sum())
+    zs = z.detach()
+    top2 = zs.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3 * (zs.max() - zs.min())            # rows whose argmax is not a near tie
+    assert torch.equal(am.cpu().long()[clear], zs.argmax(1)[clear])
+    assert abs(float(stats[1]) - float((zs.argmax(1) == tgt.reshape(-1)).sum())) <= float((~clear).sum())
+    want_dlog = (torch.softmax(zs, 1) - torch.nn.functional.one_hot(tgt.reshape(-1), V)) * (tgt.reshape(-1, 1) != 0) * scale
+    assert rel_err(dlog, want_dlog) < 2e-4
+    dx, dW, db = logits_ce_bwd(xd, dlog, Wd, B, Td, images=images)
+    torch.cuda.synchronize()
+    assert rel_err(dx, x.grad) < 3e-4 and rel_err(dW, W.grad) < 3e-4 and rel_err(db, b.grad) < 3e-4
