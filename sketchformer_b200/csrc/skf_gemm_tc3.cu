@@ -16,6 +16,12 @@
 //   * A operand from tensor memory (tcgen05.mma TS form, 256 x 128 cluster tiles): correct, 70 us on FFN-1
 //     (more L2 traffic per FLOP), 1-3 % faster only for N = 256;
 //   * 8 splitter warps, TMA L2 prefetch of the next tile: no change.
+//   * (round 2) plain epilogue with coalesced st.global read back from the staging tile (8 lanes per 128-byte row
+//     segment, no fence.proxy.async, no wait for the TMA engine): correct, 46.8 -> 50.9 us on FFN-1, every shape
+//     slower (profiles/r2_gemm_bound_ab.txt) -> the TMA store stays.
+//   * (round 2) what bounds the forward / dgrad kernel, from timing builds with parts switched off (same file): no
+//     epilogue stores 47.0 -> 36.2 us on FFN-1 (N = 1024 outputs), 46.6 -> 42.5 on FFN-2; no A loads 42.1 / 41.5; neither
+//     33.9 / 39.6; 3 stages instead of 4: 50.5 / 50.1, 2 stages 62.2 / 67.1; no A split 46.0 / 44.0.
 //   * bf16 hi / lo images of the weights prepared once per step and TMA-loaded into the stage's bf16 B tiles
 //     (the splitter then converts only A): with the B conversion merely skipped the kernel is 8-13 % faster,
 //     but the extra 16 KB of TMA writes per stage give it back (FFN-1 58.4 -> 58.1 us, dgrads 2-7 %, step 0.5 %).
@@ -66,7 +72,10 @@ constexpr int T3_SPLIT_WARPS = SKF_T3_SPLIT_WARPS;     // splitter warps per CTA
 constexpr int T3_EPI_BYTES = T3_EPI_WARPS * T3_EPI_BUFS * T3_EPI_TILE;   // 32 KB
 constexpr int T3_SPLIT_T0 = 32 * (2 + T3_EPI_WARPS);   // first splitter thread
 constexpr int T3_THREADS = T3_SPLIT_T0 + 32 * T3_SPLIT_WARPS;   // 448
-constexpr int T3_MAX_STAGES = 4;
+#ifndef SKF_T3_MAX_STAGES
+#define SKF_T3_MAX_STAGES 4
+#endif
+constexpr int T3_MAX_STAGES = SKF_T3_MAX_STAGES;
 
 // BN = columns per cluster tile (256, or 128 for N <= 256: twice as many tiles for the 74 clusters and a
 // fourth pipeline stage); each CTA stages BN / 2 columns of B.
@@ -345,16 +354,22 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
+#ifdef SKF_T3_DEBUG_SKIP_A_LOAD    // timing experiment only (wrong results): the A tile is never loaded
+          mbar_arrive_expect_tx(full_bar(s), T3_RAW - T3_A_BYTES);
+#else
           mbar_arrive_expect_tx(full_bar(s), T3_RAW);
+#endif
           const uint32_t a_s = base + s * T3_STAGE;
           const uint32_t b_s = a_s + T3_A_BYTES;
           const int k0 = kb + i * T3_BK;
+#ifndef SKF_T3_DEBUG_SKIP_A_LOAD
           if (!A_MN) {
             tma_load_2d(a_s, &tmA, full_bar(s), k0, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < T3_BM / 32; j++) tma_load_2d(a_s + j * 4096, &tmA, full_bar(s), m0 + 32 * j, k0);
           }
+#endif
           if (WS) {
             // bf16 images of the weight: hi / lo tiles with 64-byte rows (64B swizzle), where the splitter would
             // have written them
@@ -533,6 +548,10 @@ gemm3_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtenso
             for (int j = 0; j < 32; j++) v[j] = round_tf32(v[j]);
           }
         }
+#ifdef SKF_T3_DEBUG_SKIP_EPI_STORE   // timing experiment only (no output): the tile is read from tensor memory and dropped
+        if (v[0] == 123.456f && v[31] == 654.321f) asm volatile("trap;");
+        continue;
+#endif
         const uint32_t buf = nstore % T3_EPI_BUFS;
         if (lane == 0) t3_bulk_wait_read<T3_EPI_BUFS - 1>();
         __syncwarp();
