@@ -358,7 +358,10 @@ int skf_forward(skf_plan* plan, const void* tokens, void* stream);
  * (SOS, or the stroke row [0,0,1,0,0]).  skf_decode_steps runs decoder positions [first, first+n): each
  * appends argmax(logits) (or [dx,dy,softmax(pen)]) to the workspace tensor "gen.tokens" int64 [B,T+1]
  * ("gen.strokes" float [B,T+1,5]).  "gen.state" int32: [0] = number of valid output columns once every row
- * has emitted EOS (pen state 2), else 0; [1] = steps executed.  No host synchronisation inside.          */
+ * has emitted EOS (pen state 2), else 0; [1] = steps executed.  No host synchronisation inside.
+ * blind_decoder_mask=0 with expected_len == NULL (sketchformer.py:275: the cross mask of step i attends the first
+ * i + 1 keys for every position) cannot be cached: every step recomputes the prefix under its own mask — same
+ * tokens as the reference, O(T^2) position steps per call instead of O(T).                                  */
 int skf_decode_begin(skf_plan* plan, const float* embedding, const int32_t* expected_len,
                      int64_t sos_token, int64_t eos_token, void* stream);
 int skf_decode_steps(skf_plan* plan, int first_step, int n_steps, void* stream);

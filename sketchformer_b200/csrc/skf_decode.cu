@@ -186,6 +186,18 @@ int decode_init(int64_t* tokens, float* strokes, uint8_t* pad, uint8_t* cross_pa
   return SKF_OK;
 }
 
+// make_dummy_input with expected_len=None (models/sketchformer.py:230-253, 275): at step i the cross-attention keys
+// [0, width = i + 1) are attended, the rest masked, for every sample
+__global__ void decode_cross_width_k(uint8_t* __restrict__ cross_pad, int n, int T, int width) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) cross_pad[idx] = (idx % T) >= width ? 1 : 0;
+}
+int decode_cross_width(uint8_t* cross_pad, int B, int T, int width, cudaStream_t st) {
+  decode_cross_width_k<<<cdiv((long)B * T, 256), 256, 0, st>>>(cross_pad, B * T, T, width);
+  SKF_LAUNCH_CHECK();
+  return SKF_OK;
+}
+
 int decode_pick(const float* logits, int64_t ldl, int V, int64_t* tokens, float* strokes, uint8_t* pad, uint8_t* fin,
                 int32_t* state, int B, int T, int step, int64_t eos, int continuous, cudaStream_t st) {
   if (continuous)

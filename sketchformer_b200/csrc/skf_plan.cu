@@ -393,6 +393,7 @@ struct skf_plan {
   bool training = false;   // inside skf_train_step: Dropout layers are active (training=True)
   int64_t gen_sos = 0, gen_eos = 0;   // greedy decode: start / stop token ids (utils/tokenizer.py:29-33)
   bool gen_ready = false;
+  bool gen_uncached = false;          // blind_decoder_mask=False without expected_len: the prefix is recomputed every step
   // Backward pass, second stream: dW = X^T dY is off the critical path (nothing reads it before the optimizer),
   // so it is issued on `side` behind an event and fills the SMs the main chain leaves idle in the last wave of its
   // persistent GEMMs and attention kernels.  `pending` maps a gradient buffer to the event after which the side
@@ -1249,7 +1250,8 @@ static int decode_begin(skf_plan* P, const float* embedding, const int32_t* expe
 }
 
 // position `i` of every sample: decoder input = column i of the generated prefix -> column i+1
-static int decode_step(skf_plan* P, int i, bool cross_masked, cudaStream_t st) {
+// pick = false: only the position's self-attention keys / values are (re)written, no logits, no new token
+static int decode_step(skf_plan* P, int i, bool cross_masked, cudaStream_t st, bool pick = true) {
   const skf_cfg& c = P->c;
   const int B = c.B, T = c.T, d = c.d, f = c.f, H = c.H, dh = c.d / c.H;
   const int rnd = P->round_ops ? 1 : 0;
@@ -1285,6 +1287,7 @@ static int decode_step(skf_plan* P, int i, bool cross_masked, cudaStream_t st) {
     SKF_TRY(skf_add_layernorm_fwd(sb, nullptr, nullptr, P->pw(p + ".ln3.g"), P->pw(p + ".ln3.b"), nullptr, x, nullptr,
                                   nullptr, B, d, rnd, st));
   }
+  if (!pick) return SKF_OK;
   float* lg = P->wsf("gen.logits");
   if (c.continuous) {
     skf_gemm_epilogue e;
@@ -1297,6 +1300,19 @@ static int decode_step(skf_plan* P, int i, bool cross_masked, cudaStream_t st) {
   return decode_pick(lg, c.continuous ? 8 : c.V, c.V, P->wsp<int64_t>("gen.tokens"), P->wsf("gen.strokes"),
                      P->wsp<uint8_t>("gen.pad"), P->wsp<uint8_t>("gen.fin"), P->wsp<int32_t>("gen.state"), B, T, i,
                      P->gen_eos, c.continuous, st);
+}
+
+// blind_decoder_mask=False and no expected_len (models/sketchformer.py:274-281): at step i the reference attends the
+// first i + 1 cross-attention keys for EVERY decoder position, so the hidden states of the earlier positions — and
+// with them the self-attention keys / values of layers >= 1 — change at every step and no cache survives a step.
+// Like the reference, the prefix is recomputed: positions 0 .. i - 1 refill the caches under the step's mask, position
+// i produces the token.  O(T^2) position steps per sequence (the reference: O(T^2) full decoder passes); the cached
+// path above is what predict() and every blind model use.
+int decode_cross_width(uint8_t* cross_pad, int B, int T, int width, cudaStream_t st);
+static int decode_step_uncached(skf_plan* P, int i, cudaStream_t st) {
+  SKF_TRY(decode_cross_width(P->wsp<uint8_t>("gen.cross_pad"), P->c.B, P->c.T, i + 1, st));
+  for (int j = 0; j < i; j++) SKF_TRY(decode_step(P, j, true, st, false));
+  return decode_step(P, i, true, st, true);
 }
 
 }  // namespace skf
@@ -1553,9 +1569,9 @@ int skf_decode_begin(skf_plan* P, const float* embedding, const int32_t* expecte
     P->launches += skf::g_launch_count - l0;
     return SKF_OK;
   }
-  SKF_REQUIRE(P->c.blind_decoder_mask || expected_len != nullptr, SKF_ERR_UNSUPPORTED,
-              "decode: blind_decoder_mask=False needs expected_len (the i+1 cross mask of the reference changes "
-              "earlier positions every step and is not cacheable)");
+  // blind_decoder_mask=False without expected_len: the reference's i+1 cross mask changes earlier positions at every
+  // step and is not cacheable: decode_step_uncached recomputes the prefix per step
+  P->gen_uncached = !P->c.blind_decoder_mask && expected_len == nullptr;
   int64_t l0 = skf::g_launch_count;
   P->gen_sos = sos_token;
   P->gen_eos = eos_token;
@@ -1570,8 +1586,10 @@ int skf_decode_steps(skf_plan* P, int first_step, int n_steps, void* stream) {
   SKF_REQUIRE(first_step >= 0 && n_steps >= 0 && first_step + n_steps <= P->c.T, SKF_ERR_BAD_SHAPE,
               "decode_steps: steps [%d, %d) outside [0, max_seq_len=%d)", first_step, first_step + n_steps, P->c.T);
   int64_t l0 = skf::g_launch_count;
-  for (int i = first_step; i < first_step + n_steps; i++)
-    SKF_TRY(decode_step(P, i, !P->c.blind_decoder_mask, as_stream(stream)));
+  for (int i = first_step; i < first_step + n_steps; i++) {
+    if (P->gen_uncached) SKF_TRY(decode_step_uncached(P, i, as_stream(stream)));
+    else SKF_TRY(decode_step(P, i, !P->c.blind_decoder_mask, as_stream(stream)));
+  }
   P->launches += skf::g_launch_count - l0;
   return SKF_OK;
 }

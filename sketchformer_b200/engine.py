@@ -312,6 +312,10 @@ class Engine:
         if graphs is None:
             graphs = self._decode_graphs = {"warm": False}
         use_graphs = graphs["warm"] and os.environ.get("SKF_DECODE_GRAPHS", "1") != "0"
+        if not self.cfg.blind_decoder_mask and expected_len is None:
+            # the uncached mode (include/skf.h): step i is i + 1 position steps — far too many launches for one graph
+            # per chunk, and an early stop is worth checking for more often
+            use_graphs, chunk = False, min(chunk, 8)
         while i < T and cols == 0:
             n = min(chunk, T - i)
             if use_graphs:

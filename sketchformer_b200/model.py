@@ -311,7 +311,9 @@ class Transformer:
     def predict_from_embedding(self, emb, expected_len=None):
         """models/sketchformer.py:255-311 -> {'recon' (B, n<=T+1) int32 tokens | (B, n, 5) float32 strokes,
         'class' (B,) int32, 'attn_weights': None}.  KV-cached greedy decode on the device (skf_decode_*);
-        `expected_len` is ignored when blind_decoder_mask=True, exactly as the reference's decode() does.
+        `expected_len` is ignored when blind_decoder_mask=True, exactly as the reference's decode() does; with
+        blind_decoder_mask=False and no expected_len the reference's growing `i + 1` cross mask is reproduced by
+        recomputing the prefix at every step (slow, like the reference: experiments/interpolations_for_mturk.py:78).
         The per-step attention maps the reference returns are never materialised here."""
         emb = np.asarray(emb, dtype=np.float32)
         if emb.ndim == (1 if self.hps["lowerdim"] else 2):

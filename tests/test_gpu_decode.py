@@ -106,6 +106,33 @@ def test_greedy_decode_expected_len_mask():
 
 
 @pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
+def test_greedy_decode_growing_cross_mask(backend):
+    """blind_decoder_mask=False and NO expected_len (predict_from_embedding as experiments/interpolations_for_mturk.py:78
+    calls it): at step i the reference attends the first i + 1 cross keys for every position (sketchformer.py:275), so
+    the whole prefix is recomputed every step.  Tokens against the oracle's restatement of that loop; the class
+    prediction comes with it; the same through the plugin API."""
+    B = 4
+    ocfg, eng = build(TINY, B, backend, blind_decoder_mask=False)
+    p = O.init_params(ocfg, 2, torch.float64)
+    eng.load_params(p)
+    sos, eos = ocfg.vocab_size - 2, ocfg.vocab_size - 1
+    x, _ = synth.token_batch(B, ocfg.max_seq_len, ocfg.n_classes, 13, vocab=ocfg.vocab_size)
+    xt = torch.from_numpy(x)
+    emb = O.predict(p, xt, ocfg, sos=sos, eos=eos, dtype=torch.float64)["embedding"]
+    want = O.predict_from_embedding(p, emb, ocfg, expected_len=None, sos=sos, eos=eos, dtype=torch.float64)
+    eng.encode(xt.cuda())
+    got = eng.decode(None, None, sos, eos).cpu().numpy()
+    _assert_same_tokens(p, ocfg, emb, got, want["recon"].numpy())
+    # it differs from the cached decode with the true lengths (otherwise this test would not see the growing mask)
+    with_len = eng.decode(None, (xt > 0).sum(-1), sos, eos).cpu().numpy()
+    n = min(with_len.shape[1], got.shape[1])
+    assert with_len.shape != got.shape or not np.array_equal(with_len[:, :n], got[:, :n])
+    # a second call gives the same tokens (no state left over from the prefix recomputation)
+    again = eng.decode(None, None, sos, eos).cpu().numpy()
+    assert np.array_equal(again, got)
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tcgen05"])
 def test_greedy_decode_continuous(backend):
     B = 4
     ocfg, eng = build(TINY, B, backend, use_continuous_data=True)
