@@ -141,3 +141,78 @@ def test_resume_runs_one_eager_step_before_capturing(tmp_path):
     assert getattr(eng, "_graph", None) is not None
     ref = model.train_on_batch(next(dataset.batch_iterator("train", 8)))
     assert np.isfinite(ref["total_loss"])
+
+
+def test_cfg4_continuous_b128_graph_replay_matches_oracle():
+    """bench.py --config cfg4 (BASELINE.json configs[3]: use_continuous_data=True, batch 128, T 200): the same plugin path —
+    host batches, one eager step, then CUDA-graph replays — against the fp64 oracle: losses of both steps, class
+    accuracy exactly, and every gradient of the REPLAYED step (builders/losses.py:43-66 is a product of two batch
+    means, so its gradient kernel needs the stats of the whole batch first: that ordering is inside the graph too)."""
+    c = CFG2
+    Model = get_model_by_name("sketch-transformer-tf2")
+    Loader = get_dataloader_by_name("stroke3-synthetic")
+    data_hps = Loader.parse_hparams(f"max_seq_len={c['max_seq_len']},use_continuous_data=True")
+    model_hps = Model.parse_hparams(base=f"batch_size={B}",
+                                    specific=f"num_layers={c['num_layers']},d_model={c['d_model']},dff={c['dff']},"
+                                             f"num_heads={c['num_heads']},lowerdim={c['lowerdim']},dropout_rate=0.0")
+    dataset = Loader(data_hps, None, n_classes=c["n_classes"], seed=99)
+    model = Model(model_hps, dataset, None, "parity4", device="cuda:0", seed=0)
+    eng = model._train_engine
+    ocfg = O.OracleConfig(**CFG2, use_continuous_data=True)
+    p = O.init_params(ocfg, 0, torch.float64)
+    eng.load_params(p)
+    opt = O.AdamTF(p, ocfg.d_model)
+    it = dataset.batch_iterator("train", B)
+    for s in range(2):
+        x, y = next(it)
+        assert isinstance(x, np.ndarray) and x.shape == (B, ocfg.max_seq_len, 5)
+        got = model.train_on_batch((x, y))
+        torch.cuda.synchronize()
+        assert (getattr(eng, "_graph", None) is not None) == (s >= 1)
+        last = eng.last_step_metrics()
+        xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+        if s == 1:          # optimizer iterations 0 and 1: lr(0) = 0, so both sides still hold the initial weights
+            pattern = engine_relu_pattern(eng, ocfg, B)
+            own = {}
+            with O.relu_pattern(pattern, record=own):
+                want, grads = O.train_step(p, opt, xt, yt, ocfg, dtype=torch.float64)
+            flips = sum(int((own[k] != pattern[k]).sum()) for k in pattern)
+            assert flips <= 1e-3 * sum(pattern[k].numel() for k in pattern)
+            gg = eng.export_grads(grads)
+            G = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
+            bad = []
+            for k, ref in grads.items():
+                err = float((gg[k].double() - ref.double()).norm()) / max(float(ref.double().norm()), 1e-4 * G)
+                if not err < TOL:
+                    bad.append((k, err))
+            assert not bad, f"gradients of the replayed cfg4 step off: {sorted(bad, key=lambda t: -t[1])[:8]}"
+        else:
+            want, _ = O.train_step(p, opt, xt, yt, ocfg, dtype=torch.float64)
+        for k in ("recon_loss", "class_loss", "total_loss"):
+            assert abs(last[k] - want[k]) <= TOL * abs(want[k]), (s, k, last[k], want[k])
+        assert last["class_acc"] == pytest.approx(want["class_acc"], abs=1e-12)
+        assert set(got) == {"recon_loss", "class_loss", "class_acc", "total_loss"}      # no recon_acc with continuous data
+
+
+def test_predict_class_cfg2_b128_matches_oracle():
+    """bench.py --config fwd: `predict_class` at batch 128 through the plugin (encoder + bottleneck + classifier):
+    embeddings to 1e-3, class ids exactly wherever the oracle's top-2 probabilities are not a near tie."""
+    model, dataset = _model()
+    ocfg = O.OracleConfig(**CFG2)
+    p = O.init_params(ocfg, 0, torch.float64)
+    model._train_engine.load_params(p)
+    x, _ = next(dataset.batch_iterator("train", B))
+    x = _shorten(x, 5, 200, 7)
+    out = model.predict_class(x)
+    want = O.predict_class(p, torch.from_numpy(x), ocfg, torch.float64)
+    emb = torch.from_numpy(out["embedding"])
+    assert emb.shape == (B, ocfg.d_model)
+    err = float((emb.double() - want["embedding"]).norm() / want["embedding"].norm())
+    assert err < TOL, err
+    probs = O.encode_from_seq(p, torch.from_numpy(x), ocfg, torch.float64)["class"]
+    top2 = probs.topk(2, dim=1).values
+    spread = probs.max(dim=1).values - probs.min(dim=1).values
+    clear = ((top2[:, 0] - top2[:, 1]) > 2e-3 * spread).numpy()         # not a near tie at the fp32 tolerance
+    same = out["class"] == want["class"].numpy()
+    assert clear.sum() > B // 2 and same[clear].all(), np.argwhere(~same & clear).ravel()
+    assert out["class"].dtype == np.int32
