@@ -448,7 +448,10 @@ attn3_fwd_k(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUte
         for (int ch = 0; ch < nch; ch++, n++) {
           const int st = n % a.nst;
           mbar_wait_sleep(bar(RING_FULL + st), (n / a.nst) & 1u);
+#ifndef SKF_A3_DEBUG_SKIP_CONVERT    // timing experiment only (wrong results): what operand images made by the producer
+                                     // of Q / K / V would save the forward kernel
           convert_stage<false>(gen + L.ring + st * STAGE_BYTES, hi, lo, 64 * ch, TP, ct);
+#endif
           fence_proxy_async();             // the tensor core reads the tiles through the async proxy
           __syncwarp();
           if (lane == 0) {
