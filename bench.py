@@ -160,6 +160,13 @@ def cpu_reference_steps(config, steps, warmup, budget_s, batch=None):
     return {"value": batch * steps / dt, "batch": batch, "seconds": dt, "cores": cores, "tokens_per_s": tokens / dt}
 
 
+def bench_config(cfg, per_gpu, world):
+    """The `config` object of the JSON line — identical in both arms (the driver compares them): what is computed, on
+    how many ranks, and how the timed region keeps L2 from serving repeated inputs."""
+    return {"workload": workload_name(cfg, per_gpu), "parallelism": f"dp{world}", "global_batch": per_gpu * world,
+            "l2": "per-step working set (activations saved for backward, GBs) >> 126 MB L2; 8 distinct batches"}
+
+
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -176,9 +183,9 @@ def reference_main(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * r["seconds"] / steps * (full / r["batch"]), "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, full),
-                       "note": "reference TF-2.1 cannot run in this image; this is the fp32 torch-CPU op-for-op "
-                               "restatement (oracle/) on the host cores"},
+            "config": bench_config(cfg, full if args.scaling != "strong" else full // max(1, args.gpus), max(1, args.gpus)),
+            "note": "reference TF-2.1 cannot run in this image; this is the fp32 torch-CPU op-for-op restatement "
+                    "(oracle/) on the host cores of rank 0",
             "cpu_baseline": {"value": r["value"], "unit": "sketches/s", "cores": r["cores"], "kind": "port",
                              "sample": sample},
             "e2e": {"value": r["value"], "unit": "sketches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -370,16 +377,16 @@ def main():
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32 (tensor-core split products: bf16x3 GEMMs and attention; fp32 accumulate and storage)",
                 "data": "synthetic",
-                "config": {"workload": workload_name(cfg, B), "parallelism": f"dp{world}", "global_batch": B * world,
-                           "l2": "per-step working set (activations saved for backward, GBs) >> 126 MB L2; 8 distinct batches",
-                           "precision": mode, "cuda_graph": bool(getattr(eng, "_graph", None)),
-                           "dp_exchange": ("none" if world == 1 else
-                                           f"{args.dp_buckets} NCCL buckets inside the step (graph-captured, overlapped with backward)"
-                                           if args.dp_buckets else "one torch.distributed all_reduce after the step"),
-                           "api": "sketchformer_b200.model.Transformer." +
-                                  ("train_on_batch (reference models/sketchformer.py:351)" if train else
-                                   "predict_class (reference models/sketchformer.py:223)" if cfg == "fwd" else
-                                   "predict_from_embedding (reference models/sketchformer.py:255)")},
+                "config": bench_config(cfg, B, world),
+                # how this arm ran it (not part of the workload definition the two arms share)
+                "run": {"precision": mode, "cuda_graph": bool(getattr(eng, "_graph", None)),
+                        "dp_exchange": ("none" if world == 1 else
+                                        f"{args.dp_buckets} NCCL buckets inside the step (graph-captured, overlapped with backward)"
+                                        if args.dp_buckets else "one torch.distributed all_reduce after the step"),
+                        "api": "sketchformer_b200.model.Transformer." +
+                               ("train_on_batch (reference models/sketchformer.py:351)" if train else
+                                "predict_class (reference models/sketchformer.py:223)" if cfg == "fwd" else
+                                "predict_from_embedding (reference models/sketchformer.py:255)")},
                 "e2e": {"value": e2e_value, "unit": "sketches/s", "ms_per_step": ms_e2e / steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "host_submit_ms_per_step": host_submit_ms,

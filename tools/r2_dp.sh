@@ -12,7 +12,7 @@ run() {  # name, extra args
 import json
 try:
     d = json.loads(open("$OUT/${TAG}_$1.json").read().strip().splitlines()[-1])
-    print("$1", "N=$N", round(d["value"], 1), "sk/s", round(d["ms_per_step"], 3), "ms", "e2e", round(d["e2e"]["value"], 1), "dp_err", d.get("dp_grad_rel_err"), d["config"]["dp_exchange"][:40])
+    print("$1", "N=$N", round(d["value"], 1), "sk/s", round(d["ms_per_step"], 3), "ms", "e2e", round(d["e2e"]["value"], 1), "dp_err", d.get("dp_grad_rel_err"), d["run"]["dp_exchange"][:40])
 except Exception as e:
     print("$1 FAILED", e); print(open("$OUT/${TAG}_$1.err").read()[-2500:])
 PY
