@@ -639,6 +639,9 @@ pool_fwd_cl_k(const float* __restrict__ x, const float* __restrict__ u, const fl
   const int b = blockIdx.x / POOL_CL;
   const int t0 = min(T, (int)r * chunk), n = min(T, t0 + chunk) - t0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // every CTA of the cluster has started (its shared memory exists) before anyone stores into a peer's: the
+  // programming model requires it, and compute-sanitizer flags the remote stores below without it
+  pool_cluster_sync();
   // scores of this CTA's rows: warp per row
   for (int i = w; i < n; i += nw) {
     const float* ur = u + ((int64_t)b * T + t0 + i) * U;
@@ -709,6 +712,9 @@ pool_bwd_cl_k(const float* __restrict__ x, const float* __restrict__ u, const fl
   const int b = blockIdx.x / POOL_CL;
   const int t0 = min(T, (int)r * chunk), n = min(T, t0 + chunk) - t0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // every CTA of the cluster has started (its shared memory exists) before anyone stores into a peer's: the
+  // programming model requires it, and compute-sanitizer flags the remote stores below without it
+  pool_cluster_sync();
   const float* de = demb + (int64_t)b * d;
   // da_t = demb . x_t for this CTA's rows
   for (int i = w; i < n; i += nw) {

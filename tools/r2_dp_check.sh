@@ -3,7 +3,7 @@
 TAG=${1:-r2_dpc}
 N=${2:-2}
 OUT=gpurun_out; mkdir -p $OUT
-for mode in weak strong; do
+for mode in ${3:-weak strong}; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
     bench.py --gpus $N --steps 20 --warmup 5 --scaling $mode --no-loader > $OUT/${TAG}_${N}_$mode.json 2> $OUT/${TAG}_${N}_$mode.err
   python - <<PY
