@@ -74,7 +74,9 @@ class FakeEngine:
         s[0] += recon_loss; s[1] += hit_tok; s[2] += n_tok; s[3] += class_loss; s[4] += hit_cls; s[5] += B
         s[6] += total; s[7] += 1
         s[8:13] = torch.tensor([recon_loss, hit_tok / max(n_tok, 1), class_loss, hit_cls / B, total], dtype=torch.float64)
-        self.grads.fill_(total)
+        # a "gradient" that is a batch mean of a per-sample quantity, like the real losses' gradients: per-rank
+        # gradients summed over the ranks times 1/world equal the full-batch gradient (tests/test_dp_gloo.py)
+        self.grads.fill_(float(t.sum(1).mean()) * 1e-3)
         if apply_adam:
             self.apply_adam()
         if _eager:
@@ -82,7 +84,7 @@ class FakeEngine:
         self.calls.append(("train_step", B, bool(apply_adam), bool(_eager)))
 
     def apply_adam(self):
-        self.params.add_(self.grads, alpha=-1e-3)
+        self.params.add_(self.grads, alpha=-1e-3 / max(1, self.cfg.world_size))     # 1/world folded into the optimizer
         self.adam_m.mul_(0.9).add_(self.grads, alpha=0.1)
         self.adam_v.mul_(0.98).add_(self.grads * self.grads, alpha=0.02)
         self._step += 1
@@ -153,11 +155,17 @@ class FakeEngine:
         return torch.cat([torch.full((B, 1), int(sos), dtype=torch.int64), body], 1).to(torch.int32)
 
 
-def install(monkeypatch):
+def install(monkeypatch=None):
     """Run sketchformer_b200.model.Transformer on FakeEngine: the engine class and the two pinned-memory staging helpers
     (which need a CUDA context) are the only things replaced."""
     from sketchformer_b200 import model as M
     FakeEngine.instances = []
+    if monkeypatch is None:          # a spawned worker process: nothing to restore afterwards
+        class _Set:
+            @staticmethod
+            def setattr(obj, name, value):
+                setattr(obj, name, value)
+        monkeypatch = _Set
     monkeypatch.setattr(M, "Engine", FakeEngine)
 
     def to_device(self, key, arr, dtype):

@@ -90,3 +90,66 @@ def test_two_rank_gradient_average_equals_full_batch():
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     status, info = out.get(timeout=5)
     assert status == "ok", info
+
+
+# ---- the plugin's own data-parallel path (sketchformer_b200/model.py) on two gloo ranks ---------------------------------
+def _plugin_worker(rank, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    torch.set_num_threads(1)
+    try:
+        from sketchformer_b200.model import get_model_by_name
+        from tests import fake_engine
+        fake_engine.install()                      # no GPU here: the engine's arithmetic is the test double's
+        Model = get_model_by_name("sketch-transformer-tf2")
+        Loader = get_dataloader_by_name("stroke3-synthetic")
+        hps = Loader.parse_hparams("max_seq_len=32")
+        mh = "num_layers=1,d_model=64,dff=64,num_heads=4,lowerdim=16,dropout_rate=0.0"
+
+        def run(world, r, batch, n_samples):
+            ds = Loader(hps, None, n_classes=7, n_samples=n_samples, seed=5, rank=r, world_size=world, vocab=52)
+            # dp_buckets=0: the torch.distributed path (all_reduce of the arena after the step, then the optimizer)
+            m = Model(Model.parse_hparams(base=f"batch_size={batch},num_epochs=1", specific=mh), ds, None, "dp",
+                      device="cpu", world_size=world, rank=r, seed=0, dp_buckets=0, use_cuda_graph=False)
+            it = ds.batch_iterator("train", batch)
+            for _ in range(3):
+                m.train_on_batch(next(it))
+            return m
+
+        dp = run(WORLD, rank, GLOBAL_B // WORLD, 64)
+        # an epoch is n_samples // (batch_size * world) steps (core/models.py:60 counts one process)
+        assert dp.batches_per_epoch == 64 // GLOBAL_B and dp.current_step == 3
+        eng = dp._train_engine
+        assert [c[2] for c in eng.calls if c[0] == "train_step"] == [False] * 3      # Adam runs AFTER the all-reduce
+        assert eng.step_count() == 3
+        mine = eng.params.clone()
+        both = [torch.zeros_like(mine) for _ in range(WORLD)]
+        dist.all_gather(both, mine)
+        assert torch.equal(both[0], both[1]), "ranks diverged"
+        if rank == 0:
+            solo = run(1, 0, GLOBAL_B, 64)._train_engine.params        # one process, the whole global batch
+            err = float((mine - solo).norm() / solo.norm())
+            assert err < 1e-6, err
+            out.put(("ok", err))
+    except Exception as e:      # noqa: BLE001
+        out.put(("fail", repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_plugin_data_parallel_step_on_two_gloo_ranks():
+    """Transformer(world_size=2).train_on_batch on two CPU ranks (gloo) with the engine replaced by tests/fake_engine.py:
+    every rank trains on its slice of the global batches, the gradient arena is all-reduced by torch.distributed, the
+    optimizer runs after it with 1/world, the ranks stay bit-identical and equal to a single process that sees the
+    whole global batch."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_plugin_worker, args=(r, port, out)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    status = out.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+    assert status[0] == "ok", status
