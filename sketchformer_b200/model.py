@@ -97,13 +97,14 @@ class Transformer:
         self._stage = {}
         # data parallel: dp_buckets >= 1 -> bucketed NCCL all-reduce inside the step, overlapped with the backward pass
         # and captured in the CUDA graph (skf_plan_set_comm); 0 -> one torch.distributed all_reduce after the step
-        # Default: the in-step exchange on 2 ranks (measured: same step time as the torch path, exchange inside the
-        # graph), the torch path on more — the in-step exchange ran at 8 ranks with 16 sketches per rank but did not
-        # finish within the time limit at 128 per rank (profiles/r2_dp8_*), so it is opt-in there.
+        # Default: the in-step exchange on 2 ranks, the torch path on more.  Both run on 2 and 8 ranks and measure the same
+        # step time (profiles/r2_dp2_*, r2_dp8_*, r2_f2_dp8_weak_instep.json); the in-step path
+        # has not been run on 4 ranks, so it stays opt-in there.
         if dp_buckets is None:
             dp_buckets = 4 if world_size == 2 else 0
         self._dp_buckets = int(dp_buckets) if world_size > 1 else 0
         self._comm = None
+        self._dp_eager_steps = 0
         self.build_model()
 
     @property
@@ -226,7 +227,14 @@ class Transformer:
         dt = torch.int64 if not self.continuous else torch.float32
         # the optimizer runs inside the step unless the gradients still have to be all-reduced by torch afterwards
         solo = self._world == 1 or self._dp_buckets > 0
-        if self._use_graph and eng is self._train_engine and eng.eager_train_steps >= 1:
+        # Under data parallelism with the exchange inside the step, the step at which a rank starts capturing must be the
+        # SAME on every rank: NCCL does host-side work of its own at capture time (buffer registration for the graph),
+        # which is collective.  So the rule counts the eager steps THIS method has run on the training plan — every
+        # rank calls it equally often — not the engine's own history (a rank whose plan also served some other eager
+        # step, e.g. rank 0 in bench.py's gradient check, would otherwise capture one call early while the others run
+        # the collective eagerly).
+        eager_done = eng.eager_train_steps if not (self._world > 1 and self._dp_buckets) else self._dp_eager_steps
+        if self._use_graph and eng is self._train_engine and eager_done >= 1:
             # (one eager step first — also right after restore_checkpoint_if_exists(), when current_step is already
             # large: function attributes and tensor-map encoders are initialised lazily, engine.py capture_train_step)
             # steady state: pinned host -> static device buffers -> one cudaGraphLaunch for the whole step
@@ -240,6 +248,8 @@ class Transformer:
             if eng is not self._train_engine:          # odd batch size: same arenas, carry the optimizer step over
                 eng.set_step(self._train_engine.step_count())
             eng.train_step(x, y, apply_adam=solo)
+            if eng is self._train_engine:
+                self._dp_eager_steps += 1
             if eng is not self._train_engine and solo:
                 self._train_engine.set_step(eng.step_count())
         # one running mean over all steps, whatever plan ran them
